@@ -1,0 +1,172 @@
+/*
+ * okvis_b200.h -- C ABI of libokvis_b200.so: the B200-native OKVIS2 vision front-end hot path
+ * (detect -> describe -> match). Plain pointers and sizes only; no CUDA/torch/OpenCV/Eigen types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the okvis2 tree @464180aa).
+ * All functions return 0 (OKB_OK) or a negative okb_status; okb_last_error() gives the text. Nothing throws
+ * across this boundary; the C++ adapter turns a non-zero status into OKVIS_THROW(okvis::Frontend::Exception)
+ * (reference okvis_frontend/include/okvis/Frontend.hpp:60). There is NO CPU fallback: without a CUDA device
+ * okb_create fails with OKB_ERR_NO_DEVICE.
+ *
+ * Memory: all pointers are HOST pointers owned by the caller and only used during the call, except in the
+ * *_device variants (device pointers, used by the benchmark to time the resident-input path).
+ */
+#ifndef OKVIS_B200_H
+#define OKVIS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  OKB_OK = 0,
+  OKB_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path refuses to run */
+  OKB_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed */
+  OKB_ERR_ARGUMENT = -3,    /* bad argument (null pointer, size out of range, unsupported D) */
+  OKB_ERR_CAPACITY = -4,    /* a fixed-capacity device buffer overflowed (raise the config capacity) */
+  OKB_ERR_UNSUPPORTED = -5, /* feature not built (e.g. D=48 describe: reference extractor source absent) */
+  OKB_ERR_NCCL = -6
+} okb_status;
+
+/* 28-byte POD with the exact field order of cv::KeyPoint (pt.x, pt.y, size, angle, response, octave, class_id),
+ * so the adapter can memcpy into std::vector<cv::KeyPoint> (okvis::Frame::keypoints_,
+ * okvis_cv/include/okvis/Frame.hpp:247-265). */
+typedef struct {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} okb_keypoint_t;
+
+/* Per-camera detector/extractor configuration == the constructor arguments of the detector/extractor pair made
+ * in Frontend::initialiseBriskFeatureDetectors (okvis_frontend/src/Frontend.cpp:2398-2417) from
+ * FrontendParameters (okvis_common/include/okvis/Parameters.hpp:123-133). */
+typedef struct {
+  int32_t width, height;    /* image size (u8, single channel) */
+  int32_t threshold;        /* AGAST corner threshold (absolute) */
+  int32_t octaves;          /* 0 = single scale (the shipped okvis setting), n>0 = 2n scale-space layers */
+  int32_t max_keypoints;    /* FrontendParameters::max_num_keypoints: keep the N strongest; 0 = no cap */
+  int32_t descriptor_bytes; /* 64 = BRISK-512 (north_star). 48 is accepted by the matchers only. */
+  int32_t max_batch;        /* frames per batched call (>=1) */
+  float pattern_scale;      /* BRISK pattern scale (1.0) */
+} okb_camera_config_t;
+
+typedef struct okb_context okb_context_t;
+
+/* ---- life cycle (replaces Frontend::Frontend + the six setters, Frontend.cpp:2398-2417; called where
+ *      ThreadedSlam::init pushes the yaml parameters, okvis_multisensor_processing/src/ThreadedSlam.cpp:89-94) */
+int okb_create(int device, int n_cams, const okb_camera_config_t* cfgs, okb_context_t** out);
+void okb_destroy(okb_context_t* ctx);
+const char* okb_last_error(void);
+const char* okb_version(void);
+/* number of kernels of this library launched on this context so far (bench.py's gpu_launches) */
+int64_t okb_launch_count(const okb_context_t* ctx);
+/* the CUDA stream (cudaStream_t as void*) camera `cam` works on; okb_sync waits for all of them */
+void* okb_stream(okb_context_t* ctx, int cam);
+int okb_sync(okb_context_t* ctx);
+
+/* ---- detect + describe: replaces okvis::Frame::detect + okvis::Frame::describe, i.e. the calls
+ *      detector_->detect(image_, keypoints_) and extractor_->compute(image_, keypoints_, descriptors_)
+ *      (okvis_cv/include/okvis/implementation/Frame.hpp:140-154,160-175) issued by
+ *      Frontend::detectAndDescribe (Frontend.cpp:221-269). Like compute(), it may drop border keypoints; the
+ *      keypoints returned are exactly those that own a descriptor row. Thread-safe for different `cam`
+ *      (one stream + workspace per camera; reference: per-camera mutex, Frontend.cpp:226).
+ *      kp_out: cap records; desc_out: cap x descriptor_bytes, row-major, continuous (Frame.hpp:287-289);
+ *      *n_out: number written. */
+int okb_detect_describe(okb_context_t* ctx, int cam, const uint8_t* image, size_t stride_bytes,
+                        okb_keypoint_t* kp_out, uint8_t* desc_out, int cap, int* n_out);
+/* n_frames <= max_batch images of the same camera in one submission (batch replay, BASELINE config 5).
+ * images: n_frames x height x stride_bytes; kp_out: n_frames x cap; desc_out: n_frames x cap x D; n_out: n_frames */
+int okb_detect_describe_batch(okb_context_t* ctx, int cam, int n_frames, const uint8_t* images, size_t stride_bytes,
+                              okb_keypoint_t* kp_out, uint8_t* desc_out, int cap, int* n_out);
+/* Same, but `d_images` (n_frames x height x width, pitch = width) is a DEVICE pointer and results stay on the
+ * device inside the context (read them with okb_fetch_features). Asynchronous on okb_stream(ctx, cam). */
+int okb_detect_describe_batch_device(okb_context_t* ctx, int cam, int n_frames, const uint8_t* d_images);
+int okb_fetch_features(okb_context_t* ctx, int cam, int frame, okb_keypoint_t* kp_out, uint8_t* desc_out, int cap,
+                       int* n_out);
+/* device pointers of the last result of camera `cam` (valid until the next detect call on it):
+ * keypoints [max_batch][capacity], descriptors [max_batch][capacity][D], counts [max_batch] */
+int okb_device_features(okb_context_t* ctx, int cam, const okb_keypoint_t** d_kp, const uint8_t** d_desc,
+                        const int32_t** d_count, int* capacity);
+
+/* inspection hooks used by the parity tests (layer geometry and the intermediate maps of the last frame 0) */
+int okb_num_layers(okb_context_t* ctx, int cam);
+int okb_layer_info(okb_context_t* ctx, int cam, int layer, int* width, int* height, float* scale, float* offset);
+int okb_fetch_layer(okb_context_t* ctx, int cam, int frame, int layer, uint8_t* image_out, uint8_t* score_out);
+/* algorithmic bytes of the pyramid+score pass for one image of camera `cam` (read base + write
+ * reduced layers + write score maps, from the actual layer sizes) */
+int64_t okb_pyramid_score_bytes(okb_context_t* ctx, int cam);
+/* accumulated device time (ms, CUDA events on the camera stream) and launches of the pyramid+score kernels since
+ * the last okb_reset_timers; enabled by okb_enable_timers(ctx, 1) */
+int okb_enable_timers(okb_context_t* ctx, int on);
+int okb_reset_timers(okb_context_t* ctx);
+int okb_get_timers(okb_context_t* ctx, int cam, double* pyramid_score_ms, int64_t* pyramid_score_launches,
+                   double* total_ms);
+
+/* ---- matchers. Descriptors are n x D u8, D in {48, 64}. "First in the reference's iteration order wins ties"
+ *      (strict <) is honoured bit-exactly; geometric gates are evaluated on the device in fp64 without FMA
+ *      contraction. Index outputs are -1 / distance outputs are match_threshold when nothing matched. ---- */
+
+/* M1: replaces Frontend::matchToMapByThread (Frontend.cpp:1515-1590) for one camera.
+ * Candidates are the pooled landmark descriptors (descriptorPool, Frontend.cpp:1221-1223,1348) in ascending
+ * LandmarkId order, cand_lm[c] = landmark slot of descriptor c (non-decreasing), lm_proj = LandmarkToMatch::projection
+ * (Frontend.cpp:1259), lm_is3d = LandmarkToMatch::is3d. kp_use[k]=0 skips keypoint k (Frontend.cpp:1546-1550). */
+int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc, const double* kp_xy,
+                    const uint8_t* kp_use, int n_cand, const uint8_t* cand_desc, const int32_t* cand_lm, int n_lm,
+                    const double* lm_proj, const uint8_t* lm_is3d, double reprojection_threshold,
+                    uint32_t match_threshold, uint32_t* out_dist, int32_t* out_lm);
+
+/* M2: replaces Frontend::matchToMapByThreadUnitialised (Frontend.cpp:1594-1720). kp_e_W: world-frame unit rays
+ * T_WC1.C()*e1_C.normalized() (Frontend.cpp:1620-1627); cand_e_W / cand_r_W: LandmarkToMatch::e_W / r_W per pooled
+ * descriptor (Frontend.cpp:1333-1334); r_WC1 = T_WC1.r(); sigma = 1/focalLength (Frontend.cpp:1636).
+ * kp_prev_lm (may be NULL): landmark slot already assigned to k (loop-closure mode early break, :1706-1709);
+ * out_ctr counts those early breaks. out_hp_W: n_kp x 4, written only by non-parallel accepted matches (:1713-1715). */
+int okb_match_map_uninit(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc, const double* kp_e_W,
+                         const uint8_t* kp_use, const int32_t* kp_prev_lm, int n_cand, const uint8_t* cand_desc,
+                         const int32_t* cand_lm, const double* cand_e_W, const double* cand_r_W, int n_lm,
+                         const uint8_t* lm_is3d, const double r_WC1[3], double sigma, uint32_t match_threshold,
+                         uint32_t* out_dist, int32_t* out_lm, double* out_hp_W, int32_t* out_ctr);
+
+/* M3: replaces the worker lambda of Frontend::matchMotionStereo (Frontend.cpp:1809-1907) for one (older frame,
+ * camera) pair, up to and including the choice of k1_max/hps_W/initialisable; `quality` (acos, :1888) and the
+ * final 4 px re-projection check (:1897-1904) stay with the caller, who owns the camera model.
+ * use0[k0]: keypoint k0 is eligible and has a valid back-projection (:1813-1842); e0_W = (T_WC0.C()*e0_C).normalized();
+ * size_over_f0[k0] = size0/f0 (sigma = that * 0.125, :1838). Frame-1 arrays are the compacted unmatched set k1s
+ * (:1789-1801): valid1 = getBackProjection succeeded, e1_W likewise normalised. T_CW0/T_CW1: row-major 3x4 [R|t] of
+ * T_WC.inverse(). out_k1 indexes the compacted set. */
+int okb_match_motion_stereo(okb_context_t* ctx, int D, int n0, const uint8_t* desc0, const uint8_t* use0,
+                            const double* e0_W, const double* size_over_f0, int n1, const uint8_t* desc1,
+                            const uint8_t* valid1, const double* e1_W, const double r_WC0[3], const double r_WC1[3],
+                            const double T_CW0[12], const double T_CW1[12], uint32_t match_threshold,
+                            int32_t* out_k1, uint32_t* out_dist, double* out_hp_W, uint8_t* out_initialisable);
+
+/* M4: replaces the k0/k1 double loop of Frontend::matchStereo (Frontend.cpp:2016-2074) for one overlapping camera
+ * pair (im0 < im1). valid0/valid1 = getBackProjection flags; size_over_f = size/f per keypoint
+ * (sigma = max(size0/f0, size1/f1)*0.125, :2035). The serial insertion logic (:2076-2141) stays with the caller. */
+int okb_match_stereo(okb_context_t* ctx, int D, int n0, const uint8_t* desc0, const uint8_t* valid0,
+                     const double* e0_W, const double* size_over_f0, int n1, const uint8_t* desc1,
+                     const uint8_t* valid1, const double* e1_W, const double* size_over_f1, const double r_WC0[3],
+                     const double r_WC1[3], const double T_CW0[12], const double T_CW1[12], uint32_t match_threshold,
+                     int32_t* out_k1, uint32_t* out_dist, double* out_hp_W, uint8_t* out_initialisable);
+
+/* M5: replaces the descriptor matching loop of Frontend::verifyRecognisedPlace (Frontend.cpp:329-355) for one camera:
+ * per old-frame landmark (descriptors lm_offsets[i]..lm_offsets[i+1]) the best keypoint over (descriptor, k) order. */
+int okb_match_place(okb_context_t* ctx, int D, int n_lm, const int32_t* lm_offsets, const uint8_t* lm_desc, int n_kp,
+                    const uint8_t* kp_desc, uint32_t match_threshold, int32_t* out_k, uint32_t* out_dist);
+
+/* H0: brisk::Hamming::PopcntofXORed over all pairs (call sites Frontend.cpp:341,1580,1661,1846,2024): the plain
+ * n_a x n_b distance matrix, for tests and the DBoW2 adapter (okvis_frontend/src/FBrisk.cpp:66). */
+int okb_hamming_matrix(okb_context_t* ctx, int D, int n_a, const uint8_t* a, int n_b, const uint8_t* b,
+                       uint16_t* out_dist);
+
+/* Device-resident M1 (benchmark "value" leg: inputs already in HBM): matches the features the last
+ * okb_detect_describe_batch_device call left on the device for camera `cam`, frame `frame`, against a device-resident
+ * landmark pool. All d_* pointers are device pointers; d_out_* hold kp-capacity entries (okb_device_features).
+ * Asynchronous on okb_stream(ctx, cam). */
+int okb_match_map3d_device(okb_context_t* ctx, int cam, int frame, int n_cand, const uint8_t* d_cand_desc,
+                           const int32_t* d_cand_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
+                           double reprojection_threshold, uint32_t match_threshold, uint32_t* d_out_dist,
+                           int32_t* d_out_lm);
+#ifdef __cplusplus
+}
+#endif
+#endif /* OKVIS_B200_H */

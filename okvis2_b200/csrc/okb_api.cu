@@ -1,0 +1,263 @@
+// okb_api.cu -- extern "C" shim of libokvis_b200.so (declared in include/okvis_b200.h): context life cycle,
+// host<->device staging around the detect/describe kernels, inspection hooks. No CPU fallback anywhere.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "okb_internal.h"
+
+namespace okb {
+static thread_local char g_err[512] = "";
+static char g_err_global[512] = "";
+static std::mutex g_err_mutex;
+void set_error(const char* fmt, ...)
+{
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  std::lock_guard<std::mutex> lk(g_err_mutex);
+  memcpy(g_err_global, g_err, sizeof(g_err));
+}
+void detect_collect_timing(okb_context* ctx, int cam);
+int match_init(okb_context* ctx);
+void match_free(okb_context* ctx);
+}  // namespace okb
+
+using namespace okb;
+
+extern "C" {
+
+const char* okb_last_error(void) { return g_err[0] ? g_err : g_err_global; }
+const char* okb_version(void) { return "okvis2_b200 0.1 (sm_100a)"; }
+
+int okb_create(int device, int n_cams, const okb_camera_config_t* cfgs, okb_context_t** out)
+{
+  if (!out || n_cams < 0 || (n_cams > 0 && !cfgs)) { set_error("okb_create: bad arguments"); return OKB_ERR_ARGUMENT; }
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    set_error("okb_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+    return OKB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n_dev) { set_error("okb_create: device %d of %d", device, n_dev); return OKB_ERR_ARGUMENT; }
+  OKB_CUDA(cudaSetDevice(device));
+  okb_context* ctx = new okb_context();
+  ctx->device = device; ctx->n_cams = n_cams; ctx->cams.resize(n_cams);
+  float ps = n_cams > 0 ? cfgs[0].pattern_scale : 1.0f;
+  if (ps <= 0.f) ps = 1.0f;
+  int rc = tables_init(ctx, ps);
+  if (rc != OKB_OK) { delete ctx; return rc; }
+  for (int i = 0; i < n_cams; i++) {
+    ctx->cams[i].cfg = cfgs[i];
+    okb_camera_config_t& c = ctx->cams[i].cfg;
+    if (c.max_batch < 1) c.max_batch = 1;
+    if (c.descriptor_bytes == 0) c.descriptor_bytes = 64;
+    if (c.descriptor_bytes != 64) {
+      set_error("camera %d: descriptor_bytes=%d: detect/describe implements the 64-byte BRISK-512 descriptor only; the "
+                "48-byte camera-aware BRISK2 extractor of smartroboticslab/brisk has no available specification",
+                i, c.descriptor_bytes);
+      okb_destroy(ctx); return OKB_ERR_UNSUPPORTED;
+    }
+    if (c.threshold < 1 || c.threshold > 254) { set_error("camera %d: threshold %d", i, c.threshold); okb_destroy(ctx); return OKB_ERR_ARGUMENT; }
+    rc = detect_init_camera(ctx, i);
+    if (rc != OKB_OK) { okb_destroy(ctx); return rc; }
+  }
+  rc = match_init(ctx);
+  if (rc != OKB_OK) { okb_destroy(ctx); return rc; }
+  OKB_CUDA(cudaDeviceSynchronize());
+  *out = ctx;
+  return OKB_OK;
+}
+
+void okb_destroy(okb_context_t* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < ctx->n_cams; i++) detect_free_camera(ctx, i);
+  match_free(ctx);
+  tables_free(ctx);
+  delete ctx;
+}
+
+int64_t okb_launch_count(const okb_context_t* ctx) { return ctx ? ctx->launches : 0; }
+void* okb_stream(okb_context_t* ctx, int cam)
+{
+  if (!ctx) return nullptr;
+  if (cam < 0 || cam >= ctx->n_cams) return (void*)ctx->match.stream;
+  return (void*)ctx->cams[cam].stream;
+}
+int okb_sync(okb_context_t* ctx)
+{
+  if (!ctx) return OKB_ERR_ARGUMENT;
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  for (int i = 0; i < ctx->n_cams; i++) OKB_CUDA(cudaStreamSynchronize(ctx->cams[i].stream));
+  OKB_CUDA(cudaStreamSynchronize(ctx->match.stream));
+  return OKB_OK;
+}
+
+static int check_cam(okb_context_t* ctx, int cam, const char* who)
+{
+  if (!ctx || cam < 0 || cam >= ctx->n_cams) { set_error("%s: bad context/camera %d", who, cam); return OKB_ERR_ARGUMENT; }
+  return OKB_OK;
+}
+
+static int status_to_error(const CamWorkspace& ws, int n_frames)
+{
+  for (int b = 0; b < n_frames; b++)
+    if (ws.h_status[b]) {
+      set_error("detect: device capacity exceeded on frame %d (flags 0x%x: 1=candidates>%d, 2=ties, 4=keypoints>sort cap, "
+                "8=keypoints>output cap %d)", b, ws.h_status[b], ws.cand_cap, ws.kp_cap);
+      return OKB_ERR_CAPACITY;
+    }
+  return OKB_OK;
+}
+
+int okb_detect_describe_batch(okb_context_t* ctx, int cam, int n_frames, const uint8_t* images, size_t stride_bytes,
+                              okb_keypoint_t* kp_out, uint8_t* desc_out, int cap, int* n_out)
+{
+  int rc = check_cam(ctx, cam, "okb_detect_describe");
+  if (rc) return rc;
+  CamWorkspace& ws = ctx->cams[cam];
+  const int W = ws.cfg.width, H = ws.cfg.height;
+  if (!images || !kp_out || !desc_out || !n_out || cap < 0 || n_frames < 1 || n_frames > ws.cfg.max_batch || stride_bytes < (size_t)W) {
+    set_error("okb_detect_describe: bad arguments (n_frames %d of max_batch %d)", n_frames, ws.cfg.max_batch);
+    return OKB_ERR_ARGUMENT;
+  }
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ws.stream;
+  // host -> pinned -> device (the caller's buffer is pageable cv::Mat memory)
+  for (int b = 0; b < n_frames; b++)
+    for (int y = 0; y < H; y++) memcpy(ws.h_img + ((size_t)b * H + y) * W, images + ((size_t)b * H + y) * stride_bytes, (size_t)W);
+  static_assert(sizeof(okb_keypoint_t) == 28, "cv::KeyPoint layout");
+  OKB_CUDA(cudaMemcpyAsync(ws.d_in, ws.h_img, (size_t)W * H * n_frames, cudaMemcpyHostToDevice, st));
+  rc = detect_run_device(ctx, cam, n_frames, ws.d_in, W);
+  if (rc) return rc;
+  OKB_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, 4 * n_frames, cudaMemcpyDeviceToHost, st));
+  OKB_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, 4 * n_frames, cudaMemcpyDeviceToHost, st));
+  // keypoint / descriptor payload: copy the capacity-bounded blocks, then trim on the host
+  const int rows = cap < ws.kp_cap ? cap : ws.kp_cap;
+  if (n_frames == 1) {
+    OKB_CUDA(cudaMemcpyAsync(ws.h_kp, ws.d_kp, (size_t)rows * sizeof(okb_keypoint_t), cudaMemcpyDeviceToHost, st));
+    OKB_CUDA(cudaMemcpyAsync(ws.h_desc, ws.d_desc, (size_t)rows * 64, cudaMemcpyDeviceToHost, st));
+  } else {
+    OKB_CUDA(cudaMemcpyAsync(ws.h_kp, ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t) * n_frames, cudaMemcpyDeviceToHost, st));
+    OKB_CUDA(cudaMemcpyAsync(ws.h_desc, ws.d_desc, (size_t)ws.kp_cap * 64 * n_frames, cudaMemcpyDeviceToHost, st));
+  }
+  OKB_CUDA(cudaStreamSynchronize(st));
+  rc = status_to_error(ws, n_frames);
+  if (rc) return rc;
+  for (int b = 0; b < n_frames; b++) {
+    int n = ws.h_count[b];
+    if (n > cap) { set_error("okb_detect_describe: %d keypoints do not fit the caller's capacity %d", n, cap); return OKB_ERR_CAPACITY; }
+    n_out[b] = n;
+    memcpy(kp_out + (size_t)b * cap, ws.h_kp + (size_t)b * ws.kp_cap, (size_t)n * sizeof(okb_keypoint_t));
+    memcpy(desc_out + (size_t)b * cap * 64, ws.h_desc + (size_t)b * ws.kp_cap * 64, (size_t)n * 64);
+  }
+  return OKB_OK;
+}
+
+int okb_detect_describe(okb_context_t* ctx, int cam, const uint8_t* image, size_t stride_bytes, okb_keypoint_t* kp_out,
+                        uint8_t* desc_out, int cap, int* n_out)
+{
+  return okb_detect_describe_batch(ctx, cam, 1, image, stride_bytes, kp_out, desc_out, cap, n_out);
+}
+
+int okb_detect_describe_batch_device(okb_context_t* ctx, int cam, int n_frames, const uint8_t* d_images)
+{
+  int rc = check_cam(ctx, cam, "okb_detect_describe_batch_device");
+  if (rc) return rc;
+  CamWorkspace& ws = ctx->cams[cam];
+  if (!d_images || n_frames < 1 || n_frames > ws.cfg.max_batch) { set_error("okb_detect_describe_batch_device: bad arguments"); return OKB_ERR_ARGUMENT; }
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  return detect_run_device(ctx, cam, n_frames, d_images, ws.cfg.width);
+}
+
+int okb_fetch_features(okb_context_t* ctx, int cam, int frame, okb_keypoint_t* kp_out, uint8_t* desc_out, int cap, int* n_out)
+{
+  int rc = check_cam(ctx, cam, "okb_fetch_features");
+  if (rc) return rc;
+  CamWorkspace& ws = ctx->cams[cam];
+  if (frame < 0 || frame >= ws.cfg.max_batch || !n_out) { set_error("okb_fetch_features: bad arguments"); return OKB_ERR_ARGUMENT; }
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  OKB_CUDA(cudaStreamSynchronize(ws.stream));
+  int n = 0, status = 0;
+  OKB_CUDA(cudaMemcpy(&n, ws.d_count + frame, 4, cudaMemcpyDeviceToHost));
+  OKB_CUDA(cudaMemcpy(&status, ws.d_status + frame, 4, cudaMemcpyDeviceToHost));
+  if (status) { ws.h_status[0] = status; return status_to_error(ws, 1); }
+  if (n > cap) { set_error("okb_fetch_features: %d keypoints > capacity %d", n, cap); return OKB_ERR_CAPACITY; }
+  *n_out = n;
+  if (kp_out) OKB_CUDA(cudaMemcpy(kp_out, ws.d_kp + (size_t)frame * ws.kp_cap, (size_t)n * sizeof(okb_keypoint_t), cudaMemcpyDeviceToHost));
+  if (desc_out) OKB_CUDA(cudaMemcpy(desc_out, ws.d_desc + (size_t)frame * ws.kp_cap * 64, (size_t)n * 64, cudaMemcpyDeviceToHost));
+  return OKB_OK;
+}
+
+int okb_device_features(okb_context_t* ctx, int cam, const okb_keypoint_t** d_kp, const uint8_t** d_desc,
+                        const int32_t** d_count, int* capacity)
+{
+  int rc = check_cam(ctx, cam, "okb_device_features");
+  if (rc) return rc;
+  CamWorkspace& ws = ctx->cams[cam];
+  if (d_kp) *d_kp = ws.d_kp;
+  if (d_desc) *d_desc = ws.d_desc;
+  if (d_count) *d_count = ws.d_count;
+  if (capacity) *capacity = ws.kp_cap;
+  return OKB_OK;
+}
+
+int okb_num_layers(okb_context_t* ctx, int cam) { return check_cam(ctx, cam, "okb_num_layers") ? -1 : ctx->cams[cam].n_layers; }
+
+int okb_layer_info(okb_context_t* ctx, int cam, int layer, int* width, int* height, float* scale, float* offset)
+{
+  int rc = check_cam(ctx, cam, "okb_layer_info");
+  if (rc) return rc;
+  CamWorkspace& ws = ctx->cams[cam];
+  if (layer < 0 || layer >= ws.n_layers) { set_error("okb_layer_info: layer %d", layer); return OKB_ERR_ARGUMENT; }
+  const LayerGeom& g = ws.geom[layer];
+  if (width) *width = g.w; if (height) *height = g.h; if (scale) *scale = g.scale; if (offset) *offset = g.offset_px;
+  return OKB_OK;
+}
+
+int okb_fetch_layer(okb_context_t* ctx, int cam, int frame, int layer, uint8_t* image_out, uint8_t* score_out)
+{
+  int rc = check_cam(ctx, cam, "okb_fetch_layer");
+  if (rc) return rc;
+  CamWorkspace& ws = ctx->cams[cam];
+  if (layer < 0 || layer >= ws.n_layers || frame < 0 || frame >= ws.cfg.max_batch) { set_error("okb_fetch_layer: bad index"); return OKB_ERR_ARGUMENT; }
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  OKB_CUDA(cudaStreamSynchronize(ws.stream));
+  const LayerGeom& g = ws.geom[layer];
+  const size_t fo = (size_t)frame * ws.dl.frame_stride + g.offset;
+  if (image_out) {
+    if (layer == 0) OKB_CUDA(cudaMemcpy(image_out, ws.d_in + (size_t)frame * g.w * g.h, (size_t)g.w * g.h, cudaMemcpyDeviceToHost));
+    else OKB_CUDA(cudaMemcpy2D(image_out, g.w, ws.d_img + fo, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+  }
+  if (score_out) OKB_CUDA(cudaMemcpy2D(score_out, g.w, ws.d_score + fo, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+  return OKB_OK;
+}
+
+int64_t okb_pyramid_score_bytes(okb_context_t* ctx, int cam) { return check_cam(ctx, cam, "okb_pyramid_score_bytes") ? -1 : ctx->cams[cam].ps_bytes; }
+
+int okb_enable_timers(okb_context_t* ctx, int on) { if (!ctx) return OKB_ERR_ARGUMENT; ctx->timers_on = on; return OKB_OK; }
+int okb_reset_timers(okb_context_t* ctx)
+{
+  if (!ctx) return OKB_ERR_ARGUMENT;
+  for (auto& ws : ctx->cams) { if (ws.pending_timing) { cudaEventSynchronize(ws.ev[3]); ws.pending_timing = 0; } ws.ps_ms = ws.total_ms = 0; ws.ps_launches = 0; }
+  return OKB_OK;
+}
+int okb_get_timers(okb_context_t* ctx, int cam, double* pyramid_score_ms, int64_t* pyramid_score_launches, double* total_ms)
+{
+  int rc = check_cam(ctx, cam, "okb_get_timers");
+  if (rc) return rc;
+  detect_collect_timing(ctx, cam);
+  CamWorkspace& ws = ctx->cams[cam];
+  if (pyramid_score_ms) *pyramid_score_ms = ws.ps_ms;
+  if (pyramid_score_launches) *pyramid_score_launches = ws.ps_launches;
+  if (total_ms) *total_ms = ws.total_ms;
+  return OKB_OK;
+}
+
+}  // extern "C"

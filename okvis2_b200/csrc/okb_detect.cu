@@ -1,0 +1,842 @@
+// okb_detect.cu -- detect + describe kernels (sm_100a) and their host-side sequencing.
+//
+// Replaces, for one camera, detector_->detect(image_, keypoints_) and extractor_->compute(image_, keypoints_,
+// descriptors_) (reference okvis_cv/include/okvis/implementation/Frame.hpp:152,167) as driven by
+// Frontend::detectAndDescribe (reference okvis_frontend/src/Frontend.cpp:221-269).
+//
+// Pipeline per batch of frames (blockIdx.z / blockIdx.y = frame):
+//   k_resize        INTER_AREA pyramid layers (2/3-sample and half-sample), table driven, bit-exact rounding
+//   k_score         AGAST 9-16 score map of every layer (thresholded u8), tiles staged in shared memory
+//   k_nms           3x3 non-max candidates + tie flag, warp-ballot compaction
+//   k_refine        sub-pixel / scale refinement of every candidate (pure), cache-touch events of non-tie maxima
+//   k_resolve       order-exact resolution of tied maxima (touch-time map)
+//   k_finalize      order by (layer, y, x), keep the N strongest, drop border keypoints, pattern scale index
+//   k_integral_*    int32 integral image
+//   k_describe      one warp per keypoint: 2 x 60 smoothed samples, orientation, 512 bits via ballot
+#include <stdio.h>
+
+#include <algorithm>
+
+#include "okb_internal.h"
+
+namespace okb {
+
+// ---------------------------------------------------------------------------------------------------------------
+struct FrameViews {
+  LayerView L[kMaxLayers];
+  uint8_t* score[kMaxLayers];
+  uint32_t* touch[kMaxLayers];
+  int n;
+};
+
+__device__ __forceinline__ void make_views(const DeviceLayers& dl, const uint8_t* in0, int in_pitch, size_t in_frame_stride,
+                                           uint8_t* img_block, uint8_t* score_block, uint32_t* touch_block, int frame,
+                                           FrameViews& v)
+{
+  v.n = dl.n;
+  uint8_t* ib = img_block + (size_t)frame * dl.frame_stride;
+  uint8_t* sb = score_block + (size_t)frame * dl.frame_stride;
+  uint32_t* tb = touch_block ? touch_block + (size_t)frame * dl.frame_stride : nullptr;
+#pragma unroll
+  for (int i = 0; i < kMaxLayers; i++) {
+    if (i < dl.n) {
+      const DeviceLayer& d = dl.l[i];
+      v.L[i].w = d.w; v.L[i].h = d.h; v.L[i].scale = d.scale; v.L[i].offset = d.offset_px;
+      if (i == 0) { v.L[i].img = in0 + (size_t)frame * in_frame_stride; v.L[i].pitch = in_pitch; }
+      else { v.L[i].img = ib + d.offset; v.L[i].pitch = d.pitch; }
+      v.score[i] = sb + d.offset;
+      v.touch[i] = tb ? tb + d.offset : nullptr;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pyramid
+struct ResizeJob {
+  const uint8_t* src; int src_pitch; size_t src_frame_stride;
+  uint8_t* dst; int dst_pitch; size_t dst_frame_stride;
+  int dw, dh, fast2;
+  const int *xs, *xn, *ys, *yn; const float *xa, *ya;
+};
+struct ResizeJobs { ResizeJob j[2]; int n; int tiles_x[2], tiles_y[2]; };
+
+__global__ void __launch_bounds__(256) k_resize(ResizeJobs jobs)
+{
+  int t = blockIdx.x, ji = 0;
+  const int n0 = jobs.tiles_x[0] * jobs.tiles_y[0];
+  if (t >= n0) { t -= n0; ji = 1; }
+  const ResizeJob& J = jobs.j[ji];
+  const int tx = t % jobs.tiles_x[ji], ty = t / jobs.tiles_x[ji];
+  const int frame = blockIdx.y;
+  const int x = tx * 32 + (threadIdx.x & 31);
+  const int y0 = ty * 32 + (threadIdx.x >> 5) * 4;
+  if (x >= J.dw) return;
+  const uint8_t* src = J.src + (size_t)frame * J.src_frame_stride;
+  uint8_t* dst = J.dst + (size_t)frame * J.dst_frame_stride;
+  if (J.fast2) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) { const int y = y0 + r; if (y < J.dh) dst[(size_t)y * J.dst_pitch + x] = half_pixel(src, J.src_pitch, x, y); }
+  } else {
+    const int xs = J.xs[x], xn = J.xn[x];
+    float xa[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) xa[i] = J.xa[x * 4 + i];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int y = y0 + r;
+      if (y < J.dh) {
+        float ya[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) ya[i] = J.ya[y * 4 + i];
+        dst[(size_t)y * J.dst_pitch + x] = area_pixel(src, J.src_pitch, xs, xn, xa, J.ys[y], J.yn[y], ya);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// score map. Tile = 64 x 32 pixels, 256 threads, each thread 2 x 4 pixels. Halo 3 (+1 for word alignment).
+constexpr int kTileW = 64, kTileH = 32;
+constexpr int kSmemW = kTileW + 8;   // bytes per smem row: x0-4 .. x0+67
+constexpr int kSmemH = kTileH + 6;
+
+struct TileMap { int n_layers; int tile_prefix[kMaxLayers + 1]; int tiles_x[kMaxLayers]; };
+
+__device__ __forceinline__ int find_layer(const TileMap& tm, int tile)
+{
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxLayers; i++) if (i < tm.n_layers && tile >= tm.tile_prefix[i]) l = i;
+  return l;
+}
+
+__global__ void __launch_bounds__(256) k_score(DeviceLayers dl, TileMap tm, const uint8_t* in0, int in_pitch,
+                                               size_t in_frame_stride, uint8_t* img_block, uint8_t* score_block,
+                                               int threshold)
+{
+  __shared__ __align__(16) uint8_t tile[kSmemH][kSmemW];
+  const int frame = blockIdx.y;
+  const int layer = find_layer(tm, blockIdx.x);
+  const int t = blockIdx.x - tm.tile_prefix[layer];
+  const int tx = t % tm.tiles_x[layer], ty = t / tm.tiles_x[layer];
+  const DeviceLayer d = dl.l[layer];
+  const uint8_t* img; int pitch;
+  if (layer == 0) { img = in0 + (size_t)frame * in_frame_stride; pitch = in_pitch; }
+  else { img = img_block + (size_t)frame * dl.frame_stride + d.offset; pitch = d.pitch; }
+  uint8_t* score = score_block + (size_t)frame * dl.frame_stride + d.offset;
+  const int x0 = tx * kTileW, y0 = ty * kTileH;
+  // stage the tile: words of 4 bytes, zero outside the image
+  const bool word_ok = ((pitch & 3) == 0) && ((((uintptr_t)img) & 3) == 0);
+  for (int i = threadIdx.x; i < kSmemH * (kSmemW / 4); i += 256) {
+    const int r = i / (kSmemW / 4), c = i % (kSmemW / 4);
+    const int y = y0 - 3 + r, x = x0 - 4 + c * 4;
+    uint32_t w = 0;
+    if (y >= 0 && y < d.h) {
+      const uint8_t* row = img + (size_t)y * pitch;
+      if (word_ok && x >= 0 && x + 3 < d.w) w = *reinterpret_cast<const uint32_t*>(row + x);
+      else {
+#pragma unroll
+        for (int b = 0; b < 4; b++) { const int xx = x + b; if (xx >= 0 && xx < d.w) w |= (uint32_t)row[xx] << (8 * b); }
+      }
+    }
+    *reinterpret_cast<uint32_t*>(&tile[r][c * 4]) = w;
+  }
+  __syncthreads();
+  const int lx = (threadIdx.x & 15) * 4, ly = (threadIdx.x >> 4);
+#pragma unroll
+  for (int rr = 0; rr < 2; rr++) {
+    const int yy = ly + rr * 16;
+    const int y = y0 + yy;
+    if (y >= d.h) continue;
+    uint32_t out = 0;
+#pragma unroll
+    for (int px = 0; px < 4; px++) {
+      const int x = x0 + lx + px;
+      int s = 0;
+      if (x >= 3 && y >= 3 && x < d.w - 3 && y < d.h - 3) {
+        const uint8_t* c = &tile[yy + 3][lx + px + 4];
+        const int p = c[0];
+        const int a0 = c[-3], a8 = c[3], a4 = c[-3 * kSmemW], a12 = c[3 * kSmemW];
+        const int hi = p + threshold, lo = p - threshold;
+        const bool br = (a0 > hi || a8 > hi) && (a4 > hi || a12 > hi);
+        const bool dk = (a0 < lo || a8 < lo) && (a4 < lo || a12 < lo);
+        if (br || dk) {
+          const int b = bstar16(c, kSmemW);
+          s = b < threshold ? 0 : (b > 254 ? 254 : b);
+        }
+      }
+      out |= (uint32_t)s << (8 * px);
+    }
+    const int x = x0 + lx;
+    if (x + 3 < d.w && (d.pitch & 3) == 0) *reinterpret_cast<uint32_t*>(score + (size_t)y * d.pitch + x) = out;
+    else for (int b = 0; b < 4; b++) if (x + b < d.w) score[(size_t)y * d.pitch + x + b] = (uint8_t)(out >> (8 * b));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 non-max candidates. Same tiling as k_score. One u32 per candidate: time key | tie << 31.
+__global__ void __launch_bounds__(256) k_nms(DeviceLayers dl, TileMap tm, const uint8_t* score_block, uint32_t* cand,
+                                             int32_t* cand_count, int cand_cap)
+{
+  const int frame = blockIdx.y;
+  const int layer = find_layer(tm, blockIdx.x);
+  const int t = blockIdx.x - tm.tile_prefix[layer];
+  const int tx = t % tm.tiles_x[layer], ty = t / tm.tiles_x[layer];
+  const DeviceLayer d = dl.l[layer];
+  const uint8_t* score = score_block + (size_t)frame * dl.frame_stride + d.offset;
+  const int x0 = tx * kTileW + (threadIdx.x & 15) * 4, yb = ty * kTileH + (threadIdx.x >> 4);
+  const int lane = threadIdx.x & 31;
+  for (int rr = 0; rr < 2; rr++) {
+    const int y = yb + rr * 16;
+    uint32_t w = 0;
+    const bool row_ok = y >= 3 && y < d.h - 3 && x0 < d.w;
+    if (row_ok) w = *reinterpret_cast<const uint32_t*>(score + (size_t)y * d.pitch + x0);  // pitch is a multiple of 4
+    for (int px = 0; px < 4; px++) {
+      const int c = (w >> (8 * px)) & 255;
+      const int x = x0 + px;
+      bool is_c = false, tie = false;
+      if (c > 0 && x >= 3 && x < d.w - 3) {
+        const uint8_t* s = score + (size_t)y * d.pitch + x;
+        is_c = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++) {
+            if (dx == 0 && dy == 0) continue;
+            const int v = s[dy * d.pitch + dx];
+            if (v > c) is_c = false;
+            if (v == c) tie = true;
+          }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, is_c);
+      if (m) {
+        int base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(&cand_count[frame], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (is_c) {
+          const int pos = base + __popc(m & ((1u << lane) - 1u));
+          if (pos < cand_cap) cand[(size_t)frame * cand_cap + pos] = time_key(layer, x, y) | (tie ? 0x80000000u : 0u);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_touches(const DeviceLayers& dl, uint32_t* touch_frame, int layer, int x, int y,
+                                             int own_touch, int has_above, const ScanTrace& tr, uint32_t entry)
+{
+  {
+    const DeviceLayer d = dl.l[layer];
+    uint32_t* tm = touch_frame + d.offset;
+    const int hi = own_touch == 2 ? 2 : 1;
+    if (own_touch)
+      for (int dy = -1; dy <= hi; dy++) for (int dx = -1; dx <= hi; dx++) {
+        const int xx = x + dx, yy = y + dy;
+        if (xx >= 0 && yy >= 0 && xx < d.w && yy < d.h) atomicMax(&tm[(size_t)yy * d.pitch + xx], entry);
+      }
+  }
+  if (has_above) {
+    const DeviceLayer d = dl.l[layer + 1];
+    uint32_t* tm = touch_frame + d.offset;
+    for_each_above_touch(layer, x, y, tr, [&](int xx, int yy) {
+      if (xx >= 0 && yy >= 0 && xx < d.w && yy < d.h) atomicMax(&tm[(size_t)yy * d.pitch + xx], entry);
+    });
+  }
+}
+
+__global__ void __launch_bounds__(128) k_refine(DeviceLayers dl, const uint8_t* in0, int in_pitch, size_t in_frame_stride,
+                                                uint8_t* img_block, uint8_t* score_block, uint32_t* touch_block,
+                                                const uint32_t* cand, const int32_t* cand_count, int cand_cap,
+                                                CandRecord* rec, int threshold, uint32_t epoch)
+{
+  const int frame = blockIdx.y;
+  const int n = min(cand_count[frame], cand_cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  FrameViews v;
+  make_views(dl, in0, in_pitch, in_frame_stride, img_block, score_block, touch_block, frame, v);
+  const uint32_t c = cand[(size_t)frame * cand_cap + i];
+  const uint32_t key = c & 0x7fffffffu;
+  const int tie = (int)(c >> 31);
+  const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+  RefineResult r;
+  refine_candidate(v.L, v.n, layer, x, y, threshold, r);
+  CandRecord out;
+  out.x = r.x; out.y = r.y; out.size = r.size; out.response = r.response; out.key = key;
+  out.keep = r.keep; out.own_touch = r.own_touch; out.has_above = r.has_above; out.tie = (int8_t)tie;
+  out.above = r.above; out.state = tie ? 0 : 1; out.pad[0] = out.pad[1] = out.pad[2] = 0;
+  rec[(size_t)frame * cand_cap + i] = out;
+  if (!tie)
+    emit_touches(dl, touch_block + (size_t)frame * dl.frame_stride, layer, x, y, r.own_touch, r.has_above, r.above,
+                 touch_entry(epoch, key));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// block-wide bitonic sort of n (power of two) 64-bit keys in shared memory, ascending
+__device__ void bitonic_sort_u64(unsigned long long* a, int n)
+{
+  for (int k = 2; k <= n; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = a[i], y = a[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+constexpr int kMaxTies = 4096;
+
+// One CTA per frame. Resolves, in dependency rounds, the candidates whose 2-D maximum test ties with a neighbour:
+// their outcome depends on which sub-threshold scores the sequential algorithm had already cached when it reached them.
+__global__ void __launch_bounds__(256) k_resolve(DeviceLayers dl, const uint8_t* in0, int in_pitch, size_t in_frame_stride,
+                                                 uint8_t* img_block, uint8_t* score_block, uint32_t* touch_block,
+                                                 const int32_t* cand_count, int cand_cap, CandRecord* rec,
+                                                 uint32_t epoch, int32_t* status)
+{
+  __shared__ unsigned long long ties[kMaxTies];  // key << 32 | record index, sorted
+  __shared__ int8_t state[kMaxTies];
+  __shared__ int8_t newly[kMaxTies];
+  __shared__ int n_ties, n_unresolved, layer_start[kMaxLayers + 1];
+  const int frame = blockIdx.x;
+  const int n = min(cand_count[frame], cand_cap);
+  CandRecord* R = rec + (size_t)frame * cand_cap;
+  if (threadIdx.x == 0) n_ties = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (R[i].tie) {
+      const int p = atomicAdd(&n_ties, 1);
+      if (p < kMaxTies) ties[p] = ((unsigned long long)R[i].key << 32) | (unsigned)i;
+    }
+  __syncthreads();
+  int T = n_ties;
+  if (T > kMaxTies) { if (threadIdx.x == 0) atomicOr(&status[frame], 2); T = kMaxTies; }
+  if (T == 0) return;
+  int P = 1; while (P < T) P <<= 1;
+  for (int i = T + threadIdx.x; i < P; i += blockDim.x) ties[i] = ~0ull;
+  __syncthreads();
+  bitonic_sort_u64(ties, P);
+  for (int i = threadIdx.x; i < T; i += blockDim.x) state[i] = 0;
+  if (threadIdx.x <= kMaxLayers) {
+    // first tie index of every layer (ties are sorted by key, layer is the top field)
+    const int l = threadIdx.x;
+    int lo = 0, hi = T;
+    const unsigned long long target = (unsigned long long)time_key(l, 0, 0) << 32;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < target) lo = mid + 1; else hi = mid; }
+    layer_start[l] = (l >= kMaxLayers) ? T : lo;
+  }
+  if (threadIdx.x == 0) n_unresolved = T;
+  __syncthreads();
+  FrameViews v;
+  make_views(dl, in0, in_pitch, in_frame_stride, img_block, score_block, touch_block, frame, v);
+  uint32_t* touch_frame = touch_block + (size_t)frame * dl.frame_stride;
+  while (true) {
+    for (int ti = threadIdx.x; ti < T; ti += blockDim.x) {
+      newly[ti] = 0;
+      if (state[ti] != 0) continue;
+      const uint32_t key = (uint32_t)(ties[ti] >> 32);
+      const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+      bool blocked = false;
+      // earlier unresolved ties of the same layer within 4 pixels
+      {
+        const int ylo = max(y - 4, 0);
+        const unsigned long long lo_key = (unsigned long long)time_key(layer, 0, ylo) << 32;
+        int lo = layer_start[layer], hi = ti;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < lo_key) lo = mid + 1; else hi = mid; }
+        for (int u = lo; u < ti && !blocked; u++) {
+          if (state[u] != 0) continue;
+          const uint32_t uk = (uint32_t)(ties[u] >> 32);
+          const int ux = (int)(uk & 2047);
+          if (abs(ux - x) <= 4) blocked = true;  // |dy| <= 4 by the key range
+        }
+      }
+      // unresolved ties of the layer below whose above-scan can reach the 5x5 window
+      if (!blocked && layer > 0) {
+        // rows of the layer below that can map into [y-2, y+2] (+ scan margins); the ratio is 3/2 or 4/3
+        const int uy_lo = max((y - 5) * 4 / 3 - 3, 0), uy_hi = (y + 5) * 3 / 2 + 4;
+        const unsigned long long lo_key = (unsigned long long)time_key(layer - 1, 0, min(uy_lo, 2047)) << 32;
+        int lo = layer_start[layer - 1], hi = layer_start[layer];
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < lo_key) lo = mid + 1; else hi = mid; }
+        for (int u = lo; u < layer_start[layer] && !blocked; u++) {
+          const uint32_t uk = (uint32_t)(ties[u] >> 32);
+          const int uy = (int)((uk >> 11) & 2047), ux = (int)(uk & 2047);
+          if (uy > uy_hi) break;
+          if (state[u] != 0) continue;
+          ScanIter it; above_window(layer - 1, ux, uy, it);
+          const int xa = (int)it.x_1 - 1, xb = (int)it.x1 + 2, ya = (int)it.y_1 - 1, yb = (int)it.y1 + 2;
+          if (!(x + 2 < xa || x - 2 > xb || y + 2 < ya || y - 2 > yb)) blocked = true;
+        }
+      }
+      if (blocked) continue;
+      const DeviceLayer d = dl.l[layer];
+      const uint8_t* sc = v.score[layer];
+      const uint32_t* tm = touch_frame + d.offset;
+      int m[5][5];
+#pragma unroll
+      for (int dy = -2; dy <= 2; dy++)
+#pragma unroll
+        for (int dx = -2; dx <= 2; dx++) {
+          const int xx = x + dx, yy = y + dy;
+          int val = sc[(size_t)yy * d.pitch + xx];
+          if (val == 0) {
+            const uint32_t e = __ldcg(&tm[(size_t)yy * d.pitch + xx]);
+            if (touched_before(e, epoch, key)) val = b0(v.L[layer], xx, yy);
+          }
+          m[dy + 2][dx + 2] = val;
+        }
+      newly[ti] = is_max_2d_5x5(m) ? 1 : 2;
+    }
+    __syncthreads();
+    for (int ti = threadIdx.x; ti < T; ti += blockDim.x) {
+      if (!newly[ti]) continue;
+      state[ti] = newly[ti];
+      atomicSub(&n_unresolved, 1);
+      const int ri = (int)(ties[ti] & 0xffffffffu);
+      R[ri].state = newly[ti];
+      if (newly[ti] == 1) {
+        const CandRecord c = R[ri];
+        const uint32_t key = c.key;
+        emit_touches(dl, touch_frame, (int)(key >> 22), (int)(key & 2047), (int)((key >> 11) & 2047), c.own_touch,
+                     c.has_above, c.above, touch_entry(epoch, key));
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (n_unresolved <= 0) break;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSortCap = 16384;
+
+__device__ __forceinline__ uint32_t float_order_bits(float f)
+{ // monotone map float -> uint32
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// exclusive scan of one int per thread across the block (blockDim.x == 1024); returns the total in `total`
+__device__ int block_exclusive_scan_1024(int val, int* sh /*33 ints*/, int& total)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = val;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) sh[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = sh[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+    sh[lane] = wi - w;
+    if (lane == 31) sh[32] = wi;
+  }
+  __syncthreads();
+  const int res = sh[warp] + incl - val;
+  total = sh[32];
+  __syncthreads();
+  return res;
+}
+
+// One CTA (1024 threads) per frame: order the surviving keypoints by (layer, y, x), keep the max_kp strongest
+// (ties: earlier first), drop the ones whose sampling pattern leaves the image, write cv::KeyPoint records.
+__global__ void __launch_bounds__(1024) k_finalize(const int32_t* cand_count, int cand_cap, const CandRecord* rec,
+                                                   const float* scale_bounds, const uint32_t* size_list, int W, int H,
+                                                   int max_kp, int kp_cap, okb_keypoint_t* kp_out, int32_t* kscale_out,
+                                                   int32_t* count_out, int32_t* status)
+{
+  extern __shared__ unsigned long long keys[];  // kSortCap sorted (key << 32 | record index)
+  __shared__ uint8_t flag[kSortCap];
+  __shared__ int n_valid, hist[256], sh_scan[33];
+  __shared__ uint32_t sel_prefix;
+  __shared__ int sel_remaining;
+  const int frame = blockIdx.x;
+  const int n = min(cand_count[frame], cand_cap);
+  if (cand_count[frame] > cand_cap && threadIdx.x == 0) atomicOr(&status[frame], 1);
+  const CandRecord* R = rec + (size_t)frame * cand_cap;
+  if (threadIdx.x == 0) n_valid = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const CandRecord& c = R[i];
+    if (c.state == 1 && c.keep) {
+      const int p = atomicAdd(&n_valid, 1);
+      if (p < kSortCap) keys[p] = ((unsigned long long)c.key << 32) | (unsigned)i;
+    }
+  }
+  __syncthreads();
+  int V = n_valid;
+  if (V > kSortCap) { if (threadIdx.x == 0) atomicOr(&status[frame], 4); V = kSortCap; }
+  int P = 1; while (P < V) P <<= 1;
+  for (int i = V + threadIdx.x; i < P; i += blockDim.x) keys[i] = ~0ull;
+  __syncthreads();
+  if (V > 1) bitonic_sort_u64(keys, P);
+  // ---- strongest max_kp: radix select of the max_kp-th largest response
+  const bool capped = max_kp > 0 && V > max_kp;
+  uint32_t thr_bits = 0; int n_equal_keep = 0;
+  if (capped) {
+    if (threadIdx.x == 0) { sel_prefix = 0; sel_remaining = max_kp; }
+    __syncthreads();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = sel_prefix;
+      const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+      for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        const uint32_t rb = float_order_bits(R[(int)(keys[i] & 0xffffffffu)].response);
+        if ((rb & himask) == (prefix & himask)) atomicAdd(&hist[(rb >> shift) & 255], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int rem = sel_remaining, b = 255;
+        for (; b > 0; b--) { if (hist[b] >= rem) break; rem -= hist[b]; }
+        sel_prefix = prefix | ((uint32_t)b << shift);
+        sel_remaining = rem;  // how many of the elements matching the prefix so far are still to be kept
+      }
+      __syncthreads();
+    }
+    thr_bits = sel_prefix; n_equal_keep = sel_remaining;
+  }
+  // each thread owns a contiguous chunk so that the scans preserve the (layer, y, x) order
+  const int chunk = (V + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int beg = min((int)threadIdx.x * chunk, V), end = min(beg + chunk, V);
+  int total = 0;
+  if (capped) {
+    int my_eq = 0;
+    for (int i = beg; i < end; i++) my_eq += (float_order_bits(R[(int)(keys[i] & 0xffffffffu)].response) == thr_bits);
+    int eq_before = block_exclusive_scan_1024(my_eq, sh_scan, total);
+    for (int i = beg; i < end; i++) {
+      const uint32_t rb = float_order_bits(R[(int)(keys[i] & 0xffffffffu)].response);
+      bool keep = rb > thr_bits;
+      if (rb == thr_bits) { keep = eq_before < n_equal_keep; eq_before++; }
+      flag[i] = keep;
+    }
+  } else {
+    for (int i = beg; i < end; i++) flag[i] = 1;
+  }
+  int my_keep = 0;
+  for (int i = beg; i < end; i++) {
+    if (!flag[i]) continue;
+    const CandRecord& c = R[(int)(keys[i] & 0xffffffffu)];
+    const int sc = kscale_from_bounds(scale_bounds, c.size);
+    const int bd = (int)size_list[sc];
+    const bool out = c.x < (float)bd || c.x >= (float)(W - bd) || c.y < (float)bd || c.y >= (float)(H - bd);
+    flag[i] = out ? 0 : (uint8_t)(sc + 1);
+    my_keep += !out;
+  }
+  int pos = block_exclusive_scan_1024(my_keep, sh_scan, total);
+  for (int i = beg; i < end; i++) {
+    if (!flag[i]) continue;
+    if (pos < kp_cap) {
+      const CandRecord& c = R[(int)(keys[i] & 0xffffffffu)];
+      okb_keypoint_t k;
+      k.x = c.x; k.y = c.y; k.size = c.size; k.angle = -1.f; k.response = c.response;
+      k.octave = (int)(c.key >> 22); k.class_id = -1;
+      kp_out[(size_t)frame * kp_cap + pos] = k;
+      kscale_out[(size_t)frame * kp_cap + pos] = (int)flag[i] - 1;
+    }
+    pos++;
+  }
+  if (threadIdx.x == 0) {
+    if (total > kp_cap) atomicOr(&status[frame], 8);
+    count_out[frame] = min(total, kp_cap);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// integral image: I[y+1][x+1] = sum of pixels in rows <= y, cols <= x. Row pass (warp per row) then column pass.
+__global__ void __launch_bounds__(256) k_integral_rows(const uint8_t* in0, int in_pitch, size_t in_frame_stride, int W, int H,
+                                                       int32_t* integral, int ipitch)
+{
+  const int frame = blockIdx.y;
+  const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  int32_t* I = integral + (size_t)frame * ipitch * (H + 1);
+  if (blockIdx.x == 0) for (int x = threadIdx.x; x <= W; x += 256) I[x] = 0;
+  if (y >= H) return;
+  const uint8_t* row = in0 + (size_t)frame * in_frame_stride + (size_t)y * in_pitch;
+  int32_t* out = I + (size_t)(y + 1) * ipitch;
+  if (lane == 0) out[0] = 0;
+  int carry = 0;
+  for (int x0 = 0; x0 < W; x0 += 128) {
+    const int x = x0 + lane * 4;
+    int v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = (x + i < W) ? row[x + i] : 0;
+    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+    int incl = v[3];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int base = carry + incl - v[3];
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (x + i < W) out[x + i + 1] = base + v[i];
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+__global__ void __launch_bounds__(128) k_integral_cols(int W, int H, int32_t* integral, int ipitch)
+{
+  const int frame = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (x > W) return;
+  int32_t* I = integral + (size_t)frame * ipitch * (H + 1) + x;
+  int acc = 0;
+  int y = 1;
+  for (; y + 7 <= H; y += 8) {
+    int v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = I[(size_t)(y + i) * ipitch];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc += v[i]; I[(size_t)(y + i) * ipitch] = acc; }
+  }
+  for (; y <= H; y++) { acc += I[(size_t)y * ipitch]; I[(size_t)y * ipitch] = acc; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// descriptor: one warp per keypoint
+__global__ void __launch_bounds__(128) k_describe(const uint8_t* in0, int in_pitch, size_t in_frame_stride, int H,
+                                                  const int32_t* integral, int ipitch, const PatternPoint* pattern,
+                                                  const uint32_t* short_pairs, const int4* long_pairs,
+                                                  okb_keypoint_t* kp, const int32_t* kscale, const int32_t* count,
+                                                  int kp_cap, uint8_t* desc)
+{
+  __shared__ int values[4][64];
+  const int frame = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 4 + warp;
+  if (k >= count[frame]) return;
+  const uint8_t* img = in0 + (size_t)frame * in_frame_stride;
+  const int32_t* I = integral + (size_t)frame * ipitch * (H + 1);
+  okb_keypoint_t* kpp = kp + (size_t)frame * kp_cap + k;
+  const float kx = kpp->x, ky = kpp->y;
+  const int sc = kscale[(size_t)frame * kp_cap + k];
+  int* val = values[warp];
+  const PatternPoint* pat0 = pattern + ((size_t)sc * kRot) * kPoints;
+  for (int i = lane; i < kPoints; i += 32) val[i] = smoothed_intensity(img, in_pitch, I, ipitch, kx, ky, pat0[i]);
+  __syncwarp();
+  int d0 = 0, d1 = 0;
+  for (int q = lane; q < kLongPairs; q += 32) {
+    const int4 lp = __ldg(&long_pairs[q]);
+    const int dt = val[lp.x] - val[lp.y];
+    d0 += dt * lp.z / 1024;
+    d1 += dt * lp.w / 1024;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+  float angle = (float)(atan2((double)(float)d1, (double)(float)d0) / 3.14159265358979323846 * 180.0);
+  int theta = (int)((double)kRot * ((double)angle / 360.0) + 0.5);
+  if (theta < 0) theta += kRot;
+  if (theta >= kRot) theta -= kRot;
+  if (angle < 0) angle += 360.f;
+  __syncwarp();
+  const PatternPoint* pat = pattern + ((size_t)sc * kRot + theta) * kPoints;
+  for (int i = lane; i < kPoints; i += 32) val[i] = smoothed_intensity(img, in_pitch, I, ipitch, kx, ky, pat[i]);
+  __syncwarp();
+  uint32_t mine = 0;
+#pragma unroll
+  for (int w = 0; w < 16; w++) {
+    const uint32_t pr = __ldg(&short_pairs[w * 32 + lane]);
+    const uint32_t word = __ballot_sync(0xffffffffu, val[pr & 255] > val[pr >> 8]);
+    if (lane == w) mine = word;
+  }
+  if (lane < 16) reinterpret_cast<uint32_t*>(desc + ((size_t)frame * kp_cap + k) * 64)[lane] = mine;
+  if (lane == 0) kpp->angle = angle;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int detect_init_camera(okb_context* ctx, int cam)
+{
+  CamWorkspace& ws = ctx->cams[cam];
+  const okb_camera_config_t& c = ws.cfg;
+  const int W = c.width, H = c.height;
+  ws.n_layers = c.octaves == 0 ? 1 : 2 * c.octaves;
+  if (ws.n_layers > kMaxLayers || W >= 2048 || H >= 2048 || W < 16 || H < 16) {
+    set_error("unsupported geometry: %dx%d, octaves %d (max 2047x2047, 4 octaves)", W, H, c.octaves);
+    return OKB_ERR_ARGUMENT;
+  }
+  auto set = [&](int i, int w, int h, float scale, int parent) {
+    LayerGeom& g = ws.geom[i];
+    g.w = w; g.h = h; g.pitch = (int)align_up((size_t)w, 64); g.scale = scale;
+    g.offset_px = i == 0 ? 0.f : 0.5f * scale - 0.5f; g.parent = parent;
+  };
+  set(0, W, H, 1.0f, -1);
+  if (ws.n_layers > 1) set(1, 2 * (W / 3), 2 * (H / 3), 1.5f, 0);
+  for (int i = 2; i < ws.n_layers; i += 2) {
+    set(i, ws.geom[i - 2].w / 2, ws.geom[i - 2].h / 2, ws.geom[i - 2].scale * 2, i - 2);
+    set(i + 1, ws.geom[i - 1].w / 2, ws.geom[i - 1].h / 2, ws.geom[i - 1].scale * 2, i - 1);
+  }
+  size_t off = 0;
+  ws.ps_bytes = (int64_t)W * H;  // read of the base image
+  for (int i = 0; i < ws.n_layers; i++) {
+    LayerGeom& g = ws.geom[i];
+    if (g.w < 8 || g.h < 8) { set_error("layer %d too small (%dx%d)", i, g.w, g.h); return OKB_ERR_ARGUMENT; }
+    g.offset = off; off += align_up((size_t)g.pitch * g.h, 256);
+    ws.ps_bytes += (int64_t)g.w * g.h * (i == 0 ? 1 : 2);  // score map write (+ layer image write for i > 0)
+    if (i > 0) {
+      const LayerGeom& p = ws.geom[g.parent];
+      const double sx = 1. / ((double)g.w / p.w), sy = 1. / ((double)g.h / p.h);
+      g.fast2 = (sx == 2.0 && sy == 2.0) ? 1 : 0;
+      if (!g.fast2) {
+        AreaAxis ax, ay; build_area_axis(p.w, g.w, ax); build_area_axis(p.h, g.h, ay);
+        OKB_CUDA(cudaMalloc(&g.d_xs, g.w * 4)); OKB_CUDA(cudaMalloc(&g.d_xn, g.w * 4)); OKB_CUDA(cudaMalloc(&g.d_xa, g.w * 16));
+        OKB_CUDA(cudaMalloc(&g.d_ys, g.h * 4)); OKB_CUDA(cudaMalloc(&g.d_yn, g.h * 4)); OKB_CUDA(cudaMalloc(&g.d_ya, g.h * 16));
+        OKB_CUDA(cudaMemcpy(g.d_xs, ax.start.data(), g.w * 4, cudaMemcpyHostToDevice));
+        OKB_CUDA(cudaMemcpy(g.d_xn, ax.count.data(), g.w * 4, cudaMemcpyHostToDevice));
+        OKB_CUDA(cudaMemcpy(g.d_xa, ax.alpha.data(), g.w * 16, cudaMemcpyHostToDevice));
+        OKB_CUDA(cudaMemcpy(g.d_ys, ay.start.data(), g.h * 4, cudaMemcpyHostToDevice));
+        OKB_CUDA(cudaMemcpy(g.d_yn, ay.count.data(), g.h * 4, cudaMemcpyHostToDevice));
+        OKB_CUDA(cudaMemcpy(g.d_ya, ay.alpha.data(), g.h * 16, cudaMemcpyHostToDevice));
+      }
+    }
+  }
+  ws.dl.n = ws.n_layers; ws.dl.frame_stride = (uint32_t)off;
+  for (int i = 0; i < ws.n_layers; i++) {
+    const LayerGeom& g = ws.geom[i];
+    ws.dl.l[i] = DeviceLayer{g.w, g.h, g.pitch, (uint32_t)g.offset, g.scale, g.offset_px};
+  }
+  const int B = c.max_batch;
+  ws.cand_cap = std::max(16384, (W * H / 32 + 1023) / 1024 * 1024);
+  ws.kp_cap = c.max_keypoints > 0 ? (int)align_up((size_t)c.max_keypoints, 64) : kSortCap;
+  OKB_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+  OKB_CUDA(cudaMalloc(&ws.d_in, (size_t)W * H * B));
+  OKB_CUDA(cudaMalloc(&ws.d_img, off * B));
+  OKB_CUDA(cudaMalloc(&ws.d_score, off * B));
+  OKB_CUDA(cudaMalloc(&ws.d_touch, off * B * 4));
+  OKB_CUDA(cudaMemset(ws.d_touch, 0, off * B * 4));
+  OKB_CUDA(cudaMemset(ws.d_score, 0, off * B));
+  OKB_CUDA(cudaMemset(ws.d_img, 0, off * B));
+  OKB_CUDA(cudaMalloc(&ws.d_integral, (size_t)(W + 1) * (H + 1) * 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_cand, (size_t)ws.cand_cap * 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_cand_count, 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_rec, (size_t)ws.cand_cap * sizeof(CandRecord) * B));
+  OKB_CUDA(cudaMalloc(&ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t) * B));
+  OKB_CUDA(cudaMalloc(&ws.d_kscale, (size_t)ws.kp_cap * 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_desc, (size_t)ws.kp_cap * 64 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_count, 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_status, 4 * B));
+  OKB_CUDA(cudaMemset(ws.d_count, 0, 4 * B));
+  OKB_CUDA(cudaMemset(ws.d_status, 0, 4 * B));
+  OKB_CUDA(cudaMallocHost(&ws.h_img, (size_t)W * H * B));
+  OKB_CUDA(cudaMallocHost(&ws.h_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t) * B));
+  OKB_CUDA(cudaMallocHost(&ws.h_desc, (size_t)ws.kp_cap * 64 * B));
+  OKB_CUDA(cudaMallocHost(&ws.h_count, 4 * B));
+  OKB_CUDA(cudaMallocHost(&ws.h_status, 4 * B));
+  for (int i = 0; i < 4; i++) OKB_CUDA(cudaEventCreate(&ws.ev[i]));
+  OKB_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8));
+  return OKB_OK;
+}
+
+void detect_free_camera(okb_context* ctx, int cam)
+{
+  CamWorkspace& ws = ctx->cams[cam];
+  for (int i = 0; i < kMaxLayers; i++) {
+    LayerGeom& g = ws.geom[i];
+    cudaFree(g.d_xs); cudaFree(g.d_xn); cudaFree(g.d_xa); cudaFree(g.d_ys); cudaFree(g.d_yn); cudaFree(g.d_ya);
+  }
+  cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
+  cudaFree(ws.d_cand_count); cudaFree(ws.d_rec); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
+  cudaFree(ws.d_count); cudaFree(ws.d_status);
+  cudaFreeHost(ws.h_img); cudaFreeHost(ws.h_kp); cudaFreeHost(ws.h_desc); cudaFreeHost(ws.h_count); cudaFreeHost(ws.h_status);
+  for (int i = 0; i < 4; i++) if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
+  if (ws.stream) cudaStreamDestroy(ws.stream);
+}
+
+static void collect_timing(okb_context* ctx, CamWorkspace& ws)
+{
+  if (!ws.pending_timing) return;
+  cudaEventSynchronize(ws.ev[3]);
+  float a = 0, b = 0;
+  cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]);
+  cudaEventElapsedTime(&b, ws.ev[0], ws.ev[3]);
+  ws.ps_ms += a; ws.total_ms += b;
+  ws.pending_timing = 0;
+  (void)ctx;
+}
+
+// all frames are device resident: d_images = n_frames x H x src_pitch
+int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch)
+{
+  CamWorkspace& ws = ctx->cams[cam];
+  const okb_camera_config_t& c = ws.cfg;
+  const int W = c.width, H = c.height, B = n_frames;
+  cudaStream_t st = ws.stream;
+  if (ctx->timers_on) { collect_timing(ctx, ws); cudaEventRecord(ws.ev[0], st); }
+  ws.epoch++;
+  if (ws.epoch >= 127) {  // epoch field is 7 bits: recycle
+    OKB_CUDA(cudaMemsetAsync(ws.d_touch, 0, (size_t)ws.dl.frame_stride * c.max_batch * 4, st));
+    ws.epoch = 1;
+  }
+  const size_t in_stride = (size_t)src_pitch * H;
+  // ---- pyramid: layers whose parents are complete can share a launch
+  for (int i = 1; i < ws.n_layers;) {
+    ResizeJobs jobs; jobs.n = 0;
+    int total = 0;
+    auto add = [&](int li) {
+      const LayerGeom& g = ws.geom[li]; const LayerGeom& p = ws.geom[g.parent];
+      ResizeJob& J = jobs.j[jobs.n];
+      if (g.parent == 0) { J.src = d_images; J.src_pitch = src_pitch; J.src_frame_stride = in_stride; }
+      else { J.src = ws.d_img + p.offset; J.src_pitch = p.pitch; J.src_frame_stride = ws.dl.frame_stride; }
+      J.dst = ws.d_img + g.offset; J.dst_pitch = g.pitch; J.dst_frame_stride = ws.dl.frame_stride;
+      J.dw = g.w; J.dh = g.h; J.fast2 = g.fast2;
+      J.xs = g.d_xs; J.xn = g.d_xn; J.ys = g.d_ys; J.yn = g.d_yn; J.xa = g.d_xa; J.ya = g.d_ya;
+      jobs.tiles_x[jobs.n] = (g.w + 31) / 32; jobs.tiles_y[jobs.n] = (g.h + 31) / 32;
+      total += jobs.tiles_x[jobs.n] * jobs.tiles_y[jobs.n];
+      jobs.n++;
+    };
+    // layer i (odd, from i-2 or 0) and layer i+1 (even, from i-1): both parents have index < i
+    add(i);
+    if (i + 1 < ws.n_layers) add(i + 1);
+    if (jobs.n == 1) { jobs.tiles_x[1] = jobs.tiles_y[1] = 0; }
+    k_resize<<<dim3(total, B), 256, 0, st>>>(jobs);
+    ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
+    i += 2;
+  }
+  // ---- scores
+  TileMap tm; tm.n_layers = ws.n_layers; tm.tile_prefix[0] = 0;
+  for (int i = 0; i < ws.n_layers; i++) {
+    tm.tiles_x[i] = (ws.geom[i].w + kTileW - 1) / kTileW;
+    tm.tile_prefix[i + 1] = tm.tile_prefix[i] + tm.tiles_x[i] * ((ws.geom[i].h + kTileH - 1) / kTileH);
+  }
+  for (int i = ws.n_layers + 1; i <= kMaxLayers; i++) tm.tile_prefix[i] = tm.tile_prefix[ws.n_layers];
+  const int n_tiles = tm.tile_prefix[ws.n_layers];
+  k_score<<<dim3(n_tiles, B), 256, 0, st>>>(ws.dl, tm, d_images, src_pitch, in_stride, ws.d_img, ws.d_score, c.threshold);
+  ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
+  if (ctx->timers_on) cudaEventRecord(ws.ev[1], st);
+  // ---- candidates, refinement, tie resolution, selection
+  OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, 4 * B, st));
+  OKB_CUDA(cudaMemsetAsync(ws.d_status, 0, 4 * B, st));
+  k_nms<<<dim3(n_tiles, B), 256, 0, st>>>(ws.dl, tm, ws.d_score, ws.d_cand, ws.d_cand_count, ws.cand_cap);
+  k_refine<<<dim3((ws.cand_cap + 127) / 128, B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
+                                                               ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap,
+                                                               ws.d_rec, c.threshold, ws.epoch);
+  k_resolve<<<B, 256, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score, ws.d_touch, ws.d_cand_count,
+                               ws.cand_cap, ws.d_rec, ws.epoch, ws.d_status);
+  k_finalize<<<B, 1024, kSortCap * 8, st>>>(ws.d_cand_count, ws.cand_cap, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,
+                                            W, H, c.max_keypoints, ws.kp_cap, ws.d_kp, ws.d_kscale, ws.d_count, ws.d_status);
+  ctx->launches += 4;
+  if (ctx->timers_on) cudaEventRecord(ws.ev[2], st);
+  // ---- descriptors
+  const int ipitch = W + 1;
+  k_integral_rows<<<dim3((H + 7) / 8, B), 256, 0, st>>>(d_images, src_pitch, in_stride, W, H, ws.d_integral, ipitch);
+  k_integral_cols<<<dim3((W + 127) / 128, B), 128, 0, st>>>(W, H, ws.d_integral, ipitch);
+  k_describe<<<dim3((ws.kp_cap + 3) / 4, B), 128, 0, st>>>(d_images, src_pitch, in_stride, H, ws.d_integral, ipitch,
+                                                           ctx->d_pattern, ctx->d_short_pairs, ctx->d_long_pairs, ws.d_kp,
+                                                           ws.d_kscale, ws.d_count, ws.kp_cap, ws.d_desc);
+  ctx->launches += 3;
+  if (ctx->timers_on) { cudaEventRecord(ws.ev[3], st); ws.pending_timing = 1; }
+  OKB_CUDA(cudaGetLastError());
+  return OKB_OK;
+}
+
+void detect_collect_timing(okb_context* ctx, int cam) { collect_timing(ctx, ctx->cams[cam]); }
+
+}  // namespace okb

@@ -1,0 +1,125 @@
+// okb_internal.h -- context / workspace definitions shared by the translation units of libokvis_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/okvis_b200.h"
+#include "okb_core.h"
+#include "okb_tables.h"
+
+namespace okb {
+
+void set_error(const char* fmt, ...);
+
+#define OKB_CUDA(call)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      okb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return OKB_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+struct LayerGeom {
+  int w, h, pitch;
+  size_t offset;  // byte offset of this layer inside one frame's layer block
+  float scale, offset_px;
+  int parent;     // layer it is sampled from (-1 for layer 0)
+  int fast2;      // 1 = exact 2x2 mean, 0 = general area tables
+  // device copies of the area tables (general path)
+  int *d_xs = nullptr, *d_xn = nullptr, *d_ys = nullptr, *d_yn = nullptr;
+  float *d_xa = nullptr, *d_ya = nullptr;
+};
+
+struct DeviceLayer {  // POD passed to kernels
+  int w, h, pitch;
+  uint32_t offset;
+  float scale, offset_px;
+};
+struct DeviceLayers {
+  int n;
+  DeviceLayer l[kMaxLayers];
+  uint32_t frame_stride;  // bytes of one frame's layer block
+};
+
+// refined candidate record kept on the device between the refine, resolve and finalize kernels
+struct CandRecord {
+  float x, y, size, response;
+  uint32_t key;       // time key (layer, y, x)
+  int8_t keep, own_touch, has_above, tie;
+  ScanTrace above;    // 8 bytes
+  int8_t state;       // ties: 0 unresolved, 1 = is a maximum, 2 = rejected; non-ties: 1
+  int8_t pad[3];
+};
+
+struct CamWorkspace {
+  okb_camera_config_t cfg;
+  cudaStream_t stream = nullptr;
+  int n_layers = 0;
+  LayerGeom geom[kMaxLayers];
+  DeviceLayers dl;
+  int cand_cap = 0;   // candidate capacity per frame
+  int kp_cap = 0;     // keypoint capacity per frame (output rows)
+  uint32_t epoch = 0;
+  // device buffers ([max_batch] leading dimension)
+  uint8_t* d_in = nullptr;      // input frames (pitch = width) of the host-buffer entry points
+  uint8_t* d_img = nullptr;     // layer images (layers >= 1)
+  uint8_t* d_score = nullptr;   // thresholded score maps
+  uint32_t* d_touch = nullptr;  // touch-time maps
+  int32_t* d_integral = nullptr;  // (w+1) x (h+1) per frame
+  uint32_t* d_cand = nullptr;   // candidate keys
+  int32_t* d_cand_count = nullptr;
+  CandRecord* d_rec = nullptr;
+  okb_keypoint_t* d_kp = nullptr;
+  int32_t* d_kscale = nullptr;
+  uint8_t* d_desc = nullptr;
+  int32_t* d_count = nullptr;
+  int32_t* d_status = nullptr;  // per frame overflow flags
+  // pinned staging
+  uint8_t* h_img = nullptr;
+  okb_keypoint_t* h_kp = nullptr;
+  uint8_t* h_desc = nullptr;
+  int32_t* h_count = nullptr;
+  int32_t* h_status = nullptr;
+  // timers
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double ps_ms = 0, total_ms = 0;
+  int64_t ps_launches = 0;
+  int pending_timing = 0;
+  int64_t ps_bytes = 0;
+};
+
+struct MatchWorkspace {
+  cudaStream_t stream = nullptr;
+  void* d_buf = nullptr; size_t d_cap = 0;
+  void* h_buf = nullptr; size_t h_cap = 0;
+};
+
+}  // namespace okb
+
+struct okb_context {
+  int device = 0;
+  int n_cams = 0;
+  std::vector<okb::CamWorkspace> cams;
+  okb::MatchWorkspace match;
+  // static tables
+  okb::PatternPoint* d_pattern = nullptr;  // [scale][rot][point]
+  uint32_t* d_short_pairs = nullptr;       // packed (i | j << 8)
+  int4* d_long_pairs = nullptr;            // (i, j, wdx, wdy)
+  int n_short = 0, n_long = 0;
+  float* d_scale_bounds = nullptr;         // 63 float boundaries of the keypoint-size -> scale-index map
+  uint32_t* d_size_list = nullptr;         // pattern extent per scale index
+  float pattern_scale = 1.0f;
+  int timers_on = 0;
+  int64_t launches = 0;
+};
+
+namespace okb {
+int detect_init_camera(okb_context* ctx, int cam);
+void detect_free_camera(okb_context* ctx, int cam);
+int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch);
+int tables_init(okb_context* ctx, float pattern_scale);
+void tables_free(okb_context* ctx);
+}  // namespace okb

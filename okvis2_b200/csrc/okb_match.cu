@@ -1,0 +1,664 @@
+// okb_match.cu -- brute-force Hamming matchers with the reference's geometric gates (sm_100a).
+//
+// Replaces the five match loops of okvis::Frontend (reference okvis_frontend/src/Frontend.cpp):
+//   M1 matchToMapByThread :1515-1590      M2 matchToMapByThreadUnitialised :1594-1720
+//   M3 matchMotionStereo worker :1809-1907  M4 matchStereo :2016-2074   M5 verifyRecognisedPlace :329-355
+// and triangulation::triangulateFast (okvis_frontend/src/stereo_triangulation.cpp:50-132).
+//
+// Layout: one warp per query descriptor (held in registers as uint4 words), candidates streamed through shared
+// memory in tiles of 256 (word-plane layout -> conflict-free uint4 reads), distance = __popcll over the XOR.
+// M1/M5 have no gate after the Hamming test, so "first minimum in iteration order" is a lexicographic
+// (distance, position) minimum reduced with warp shuffles. M2-M4 evaluate their gates only when a candidate beats
+// the running best, exactly like the sequential loops: lanes are replayed in candidate order (ballot + ffs), the
+// gate is computed warp-uniformly in fp64 (no FMA contraction: compiled with -fmad=false).
+#include <math.h>
+#include <string.h>
+
+#include "okb_internal.h"
+
+namespace okb {
+
+// ---- fp64 geometry with a fixed association order (left to right), mirrored by the oracle ----------------------
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 v3(const double* p) { return V3{p[0], p[1], p[2]}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator*(double s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double norm(V3 a) { return sqrt(dot(a, a)); }
+__device__ __forceinline__ V3 normalized(V3 a)
+{
+  const double z = dot(a, a);
+  if (z > 0.0) { const double n = sqrt(z); return V3{a.x / n, a.y / n, a.z / n}; }
+  return a;
+}
+
+struct Tri { V3 p; bool valid, parallel; };
+
+// triangulation::triangulateFast; cos26 = cos(2.6 sigma), cos6 = cos(6 sigma) come from the host libm
+__device__ Tri triangulate_fast(V3 p1, V3 e1, V3 p2, V3 e2, double cos26, double cos6)
+{
+  Tri r; r.parallel = false; r.valid = true;
+  const V3 t12 = p2 - p1;
+  const double b0 = dot(t12, e1), b1 = dot(t12, e2);
+  const double A00 = dot(e1, e1), A10 = dot(e1, e2), A01 = -A10, A11 = -dot(e2, e2);
+  const double det = A00 * A11 - A10 * A01;
+  const bool invertible = fabs(det) > 1.0e-12;
+  double l0 = 0, l1 = 0;
+  if (invertible) {
+    const double invdet = 1.0 / det;
+    const double i00 = A11 * invdet, i10 = -A10 * invdet, i01 = -A01 * invdet, i11 = A00 * invdet;
+    l0 = i00 * b0 + i01 * b1;
+    l1 = i10 * b0 + i11 * b1;
+  }
+  if (!invertible || l0 < 0.01 || l1 < 0.01) {
+    r.parallel = true;
+    const V3 m = p1 + 0.5 * t12;
+    const double nt = norm(t12);
+    const V3 mid = m + (40.0 * (0.01 < nt ? nt : 0.01)) * (e1 + e2);
+    r.p = mid;
+    if (dot(e1, normalized(mid - p1)) < cos26) r.valid = false;
+    if (dot(e2, normalized(mid - p2)) < cos26) r.valid = false;
+    return r;
+  }
+  const V3 xm = l0 * e1 + p1;
+  const V3 xn = l1 * e2 + p2;
+  const V3 s = xm + xn;
+  const V3 mid = V3{s.x / 2.0, s.y / 2.0, s.z / 2.0};
+  r.p = mid;
+  if (dot(e1, normalized(mid - p1)) < cos26) r.valid = false;
+  if (dot(e2, normalized(mid - p2)) < cos26) r.valid = false;
+  if (dot(normalized(mid - p2), normalized(mid - p1)) > cos6) r.parallel = true;
+  return r;
+}
+
+// z / w of T_CW * hp with T_CW = [R | t] row-major 3x4 and hp = (p, 1)
+__device__ __forceinline__ double depth_in(const double* T, V3 p)
+{
+  const double z = ((T[8] * p.x + T[9] * p.y) + T[10] * p.z) + T[11] * 1.0;
+  return z / 1.0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+enum { MODE_M2 = 2, MODE_M3 = 3, MODE_M4 = 4 };
+
+struct MatchArgs {
+  int nq, nc;
+  const uint8_t* q_desc; const uint8_t* c_desc;
+  const uint8_t* q_use;
+  // M1
+  const double* q_xy; const okb_keypoint_t* q_kp; const int32_t* q_count; const int32_t* c_lm; const double* lm_proj; const uint8_t* lm_is3d; double thr_sq;
+  // M2
+  const double* q_e; const int32_t* q_prev_lm; const double* c_e; const double* c_r;
+  double r0[3], r1[3]; double cos26, cos6;
+  // M3 / M4
+  const double* q_sof; const double* q_cos26; const double* q_cos6;
+  const uint8_t* c_valid; const double* c_sof; const double* c_cos26; const double* c_cos6;
+  double T0[12], T1[12];
+  uint32_t thr;
+  uint32_t* out_dist; int32_t* out_idx; double* out_hp; uint8_t* out_init; int32_t* out_ctr;
+};
+
+constexpr int kTile = 256;
+
+template <int D16>
+__device__ __forceinline__ void load_query(const uint8_t* desc, int q, uint4 (&qd)[D16])
+{
+  const uint4* p = reinterpret_cast<const uint4*>(desc) + (size_t)q * D16;
+#pragma unroll
+  for (int i = 0; i < D16; i++) qd[i] = __ldg(p + i);
+}
+template <int D16>
+__device__ __forceinline__ void stage_tile(const uint8_t* c_desc, int nc, int tile0, uint4 (*s_desc)[kTile])
+{
+  const uint4* g = reinterpret_cast<const uint4*>(c_desc);
+  for (int i = threadIdx.x; i < kTile * D16; i += blockDim.x) {
+    const int c = tile0 + i / D16, w = i % D16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c < nc) v = __ldg(g + (size_t)c * D16 + w);
+    s_desc[w][i / D16] = v;
+  }
+}
+template <int D16>
+__device__ __forceinline__ uint32_t hamming(const uint4 (&qd)[D16], uint4 (*s_desc)[kTile], int ci)
+{
+  uint32_t d = 0;
+#pragma unroll
+  for (int w = 0; w < D16; w++) {
+    const uint4 c = s_desc[w][ci];
+    d += __popcll(((unsigned long long)(qd[w].x ^ c.x) << 32) | (qd[w].y ^ c.y));
+    d += __popcll(((unsigned long long)(qd[w].z ^ c.z) << 32) | (qd[w].w ^ c.w));
+  }
+  return d;
+}
+
+// M1: reprojection pre-gate (fp64) then lexicographic (distance, candidate) minimum
+template <int D16>
+__global__ void __launch_bounds__(256) k_match_map3d(MatchArgs a)
+{
+  __shared__ uint4 s_desc[D16][kTile];
+  __shared__ double2 s_proj[kTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + warp;
+  const int nq = a.q_count ? min(*a.q_count, a.nq) : a.nq;
+  const bool active = q < nq && (a.q_use == nullptr || a.q_use[q]);
+  uint4 qd[D16];
+  double kx = 0, ky = 0;
+  if (active) {
+    load_query<D16>(a.q_desc, q, qd);
+    if (a.q_kp) { kx = (double)a.q_kp[q].x; ky = (double)a.q_kp[q].y; }  // MultiFrame::getKeypoint: float -> double
+    else { kx = a.q_xy[2 * q]; ky = a.q_xy[2 * q + 1]; }
+  }
+  unsigned long long best = ((unsigned long long)a.thr << 32);
+  for (int tile0 = 0; tile0 < a.nc; tile0 += kTile) {
+    __syncthreads();
+    stage_tile<D16>(a.c_desc, a.nc, tile0, s_desc);
+    {
+      const int c = tile0 + threadIdx.x;
+      double2 p = make_double2(INFINITY, INFINITY);
+      if (c < a.nc) { const int lm = a.c_lm[c]; if (a.lm_is3d[lm]) p = make_double2(a.lm_proj[2 * lm], a.lm_proj[2 * lm + 1]); }
+      s_proj[threadIdx.x] = p;
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll 2
+      for (int j = 0; j < kTile / 32; j++) {
+        const int ci = j * 32 + lane;
+        const double2 p = s_proj[ci];
+        const double dx = p.x - kx, dy = p.y - ky;
+        const double d2 = dx * dx + dy * dy;
+        if (!(d2 > a.thr_sq)) {
+          const uint32_t d = hamming<D16>(qd, s_desc, ci);
+          const unsigned long long key = ((unsigned long long)d << 32) | (unsigned)(tile0 + ci);
+          if (key < best) best = key;
+        }
+      }
+    }
+  }
+  if (q >= a.nq) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); if (t < best) best = t; }
+  if (lane == 0) {
+    const uint32_t d = (uint32_t)(best >> 32);
+    if (active && d < a.thr) { a.out_dist[q] = d; a.out_idx[q] = a.c_lm[(uint32_t)best]; }
+    else { a.out_dist[q] = a.thr; a.out_idx[q] = -1; }
+  }
+}
+
+// M5: per landmark (group of descriptors) the best keypoint over (descriptor, k) order
+template <int D16>
+__global__ void __launch_bounds__(256) k_match_place(int n_lm, const int32_t* lm_offsets, const uint8_t* lm_desc, int n_kp,
+                                                     const uint8_t* kp_desc, uint32_t thr, int32_t* out_k, uint32_t* out_dist)
+{
+  __shared__ uint4 s_desc[D16][kTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + warp;
+  const bool active = q < n_lm;
+  const int d_beg = active ? lm_offsets[q] : 0, d_end = active ? lm_offsets[q + 1] : 0;
+  int max_nd = d_end - d_beg;
+  // all warps of the CTA must run the same number of descriptor rounds (tiles are staged cooperatively)
+  __shared__ int s_max;
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  if (lane == 0) atomicMax(&s_max, max_nd);
+  __syncthreads();
+  max_nd = s_max;
+  unsigned long long best = ((unsigned long long)thr << 32);
+  for (int tile0 = 0; tile0 < n_kp; tile0 += kTile) {
+    __syncthreads();
+    stage_tile<D16>(kp_desc, n_kp, tile0, s_desc);
+    __syncthreads();
+    for (int dd = 0; dd < max_nd; dd++) {
+      if (d_beg + dd < d_end) {
+        uint4 qd[D16];
+        load_query<D16>(lm_desc, d_beg + dd, qd);
+        for (int j = 0; j < kTile / 32; j++) {
+          const int ci = j * 32 + lane, k = tile0 + ci;
+          if (k < n_kp) {
+            const uint32_t d = hamming<D16>(qd, s_desc, ci);
+            // order position: descriptor-major, then k (fits: dd < 2^12, k < 2^20)
+            const unsigned long long key = ((unsigned long long)d << 32) | ((unsigned)dd << 20) | (unsigned)k;
+            if (key < best) best = key;
+          }
+        }
+      }
+    }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); if (t < best) best = t; }
+  if (lane == 0) {
+    const uint32_t d = (uint32_t)(best >> 32);
+    if (d < thr) { out_dist[q] = d; out_k[q] = (int)(best & 0xfffffu); } else { out_dist[q] = thr; out_k[q] = -1; }
+  }
+}
+
+// M2 / M3 / M4: sequential-order replay with gates
+template <int D16, int MODE>
+__global__ void __launch_bounds__(256) k_match_gated(MatchArgs a)
+{
+  __shared__ uint4 s_desc[D16][kTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + warp;
+  const bool active = q < a.nq && (a.q_use == nullptr || a.q_use[q]);
+  uint4 qd[D16];
+  V3 eq = V3{0, 0, 0};
+  double q_c26 = 0, q_c6 = 0, q_sof = 0;
+  int prev_lm = -1;
+  if (active) {
+    load_query<D16>(a.q_desc, q, qd);
+    eq = v3(a.q_e + 3 * (size_t)q);
+    if (MODE == MODE_M2) { q_c26 = a.cos26; q_c6 = a.cos6; if (a.q_prev_lm) prev_lm = a.q_prev_lm[q]; }
+    else { q_c26 = a.q_cos26[q]; q_c6 = a.q_cos6[q]; q_sof = a.q_sof[q]; }
+  }
+  uint32_t best = a.thr;
+  int best_idx = -1;
+  V3 best_hp = V3{0, 0, 0}; bool have_hp = false; bool best_init = false;
+  int ctr = 0, skip_lm = -1;
+  const V3 r0 = v3(a.r0), r1 = v3(a.r1);
+  for (int tile0 = 0; tile0 < a.nc; tile0 += kTile) {
+    __syncthreads();
+    stage_tile<D16>(a.c_desc, a.nc, tile0, s_desc);
+    __syncthreads();
+    if (!active) continue;
+    for (int j = 0; j < kTile / 32; j++) {
+      const int ci = j * 32 + lane, c = tile0 + ci;
+      if (tile0 + j * 32 >= a.nc) break;
+      uint32_t d = 0xffffu;
+      int lm = -1;
+      if (c < a.nc) {
+        bool ok = true;
+        if (MODE == MODE_M2) { lm = a.c_lm[c]; ok = !a.lm_is3d[lm]; }
+        if (ok) d = hamming<D16>(qd, s_desc, ci);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, d < best);
+      while (m) {
+        const int jl = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t dj = __shfl_sync(0xffffffffu, d, jl);
+        const int cj = tile0 + j * 32 + jl;
+        if (!(dj < best)) continue;
+        int lmj = -1;
+        bool pass = true, parallel = false;
+        V3 hp = V3{0, 0, 0};
+        if (MODE == MODE_M2) {
+          lmj = __shfl_sync(0xffffffffu, lm, jl);
+          if (lmj == skip_lm) continue;
+          const V3 e0 = v3(a.c_e + 3 * (size_t)cj), rr0 = v3(a.c_r + 3 * (size_t)cj);
+          if (dot(e0, eq) < q_c6) {
+            const V3 et = normalized(r1 - rr0);
+            const V3 n0 = normalized(cross(e0, et));
+            const V3 n1 = normalized(cross(eq, et));
+            if (dot(n0, n1) < q_c6) pass = false;
+            else if (dot(cross(e0, eq), normalized(n0 + n0)) > 0.0) pass = false;
+          }
+          if (pass) {
+            const Tri t = triangulate_fast(rr0, e0, r1, eq, q_c26, q_c6);
+            pass = t.valid; parallel = t.parallel; hp = t.p;
+            if (pass && !parallel) {
+              if (norm(hp - rr0) < 0.2) pass = false;
+              if (norm(hp - r1) < 0.2) pass = false;
+            }
+          }
+          if (pass && lmj == prev_lm && prev_lm >= 0) { ctr++; skip_lm = lmj; continue; }
+        } else {
+          if (!a.c_valid[cj]) continue;
+          const V3 e1 = v3(a.c_e + 3 * (size_t)cj);
+          double c26 = q_c26, c6 = q_c6;
+          if (MODE == MODE_M4) { const double s1 = a.c_sof[cj]; if (q_sof < s1) { c26 = a.c_cos26[cj]; c6 = a.c_cos6[cj]; } }
+          if (MODE == MODE_M3) { if (dot(eq, e1) < 0.5) continue; }
+          const Tri t = triangulate_fast(r0, eq, r1, e1, c26, c6);
+          pass = t.valid; parallel = t.parallel; hp = t.p;
+          if (MODE == MODE_M3) {
+            if (!pass) continue;
+            if (dot(eq, e1) < 0.8) pass = false;
+            if (!parallel) {
+              if (depth_in(a.T0, hp) < 0.2) pass = false;
+              if (depth_in(a.T1, hp) < 0.2) pass = false;
+            }
+          } else {
+            if (!parallel) {
+              if (depth_in(a.T0, hp) < 0.05) pass = false;
+              if (depth_in(a.T1, hp) < 0.05) pass = false;
+              if (dot(eq, e1) < 0.8) pass = false;
+            }
+          }
+        }
+        if (!pass) continue;
+        best = dj; best_idx = (MODE == MODE_M2) ? lmj : cj;
+        if (MODE == MODE_M2) { if (!parallel) { best_hp = hp; have_hp = true; } }
+        else { best_hp = hp; have_hp = true; best_init = !parallel; }
+        m &= __ballot_sync(0xffffffffu, d < best);
+      }
+    }
+  }
+  if (q >= a.nq) return;
+  if (lane == 0) {
+    a.out_dist[q] = best; a.out_idx[q] = best_idx;
+    double* hp = a.out_hp + 4 * (size_t)q;
+    if (have_hp) { hp[0] = best_hp.x; hp[1] = best_hp.y; hp[2] = best_hp.z; hp[3] = 1.0; }
+    else { hp[0] = hp[1] = hp[2] = hp[3] = 0.0; }
+    if (a.out_init) a.out_init[q] = best_init ? 1 : 0;
+    if (MODE == MODE_M2 && a.out_ctr && ctr) atomicAdd(a.out_ctr, ctr);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_hamming_matrix(int D16, int na, const uint8_t* A, int nb, const uint8_t* B, uint16_t* out)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= nb || i >= na) return;
+  const uint4* a = reinterpret_cast<const uint4*>(A) + (size_t)i * D16;
+  const uint4* b = reinterpret_cast<const uint4*>(B) + (size_t)j * D16;
+  uint32_t d = 0;
+  for (int w = 0; w < D16; w++) {
+    const uint4 x = __ldg(a + w), y = __ldg(b + w);
+    d += __popcll(((unsigned long long)(x.x ^ y.x) << 32) | (x.y ^ y.y)) + __popcll(((unsigned long long)(x.z ^ y.z) << 32) | (x.w ^ y.w));
+  }
+  out[(size_t)i * nb + j] = (uint16_t)d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: staging arena
+struct Arena {
+  okb_context* ctx; size_t off = 0; bool dry = true;
+  uint8_t* h = nullptr; uint8_t* d = nullptr;
+  template <class T> const T* in(const T* src, size_t n)
+  {
+    off = (off + 255) & ~(size_t)255;
+    const size_t o = off; off += n * sizeof(T);
+    if (dry || !src) return nullptr;
+    memcpy(h + o, src, n * sizeof(T));
+    return reinterpret_cast<const T*>(d + o);
+  }
+  template <class T> T* out(size_t n, size_t* host_off)
+  {
+    off = (off + 255) & ~(size_t)255;
+    const size_t o = off; off += n * sizeof(T);
+    if (host_off) *host_off = o;
+    return dry ? nullptr : reinterpret_cast<T*>(d + o);
+  }
+};
+
+static int ensure(okb_context* ctx, size_t bytes)
+{
+  MatchWorkspace& m = ctx->match;
+  if (bytes <= m.d_cap) return OKB_OK;
+  OKB_CUDA(cudaStreamSynchronize(m.stream));
+  if (m.d_buf) cudaFree(m.d_buf);
+  if (m.h_buf) cudaFreeHost(m.h_buf);
+  m.d_buf = m.h_buf = nullptr; m.d_cap = m.h_cap = 0;
+  const size_t cap = bytes + bytes / 2 + (1 << 20);
+  OKB_CUDA(cudaMalloc(&m.d_buf, cap));
+  OKB_CUDA(cudaMallocHost(&m.h_buf, cap));
+  m.d_cap = m.h_cap = cap;
+  return OKB_OK;
+}
+
+int match_init(okb_context* ctx)
+{
+  OKB_CUDA(cudaStreamCreateWithFlags(&ctx->match.stream, cudaStreamNonBlocking));
+  return ensure(ctx, 8 << 20);
+}
+void match_free(okb_context* ctx)
+{
+  if (ctx->match.d_buf) cudaFree(ctx->match.d_buf);
+  if (ctx->match.h_buf) cudaFreeHost(ctx->match.h_buf);
+  if (ctx->match.stream) cudaStreamDestroy(ctx->match.stream);
+}
+
+static bool bad_D(int D) { return D != 48 && D != 64; }
+
+}  // namespace okb
+
+using namespace okb;
+
+#define OKB_CHECK_ARGS(cond, who)                                  \
+  if (!(cond)) { set_error("%s: bad arguments", who); return OKB_ERR_ARGUMENT; }
+
+// Runs `body(arena)` twice: a dry pass that sizes the arena and a real pass that fills the pinned buffer.
+#define OKB_TWO_PASS(ctx, A, BODY)                                                        \
+  Arena A; A.ctx = ctx;                                                                   \
+  { A.dry = true; A.off = 0; BODY; }                                                      \
+  const size_t in_bytes__ = A.off; (void)in_bytes__;
+
+extern "C" {
+
+int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc, const double* kp_xy, const uint8_t* kp_use,
+                    int n_cand, const uint8_t* cand_desc, const int32_t* cand_lm, int n_lm, const double* lm_proj,
+                    const uint8_t* lm_is3d, double reprojection_threshold, uint32_t match_threshold, uint32_t* out_dist,
+                    int32_t* out_lm)
+{
+  OKB_CHECK_ARGS(ctx && !bad_D(D) && n_kp >= 0 && n_cand >= 0 && n_lm >= 0 && out_dist && out_lm, "okb_match_map3d");
+  OKB_CHECK_ARGS(n_kp == 0 || (kp_desc && kp_xy), "okb_match_map3d");
+  OKB_CHECK_ARGS(n_cand == 0 || (cand_desc && cand_lm && lm_proj && lm_is3d), "okb_match_map3d");
+  if (n_kp == 0) return OKB_OK;
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->match.stream;
+  MatchArgs a; memset(&a, 0, sizeof(a));
+  size_t o_dist = 0, o_idx = 0, in_end = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
+    a.q_desc = A.in(kp_desc, (size_t)n_kp * D); a.q_xy = A.in(kp_xy, (size_t)n_kp * 2);
+    a.q_use = kp_use ? A.in(kp_use, (size_t)n_kp) : nullptr;
+    a.c_desc = A.in(cand_desc, (size_t)n_cand * D); a.c_lm = A.in(cand_lm, (size_t)n_cand);
+    a.lm_proj = A.in(lm_proj, (size_t)n_lm * 2); a.lm_is3d = A.in(lm_is3d, (size_t)n_lm);
+    in_end = A.off;
+    a.out_dist = A.out<uint32_t>(n_kp, &o_dist); a.out_idx = A.out<int32_t>(n_kp, &o_idx);
+    if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
+  }
+  a.nq = n_kp; a.nc = n_cand; a.thr = match_threshold; a.thr_sq = reprojection_threshold * reprojection_threshold;
+  OKB_CUDA(cudaMemcpyAsync(ctx->match.d_buf, ctx->match.h_buf, in_end, cudaMemcpyHostToDevice, st));
+  const int grid = (n_kp + 7) / 8;
+  if (D == 64) k_match_map3d<4><<<grid, 256, 0, st>>>(a); else k_match_map3d<3><<<grid, 256, 0, st>>>(a);
+  ctx->launches++;
+  OKB_CUDA(cudaGetLastError());
+  uint8_t* h = (uint8_t*)ctx->match.h_buf; uint8_t* d = (uint8_t*)ctx->match.d_buf;
+  OKB_CUDA(cudaMemcpyAsync(h + o_dist, d + o_dist, (o_idx - o_dist) + (size_t)n_kp * 4, cudaMemcpyDeviceToHost, st));
+  OKB_CUDA(cudaStreamSynchronize(st));
+  memcpy(out_dist, h + o_dist, (size_t)n_kp * 4); memcpy(out_lm, h + o_idx, (size_t)n_kp * 4);
+  return OKB_OK;
+}
+
+static int run_gated(okb_context_t* ctx, int mode, int D, MatchArgs& a, size_t in_end, size_t o_dist, size_t o_end,
+                     size_t o_idx, size_t o_hp, size_t o_init, size_t o_ctr, uint32_t* out_dist, int32_t* out_idx,
+                     double* out_hp, uint8_t* out_init, int32_t* out_ctr)
+{
+  cudaStream_t st = ctx->match.stream;
+  uint8_t* h = (uint8_t*)ctx->match.h_buf; uint8_t* d = (uint8_t*)ctx->match.d_buf;
+  OKB_CUDA(cudaMemcpyAsync(d, h, in_end, cudaMemcpyHostToDevice, st));
+  if (a.out_ctr) OKB_CUDA(cudaMemsetAsync(a.out_ctr, 0, 4, st));
+  const int grid = (a.nq + 7) / 8;
+  if (D == 64) {
+    if (mode == MODE_M2) k_match_gated<4, MODE_M2><<<grid, 256, 0, st>>>(a);
+    else if (mode == MODE_M3) k_match_gated<4, MODE_M3><<<grid, 256, 0, st>>>(a);
+    else k_match_gated<4, MODE_M4><<<grid, 256, 0, st>>>(a);
+  } else {
+    if (mode == MODE_M2) k_match_gated<3, MODE_M2><<<grid, 256, 0, st>>>(a);
+    else if (mode == MODE_M3) k_match_gated<3, MODE_M3><<<grid, 256, 0, st>>>(a);
+    else k_match_gated<3, MODE_M4><<<grid, 256, 0, st>>>(a);
+  }
+  ctx->launches++;
+  OKB_CUDA(cudaGetLastError());
+  OKB_CUDA(cudaMemcpyAsync(h + o_dist, d + o_dist, o_end - o_dist, cudaMemcpyDeviceToHost, st));
+  OKB_CUDA(cudaStreamSynchronize(st));
+  const size_t n = (size_t)a.nq;
+  memcpy(out_dist, h + o_dist, n * 4); memcpy(out_idx, h + o_idx, n * 4);
+  if (out_hp) memcpy(out_hp, h + o_hp, n * 32);
+  if (out_init) memcpy(out_init, h + o_init, n);
+  if (out_ctr) memcpy(out_ctr, h + o_ctr, 4);
+  return OKB_OK;
+}
+
+int okb_match_map_uninit(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc, const double* kp_e_W,
+                         const uint8_t* kp_use, const int32_t* kp_prev_lm, int n_cand, const uint8_t* cand_desc,
+                         const int32_t* cand_lm, const double* cand_e_W, const double* cand_r_W, int n_lm,
+                         const uint8_t* lm_is3d, const double r_WC1[3], double sigma, uint32_t match_threshold,
+                         uint32_t* out_dist, int32_t* out_lm, double* out_hp_W, int32_t* out_ctr)
+{
+  OKB_CHECK_ARGS(ctx && !bad_D(D) && n_kp >= 0 && n_cand >= 0 && out_dist && out_lm && out_hp_W && r_WC1, "okb_match_map_uninit");
+  OKB_CHECK_ARGS(n_kp == 0 || (kp_desc && kp_e_W), "okb_match_map_uninit");
+  OKB_CHECK_ARGS(n_cand == 0 || (cand_desc && cand_lm && cand_e_W && cand_r_W && lm_is3d), "okb_match_map_uninit");
+  if (out_ctr) *out_ctr = 0;
+  if (n_kp == 0) return OKB_OK;
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  MatchArgs a; memset(&a, 0, sizeof(a));
+  size_t o_dist = 0, o_idx = 0, o_hp = 0, o_ctr = 0, in_end = 0, o_end = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
+    a.q_desc = A.in(kp_desc, (size_t)n_kp * D); a.q_e = A.in(kp_e_W, (size_t)n_kp * 3);
+    a.q_use = kp_use ? A.in(kp_use, (size_t)n_kp) : nullptr;
+    a.q_prev_lm = kp_prev_lm ? A.in(kp_prev_lm, (size_t)n_kp) : nullptr;
+    a.c_desc = A.in(cand_desc, (size_t)n_cand * D); a.c_lm = A.in(cand_lm, (size_t)n_cand);
+    a.c_e = A.in(cand_e_W, (size_t)n_cand * 3); a.c_r = A.in(cand_r_W, (size_t)n_cand * 3);
+    a.lm_is3d = A.in(lm_is3d, (size_t)n_lm);
+    in_end = A.off;
+    a.out_dist = A.out<uint32_t>(n_kp, &o_dist); a.out_idx = A.out<int32_t>(n_kp, &o_idx);
+    a.out_hp = A.out<double>((size_t)n_kp * 4, &o_hp); a.out_ctr = A.out<int32_t>(1, &o_ctr);
+    o_end = A.off;
+    if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
+  }
+  a.nq = n_kp; a.nc = n_cand; a.thr = match_threshold;
+  for (int i = 0; i < 3; i++) a.r1[i] = r_WC1[i];
+  a.cos26 = cos(2.6 * sigma); a.cos6 = cos(6.0 * sigma);  // host libm, as in the reference
+  return run_gated(ctx, MODE_M2, D, a, in_end, o_dist, o_end, o_idx, o_hp, 0, o_ctr, out_dist, out_lm, out_hp_W, nullptr, out_ctr);
+}
+
+static int stereo_like(okb_context_t* ctx, int mode, int D, int n0, const uint8_t* desc0, const uint8_t* use0,
+                       const double* e0_W, const double* sof0, int n1, const uint8_t* desc1, const uint8_t* valid1,
+                       const double* e1_W, const double* sof1, const double r_WC0[3], const double r_WC1[3],
+                       const double T_CW0[12], const double T_CW1[12], uint32_t thr, int32_t* out_k1, uint32_t* out_dist,
+                       double* out_hp_W, uint8_t* out_init, const char* who)
+{
+  OKB_CHECK_ARGS(ctx && !bad_D(D) && n0 >= 0 && n1 >= 0 && out_k1 && out_dist && out_hp_W && out_init && r_WC0 && r_WC1 && T_CW0 && T_CW1, who);
+  OKB_CHECK_ARGS(n0 == 0 || (desc0 && e0_W && sof0), who);
+  OKB_CHECK_ARGS(n1 == 0 || (desc1 && e1_W && valid1 && (mode == MODE_M3 || sof1)), who);
+  if (n0 == 0) return OKB_OK;
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  // per-keypoint cos(2.6 sigma), cos(6 sigma) tables with the host libm (sigma = size/f * 0.125)
+  std::vector<double> c26_0(n0), c6_0(n0), c26_1, c6_1;
+  for (int i = 0; i < n0; i++) { const double s = sof0[i] * 0.125; c26_0[i] = cos(2.6 * s); c6_0[i] = cos(6.0 * s); }
+  if (mode == MODE_M4) {
+    c26_1.resize(n1); c6_1.resize(n1);
+    for (int i = 0; i < n1; i++) { const double s = sof1[i] * 0.125; c26_1[i] = cos(2.6 * s); c6_1[i] = cos(6.0 * s); }
+  }
+  MatchArgs a; memset(&a, 0, sizeof(a));
+  size_t o_dist = 0, o_idx = 0, o_hp = 0, o_init = 0, in_end = 0, o_end = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
+    a.q_desc = A.in(desc0, (size_t)n0 * D); a.q_e = A.in(e0_W, (size_t)n0 * 3);
+    a.q_use = use0 ? A.in(use0, (size_t)n0) : nullptr;
+    a.q_sof = A.in(sof0, (size_t)n0); a.q_cos26 = A.in(c26_0.data(), (size_t)n0); a.q_cos6 = A.in(c6_0.data(), (size_t)n0);
+    a.c_desc = A.in(desc1, (size_t)n1 * D); a.c_e = A.in(e1_W, (size_t)n1 * 3); a.c_valid = A.in(valid1, (size_t)n1);
+    if (mode == MODE_M4) { a.c_sof = A.in(sof1, (size_t)n1); a.c_cos26 = A.in(c26_1.data(), (size_t)n1); a.c_cos6 = A.in(c6_1.data(), (size_t)n1); }
+    in_end = A.off;
+    a.out_dist = A.out<uint32_t>(n0, &o_dist); a.out_idx = A.out<int32_t>(n0, &o_idx);
+    a.out_hp = A.out<double>((size_t)n0 * 4, &o_hp); a.out_init = A.out<uint8_t>(n0, &o_init);
+    o_end = A.off;
+    if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
+  }
+  a.nq = n0; a.nc = n1; a.thr = thr;
+  for (int i = 0; i < 3; i++) { a.r0[i] = r_WC0[i]; a.r1[i] = r_WC1[i]; }
+  for (int i = 0; i < 12; i++) { a.T0[i] = T_CW0[i]; a.T1[i] = T_CW1[i]; }
+  return run_gated(ctx, mode, D, a, in_end, o_dist, o_end, o_idx, o_hp, o_init, 0, out_dist, out_k1, out_hp_W, out_init, nullptr);
+}
+
+int okb_match_motion_stereo(okb_context_t* ctx, int D, int n0, const uint8_t* desc0, const uint8_t* use0, const double* e0_W,
+                            const double* size_over_f0, int n1, const uint8_t* desc1, const uint8_t* valid1,
+                            const double* e1_W, const double r_WC0[3], const double r_WC1[3], const double T_CW0[12],
+                            const double T_CW1[12], uint32_t match_threshold, int32_t* out_k1, uint32_t* out_dist,
+                            double* out_hp_W, uint8_t* out_initialisable)
+{
+  return stereo_like(ctx, MODE_M3, D, n0, desc0, use0, e0_W, size_over_f0, n1, desc1, valid1, e1_W, nullptr, r_WC0, r_WC1,
+                     T_CW0, T_CW1, match_threshold, out_k1, out_dist, out_hp_W, out_initialisable, "okb_match_motion_stereo");
+}
+
+int okb_match_stereo(okb_context_t* ctx, int D, int n0, const uint8_t* desc0, const uint8_t* valid0, const double* e0_W,
+                     const double* size_over_f0, int n1, const uint8_t* desc1, const uint8_t* valid1, const double* e1_W,
+                     const double* size_over_f1, const double r_WC0[3], const double r_WC1[3], const double T_CW0[12],
+                     const double T_CW1[12], uint32_t match_threshold, int32_t* out_k1, uint32_t* out_dist, double* out_hp_W,
+                     uint8_t* out_initialisable)
+{
+  return stereo_like(ctx, MODE_M4, D, n0, desc0, valid0, e0_W, size_over_f0, n1, desc1, valid1, e1_W, size_over_f1, r_WC0,
+                     r_WC1, T_CW0, T_CW1, match_threshold, out_k1, out_dist, out_hp_W, out_initialisable, "okb_match_stereo");
+}
+
+int okb_match_map3d_device(okb_context_t* ctx, int cam, int frame, int n_cand, const uint8_t* d_cand_desc,
+                           const int32_t* d_cand_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
+                           double reprojection_threshold, uint32_t match_threshold, uint32_t* d_out_dist, int32_t* d_out_lm)
+{
+  OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams && n_cand >= 0 && d_out_dist && d_out_lm, "okb_match_map3d_device");
+  CamWorkspace& ws = ctx->cams[cam];
+  OKB_CHECK_ARGS(frame >= 0 && frame < ws.cfg.max_batch, "okb_match_map3d_device");
+  OKB_CHECK_ARGS(n_cand == 0 || (d_cand_desc && d_cand_lm && d_lm_proj && d_lm_is3d), "okb_match_map3d_device");
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  MatchArgs a; memset(&a, 0, sizeof(a));
+  a.nq = ws.kp_cap; a.q_count = ws.d_count + frame;
+  a.q_desc = ws.d_desc + (size_t)frame * ws.kp_cap * 64; a.q_kp = ws.d_kp + (size_t)frame * ws.kp_cap;
+  a.nc = n_cand; a.c_desc = d_cand_desc; a.c_lm = d_cand_lm; a.lm_proj = d_lm_proj; a.lm_is3d = d_lm_is3d;
+  a.thr = match_threshold; a.thr_sq = reprojection_threshold * reprojection_threshold;
+  a.out_dist = d_out_dist; a.out_idx = d_out_lm;
+  k_match_map3d<4><<<(ws.kp_cap + 7) / 8, 256, 0, ws.stream>>>(a);
+  ctx->launches++;
+  OKB_CUDA(cudaGetLastError());
+  return OKB_OK;
+}
+
+int okb_match_place(okb_context_t* ctx, int D, int n_lm, const int32_t* lm_offsets, const uint8_t* lm_desc, int n_kp,
+                    const uint8_t* kp_desc, uint32_t match_threshold, int32_t* out_k, uint32_t* out_dist)
+{
+  OKB_CHECK_ARGS(ctx && !bad_D(D) && n_lm >= 0 && n_kp >= 0 && n_kp < (1 << 20) && out_k && out_dist, "okb_match_place");
+  OKB_CHECK_ARGS(n_lm == 0 || (lm_offsets && lm_desc), "okb_match_place");
+  if (n_lm == 0) return OKB_OK;
+  const int n_desc = lm_offsets[n_lm];
+  for (int i = 0; i < n_lm; i++) OKB_CHECK_ARGS(lm_offsets[i + 1] >= lm_offsets[i] && lm_offsets[i + 1] - lm_offsets[i] < 4096, "okb_match_place");
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->match.stream;
+  const int32_t* d_off = nullptr; const uint8_t *d_ld = nullptr, *d_kd = nullptr; int32_t* d_ok = nullptr; uint32_t* d_od = nullptr;
+  size_t o_k = 0, o_d = 0, in_end = 0, o_end = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
+    d_off = A.in(lm_offsets, (size_t)n_lm + 1); d_ld = A.in(lm_desc, (size_t)n_desc * D); d_kd = A.in(kp_desc, (size_t)n_kp * D);
+    in_end = A.off;
+    d_ok = A.out<int32_t>(n_lm, &o_k); d_od = A.out<uint32_t>(n_lm, &o_d); o_end = A.off;
+    if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
+  }
+  uint8_t* h = (uint8_t*)ctx->match.h_buf; uint8_t* d = (uint8_t*)ctx->match.d_buf;
+  OKB_CUDA(cudaMemcpyAsync(d, h, in_end, cudaMemcpyHostToDevice, st));
+  const int grid = (n_lm + 7) / 8;
+  if (D == 64) k_match_place<4><<<grid, 256, 0, st>>>(n_lm, d_off, d_ld, n_kp, d_kd, match_threshold, d_ok, d_od);
+  else k_match_place<3><<<grid, 256, 0, st>>>(n_lm, d_off, d_ld, n_kp, d_kd, match_threshold, d_ok, d_od);
+  ctx->launches++;
+  OKB_CUDA(cudaGetLastError());
+  OKB_CUDA(cudaMemcpyAsync(h + o_k, d + o_k, o_end - o_k, cudaMemcpyDeviceToHost, st));
+  OKB_CUDA(cudaStreamSynchronize(st));
+  memcpy(out_k, h + o_k, (size_t)n_lm * 4); memcpy(out_dist, h + o_d, (size_t)n_lm * 4);
+  return OKB_OK;
+}
+
+int okb_hamming_matrix(okb_context_t* ctx, int D, int n_a, const uint8_t* a, int n_b, const uint8_t* b, uint16_t* out_dist)
+{
+  OKB_CHECK_ARGS(ctx && !bad_D(D) && n_a >= 0 && n_b >= 0 && out_dist, "okb_hamming_matrix");
+  if (n_a == 0 || n_b == 0) return OKB_OK;
+  OKB_CHECK_ARGS(a && b, "okb_hamming_matrix");
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->match.stream;
+  const uint8_t *da = nullptr, *db = nullptr; uint16_t* dout = nullptr; size_t o_out = 0, in_end = 0, o_end = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
+    da = A.in(a, (size_t)n_a * D); db = A.in(b, (size_t)n_b * D); in_end = A.off;
+    dout = A.out<uint16_t>((size_t)n_a * n_b, &o_out); o_end = A.off;
+    if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
+  }
+  uint8_t* h = (uint8_t*)ctx->match.h_buf; uint8_t* d = (uint8_t*)ctx->match.d_buf;
+  OKB_CUDA(cudaMemcpyAsync(d, h, in_end, cudaMemcpyHostToDevice, st));
+  k_hamming_matrix<<<dim3((n_b + 255) / 256, n_a), 256, 0, st>>>(D / 16, n_a, da, n_b, db, dout);
+  ctx->launches++;
+  OKB_CUDA(cudaGetLastError());
+  OKB_CUDA(cudaMemcpyAsync(h + o_out, d + o_out, o_end - o_out, cudaMemcpyDeviceToHost, st));
+  OKB_CUDA(cudaStreamSynchronize(st));
+  memcpy(out_dist, h + o_out, (size_t)n_a * n_b * 2);
+  return OKB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference's front-end interface for the detect -> describe -> match path.
+
+Same names, argument meaning and error behaviour as okvis::Frame / okvis::MultiFrame
+(reference okvis_cv/include/okvis/Frame.hpp:247-265, MultiFrame.hpp:53-332) and okvis::Frontend
+(reference okvis_frontend/include/okvis/Frontend.hpp:87-115,201-238; src/Frontend.cpp:221-269, 1515-2074).
+All arithmetic of the path runs inside libokvis_b200.so (CUDA, sm_100a) through the C ABI; nothing here computes
+features or distances on the host.
+"""
+import threading
+
+import numpy as np
+
+from . import lib as _l
+from .lib import KP_DTYPE, CameraConfig, OkbError, check, ptr
+
+import ctypes as C
+
+
+class Frame:
+    """okvis::Frame: image + keypoints + contiguous N x D descriptor matrix + landmark ids."""
+
+    def __init__(self):
+        self.image = None
+        self.keypoints = np.zeros(0, KP_DTYPE)          # std::vector<cv::KeyPoint>
+        self.descriptors = np.zeros((0, 64), np.uint8)  # cv::Mat N x D CV_8UC1, continuous
+        self.landmarkIds = np.zeros(0, np.uint64)       # zero-filled after describe (Frame.hpp:170)
+        self.backProjections = np.zeros((0, 3), np.float64)
+        self.backProjectionsValid = np.zeros(0, np.uint8)
+
+    def numKeypoints(self):
+        return len(self.keypoints)
+
+    def keypointDescriptor(self, k):
+        return self.descriptors[k]
+
+    def resetKeypoints(self, keypoints):
+        self.keypoints = np.ascontiguousarray(keypoints, KP_DTYPE)
+        self.landmarkIds = np.zeros(len(self.keypoints), np.uint64)
+
+    def resetDescriptors(self, descriptors):
+        self.descriptors = np.ascontiguousarray(descriptors, np.uint8)
+
+
+class MultiFrame:
+    """okvis::MultiFrame: one Frame per camera of the NCameraSystem (MultiFrame.hpp:327-331)."""
+
+    def __init__(self, numCameras, timestamp=0.0, id=0):
+        self.frames = [Frame() for _ in range(numCameras)]
+        self.timestamp = timestamp
+        self.id = id
+
+    def numFrames(self):
+        return len(self.frames)
+
+    def setImage(self, cameraIdx, image):
+        image = np.asarray(image)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise OkbError(_l.OKB_ERR_ARGUMENT, "setImage: expected a single-channel u8 image")
+        self.frames[cameraIdx].image = image
+
+    def numKeypoints(self, cameraIdx=None):
+        if cameraIdx is None:
+            return sum(f.numKeypoints() for f in self.frames)
+        return self.frames[cameraIdx].numKeypoints()
+
+    def keypointDescriptor(self, cameraIdx, k):
+        return self.frames[cameraIdx].descriptors[k]
+
+    def landmarkId(self, cameraIdx, k):
+        return int(self.frames[cameraIdx].landmarkIds[k])
+
+    def setLandmarkId(self, cameraIdx, k, lmId):
+        self.frames[cameraIdx].landmarkIds[k] = lmId
+
+
+class Frontend:
+    """okvis::Frontend restricted to the hot path. One CUDA context (okb_context_t) per instance."""
+
+    def __init__(self, numCameras, width=752, height=480, device=0, max_batch=1, descriptor_bytes=64):
+        self.numCameras = numCameras
+        self._geom = [(width, height)] * numCameras if np.isscalar(width) else list(zip(width, height))
+        # defaults of okvis::Frontend::Frontend (Frontend.cpp:133-147), threshold re-interpreted as the AGAST threshold
+        self.briskDetectionOctaves_ = 0
+        self.briskDetectionThreshold_ = 40.0
+        self.briskDetectionAbsoluteThreshold_ = 200.0
+        self.briskDetectionMaximumKeypoints_ = 450
+        self.briskDescriptionRotationInvariance_ = True
+        self.briskDescriptionScaleInvariance_ = False
+        self.briskMatchingThreshold_ = 60.0
+        self._device, self._max_batch, self._D = device, max_batch, descriptor_bytes
+        self._ctx = None
+        self._locks = [threading.Lock() for _ in range(numCameras)]  # featureDetectorMutexes_ (Frontend.cpp:226)
+        self.initialiseBriskFeatureDetectors()
+
+    # ---- setters (Frontend.hpp:201-238): each one re-creates the detectors/extractors, as in the reference
+    def setBriskDetectionOctaves(self, octaves):
+        self.briskDetectionOctaves_ = int(octaves); self.initialiseBriskFeatureDetectors()
+
+    def setBriskDetectionThreshold(self, threshold):
+        self.briskDetectionThreshold_ = float(threshold); self.initialiseBriskFeatureDetectors()
+
+    def setBriskDetectionAbsoluteThreshold(self, threshold):
+        self.briskDetectionAbsoluteThreshold_ = float(threshold); self.initialiseBriskFeatureDetectors()
+
+    def setBriskDetectionMaximumKeypoints(self, maxKeypoints):
+        self.briskDetectionMaximumKeypoints_ = int(maxKeypoints); self.initialiseBriskFeatureDetectors()
+
+    def setBriskDescriptionRotationInvariance(self, invariance):
+        if not invariance:
+            raise OkbError(_l.OKB_ERR_UNSUPPORTED, "only rotation-invariant BRISK is implemented")
+        self.briskDescriptionRotationInvariance_ = True
+
+    def setBriskDescriptionScaleInvariance(self, invariance):
+        self.briskDescriptionScaleInvariance_ = bool(invariance)
+
+    def setBriskMatchingThreshold(self, threshold):
+        self.briskMatchingThreshold_ = float(threshold)
+
+    def configure(self, threshold=None, octaves=None, max_keypoints=None, matching_threshold=None):
+        """Set several parameters with a single re-initialisation."""
+        if threshold is not None: self.briskDetectionThreshold_ = float(threshold)
+        if octaves is not None: self.briskDetectionOctaves_ = int(octaves)
+        if max_keypoints is not None: self.briskDetectionMaximumKeypoints_ = int(max_keypoints)
+        if matching_threshold is not None: self.briskMatchingThreshold_ = float(matching_threshold)
+        self.initialiseBriskFeatureDetectors()
+
+    def initialiseBriskFeatureDetectors(self):
+        """Frontend::initialiseBriskFeatureDetectors (Frontend.cpp:2398-2417): (re)create the per-camera objects."""
+        self.close()
+        cfgs = (CameraConfig * self.numCameras)()
+        for i, (w, h) in enumerate(self._geom):
+            cfgs[i] = CameraConfig(w, h, int(self.briskDetectionThreshold_), self.briskDetectionOctaves_,
+                                   self.briskDetectionMaximumKeypoints_, self._D, self._max_batch, 1.0)
+        ctx = C.c_void_p()
+        check(_l.lib().okb_create(self._device, self.numCameras, cfgs, C.byref(ctx)))
+        self._ctx = ctx
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            _l.lib().okb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def ctx(self):
+        return self._ctx
+
+    # ---- detect + describe
+    def _capacity(self, cam):
+        n = self.briskDetectionMaximumKeypoints_
+        return n if n > 0 else 16384
+
+    def detectAndDescribe(self, cameraIndex, frameOut, T_WC=None, keypoints=None):
+        """Frontend::detectAndDescribe (Frontend.cpp:221-269). Thread-safe per camera; returns True."""
+        if keypoints is not None:  # Frontend.cpp:229: "external keypoints currently not supported"
+            raise OkbError(_l.OKB_ERR_UNSUPPORTED, "external keypoints currently not supported")
+        with self._locks[cameraIndex]:
+            fr = frameOut.frames[cameraIndex]
+            img = np.ascontiguousarray(fr.image)
+            w, h = self._geom[cameraIndex]
+            if img.shape != (h, w):
+                raise OkbError(_l.OKB_ERR_ARGUMENT, f"image is {img.shape}, camera {cameraIndex} is {(h, w)}")
+            cap = self._capacity(cameraIndex)
+            kp = np.zeros(cap, KP_DTYPE)
+            desc = np.zeros((cap, self._D), np.uint8)
+            n = C.c_int(0)
+            check(_l.lib().okb_detect_describe(self._ctx, cameraIndex, img.ctypes.data, img.strides[0], kp.ctypes.data,
+                                               desc.ctypes.data, cap, C.byref(n)))
+            fr.keypoints = kp[:n.value].copy()
+            fr.descriptors = np.ascontiguousarray(desc[:n.value])
+            fr.landmarkIds = np.zeros(n.value, np.uint64)  # Frame::describe zero-fills them (Frame.hpp:170)
+        return True
+
+    def detectAndDescribeBatch(self, cameraIndex, images):
+        """Batch replay: `images` is n x H x W u8. Returns a list of (keypoints, descriptors)."""
+        images = np.ascontiguousarray(images, np.uint8)
+        n_frames = images.shape[0]
+        cap = self._capacity(cameraIndex)
+        kp = np.zeros((n_frames, cap), KP_DTYPE)
+        desc = np.zeros((n_frames, cap, self._D), np.uint8)
+        n = np.zeros(n_frames, np.int32)
+        with self._locks[cameraIndex]:
+            check(_l.lib().okb_detect_describe_batch(self._ctx, cameraIndex, n_frames, images.ctypes.data,
+                                                     images.strides[1], kp.ctypes.data, desc.ctypes.data, cap,
+                                                     n.ctypes.data))
+        return [(kp[b, :n[b]].copy(), desc[b, :n[b]].copy()) for b in range(n_frames)]
+
+    def layers(self, cameraIndex, frame=0):
+        """Pyramid layer images and thresholded score maps of the last detect call (test hook)."""
+        L = _l.lib()
+        out = []
+        for i in range(L.okb_num_layers(self._ctx, cameraIndex)):
+            w, h, s, o = C.c_int(), C.c_int(), C.c_float(), C.c_float()
+            check(L.okb_layer_info(self._ctx, cameraIndex, i, C.byref(w), C.byref(h), C.byref(s), C.byref(o)))
+            img = np.zeros((h.value, w.value), np.uint8)
+            sc = np.zeros((h.value, w.value), np.uint8)
+            check(L.okb_fetch_layer(self._ctx, cameraIndex, frame, i, img.ctypes.data, sc.ctypes.data))
+            out.append((img, sc, s.value, o.value))
+        return out
+
+    # ---- matchers (thin, array-in / array-out forms of the five loops)
+    def matchToMapByThread(self, kp_desc, kp_xy, kp_use, cand_desc, cand_lm, lm_proj, lm_is3d, use_imu=True):
+        """Frontend::matchToMapByThread (Frontend.cpp:1515-1590) for all keypoints of one camera."""
+        kp_desc = np.ascontiguousarray(kp_desc, np.uint8); cand_desc = np.ascontiguousarray(cand_desc, np.uint8)
+        n, D = kp_desc.shape[0], kp_desc.shape[1] if kp_desc.ndim == 2 else self._D
+        kp_xy = np.ascontiguousarray(kp_xy, np.float64); cand_lm = np.ascontiguousarray(cand_lm, np.int32)
+        lm_proj = np.ascontiguousarray(lm_proj, np.float64); lm_is3d = np.ascontiguousarray(lm_is3d, np.uint8)
+        kp_use = None if kp_use is None else np.ascontiguousarray(kp_use, np.uint8)
+        dist = np.zeros(n, np.uint32); lm = np.zeros(n, np.int32)
+        thr = 20.0 if use_imu else 150.0  # Frontend.cpp:1530
+        check(_l.lib().okb_match_map3d(self._ctx, D, n, ptr(kp_desc), ptr(kp_xy), ptr(kp_use), len(cand_desc),
+                                       ptr(cand_desc), ptr(cand_lm), len(lm_is3d), ptr(lm_proj), ptr(lm_is3d), thr,
+                                       int(self.briskMatchingThreshold_), ptr(dist), ptr(lm)))
+        return dist, lm
+
+    def matchToMapByThreadUnitialised(self, kp_desc, kp_e_W, kp_use, cand_desc, cand_lm, cand_e_W, cand_r_W, lm_is3d,
+                                      r_WC1, focalLength, kp_prev_lm=None):
+        """Frontend::matchToMapByThreadUnitialised (Frontend.cpp:1594-1720)."""
+        kp_desc = np.ascontiguousarray(kp_desc, np.uint8); cand_desc = np.ascontiguousarray(cand_desc, np.uint8)
+        n, D = kp_desc.shape
+        kp_e_W = np.ascontiguousarray(kp_e_W, np.float64); cand_e_W = np.ascontiguousarray(cand_e_W, np.float64)
+        cand_r_W = np.ascontiguousarray(cand_r_W, np.float64); cand_lm = np.ascontiguousarray(cand_lm, np.int32)
+        lm_is3d = np.ascontiguousarray(lm_is3d, np.uint8); r = np.ascontiguousarray(r_WC1, np.float64)
+        kp_use = None if kp_use is None else np.ascontiguousarray(kp_use, np.uint8)
+        kp_prev_lm = None if kp_prev_lm is None else np.ascontiguousarray(kp_prev_lm, np.int32)
+        dist = np.zeros(n, np.uint32); lm = np.zeros(n, np.int32); hp = np.zeros((n, 4), np.float64); ctr = C.c_int32(0)
+        check(_l.lib().okb_match_map_uninit(self._ctx, D, n, ptr(kp_desc), ptr(kp_e_W), ptr(kp_use), ptr(kp_prev_lm),
+                                            len(cand_desc), ptr(cand_desc), ptr(cand_lm), ptr(cand_e_W), ptr(cand_r_W),
+                                            len(lm_is3d), ptr(lm_is3d), ptr(r), 1.0 / focalLength,
+                                            int(self.briskMatchingThreshold_), ptr(dist), ptr(lm), ptr(hp), C.byref(ctr)))
+        return dist, lm, hp, ctr.value
+
+    def _stereo(self, fn, desc0, use0, e0, sof0, desc1, valid1, e1, sof1, r0, r1, T0, T1):
+        desc0 = np.ascontiguousarray(desc0, np.uint8); desc1 = np.ascontiguousarray(desc1, np.uint8)
+        n0, D = desc0.shape
+        a = lambda x, t: None if x is None else np.ascontiguousarray(x, t)
+        use0, valid1 = a(use0, np.uint8), a(valid1, np.uint8)
+        e0, e1, sof0, sof1 = a(e0, np.float64), a(e1, np.float64), a(sof0, np.float64), a(sof1, np.float64)
+        r0, r1, T0, T1 = a(r0, np.float64), a(r1, np.float64), a(T0, np.float64), a(T1, np.float64)
+        k1 = np.zeros(n0, np.int32); dist = np.zeros(n0, np.uint32); hp = np.zeros((n0, 4), np.float64)
+        init = np.zeros(n0, np.uint8)
+        thr = int(self.briskMatchingThreshold_)
+        if fn == "motion":
+            check(_l.lib().okb_match_motion_stereo(self._ctx, D, n0, ptr(desc0), ptr(use0), ptr(e0), ptr(sof0), len(desc1),
+                                                   ptr(desc1), ptr(valid1), ptr(e1), ptr(r0), ptr(r1), ptr(T0), ptr(T1), thr,
+                                                   ptr(k1), ptr(dist), ptr(hp), ptr(init)))
+        else:
+            check(_l.lib().okb_match_stereo(self._ctx, D, n0, ptr(desc0), ptr(use0), ptr(e0), ptr(sof0), len(desc1),
+                                            ptr(desc1), ptr(valid1), ptr(e1), ptr(sof1), ptr(r0), ptr(r1), ptr(T0), ptr(T1),
+                                            thr, ptr(k1), ptr(dist), ptr(hp), ptr(init)))
+        return k1, dist, hp, init
+
+    def matchMotionStereo(self, desc0, use0, e0_W, size_over_f0, desc1, valid1, e1_W, r_WC0, r_WC1, T_CW0, T_CW1):
+        """Worker loop of Frontend::matchMotionStereo (Frontend.cpp:1809-1907) for one (older frame, camera)."""
+        return self._stereo("motion", desc0, use0, e0_W, size_over_f0, desc1, valid1, e1_W, None, r_WC0, r_WC1, T_CW0, T_CW1)
+
+    def matchStereo(self, desc0, valid0, e0_W, size_over_f0, desc1, valid1, e1_W, size_over_f1, r_WC0, r_WC1, T_CW0, T_CW1):
+        """k0/k1 loops of Frontend::matchStereo (Frontend.cpp:2016-2074) for one overlapping camera pair."""
+        return self._stereo("stereo", desc0, valid0, e0_W, size_over_f0, desc1, valid1, e1_W, size_over_f1, r_WC0, r_WC1,
+                            T_CW0, T_CW1)
+
+    def verifyRecognisedPlaceMatch(self, lm_offsets, lm_desc, kp_desc):
+        """Descriptor matching loop of Frontend::verifyRecognisedPlace (Frontend.cpp:329-355)."""
+        lm_offsets = np.ascontiguousarray(lm_offsets, np.int32); lm_desc = np.ascontiguousarray(lm_desc, np.uint8)
+        kp_desc = np.ascontiguousarray(kp_desc, np.uint8)
+        n_lm = len(lm_offsets) - 1
+        D = kp_desc.shape[1]
+        k = np.zeros(n_lm, np.int32); dist = np.zeros(n_lm, np.uint32)
+        check(_l.lib().okb_match_place(self._ctx, D, n_lm, ptr(lm_offsets), ptr(lm_desc), len(kp_desc), ptr(kp_desc),
+                                       int(self.briskMatchingThreshold_), ptr(k), ptr(dist)))
+        return k, dist
+
+    def hammingMatrix(self, a, b):
+        """brisk::Hamming::PopcntofXORed over all pairs."""
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        out = np.zeros((len(a), len(b)), np.uint16)
+        check(_l.lib().okb_hamming_matrix(self._ctx, a.shape[1], len(a), ptr(a), len(b), ptr(b), ptr(out)))
+        return out

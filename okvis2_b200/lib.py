@@ -1,0 +1,100 @@
+"""ctypes binding of libokvis_b200.so (the C ABI declared in include/okvis_b200.h).
+
+The library is the product; this module only loads it and declares prototypes. There is no fallback:
+if the shared object is missing, or no CUDA device is present, the calls fail loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libokvis_b200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+OKB_OK, OKB_ERR_NO_DEVICE, OKB_ERR_CUDA, OKB_ERR_ARGUMENT, OKB_ERR_CAPACITY, OKB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+
+class OkbError(RuntimeError):
+    """Mirror of okvis::Frontend::Exception (reference okvis_frontend/include/okvis/Frontend.hpp:60)."""
+
+    def __init__(self, status, msg):
+        super().__init__(f"okvis_b200 status {status}: {msg}")
+        self.status = status
+
+
+class CameraConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("threshold", C.c_int32), ("octaves", C.c_int32),
+                ("max_keypoints", C.c_int32), ("descriptor_bytes", C.c_int32), ("max_batch", C.c_int32),
+                ("pattern_scale", C.c_float)]
+
+
+def build(force=False):
+    """Compile libokvis_b200.so for sm_100a with nvcc (okvis2_b200/csrc/Makefile)."""
+    src = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(src, f) for f in os.listdir(src) if f.endswith((".cu", ".h"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "okvis_b200.h"))
+    stale = not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-j4", "-C", src])
+    return SO_PATH
+
+
+_LIB = None
+vp, i32, u32, f64 = C.c_void_p, C.c_int, C.c_uint32, C.c_double
+
+_PROTOS = {
+    "okb_create": (i32, [i32, i32, vp, C.POINTER(vp)]),
+    "okb_destroy": (None, [vp]),
+    "okb_last_error": (C.c_char_p, []),
+    "okb_version": (C.c_char_p, []),
+    "okb_launch_count": (C.c_int64, [vp]),
+    "okb_stream": (vp, [vp, i32]),
+    "okb_sync": (i32, [vp]),
+    "okb_detect_describe": (i32, [vp, i32, vp, C.c_size_t, vp, vp, i32, vp]),
+    "okb_detect_describe_batch": (i32, [vp, i32, i32, vp, C.c_size_t, vp, vp, i32, vp]),
+    "okb_detect_describe_batch_device": (i32, [vp, i32, i32, vp]),
+    "okb_fetch_features": (i32, [vp, i32, i32, vp, vp, i32, vp]),
+    "okb_device_features": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]),
+    "okb_num_layers": (i32, [vp, i32]),
+    "okb_layer_info": (i32, [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "okb_fetch_layer": (i32, [vp, i32, i32, i32, vp, vp]),
+    "okb_pyramid_score_bytes": (C.c_int64, [vp, i32]),
+    "okb_enable_timers": (i32, [vp, i32]),
+    "okb_reset_timers": (i32, [vp]),
+    "okb_get_timers": (i32, [vp, i32, C.POINTER(f64), C.POINTER(C.c_int64), C.POINTER(f64)]),
+    "okb_match_map3d": (i32, [vp, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, f64, u32, vp, vp]),
+    "okb_match_map_uninit": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, f64, u32, vp, vp, vp, vp]),
+    "okb_match_motion_stereo": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
+    "okb_match_stereo": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
+    "okb_match_place": (i32, [vp, i32, i32, vp, vp, i32, vp, u32, vp, vp]),
+    "okb_hamming_matrix": (i32, [vp, i32, i32, vp, i32, vp, vp]),
+    "okb_match_map3d_device": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, f64, u32, vp, vp]),
+}
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise OkbError(OKB_ERR_UNSUPPORTED, f"{SO_PATH} is missing: build it with __graft_entry__.build() "
+                           "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(status):
+    if status != 0:
+        raise OkbError(status, lib().okb_last_error().decode(errors="replace"))
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data

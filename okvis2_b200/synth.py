@@ -83,3 +83,93 @@ def noisy_copies(desc, n, flip_p, rng):
     bits = np.unpackbits(desc[idx], axis=1)
     flips = (rng.random(bits.shape) < flip_p).astype(np.uint8)
     return np.packbits(bits ^ flips, axis=1), idx
+
+
+# ---- synthetic matcher inputs -------------------------------------------------------------------
+def random_descriptors(rng, n, D):
+    return rng.integers(0, 256, (n, D), dtype=np.uint8)
+
+
+def map_scene(seed, kp_xy, kp_desc, n_lm, frac_copy=0.6, frac_near=0.10, frac_3d=0.7, flip_p=0.08, W=1024, H=1024):
+    """Landmark pool for M1/M2: n_lm landmarks with 1-3 descriptors each (ascending landmark slot).
+
+    frac_copy of the landmarks carry noisy copies of query descriptors (true matches below threshold 60), the rest are
+    random. frac_near of the landmarks project within 20 px of their source keypoint; the others land anywhere.
+    Returns dict(cand_desc, cand_lm, lm_proj, lm_is3d, cand_e_W, cand_r_W).
+    """
+    rng = np.random.default_rng(seed)
+    n_kp, D = kp_desc.shape
+    n_desc = rng.integers(1, 4, n_lm)
+    cand_lm = np.repeat(np.arange(n_lm, dtype=np.int32), n_desc)
+    n_cand = len(cand_lm)
+    src = rng.integers(0, max(n_kp, 1), n_lm)
+    is_copy = rng.random(n_lm) < frac_copy
+    cand_desc = random_descriptors(rng, n_cand, D)
+    if n_kp:
+        csrc = src[cand_lm]
+        bits = np.unpackbits(kp_desc[csrc], axis=1)
+        flips = (rng.random(bits.shape) < flip_p).astype(np.uint8)
+        noisy = np.packbits(bits ^ flips, axis=1)
+        m = is_copy[cand_lm]
+        cand_desc[m] = noisy[m]
+    near = rng.random(n_lm) < frac_near
+    lm_proj = np.stack([rng.uniform(-20, W + 20, n_lm), rng.uniform(-20, H + 20, n_lm)], 1)
+    if n_kp:
+        off = rng.uniform(-14, 14, (n_lm, 2))
+        lm_proj[near] = kp_xy[src[near]] + off[near]
+    lm_is3d = (rng.random(n_lm) < frac_3d).astype(np.uint8)
+    # observation rays of the pooled descriptors (for M2): unit vectors around +z, observer positions near the origin
+    e = rng.normal(0, 0.25, (n_cand, 3)); e[:, 2] = 1.0
+    e /= np.linalg.norm(e, axis=1, keepdims=True)
+    r = rng.normal(0, 0.3, (n_cand, 3))
+    return dict(cand_desc=cand_desc, cand_lm=cand_lm, lm_proj=lm_proj, lm_is3d=lm_is3d, cand_e_W=e, cand_r_W=r,
+                src=src, is_copy=is_copy)
+
+
+def rot(axis, a):
+    c, s = np.cos(a), np.sin(a)
+    x, y, z = axis
+    return np.array([[c + x * x * (1 - c), x * y * (1 - c) - z * s, x * z * (1 - c) + y * s],
+                     [y * x * (1 - c) + z * s, c + y * y * (1 - c), y * z * (1 - c) - x * s],
+                     [z * x * (1 - c) - y * s, z * y * (1 - c) + x * s, c + z * z * (1 - c)]])
+
+
+def stereo_scene(seed, n0, n1, D=64, f=458.0, baseline=0.11, flip_p=0.04, frac_match=0.7, ray_noise=2e-4):
+    """Two views of random 3-D points for M2/M3/M4: world-frame unit rays, descriptors, keypoint sizes, poses."""
+    rng = np.random.default_rng(seed)
+    C0 = rot((0, 1, 0), 0.02) @ rot((1, 0, 0), -0.01)
+    C1 = rot((0, 1, 0), -0.015) @ rot((0, 0, 1), 0.01)
+    r0 = np.array([0.0, 0.0, 0.0]); r1 = np.array([baseline, 0.003, -0.002])
+    n_pts = max(n0, n1)
+    depth = np.exp(rng.uniform(np.log(0.15), np.log(60.0), n_pts))
+    dirs = rng.normal(0, 0.35, (n_pts, 3)); dirs[:, 2] = 1.0
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    P = dirs * depth[:, None]
+    desc_pts = random_descriptors(rng, n_pts, D)
+
+    def view(n, r, noise_seed):
+        g = np.random.default_rng(noise_seed)
+        idx = g.permutation(n_pts)[:n]
+        e = P[idx] - r
+        e /= np.linalg.norm(e, axis=1, keepdims=True)
+        e += g.normal(0, ray_noise, e.shape)
+        e /= np.linalg.norm(e, axis=1, keepdims=True)
+        bits = np.unpackbits(desc_pts[idx], axis=1)
+        flips = (g.random(bits.shape) < flip_p).astype(np.uint8)
+        d = np.packbits(bits ^ flips, axis=1)
+        outl = g.random(n) > frac_match
+        d[outl] = random_descriptors(g, int(outl.sum()), D)
+        size = g.choice([12.0, 18.0, 24.0, 36.0, 48.0], n) * g.uniform(0.9, 1.1, n)
+        valid = (g.random(n) > 0.03).astype(np.uint8)
+        return idx, np.ascontiguousarray(e), d, size / f, valid
+
+    i0, e0, d0, sof0, v0 = view(n0, r0, seed * 3 + 1)
+    i1, e1, d1, sof1, v1 = view(n1, r1, seed * 3 + 2)
+
+    def T_CW(Cm, r):
+        R = Cm.T
+        t = -(R @ r)
+        return np.ascontiguousarray(np.concatenate([R, t[:, None]], 1).reshape(12))
+
+    return dict(desc0=d0, e0_W=e0, sof0=sof0, valid0=v0, desc1=d1, e1_W=e1, sof1=sof1, valid1=v1, r_WC0=r0, r_WC1=r1,
+                T_CW0=T_CW(C0, r0), T_CW1=T_CW(C1, r1), idx0=i0, idx1=i1, f=f)

@@ -146,3 +146,95 @@ def cv_keypoints_to_array(kps):
     for i, k in enumerate(kps):
         a[i] = (k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave, k.class_id)
     return a
+
+
+# ---- matchers (match_oracle.cpp) ------------------------------------------------------------------------------
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def _c(a, t):
+    return None if a is None else np.ascontiguousarray(a, t)
+
+
+def hamming_matrix(a, b):
+    a, b = _c(a, np.uint8), _c(b, np.uint8)
+    out = np.zeros((len(a), len(b)), np.uint16)
+    lib().okvo_hamming_matrix(C.c_int(a.shape[1]), C.c_int(len(a)), C.c_void_p(_p(a)), C.c_int(len(b)), C.c_void_p(_p(b)),
+                              C.c_void_p(_p(out)))
+    return out
+
+
+def triangulate_fast(p1, e1, p2, e2, sigma):
+    a = [np.ascontiguousarray(v, np.float64) for v in (p1, e1, p2, e2)]
+    hp = np.zeros(4); v, p = C.c_int(), C.c_int()
+    lib().okvo_triangulate_fast(*[C.c_void_p(x.ctypes.data) for x in a], C.c_double(sigma), C.c_void_p(hp.ctypes.data),
+                                C.byref(v), C.byref(p))
+    return hp, bool(v.value), bool(p.value)
+
+
+def match_map3d(kp_desc, kp_xy, kp_use, cand_desc, cand_lm, lm_proj, lm_is3d, reproj_thr, match_thr, n_threads=1):
+    kp_desc, cand_desc = _c(kp_desc, np.uint8), _c(cand_desc, np.uint8)
+    n, D = kp_desc.shape
+    kp_xy, kp_use = _c(kp_xy, np.float64), _c(kp_use, np.uint8)
+    cand_lm, lm_proj, lm_is3d = _c(cand_lm, np.int32), _c(lm_proj, np.float64), _c(lm_is3d, np.uint8)
+    dist = np.zeros(n, np.uint32); lm = np.zeros(n, np.int32)
+    f = lib().okvo_match_map3d
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+    f(D, n, _p(kp_desc), _p(kp_xy), _p(kp_use), len(cand_desc), _p(cand_desc), _p(cand_lm), len(lm_is3d), _p(lm_proj),
+      _p(lm_is3d), reproj_thr, match_thr, _p(dist), _p(lm), n_threads)
+    return dist, lm
+
+
+def match_map_uninit(kp_desc, kp_e_W, kp_use, kp_prev_lm, cand_desc, cand_lm, cand_e_W, cand_r_W, lm_is3d, r_WC1, sigma,
+                     match_thr, n_threads=1):
+    kp_desc, cand_desc = _c(kp_desc, np.uint8), _c(cand_desc, np.uint8)
+    n, D = kp_desc.shape
+    kp_e_W, kp_use, kp_prev_lm = _c(kp_e_W, np.float64), _c(kp_use, np.uint8), _c(kp_prev_lm, np.int32)
+    cand_lm, cand_e_W, cand_r_W = _c(cand_lm, np.int32), _c(cand_e_W, np.float64), _c(cand_r_W, np.float64)
+    lm_is3d, r = _c(lm_is3d, np.uint8), _c(r_WC1, np.float64)
+    dist = np.zeros(n, np.uint32); lm = np.zeros(n, np.int32); hp = np.zeros((n, 4)); ctr = C.c_int32(0)
+    f = lib().okvo_match_map_uninit
+    f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p,
+                  C.c_double, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    f(D, n, _p(kp_desc), _p(kp_e_W), _p(kp_use), _p(kp_prev_lm), len(cand_desc), _p(cand_desc), _p(cand_lm), _p(cand_e_W),
+      _p(cand_r_W), len(lm_is3d), _p(lm_is3d), _p(r), sigma, match_thr, _p(dist), _p(lm), _p(hp), C.addressof(ctr), n_threads)
+    return dist, lm, hp, ctr.value
+
+
+def _stereo(name, desc0, use0, e0, sof0, desc1, valid1, e1, sof1, r0, r1, T0, T1, match_thr, n_threads):
+    desc0, desc1 = _c(desc0, np.uint8), _c(desc1, np.uint8)
+    n0, D = desc0.shape
+    use0, valid1 = _c(use0, np.uint8), _c(valid1, np.uint8)
+    e0, e1, sof0, sof1 = _c(e0, np.float64), _c(e1, np.float64), _c(sof0, np.float64), _c(sof1, np.float64)
+    r0, r1, T0, T1 = _c(r0, np.float64), _c(r1, np.float64), _c(T0, np.float64), _c(T1, np.float64)
+    k1 = np.zeros(n0, np.int32); dist = np.zeros(n0, np.uint32); hp = np.zeros((n0, 4)); init = np.zeros(n0, np.uint8)
+    f = getattr(lib(), name)
+    if name == "okvo_match_motion_stereo":
+        f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 7 + [C.c_uint32] + [C.c_void_p] * 4 + [C.c_int]
+        f(D, n0, _p(desc0), _p(use0), _p(e0), _p(sof0), len(desc1), _p(desc1), _p(valid1), _p(e1), _p(r0), _p(r1), _p(T0),
+          _p(T1), match_thr, _p(k1), _p(dist), _p(hp), _p(init), n_threads)
+    else:
+        f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 8 + [C.c_uint32] + [C.c_void_p] * 4 + [C.c_int]
+        f(D, n0, _p(desc0), _p(use0), _p(e0), _p(sof0), len(desc1), _p(desc1), _p(valid1), _p(e1), _p(sof1), _p(r0), _p(r1),
+          _p(T0), _p(T1), match_thr, _p(k1), _p(dist), _p(hp), _p(init), n_threads)
+    return k1, dist, hp, init
+
+
+def match_motion_stereo(desc0, use0, e0, sof0, desc1, valid1, e1, r0, r1, T0, T1, match_thr, n_threads=1):
+    return _stereo("okvo_match_motion_stereo", desc0, use0, e0, sof0, desc1, valid1, e1, None, r0, r1, T0, T1, match_thr, n_threads)
+
+
+def match_stereo(desc0, valid0, e0, sof0, desc1, valid1, e1, sof1, r0, r1, T0, T1, match_thr, n_threads=1):
+    return _stereo("okvo_match_stereo", desc0, valid0, e0, sof0, desc1, valid1, e1, sof1, r0, r1, T0, T1, match_thr, n_threads)
+
+
+def match_place(lm_offsets, lm_desc, kp_desc, match_thr):
+    lm_offsets, lm_desc, kp_desc = _c(lm_offsets, np.int32), _c(lm_desc, np.uint8), _c(kp_desc, np.uint8)
+    n_lm = len(lm_offsets) - 1
+    k = np.zeros(n_lm, np.int32); dist = np.zeros(n_lm, np.uint32)
+    f = lib().okvo_match_place
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    f(kp_desc.shape[1], n_lm, _p(lm_offsets), _p(lm_desc), len(kp_desc), _p(kp_desc), match_thr, _p(k), _p(dist))
+    return k, dist

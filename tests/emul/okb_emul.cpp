@@ -1,0 +1,192 @@
+// tests/emul/okb_emul.cpp -- TEST INFRASTRUCTURE. Serial host execution of the *parallel formulation* that the CUDA
+// kernels implement (same per-element functions from okvis2_b200/csrc/okb_core.h, same phases, same touch-time map),
+// so that the formulation can be checked against the oracle on a machine without a GPU. Not part of the product.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../okvis2_b200/csrc/okb_core.h"
+#include "../../okvis2_b200/csrc/okb_tables.h"
+
+using namespace okb;
+
+struct Kp { float x, y, size, angle, response; int32_t octave, class_id; };
+
+struct HostLayer { int w, h, pitch; float scale, offset; std::vector<uint8_t> img, score; std::vector<uint32_t> touch; };
+
+static HostTables* g_tables = nullptr;
+
+static void resize_layer(const HostLayer& s, HostLayer& d)
+{
+  const double sx = 1. / ((double)d.w / s.w), sy = 1. / ((double)d.h / s.h);
+  const bool fast = sx == 2.0 && sy == 2.0;
+  if (fast) {
+    for (int y = 0; y < d.h; y++) for (int x = 0; x < d.w; x++) d.img[(size_t)y * d.pitch + x] = half_pixel(s.img.data(), s.pitch, x, y);
+    return;
+  }
+  AreaAxis ax, ay; build_area_axis(s.w, d.w, ax); build_area_axis(s.h, d.h, ay);
+  for (int y = 0; y < d.h; y++)
+    for (int x = 0; x < d.w; x++)
+      d.img[(size_t)y * d.pitch + x] = area_pixel(s.img.data(), s.pitch, ax.start[x], ax.count[x], &ax.alpha[(size_t)x * 4],
+                                                   ay.start[y], ay.count[y], &ay.alpha[(size_t)y * 4]);
+}
+
+struct Cand { uint32_t key; int layer, x, y; bool tie; RefineResult r; int state; };
+
+extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int threshold, int octaves, int max_kp,
+                                        Kp* kp_out, uint8_t* desc_out, int cap, int* stats /*[4]: cands, ties, rounds, raw*/)
+{
+  if (!g_tables) { g_tables = new HostTables(); if (!build_host_tables(1.0f, *g_tables)) return -1; }
+  const HostTables& T = *g_tables;
+  const int n_layers = octaves == 0 ? 1 : 2 * octaves;
+  std::vector<HostLayer> HL(n_layers);
+  auto init = [&](HostLayer& l, int w, int h, float scale) {
+    l.w = w; l.h = h; l.pitch = (w + 15) / 16 * 16; l.scale = scale; l.offset = 0.5f * scale - 0.5f;
+    l.img.assign((size_t)l.pitch * h, 0); l.score.assign((size_t)l.pitch * h, 0); l.touch.assign((size_t)l.pitch * h, 0);
+  };
+  init(HL[0], W, H, 1.0f); HL[0].offset = 0.f;
+  for (int y = 0; y < H; y++) memcpy(&HL[0].img[(size_t)y * HL[0].pitch], img + (size_t)y * W, W);
+  if (n_layers > 1) { init(HL[1], 2 * (W / 3), 2 * (H / 3), 1.5f); resize_layer(HL[0], HL[1]); }
+  for (int i = 2; i < n_layers; i += 2) {
+    init(HL[i], HL[i - 2].w / 2, HL[i - 2].h / 2, HL[i - 2].scale * 2); resize_layer(HL[i - 2], HL[i]);
+    init(HL[i + 1], HL[i - 1].w / 2, HL[i - 1].h / 2, HL[i - 1].scale * 2); resize_layer(HL[i - 1], HL[i + 1]);
+  }
+  LayerView L[kMaxLayers];
+  for (int i = 0; i < n_layers; i++) L[i] = LayerView{HL[i].img.data(), HL[i].w, HL[i].h, HL[i].pitch, HL[i].scale, HL[i].offset};
+  // phase: score maps
+  for (int i = 0; i < n_layers; i++)
+    for (int y = 0; y < HL[i].h; y++) for (int x = 0; x < HL[i].w; x++)
+      HL[i].score[(size_t)y * HL[i].pitch + x] = (uint8_t)score_thresholded(L[i], x, y, threshold);
+  // phase: candidates (any order on the device; the order here is irrelevant by construction)
+  std::vector<Cand> C;
+  for (int i = n_layers - 1; i >= 0; i--) {  // deliberately reversed to prove order independence
+    const HostLayer& l = HL[i];
+    for (int y = l.h - 4; y >= 3; y--) for (int x = 3; x < l.w - 3; x++) {
+      const uint8_t* s = &l.score[(size_t)y * l.pitch + x];
+      const int c = s[0];
+      if (c == 0) continue;
+      bool ok = true, tie = false;
+      for (int dy = -1; dy <= 1 && ok; dy++) for (int dx = -1; dx <= 1; dx++) {
+        if (!dx && !dy) continue;
+        const int v = s[dy * l.pitch + dx];
+        if (v > c) { ok = false; break; }
+        if (v == c) tie = true;
+      }
+      if (!ok) continue;
+      Cand cd; cd.key = time_key(i, x, y); cd.layer = i; cd.x = x; cd.y = y; cd.tie = tie; cd.state = tie ? 0 : 1;
+      C.push_back(cd);
+    }
+  }
+  const uint32_t epoch = 1;
+  auto touch = [&](int layer, int x, int y, uint32_t time) {
+    HostLayer& l = HL[layer];
+    if (x < 0 || y < 0 || x >= l.w || y >= l.h) return;
+    uint32_t& e = l.touch[(size_t)y * l.pitch + x];
+    e = std::max(e, touch_entry(epoch, time));
+  };
+  auto emit = [&](const Cand& c) {
+    if (c.r.own_touch == 1) { for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) touch(c.layer, c.x + dx, c.y + dy, c.key); }
+    else if (c.r.own_touch == 2) { for (int dy = -1; dy <= 2; dy++) for (int dx = -1; dx <= 2; dx++) touch(c.layer, c.x + dx, c.y + dy, c.key); }
+    if (c.r.has_above) for_each_above_touch(c.layer, c.x, c.y, c.r.above, [&](int x, int y) { touch(c.layer + 1, x, y, c.key); });
+  };
+  // phase: refine (pure) + touches of the non-tie maxima
+  for (auto& c : C) { refine_candidate(L, n_layers, c.layer, c.x, c.y, threshold, c.r); if (!c.tie) emit(c); }
+  // phase: resolve ties in dependency rounds
+  std::vector<int> ties;
+  for (size_t i = 0; i < C.size(); i++) if (C[i].tie) ties.push_back((int)i);
+  auto near_ = [&](const Cand& u, const Cand& t) {  // can events of u reach the 5x5 window of t ?
+    if (u.layer == t.layer) return abs(u.x - t.x) <= 4 && abs(u.y - t.y) <= 4;
+    if (u.layer + 1 == t.layer) {
+      ScanIter it; above_window(u.layer, u.x, u.y, it);
+      const int xa = (int)it.x_1 - 1, xb = (int)it.x1 + 2, ya = (int)it.y_1 - 1, yb = (int)it.y1 + 2;
+      return !(t.x + 2 < xa || t.x - 2 > xb || t.y + 2 < ya || t.y - 2 > yb);
+    }
+    return false;
+  };
+  int rounds = 0, unresolved = (int)ties.size();
+  while (unresolved > 0) {
+    rounds++;
+    std::vector<int> newly;
+    for (int ti : ties) {
+      Cand& t = C[ti];
+      if (t.state != 0) continue;
+      bool blocked = false;
+      for (int ui : ties) { const Cand& u = C[ui]; if (u.state == 0 && u.key < t.key && near_(u, t)) { blocked = true; break; } }
+      if (blocked) continue;
+      const HostLayer& l = HL[t.layer];
+      int m[5][5];
+      for (int dy = -2; dy <= 2; dy++) for (int dx = -2; dx <= 2; dx++) {
+        const int x = t.x + dx, y = t.y + dy;
+        int v = l.score[(size_t)y * l.pitch + x];
+        if (v == 0 && touched_before(l.touch[(size_t)y * l.pitch + x], epoch, t.key)) v = b0(L[t.layer], x, y);
+        m[dy + 2][dx + 2] = v;
+      }
+      newly.push_back(is_max_2d_5x5(m) ? ti : -ti - 1);
+    }
+    for (int v : newly) {
+      if (v >= 0) { C[v].state = 1; emit(C[v]); } else C[-v - 1].state = 2;
+      unresolved--;
+    }
+  }
+  // phase: finalize (order by key, cap, border removal)
+  std::vector<int> order;
+  for (size_t i = 0; i < C.size(); i++) if (C[i].state == 1 && C[i].r.keep) order.push_back((int)i);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return C[a].key < C[b].key; });
+  const int raw = (int)order.size();
+  std::vector<char> keep(order.size(), 1);
+  if (max_kp > 0 && (int)order.size() > max_kp) {
+    std::vector<int> pos(order.size());
+    for (size_t i = 0; i < pos.size(); i++) pos[i] = (int)i;
+    std::sort(pos.begin(), pos.end(), [&](int a, int b) {
+      const float ra = C[order[a]].r.response, rb = C[order[b]].r.response;
+      return ra > rb || (ra == rb && a < b);
+    });
+    std::fill(keep.begin(), keep.end(), 0);
+    for (int i = 0; i < max_kp; i++) keep[pos[i]] = 1;
+  }
+  std::vector<Kp> kps; std::vector<int> kscale;
+  for (size_t i = 0; i < order.size(); i++) {
+    if (!keep[i]) continue;
+    const Cand& c = C[order[i]];
+    const int sc = kscale_from_bounds(T.scale_bounds.data(), c.r.size);
+    const int border = (int)T.size_list[sc];
+    if (c.r.x < (float)border || c.r.x >= (float)(W - border) || c.r.y < (float)border || c.r.y >= (float)(H - border)) continue;
+    kps.push_back(Kp{c.r.x, c.r.y, c.r.size, -1.f, c.r.response, c.layer, -1});
+    kscale.push_back(sc);
+  }
+  // phase: integral + describe
+  const int ipitch = W + 1;
+  std::vector<int32_t> integral((size_t)(W + 1) * (H + 1), 0);
+  for (int y = 0; y < H; y++) {
+    int32_t rs = 0;
+    for (int x = 0; x < W; x++) { rs += HL[0].img[(size_t)y * HL[0].pitch + x]; integral[(size_t)(y + 1) * ipitch + x + 1] = integral[(size_t)y * ipitch + x + 1] + rs; }
+  }
+  const int n = std::min((int)kps.size(), cap);
+  for (int k = 0; k < n; k++) {
+    Kp& p = kps[k];
+    int values[kPoints];
+    const PatternPoint* pat0 = &T.pattern[((size_t)kscale[k] * kRot + 0) * kPoints];
+    for (int i = 0; i < kPoints; i++) values[i] = smoothed_intensity(HL[0].img.data(), HL[0].pitch, integral.data(), ipitch, p.x, p.y, pat0[i]);
+    int d0 = 0, d1 = 0;
+    for (const LongPair& lp : T.long_pairs) { const int dt = values[lp.i] - values[lp.j]; d0 += dt * lp.wdx / 1024; d1 += dt * lp.wdy / 1024; }
+    p.angle = (float)(atan2((double)(float)d1, (double)(float)d0) / M_PI * 180.0);
+    int theta = (int)(kRot * ((double)p.angle / 360.0) + 0.5);
+    if (theta < 0) theta += kRot;
+    if (theta >= kRot) theta -= kRot;
+    if (p.angle < 0) p.angle += 360.f;
+    const PatternPoint* pat = &T.pattern[((size_t)kscale[k] * kRot + theta) * kPoints];
+    for (int i = 0; i < kPoints; i++) values[i] = smoothed_intensity(HL[0].img.data(), HL[0].pitch, integral.data(), ipitch, p.x, p.y, pat[i]);
+    uint32_t* out = (uint32_t*)(desc_out + (size_t)k * 64);
+    for (int w = 0; w < 16; w++) {
+      uint32_t word = 0;
+      for (int b = 0; b < 32; b++) { const uint32_t pr = T.short_pairs[w * 32 + b]; if (values[pr & 255] > values[pr >> 8]) word |= 1u << b; }
+      out[w] = word;
+    }
+    kp_out[k] = p;
+  }
+  if (stats) { stats[0] = (int)C.size(); stats[1] = (int)ties.size(); stats[2] = rounds; stats[3] = raw; }
+  return (int)kps.size();
+}

@@ -1,0 +1,50 @@
+"""CPU suite: the *parallel formulation* implemented by the CUDA kernels (same per-element code, okvis2_b200/csrc/okb_core.h,
+executed serially by tests/emul/okb_emul.cpp) must reproduce the oracle bit for bit, including the order-dependent
+tie-breaks of the reference's lazily cached score map."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT, assert_same_features, kp_struct
+from okvis2_b200.synth import synth_frame
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(ROOT, "tests", "emul", "libokb_emul.so")
+    src = os.path.join(ROOT, "tests", "emul", "okb_emul.cpp")
+    deps = [src, os.path.join(ROOT, "okvis2_b200", "csrc", "okb_core.h"), os.path.join(ROOT, "okvis2_b200", "csrc", "okb_tables.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.okb_emul_detect_describe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_int, C.c_void_p]
+
+    def run(img, thr, octv, max_kp=0, cap=1 << 16):
+        img = np.ascontiguousarray(img)
+        kp = np.zeros(cap, oracle.KP_DTYPE); d = np.zeros((cap, 64), np.uint8); st = np.zeros(4, np.int32)
+        n = lib.okb_emul_detect_describe(img.ctypes.data, img.shape[1], img.shape[0], thr, octv, max_kp, kp.ctypes.data,
+                                         d.ctypes.data, cap, st.ctypes.data)
+        return kp[:n], d[:n], st
+    return run
+
+
+@pytest.mark.parametrize("seed,W,H,thr,octv,max_kp", [(1000, 752, 480, 30, 3, 1000), (11, 752, 480, 30, 0, 0),
+                                                      (12, 640, 400, 12, 2, 0), (13, 341, 255, 20, 2, 300)])
+def test_parallel_formulation_equals_oracle(emul, seed, W, H, thr, octv, max_kp):
+    img = synth_frame(seed, W, H)
+    rk, rd = oracle.Brisk(thr, octv).detect_and_compute(img, max_kp)
+    kp, d, st = emul(img, thr, octv, max_kp)
+    assert st[1] > 0, "the case must exercise tied maxima"
+    assert_same_features(kp, d, rk, rd, f"seed {seed}")
+
+
+def test_parallel_formulation_on_real_image(emul, golden):
+    img = golden["real752_img"]
+    kp, d, st = emul(img, 30, 3)
+    assert_same_features(kp, d, kp_struct(golden["real752_t30_o3_kp"]), golden["real752_t30_o3_desc"], "real752")
+    assert st[2] >= 2  # several dependency rounds were needed

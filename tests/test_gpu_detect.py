@@ -1,0 +1,138 @@
+"""GPU suite: detect + describe through the C ABI (CUDA kernels) against the oracle and the cv2 golden vectors. Bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_same_features, kp_struct
+from okvis2_b200.frontend import Frontend, MultiFrame
+from okvis2_b200.synth import synth_frame, synth_stereo
+
+pytestmark = pytest.mark.gpu
+
+
+def run(fe, img, cam=0):
+    mf = MultiFrame(fe.numCameras)
+    mf.setImage(cam, img)
+    assert fe.detectAndDescribe(cam, mf, None, None) is True
+    fr = mf.frames[cam]
+    assert fr.descriptors.flags["C_CONTIGUOUS"] and (fr.landmarkIds == 0).all() and len(fr.landmarkIds) == len(fr.keypoints)
+    return fr.keypoints, fr.descriptors
+
+
+@pytest.mark.parametrize("name,W,H,thr,octv", [("real752", 752, 480, 30, 0), ("real752", 752, 480, 30, 3),
+                                               ("real752", 752, 480, 60, 2), ("real341", 341, 255, 25, 2)])
+def test_cuda_equals_cv2_golden_real(golden, name, W, H, thr, octv):
+    fe = Frontend(1, W, H)
+    fe.configure(threshold=thr, octaves=octv, max_keypoints=0)
+    kp, d = run(fe, golden[f"{name}_img"])
+    assert_same_features(kp, d, kp_struct(golden[f"{name}_t{thr}_o{octv}_kp"]), golden[f"{name}_t{thr}_o{octv}_desc"], name)
+    fe.close()
+
+
+@pytest.mark.parametrize("seed,W,H,thr,octv", [(1000, 752, 480, 30, 3), (1001, 752, 480, 30, 0), (2000, 1024, 1024, 30, 3),
+                                               (3000, 720, 540, 30, 3)])
+def test_cuda_equals_cv2_golden_synth(golden, seed, W, H, thr, octv):
+    fe = Frontend(1, W, H)
+    fe.configure(threshold=thr, octaves=octv, max_keypoints=0)
+    kp, d = run(fe, synth_frame(seed, W, H))
+    key = f"synth{seed}_{W}x{H}_t{thr}_o{octv}"
+    assert_same_features(kp, d, kp_struct(golden[key + "_kp"]), golden[key + "_desc"], key)
+    fe.close()
+
+
+def test_layers_and_score_maps_equal_oracle(golden):
+    img = golden["real752_img"]
+    fe = Frontend(1, 752, 480)
+    fe.configure(threshold=30, octaves=3, max_keypoints=0)
+    run(fe, img)
+    got = fe.layers(0)
+    o = oracle.Brisk(30, 3)
+    o.detect_raw(img)
+    ref = o.layers()
+    assert len(got) == len(ref) == 6
+    for i, ((gi, gs, gsc, go), (ri, rs, rsc, ro)) in enumerate(zip(got, ref)):
+        assert gi.shape == ri.shape and gsc == rsc and go == ro
+        assert np.array_equal(gi, ri), f"layer {i} image"
+        # oracle score cache = thresholded map + lazily cached sub-threshold values; compare where >= threshold
+        assert np.array_equal(gs, np.where(rs >= 30, rs, 0)), f"layer {i} scores"
+        assert (gs[gs > 0] >= 30).all()
+    fe.close()
+
+
+@pytest.mark.parametrize("max_kp", [1000, 400, 37])
+def test_max_keypoints_cap_equals_oracle(max_kp):
+    img = synth_frame(77, 752, 480)
+    fe = Frontend(1, 752, 480)
+    fe.configure(threshold=30, octaves=3, max_keypoints=max_kp)
+    kp, d = run(fe, img)
+    rk, rd = oracle.Brisk(30, 3).detect_and_compute(img, max_kp)
+    assert 0 < len(kp) <= max_kp
+    assert_same_features(kp, d, rk, rd, f"cap {max_kp}")
+    fe.close()
+
+
+def test_stereo_two_cameras_and_reuse():
+    fe = Frontend(2, 752, 480)
+    fe.configure(threshold=30, octaves=3, max_keypoints=1000)
+    o = oracle.Brisk(30, 3)
+    for t in range(3):  # repeated frames reuse the per-camera workspace (touch-map epochs)
+        l, r = synth_stereo(500, 752, 480, t=t)
+        for cam, img in enumerate((l, r)):
+            kp, d = run(fe, img, cam)
+            rk, rd = o.detect_and_compute(img, 1000)
+            assert_same_features(kp, d, rk, rd, f"t={t} cam={cam}")
+    fe.close()
+
+
+def test_batch_equals_single():
+    fe = Frontend(1, 752, 480, max_batch=4)
+    fe.configure(threshold=30, octaves=3, max_keypoints=1000)
+    imgs = np.stack([synth_frame(900 + i, 752, 480) for i in range(4)])
+    res = fe.detectAndDescribeBatch(0, imgs)
+    o = oracle.Brisk(30, 3)
+    for i, (kp, d) in enumerate(res):
+        rk, rd = o.detect_and_compute(imgs[i], 1000)
+        assert_same_features(kp, d, rk, rd, f"batch frame {i}")
+    fe.close()
+
+
+def test_edge_cases():
+    fe = Frontend(1, 120, 100)
+    fe.configure(threshold=30, octaves=2, max_keypoints=0)
+    for img in (np.zeros((100, 120), np.uint8), np.full((100, 120), 255, np.uint8)):
+        kp, d = run(fe, img)
+        assert len(kp) == 0 and d.shape == (0, 64)
+    # strided input (cv::Mat ROI): same result as the contiguous copy
+    big = synth_frame(5, 200, 100)
+    roi = big[:, 40:160]
+    kp, d = run(fe, roi)
+    rk, rd = oracle.Brisk(30, 2).detect_and_compute(np.ascontiguousarray(roi))
+    assert_same_features(kp, d, rk, rd, "roi")
+    # wrong size and external keypoints are rejected like the reference does
+    from okvis2_b200.lib import OkbError
+    mf = MultiFrame(1); mf.setImage(0, np.zeros((50, 50), np.uint8))
+    with pytest.raises(OkbError):
+        fe.detectAndDescribe(0, mf)
+    with pytest.raises(OkbError):
+        fe.detectAndDescribe(0, mf, None, keypoints=[1])
+    fe.close()
+
+
+def test_properties_at_full_size():
+    """size-independent properties at BASELINE size: determinism, translation covariance of an integer shift."""
+    img = synth_frame(31, 1024, 1024)
+    fe = Frontend(1, 1024, 1024)
+    fe.configure(threshold=30, octaves=0, max_keypoints=0)
+    kp1, d1 = run(fe, img)
+    kp2, d2 = run(fe, img)
+    assert_same_features(kp1, d1, kp2, d2, "determinism")
+    assert len(kp1) > 1500
+    # single-scale detection commutes with an integer translation away from the borders
+    sh = np.zeros_like(img); sh[8:, 16:] = img[:-8, :-16]
+    kp3, d3 = run(fe, sh)
+    a = {(round(float(k["x"]) + 16, 3), round(float(k["y"]) + 8, 3)): bytes(dd) for k, dd in zip(kp1, d1) if 80 < k["x"] < 900 and 80 < k["y"] < 900}
+    b = {(round(float(k["x"]), 3), round(float(k["y"]), 3)): bytes(dd) for k, dd in zip(kp3, d3)}
+    common = [k for k in a if k in b]
+    assert len(common) > 0.95 * len(a)
+    assert all(a[k] == b[k] for k in common)
+    fe.close()
