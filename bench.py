@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frames/s for detect + describe + match on N B200s, beside the CPU path on the same box.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
+A step = one pass of the hot path over one batch of synthetic stereo frames:
+  detect+describe of both cameras (batched launch), M1 match-to-map of every frame of both cameras.
+  * value : inputs (images, landmark pool) already resident in HBM, results left in HBM, device-timed (CUDA events).
+  * e2e   : the same work through the reference-facing calls with HOST buffers, per stereo frame (streaming use):
+            Frontend.detectAndDescribe per camera (one host thread per camera, like ThreadedSlam.cpp:432-448), then
+            Frontend.matchStereo (M4) and Frontend.matchToMapByThread (M1) -- H2D/D2H copies inside the timed region.
+  * cpu_baseline / --impl reference : the CPU oracle port (oracle/, restatement of OpenCV-BRISK + the reference's match
+            loops) on the host cores, bounded sample. It is the only place this file executes oracle/ code.
+N > 1: one process per GPU (torchrun), each rank replays its own independent sequences (BASELINE config 5: replicas, no
+data-path collective); time = max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1]: EuRoC stereo 752x480 stream, 1000 kpts/frame
+    "euroc": dict(W=752, H=480, max_kp=1000, threshold=30, octaves=3, n_lm=5000, batch=32, ring=6, f=458.0),
+    # BASELINE.json configs[2]: TUM-VI 1024x1024 stereo, 2000 kpts/frame, 50-keyframe landmark set
+    "tumvi": dict(W=1024, H=1024, max_kp=2000, threshold=30, octaves=3, n_lm=50000, batch=16, ring=5, f=190.0),
+}
+
+
+def make_frames(cfg, n, seed0, base=8):
+    """n stereo pairs: `base` rendered scenes + integer-shifted variants (distinct pixels, same statistics)."""
+    from okvis2_b200.synth import synth_stereo
+    W, H = cfg["W"], cfg["H"]
+    scenes = [synth_stereo(seed0 + i, W, H) for i in range(min(base, n))]
+    L = np.empty((n, H, W), np.uint8); R = np.empty((n, H, W), np.uint8)
+    for i in range(n):
+        l, r = scenes[i % len(scenes)]
+        s = i // len(scenes)
+        L[i] = np.roll(l, (3 * s, 5 * s), (0, 1)); R[i] = np.roll(r, (3 * s, 5 * s), (0, 1))
+    return L, R
+
+
+def make_map(cfg, kp, desc, seed):
+    from okvis2_b200.synth import map_scene
+    xy = np.stack([kp["x"], kp["y"]], 1).astype(np.float64)
+    return map_scene(seed, xy, desc, cfg["n_lm"], W=cfg["W"], H=cfg["H"])
+
+
+def pinhole_rays(kp, cfg, R_WC, dx=0.0):
+    """world-frame unit rays of an ideal pinhole camera (host-side stand-in for Frame::computeBackProjections)."""
+    x = (kp["x"].astype(np.float64) - cfg["W"] / 2 - dx) / cfg["f"]
+    y = (kp["y"].astype(np.float64) - cfg["H"] / 2) / cfg["f"]
+    e = np.stack([x, y, np.ones_like(x)], 1)
+    e /= np.linalg.norm(e, axis=1, keepdims=True)
+    return np.ascontiguousarray(e @ R_WC.T)
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_run(cfg, L, R, maps, n_threads):
+    """CPU oracle port over the given stereo frames; returns seconds. One worker per (frame, camera) job + matchers."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    n = len(L)
+    jobs = [(i, c) for i in range(n) for c in range(2)]
+    local = threading.local()
+
+    def work(job):
+        i, c = job
+        if not hasattr(local, "brisk"):
+            local.brisk = oracle.Brisk(cfg["threshold"], cfg["octaves"])
+        kp, d = local.brisk.detect_and_compute((L, R)[c][i], cfg["max_kp"])
+        m = maps[c]
+        xy = np.stack([kp["x"], kp["y"]], 1).astype(np.float64)
+        oracle.match_map3d(d, xy, None, m["cand_desc"], m["cand_lm"], m["lm_proj"], m["lm_is3d"], 20.0, 60, 1)
+        return len(kp)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(n_threads) as ex:
+        list(ex.map(work, jobs))
+    return time.perf_counter() - t0
+
+
+def run_reference(args, cfg, rank, world):
+    """--impl reference: the CPU path (oracle port; the real reference front-end cannot be built here)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = max(2, min(16, cores // 2))   # bounded sample: stereo frames per step
+    L, R = make_frames(cfg, n, 1000)
+    import oracle
+    o = oracle.Brisk(cfg["threshold"], cfg["octaves"])
+    maps = []
+    for c, img in enumerate((L[0], R[0])):
+        kp, d = o.detect_and_compute(img, cfg["max_kp"])
+        maps.append(make_map(cfg, kp, d, 40 + c))
+    for _ in range(max(args.warmup, 1)):
+        cpu_run(cfg, L[:2], R[:2], maps, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_run(cfg, L, R, maps, cores)
+    value = n * args.steps / t
+    line = {"impl": "reference", "metric": "stereo frames/sec detect+describe+match", "value": value, "unit": "stereo frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.config, "sample": f"{n} stereo frames per step", **{k: cfg[k] for k in ("W", "H", "max_kp", "threshold", "octaves", "n_lm")}},
+            "cpu_baseline": {"value": value, "unit": "stereo frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} stereo frames x {args.steps} steps, oracle port (OpenCV-BRISK restatement + reference match loops), {cores} threads"},
+            "e2e": {"value": value, "unit": "stereo frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="euroc", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from okvis2_b200 import lib as okl
+    from okvis2_b200.frontend import Frontend, MultiFrame
+    L_ = okl.lib()
+
+    W, H, B, ring = cfg["W"], cfg["H"], cfg["batch"], cfg["ring"]
+    warm = max(args.warmup, 3)
+    fe = Frontend(2, W, H, device=local_rank, max_batch=B)
+    fe.configure(threshold=cfg["threshold"], octaves=cfg["octaves"], max_keypoints=cfg["max_kp"])
+    ctx = fe.ctx
+    # ---- synthetic inputs: ring * B stereo frames per rank (ring * B * 2 * W * H bytes > L2 so steps do not hit in L2)
+    n_frames = ring * B
+    Lh, Rh = make_frames(cfg, n_frames, 1000 + 100 * rank)
+    in_bytes = 2 * n_frames * W * H
+    d_img = [torch.from_numpy(Lh).cuda(), torch.from_numpy(Rh).cuda()]
+    # landmark pools (one per camera) built from the features of frame 0, resident in HBM
+    mf = MultiFrame(2); maps = []; d_maps = []
+    for c, img in enumerate((Lh[0], Rh[0])):
+        mf.setImage(c, img); fe.detectAndDescribe(c, mf)
+        fr = mf.frames[c]
+        m = make_map(cfg, fr.keypoints, fr.descriptors, 40 + c); maps.append(m)
+        proj = np.broadcast_to(m["lm_proj"], (B,) + m["lm_proj"].shape).copy()
+        d_maps.append(dict(desc=torch.from_numpy(m["cand_desc"]).cuda(), lm=torch.from_numpy(m["cand_lm"]).cuda(),
+                           proj=torch.from_numpy(proj).cuda(), is3d=torch.from_numpy(m["lm_is3d"]).cuda()))
+    cap = C.c_int(0)
+    L_.okb_device_features(ctx, 0, None, None, None, C.byref(cap))
+    kp_cap = cap.value
+    d_out = [dict(dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), lm=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda")) for _ in range(2)]
+    streams = [torch.cuda.ExternalStream(L_.okb_stream(ctx, c)) for c in range(2)]
+
+    chain = [torch.cuda.Event() for _ in range(2)]
+
+    def device_step(s):
+        for c in range(2):
+            # one camera after the other (each batch already fills the GPU): clean per-kernel timing on each stream
+            streams[c].wait_event(chain[1 - c])
+            frames = d_img[c][(s % ring) * B:(s % ring + 1) * B]
+            okl.check(L_.okb_detect_describe_batch_device(ctx, c, B, frames.data_ptr()))
+            dm = d_maps[c]
+            okl.check(L_.okb_match_map3d_device(ctx, c, B, len(dm["lm"]), dm["desc"].data_ptr(), dm["lm"].data_ptr(),
+                                                len(dm["is3d"]), dm["proj"].data_ptr(), dm["is3d"].data_ptr(), 20.0, 60,
+                                                d_out[c]["dist"].data_ptr(), d_out[c]["lm"].data_ptr()))
+            chain[c].record(streams[c])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident, device-timed
+    for s in range(warm):
+        device_step(s)
+    okl.check(L_.okb_sync(ctx))
+    L_.okb_enable_timers(ctx, 1); L_.okb_reset_timers(ctx)
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    launches0 = L_.okb_launch_count(ctx)
+    ev0 = torch.cuda.Event(enable_timing=True); ev0.record(streams[0])
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for s in range(args.steps):
+        device_step(warm + s)
+    for c in range(2):
+        ends[c].record(streams[c])
+    barrier()
+    dev_ms = max(ev0.elapsed_time(e) for e in ends)
+    launches = L_.okb_launch_count(ctx) - launches0
+    clocks = sampler.stop()
+    ps_ms = C.c_double(); ps_l = C.c_int64(); tot = C.c_double()
+    ps_total_ms, ps_total_launches = 0.0, 0
+    for c in range(2):
+        L_.okb_get_timers(ctx, c, C.byref(ps_ms), C.byref(ps_l), C.byref(tot))
+        ps_total_ms += ps_ms.value; ps_total_launches += ps_l.value
+    L_.okb_enable_timers(ctx, 0)
+    if world > 1:
+        t = torch.tensor([dev_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
+    value = world * B * args.steps / (dev_ms * 1e-3)
+
+    # ---- roofline of the pyramid+score pass (all its launches: resize x3 + score), device time from CUDA events
+    ps_bytes = L_.okb_pyramid_score_bytes(ctx, 0)       # algorithmic bytes per image (actual layer sizes)
+    passes = 2 * args.steps                            # one pass per camera per step, B images each
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = ps_bytes * B * passes / (ps_total_ms * 1e-3) / 1e9 if ps_total_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": "pyramid+score pass (k_resize x3 + k_score)", "bytes_per_image": int(ps_bytes),
+                "images_per_pass": B, "ms_per_pass": ps_total_ms / passes, "launches_per_pass": ps_total_launches / passes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
+
+    # ---- e2e: host buffers through the Frontend mirror, per stereo frame, one host thread per camera for detection
+    from okvis2_b200.synth import rot
+    T0 = np.concatenate([np.eye(3), np.zeros((3, 1))], 1).reshape(12)
+    r1 = np.array([0.11, 0.0, 0.0]); T1 = np.concatenate([np.eye(3), -r1[:, None]], 1).reshape(12)
+    e2e_frames = min(n_frames, max(8, 2 * B))
+    h2d = d2h = 0
+
+    def e2e_frame(i):
+        nonlocal h2d, d2h
+        mf = MultiFrame(2)
+        mf.setImage(0, Lh[i]); mf.setImage(1, Rh[i])
+        th = threading.Thread(target=fe.detectAndDescribe, args=(1, mf))
+        th.start(); fe.detectAndDescribe(0, mf); th.join()
+        f0, f1 = mf.frames
+        e0 = pinhole_rays(f0.keypoints, cfg, np.eye(3)); e1 = pinhole_rays(f1.keypoints, cfg, np.eye(3))
+        v0 = np.ones(len(e0), np.uint8); v1 = np.ones(len(e1), np.uint8)
+        fe.matchStereo(f0.descriptors, v0, e0, f0.keypoints["size"] / cfg["f"], f1.descriptors, v1, e1,
+                       f1.keypoints["size"] / cfg["f"], np.zeros(3), r1, T0, T1)
+        for c, fr in enumerate((f0, f1)):
+            xy = np.stack([fr.keypoints["x"], fr.keypoints["y"]], 1).astype(np.float64)
+            m = maps[c]
+            fe.matchToMapByThread(fr.descriptors, xy, None, m["cand_desc"], m["cand_lm"], m["lm_proj"], m["lm_is3d"])
+            h2d += W * H + fr.descriptors.nbytes + xy.nbytes + m["cand_desc"].nbytes + m["cand_lm"].nbytes + m["lm_proj"].nbytes + m["lm_is3d"].nbytes
+            d2h += fr.keypoints.nbytes + fr.descriptors.nbytes + 8 * len(fr.keypoints)
+        h2d += f0.descriptors.nbytes + f1.descriptors.nbytes + 2 * (e0.nbytes + e1.nbytes)
+        d2h += 45 * len(f0.keypoints)
+
+    for i in range(3):
+        e2e_frame(i)
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_frames):
+        e2e_frame(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    e2e = {"value": world * e2e_frames / e2e_s, "unit": "stereo frames/s", "h2d_bytes_per_step": int(h2d / e2e_frames),
+           "d2h_bytes_per_step": int(d2h / e2e_frames), "step": "one stereo frame (2 detectAndDescribe + matchStereo + 2 matchToMap)",
+           "frames": e2e_frames}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = max(2, min(8, cores // 2))
+        cpu_run(cfg, Lh[:2], Rh[:2], maps, cores)
+        t = cpu_run(cfg, Lh[:n], Rh[:n], maps, cores)
+        cpu = {"value": n / t, "unit": "stereo frames/s", "cores": cores, "kind": "port",
+               "sample": f"{n} stereo frames (detect+describe both cameras + M1), oracle port, {cores} host threads"}
+
+    if rank == 0:
+        line = {"metric": "stereo frames/sec detect+describe+match", "value": value, "unit": "stereo frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": args.config, "stereo_frames_per_step_per_gpu": B, "l2_policy": f"inputs larger than L2: ring of {ring} batches = {in_bytes >> 20} MiB per GPU",
+                           "parallelism": "replicas (independent sequences per GPU)" if world > 1 else "single GPU",
+                           **{k: cfg[k] for k in ("W", "H", "max_kp", "threshold", "octaves", "n_lm")}},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line))
+    fe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -88,7 +88,8 @@ int okb_fetch_features(okb_context_t* ctx, int cam, int frame, okb_keypoint_t* k
 int okb_device_features(okb_context_t* ctx, int cam, const okb_keypoint_t** d_kp, const uint8_t** d_desc,
                         const int32_t** d_count, int* capacity);
 
-/* inspection hooks used by the parity tests (layer geometry and the intermediate maps of the last frame 0) */
+/* inspection hooks used by the parity tests: layer geometry, layer images and the dense AGAST score maps
+ * (b0 = largest threshold at which the pixel is still a 9-16 corner, 0 in the 3-pixel margin) of the last call */
 int okb_num_layers(okb_context_t* ctx, int cam);
 int okb_layer_info(okb_context_t* ctx, int cam, int layer, int* width, int* height, float* scale, float* offset);
 int okb_fetch_layer(okb_context_t* ctx, int cam, int frame, int layer, uint8_t* image_out, uint8_t* score_out);
@@ -158,14 +159,16 @@ int okb_match_place(okb_context_t* ctx, int D, int n_lm, const int32_t* lm_offse
 int okb_hamming_matrix(okb_context_t* ctx, int D, int n_a, const uint8_t* a, int n_b, const uint8_t* b,
                        uint16_t* out_dist);
 
-/* Device-resident M1 (benchmark "value" leg: inputs already in HBM): matches the features the last
- * okb_detect_describe_batch_device call left on the device for camera `cam`, frame `frame`, against a device-resident
- * landmark pool. All d_* pointers are device pointers; d_out_* hold kp-capacity entries (okb_device_features).
- * Asynchronous on okb_stream(ctx, cam). */
-int okb_match_map3d_device(okb_context_t* ctx, int cam, int frame, int n_cand, const uint8_t* d_cand_desc,
-                           const int32_t* d_cand_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
+/* Device-resident, batched M1 (benchmark "value" leg: inputs already in HBM): matches the features that the last
+ * okb_detect_describe_batch_device call left on the device for frames 0..n_frames-1 of camera `cam` against a
+ * device-resident landmark pool. d_lm_proj holds one projection table per frame (n_frames x n_lm x 2 doubles: the
+ * camera moves between frames). d_out_* hold n_frames x capacity entries (capacity from okb_device_features).
+ * All d_* pointers are device pointers. Asynchronous on okb_stream(ctx, cam). */
+int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand, const uint8_t* d_cand_desc,
+                           const int32_t* d_cand_lm, int n_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
                            double reprojection_threshold, uint32_t match_threshold, uint32_t* d_out_dist,
                            int32_t* d_out_lm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,8 @@ constexpr int kLongPairs = 870;
 
 struct LayerView {
   const uint8_t* img;  // pitch-linear u8
-  int w, h, pitch;
+  const uint8_t* b0;   // dense score map b0(q) of this layer (same size, pitch bpitch), zero in the 3-pixel margin
+  int w, h, pitch, bpitch;
   float scale, offset;
 };
 
@@ -99,12 +100,19 @@ OKB_UNROLL
   return imax(best_b - p, p - best_d) - 1;
 }
 
-// value every threshold-1 score query of the sequential algorithm returns (0 outside the 3-pixel margin)
-OKB_HD int b0(const LayerView& l, int x, int y)
+// value every threshold-1 score query of the sequential algorithm returns (0 outside the 3-pixel margin):
+// computed from the image ...
+OKB_HD int b0_compute(const LayerView& l, int x, int y)
 {
   if (x < 3 || y < 3 || x >= l.w - 3 || y >= l.h - 3) return 0;
   int s = bstar16(l.img + (size_t)y * l.pitch + x, l.pitch);
   return s < 1 ? 0 : (s > 254 ? 254 : s);
+}
+// ... or read from the dense map the score pass has written (what refinement and tie resolution use)
+OKB_HD int b0(const LayerView& l, int x, int y)
+{
+  if (x < 3 || y < 3 || x >= l.w - 3 || y >= l.h - 3) return 0;
+  return l.b0[(size_t)y * l.bpitch + x];
 }
 OKB_HD int b0_58(const LayerView& l, int x, int y)
 {
@@ -148,14 +156,6 @@ OKB_HD uint8_t half_pixel(const uint8_t* src, int pitch, int x, int y)
 {
   const uint8_t* r0 = src + (size_t)(2 * y) * pitch + 2 * x;
   return (uint8_t)(((int)r0[0] + r0[1] + r0[pitch] + r0[pitch + 1] + 2) >> 2);
-}
-
-// thresholded score (what the detection pass leaves in the score map): B* if B* >= threshold else 0
-OKB_HD int score_thresholded(const LayerView& l, int x, int y, int threshold)
-{
-  if (x < 3 || y < 3 || x >= l.w - 3 || y >= l.h - 3) return 0;
-  const int s = bstar16(l.img + (size_t)y * l.pitch + x, l.pitch);
-  return s < threshold ? 0 : (s > 254 ? 254 : s);
 }
 
 // keypoint size -> pattern scale index through the 63 host-built boundaries (count of boundaries <= size)

@@ -6,7 +6,7 @@
 //
 // Pipeline per batch of frames (blockIdx.z / blockIdx.y = frame):
 //   k_resize        INTER_AREA pyramid layers (2/3-sample and half-sample), table driven, bit-exact rounding
-//   k_score         AGAST 9-16 score map of every layer (thresholded u8), tiles staged in shared memory
+//   k_score         dense AGAST 9-16 score map b0 of every layer (u8), tiles staged in shared memory, 16x2 SIMD min/max
 //   k_nms           3x3 non-max candidates + tie flag, warp-ballot compaction
 //   k_refine        sub-pixel / scale refinement of every candidate (pure), cache-touch events of non-tie maxima
 //   k_resolve       order-exact resolution of tied maxima (touch-time map)
@@ -44,6 +44,7 @@ __device__ __forceinline__ void make_views(const DeviceLayers& dl, const uint8_t
       v.L[i].w = d.w; v.L[i].h = d.h; v.L[i].scale = d.scale; v.L[i].offset = d.offset_px;
       if (i == 0) { v.L[i].img = in0 + (size_t)frame * in_frame_stride; v.L[i].pitch = in_pitch; }
       else { v.L[i].img = ib + d.offset; v.L[i].pitch = d.pitch; }
+      v.L[i].b0 = sb + d.offset; v.L[i].bpitch = d.pitch;
       v.score[i] = sb + d.offset;
       v.touch[i] = tb ? tb + d.offset : nullptr;
     }
@@ -110,9 +111,39 @@ __device__ __forceinline__ int find_layer(const TileMap& tm, int tile)
   return l;
 }
 
+// Dense AGAST 9-16 score b0 = clamp(B*, 0, 254) of four horizontally adjacent pixels, two at a time in 16x2 SIMD
+// (VIMNMX3.U16x2): B* = max(max_arcs min_arc(ring) - p, p - min_arcs max_arc(ring)) - 1 over the 16 arcs of 9 pixels.
+__device__ __forceinline__ uint32_t u16x2_lo(uint32_t w) { return __byte_perm(w, 0, 0x4140); }  // (b0, b1)
+__device__ __forceinline__ uint32_t u16x2_hi(uint32_t w) { return __byte_perm(w, 0, 0x4342); }  // (b2, b3)
+
+__device__ __forceinline__ uint32_t b0_pair(const uint32_t (&v)[16], uint32_t p)
+{
+  uint32_t m3[16], M3[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    m3[i] = __vimin3_u16x2(v[i], v[(i + 1) & 15], v[(i + 2) & 15]);
+    M3[i] = __vimax3_u16x2(v[i], v[(i + 1) & 15], v[(i + 2) & 15]);
+  }
+  uint32_t m9[16], M9[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    m9[i] = __vimin3_u16x2(m3[i], m3[(i + 3) & 15], m3[(i + 6) & 15]);
+    M9[i] = __vimax3_u16x2(M3[i], M3[(i + 3) & 15], M3[(i + 6) & 15]);
+  }
+  uint32_t bb = __vimax3_u16x2(m9[0], m9[1], m9[2]), bd = __vimin3_u16x2(M9[0], M9[1], M9[2]);
+#pragma unroll
+  for (int i = 3; i < 15; i += 2) { bb = __vimax3_u16x2(bb, m9[i], m9[i + 1]); bd = __vimin3_u16x2(bd, M9[i], M9[i + 1]); }
+  bb = __vmaxu2(bb, m9[15]); bd = __vminu2(bd, M9[15]);
+  // per half: t = max(bb - p, p - bd, 0) computed without borrows; b0 = min(max(t, 1) - 1, 254)
+  const uint32_t tb = __vmaxu2(bb, p) - p;
+  const uint32_t td = p - __vminu2(bd, p);
+  const uint32_t t = __vmaxu2(tb, td);
+  return __vminu2(__vmaxu2(t, 0x00010001u) - 0x00010001u, 0x00FE00FEu);
+}
+
+// score map: tile = 64 x 32 pixels, 256 threads, each thread 2 rows x 4 pixels. Halo 3 (+1 for word alignment).
 __global__ void __launch_bounds__(256) k_score(DeviceLayers dl, TileMap tm, const uint8_t* in0, int in_pitch,
-                                               size_t in_frame_stride, uint8_t* img_block, uint8_t* score_block,
-                                               int threshold)
+                                               size_t in_frame_stride, uint8_t* img_block, uint8_t* score_block)
 {
   __shared__ __align__(16) uint8_t tile[kSmemH][kSmemW];
   const int frame = blockIdx.y;
@@ -143,40 +174,50 @@ __global__ void __launch_bounds__(256) k_score(DeviceLayers dl, TileMap tm, cons
   }
   __syncthreads();
   const int lx = (threadIdx.x & 15) * 4, ly = (threadIdx.x >> 4);
-#pragma unroll
+#pragma unroll 1
   for (int rr = 0; rr < 2; rr++) {
     const int yy = ly + rr * 16;
     const int y = y0 + yy;
     if (y >= d.h) continue;
-    uint32_t out = 0;
+    // words W0 (x-4..x-1), W1 (x..x+3), W2 (x+4..x+7) of the seven rows y-3..y+3
+    uint32_t lo[16], hi[16];
+    uint32_t W[7][3];
 #pragma unroll
-    for (int px = 0; px < 4; px++) {
-      const int x = x0 + lx + px;
-      int s = 0;
-      if (x >= 3 && y >= 3 && x < d.w - 3 && y < d.h - 3) {
-        const uint8_t* c = &tile[yy + 3][lx + px + 4];
-        const int p = c[0];
-        const int a0 = c[-3], a8 = c[3], a4 = c[-3 * kSmemW], a12 = c[3 * kSmemW];
-        const int hi = p + threshold, lo = p - threshold;
-        const bool br = (a0 > hi || a8 > hi) && (a4 > hi || a12 > hi);
-        const bool dk = (a0 < lo || a8 < lo) && (a4 < lo || a12 < lo);
-        if (br || dk) {
-          const int b = bstar16(c, kSmemW);
-          s = b < threshold ? 0 : (b > 254 ? 254 : b);
-        }
-      }
-      out |= (uint32_t)s << (8 * px);
+    for (int r = 0; r < 7; r++) {
+      const uint32_t* rowp = reinterpret_cast<const uint32_t*>(&tile[yy + r][lx]);
+      W[r][0] = rowp[0]; W[r][1] = rowp[1]; W[r][2] = rowp[2];
     }
+    // ring in AGAST order: (dx,dy) = (-3,0)(-3,-1)(-2,-2)(-1,-3)(0,-3)(1,-3)(2,-2)(3,-1)(3,0)(3,1)(2,2)(1,3)(0,3)(-1,3)(-2,2)(-3,1)
+#define OKB_RING(i, dx, dy)                                                                                            \
+    {                                                                                                                  \
+      const uint32_t w = (dx) < 0 ? __funnelshift_r(W[(dy) + 3][0], W[(dy) + 3][1], 8 * (4 + (dx)))                    \
+                                  : ((dx) > 0 ? __funnelshift_r(W[(dy) + 3][1], W[(dy) + 3][2], 8 * (dx)) : W[(dy) + 3][1]); \
+      lo[i] = u16x2_lo(w); hi[i] = u16x2_hi(w);                                                                        \
+    }
+    OKB_RING(0, -3, 0) OKB_RING(1, -3, -1) OKB_RING(2, -2, -2) OKB_RING(3, -1, -3) OKB_RING(4, 0, -3) OKB_RING(5, 1, -3)
+    OKB_RING(6, 2, -2) OKB_RING(7, 3, -1) OKB_RING(8, 3, 0) OKB_RING(9, 3, 1) OKB_RING(10, 2, 2) OKB_RING(11, 1, 3)
+    OKB_RING(12, 0, 3) OKB_RING(13, -1, 3) OKB_RING(14, -2, 2) OKB_RING(15, -3, 1)
+#undef OKB_RING
+    const uint32_t c = W[3][1];
+    const uint32_t r_lo = b0_pair(lo, u16x2_lo(c));
+    const uint32_t r_hi = b0_pair(hi, u16x2_hi(c));
+    uint32_t out = __byte_perm(r_lo, r_hi, 0x6420);
+    // zero the 3-pixel margin (and anything beyond the image)
     const int x = x0 + lx;
-    if (x + 3 < d.w && (d.pitch & 3) == 0) *reinterpret_cast<uint32_t*>(score + (size_t)y * d.pitch + x) = out;
-    else for (int b = 0; b < 4; b++) if (x + b < d.w) score[(size_t)y * d.pitch + x + b] = (uint8_t)(out >> (8 * b));
+    uint32_t mask = 0;
+    if (y >= 3 && y < d.h - 3) {
+#pragma unroll
+      for (int px = 0; px < 4; px++) if (x + px >= 3 && x + px < d.w - 3) mask |= 0xffu << (8 * px);
+    }
+    out &= mask;
+    if (x < d.pitch) *reinterpret_cast<uint32_t*>(score + (size_t)y * d.pitch + x) = out;  // pitch is a multiple of 64
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // 3x3 non-max candidates. Same tiling as k_score. One u32 per candidate: time key | tie << 31.
 __global__ void __launch_bounds__(256) k_nms(DeviceLayers dl, TileMap tm, const uint8_t* score_block, uint32_t* cand,
-                                             int32_t* cand_count, int cand_cap)
+                                             int32_t* cand_count, int cand_cap, int threshold)
 {
   const int frame = blockIdx.y;
   const int layer = find_layer(tm, blockIdx.x);
@@ -195,7 +236,7 @@ __global__ void __launch_bounds__(256) k_nms(DeviceLayers dl, TileMap tm, const 
       const int c = (w >> (8 * px)) & 255;
       const int x = x0 + px;
       bool is_c = false, tie = false;
-      if (c > 0 && x >= 3 && x < d.w - 3) {
+      if (c >= threshold && x >= 3 && x < d.w - 3) {  // the map is the dense b0; only scores >= threshold are corners
         const uint8_t* s = score + (size_t)y * d.pitch + x;
         is_c = true;
 #pragma unroll
@@ -253,10 +294,12 @@ __global__ void __launch_bounds__(128) k_refine(DeviceLayers dl, const uint8_t* 
 {
   const int frame = blockIdx.y;
   const int n = min(cand_count[frame], cand_cap);
+  if (blockIdx.x * blockDim.x >= n) return;
+  __shared__ FrameViews v;  // dynamically indexed by layer: keep it out of local memory
+  if (threadIdx.x == 0) make_views(dl, in0, in_pitch, in_frame_stride, img_block, score_block, touch_block, frame, v);
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  FrameViews v;
-  make_views(dl, in0, in_pitch, in_frame_stride, img_block, score_block, touch_block, frame, v);
   const uint32_t c = cand[(size_t)frame * cand_cap + i];
   const uint32_t key = c & 0x7fffffffu;
   const int tie = (int)(c >> 31);
@@ -292,17 +335,24 @@ __device__ void bitonic_sort_u64(unsigned long long* a, int n)
 }
 
 constexpr int kMaxTies = 4096;
+constexpr int kMaxBlockers = 12;
+constexpr int kResolveSmem = kMaxTies * (8 + 2 * kMaxBlockers + 3);
 
 // One CTA per frame. Resolves, in dependency rounds, the candidates whose 2-D maximum test ties with a neighbour:
 // their outcome depends on which sub-threshold scores the sequential algorithm had already cached when it reached them.
-__global__ void __launch_bounds__(256) k_resolve(DeviceLayers dl, const uint8_t* in0, int in_pitch, size_t in_frame_stride,
-                                                 uint8_t* img_block, uint8_t* score_block, uint32_t* touch_block,
+// A tie waits only for EARLIER ties whose cache touches can reach its 5x5 window: same layer within 4 px, or the layer
+// below through the window of its above-scan. The (few) possible blockers of every tie are listed once; a round is
+// then a handful of shared-memory reads per unresolved tie.
+__global__ void __launch_bounds__(256) k_resolve(DeviceLayers dl, const uint8_t* score_block, uint32_t* touch_block,
                                                  const int32_t* cand_count, int cand_cap, CandRecord* rec,
-                                                 uint32_t epoch, int32_t* status)
+                                                 uint32_t epoch, int threshold, int32_t* status)
 {
-  __shared__ unsigned long long ties[kMaxTies];  // key << 32 | record index, sorted
-  __shared__ int8_t state[kMaxTies];
-  __shared__ int8_t newly[kMaxTies];
+  extern __shared__ unsigned long long resolve_smem[];
+  unsigned long long* ties = resolve_smem;                                   // key << 32 | record index, sorted
+  uint16_t (*blockers)[kMaxBlockers] = reinterpret_cast<uint16_t (*)[kMaxBlockers]>(ties + kMaxTies);
+  int8_t* state = reinterpret_cast<int8_t*>(blockers + kMaxTies);            // 0 unresolved, 1 maximum, 2 rejected
+  int8_t* newly = state + kMaxTies;
+  int8_t* n_block = newly + kMaxTies;                                        // -1: list overflowed, scan every round
   __shared__ int n_ties, n_unresolved, layer_start[kMaxLayers + 1];
   const int frame = blockIdx.x;
   const int n = min(cand_count[frame], cand_cap);
@@ -333,49 +383,61 @@ __global__ void __launch_bounds__(256) k_resolve(DeviceLayers dl, const uint8_t*
   }
   if (threadIdx.x == 0) n_unresolved = T;
   __syncthreads();
-  FrameViews v;
-  make_views(dl, in0, in_pitch, in_frame_stride, img_block, score_block, touch_block, frame, v);
+  // enumerate the possible blockers of tie ti; F(u) returns true to stop
+  auto for_each_blocker = [&](int ti, auto F) {
+    const uint32_t key = (uint32_t)(ties[ti] >> 32);
+    const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+    {
+      const unsigned long long lo_key = (unsigned long long)time_key(layer, 0, max(y - 4, 0)) << 32;
+      int lo = layer_start[layer], hi = ti;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < lo_key) lo = mid + 1; else hi = mid; }
+      for (int u = lo; u < ti; u++) {
+        const int ux = (int)((uint32_t)(ties[u] >> 32) & 2047);
+        if (abs(ux - x) <= 4) if (F(u)) return;   // |dy| <= 4 by the key range
+      }
+    }
+    if (layer > 0) {
+      // rows of the layer below that can map into [y-2, y+2] (+ scan margins); the ratio is 3/2 or 4/3
+      const int uy_lo = max((y - 5) * 4 / 3 - 3, 0), uy_hi = (y + 5) * 3 / 2 + 4;
+      const unsigned long long lo_key = (unsigned long long)time_key(layer - 1, 0, min(uy_lo, 2047)) << 32;
+      int lo = layer_start[layer - 1], hi = layer_start[layer];
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < lo_key) lo = mid + 1; else hi = mid; }
+      for (int u = lo; u < layer_start[layer]; u++) {
+        const uint32_t uk = (uint32_t)(ties[u] >> 32);
+        const int uy = (int)((uk >> 11) & 2047), ux = (int)(uk & 2047);
+        if (uy > uy_hi) break;
+        // cheap integer pre-test (the exact window follows): centre maps to about 2/3 .. 3/4 of (ux, uy)
+        if (abs(ux * 3 / 4 - x) > 8 + ux / 12) continue;
+        ScanIter it; above_window(layer - 1, ux, uy, it);
+        const int xa = (int)it.x_1 - 1, xb = (int)it.x1 + 2, ya = (int)it.y_1 - 1, yb = (int)it.y1 + 2;
+        if (!(x + 2 < xa || x - 2 > xb || y + 2 < ya || y - 2 > yb)) if (F(u)) return;
+      }
+    }
+  };
+  for (int ti = threadIdx.x; ti < T; ti += blockDim.x) {
+    int nb = 0;
+    for_each_blocker(ti, [&](int u) {
+      if (nb < kMaxBlockers) { blockers[ti][nb++] = (uint16_t)u; return false; }
+      nb = -1; return true;
+    });
+    n_block[ti] = (int8_t)nb;
+  }
+  __syncthreads();
+  const uint8_t* score_frame = score_block + (size_t)frame * dl.frame_stride;
   uint32_t* touch_frame = touch_block + (size_t)frame * dl.frame_stride;
   while (true) {
     for (int ti = threadIdx.x; ti < T; ti += blockDim.x) {
       newly[ti] = 0;
       if (state[ti] != 0) continue;
+      bool blocked = false;
+      const int nb = n_block[ti];
+      if (nb >= 0) { for (int i = 0; i < nb; i++) if (state[blockers[ti][i]] == 0) { blocked = true; break; } }
+      else for_each_blocker(ti, [&](int u) { if (state[u] == 0) { blocked = true; return true; } return false; });
+      if (blocked) continue;
       const uint32_t key = (uint32_t)(ties[ti] >> 32);
       const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
-      bool blocked = false;
-      // earlier unresolved ties of the same layer within 4 pixels
-      {
-        const int ylo = max(y - 4, 0);
-        const unsigned long long lo_key = (unsigned long long)time_key(layer, 0, ylo) << 32;
-        int lo = layer_start[layer], hi = ti;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < lo_key) lo = mid + 1; else hi = mid; }
-        for (int u = lo; u < ti && !blocked; u++) {
-          if (state[u] != 0) continue;
-          const uint32_t uk = (uint32_t)(ties[u] >> 32);
-          const int ux = (int)(uk & 2047);
-          if (abs(ux - x) <= 4) blocked = true;  // |dy| <= 4 by the key range
-        }
-      }
-      // unresolved ties of the layer below whose above-scan can reach the 5x5 window
-      if (!blocked && layer > 0) {
-        // rows of the layer below that can map into [y-2, y+2] (+ scan margins); the ratio is 3/2 or 4/3
-        const int uy_lo = max((y - 5) * 4 / 3 - 3, 0), uy_hi = (y + 5) * 3 / 2 + 4;
-        const unsigned long long lo_key = (unsigned long long)time_key(layer - 1, 0, min(uy_lo, 2047)) << 32;
-        int lo = layer_start[layer - 1], hi = layer_start[layer];
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < lo_key) lo = mid + 1; else hi = mid; }
-        for (int u = lo; u < layer_start[layer] && !blocked; u++) {
-          const uint32_t uk = (uint32_t)(ties[u] >> 32);
-          const int uy = (int)((uk >> 11) & 2047), ux = (int)(uk & 2047);
-          if (uy > uy_hi) break;
-          if (state[u] != 0) continue;
-          ScanIter it; above_window(layer - 1, ux, uy, it);
-          const int xa = (int)it.x_1 - 1, xb = (int)it.x1 + 2, ya = (int)it.y_1 - 1, yb = (int)it.y1 + 2;
-          if (!(x + 2 < xa || x - 2 > xb || y + 2 < ya || y - 2 > yb)) blocked = true;
-        }
-      }
-      if (blocked) continue;
       const DeviceLayer d = dl.l[layer];
-      const uint8_t* sc = v.score[layer];
+      const uint8_t* sc = score_frame + d.offset;
       const uint32_t* tm = touch_frame + d.offset;
       int m[5][5];
 #pragma unroll
@@ -383,10 +445,10 @@ __global__ void __launch_bounds__(256) k_resolve(DeviceLayers dl, const uint8_t*
 #pragma unroll
         for (int dx = -2; dx <= 2; dx++) {
           const int xx = x + dx, yy = y + dy;
-          int val = sc[(size_t)yy * d.pitch + xx];
-          if (val == 0) {
+          int val = sc[(size_t)yy * d.pitch + xx];  // dense b0 = what the cache holds once the pixel was touched
+          if (val < threshold) {
             const uint32_t e = __ldcg(&tm[(size_t)yy * d.pitch + xx]);
-            if (touched_before(e, epoch, key)) val = b0(v.L[layer], xx, yy);
+            if (!touched_before(e, epoch, key)) val = 0;
           }
           m[dy + 2][dx + 2] = val;
         }
@@ -453,7 +515,8 @@ __global__ void __launch_bounds__(1024) k_finalize(const int32_t* cand_count, in
                                                    int max_kp, int kp_cap, okb_keypoint_t* kp_out, int32_t* kscale_out,
                                                    int32_t* count_out, int32_t* status)
 {
-  extern __shared__ unsigned long long keys[];  // kSortCap sorted (key << 32 | record index)
+  extern __shared__ unsigned long long keys[];  // kSortCap sorted (key << 32 | record index), then kSortCap response bits
+  uint32_t* resp = reinterpret_cast<uint32_t*>(keys + kSortCap);
   __shared__ uint8_t flag[kSortCap];
   __shared__ int n_valid, hist[256], sh_scan[33];
   __shared__ uint32_t sel_prefix;
@@ -478,6 +541,8 @@ __global__ void __launch_bounds__(1024) k_finalize(const int32_t* cand_count, in
   for (int i = V + threadIdx.x; i < P; i += blockDim.x) keys[i] = ~0ull;
   __syncthreads();
   if (V > 1) bitonic_sort_u64(keys, P);
+  for (int i = threadIdx.x; i < V; i += blockDim.x) resp[i] = float_order_bits(R[(int)(keys[i] & 0xffffffffu)].response);
+  __syncthreads();
   // ---- strongest max_kp: radix select of the max_kp-th largest response
   const bool capped = max_kp > 0 && V > max_kp;
   uint32_t thr_bits = 0; int n_equal_keep = 0;
@@ -490,7 +555,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const int32_t* cand_count, in
       const uint32_t prefix = sel_prefix;
       const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
       for (int i = threadIdx.x; i < V; i += blockDim.x) {
-        const uint32_t rb = float_order_bits(R[(int)(keys[i] & 0xffffffffu)].response);
+        const uint32_t rb = resp[i];
         if ((rb & himask) == (prefix & himask)) atomicAdd(&hist[(rb >> shift) & 255], 1);
       }
       __syncthreads();
@@ -510,10 +575,10 @@ __global__ void __launch_bounds__(1024) k_finalize(const int32_t* cand_count, in
   int total = 0;
   if (capped) {
     int my_eq = 0;
-    for (int i = beg; i < end; i++) my_eq += (float_order_bits(R[(int)(keys[i] & 0xffffffffu)].response) == thr_bits);
+    for (int i = beg; i < end; i++) my_eq += (resp[i] == thr_bits);
     int eq_before = block_exclusive_scan_1024(my_eq, sh_scan, total);
     for (int i = beg; i < end; i++) {
-      const uint32_t rb = float_order_bits(R[(int)(keys[i] & 0xffffffffu)].response);
+      const uint32_t rb = resp[i];
       bool keep = rb > thr_bits;
       if (rb == thr_bits) { keep = eq_before < n_equal_keep; eq_before++; }
       flag[i] = keep;
@@ -580,22 +645,30 @@ __global__ void __launch_bounds__(256) k_integral_rows(const uint8_t* in0, int i
     carry += __shfl_sync(0xffffffffu, incl, 31);
   }
 }
-__global__ void __launch_bounds__(128) k_integral_cols(int W, int H, int32_t* integral, int ipitch)
+// Column pass: one CTA per strip of 32 columns, 32 warps each owning a band of rows: band sums -> prefix over the
+// bands in shared memory -> every warp rewrites its band with the carried-in prefix (two coalesced sweeps, 32x the
+// parallelism of one thread per column).
+__global__ void __launch_bounds__(1024) k_integral_cols(int W, int H, int32_t* integral, int ipitch)
 {
+  __shared__ int band[32][33];
   const int frame = blockIdx.y;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (x > W) return;
-  int32_t* I = integral + (size_t)frame * ipitch * (H + 1) + x;
-  int acc = 0;
-  int y = 1;
-  for (; y + 7 <= H; y += 8) {
-    int v[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = I[(size_t)(y + i) * ipitch];
-#pragma unroll
-    for (int i = 0; i < 8; i++) { acc += v[i]; I[(size_t)(y + i) * ipitch] = acc; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + lane + 1;
+  const int rows = (H + 31) / 32;
+  const int y0 = 1 + warp * rows, y1 = min(y0 + rows, H + 1);
+  int32_t* I = integral + (size_t)frame * ipitch * (H + 1);
+  int sum = 0;
+  if (x <= W) for (int y = y0; y < y1; y++) sum += I[(size_t)y * ipitch + x];
+  band[warp][lane] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    int acc = 0;
+    for (int w = 0; w < 32; w++) { const int v = band[w][lane]; band[w][lane] = acc; acc += v; }
   }
-  for (; y <= H; y++) { acc += I[(size_t)y * ipitch]; I[(size_t)y * ipitch] = acc; }
+  __syncthreads();
+  if (x > W) return;
+  int acc = band[warp][lane];
+  for (int y = y0; y < y1; y++) { acc += I[(size_t)y * ipitch + x]; I[(size_t)y * ipitch + x] = acc; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -731,7 +804,8 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMallocHost(&ws.h_count, 4 * B));
   OKB_CUDA(cudaMallocHost(&ws.h_status, 4 * B));
   for (int i = 0; i < 4; i++) OKB_CUDA(cudaEventCreate(&ws.ev[i]));
-  OKB_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8));
+  OKB_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 12));
+  OKB_CUDA(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, kResolveSmem));
   return OKB_OK;
 }
 
@@ -808,26 +882,26 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   }
   for (int i = ws.n_layers + 1; i <= kMaxLayers; i++) tm.tile_prefix[i] = tm.tile_prefix[ws.n_layers];
   const int n_tiles = tm.tile_prefix[ws.n_layers];
-  k_score<<<dim3(n_tiles, B), 256, 0, st>>>(ws.dl, tm, d_images, src_pitch, in_stride, ws.d_img, ws.d_score, c.threshold);
+  k_score<<<dim3(n_tiles, B), 256, 0, st>>>(ws.dl, tm, d_images, src_pitch, in_stride, ws.d_img, ws.d_score);
   ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
   if (ctx->timers_on) cudaEventRecord(ws.ev[1], st);
   // ---- candidates, refinement, tie resolution, selection
   OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, 4 * B, st));
   OKB_CUDA(cudaMemsetAsync(ws.d_status, 0, 4 * B, st));
-  k_nms<<<dim3(n_tiles, B), 256, 0, st>>>(ws.dl, tm, ws.d_score, ws.d_cand, ws.d_cand_count, ws.cand_cap);
+  k_nms<<<dim3(n_tiles, B), 256, 0, st>>>(ws.dl, tm, ws.d_score, ws.d_cand, ws.d_cand_count, ws.cand_cap, c.threshold);
   k_refine<<<dim3((ws.cand_cap + 127) / 128, B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
                                                                ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap,
                                                                ws.d_rec, c.threshold, ws.epoch);
-  k_resolve<<<B, 256, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score, ws.d_touch, ws.d_cand_count,
-                               ws.cand_cap, ws.d_rec, ws.epoch, ws.d_status);
-  k_finalize<<<B, 1024, kSortCap * 8, st>>>(ws.d_cand_count, ws.cand_cap, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,
+  k_resolve<<<B, 256, kResolveSmem, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_cand_count, ws.cand_cap, ws.d_rec, ws.epoch, c.threshold,
+                               ws.d_status);
+  k_finalize<<<B, 1024, kSortCap * 12, st>>>(ws.d_cand_count, ws.cand_cap, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,
                                             W, H, c.max_keypoints, ws.kp_cap, ws.d_kp, ws.d_kscale, ws.d_count, ws.d_status);
   ctx->launches += 4;
   if (ctx->timers_on) cudaEventRecord(ws.ev[2], st);
   // ---- descriptors
   const int ipitch = W + 1;
   k_integral_rows<<<dim3((H + 7) / 8, B), 256, 0, st>>>(d_images, src_pitch, in_stride, W, H, ws.d_integral, ipitch);
-  k_integral_cols<<<dim3((W + 127) / 128, B), 128, 0, st>>>(W, H, ws.d_integral, ipitch);
+  k_integral_cols<<<dim3((W + 31) / 32, B), 1024, 0, st>>>(W, H, ws.d_integral, ipitch);
   k_describe<<<dim3((ws.kp_cap + 3) / 4, B), 128, 0, st>>>(d_images, src_pitch, in_stride, H, ws.d_integral, ipitch,
                                                            ctx->d_pattern, ctx->d_short_pairs, ctx->d_long_pairs, ws.d_kp,
                                                            ws.d_kscale, ws.d_count, ws.kp_cap, ws.d_desc);

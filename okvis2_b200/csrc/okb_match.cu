@@ -97,6 +97,8 @@ struct MatchArgs {
   const uint8_t* c_valid; const double* c_sof; const double* c_cos26; const double* c_cos6;
   double T0[12], T1[12];
   uint32_t thr;
+  // batched device form (blockIdx.y = frame): element strides of the per-frame arrays, 0 for the single-frame host form
+  size_t q_stride, proj_stride;
   uint32_t* out_dist; int32_t* out_idx; double* out_hp; uint8_t* out_init; int32_t* out_ctr;
 };
 
@@ -120,6 +122,24 @@ __device__ __forceinline__ void stage_tile(const uint8_t* c_desc, int nc, int ti
     s_desc[w][i / D16] = v;
   }
 }
+// asynchronous variant (cp.async / LDGSTS, 16 bytes per request, zero fill past the end); completes with cp_async_wait
+template <int D16>
+__device__ __forceinline__ void stage_tile_async(const uint8_t* c_desc, int nc, int tile0, uint4 (*s_desc)[kTile])
+{
+  const uint4* g = reinterpret_cast<const uint4*>(c_desc);
+  for (int i = threadIdx.x; i < kTile * D16; i += blockDim.x) {
+    const int c = tile0 + i / D16, w = i % D16;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_desc[w][i / D16]);
+    const bool ok = c < nc;
+    const uint4* src = g + (ok ? (size_t)c * D16 + w : 0);
+    const int src_bytes = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int D16>
 __device__ __forceinline__ uint32_t hamming(const uint4 (&qd)[D16], uint4 (*s_desc)[kTile], int ci)
 {
@@ -133,56 +153,79 @@ __device__ __forceinline__ uint32_t hamming(const uint4 (&qd)[D16], uint4 (*s_de
   return d;
 }
 
-// M1: reprojection pre-gate (fp64) then lexicographic (distance, candidate) minimum
+// M1: reprojection pre-gate (fp64) then lexicographic (distance, candidate) minimum.
+// Candidate tiles are double buffered: descriptors by cp.async, projections through registers one tile ahead and the
+// landmark index two tiles ahead, so that the dependent loads c_lm -> is3d/proj never stall the compute of a tile.
 template <int D16>
 __global__ void __launch_bounds__(256) k_match_map3d(MatchArgs a)
 {
-  __shared__ uint4 s_desc[D16][kTile];
-  __shared__ double2 s_proj[kTile];
+  __shared__ uint4 s_desc[2][D16][kTile];
+  __shared__ double2 s_proj[2][kTile];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 8 + warp;
-  const int nq = a.q_count ? min(*a.q_count, a.nq) : a.nq;
+  const size_t fq = (size_t)blockIdx.y * a.q_stride;       // first query slot of this frame
+  const double* lm_proj = a.lm_proj + (size_t)blockIdx.y * a.proj_stride;
+  const int nq = a.q_count ? min(a.q_count[blockIdx.y], a.nq) : a.nq;
+  if (blockIdx.x * 8 >= nq && a.q_count) {  // whole CTA beyond the frame's keypoint count: only the defaults
+    if (q < a.nq && lane == 0) { a.out_dist[fq + q] = a.thr; a.out_idx[fq + q] = -1; }
+    return;
+  }
   const bool active = q < nq && (a.q_use == nullptr || a.q_use[q]);
   uint4 qd[D16];
   double kx = 0, ky = 0;
   if (active) {
-    load_query<D16>(a.q_desc, q, qd);
-    if (a.q_kp) { kx = (double)a.q_kp[q].x; ky = (double)a.q_kp[q].y; }  // MultiFrame::getKeypoint: float -> double
+    load_query<D16>(a.q_desc, (int)(fq + q), qd);
+    if (a.q_kp) { kx = (double)a.q_kp[fq + q].x; ky = (double)a.q_kp[fq + q].y; }  // MultiFrame::getKeypoint: float -> double
     else { kx = a.q_xy[2 * q]; ky = a.q_xy[2 * q + 1]; }
   }
   unsigned long long best = ((unsigned long long)a.thr << 32);
-  for (int tile0 = 0; tile0 < a.nc; tile0 += kTile) {
-    __syncthreads();
-    stage_tile<D16>(a.c_desc, a.nc, tile0, s_desc);
-    {
-      const int c = tile0 + threadIdx.x;
-      double2 p = make_double2(INFINITY, INFINITY);
-      if (c < a.nc) { const int lm = a.c_lm[c]; if (a.lm_is3d[lm]) p = make_double2(a.lm_proj[2 * lm], a.lm_proj[2 * lm + 1]); }
-      s_proj[threadIdx.x] = p;
+  const int n_tiles = (a.nc + kTile - 1) / kTile;
+  const double2 far = make_double2(INFINITY, INFINITY);
+  auto load_lm = [&](int tile) { const int c = tile * kTile + (int)threadIdx.x; return (tile < n_tiles && c < a.nc) ? __ldg(&a.c_lm[c]) : -1; };
+  auto load_proj = [&](int lm) {
+    double2 p = far;
+    if (lm >= 0 && a.lm_is3d[lm]) p = make_double2(lm_proj[2 * lm], lm_proj[2 * lm + 1]);
+    return p;
+  };
+  int lm_next = load_lm(1);
+  double2 proj_cur = load_proj(load_lm(0));
+  if (n_tiles > 0) stage_tile_async<D16>(a.c_desc, a.nc, 0, s_desc[0]);
+  for (int t = 0; t < n_tiles; t++) {
+    const int buf = t & 1;
+    s_proj[buf][threadIdx.x] = proj_cur;
+    if (t + 1 < n_tiles) {
+      stage_tile_async<D16>(a.c_desc, a.nc, (t + 1) * kTile, s_desc[buf ^ 1]);
+      proj_cur = load_proj(lm_next);   // consumed at the top of the next iteration
+      lm_next = load_lm(t + 2);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     if (active) {
+      const int tile0 = t * kTile;
 #pragma unroll 2
       for (int j = 0; j < kTile / 32; j++) {
         const int ci = j * 32 + lane;
-        const double2 p = s_proj[ci];
+        const double2 p = s_proj[buf][ci];
         const double dx = p.x - kx, dy = p.y - ky;
         const double d2 = dx * dx + dy * dy;
         if (!(d2 > a.thr_sq)) {
-          const uint32_t d = hamming<D16>(qd, s_desc, ci);
+          const uint32_t d = hamming<D16>(qd, s_desc[buf], ci);
           const unsigned long long key = ((unsigned long long)d << 32) | (unsigned)(tile0 + ci);
           if (key < best) best = key;
         }
       }
     }
+    __syncthreads();
   }
   if (q >= a.nq) return;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); if (t < best) best = t; }
   if (lane == 0) {
     const uint32_t d = (uint32_t)(best >> 32);
-    if (active && d < a.thr) { a.out_dist[q] = d; a.out_idx[q] = a.c_lm[(uint32_t)best]; }
-    else { a.out_dist[q] = a.thr; a.out_idx[q] = -1; }
+    if (active && d < a.thr) { a.out_dist[fq + q] = d; a.out_idx[fq + q] = a.c_lm[(uint32_t)best]; }
+    else { a.out_dist[fq + q] = a.thr; a.out_idx[fq + q] = -1; }
   }
 }
 
@@ -238,7 +281,7 @@ __global__ void __launch_bounds__(256) k_match_place(int n_lm, const int32_t* lm
 template <int D16, int MODE>
 __global__ void __launch_bounds__(256) k_match_gated(MatchArgs a)
 {
-  __shared__ uint4 s_desc[D16][kTile];
+  __shared__ uint4 s_desc2[2][D16][kTile];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 8 + warp;
   const bool active = q < a.nq && (a.q_use == nullptr || a.q_use[q]);
@@ -257,12 +300,15 @@ __global__ void __launch_bounds__(256) k_match_gated(MatchArgs a)
   V3 best_hp = V3{0, 0, 0}; bool have_hp = false; bool best_init = false;
   int ctr = 0, skip_lm = -1;
   const V3 r0 = v3(a.r0), r1 = v3(a.r1);
-  for (int tile0 = 0; tile0 < a.nc; tile0 += kTile) {
+  const int n_tiles = (a.nc + kTile - 1) / kTile;
+  if (n_tiles > 0) stage_tile_async<D16>(a.c_desc, a.nc, 0, s_desc2[0]);
+  for (int tt = 0; tt < n_tiles; tt++) {
+    const int tile0 = tt * kTile;
+    uint4 (*s_desc)[kTile] = s_desc2[tt & 1];
+    if (tt + 1 < n_tiles) { stage_tile_async<D16>(a.c_desc, a.nc, tile0 + kTile, s_desc2[(tt & 1) ^ 1]); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
     __syncthreads();
-    stage_tile<D16>(a.c_desc, a.nc, tile0, s_desc);
-    __syncthreads();
-    if (!active) continue;
-    for (int j = 0; j < kTile / 32; j++) {
+    for (int j = 0; active && j < kTile / 32; j++) {
       const int ci = j * 32 + lane, c = tile0 + ci;
       if (tile0 + j * 32 >= a.nc) break;
       uint32_t d = 0xffffu;
@@ -332,6 +378,7 @@ __global__ void __launch_bounds__(256) k_match_gated(MatchArgs a)
         m &= __ballot_sync(0xffffffffu, d < best);
       }
     }
+    __syncthreads();  // everyone is done with this buffer before the next prefetch overwrites it
   }
   if (q >= a.nq) return;
   if (lane == 0) {
@@ -583,22 +630,22 @@ int okb_match_stereo(okb_context_t* ctx, int D, int n0, const uint8_t* desc0, co
                      r_WC1, T_CW0, T_CW1, match_threshold, out_k1, out_dist, out_hp_W, out_initialisable, "okb_match_stereo");
 }
 
-int okb_match_map3d_device(okb_context_t* ctx, int cam, int frame, int n_cand, const uint8_t* d_cand_desc,
-                           const int32_t* d_cand_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
+int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand, const uint8_t* d_cand_desc,
+                           const int32_t* d_cand_lm, int n_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
                            double reprojection_threshold, uint32_t match_threshold, uint32_t* d_out_dist, int32_t* d_out_lm)
 {
-  OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams && n_cand >= 0 && d_out_dist && d_out_lm, "okb_match_map3d_device");
+  OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams && n_cand >= 0 && n_lm >= 0 && d_out_dist && d_out_lm, "okb_match_map3d_device");
   CamWorkspace& ws = ctx->cams[cam];
-  OKB_CHECK_ARGS(frame >= 0 && frame < ws.cfg.max_batch, "okb_match_map3d_device");
+  OKB_CHECK_ARGS(n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_map3d_device");
   OKB_CHECK_ARGS(n_cand == 0 || (d_cand_desc && d_cand_lm && d_lm_proj && d_lm_is3d), "okb_match_map3d_device");
   OKB_CUDA(cudaSetDevice(ctx->device));
   MatchArgs a; memset(&a, 0, sizeof(a));
-  a.nq = ws.kp_cap; a.q_count = ws.d_count + frame;
-  a.q_desc = ws.d_desc + (size_t)frame * ws.kp_cap * 64; a.q_kp = ws.d_kp + (size_t)frame * ws.kp_cap;
+  a.nq = ws.kp_cap; a.q_count = ws.d_count; a.q_stride = (size_t)ws.kp_cap; a.proj_stride = (size_t)n_lm * 2;
+  a.q_desc = ws.d_desc; a.q_kp = ws.d_kp;
   a.nc = n_cand; a.c_desc = d_cand_desc; a.c_lm = d_cand_lm; a.lm_proj = d_lm_proj; a.lm_is3d = d_lm_is3d;
   a.thr = match_threshold; a.thr_sq = reprojection_threshold * reprojection_threshold;
   a.out_dist = d_out_dist; a.out_idx = d_out_lm;
-  k_match_map3d<4><<<(ws.kp_cap + 7) / 8, 256, 0, ws.stream>>>(a);
+  k_match_map3d<4><<<dim3((ws.kp_cap + 7) / 8, n_frames), 256, 0, ws.stream>>>(a);
   ctx->launches++;
   OKB_CUDA(cudaGetLastError());
   return OKB_OK;

@@ -72,7 +72,7 @@ _PROTOS = {
     "okb_match_stereo": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
     "okb_match_place": (i32, [vp, i32, i32, vp, vp, i32, vp, u32, vp, vp]),
     "okb_hamming_matrix": (i32, [vp, i32, i32, vp, i32, vp, vp]),
-    "okb_match_map3d_device": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, f64, u32, vp, vp]),
+    "okb_match_map3d_device": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, vp, vp]),
 }
 
 

@@ -64,6 +64,15 @@ def resize_area(src, dw, dh):
     return dst
 
 
+def dense_b0(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    f = lib().okvo_dense_b0
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    f(img.ctypes.data, img.shape[1], img.shape[0], out.ctypes.data)
+    return out
+
+
 def integral(img):
     img = np.ascontiguousarray(img, np.uint8)
     H, W = img.shape

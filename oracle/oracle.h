@@ -18,6 +18,7 @@ typedef struct okvo_brisk okvo_brisk_t;
 void okvo_resize_area(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);
 int okvo_oast916_bstar(const uint8_t* p, int stride);
 int okvo_agast58_bstar(const uint8_t* p, int stride);
+void okvo_dense_b0(const uint8_t* img, int w, int h, uint8_t* out);
 void okvo_integral(const uint8_t* img, int W, int H, int stride, int32_t* integral);
 
 okvo_brisk_t* okvo_brisk_create(int threshold, int octaves, float pattern_scale);

@@ -55,11 +55,12 @@ extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int th
     init(HL[i + 1], HL[i - 1].w / 2, HL[i - 1].h / 2, HL[i - 1].scale * 2); resize_layer(HL[i - 1], HL[i + 1]);
   }
   LayerView L[kMaxLayers];
-  for (int i = 0; i < n_layers; i++) L[i] = LayerView{HL[i].img.data(), HL[i].w, HL[i].h, HL[i].pitch, HL[i].scale, HL[i].offset};
-  // phase: score maps
+  for (int i = 0; i < n_layers; i++)
+    L[i] = LayerView{HL[i].img.data(), HL[i].score.data(), HL[i].w, HL[i].h, HL[i].pitch, HL[i].pitch, HL[i].scale, HL[i].offset};
+  // phase: dense score maps b0 (k_score)
   for (int i = 0; i < n_layers; i++)
     for (int y = 0; y < HL[i].h; y++) for (int x = 0; x < HL[i].w; x++)
-      HL[i].score[(size_t)y * HL[i].pitch + x] = (uint8_t)score_thresholded(L[i], x, y, threshold);
+      HL[i].score[(size_t)y * HL[i].pitch + x] = (uint8_t)b0_compute(L[i], x, y);
   // phase: candidates (any order on the device; the order here is irrelevant by construction)
   std::vector<Cand> C;
   for (int i = n_layers - 1; i >= 0; i--) {  // deliberately reversed to prove order independence
@@ -67,11 +68,11 @@ extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int th
     for (int y = l.h - 4; y >= 3; y--) for (int x = 3; x < l.w - 3; x++) {
       const uint8_t* s = &l.score[(size_t)y * l.pitch + x];
       const int c = s[0];
-      if (c == 0) continue;
+      if (c < threshold) continue;
       bool ok = true, tie = false;
       for (int dy = -1; dy <= 1 && ok; dy++) for (int dx = -1; dx <= 1; dx++) {
         if (!dx && !dy) continue;
-        const int v = s[dy * l.pitch + dx];
+        const int v = s[dy * l.pitch + dx];  // values below the threshold can neither exceed nor tie c
         if (v > c) { ok = false; break; }
         if (v == c) tie = true;
       }
@@ -120,8 +121,8 @@ extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int th
       int m[5][5];
       for (int dy = -2; dy <= 2; dy++) for (int dx = -2; dx <= 2; dx++) {
         const int x = t.x + dx, y = t.y + dy;
-        int v = l.score[(size_t)y * l.pitch + x];
-        if (v == 0 && touched_before(l.touch[(size_t)y * l.pitch + x], epoch, t.key)) v = b0(L[t.layer], x, y);
+        int v = l.score[(size_t)y * l.pitch + x];  // b0: what the cache holds once touched
+        if (v < threshold && !touched_before(l.touch[(size_t)y * l.pitch + x], epoch, t.key)) v = 0;
         m[dy + 2][dx + 2] = v;
       }
       newly.push_back(is_max_2d_5x5(m) ? ti : -ti - 1);
