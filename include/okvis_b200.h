@@ -93,6 +93,9 @@ int okb_device_features(okb_context_t* ctx, int cam, const okb_keypoint_t** d_kp
 int okb_num_layers(okb_context_t* ctx, int cam);
 int okb_layer_info(okb_context_t* ctx, int cam, int layer, int* width, int* height, float* scale, float* offset);
 int okb_fetch_layer(okb_context_t* ctx, int cam, int frame, int layer, uint8_t* image_out, uint8_t* score_out);
+/* SM cycle stamps (clock64) of the phases of the two single-CTA kernels (tie resolution, selection) of the last call:
+ * out16[0..4] resolve phases, [5] rounds, [6] ties, [8..12] finalize phases, [13] keypoints before the cap, [14] candidates */
+int okb_debug_stamps(okb_context_t* ctx, int cam, int frame, long long* out16);
 /* algorithmic bytes of the pyramid+score pass for one image of camera `cam` (read base + write
  * reduced layers + write score maps, from the actual layer sizes) */
 int64_t okb_pyramid_score_bytes(okb_context_t* ctx, int cam);

@@ -239,6 +239,18 @@ int okb_fetch_layer(okb_context_t* ctx, int cam, int frame, int layer, uint8_t* 
   return OKB_OK;
 }
 
+int okb_debug_stamps(okb_context_t* ctx, int cam, int frame, long long* out16)
+{
+  int rc = check_cam(ctx, cam, "okb_debug_stamps");
+  if (rc) return rc;
+  CamWorkspace& ws = ctx->cams[cam];
+  if (frame < 0 || frame >= ws.cfg.max_batch || !out16) { set_error("okb_debug_stamps: bad arguments"); return OKB_ERR_ARGUMENT; }
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  OKB_CUDA(cudaStreamSynchronize(ws.stream));
+  OKB_CUDA(cudaMemcpy(out16, ws.d_dbg + (size_t)frame * 16, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return OKB_OK;
+}
+
 int64_t okb_pyramid_score_bytes(okb_context_t* ctx, int cam) { return check_cam(ctx, cam, "okb_pyramid_score_bytes") ? -1 : ctx->cams[cam].ps_bytes; }
 
 int okb_enable_timers(okb_context_t* ctx, int on) { if (!ctx) return OKB_ERR_ARGUMENT; ctx->timers_on = on; return OKB_OK; }

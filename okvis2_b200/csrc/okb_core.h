@@ -312,64 +312,58 @@ struct ScanIter {
   }
 };
 
-// Generic scan used for both directions. BELOW adds the reference's tie rule for interior integer positions.
+// Generic scan used for both directions, written with a fixed iteration structure (one loop over the at most 16
+// grid positions, the early exit kept as a flag) so that the 32 candidates of a warp stay in lockstep on the device.
+// Sequential semantics reproduced: positions visited in row-major order of the grid
+//   rows  = [y_1, ya..yb, y1],  columns = [x_1, xa..xb, x1]   (first/last are float, bilinear reads)
+// every row but the last leaves (ismax = false) at the first value above `threshold`; the running maximum is updated
+// on strict >, its position following the reference's per-position formulas. BELOW adds the reference's tie rule for
+// interior integer positions. An interior position read bilinearly at integer coordinates returns exactly b0.
 template <bool BELOW>
 OKB_HDN float scan_neighbour_layer(const LayerView& nl, const ScanIter& it, const int threshold, bool& ismax,
                                    int& max_x, int& max_y, ScanTrace* tr)
 {
-  ismax = false;
-  const float x_1 = it.x_1, x1 = it.x1, y_1 = it.y_1, y1 = it.y1;
-  max_x = (int)x_1 + 1;
-  max_y = (int)y_1 + 1;
-  int nq = 0;
-  float tmp_max;
-  float maxval = (float)b0_f(nl, x_1, y_1); nq++;
-#define OKB_EXIT_IF(c) if (c) { if (tr) { tr->n_queries = (int16_t)nq; tr->exited = 1; tr->max_x = 0; tr->max_y = 0; } return 0.0f; }
-  OKB_EXIT_IF(maxval > threshold)
-  for (int x = it.xa; x <= it.xb; x++) {
-    tmp_max = (float)b0_f(nl, (float)x, y_1); nq++;
-    OKB_EXIT_IF(tmp_max > threshold)
-    if (tmp_max > maxval) { maxval = tmp_max; max_x = x; }
-  }
-  tmp_max = (float)b0_f(nl, x1, y_1); nq++;
-  OKB_EXIT_IF(tmp_max > threshold)
-  if (tmp_max > maxval) { maxval = tmp_max; max_x = (int)x1; }
-  for (int y = it.ya; y <= it.yb; y++) {
-    tmp_max = (float)b0_f(nl, x_1, (float)y); nq++;
-    OKB_EXIT_IF(tmp_max > threshold)
-    if (tmp_max > maxval) { maxval = tmp_max; max_x = (int)(x_1 + 1); max_y = y; }
-    for (int x = it.xa; x <= it.xb; x++) {
-      tmp_max = (float)b0(nl, x, y); nq++;
-      OKB_EXIT_IF(tmp_max > threshold)
-      if (BELOW) {
-        if (tmp_max == maxval) {
-          const int t1 = 2 * (b0(nl, x - 1, y) + b0(nl, x + 1, y) + b0(nl, x, y + 1) + b0(nl, x, y - 1)) +
-                         (b0(nl, x + 1, y + 1) + b0(nl, x - 1, y + 1) + b0(nl, x + 1, y - 1) + b0(nl, x - 1, y - 1));
-          const int t2 = 2 * (b0(nl, max_x - 1, max_y) + b0(nl, max_x + 1, max_y) + b0(nl, max_x, max_y + 1) +
-                              b0(nl, max_x, max_y - 1)) +
-                         (b0(nl, max_x + 1, max_y + 1) + b0(nl, max_x - 1, max_y + 1) + b0(nl, max_x + 1, max_y - 1) +
-                          b0(nl, max_x - 1, max_y - 1));
-          if (t1 > t2) { max_x = x; max_y = y; }
+  const int nx = imax(it.xb - it.xa + 1, 0), ny = imax(it.yb - it.ya + 1, 0);
+  const int rowlen = nx + 2, Q = (ny + 2) * rowlen;
+  int mx = (int)it.x_1 + 1, my = (int)it.y_1 + 1;
+  float maxval = 0.f;
+  bool exited = false;
+  int nq = Q;
+  int r = 0, c = 0;
+  for (int q = 0; q < 16; q++) {
+    if (q >= Q) break;
+    const bool row_first = r == 0, row_last = r == ny + 1, col_first = c == 0, col_last = c == rowlen - 1;
+    const int xi = it.xa + c - 1, yi = it.ya + r - 1;
+    const float xf = col_first ? it.x_1 : (col_last ? it.x1 : (float)xi);
+    const float yf = row_first ? it.y_1 : (row_last ? it.y1 : (float)yi);
+    const float tmp = exited ? 0.f : (float)b0_f(nl, xf, yf);
+    if (!exited) {
+      if (!row_last && tmp > (float)threshold) { exited = true; nq = q + 1; }
+      else if (q == 0) maxval = tmp;
+      else {
+        if (BELOW) {
+          if (!row_first && !row_last && !col_first && !col_last && tmp == maxval) {
+            const int x = xi, y = yi;
+            const int t1 = 2 * (b0(nl, x - 1, y) + b0(nl, x + 1, y) + b0(nl, x, y + 1) + b0(nl, x, y - 1)) +
+                           (b0(nl, x + 1, y + 1) + b0(nl, x - 1, y + 1) + b0(nl, x + 1, y - 1) + b0(nl, x - 1, y - 1));
+            const int t2 = 2 * (b0(nl, mx - 1, my) + b0(nl, mx + 1, my) + b0(nl, mx, my + 1) + b0(nl, mx, my - 1)) +
+                           (b0(nl, mx + 1, my + 1) + b0(nl, mx - 1, my + 1) + b0(nl, mx + 1, my - 1) + b0(nl, mx - 1, my - 1));
+            if (t1 > t2) { mx = x; my = y; }
+          }
+        }
+        if (tmp > maxval) {
+          maxval = tmp;
+          mx = col_first ? (int)(it.x_1 + 1) : (col_last ? (int)it.x1 : xi);
+          if (!row_first) my = row_last ? (int)it.y1 : yi;
         }
       }
-      if (tmp_max > maxval) { maxval = tmp_max; max_x = x; max_y = y; }
     }
-    tmp_max = (float)b0_f(nl, x1, (float)y); nq++;
-    OKB_EXIT_IF(tmp_max > threshold)
-    if (tmp_max > maxval) { maxval = tmp_max; max_x = (int)x1; max_y = y; }
+    if (++c == rowlen) { c = 0; r++; }
   }
-#undef OKB_EXIT_IF
-  tmp_max = (float)b0_f(nl, x_1, y1); nq++;
-  if (tmp_max > maxval) { maxval = tmp_max; max_x = (int)(x_1 + 1); max_y = (int)y1; }
-  for (int x = it.xa; x <= it.xb; x++) {
-    tmp_max = (float)b0_f(nl, (float)x, y1); nq++;
-    if (tmp_max > maxval) { maxval = tmp_max; max_x = x; max_y = (int)y1; }
-  }
-  tmp_max = (float)b0_f(nl, x1, y1); nq++;
-  if (tmp_max > maxval) { maxval = tmp_max; max_x = (int)x1; max_y = (int)y1; }
-  if (tr) { tr->n_queries = (int16_t)nq; tr->exited = 0; tr->max_x = (int16_t)max_x; tr->max_y = (int16_t)max_y; }
-  ismax = true;
-  return maxval;
+  max_x = mx; max_y = my;
+  if (tr) { tr->n_queries = (int16_t)nq; tr->exited = exited ? 1 : 0; tr->max_x = exited ? 0 : (int16_t)mx; tr->max_y = exited ? 0 : (int16_t)my; }
+  ismax = !exited;
+  return exited ? 0.0f : maxval;
 }
 
 OKB_HD void above_window(int layer, int x_layer, int y_layer, ScanIter& it)
@@ -591,6 +585,19 @@ OKB_HDN void for_each_above_touch(int layer, int x_layer, int y_layer, const Sca
   if (q++ < n) fl(it.x1, it.y1);
   if (!tr.exited)
     for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) f(tr.max_x + dx, tr.max_y + dy);
+}
+
+// Closed form of the scan order above: query q of the above-layer scan of a candidate sits in row q / (nx + 2) and
+// column q % (nx + 2) of a grid whose first/last rows and columns are float (bilinear, 2x2 block) positions.
+// Returns the integer base pixel (X, Y) and whether the 2x2 block is touched.
+OKB_HD void above_query_pos(const ScanIter& it, int q, int& X, int& Y, bool& block2x2)
+{
+  const int nx = imax(it.xb - it.xa + 1, 0), ny = imax(it.yb - it.ya + 1, 0);
+  const int rowlen = nx + 2;
+  const int r = q / rowlen, c = q % rowlen;
+  X = c == 0 ? (int)it.x_1 : (c == rowlen - 1 ? (int)it.x1 : it.xa + c - 1);
+  Y = r == 0 ? (int)it.y_1 : (r == ny + 1 ? (int)it.y1 : it.ya + r - 1);
+  block2x2 = (r == 0) || (r == ny + 1) || (c == 0) || (c == rowlen - 1);
 }
 
 // 2-D maximum test with tie-break, on the effective map M(q) the sequential algorithm would see.

@@ -265,25 +265,33 @@ __global__ void __launch_bounds__(256) k_nms(DeviceLayers dl, TileMap tm, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void emit_touches(const DeviceLayers& dl, uint32_t* touch_frame, int layer, int x, int y,
-                                             int own_touch, int has_above, const ScanTrace& tr, uint32_t entry)
+// Cache-touch events of one maximum, emitted by a full warp (all arguments warp-uniform): lanes take the positions of
+// the above-layer scan (closed form of the scan order in okb_core.h: rows of [x_1, xa..xb, x1]) and of the 3x3 / 4x4
+// patches, so the divergent, sequential replay of for_each_above_touch never runs on the device.
+__device__ __forceinline__ void emit_touches_warp(const DeviceLayers& dl, uint32_t* touch_frame, uint32_t key, int own_touch,
+                                                  int has_above, ScanTrace tr, uint32_t entry, int lane)
 {
-  {
+  const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+  if (own_touch && lane < 16) {
     const DeviceLayer d = dl.l[layer];
-    uint32_t* tm = touch_frame + d.offset;
     const int hi = own_touch == 2 ? 2 : 1;
-    if (own_touch)
-      for (int dy = -1; dy <= hi; dy++) for (int dx = -1; dx <= hi; dx++) {
-        const int xx = x + dx, yy = y + dy;
-        if (xx >= 0 && yy >= 0 && xx < d.w && yy < d.h) atomicMax(&tm[(size_t)yy * d.pitch + xx], entry);
-      }
+    const int dx = (lane & 3) - 1, dy = (lane >> 2) - 1;
+    const int xx = x + dx, yy = y + dy;
+    if (dx <= hi && dy <= hi && xx >= 0 && yy >= 0 && xx < d.w && yy < d.h)
+      atomicMax(&touch_frame[d.offset + (size_t)yy * d.pitch + xx], entry);
   }
   if (has_above) {
     const DeviceLayer d = dl.l[layer + 1];
     uint32_t* tm = touch_frame + d.offset;
-    for_each_above_touch(layer, x, y, tr, [&](int xx, int yy) {
-      if (xx >= 0 && yy >= 0 && xx < d.w && yy < d.h) atomicMax(&tm[(size_t)yy * d.pitch + xx], entry);
-    });
+    ScanIter it; above_window(layer, x, y, it);
+    auto put = [&](int xx, int yy) { if (xx >= 0 && yy >= 0 && xx < d.w && yy < d.h) atomicMax(&tm[(size_t)yy * d.pitch + xx], entry); };
+    for (int q = lane; q < tr.n_queries; q += 32) {
+      int X, Y; bool blk;
+      above_query_pos(it, q, X, Y, blk);
+      put(X, Y);
+      if (blk) { put(X + 1, Y); put(X, Y + 1); put(X + 1, Y + 1); }  // bilinear read: 2x2 block
+    }
+    if (!tr.exited && lane < 9) put(tr.max_x + lane % 3 - 1, tr.max_y + lane / 3 - 1);
   }
 }
 
@@ -299,21 +307,38 @@ __global__ void __launch_bounds__(128) k_refine(DeviceLayers dl, const uint8_t* 
   if (threadIdx.x == 0) make_views(dl, in0, in_pitch, in_frame_stride, img_block, score_block, touch_block, frame, v);
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t c = cand[(size_t)frame * cand_cap + i];
-  const uint32_t key = c & 0x7fffffffu;
-  const int tie = (int)(c >> 31);
-  const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+  const int lane = threadIdx.x & 31;
+  const bool have = i < n;
+  uint32_t key = 0; int tie = 0;
   RefineResult r;
-  refine_candidate(v.L, v.n, layer, x, y, threshold, r);
-  CandRecord out;
-  out.x = r.x; out.y = r.y; out.size = r.size; out.response = r.response; out.key = key;
-  out.keep = r.keep; out.own_touch = r.own_touch; out.has_above = r.has_above; out.tie = (int8_t)tie;
-  out.above = r.above; out.state = tie ? 0 : 1; out.pad[0] = out.pad[1] = out.pad[2] = 0;
-  rec[(size_t)frame * cand_cap + i] = out;
-  if (!tie)
-    emit_touches(dl, touch_block + (size_t)frame * dl.frame_stride, layer, x, y, r.own_touch, r.has_above, r.above,
-                 touch_entry(epoch, key));
+  r.keep = 0; r.own_touch = 0; r.has_above = 0; r.above.n_queries = 0; r.above.exited = 1; r.above.max_x = r.above.max_y = 0;
+  if (have) {
+    const uint32_t c = cand[(size_t)frame * cand_cap + i];
+    key = c & 0x7fffffffu; tie = (int)(c >> 31);
+    refine_candidate(v.L, v.n, (int)(key >> 22), (int)(key & 2047), (int)((key >> 11) & 2047), threshold, r);
+    CandRecord out;
+    out.x = r.x; out.y = r.y; out.size = r.size; out.response = r.response; out.key = key;
+    out.keep = r.keep; out.own_touch = r.own_touch; out.has_above = r.has_above; out.tie = (int8_t)tie;
+    out.above = r.above; out.state = tie ? 0 : 1; out.pad[0] = out.pad[1] = out.pad[2] = 0;
+    rec[(size_t)frame * cand_cap + i] = out;
+  }
+  // cache-touch events of the non-tied maxima, one maximum at a time by the whole warp
+  uint32_t* touch_frame = touch_block + (size_t)frame * dl.frame_stride;
+  const bool emits = have && !tie && (r.own_touch || r.has_above);
+  unsigned m = __ballot_sync(0xffffffffu, emits);
+  const unsigned tr_a = (uint32_t)(uint16_t)r.above.n_queries | ((uint32_t)(uint16_t)r.above.exited << 16);
+  const unsigned tr_b = (uint32_t)(uint16_t)r.above.max_x | ((uint32_t)(uint16_t)r.above.max_y << 16);
+  const unsigned flags = (uint32_t)r.own_touch | ((uint32_t)r.has_above << 8);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t k2 = __shfl_sync(0xffffffffu, key, src);
+    const unsigned a2 = __shfl_sync(0xffffffffu, tr_a, src), b2 = __shfl_sync(0xffffffffu, tr_b, src);
+    const unsigned f2 = __shfl_sync(0xffffffffu, flags, src);
+    ScanTrace t2; t2.n_queries = (int16_t)(a2 & 0xffff); t2.exited = (int16_t)(a2 >> 16);
+    t2.max_x = (int16_t)(b2 & 0xffff); t2.max_y = (int16_t)(b2 >> 16);
+    emit_touches_warp(dl, touch_frame, k2, (int)(f2 & 0xff), (int)(f2 >> 8), t2, touch_entry(epoch, k2), lane);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -336,23 +361,33 @@ __device__ void bitonic_sort_u64(unsigned long long* a, int n)
 
 constexpr int kMaxTies = 4096;
 constexpr int kMaxBlockers = 12;
-constexpr int kResolveSmem = kMaxTies * (8 + 2 * kMaxBlockers + 3);
+constexpr int kResolveSmem = kMaxTies * (8 + 2 * kMaxBlockers + 2 + 8 + 4);
+
+struct TieInfo {  // what a tie's cache touches look like if it turns out to be a maximum (8 bytes)
+  int8_t own_touch, has_above, exited, n_queries;
+  int16_t max_x, max_y;
+};
 
 // One CTA per frame. Resolves, in dependency rounds, the candidates whose 2-D maximum test ties with a neighbour:
 // their outcome depends on which sub-threshold scores the sequential algorithm had already cached when it reached them.
-// A tie waits only for EARLIER ties whose cache touches can reach its 5x5 window: same layer within 4 px, or the layer
-// below through the window of its above-scan. The (few) possible blockers of every tie are listed once; a round is
-// then a handful of shared-memory reads per unresolved tie.
-__global__ void __launch_bounds__(256) k_resolve(DeviceLayers dl, const uint8_t* score_block, uint32_t* touch_block,
+// Touches by NON-tied maxima are already in the touch-time map (k_refine); touches by EARLIER TIES are applied here
+// from shared memory: a tie waits only for the earlier ties whose touches can reach its 5x5 window (same layer within
+// 4 px, or the layer below through the window of its above-scan), listed once; when they are all decided it ORs the
+// footprint of the winners among them into its 25-bit "touched" mask and evaluates the reference's isMax2D.
+__global__ void __launch_bounds__(512) k_resolve(DeviceLayers dl, const uint8_t* score_block, const uint32_t* touch_block,
                                                  const int32_t* cand_count, int cand_cap, CandRecord* rec,
-                                                 uint32_t epoch, int threshold, int32_t* status)
+                                                 uint32_t epoch, int threshold, int32_t* status, long long* dbg)
 {
+#define OKB_STAMP(i) if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + (i)] = clock64()
+  OKB_STAMP(0);
   extern __shared__ unsigned long long resolve_smem[];
   unsigned long long* ties = resolve_smem;                                   // key << 32 | record index, sorted
   uint16_t (*blockers)[kMaxBlockers] = reinterpret_cast<uint16_t (*)[kMaxBlockers]>(ties + kMaxTies);
-  int8_t* state = reinterpret_cast<int8_t*>(blockers + kMaxTies);            // 0 unresolved, 1 maximum, 2 rejected
-  int8_t* newly = state + kMaxTies;
-  int8_t* n_block = newly + kMaxTies;                                        // -1: list overflowed, scan every round
+  short4* box = reinterpret_cast<short4*>(blockers + kMaxTies);              // above-scan window (layer+1 coords) ...
+  TieInfo* info = reinterpret_cast<TieInfo*>(box);                           // ... replaced by the touch info after the lists are built
+  uint32_t* tmask = reinterpret_cast<uint32_t*>(box + kMaxTies);             // window pixels touched before this tie
+  int8_t* state = reinterpret_cast<int8_t*>(tmask + kMaxTies);               // 0 unresolved, 1 maximum, 2 rejected
+  int8_t* n_block = state + kMaxTies;                                        // -1: list overflowed, scan instead
   __shared__ int n_ties, n_unresolved, layer_start[kMaxLayers + 1];
   const int frame = blockIdx.x;
   const int n = min(cand_count[frame], cand_cap);
@@ -371,8 +406,9 @@ __global__ void __launch_bounds__(256) k_resolve(DeviceLayers dl, const uint8_t*
   int P = 1; while (P < T) P <<= 1;
   for (int i = T + threadIdx.x; i < P; i += blockDim.x) ties[i] = ~0ull;
   __syncthreads();
+  OKB_STAMP(1);
   bitonic_sort_u64(ties, P);
-  for (int i = threadIdx.x; i < T; i += blockDim.x) state[i] = 0;
+  OKB_STAMP(2);
   if (threadIdx.x <= kMaxLayers) {
     // first tie index of every layer (ties are sorted by key, layer is the top field)
     const int l = threadIdx.x;
@@ -382,8 +418,27 @@ __global__ void __launch_bounds__(256) k_resolve(DeviceLayers dl, const uint8_t*
     layer_start[l] = (l >= kMaxLayers) ? T : lo;
   }
   if (threadIdx.x == 0) n_unresolved = T;
+  const uint8_t* score_frame = score_block + (size_t)frame * dl.frame_stride;
+  const uint32_t* touch_frame = touch_block + (size_t)frame * dl.frame_stride;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    const uint32_t key = (uint32_t)(ties[i] >> 32);
+    const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+    state[i] = 0;
+    ScanIter it; above_window(layer, x, y, it);
+    box[i] = make_short4((short)((int)it.x_1 - 1), (short)((int)it.x1 + 2), (short)((int)it.y_1 - 1), (short)((int)it.y1 + 2));
+    // touches by the non-tied maxima (all emitted before this kernel started)
+    const DeviceLayer d = dl.l[layer];
+    const uint32_t* tm = touch_frame + d.offset;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int j = 0; j < 25; j++) {
+      const uint32_t e = __ldcg(&tm[(size_t)(y + j / 5 - 2) * d.pitch + (x + j % 5 - 2)]);
+      if (touched_before(e, epoch, key)) mask |= 1u << j;
+    }
+    tmask[i] = mask;
+  }
   __syncthreads();
-  // enumerate the possible blockers of tie ti; F(u) returns true to stop
+  // enumerate the possible blockers of tie ti (earlier ties whose touches can reach its window); F(u) true = stop
   auto for_each_blocker = [&](int ti, auto F) {
     const uint32_t key = (uint32_t)(ties[ti] >> 32);
     const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
@@ -403,14 +458,10 @@ __global__ void __launch_bounds__(256) k_resolve(DeviceLayers dl, const uint8_t*
       int lo = layer_start[layer - 1], hi = layer_start[layer];
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < lo_key) lo = mid + 1; else hi = mid; }
       for (int u = lo; u < layer_start[layer]; u++) {
-        const uint32_t uk = (uint32_t)(ties[u] >> 32);
-        const int uy = (int)((uk >> 11) & 2047), ux = (int)(uk & 2047);
+        const int uy = (int)(((uint32_t)(ties[u] >> 32) >> 11) & 2047);
         if (uy > uy_hi) break;
-        // cheap integer pre-test (the exact window follows): centre maps to about 2/3 .. 3/4 of (ux, uy)
-        if (abs(ux * 3 / 4 - x) > 8 + ux / 12) continue;
-        ScanIter it; above_window(layer - 1, ux, uy, it);
-        const int xa = (int)it.x_1 - 1, xb = (int)it.x1 + 2, ya = (int)it.y_1 - 1, yb = (int)it.y1 + 2;
-        if (!(x + 2 < xa || x - 2 > xb || y + 2 < ya || y - 2 > yb)) if (F(u)) return;
+        const short4 bx = box[u];
+        if (!(x + 2 < bx.x || x - 2 > bx.y || y + 2 < bx.z || y - 2 > bx.w)) if (F(u)) return;
       }
     }
   };
@@ -423,56 +474,101 @@ __global__ void __launch_bounds__(256) k_resolve(DeviceLayers dl, const uint8_t*
     n_block[ti] = (int8_t)nb;
   }
   __syncthreads();
-  const uint8_t* score_frame = score_block + (size_t)frame * dl.frame_stride;
-  uint32_t* touch_frame = touch_block + (size_t)frame * dl.frame_stride;
+  // the boxes are no longer needed unless a list overflowed (then the scan above is reused every round, with boxes):
+  // keep them in that (rare) case and read the touch info from the records instead
+  __shared__ int any_overflow;
+  if (threadIdx.x == 0) any_overflow = 0;
+  __syncthreads();
+  for (int ti = threadIdx.x; ti < T; ti += blockDim.x) if (n_block[ti] < 0) any_overflow = 1;
+  __syncthreads();
+  const bool use_info = !any_overflow;
+  if (use_info)
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+      const CandRecord& c = R[(int)(ties[i] & 0xffffffffu)];
+      TieInfo ti; ti.own_touch = c.own_touch; ti.has_above = c.has_above; ti.exited = (int8_t)c.above.exited;
+      ti.n_queries = (int8_t)c.above.n_queries; ti.max_x = c.above.max_x; ti.max_y = c.above.max_y;
+      info[i] = ti;
+    }
+  __syncthreads();
+  OKB_STAMP(3);
+  auto get_info = [&](int u) {
+    if (use_info) return info[u];
+    const CandRecord& c = R[(int)(ties[u] & 0xffffffffu)];
+    TieInfo ti; ti.own_touch = c.own_touch; ti.has_above = c.has_above; ti.exited = (int8_t)c.above.exited;
+    ti.n_queries = (int8_t)c.above.n_queries; ti.max_x = c.above.max_x; ti.max_y = c.above.max_y;
+    return ti;
+  };
+  // window pixels of tie (layer, x, y) that winner u would have touched
+  auto footprint = [&](int u, int layer, int x, int y) {
+    const uint32_t uk = (uint32_t)(ties[u] >> 32);
+    const int ul = (int)(uk >> 22), uy = (int)((uk >> 11) & 2047), ux = (int)(uk & 2047);
+    const TieInfo f = get_info(u);
+    uint32_t mask = 0;
+    auto mark = [&](int px, int py) {
+      const int dx = px - x + 2, dy = py - y + 2;
+      if ((unsigned)dx < 5u && (unsigned)dy < 5u) mask |= 1u << (dy * 5 + dx);
+    };
+    if (ul == layer) {
+      if (f.own_touch) {
+        const int hi = f.own_touch == 2 ? 2 : 1;
+        for (int dy = -1; dy <= hi; dy++) for (int dx = -1; dx <= hi; dx++) mark(ux + dx, uy + dy);
+      }
+    } else if (f.has_above) {
+      ScanIter it; above_window(ul, ux, uy, it);
+      for (int q = 0; q < f.n_queries; q++) {
+        int X, Y; bool blk; above_query_pos(it, q, X, Y, blk);
+        mark(X, Y);
+        if (blk) { mark(X + 1, Y); mark(X, Y + 1); mark(X + 1, Y + 1); }
+      }
+      if (!f.exited) for (int j = 0; j < 9; j++) mark(f.max_x + j % 3 - 1, f.max_y + j / 3 - 1);
+    }
+    return mask;
+  };
+  int rounds = 0;
   while (true) {
-    for (int ti = threadIdx.x; ti < T; ti += blockDim.x) {
-      newly[ti] = 0;
+    int8_t decided[(kMaxTies + 511) / 512];
+    int nd = 0;
+    for (int ti = threadIdx.x; ti < T; ti += blockDim.x, nd++) {
+      decided[nd] = 0;
       if (state[ti] != 0) continue;
-      bool blocked = false;
-      const int nb = n_block[ti];
-      if (nb >= 0) { for (int i = 0; i < nb; i++) if (state[blockers[ti][i]] == 0) { blocked = true; break; } }
-      else for_each_blocker(ti, [&](int u) { if (state[u] == 0) { blocked = true; return true; } return false; });
-      if (blocked) continue;
       const uint32_t key = (uint32_t)(ties[ti] >> 32);
       const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+      bool blocked = false;
+      uint32_t mask = tmask[ti];
+      const int nb = n_block[ti];
+      if (nb >= 0) {
+        for (int i = 0; i < nb; i++) if (state[blockers[ti][i]] == 0) { blocked = true; break; }
+        if (!blocked) for (int i = 0; i < nb; i++) { const int u = blockers[ti][i]; if (state[u] == 1) mask |= footprint(u, layer, x, y); }
+      } else {
+        for_each_blocker(ti, [&](int u) { if (state[u] == 0) { blocked = true; return true; } return false; });
+        if (!blocked) for_each_blocker(ti, [&](int u) { if (state[u] == 1) mask |= footprint(u, layer, x, y); return false; });
+      }
+      if (blocked) continue;
       const DeviceLayer d = dl.l[layer];
       const uint8_t* sc = score_frame + d.offset;
-      const uint32_t* tm = touch_frame + d.offset;
       int m[5][5];
 #pragma unroll
       for (int dy = -2; dy <= 2; dy++)
 #pragma unroll
         for (int dx = -2; dx <= 2; dx++) {
-          const int xx = x + dx, yy = y + dy;
-          int val = sc[(size_t)yy * d.pitch + xx];  // dense b0 = what the cache holds once the pixel was touched
-          if (val < threshold) {
-            const uint32_t e = __ldcg(&tm[(size_t)yy * d.pitch + xx]);
-            if (!touched_before(e, epoch, key)) val = 0;
-          }
+          int val = sc[(size_t)(y + dy) * d.pitch + (x + dx)];  // dense b0 = what the cache holds once the pixel was touched
+          if (val < threshold && !((mask >> ((dy + 2) * 5 + dx + 2)) & 1u)) val = 0;
           m[dy + 2][dx + 2] = val;
         }
-      newly[ti] = is_max_2d_5x5(m) ? 1 : 2;
+      decided[nd] = is_max_2d_5x5(m) ? 1 : 2;
     }
+    __syncthreads();   // every thread has read the states of this round
+    nd = 0;
+    for (int ti = threadIdx.x; ti < T; ti += blockDim.x, nd++)
+      if (decided[nd]) { state[ti] = decided[nd]; atomicSub(&n_unresolved, 1); }
     __syncthreads();
-    for (int ti = threadIdx.x; ti < T; ti += blockDim.x) {
-      if (!newly[ti]) continue;
-      state[ti] = newly[ti];
-      atomicSub(&n_unresolved, 1);
-      const int ri = (int)(ties[ti] & 0xffffffffu);
-      R[ri].state = newly[ti];
-      if (newly[ti] == 1) {
-        const CandRecord c = R[ri];
-        const uint32_t key = c.key;
-        emit_touches(dl, touch_frame, (int)(key >> 22), (int)(key & 2047), (int)((key >> 11) & 2047), c.own_touch,
-                     c.has_above, c.above, touch_entry(epoch, key));
-      }
-    }
-    __threadfence();
-    __syncthreads();
+    rounds++;
     if (n_unresolved <= 0) break;
-    __syncthreads();
   }
+  OKB_STAMP(4);
+  for (int ti = threadIdx.x; ti < T; ti += blockDim.x) R[(int)(ties[ti] & 0xffffffffu)].state = state[ti];
+  if (dbg && threadIdx.x == 0) { dbg[blockIdx.x * 16 + 5] = rounds; dbg[blockIdx.x * 16 + 6] = T; }
+#undef OKB_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -508,39 +604,93 @@ __device__ int block_exclusive_scan_1024(int val, int* sh /*33 ints*/, int& tota
   return res;
 }
 
+constexpr int kMaxRows = 8192;   // sum of the layer heights
+constexpr int kFinalizeSmem = kSortCap * 8 + kSortCap * 4 + (kMaxRows + 2) * 2 + kSortCap;
+
 // One CTA (1024 threads) per frame: order the surviving keypoints by (layer, y, x), keep the max_kp strongest
 // (ties: earlier first), drop the ones whose sampling pattern leaves the image, write cv::KeyPoint records.
-__global__ void __launch_bounds__(1024) k_finalize(const int32_t* cand_count, int cand_cap, const CandRecord* rec,
+// Ordering is a counting sort by (layer, row) followed by a tiny in-place insertion sort inside every row group.
+__global__ void __launch_bounds__(1024) k_finalize(DeviceLayers dl, const int32_t* cand_count, int cand_cap, const CandRecord* rec,
                                                    const float* scale_bounds, const uint32_t* size_list, int W, int H,
                                                    int max_kp, int kp_cap, okb_keypoint_t* kp_out, int32_t* kscale_out,
-                                                   int32_t* count_out, int32_t* status)
+                                                   int32_t* count_out, int32_t* status, long long* dbg)
 {
-  extern __shared__ unsigned long long keys[];  // kSortCap sorted (key << 32 | record index), then kSortCap response bits
-  uint32_t* resp = reinterpret_cast<uint32_t*>(keys + kSortCap);
-  __shared__ uint8_t flag[kSortCap];
-  __shared__ int n_valid, hist[256], sh_scan[33];
+#define OKB_STAMP(i) if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + (i)] = clock64()
+  OKB_STAMP(8);
+  extern __shared__ unsigned long long keys[];  // kSortCap (key << 32 | record index), ordered
+  uint32_t* resp = reinterpret_cast<uint32_t*>(keys + kSortCap);          // kSortCap response bits
+  uint16_t* rowoff = reinterpret_cast<uint16_t*>(resp + kSortCap);        // kMaxRows + 1 group offsets
+  uint8_t* flag = reinterpret_cast<uint8_t*>(rowoff + kMaxRows + 2);      // kSortCap keep flags
+  __shared__ int n_valid, hist[256], sh_scan[33], rowbase[kMaxLayers + 1];
   __shared__ uint32_t sel_prefix;
   __shared__ int sel_remaining;
   const int frame = blockIdx.x;
   const int n = min(cand_count[frame], cand_cap);
   if (cand_count[frame] > cand_cap && threadIdx.x == 0) atomicOr(&status[frame], 1);
   const CandRecord* R = rec + (size_t)frame * cand_cap;
-  if (threadIdx.x == 0) n_valid = 0;
+  if (threadIdx.x == 0) {
+    n_valid = 0;
+    int acc = 0;
+    for (int l = 0; l < kMaxLayers; l++) { rowbase[l] = acc; if (l < dl.n) acc += dl.l[l].h; }
+    rowbase[kMaxLayers] = acc;
+  }
+  __syncthreads();
+  const int n_rows = rowbase[kMaxLayers];
+  uint32_t* rowcnt = reinterpret_cast<uint32_t*>(keys);   // counts live in the (still unused) key array during pass 1
+  for (int i = threadIdx.x; i <= n_rows; i += blockDim.x) rowcnt[i] = 0;
+  __syncthreads();
+  auto row_of = [&](uint32_t key) { return rowbase[key >> 22] + (int)((key >> 11) & 2047); };
+  // pass 1: count the valid keypoints per (layer, row)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const CandRecord& c = R[i];
+    if (c.state == 1 && c.keep) { atomicAdd(&rowcnt[row_of(c.key)], 1u); atomicAdd(&n_valid, 1); }
+  }
+  __syncthreads();
+  int V = n_valid;
+  const bool overflow = V > kSortCap || n_rows > kMaxRows;
+  if (overflow) { if (threadIdx.x == 0) { atomicOr(&status[frame], 4); count_out[frame] = 0; } return; }
+  // exclusive scan of the row counts -> group offsets (16 bit: V <= 16384)
+  {
+    const int chunk = (n_rows + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int beg = min((int)threadIdx.x * chunk, n_rows), end = min(beg + chunk, n_rows);
+    int sum = 0;
+    for (int i = beg; i < end; i++) sum += (int)rowcnt[i];
+    int total = 0;
+    int run = block_exclusive_scan_1024(sum, sh_scan, total);
+    // the counts must be consumed before the offsets overwrite anything: stage this thread's counts in registers
+    // (chunk <= 8 for kMaxRows = 8192)
+    int cnts[8];
+    for (int i = beg, j = 0; i < end; i++, j++) cnts[j] = (int)rowcnt[i];
+    __syncthreads();
+    for (int i = beg, j = 0; i < end; i++, j++) { rowoff[i] = (uint16_t)run; run += cnts[j]; }
+    if (threadIdx.x == blockDim.x - 1) rowoff[n_rows] = (uint16_t)V;
+    if (end == n_rows && beg < end) rowoff[n_rows] = (uint16_t)run;
+  }
+  __syncthreads();
+  // pass 2: scatter into the row groups (fill counters reuse flag[] as 8-bit counters is too small: use resp[] as 32-bit)
+  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) resp[i] = 0;   // n_rows <= kMaxRows <= kSortCap
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const CandRecord& c = R[i];
     if (c.state == 1 && c.keep) {
-      const int p = atomicAdd(&n_valid, 1);
-      if (p < kSortCap) keys[p] = ((unsigned long long)c.key << 32) | (unsigned)i;
+      const int row = row_of(c.key);
+      const int slot = (int)rowoff[row] + (int)atomicAdd(&resp[row], 1u);
+      keys[slot] = ((unsigned long long)c.key << 32) | (unsigned)i;
     }
   }
   __syncthreads();
-  int V = n_valid;
-  if (V > kSortCap) { if (threadIdx.x == 0) atomicOr(&status[frame], 4); V = kSortCap; }
-  int P = 1; while (P < V) P <<= 1;
-  for (int i = V + threadIdx.x; i < P; i += blockDim.x) keys[i] = ~0ull;
+  // pass 3: order inside every row group (a handful of entries) by insertion sort, one thread per group
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    const int beg = rowoff[r], end = rowoff[r + 1];
+    for (int i = beg + 1; i < end; i++) {
+      const unsigned long long k = keys[i];
+      int j = i - 1;
+      while (j >= beg && keys[j] > k) { keys[j + 1] = keys[j]; j--; }
+      keys[j + 1] = k;
+    }
+  }
   __syncthreads();
-  if (V > 1) bitonic_sort_u64(keys, P);
+  OKB_STAMP(10);
   for (int i = threadIdx.x; i < V; i += blockDim.x) resp[i] = float_order_bits(R[(int)(keys[i] & 0xffffffffu)].response);
   __syncthreads();
   // ---- strongest max_kp: radix select of the max_kp-th largest response
@@ -559,16 +709,30 @@ __global__ void __launch_bounds__(1024) k_finalize(const int32_t* cand_count, in
         if ((rb & himask) == (prefix & himask)) atomicAdd(&hist[(rb >> shift) & 255], 1);
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        int rem = sel_remaining, b = 255;
-        for (; b > 0; b--) { if (hist[b] >= rem) break; rem -= hist[b]; }
-        sel_prefix = prefix | ((uint32_t)b << shift);
-        sel_remaining = rem;  // how many of the elements matching the prefix so far are still to be kept
+      if (threadIdx.x < 32) {
+        // find the bin b (from the top) where the running count reaches `remaining`: lane l owns bins 8l .. 8l+7
+        const int lane = threadIdx.x;
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) mine += hist[lane * 8 + j];
+        const int rem = sel_remaining;
+        int suffix = mine;   // inclusive suffix sum over the lanes (higher lanes own higher bins)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, suffix, o); if (lane + o < 32) suffix += t; }
+        const int above = suffix - mine;
+        const bool owner = above < rem && above + mine >= rem;   // exactly one lane (total >= rem)
+        if (owner) {
+          int r2 = rem - above, b = lane * 8 + 7;
+          for (; b > lane * 8; b--) { if (hist[b] >= r2) break; r2 -= hist[b]; }
+          sel_prefix = prefix | ((uint32_t)b << shift);
+          sel_remaining = r2;  // how many of the elements matching the prefix so far are still to be kept
+        }
       }
       __syncthreads();
     }
     thr_bits = sel_prefix; n_equal_keep = sel_remaining;
   }
+  OKB_STAMP(11);
   // each thread owns a contiguous chunk so that the scans preserve the (layer, y, x) order
   const int chunk = (V + (int)blockDim.x - 1) / (int)blockDim.x;
   const int beg = min((int)threadIdx.x * chunk, V), end = min(beg + chunk, V);
@@ -613,6 +777,9 @@ __global__ void __launch_bounds__(1024) k_finalize(const int32_t* cand_count, in
     if (total > kp_cap) atomicOr(&status[frame], 8);
     count_out[frame] = min(total, kp_cap);
   }
+  OKB_STAMP(12);
+  if (dbg && threadIdx.x == 0) { dbg[blockIdx.x * 16 + 13] = V; dbg[blockIdx.x * 16 + 14] = n; }
+#undef OKB_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -796,6 +963,11 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMalloc(&ws.d_desc, (size_t)ws.kp_cap * 64 * B));
   OKB_CUDA(cudaMalloc(&ws.d_count, 4 * B));
   OKB_CUDA(cudaMalloc(&ws.d_status, 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_dbg, (size_t)16 * 8 * B));
+  OKB_CUDA(cudaMemset(ws.d_dbg, 0, (size_t)16 * 8 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_m1_cell_off, (size_t)4097 * 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_m1_cell_list, (size_t)ws.kp_cap * 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_m1_best, (size_t)ws.kp_cap * 8 * B));
   OKB_CUDA(cudaMemset(ws.d_count, 0, 4 * B));
   OKB_CUDA(cudaMemset(ws.d_status, 0, 4 * B));
   OKB_CUDA(cudaMallocHost(&ws.h_img, (size_t)W * H * B));
@@ -804,7 +976,7 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMallocHost(&ws.h_count, 4 * B));
   OKB_CUDA(cudaMallocHost(&ws.h_status, 4 * B));
   for (int i = 0; i < 4; i++) OKB_CUDA(cudaEventCreate(&ws.ev[i]));
-  OKB_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 12));
+  OKB_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalizeSmem));
   OKB_CUDA(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, kResolveSmem));
   return OKB_OK;
 }
@@ -818,7 +990,7 @@ void detect_free_camera(okb_context* ctx, int cam)
   }
   cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
   cudaFree(ws.d_cand_count); cudaFree(ws.d_rec); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
-  cudaFree(ws.d_count); cudaFree(ws.d_status);
+  cudaFree(ws.d_count); cudaFree(ws.d_status); cudaFree(ws.d_m1_cell_off); cudaFree(ws.d_m1_cell_list); cudaFree(ws.d_m1_best); cudaFree(ws.d_dbg);
   cudaFreeHost(ws.h_img); cudaFreeHost(ws.h_kp); cudaFreeHost(ws.h_desc); cudaFreeHost(ws.h_count); cudaFreeHost(ws.h_status);
   for (int i = 0; i < 4; i++) if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
   if (ws.stream) cudaStreamDestroy(ws.stream);
@@ -892,10 +1064,10 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   k_refine<<<dim3((ws.cand_cap + 127) / 128, B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
                                                                ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap,
                                                                ws.d_rec, c.threshold, ws.epoch);
-  k_resolve<<<B, 256, kResolveSmem, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_cand_count, ws.cand_cap, ws.d_rec, ws.epoch, c.threshold,
-                               ws.d_status);
-  k_finalize<<<B, 1024, kSortCap * 12, st>>>(ws.d_cand_count, ws.cand_cap, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,
-                                            W, H, c.max_keypoints, ws.kp_cap, ws.d_kp, ws.d_kscale, ws.d_count, ws.d_status);
+  k_resolve<<<B, 512, kResolveSmem, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_cand_count, ws.cand_cap, ws.d_rec, ws.epoch, c.threshold,
+                                          ws.d_status, ws.d_dbg);
+  k_finalize<<<B, 1024, kFinalizeSmem, st>>>(ws.dl, ws.d_cand_count, ws.cand_cap, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,
+                                            W, H, c.max_keypoints, ws.kp_cap, ws.d_kp, ws.d_kscale, ws.d_count, ws.d_status, ws.d_dbg);
   ctx->launches += 4;
   if (ctx->timers_on) cudaEventRecord(ws.ev[2], st);
   // ---- descriptors

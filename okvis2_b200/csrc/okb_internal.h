@@ -77,6 +77,9 @@ struct CamWorkspace {
   uint8_t* d_desc = nullptr;
   int32_t* d_count = nullptr;
   int32_t* d_status = nullptr;  // per frame overflow flags
+  // M1 (device-resident form): keypoint grid and merge slots
+  long long* d_dbg = nullptr;   // per-frame cycle stamps of the single-CTA kernels (okb_debug_stamps)
+  int32_t* d_m1_cell_off = nullptr; int32_t* d_m1_cell_list = nullptr; unsigned long long* d_m1_best = nullptr;
   // pinned staging
   uint8_t* h_img = nullptr;
   okb_keypoint_t* h_kp = nullptr;

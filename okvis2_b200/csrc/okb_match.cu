@@ -153,80 +153,160 @@ __device__ __forceinline__ uint32_t hamming(const uint4 (&qd)[D16], uint4 (*s_de
   return d;
 }
 
-// M1: reprojection pre-gate (fp64) then lexicographic (distance, candidate) minimum.
-// Candidate tiles are double buffered: descriptors by cp.async, projections through registers one tile ahead and the
-// landmark index two tiles ahead, so that the dependent loads c_lm -> is3d/proj never stall the compute of a tile.
-template <int D16>
-__global__ void __launch_bounds__(256) k_match_map3d(MatchArgs a)
+// M1. The reprojection gate makes the problem sparse: a keypoint can only match landmarks that project within
+// `thr` pixels of it. Keypoints are binned into a grid of cells >= thr wide (k_m1_bin, one CTA per frame); every pooled
+// descriptor then visits the 3x3 cells around its landmark's projection, evaluates the reference's exact fp64 gate
+// (reprDist.dot(reprDist) > thr^2 -> skip) and the Hamming distance, and merges (distance, candidate index) into the
+// keypoint's slot with a 64-bit atomicMin. The lexicographic minimum is exactly "first strict minimum in ascending
+// LandmarkId / descriptor order" of the sequential loop, and it is order independent, so the result is bit-identical.
+constexpr int kMaxCells = 4096;
+
+struct M1Args {
+  int nq;                       // keypoint capacity per frame
+  const int32_t* q_count;       // per-frame keypoint count (device) or nullptr
+  const uint8_t* q_desc; const uint8_t* q_use;
+  const double* q_xy; const okb_keypoint_t* q_kp;
+  size_t q_stride, proj_stride; // per-frame strides (elements) for the batched device form
+  int nc; const uint8_t* c_desc; const int32_t* c_lm; const double* lm_proj; const uint8_t* lm_is3d;
+  double thr_sq; uint32_t thr;
+  int cell, gx, gy;             // grid
+  int32_t* cell_off;            // [frames][kMaxCells + 1]
+  int32_t* cell_list;           // [frames][nq]
+  unsigned long long* best;     // [frames][nq]
+  uint32_t* out_dist; int32_t* out_idx;
+};
+
+__device__ __forceinline__ void m1_kp_xy(const M1Args& a, size_t fq, int k, double& x, double& y)
 {
-  __shared__ uint4 s_desc[2][D16][kTile];
-  __shared__ double2 s_proj[2][kTile];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * 8 + warp;
-  const size_t fq = (size_t)blockIdx.y * a.q_stride;       // first query slot of this frame
-  const double* lm_proj = a.lm_proj + (size_t)blockIdx.y * a.proj_stride;
-  const int nq = a.q_count ? min(a.q_count[blockIdx.y], a.nq) : a.nq;
-  if (blockIdx.x * 8 >= nq && a.q_count) {  // whole CTA beyond the frame's keypoint count: only the defaults
-    if (q < a.nq && lane == 0) { a.out_dist[fq + q] = a.thr; a.out_idx[fq + q] = -1; }
-    return;
-  }
-  const bool active = q < nq && (a.q_use == nullptr || a.q_use[q]);
-  uint4 qd[D16];
-  double kx = 0, ky = 0;
-  if (active) {
-    load_query<D16>(a.q_desc, (int)(fq + q), qd);
-    if (a.q_kp) { kx = (double)a.q_kp[fq + q].x; ky = (double)a.q_kp[fq + q].y; }  // MultiFrame::getKeypoint: float -> double
-    else { kx = a.q_xy[2 * q]; ky = a.q_xy[2 * q + 1]; }
-  }
-  unsigned long long best = ((unsigned long long)a.thr << 32);
-  const int n_tiles = (a.nc + kTile - 1) / kTile;
-  const double2 far = make_double2(INFINITY, INFINITY);
-  auto load_lm = [&](int tile) { const int c = tile * kTile + (int)threadIdx.x; return (tile < n_tiles && c < a.nc) ? __ldg(&a.c_lm[c]) : -1; };
-  auto load_proj = [&](int lm) {
-    double2 p = far;
-    if (lm >= 0 && a.lm_is3d[lm]) p = make_double2(lm_proj[2 * lm], lm_proj[2 * lm + 1]);
-    return p;
-  };
-  int lm_next = load_lm(1);
-  double2 proj_cur = load_proj(load_lm(0));
-  if (n_tiles > 0) stage_tile_async<D16>(a.c_desc, a.nc, 0, s_desc[0]);
-  for (int t = 0; t < n_tiles; t++) {
-    const int buf = t & 1;
-    s_proj[buf][threadIdx.x] = proj_cur;
-    if (t + 1 < n_tiles) {
-      stage_tile_async<D16>(a.c_desc, a.nc, (t + 1) * kTile, s_desc[buf ^ 1]);
-      proj_cur = load_proj(lm_next);   // consumed at the top of the next iteration
-      lm_next = load_lm(t + 2);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+  if (a.q_kp) { x = (double)a.q_kp[fq + k].x; y = (double)a.q_kp[fq + k].y; }  // MultiFrame::getKeypoint: float -> double
+  else { x = a.q_xy[2 * k]; y = a.q_xy[2 * k + 1]; }
+}
+__device__ __forceinline__ int m1_cell_of(const M1Args& a, double x, double y)
+{
+  int cx = (int)floor(x / a.cell), cy = (int)floor(y / a.cell);
+  cx = min(max(cx, 0), a.gx - 1); cy = min(max(cy, 0), a.gy - 1);
+  return cy * a.gx + cx;
+}
+
+__global__ void __launch_bounds__(256) k_m1_bin(M1Args a)
+{
+  __shared__ int cnt[kMaxCells + 1];
+  const int frame = blockIdx.x;
+  const size_t fq = (size_t)frame * a.q_stride;
+  const int nq = a.q_count ? min(a.q_count[frame], a.nq) : a.nq;
+  const int n_cells = a.gx * a.gy;
+  for (int i = threadIdx.x; i <= n_cells; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  for (int k = threadIdx.x; k < a.nq; k += blockDim.x) {
+    a.best[fq + k] = ((unsigned long long)a.thr << 32) | 0xffffffffull;
+    if (k < nq && (a.q_use == nullptr || a.q_use[k])) {
+      double x, y; m1_kp_xy(a, fq, k, x, y);
+      if (x == x && y == y) atomicAdd(&cnt[m1_cell_of(a, x, y)], 1);
     }
-    __syncthreads();
-    if (active) {
-      const int tile0 = t * kTile;
-#pragma unroll 2
-      for (int j = 0; j < kTile / 32; j++) {
-        const int ci = j * 32 + lane;
-        const double2 p = s_proj[buf][ci];
-        const double dx = p.x - kx, dy = p.y - ky;
-        const double d2 = dx * dx + dy * dy;
-        if (!(d2 > a.thr_sq)) {
-          const uint32_t d = hamming<D16>(qd, s_desc[buf], ci);
-          const unsigned long long key = ((unsigned long long)d << 32) | (unsigned)(tile0 + ci);
-          if (key < best) best = key;
-        }
-      }
-    }
-    __syncthreads();
   }
-  if (q >= a.nq) return;
+  __syncthreads();
+  // exclusive scan of the cell counts (<= 4096 cells): one warp, 128 cells per lane
+  if (threadIdx.x < 32) {
+    const int per = (n_cells + 31) / 32, beg = min((int)threadIdx.x * per, n_cells), end = min(beg + per, n_cells);
+    int s = 0;
+    for (int i = beg; i < end; i++) s += cnt[i];
+    int incl = s;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+    int run = incl - s;
+    for (int i = beg; i < end; i++) { const int c = cnt[i]; cnt[i] = run; run += c; }
+    if (threadIdx.x == 31) cnt[n_cells] = incl;
+  }
+  __syncthreads();
+  int32_t* off = a.cell_off + (size_t)frame * (kMaxCells + 1);
+  for (int i = threadIdx.x; i <= n_cells; i += blockDim.x) off[i] = cnt[i];
+  __syncthreads();
+  int32_t* list = a.cell_list + fq;
+  for (int k = threadIdx.x; k < nq; k += blockDim.x) {
+    if (a.q_use == nullptr || a.q_use[k]) {
+      double x, y; m1_kp_xy(a, fq, k, x, y);
+      if (x == x && y == y) list[atomicAdd(&cnt[m1_cell_of(a, x, y)], 1)] = k;
+    }
+  }
+}
+
+template <int D16>
+__global__ void __launch_bounds__(128) k_m1_match(M1Args a)
+{
+  const int frame = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.nc) return;
+  const int lm = __ldg(&a.c_lm[c]);
+  if (!a.lm_is3d[lm]) return;
+  const double* lp = a.lm_proj + (size_t)frame * a.proj_stride + 2 * (size_t)lm;
+  const double px = lp[0], py = lp[1];
+  const size_t fq = (size_t)frame * a.q_stride;
+  const int32_t* off = a.cell_off + (size_t)frame * (kMaxCells + 1);
+  const int32_t* list = a.cell_list + fq;
+  int cx0 = 0, cx1 = a.gx - 1, cy0 = 0, cy1 = a.gy - 1;   // NaN projections are not gated by the reference: visit all
+  if (px == px && py == py) {
+    const double fx = floor(px / a.cell), fy = floor(py / a.cell);
+    if (!(fabs(fx) < 1e8) || !(fabs(fy) < 1e8)) return;   // infinitely far away: every gate fails
+    cx0 = max((int)fx - 1, 0); cx1 = min((int)fx + 1, a.gx - 1);
+    cy0 = max((int)fy - 1, 0); cy1 = min((int)fy + 1, a.gy - 1);
+  }
+  uint4 cd[D16];
+  bool loaded = false;
+  for (int cy = cy0; cy <= cy1; cy++) {
+    if (cx0 > cx1) break;
+    const int beg = off[cy * a.gx + cx0], end = off[cy * a.gx + cx1 + 1];   // cells of one row are contiguous
+    for (int i = beg; i < end; i++) {
+      const int k = list[i];
+      double kx, ky; m1_kp_xy(a, fq, k, kx, ky);
+      const double dx = px - kx, dy = py - ky;
+      const double d2 = dx * dx + dy * dy;
+      if (d2 > a.thr_sq) continue;
+      if (!loaded) { load_query<D16>(a.c_desc, c, cd); loaded = true; }
+      const uint4* qp = reinterpret_cast<const uint4*>(a.q_desc) + (fq + k) * D16;
+      uint32_t d = 0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); if (t < best) best = t; }
-  if (lane == 0) {
-    const uint32_t d = (uint32_t)(best >> 32);
-    if (active && d < a.thr) { a.out_dist[fq + q] = d; a.out_idx[fq + q] = a.c_lm[(uint32_t)best]; }
-    else { a.out_dist[fq + q] = a.thr; a.out_idx[fq + q] = -1; }
+      for (int w = 0; w < D16; w++) {
+        const uint4 qv = __ldg(qp + w);
+        d += __popcll(((unsigned long long)(qv.x ^ cd[w].x) << 32) | (qv.y ^ cd[w].y));
+        d += __popcll(((unsigned long long)(qv.z ^ cd[w].z) << 32) | (qv.w ^ cd[w].w));
+      }
+      if (d < a.thr) atomicMin(&a.best[fq + k], ((unsigned long long)d << 32) | (unsigned)c);
+    }
   }
+}
+
+__global__ void __launch_bounds__(256) k_m1_unpack(M1Args a)
+{
+  const int frame = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.nq) return;
+  const size_t fq = (size_t)frame * a.q_stride;
+  const unsigned long long b = a.best[fq + k];
+  const uint32_t d = (uint32_t)(b >> 32);
+  if (d < a.thr) { a.out_dist[fq + k] = d; a.out_idx[fq + k] = a.c_lm[(uint32_t)b]; }
+  else { a.out_dist[fq + k] = a.thr; a.out_idx[fq + k] = -1; }
+}
+
+static void m1_grid(double thr, double max_x, double max_y, int& cell, int& gx, int& gy)
+{
+  cell = (int)ceil(thr); if (cell < 8) cell = 8;
+  for (;;) {
+    gx = (int)(max_x / cell) + 1; gy = (int)(max_y / cell) + 1;
+    if ((long long)gx * gy <= kMaxCells) break;
+    cell *= 2;
+  }
+}
+
+static int m1_launch(okb_context* ctx, M1Args& a, int D, int n_frames, cudaStream_t st)
+{
+  k_m1_bin<<<n_frames, 256, 0, st>>>(a);
+  if (a.nc > 0) {
+    if (D == 64) k_m1_match<4><<<dim3((a.nc + 127) / 128, n_frames), 128, 0, st>>>(a);
+    else k_m1_match<3><<<dim3((a.nc + 127) / 128, n_frames), 128, 0, st>>>(a);
+  }
+  k_m1_unpack<<<dim3((a.nq + 255) / 256, n_frames), 256, 0, st>>>(a);
+  ctx->launches += a.nc > 0 ? 3 : 2;
+  OKB_CUDA(cudaGetLastError());
+  return OKB_OK;
 }
 
 // M5: per landmark (group of descriptors) the best keypoint over (descriptor, k) order
@@ -479,10 +559,15 @@ int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc,
   OKB_CHECK_ARGS(ctx && !bad_D(D) && n_kp >= 0 && n_cand >= 0 && n_lm >= 0 && out_dist && out_lm, "okb_match_map3d");
   OKB_CHECK_ARGS(n_kp == 0 || (kp_desc && kp_xy), "okb_match_map3d");
   OKB_CHECK_ARGS(n_cand == 0 || (cand_desc && cand_lm && lm_proj && lm_is3d), "okb_match_map3d");
+  OKB_CHECK_ARGS(reprojection_threshold >= 0.0 && reprojection_threshold < 1e6, "okb_match_map3d");
   if (n_kp == 0) return OKB_OK;
   OKB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->match.stream;
-  MatchArgs a; memset(&a, 0, sizeof(a));
+  double max_x = 0, max_y = 0;   // extent of the keypoint cloud (sizes the grid; not part of the arithmetic)
+  for (int k = 0; k < n_kp; k++) { if (kp_xy[2 * k] > max_x) max_x = kp_xy[2 * k]; if (kp_xy[2 * k + 1] > max_y) max_y = kp_xy[2 * k + 1]; }
+  if (!(max_x < 1e6)) max_x = 1e6; if (!(max_y < 1e6)) max_y = 1e6;
+  M1Args a; memset(&a, 0, sizeof(a));
+  m1_grid(reprojection_threshold, max_x, max_y, a.cell, a.gx, a.gy);
   size_t o_dist = 0, o_idx = 0, in_end = 0;
   for (int pass = 0; pass < 2; pass++) {
     Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
@@ -491,15 +576,15 @@ int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc,
     a.c_desc = A.in(cand_desc, (size_t)n_cand * D); a.c_lm = A.in(cand_lm, (size_t)n_cand);
     a.lm_proj = A.in(lm_proj, (size_t)n_lm * 2); a.lm_is3d = A.in(lm_is3d, (size_t)n_lm);
     in_end = A.off;
+    a.cell_off = A.out<int32_t>(kMaxCells + 1, nullptr); a.cell_list = A.out<int32_t>(n_kp, nullptr);
+    a.best = A.out<unsigned long long>(n_kp, nullptr);
     a.out_dist = A.out<uint32_t>(n_kp, &o_dist); a.out_idx = A.out<int32_t>(n_kp, &o_idx);
     if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
   }
   a.nq = n_kp; a.nc = n_cand; a.thr = match_threshold; a.thr_sq = reprojection_threshold * reprojection_threshold;
   OKB_CUDA(cudaMemcpyAsync(ctx->match.d_buf, ctx->match.h_buf, in_end, cudaMemcpyHostToDevice, st));
-  const int grid = (n_kp + 7) / 8;
-  if (D == 64) k_match_map3d<4><<<grid, 256, 0, st>>>(a); else k_match_map3d<3><<<grid, 256, 0, st>>>(a);
-  ctx->launches++;
-  OKB_CUDA(cudaGetLastError());
+  int rc = m1_launch(ctx, a, D, 1, st);
+  if (rc) return rc;
   uint8_t* h = (uint8_t*)ctx->match.h_buf; uint8_t* d = (uint8_t*)ctx->match.d_buf;
   OKB_CUDA(cudaMemcpyAsync(h + o_dist, d + o_dist, (o_idx - o_dist) + (size_t)n_kp * 4, cudaMemcpyDeviceToHost, st));
   OKB_CUDA(cudaStreamSynchronize(st));
@@ -638,17 +723,17 @@ int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand
   CamWorkspace& ws = ctx->cams[cam];
   OKB_CHECK_ARGS(n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_map3d_device");
   OKB_CHECK_ARGS(n_cand == 0 || (d_cand_desc && d_cand_lm && d_lm_proj && d_lm_is3d), "okb_match_map3d_device");
+  OKB_CHECK_ARGS(reprojection_threshold >= 0.0 && reprojection_threshold < 1e6, "okb_match_map3d_device");
   OKB_CUDA(cudaSetDevice(ctx->device));
-  MatchArgs a; memset(&a, 0, sizeof(a));
+  M1Args a; memset(&a, 0, sizeof(a));
+  m1_grid(reprojection_threshold, ws.cfg.width, ws.cfg.height, a.cell, a.gx, a.gy);
   a.nq = ws.kp_cap; a.q_count = ws.d_count; a.q_stride = (size_t)ws.kp_cap; a.proj_stride = (size_t)n_lm * 2;
   a.q_desc = ws.d_desc; a.q_kp = ws.d_kp;
   a.nc = n_cand; a.c_desc = d_cand_desc; a.c_lm = d_cand_lm; a.lm_proj = d_lm_proj; a.lm_is3d = d_lm_is3d;
   a.thr = match_threshold; a.thr_sq = reprojection_threshold * reprojection_threshold;
+  a.cell_off = ws.d_m1_cell_off; a.cell_list = ws.d_m1_cell_list; a.best = ws.d_m1_best;
   a.out_dist = d_out_dist; a.out_idx = d_out_lm;
-  k_match_map3d<4><<<dim3((ws.kp_cap + 7) / 8, n_frames), 256, 0, ws.stream>>>(a);
-  ctx->launches++;
-  OKB_CUDA(cudaGetLastError());
-  return OKB_OK;
+  return m1_launch(ctx, a, 64, n_frames, ws.stream);
 }
 
 int okb_match_place(okb_context_t* ctx, int D, int n_lm, const int32_t* lm_offsets, const uint8_t* lm_desc, int n_kp,

@@ -62,6 +62,7 @@ _PROTOS = {
     "okb_num_layers": (i32, [vp, i32]),
     "okb_layer_info": (i32, [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "okb_fetch_layer": (i32, [vp, i32, i32, i32, vp, vp]),
+    "okb_debug_stamps": (i32, [vp, i32, i32, vp]),
     "okb_pyramid_score_bytes": (C.c_int64, [vp, i32]),
     "okb_enable_timers": (i32, [vp, i32]),
     "okb_reset_timers": (i32, [vp]),

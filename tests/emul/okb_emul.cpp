@@ -18,6 +18,7 @@ struct Kp { float x, y, size, angle, response; int32_t octave, class_id; };
 struct HostLayer { int w, h, pitch; float scale, offset; std::vector<uint8_t> img, score; std::vector<uint32_t> touch; };
 
 static HostTables* g_tables = nullptr;
+static int closed_form_mismatches = 0;
 
 static void resize_layer(const HostLayer& s, HostLayer& d)
 {
@@ -91,7 +92,22 @@ extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int th
   auto emit = [&](const Cand& c) {
     if (c.r.own_touch == 1) { for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) touch(c.layer, c.x + dx, c.y + dy, c.key); }
     else if (c.r.own_touch == 2) { for (int dy = -1; dy <= 2; dy++) for (int dx = -1; dx <= 2; dx++) touch(c.layer, c.x + dx, c.y + dy, c.key); }
-    if (c.r.has_above) for_each_above_touch(c.layer, c.x, c.y, c.r.above, [&](int x, int y) { touch(c.layer + 1, x, y, c.key); });
+    if (c.r.has_above) {
+      for_each_above_touch(c.layer, c.x, c.y, c.r.above, [&](int x, int y) { touch(c.layer + 1, x, y, c.key); });
+      // the device emits the same set through the closed form (one lane per query): check the two enumerations agree
+      std::vector<std::pair<int, int>> a, b;
+      for_each_above_touch(c.layer, c.x, c.y, c.r.above, [&](int x, int y) { a.push_back({x, y}); });
+      ScanIter it; above_window(c.layer, c.x, c.y, it);
+      for (int q = 0; q < c.r.above.n_queries; q++) {
+        int X, Y; bool blk; above_query_pos(it, q, X, Y, blk);
+        b.push_back({X, Y});
+        if (blk) { b.push_back({X + 1, Y}); b.push_back({X, Y + 1}); b.push_back({X + 1, Y + 1}); }
+      }
+      if (!c.r.above.exited) for (int j = 0; j < 9; j++) b.push_back({c.r.above.max_x + j % 3 - 1, c.r.above.max_y + j / 3 - 1});
+      std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end());
+      std::sort(b.begin(), b.end()); b.erase(std::unique(b.begin(), b.end()), b.end());
+      if (a != b) closed_form_mismatches++;
+    }
   };
   // phase: refine (pure) + touches of the non-tie maxima
   for (auto& c : C) { refine_candidate(L, n_layers, c.layer, c.x, c.y, threshold, c.r); if (!c.tie) emit(c); }
@@ -188,6 +204,7 @@ extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int th
     }
     kp_out[k] = p;
   }
+  if (closed_form_mismatches) return -1000 - closed_form_mismatches;
   if (stats) { stats[0] = (int)C.size(); stats[1] = (int)ties.size(); stats[2] = rounds; stats[3] = raw; }
   return (int)kps.size();
 }
