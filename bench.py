@@ -3,7 +3,8 @@
 
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
 A step = one pass of the hot path over one batch of synthetic stereo frames:
-  detect+describe of both cameras (batched launch), M1 match-to-map of every frame of both cameras.
+  detect+describe+back-project of both cameras (batched launches), M1 match-to-map of every frame of both cameras,
+  M4 stereo match camera 0 -> camera 1 of every frame.
   * value : inputs (images, landmark pool) already resident in HBM, results left in HBM, device-timed (CUDA events).
   * e2e   : the same work through the reference-facing calls with HOST buffers, per stereo frame (streaming use):
             Frontend.detectAndDescribe per camera (one host thread per camera, like ThreadedSlam.cpp:432-448), then
@@ -185,7 +186,11 @@ def main():
     warm = max(args.warmup, 3)
     fe = Frontend(2, W, H, device=local_rank, max_batch=B)
     fe.configure(threshold=cfg["threshold"], octaves=cfg["octaves"], max_keypoints=cfg["max_kp"])
+    for c in range(2):   # radial-tangential pinhole cameras (EuRoC-like intrinsics scaled to the image size)
+        fe.setCameraModel(c, "radialtangential", (cfg["f"], cfg["f"] * 0.997), (W / 2 - 8.8 + 12 * c, H / 2 + 8.4 + 7 * c),
+                          [-0.2834, 0.0740, 0.00019, 1.76e-05])
     ctx = fe.ctx
+    C_WC = [np.eye(3), np.eye(3)]; r_WC = [np.zeros(3), np.array([0.11, 0.0, 0.0])]
     # ---- synthetic inputs: ring * B stereo frames per rank (ring * B * 2 * W * H bytes > L2 so steps do not hit in L2)
     n_frames = ring * B
     Lh, Rh = make_frames(cfg, n_frames, 1000 + 100 * rank)
@@ -204,6 +209,8 @@ def main():
     L_.okb_device_features(ctx, 0, None, None, None, C.byref(cap))
     kp_cap = cap.value
     d_out = [dict(dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), lm=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda")) for _ in range(2)]
+    d_st = dict(k1=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"),
+                hp=torch.zeros((B, kp_cap, 4), dtype=torch.float64, device="cuda"), init=torch.zeros((B, kp_cap), dtype=torch.uint8, device="cuda"))
     streams = [torch.cuda.ExternalStream(L_.okb_stream(ctx, c)) for c in range(2)]
 
     chain = [torch.cuda.Event() for _ in range(2)]
@@ -219,6 +226,10 @@ def main():
                                                 len(dm["is3d"]), dm["proj"].data_ptr(), dm["is3d"].data_ptr(), 20.0, 60,
                                                 d_out[c]["dist"].data_ptr(), d_out[c]["lm"].data_ptr()))
             chain[c].record(streams[c])
+        # M4: stereo matching camera 0 -> camera 1 of every frame of the batch (back-projection on the device)
+        okl.check(L_.okb_match_stereo_device(ctx, 0, 1, B, C_WC[0].ctypes.data, r_WC[0].ctypes.data, C_WC[1].ctypes.data,
+                                             r_WC[1].ctypes.data, 60, d_st["k1"].data_ptr(), d_st["dist"].data_ptr(),
+                                             d_st["hp"].data_ptr(), d_st["init"].data_ptr()))
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,47 +280,31 @@ def main():
                 "images_per_pass": B, "ms_per_pass": ps_total_ms / passes, "launches_per_pass": ps_total_launches / passes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
 
-    # ---- e2e: host buffers through the Frontend mirror, per stereo frame, one host thread per camera for detection
-    from okvis2_b200.synth import rot
-    T0 = np.concatenate([np.eye(3), np.zeros((3, 1))], 1).reshape(12)
-    r1 = np.array([0.11, 0.0, 0.0]); T1 = np.concatenate([np.eye(3), -r1[:, None]], 1).reshape(12)
-    e2e_frames = min(n_frames, max(8, 2 * B))
-    h2d = d2h = 0
-
-    def e2e_frame(i):
-        nonlocal h2d, d2h
-        mf = MultiFrame(2)
-        mf.setImage(0, Lh[i]); mf.setImage(1, Rh[i])
-        th = threading.Thread(target=fe.detectAndDescribe, args=(1, mf))
-        th.start(); fe.detectAndDescribe(0, mf); th.join()
-        f0, f1 = mf.frames
-        e0 = pinhole_rays(f0.keypoints, cfg, np.eye(3)); e1 = pinhole_rays(f1.keypoints, cfg, np.eye(3))
-        v0 = np.ones(len(e0), np.uint8); v1 = np.ones(len(e1), np.uint8)
-        fe.matchStereo(f0.descriptors, v0, e0, f0.keypoints["size"] / cfg["f"], f1.descriptors, v1, e1,
-                       f1.keypoints["size"] / cfg["f"], np.zeros(3), r1, T0, T1)
-        for c, fr in enumerate((f0, f1)):
-            xy = np.stack([fr.keypoints["x"], fr.keypoints["y"]], 1).astype(np.float64)
-            m = maps[c]
-            fe.matchToMapByThread(fr.descriptors, xy, None, m["cand_desc"], m["cand_lm"], m["lm_proj"], m["lm_is3d"])
-            h2d += W * H + fr.descriptors.nbytes + xy.nbytes + m["cand_desc"].nbytes + m["cand_lm"].nbytes + m["lm_proj"].nbytes + m["lm_is3d"].nbytes
-            d2h += fr.keypoints.nbytes + fr.descriptors.nbytes + 8 * len(fr.keypoints)
-        h2d += f0.descriptors.nbytes + f1.descriptors.nbytes + 2 * (e0.nbytes + e1.nbytes)
-        d2h += 45 * len(f0.keypoints)
-
-    for i in range(3):
-        e2e_frame(i)
-    h2d = d2h = 0
+    # ---- e2e: HOST buffers through the C ABI, per stereo frame (streaming use), driven by the C++ host loop of
+    #      bench/e2e_driver.cpp (what an integrator of the library writes; one host thread per camera for detection,
+    #      ThreadedSlam.cpp:432-448; then okb_match_stereo and okb_match_map3d). All H2D/D2H copies are inside.
+    e2e_frames = min(n_frames, max(16, 4 * B))
+    drv = C.CDLL(os.path.join(ROOT, "bench", "libokb_e2e.so"))
+    PP = C.POINTER(C.c_void_p)
+    arr_i = lambda v: (C.c_int * 2)(*v)
+    arr_p = lambda v: (C.c_void_p * 2)(*[x.ctypes.data for x in v])
+    keep = [[np.ascontiguousarray(m[k]) for m in maps] for k in ("cand_desc", "cand_lm", "lm_proj", "lm_is3d")]
+    sec = C.c_double(); h2d = C.c_longlong(); d2h = C.c_longlong(); nkp = C.c_longlong(); nm = C.c_longlong()
+    drv.okb_e2e_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_frames):
-        e2e_frame(i)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    rc = drv.okb_e2e_run(ctx, e2e_frames, 4, W, H, Lh.ctypes.data, Rh.ctypes.data, kp_cap, cfg["f"],
+                         arr_i([len(x) for x in keep[1]]), arr_p(keep[0]), arr_p(keep[1]), arr_i([len(x) for x in keep[3]]),
+                         arr_p(keep[2]), arr_p(keep[3]), C.byref(sec), C.byref(h2d), C.byref(d2h), C.byref(nkp), C.byref(nm))
+    okl.check(rc)
+    e2e_s = sec.value
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
-    e2e = {"value": world * e2e_frames / e2e_s, "unit": "stereo frames/s", "h2d_bytes_per_step": int(h2d / e2e_frames),
-           "d2h_bytes_per_step": int(d2h / e2e_frames), "step": "one stereo frame (2 detectAndDescribe + matchStereo + 2 matchToMap)",
-           "frames": e2e_frames}
+    e2e = {"value": world * e2e_frames / e2e_s, "unit": "stereo frames/s", "h2d_bytes_per_step": int(h2d.value / e2e_frames),
+           "d2h_bytes_per_step": int(d2h.value / e2e_frames), "ms_per_stereo_frame": 1e3 * e2e_s / e2e_frames,
+           "step": "one stereo frame: 2x okb_detect_describe (one host thread per camera) + okb_match_stereo + 2x okb_match_map3d, host buffers",
+           "frames": e2e_frames, "keypoints_per_frame": nkp.value / e2e_frames / 2, "matches_per_frame": nm.value / e2e_frames}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
     cpu = None

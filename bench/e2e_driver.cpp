@@ -1,0 +1,101 @@
+// bench/e2e_driver.cpp -- the host loop a C++ integrator of libokvis_b200.so runs per stereo frame, used by bench.py for
+// the `e2e` figure (HOST buffers in, HOST buffers out, every H2D/D2H copy inside the timed region). It mirrors the
+// reference's per-frame driver: one host thread per camera for detect+describe
+// (okvis_multisensor_processing/src/ThreadedSlam.cpp:432-448), then stereo matching (Frontend::matchStereo,
+// Frontend.cpp:1982) and map matching (Frontend::matchToMap, Frontend.cpp:1171) from the main thread.
+// Only the C ABI of include/okvis_b200.h is used.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../include/okvis_b200.h"
+
+namespace {
+struct Worker {  // persistent detection thread of one camera
+  std::thread th; std::mutex m; std::condition_variable cv;
+  bool has_job = false, done = false, quit = false;
+  std::function<void()> job;
+  void start() {
+    th = std::thread([this] {
+      std::unique_lock<std::mutex> lk(m);
+      for (;;) {
+        cv.wait(lk, [this] { return has_job || quit; });
+        if (quit) return;
+        lk.unlock(); job(); lk.lock();
+        has_job = false; done = true; cv.notify_all();
+      }
+    });
+  }
+  void submit(std::function<void()> j) { std::lock_guard<std::mutex> lk(m); job = std::move(j); has_job = true; done = false; cv.notify_all(); }
+  void wait() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [this] { return done; }); }
+  void stop() { { std::lock_guard<std::mutex> lk(m); quit = true; cv.notify_all(); } th.join(); }
+};
+}  // namespace
+
+extern "C" int okb_e2e_run(okb_context_t* ctx, int n_frames, int warmup, int W, int H, const uint8_t* left, const uint8_t* right,
+                           int cap, double f, const int* n_cand, const uint8_t* const* cand_desc, const int32_t* const* cand_lm,
+                           const int* n_lm, const double* const* lm_proj, const uint8_t* const* lm_is3d, double* seconds,
+                           long long* h2d_bytes, long long* d2h_bytes, long long* total_kp, long long* total_matches)
+{
+  std::vector<okb_keypoint_t> kp[2]; std::vector<uint8_t> desc[2]; int n[2] = {0, 0}; int rc2[2] = {0, 0};
+  for (int c = 0; c < 2; c++) { kp[c].resize(cap); desc[c].resize((size_t)cap * 64); }
+  std::vector<double> e[2], sof[2], xy[2]; std::vector<uint8_t> valid[2];
+  std::vector<int32_t> k1(cap), lm(cap); std::vector<uint32_t> dist(cap); std::vector<double> hp((size_t)cap * 4); std::vector<uint8_t> init(cap);
+  const double r0[3] = {0, 0, 0}, r1[3] = {0.11, 0, 0};
+  const double T0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}, T1[12] = {1, 0, 0, -0.11, 0, 1, 0, 0, 0, 0, 1, 0};
+  Worker w; w.start();
+  long long h2d = 0, d2h = 0, nkp = 0, nm = 0;
+  const uint8_t* imgs[2] = {left, right};
+  auto frame = [&](int i) -> int {
+    w.submit([&, i] { rc2[1] = okb_detect_describe(ctx, 1, imgs[1] + (size_t)i * W * H, W, kp[1].data(), desc[1].data(), cap, &n[1]); });
+    rc2[0] = okb_detect_describe(ctx, 0, imgs[0] + (size_t)i * W * H, W, kp[0].data(), desc[0].data(), cap, &n[0]);
+    w.wait();
+    if (rc2[0] || rc2[1]) return rc2[0] ? rc2[0] : rc2[1];
+    for (int c = 0; c < 2; c++) {  // Frame::computeBackProjections on the device, then the packing the matchers need
+      e[c].resize((size_t)n[c] * 3); sof[c].resize(n[c]); xy[c].resize((size_t)n[c] * 2); valid[c].resize(n[c]);
+      const int rcb = okb_back_project(ctx, c, n[c], kp[c].data(), e[c].data(), valid[c].data());
+      if (rcb) return rcb;
+      for (int k = 0; k < n[c]; k++) {   // e_W = (C_WC * e_C).normalized() with C_WC = I
+        const double x = e[c][3 * k], y = e[c][3 * k + 1], z = e[c][3 * k + 2];
+        const double nn = sqrt((x * x + y * y) + z * z);
+        e[c][3 * k] = x / nn; e[c][3 * k + 1] = y / nn; e[c][3 * k + 2] = z / nn;
+        sof[c][k] = (double)kp[c][k].size / f; xy[c][2 * k] = kp[c][k].x; xy[c][2 * k + 1] = kp[c][k].y;
+      }
+      h2d += (long long)n[c] * 28; d2h += (long long)n[c] * 25;
+    }
+    int rc = okb_match_stereo(ctx, 64, n[0], desc[0].data(), valid[0].data(), e[0].data(), sof[0].data(), n[1], desc[1].data(),
+                              valid[1].data(), e[1].data(), sof[1].data(), r0, r1, T0, T1, 60, k1.data(), dist.data(), hp.data(), init.data());
+    if (rc) return rc;
+    for (int k = 0; k < n[0]; k++) nm += k1[k] >= 0;
+    h2d += (long long)(n[0] + n[1]) * (64 + 24 + 8 + 2 * 8 + 1); d2h += (long long)n[0] * (4 + 4 + 32 + 1);
+    for (int c = 0; c < 2; c++) {
+      rc = okb_match_map3d(ctx, 64, n[c], desc[c].data(), xy[c].data(), nullptr, n_cand[c], cand_desc[c], cand_lm[c], n_lm[c],
+                           lm_proj[c], lm_is3d[c], 20.0, 60, dist.data(), lm.data());
+      if (rc) return rc;
+      for (int k = 0; k < n[c]; k++) nm += lm[k] >= 0;
+      h2d += (long long)W * H + (long long)n[c] * (64 + 16) + (long long)n_cand[c] * 68 + (long long)n_lm[c] * 17;
+      d2h += (long long)n[c] * (28 + 64 + 8);
+      nkp += n[c];
+    }
+    return 0;
+  };
+  int rc = 0;
+  for (int i = 0; i < warmup && !rc; i++) rc = frame(i % n_frames);
+  h2d = d2h = nkp = nm = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < n_frames && !rc; i++) rc = frame(i);
+  if (!rc) rc = okb_sync(ctx);
+  const auto t1 = std::chrono::steady_clock::now();
+  w.stop();
+  *seconds = std::chrono::duration<double>(t1 - t0).count();
+  *h2d_bytes = h2d; *d2h_bytes = d2h; *total_kp = nkp; *total_matches = nm;
+  return rc;
+}

@@ -106,6 +106,19 @@ int okb_reset_timers(okb_context_t* ctx);
 int okb_get_timers(okb_context_t* ctx, int cam, double* pyramid_score_ms, int64_t* pyramid_score_launches,
                    double* total_ms);
 
+/* ---- D4: back-projection. Replaces okvis::Frame::computeBackProjections (okvis_cv/include/okvis/implementation/Frame.hpp:
+ *      178-193) -> PinholeCamera<D>::backProject (cameras/implementation/PinholeCamera.hpp:574-592) -> Distortion::undistort.
+ *      model: 0 = no distortion, 1 = radial-tangential (k1,k2,p1,p2; 5 Gauss-Newton iterations, exact fp64),
+ *             2 = equidistant (k1..k4; 20 iterations; uses atan, equal to libm within the last bits). */
+typedef struct {
+  int32_t model, reserved;
+  double fu, fv, cu, cv;
+  double k[4];
+} okb_camera_model_t;
+int okb_set_camera_model(okb_context_t* ctx, int cam, const okb_camera_model_t* model);
+/* rays_out: n x 3 doubles (x, y, 1); valid_out: n success flags (Frame::backProjectionsValid_). Host buffers. */
+int okb_back_project(okb_context_t* ctx, int cam, int n, const okb_keypoint_t* kp, double* rays_out, uint8_t* valid_out);
+
 /* ---- matchers. Descriptors are n x D u8, D in {48, 64}. "First in the reference's iteration order wins ties"
  *      (strict <) is honoured bit-exactly; geometric gates are evaluated on the device in fp64 without FMA
  *      contraction. Index outputs are -1 / distance outputs are match_threshold when nothing matched. ---- */
@@ -171,6 +184,24 @@ int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand
                            const int32_t* d_cand_lm, int n_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
                            double reprojection_threshold, uint32_t match_threshold, uint32_t* d_out_dist,
                            int32_t* d_out_lm);
+
+/* Device-resident, batched M4 for the benchmark "value" leg and the camera-sharded multi-GPU mode: stereo-matches the
+ * features of camera cam0 (queries) against camera cam1 left on the device by okb_detect_describe_batch_device, frame by
+ * frame. Back-projection (D4, camera models from okb_set_camera_model), e_W = (C_WC * e_C).normalized(), size/f and the
+ * cos tables are computed on the device (cos within 1 ulp of libm). C_WC: row-major 3x3 rotation, r_WC: position.
+ * Outputs: n_frames x capacity(cam0) entries, device pointers. */
+int okb_match_stereo_device(okb_context_t* ctx, int cam0, int cam1, int n_frames, const double C_WC0[9], const double r_WC0[3],
+                            const double C_WC1[9], const double r_WC1[3], uint32_t match_threshold, int32_t* d_out_k1,
+                            uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_initialisable);
+/* Same on explicit device feature blocks (e.g. a peer camera's block received by NCCL all-gather): keypoints
+ * [n_frames][cap], descriptors [n_frames][cap][64], counts [n_frames]. `stream` = cudaStream_t (NULL: the context's
+ * match stream); the caller orders it after the producers of the inputs. */
+int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, const okb_keypoint_t* d_kp0, const uint8_t* d_desc0,
+                                const int32_t* d_count0, const okb_camera_model_t* model0, const double C_WC0[9],
+                                const double r_WC0[3], int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
+                                const int32_t* d_count1, const okb_camera_model_t* model1, const double C_WC1[9],
+                                const double r_WC1[3], uint32_t match_threshold, void* stream, int32_t* d_out_k1,
+                                uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_initialisable);
 
 #ifdef __cplusplus
 }

@@ -6,8 +6,8 @@
 //
 // Pipeline per batch of frames (blockIdx.z / blockIdx.y = frame):
 //   k_resize        INTER_AREA pyramid layers (2/3-sample and half-sample), table driven, bit-exact rounding
-//   k_score         dense AGAST 9-16 score map b0 of every layer (u8), tiles staged in shared memory, 16x2 SIMD min/max
-//   k_nms           3x3 non-max candidates + tie flag, warp-ballot compaction
+//   k_score_nms     dense AGAST 9-16 score map b0 of every layer (u8; tiles staged in shared memory, 16x2 SIMD min/max)
+//                   fused with the 3x3 non-max candidates + tie flag (warp-ballot compaction)
 //   k_refine        sub-pixel / scale refinement of every candidate (pure), cache-touch events of non-tie maxima
 //   k_resolve       order-exact resolution of tied maxima (touch-time map)
 //   k_finalize      order by (layer, y, x), keep the N strongest, drop border keypoints, pattern scale index
@@ -69,15 +69,29 @@ __global__ void __launch_bounds__(256) k_resize(ResizeJobs jobs)
   const ResizeJob& J = jobs.j[ji];
   const int tx = t % jobs.tiles_x[ji], ty = t / jobs.tiles_x[ji];
   const int frame = blockIdx.y;
-  const int x = tx * 32 + (threadIdx.x & 31);
-  const int y0 = ty * 32 + (threadIdx.x >> 5) * 4;
-  if (x >= J.dw) return;
   const uint8_t* src = J.src + (size_t)frame * J.src_frame_stride;
   uint8_t* dst = J.dst + (size_t)frame * J.dst_frame_stride;
   if (J.fast2) {
-#pragma unroll
-    for (int r = 0; r < 4; r++) { const int y = y0 + r; if (y < J.dh) dst[(size_t)y * J.dst_pitch + x] = half_pixel(src, J.src_pitch, x, y); }
+    // tile = 128 x 8 destination pixels; a thread makes 4 of them from two 8-byte source loads
+    const int x = tx * 128 + (threadIdx.x & 31) * 4, y = ty * 8 + (threadIdx.x >> 5);
+    if (x >= J.dw || y >= J.dh) return;
+    const uint8_t* r0 = src + (size_t)(2 * y) * J.src_pitch + 2 * x;
+    const bool vec = ((J.src_pitch & 7) == 0) && ((((uintptr_t)src) & 7) == 0) && (x + 3 < J.dw) && ((J.dst_pitch & 3) == 0);
+    if (vec) {
+      const uint2 a = *reinterpret_cast<const uint2*>(r0), b = *reinterpret_cast<const uint2*>(r0 + J.src_pitch);
+      auto px = [](uint32_t u, uint32_t v, int sh) {
+        return (((u >> sh) & 255u) + ((u >> (sh + 8)) & 255u) + ((v >> sh) & 255u) + ((v >> (sh + 8)) & 255u) + 2u) >> 2;
+      };
+      const uint32_t out = px(a.x, b.x, 0) | (px(a.x, b.x, 16) << 8) | (px(a.y, b.y, 0) << 16) | (px(a.y, b.y, 16) << 24);
+      *reinterpret_cast<uint32_t*>(dst + (size_t)y * J.dst_pitch + x) = out;
+    } else {
+      for (int i = 0; i < 4 && x + i < J.dw; i++) dst[(size_t)y * J.dst_pitch + x + i] = half_pixel(src, J.src_pitch, x + i, y);
+    }
   } else {
+    // tile = 32 x 32 destination pixels, 4 rows per thread
+    const int x = tx * 32 + (threadIdx.x & 31);
+    const int y0 = ty * 32 + (threadIdx.x >> 5) * 4;
+    if (x >= J.dw) return;
     const int xs = J.xs[x], xn = J.xn[x];
     float xa[4];
 #pragma unroll
@@ -96,10 +110,8 @@ __global__ void __launch_bounds__(256) k_resize(ResizeJobs jobs)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// score map. Tile = 64 x 32 pixels, 256 threads, each thread 2 x 4 pixels. Halo 3 (+1 for word alignment).
-constexpr int kTileW = 64, kTileH = 32;
-constexpr int kSmemW = kTileW + 8;   // bytes per smem row: x0-4 .. x0+67
-constexpr int kSmemH = kTileH + 6;
+// score map tiling
+constexpr int kTileW = 56, kTileH = 30;   // (30 + 2) rows x (56 / 4 + 2) groups = 512 score items = 2 per thread
 
 struct TileMap { int n_layers; int tile_prefix[kMaxLayers + 1]; int tiles_x[kMaxLayers]; };
 
@@ -141,11 +153,26 @@ __device__ __forceinline__ uint32_t b0_pair(const uint32_t (&v)[16], uint32_t p)
   return __vminu2(__vmaxu2(t, 0x00010001u) - 0x00010001u, 0x00FE00FEu);
 }
 
-// score map: tile = 64 x 32 pixels, 256 threads, each thread 2 rows x 4 pixels. Halo 3 (+1 for word alignment).
-__global__ void __launch_bounds__(256) k_score(DeviceLayers dl, TileMap tm, const uint8_t* in0, int in_pitch,
-                                               size_t in_frame_stride, uint8_t* img_block, uint8_t* score_block)
+// Fused score + non-max suppression. Tile = kTileW x kTileH pixels of one layer of one frame, 256 threads.
+//   1. the image tile with a 4-pixel halo (3 for the ring + 1 because candidates need their neighbours' scores) is
+//      staged in shared memory as 32-bit words, zero outside the image;
+//   2. dense scores b0 for the tile + 1-pixel halo ((kTileH+2) rows x (kTileW/4+2) groups of 4 pixels = 512 items, two per
+//      thread) by 16x2 SIMD min/max, written to a
+//      shared score tile and (inner part) to the global score map;
+//   3. 3x3 non-max test (>= all neighbours, tie flag) on the inner pixels from shared memory, warp-ballot compaction of
+//      the candidates into the per-frame list: one u32 per candidate = time key | tie << 31.
+constexpr int kImgW = kTileW + 16;   // bytes per staged image row: x0-8 .. x0+71
+constexpr int kImgH = kTileH + 8;    // rows y0-4 .. y0+35
+constexpr int kScW = kTileW + 8;     // score tile row: x0-4 .. x0+67
+constexpr int kScH = kTileH + 2;     // rows y0-1 .. y0+32
+constexpr int kScoreThreads = 256;
+
+__global__ void __launch_bounds__(kScoreThreads) k_score_nms(DeviceLayers dl, TileMap tm, const uint8_t* in0, int in_pitch,
+                                                   size_t in_frame_stride, uint8_t* img_block, uint8_t* score_block,
+                                                   uint32_t* cand, int32_t* cand_count, int cand_cap, int threshold)
 {
-  __shared__ __align__(16) uint8_t tile[kSmemH][kSmemW];
+  __shared__ __align__(16) uint8_t tile[kImgH][kImgW];
+  __shared__ __align__(16) uint8_t sc[kScH][kScW];
   const int frame = blockIdx.y;
   const int layer = find_layer(tm, blockIdx.x);
   const int t = blockIdx.x - tm.tile_prefix[layer];
@@ -156,11 +183,10 @@ __global__ void __launch_bounds__(256) k_score(DeviceLayers dl, TileMap tm, cons
   else { img = img_block + (size_t)frame * dl.frame_stride + d.offset; pitch = d.pitch; }
   uint8_t* score = score_block + (size_t)frame * dl.frame_stride + d.offset;
   const int x0 = tx * kTileW, y0 = ty * kTileH;
-  // stage the tile: words of 4 bytes, zero outside the image
   const bool word_ok = ((pitch & 3) == 0) && ((((uintptr_t)img) & 3) == 0);
-  for (int i = threadIdx.x; i < kSmemH * (kSmemW / 4); i += 256) {
-    const int r = i / (kSmemW / 4), c = i % (kSmemW / 4);
-    const int y = y0 - 3 + r, x = x0 - 4 + c * 4;
+  for (int i = threadIdx.x; i < kImgH * (kImgW / 4); i += kScoreThreads) {
+    const int r = i / (kImgW / 4), c = i % (kImgW / 4);
+    const int y = y0 - 4 + r, x = x0 - 8 + c * 4;
     uint32_t w = 0;
     if (y >= 0 && y < d.h) {
       const uint8_t* row = img + (size_t)y * pitch;
@@ -173,78 +199,65 @@ __global__ void __launch_bounds__(256) k_score(DeviceLayers dl, TileMap tm, cons
     *reinterpret_cast<uint32_t*>(&tile[r][c * 4]) = w;
   }
   __syncthreads();
-  const int lx = (threadIdx.x & 15) * 4, ly = (threadIdx.x >> 4);
 #pragma unroll 1
-  for (int rr = 0; rr < 2; rr++) {
-    const int yy = ly + rr * 16;
-    const int y = y0 + yy;
-    if (y >= d.h) continue;
-    // words W0 (x-4..x-1), W1 (x..x+3), W2 (x+4..x+7) of the seven rows y-3..y+3
-    uint32_t lo[16], hi[16];
-    uint32_t W[7][3];
+  for (int item = threadIdx.x; item < kScH * (kScW / 4); item += kScoreThreads) {
+    const int rr = item / (kScW / 4), g = item % (kScW / 4);
+    const int y = y0 - 1 + rr, x = x0 - 4 + 4 * g;
+    uint32_t out = 0;
+    if (y >= 3 && y < d.h - 3 && x + 3 >= 3 && x < d.w - 3) {   // warp-divergent only at the image border
+      uint32_t lo[16], hi[16];
+      uint32_t W[7][3];
 #pragma unroll
-    for (int r = 0; r < 7; r++) {
-      const uint32_t* rowp = reinterpret_cast<const uint32_t*>(&tile[yy + r][lx]);
-      W[r][0] = rowp[0]; W[r][1] = rowp[1]; W[r][2] = rowp[2];
-    }
-    // ring in AGAST order: (dx,dy) = (-3,0)(-3,-1)(-2,-2)(-1,-3)(0,-3)(1,-3)(2,-2)(3,-1)(3,0)(3,1)(2,2)(1,3)(0,3)(-1,3)(-2,2)(-3,1)
+      for (int r = 0; r < 7; r++) {
+        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(&tile[rr + r][4 * g]);
+        W[r][0] = rowp[0]; W[r][1] = rowp[1]; W[r][2] = rowp[2];
+      }
 #define OKB_RING(i, dx, dy)                                                                                            \
-    {                                                                                                                  \
-      const uint32_t w = (dx) < 0 ? __funnelshift_r(W[(dy) + 3][0], W[(dy) + 3][1], 8 * (4 + (dx)))                    \
-                                  : ((dx) > 0 ? __funnelshift_r(W[(dy) + 3][1], W[(dy) + 3][2], 8 * (dx)) : W[(dy) + 3][1]); \
-      lo[i] = u16x2_lo(w); hi[i] = u16x2_hi(w);                                                                        \
-    }
-    OKB_RING(0, -3, 0) OKB_RING(1, -3, -1) OKB_RING(2, -2, -2) OKB_RING(3, -1, -3) OKB_RING(4, 0, -3) OKB_RING(5, 1, -3)
-    OKB_RING(6, 2, -2) OKB_RING(7, 3, -1) OKB_RING(8, 3, 0) OKB_RING(9, 3, 1) OKB_RING(10, 2, 2) OKB_RING(11, 1, 3)
-    OKB_RING(12, 0, 3) OKB_RING(13, -1, 3) OKB_RING(14, -2, 2) OKB_RING(15, -3, 1)
+      {                                                                                                                \
+        const uint32_t w = (dx) < 0 ? __funnelshift_r(W[(dy) + 3][0], W[(dy) + 3][1], 8 * (4 + (dx)))                  \
+                                    : ((dx) > 0 ? __funnelshift_r(W[(dy) + 3][1], W[(dy) + 3][2], 8 * (dx)) : W[(dy) + 3][1]); \
+        lo[i] = u16x2_lo(w); hi[i] = u16x2_hi(w);                                                                      \
+      }
+      OKB_RING(0, -3, 0) OKB_RING(1, -3, -1) OKB_RING(2, -2, -2) OKB_RING(3, -1, -3) OKB_RING(4, 0, -3) OKB_RING(5, 1, -3)
+      OKB_RING(6, 2, -2) OKB_RING(7, 3, -1) OKB_RING(8, 3, 0) OKB_RING(9, 3, 1) OKB_RING(10, 2, 2) OKB_RING(11, 1, 3)
+      OKB_RING(12, 0, 3) OKB_RING(13, -1, 3) OKB_RING(14, -2, 2) OKB_RING(15, -3, 1)
 #undef OKB_RING
-    const uint32_t c = W[3][1];
-    const uint32_t r_lo = b0_pair(lo, u16x2_lo(c));
-    const uint32_t r_hi = b0_pair(hi, u16x2_hi(c));
-    uint32_t out = __byte_perm(r_lo, r_hi, 0x6420);
-    // zero the 3-pixel margin (and anything beyond the image)
-    const int x = x0 + lx;
-    uint32_t mask = 0;
-    if (y >= 3 && y < d.h - 3) {
+      const uint32_t c = W[3][1];
+      out = __byte_perm(b0_pair(lo, u16x2_lo(c)), b0_pair(hi, u16x2_hi(c)), 0x6420);
+      uint32_t mask = 0;
 #pragma unroll
       for (int px = 0; px < 4; px++) if (x + px >= 3 && x + px < d.w - 3) mask |= 0xffu << (8 * px);
+      out &= mask;
     }
-    out &= mask;
-    if (x < d.pitch) *reinterpret_cast<uint32_t*>(score + (size_t)y * d.pitch + x) = out;  // pitch is a multiple of 64
+    *reinterpret_cast<uint32_t*>(&sc[rr][4 * g]) = out;
+    if (rr >= 1 && rr <= kTileH && g >= 1 && g <= kTileW / 4 && y < d.h && x < d.pitch)
+      *reinterpret_cast<uint32_t*>(score + (size_t)y * d.pitch + x) = out;   // pitch is a multiple of 64
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// 3x3 non-max candidates. Same tiling as k_score. One u32 per candidate: time key | tie << 31.
-__global__ void __launch_bounds__(256) k_nms(DeviceLayers dl, TileMap tm, const uint8_t* score_block, uint32_t* cand,
-                                             int32_t* cand_count, int cand_cap, int threshold)
-{
-  const int frame = blockIdx.y;
-  const int layer = find_layer(tm, blockIdx.x);
-  const int t = blockIdx.x - tm.tile_prefix[layer];
-  const int tx = t % tm.tiles_x[layer], ty = t / tm.tiles_x[layer];
-  const DeviceLayer d = dl.l[layer];
-  const uint8_t* score = score_block + (size_t)frame * dl.frame_stride + d.offset;
-  const int x0 = tx * kTileW + (threadIdx.x & 15) * 4, yb = ty * kTileH + (threadIdx.x >> 4);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  for (int rr = 0; rr < 2; rr++) {
-    const int y = yb + rr * 16;
-    uint32_t w = 0;
-    const bool row_ok = y >= 3 && y < d.h - 3 && x0 < d.w;
-    if (row_ok) w = *reinterpret_cast<const uint32_t*>(score + (size_t)y * d.pitch + x0);  // pitch is a multiple of 4
+  constexpr int kWords = kTileH * (kTileW / 4);                              // inner words of the tile
+  constexpr int kWordsPadded = (kWords + kScoreThreads - 1) / kScoreThreads * kScoreThreads;
+#pragma unroll 1
+  for (int wi = threadIdx.x; wi < kWordsPadded; wi += kScoreThreads) {        // whole warps iterate together (ballots below)
+    const bool in = wi < kWords;
+    const int r = in ? wi / (kTileW / 4) : 0, g = in ? wi % (kTileW / 4) : 0;  // inner word (row r, pixels 4g..4g+3)
+    const int y = y0 + r, xb = x0 + 4 * g;
+    const uint32_t w = in ? *reinterpret_cast<const uint32_t*>(&sc[r + 1][4 * g + 4]) : 0u;
+    const bool any_corner = ((w & 255u) >= (unsigned)threshold) | (((w >> 8) & 255u) >= (unsigned)threshold) |
+                            (((w >> 16) & 255u) >= (unsigned)threshold) | ((w >> 24) >= (unsigned)threshold);
+    if (!__any_sync(0xffffffffu, any_corner)) continue;
     for (int px = 0; px < 4; px++) {
       const int c = (w >> (8 * px)) & 255;
-      const int x = x0 + px;
       bool is_c = false, tie = false;
-      if (c >= threshold && x >= 3 && x < d.w - 3) {  // the map is the dense b0; only scores >= threshold are corners
-        const uint8_t* s = score + (size_t)y * d.pitch + x;
+      if (c >= threshold) {   // scores are zero in the margin and outside the image
+        const uint8_t* s = &sc[r + 1][4 * g + 4 + px];
         is_c = true;
 #pragma unroll
         for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
           for (int dx = -1; dx <= 1; dx++) {
             if (dx == 0 && dy == 0) continue;
-            const int v = s[dy * d.pitch + dx];
+            const int v = s[dy * kScW + dx];
             if (v > c) is_c = false;
             if (v == c) tie = true;
           }
@@ -257,14 +270,13 @@ __global__ void __launch_bounds__(256) k_nms(DeviceLayers dl, TileMap tm, const 
         base = __shfl_sync(0xffffffffu, base, leader);
         if (is_c) {
           const int pos = base + __popc(m & ((1u << lane) - 1u));
-          if (pos < cand_cap) cand[(size_t)frame * cand_cap + pos] = time_key(layer, x, y) | (tie ? 0x80000000u : 0u);
+          if (pos < cand_cap) cand[(size_t)frame * cand_cap + pos] = time_key(layer, xb + px, y) | (tie ? 0x80000000u : 0u);
         }
       }
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
 // Cache-touch events of one maximum, emitted by a full warp (all arguments warp-uniform): lanes take the positions of
 // the above-layer scan (closed form of the scan order in okb_core.h: rows of [x_1, xa..xb, x1]) and of the 3x3 / 4x4
 // patches, so the divergent, sequential replay of for_each_above_touch never runs on the device.
@@ -963,6 +975,9 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMalloc(&ws.d_desc, (size_t)ws.kp_cap * 64 * B));
   OKB_CUDA(cudaMalloc(&ws.d_count, 4 * B));
   OKB_CUDA(cudaMalloc(&ws.d_status, 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_rays, (size_t)ws.kp_cap * 24 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_rays_valid, (size_t)ws.kp_cap * B));
+  OKB_CUDA(cudaEventCreateWithFlags(&ws.ev_done, cudaEventDisableTiming));
   OKB_CUDA(cudaMalloc(&ws.d_dbg, (size_t)16 * 8 * B));
   OKB_CUDA(cudaMemset(ws.d_dbg, 0, (size_t)16 * 8 * B));
   OKB_CUDA(cudaMalloc(&ws.d_m1_cell_off, (size_t)4097 * 4 * B));
@@ -990,7 +1005,8 @@ void detect_free_camera(okb_context* ctx, int cam)
   }
   cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
   cudaFree(ws.d_cand_count); cudaFree(ws.d_rec); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
-  cudaFree(ws.d_count); cudaFree(ws.d_status); cudaFree(ws.d_m1_cell_off); cudaFree(ws.d_m1_cell_list); cudaFree(ws.d_m1_best); cudaFree(ws.d_dbg);
+  cudaFree(ws.d_count); cudaFree(ws.d_status); cudaFree(ws.d_m1_cell_off); cudaFree(ws.d_m1_cell_list); cudaFree(ws.d_m1_best); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);
+  if (ws.ev_done) cudaEventDestroy(ws.ev_done);
   cudaFreeHost(ws.h_img); cudaFreeHost(ws.h_kp); cudaFreeHost(ws.h_desc); cudaFreeHost(ws.h_count); cudaFreeHost(ws.h_status);
   for (int i = 0; i < 4; i++) if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
   if (ws.stream) cudaStreamDestroy(ws.stream);
@@ -1034,7 +1050,8 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
       J.dst = ws.d_img + g.offset; J.dst_pitch = g.pitch; J.dst_frame_stride = ws.dl.frame_stride;
       J.dw = g.w; J.dh = g.h; J.fast2 = g.fast2;
       J.xs = g.d_xs; J.xn = g.d_xn; J.ys = g.d_ys; J.yn = g.d_yn; J.xa = g.d_xa; J.ya = g.d_ya;
-      jobs.tiles_x[jobs.n] = (g.w + 31) / 32; jobs.tiles_y[jobs.n] = (g.h + 31) / 32;
+      if (g.fast2) { jobs.tiles_x[jobs.n] = (g.w + 127) / 128; jobs.tiles_y[jobs.n] = (g.h + 7) / 8; }
+      else { jobs.tiles_x[jobs.n] = (g.w + 31) / 32; jobs.tiles_y[jobs.n] = (g.h + 31) / 32; }
       total += jobs.tiles_x[jobs.n] * jobs.tiles_y[jobs.n];
       jobs.n++;
     };
@@ -1054,13 +1071,13 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   }
   for (int i = ws.n_layers + 1; i <= kMaxLayers; i++) tm.tile_prefix[i] = tm.tile_prefix[ws.n_layers];
   const int n_tiles = tm.tile_prefix[ws.n_layers];
-  k_score<<<dim3(n_tiles, B), 256, 0, st>>>(ws.dl, tm, d_images, src_pitch, in_stride, ws.d_img, ws.d_score);
+  OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, 4 * B, st));
+  OKB_CUDA(cudaMemsetAsync(ws.d_status, 0, 4 * B, st));
+  k_score_nms<<<dim3(n_tiles, B), kScoreThreads, 0, st>>>(ws.dl, tm, d_images, src_pitch, in_stride, ws.d_img, ws.d_score, ws.d_cand,
+                                                ws.d_cand_count, ws.cand_cap, c.threshold);
   ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
   if (ctx->timers_on) cudaEventRecord(ws.ev[1], st);
   // ---- candidates, refinement, tie resolution, selection
-  OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, 4 * B, st));
-  OKB_CUDA(cudaMemsetAsync(ws.d_status, 0, 4 * B, st));
-  k_nms<<<dim3(n_tiles, B), 256, 0, st>>>(ws.dl, tm, ws.d_score, ws.d_cand, ws.d_cand_count, ws.cand_cap, c.threshold);
   k_refine<<<dim3((ws.cand_cap + 127) / 128, B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
                                                                ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap,
                                                                ws.d_rec, c.threshold, ws.epoch);
@@ -1068,7 +1085,7 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
                                           ws.d_status, ws.d_dbg);
   k_finalize<<<B, 1024, kFinalizeSmem, st>>>(ws.dl, ws.d_cand_count, ws.cand_cap, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,
                                             W, H, c.max_keypoints, ws.kp_cap, ws.d_kp, ws.d_kscale, ws.d_count, ws.d_status, ws.d_dbg);
-  ctx->launches += 4;
+  ctx->launches += 3;
   if (ctx->timers_on) cudaEventRecord(ws.ev[2], st);
   // ---- descriptors
   const int ipitch = W + 1;
@@ -1078,6 +1095,7 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
                                                            ctx->d_pattern, ctx->d_short_pairs, ctx->d_long_pairs, ws.d_kp,
                                                            ws.d_kscale, ws.d_count, ws.kp_cap, ws.d_desc);
   ctx->launches += 3;
+  { int rc = camera_backproject_batch(ctx, cam, B); if (rc) return rc; }
   if (ctx->timers_on) { cudaEventRecord(ws.ev[3], st); ws.pending_timing = 1; }
   OKB_CUDA(cudaGetLastError());
   return OKB_OK;

@@ -78,6 +78,10 @@ struct CamWorkspace {
   int32_t* d_count = nullptr;
   int32_t* d_status = nullptr;  // per frame overflow flags
   // M1 (device-resident form): keypoint grid and merge slots
+  // D4: camera model and the rays of the last batch
+  okb_camera_model_t model; int has_model = 0;
+  double* d_rays = nullptr; uint8_t* d_rays_valid = nullptr;
+  cudaEvent_t ev_done = nullptr;
   long long* d_dbg = nullptr;   // per-frame cycle stamps of the single-CTA kernels (okb_debug_stamps)
   int32_t* d_m1_cell_off = nullptr; int32_t* d_m1_cell_list = nullptr; unsigned long long* d_m1_best = nullptr;
   // pinned staging
@@ -116,6 +120,7 @@ struct okb_context {
   uint32_t* d_size_list = nullptr;         // pattern extent per scale index
   float pattern_scale = 1.0f;
   int timers_on = 0;
+  void* stereo_scratch = nullptr; size_t stereo_cap = 0;   // device scratch of okb_match_stereo_device*
   int64_t launches = 0;
 };
 
@@ -123,6 +128,10 @@ namespace okb {
 int detect_init_camera(okb_context* ctx, int cam);
 void detect_free_camera(okb_context* ctx, int cam);
 int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch);
+int camera_backproject_batch(okb_context* ctx, int cam, int n_frames);
+int camera_stereo_prep(okb_context* ctx, const okb_camera_model_t& model, const double C_WC[9], const okb_keypoint_t* d_kp,
+                       const int32_t* d_count, int cap, int n_frames, double* d_rays, uint8_t* d_valid, double* d_eW, double* d_sof,
+                       double* d_c26, double* d_c6, cudaStream_t st);
 int tables_init(okb_context* ctx, float pattern_scale);
 void tables_free(okb_context* ctx);
 }  // namespace okb

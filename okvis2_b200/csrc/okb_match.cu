@@ -88,7 +88,7 @@ struct MatchArgs {
   const uint8_t* q_desc; const uint8_t* c_desc;
   const uint8_t* q_use;
   // M1
-  const double* q_xy; const okb_keypoint_t* q_kp; const int32_t* q_count; const int32_t* c_lm; const double* lm_proj; const uint8_t* lm_is3d; double thr_sq;
+  const double* q_xy; const okb_keypoint_t* q_kp; const int32_t* c_lm; const double* lm_proj; const uint8_t* lm_is3d; double thr_sq;
   // M2
   const double* q_e; const int32_t* q_prev_lm; const double* c_e; const double* c_r;
   double r0[3], r1[3]; double cos26, cos6;
@@ -98,7 +98,8 @@ struct MatchArgs {
   double T0[12], T1[12];
   uint32_t thr;
   // batched device form (blockIdx.y = frame): element strides of the per-frame arrays, 0 for the single-frame host form
-  size_t q_stride, proj_stride;
+  size_t q_stride, proj_stride, c_stride;
+  const int32_t* q_count; const int32_t* c_count;   // per-frame counts (device) or nullptr
   uint32_t* out_dist; int32_t* out_idx; double* out_hp; uint8_t* out_init; int32_t* out_ctr;
 };
 
@@ -364,38 +365,43 @@ __global__ void __launch_bounds__(256) k_match_gated(MatchArgs a)
   __shared__ uint4 s_desc2[2][D16][kTile];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 8 + warp;
-  const bool active = q < a.nq && (a.q_use == nullptr || a.q_use[q]);
+  // batched device form: blockIdx.y = frame, per-frame strides (elements) and counts; all zero/null for the host form
+  const size_t fq = (size_t)blockIdx.y * a.q_stride, fc = (size_t)blockIdx.y * a.c_stride;
+  const int nq = a.q_count ? min(a.q_count[blockIdx.y], a.nq) : a.nq;
+  const int nc = a.c_count ? min(a.c_count[blockIdx.y], a.nc) : a.nc;
+  const uint8_t* c_desc = a.c_desc + fc * (D16 * 16);
+  const bool active = q < nq && (a.q_use == nullptr || a.q_use[fq + q]);
   uint4 qd[D16];
   V3 eq = V3{0, 0, 0};
   double q_c26 = 0, q_c6 = 0, q_sof = 0;
   int prev_lm = -1;
   if (active) {
-    load_query<D16>(a.q_desc, q, qd);
-    eq = v3(a.q_e + 3 * (size_t)q);
-    if (MODE == MODE_M2) { q_c26 = a.cos26; q_c6 = a.cos6; if (a.q_prev_lm) prev_lm = a.q_prev_lm[q]; }
-    else { q_c26 = a.q_cos26[q]; q_c6 = a.q_cos6[q]; q_sof = a.q_sof[q]; }
+    load_query<D16>(a.q_desc, (int)(fq + q), qd);
+    eq = v3(a.q_e + 3 * (fq + q));
+    if (MODE == MODE_M2) { q_c26 = a.cos26; q_c6 = a.cos6; if (a.q_prev_lm) prev_lm = a.q_prev_lm[fq + q]; }
+    else { q_c26 = a.q_cos26[fq + q]; q_c6 = a.q_cos6[fq + q]; q_sof = a.q_sof[fq + q]; }
   }
   uint32_t best = a.thr;
   int best_idx = -1;
   V3 best_hp = V3{0, 0, 0}; bool have_hp = false; bool best_init = false;
   int ctr = 0, skip_lm = -1;
   const V3 r0 = v3(a.r0), r1 = v3(a.r1);
-  const int n_tiles = (a.nc + kTile - 1) / kTile;
-  if (n_tiles > 0) stage_tile_async<D16>(a.c_desc, a.nc, 0, s_desc2[0]);
+  const int n_tiles = (nc + kTile - 1) / kTile;
+  if (n_tiles > 0) stage_tile_async<D16>(c_desc, nc, 0, s_desc2[0]);
   for (int tt = 0; tt < n_tiles; tt++) {
     const int tile0 = tt * kTile;
     uint4 (*s_desc)[kTile] = s_desc2[tt & 1];
-    if (tt + 1 < n_tiles) { stage_tile_async<D16>(a.c_desc, a.nc, tile0 + kTile, s_desc2[(tt & 1) ^ 1]); cp_async_wait<1>(); }
+    if (tt + 1 < n_tiles) { stage_tile_async<D16>(c_desc, nc, tile0 + kTile, s_desc2[(tt & 1) ^ 1]); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     __syncthreads();
     for (int j = 0; active && j < kTile / 32; j++) {
       const int ci = j * 32 + lane, c = tile0 + ci;
-      if (tile0 + j * 32 >= a.nc) break;
+      if (tile0 + j * 32 >= nc) break;
       uint32_t d = 0xffffu;
       int lm = -1;
-      if (c < a.nc) {
+      if (c < nc) {
         bool ok = true;
-        if (MODE == MODE_M2) { lm = a.c_lm[c]; ok = !a.lm_is3d[lm]; }
+        if (MODE == MODE_M2) { lm = a.c_lm[fc + c]; ok = !a.lm_is3d[lm]; }
         if (ok) d = hamming<D16>(qd, s_desc, ci);
       }
       unsigned m = __ballot_sync(0xffffffffu, d < best);
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(256) k_match_gated(MatchArgs a)
         if (MODE == MODE_M2) {
           lmj = __shfl_sync(0xffffffffu, lm, jl);
           if (lmj == skip_lm) continue;
-          const V3 e0 = v3(a.c_e + 3 * (size_t)cj), rr0 = v3(a.c_r + 3 * (size_t)cj);
+          const V3 e0 = v3(a.c_e + 3 * (fc + cj)), rr0 = v3(a.c_r + 3 * (fc + cj));
           if (dot(e0, eq) < q_c6) {
             const V3 et = normalized(r1 - rr0);
             const V3 n0 = normalized(cross(e0, et));
@@ -429,10 +435,10 @@ __global__ void __launch_bounds__(256) k_match_gated(MatchArgs a)
           }
           if (pass && lmj == prev_lm && prev_lm >= 0) { ctr++; skip_lm = lmj; continue; }
         } else {
-          if (!a.c_valid[cj]) continue;
-          const V3 e1 = v3(a.c_e + 3 * (size_t)cj);
+          if (!a.c_valid[fc + cj]) continue;
+          const V3 e1 = v3(a.c_e + 3 * (fc + cj));
           double c26 = q_c26, c6 = q_c6;
-          if (MODE == MODE_M4) { const double s1 = a.c_sof[cj]; if (q_sof < s1) { c26 = a.c_cos26[cj]; c6 = a.c_cos6[cj]; } }
+          if (MODE == MODE_M4) { const double s1 = a.c_sof[fc + cj]; if (q_sof < s1) { c26 = a.c_cos26[fc + cj]; c6 = a.c_cos6[fc + cj]; } }
           if (MODE == MODE_M3) { if (dot(eq, e1) < 0.5) continue; }
           const Tri t = triangulate_fast(r0, eq, r1, e1, c26, c6);
           pass = t.valid; parallel = t.parallel; hp = t.p;
@@ -462,11 +468,11 @@ __global__ void __launch_bounds__(256) k_match_gated(MatchArgs a)
   }
   if (q >= a.nq) return;
   if (lane == 0) {
-    a.out_dist[q] = best; a.out_idx[q] = best_idx;
-    double* hp = a.out_hp + 4 * (size_t)q;
+    a.out_dist[fq + q] = best; a.out_idx[fq + q] = best_idx;
+    double* hp = a.out_hp + 4 * (fq + q);
     if (have_hp) { hp[0] = best_hp.x; hp[1] = best_hp.y; hp[2] = best_hp.z; hp[3] = 1.0; }
     else { hp[0] = hp[1] = hp[2] = hp[3] = 0.0; }
-    if (a.out_init) a.out_init[q] = best_init ? 1 : 0;
+    if (a.out_init) a.out_init[fq + q] = best_init ? 1 : 0;
     if (MODE == MODE_M2 && a.out_ctr && ctr) atomicAdd(a.out_ctr, ctr);
   }
 }
@@ -734,6 +740,81 @@ int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand
   a.cell_off = ws.d_m1_cell_off; a.cell_list = ws.d_m1_cell_list; a.best = ws.d_m1_best;
   a.out_dist = d_out_dist; a.out_idx = d_out_lm;
   return m1_launch(ctx, a, 64, n_frames, ws.stream);
+}
+
+// T_CW = T_WC.inverse() = [C^T | -(C^T r)] as row-major 3x4 (kinematics/implementation/Transformation.hpp:207-209)
+static void invert_pose(const double C[9], const double r[3], double T[12])
+{
+  for (int i = 0; i < 3; i++) {
+    T[4 * i] = C[i]; T[4 * i + 1] = C[3 + i]; T[4 * i + 2] = C[6 + i];
+    T[4 * i + 3] = -((C[i] * r[0] + C[3 + i] * r[1]) + C[6 + i] * r[2]);
+  }
+}
+
+int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, const okb_keypoint_t* d_kp0, const uint8_t* d_desc0,
+                                const int32_t* d_count0, const okb_camera_model_t* model0, const double C_WC0[9],
+                                const double r_WC0[3], int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
+                                const int32_t* d_count1, const okb_camera_model_t* model1, const double C_WC1[9],
+                                const double r_WC1[3], uint32_t match_threshold, void* stream, int32_t* d_out_k1,
+                                uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_initialisable)
+{
+  OKB_CHECK_ARGS(ctx && n_frames >= 1 && cap0 > 0 && cap1 > 0 && d_kp0 && d_desc0 && d_count0 && model0 && d_kp1 && d_desc1 &&
+                 d_count1 && model1 && C_WC0 && r_WC0 && C_WC1 && r_WC1 && d_out_k1 && d_out_dist && d_out_hp_W && d_out_initialisable,
+                 "okb_match_stereo_device_ptr");
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->match.stream;
+  // scratch: per side rays(3) eW(3) sof c26 c6 doubles + valid bytes
+  const size_t n0 = (size_t)n_frames * cap0, n1 = (size_t)n_frames * cap1;
+  const size_t need = (n0 + n1) * (9 * 8 + 8);
+  if (need > ctx->stereo_cap) {
+    OKB_CUDA(cudaDeviceSynchronize());
+    if (ctx->stereo_scratch) cudaFree(ctx->stereo_scratch);
+    ctx->stereo_scratch = nullptr; ctx->stereo_cap = 0;
+    OKB_CUDA(cudaMalloc(&ctx->stereo_scratch, need + need / 4));
+    ctx->stereo_cap = need + need / 4;
+  }
+  double* base = (double*)ctx->stereo_scratch;
+  double *rays0 = base, *eW0 = rays0 + 3 * n0, *sof0 = eW0 + 3 * n0, *c26_0 = sof0 + n0, *c6_0 = c26_0 + n0;
+  double *rays1 = c6_0 + n0, *eW1 = rays1 + 3 * n1, *sof1 = eW1 + 3 * n1, *c26_1 = sof1 + n1, *c6_1 = c26_1 + n1;
+  uint8_t* valid0 = (uint8_t*)(c6_1 + n1); uint8_t* valid1 = valid0 + ((n0 + 7) & ~(size_t)7);
+  int rc = okb::camera_stereo_prep(ctx, *model0, C_WC0, d_kp0, d_count0, cap0, n_frames, rays0, valid0, eW0, sof0, c26_0, c6_0, st);
+  if (rc) return rc;
+  rc = okb::camera_stereo_prep(ctx, *model1, C_WC1, d_kp1, d_count1, cap1, n_frames, rays1, valid1, eW1, sof1, c26_1, c6_1, st);
+  if (rc) return rc;
+  MatchArgs a; memset(&a, 0, sizeof(a));
+  a.nq = cap0; a.nc = cap1; a.q_stride = (size_t)cap0; a.c_stride = (size_t)cap1; a.q_count = d_count0; a.c_count = d_count1;
+  a.q_desc = d_desc0; a.c_desc = d_desc1; a.q_use = valid0; a.q_e = eW0; a.q_sof = sof0; a.q_cos26 = c26_0; a.q_cos6 = c6_0;
+  a.c_valid = valid1; a.c_e = eW1; a.c_sof = sof1; a.c_cos26 = c26_1; a.c_cos6 = c6_1;
+  for (int i = 0; i < 3; i++) { a.r0[i] = r_WC0[i]; a.r1[i] = r_WC1[i]; }
+  invert_pose(C_WC0, r_WC0, a.T0); invert_pose(C_WC1, r_WC1, a.T1);
+  a.thr = match_threshold;
+  a.out_dist = d_out_dist; a.out_idx = d_out_k1; a.out_hp = d_out_hp_W; a.out_init = d_out_initialisable;
+  k_match_gated<4, MODE_M4><<<dim3((cap0 + 7) / 8, n_frames), 256, 0, st>>>(a);
+  ctx->launches++;
+  OKB_CUDA(cudaGetLastError());
+  return OKB_OK;
+}
+
+int okb_match_stereo_device(okb_context_t* ctx, int cam0, int cam1, int n_frames, const double C_WC0[9], const double r_WC0[3],
+                            const double C_WC1[9], const double r_WC1[3], uint32_t match_threshold, int32_t* d_out_k1,
+                            uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_initialisable)
+{
+  OKB_CHECK_ARGS(ctx && cam0 >= 0 && cam0 < ctx->n_cams && cam1 >= 0 && cam1 < ctx->n_cams && cam0 != cam1, "okb_match_stereo_device");
+  CamWorkspace& w0 = ctx->cams[cam0]; CamWorkspace& w1 = ctx->cams[cam1];
+  OKB_CHECK_ARGS(w0.has_model && w1.has_model && n_frames >= 1 && n_frames <= w0.cfg.max_batch && n_frames <= w1.cfg.max_batch,
+                 "okb_match_stereo_device (camera models set? okb_set_camera_model)");
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  // runs on camera 0's stream once camera 1's features are complete
+  OKB_CUDA(cudaEventRecord(w1.ev_done, w1.stream));
+  OKB_CUDA(cudaStreamWaitEvent(w0.stream, w1.ev_done, 0));
+  int rc = okb_match_stereo_device_ptr(ctx, n_frames, w0.kp_cap, w0.d_kp, w0.d_desc, w0.d_count, &w0.model, C_WC0, r_WC0, w1.kp_cap,
+                                       w1.d_kp, w1.d_desc, w1.d_count, &w1.model, C_WC1, r_WC1, match_threshold, (void*)w0.stream,
+                                       d_out_k1, d_out_dist, d_out_hp_W, d_out_initialisable);
+  if (rc) return rc;
+  // camera 1 must not overwrite its features before the matcher has read them
+  OKB_CUDA(cudaEventRecord(w0.ev_done, w0.stream));
+  OKB_CUDA(cudaStreamWaitEvent(w1.stream, w0.ev_done, 0));
+  return OKB_OK;
 }
 
 int okb_match_place(okb_context_t* ctx, int D, int n_lm, const int32_t* lm_offsets, const uint8_t* lm_desc, int n_kp,

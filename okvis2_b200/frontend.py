@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 from . import lib as _l
-from .lib import KP_DTYPE, CameraConfig, OkbError, check, ptr
+from .lib import KP_DTYPE, CameraConfig, CameraModel, OkbError, check, ptr
 
 import ctypes as C
 
@@ -89,6 +89,7 @@ class Frontend:
         self.briskMatchingThreshold_ = 60.0
         self._device, self._max_batch, self._D = device, max_batch, descriptor_bytes
         self._ctx = None
+        self._models = {}
         self._locks = [threading.Lock() for _ in range(numCameras)]  # featureDetectorMutexes_ (Frontend.cpp:226)
         self.initialiseBriskFeatureDetectors()
 
@@ -124,6 +125,30 @@ class Frontend:
         if matching_threshold is not None: self.briskMatchingThreshold_ = float(matching_threshold)
         self.initialiseBriskFeatureDetectors()
 
+    # ---- camera models (D4)
+    MODELS = {"none": 0, "radialtangential": 1, "equidistant": 2}
+
+    def setCameraModel(self, cameraIndex, distortion_type, focal_length, principal_point, distortion_coefficients):
+        """Same fields as the `cameras:` entries of the okvis yaml files (config/euroc.yaml:9-12)."""
+        m = CameraModel()
+        m.model = self.MODELS[distortion_type]
+        m.fu, m.fv = focal_length
+        m.cu, m.cv = principal_point
+        for i in range(4):
+            m.k[i] = distortion_coefficients[i] if i < len(distortion_coefficients) else 0.0
+        self._models[cameraIndex] = m
+        check(_l.lib().okb_set_camera_model(self._ctx, cameraIndex, C.byref(m)))
+
+    def computeBackProjections(self, frameOut, cameraIndex):
+        """MultiFrame::computeBackProjections(im) (Frame.hpp:178-193): fills backProjections / backProjectionsValid."""
+        fr = frameOut.frames[cameraIndex]
+        n = len(fr.keypoints)
+        rays = np.zeros((n, 3), np.float64); valid = np.zeros(n, np.uint8)
+        kp = np.ascontiguousarray(fr.keypoints, KP_DTYPE)
+        check(_l.lib().okb_back_project(self._ctx, cameraIndex, n, ptr(kp), ptr(rays), ptr(valid)))
+        fr.backProjections, fr.backProjectionsValid = rays, valid
+        return int(valid.sum())
+
     def initialiseBriskFeatureDetectors(self):
         """Frontend::initialiseBriskFeatureDetectors (Frontend.cpp:2398-2417): (re)create the per-camera objects."""
         self.close()
@@ -134,6 +159,8 @@ class Frontend:
         ctx = C.c_void_p()
         check(_l.lib().okb_create(self._device, self.numCameras, cfgs, C.byref(ctx)))
         self._ctx = ctx
+        for i, m in getattr(self, "_models", {}).items():   # the camera models survive a re-initialisation
+            check(_l.lib().okb_set_camera_model(self._ctx, i, C.byref(m)))
 
     def close(self):
         if getattr(self, "_ctx", None):

@@ -32,6 +32,12 @@ class CameraConfig(C.Structure):
                 ("pattern_scale", C.c_float)]
 
 
+class CameraModel(C.Structure):
+    """okb_camera_model_t: model 0 none / 1 radial-tangential / 2 equidistant"""
+    _fields_ = [("model", C.c_int32), ("reserved", C.c_int32), ("fu", C.c_double), ("fv", C.c_double), ("cu", C.c_double),
+                ("cv", C.c_double), ("k", C.c_double * 4)]
+
+
 def build(force=False):
     """Compile libokvis_b200.so for sm_100a with nvcc (okvis2_b200/csrc/Makefile)."""
     src = os.path.join(_HERE, "csrc")
@@ -73,6 +79,10 @@ _PROTOS = {
     "okb_match_stereo": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
     "okb_match_place": (i32, [vp, i32, i32, vp, vp, i32, vp, u32, vp, vp]),
     "okb_hamming_matrix": (i32, [vp, i32, i32, vp, i32, vp, vp]),
+    "okb_set_camera_model": (i32, [vp, i32, vp]),
+    "okb_back_project": (i32, [vp, i32, i32, vp, vp, vp]),
+    "okb_match_stereo_device": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
+    "okb_match_stereo_device_ptr": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]),
     "okb_match_map3d_device": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, vp, vp]),
 }
 

@@ -247,3 +247,15 @@ def match_place(lm_offsets, lm_desc, kp_desc, match_thr):
     f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     f(kp_desc.shape[1], n_lm, _p(lm_offsets), _p(lm_desc), len(kp_desc), _p(kp_desc), match_thr, _p(k), _p(dist))
     return k, dist
+
+
+def back_project(model, fu, fv, cu, cv, k, kp):
+    """Frame::computeBackProjections restatement. kp: structured keypoint array. Returns (rays n x 3, valid n)."""
+    kp = np.ascontiguousarray(kp, KP_DTYPE)
+    n = len(kp)
+    rays = np.zeros((n, 3)); valid = np.zeros(n, np.uint8)
+    kk = np.ascontiguousarray(k, np.float64)
+    f = lib().okvo_back_project
+    f.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    f(model, fu, fv, cu, cv, kk.ctypes.data, n, kp.ctypes.data, 7, rays.ctypes.data, valid.ctypes.data)
+    return rays, valid

@@ -1,0 +1,116 @@
+"""GPU suite: D4 back-projection and the device-resident stereo pipeline (detect -> describe -> back-project -> M4)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from okvis2_b200 import lib as okl
+from okvis2_b200.frontend import Frontend, MultiFrame
+from okvis2_b200.synth import synth_stereo
+
+pytestmark = pytest.mark.gpu
+
+EUROC = [dict(distortion_type="radialtangential", focal_length=(458.654880721, 457.296696463),
+              principal_point=(367.215803962, 248.37534061),
+              distortion_coefficients=[-0.28340811217, 0.0739590738929, 0.000193595028569, 1.76187114545e-05]),
+         dict(distortion_type="radialtangential", focal_length=(457.587426604, 456.13442556),
+              principal_point=(379.99944652, 255.238185386),
+              distortion_coefficients=[-0.283683654496, 0.0745128430929, -0.000104738949098, -3.55590700274e-05])]
+HILTI0 = dict(distortion_type="equidistant", focal_length=(351.31400364193297, 351.4911744656785),
+              principal_point=(367.8522793375995, 253.84021449809963),
+              distortion_coefficients=[-0.03696737352869157, -0.008917880497032812, 0.008912969593422046, -0.0037685977496087313])
+
+
+def oracle_bp(cfg, kp):
+    return oracle.back_project(Frontend.MODELS[cfg["distortion_type"]], *cfg["focal_length"], *cfg["principal_point"],
+                               cfg["distortion_coefficients"], kp)
+
+
+def test_back_projection_radtan_exact_and_equidistant_close():
+    fe = Frontend(1, 752, 480)
+    rng = np.random.default_rng(0)
+    mf = MultiFrame(1)
+    kp = np.zeros(3000, okl.KP_DTYPE)
+    kp["x"] = rng.uniform(0, 752, 3000).astype(np.float32); kp["y"] = rng.uniform(0, 480, 3000).astype(np.float32)
+    mf.frames[0].keypoints = kp
+    fe.setCameraModel(0, **EUROC[0])
+    n_ok = fe.computeBackProjections(mf, 0)
+    rays, valid = oracle_bp(EUROC[0], kp)
+    assert np.array_equal(mf.frames[0].backProjections.view(np.uint64), rays.view(np.uint64))   # bit-exact
+    assert np.array_equal(mf.frames[0].backProjectionsValid, valid) and n_ok == valid.sum() > 2900
+    fe.setCameraModel(0, "none", (458.0, 457.0), (367.0, 248.0), [])
+    fe.computeBackProjections(mf, 0)
+    rays, valid = oracle.back_project(0, 458.0, 457.0, 367.0, 248.0, [0, 0, 0, 0], kp)
+    assert np.array_equal(mf.frames[0].backProjections.view(np.uint64), rays.view(np.uint64))
+    # equidistant needs atan: device and libm agree to the last bits only (tolerance stated: 1e-13 absolute)
+    fe.setCameraModel(0, **HILTI0)
+    kp["x"] = rng.uniform(0, 720, 3000).astype(np.float32); kp["y"] = rng.uniform(0, 540, 3000).astype(np.float32)
+    mf.frames[0].keypoints = kp
+    fe.computeBackProjections(mf, 0)
+    rays, valid = oracle_bp(HILTI0, kp)
+    assert np.array_equal(mf.frames[0].backProjectionsValid, valid)
+    assert np.abs(mf.frames[0].backProjections - rays).max() <= 1e-13
+    fe.close()
+
+
+def world_rays(C_WC, rays):
+    """(C_WC * e_C).normalized() with the library's association order"""
+    x, y, z = rays[:, 0], rays[:, 1], rays[:, 2]
+    w = [(C_WC[i, 0] * x + C_WC[i, 1] * y) + C_WC[i, 2] * z for i in range(3)]
+    n = np.sqrt((w[0] * w[0] + w[1] * w[1]) + w[2] * w[2])
+    return np.ascontiguousarray(np.stack([w[0] / n, w[1] / n, w[2] / n], 1))
+
+
+def T_CW(C_WC, r):
+    T = np.zeros((3, 4))
+    for i in range(3):
+        T[i, :3] = C_WC[:, i]
+        T[i, 3] = -((C_WC[0, i] * r[0] + C_WC[1, i] * r[1]) + C_WC[2, i] * r[2])
+    return T.reshape(12)
+
+
+def test_device_resident_stereo_pipeline_equals_oracle():
+    import torch
+    B = 3
+    fe = Frontend(2, 752, 480, max_batch=B)
+    fe.configure(threshold=30, octaves=3, max_keypoints=1000)
+    for c in range(2):
+        fe.setCameraModel(c, **EUROC[c])
+    L_ = okl.lib()
+    imgs = [np.stack([synth_stereo(700 + t, 752, 480)[c] for t in range(B)]) for c in range(2)]
+    d_imgs = [torch.from_numpy(a).cuda() for a in imgs]
+    for c in range(2):
+        okl.check(L_.okb_detect_describe_batch_device(fe.ctx, c, B, d_imgs[c].data_ptr()))
+    cap = C.c_int(0)
+    L_.okb_device_features(fe.ctx, 0, None, None, None, C.byref(cap)); cap = cap.value
+    C0 = np.eye(3); r0 = np.zeros(3)
+    a = 0.01
+    C1 = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]); r1 = np.array([0.11, 0.001, -0.002])
+    k1 = torch.zeros((B, cap), dtype=torch.int32, device="cuda"); dist = torch.zeros((B, cap), dtype=torch.int32, device="cuda")
+    hp = torch.zeros((B, cap, 4), dtype=torch.float64, device="cuda"); init = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
+    okl.check(L_.okb_match_stereo_device(fe.ctx, 0, 1, B, C0.ctypes.data, r0.ctypes.data, np.ascontiguousarray(C1).ctypes.data,
+                                         r1.ctypes.data, 60, k1.data_ptr(), dist.data_ptr(), hp.data_ptr(), init.data_ptr()))
+    okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    k1, dist, hp, init = k1.cpu().numpy(), dist.cpu().numpy().view(np.uint32), hp.cpu().numpy(), init.cpu().numpy()
+    total = 0
+    for b in range(B):
+        feats = []
+        for c in range(2):
+            kp = np.zeros(cap, okl.KP_DTYPE); d = np.zeros((cap, 64), np.uint8); n = C.c_int(0)
+            okl.check(L_.okb_fetch_features(fe.ctx, c, b, kp.ctypes.data, d.ctypes.data, cap, C.byref(n)))
+            feats.append((kp[:n.value], d[:n.value]))
+        (kp0, d0), (kp1, d1) = feats
+        rk, rd = oracle.Brisk(30, 3).detect_and_compute(imgs[0][b], 1000)
+        assert kp0.tobytes() == rk.tobytes() and np.array_equal(d0, rd)
+        rays0, v0 = oracle_bp(EUROC[0], kp0); rays1, v1 = oracle_bp(EUROC[1], kp1)
+        f0 = 0.5 * sum(EUROC[0]["focal_length"]); f1 = 0.5 * sum(EUROC[1]["focal_length"])
+        ref = oracle.match_stereo(d0, v0, world_rays(C0, rays0), kp0["size"].astype(np.float64) / f0, d1, v1, world_rays(C1, rays1),
+                                  kp1["size"].astype(np.float64) / f1, r0, r1, T_CW(C0, r0), T_CW(C1, r1), 60)
+        n0 = len(kp0)
+        assert np.array_equal(k1[b, :n0], ref[0]) and np.array_equal(dist[b, :n0], ref[1])
+        assert np.array_equal(hp[b, :n0].view(np.uint64), ref[2].view(np.uint64)) and np.array_equal(init[b, :n0], ref[3])
+        assert (k1[b, n0:] == -1).all()
+        total += (ref[0] >= 0).sum()
+    assert total > 5
+    fe.close()
