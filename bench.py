@@ -33,6 +33,8 @@ CONFIGS = {
     "euroc": dict(W=752, H=480, max_kp=1000, threshold=30, octaves=3, n_lm=5000, batch=32, ring=6, f=458.0),
     # BASELINE.json configs[2]: TUM-VI 1024x1024 stereo, 2000 kpts/frame, 50-keyframe landmark set
     "tumvi": dict(W=1024, H=1024, max_kp=2000, threshold=30, octaves=3, n_lm=50000, batch=16, ring=5, f=190.0),
+    # BASELINE.json configs[3]: Hilti-2022 5-camera rig, cameras sharded over the GPUs, NCCL all-gather for stereo matching
+    "hilti": dict(W=720, H=540, max_kp=700, threshold=30, octaves=3, n_lm=5000, batch=16, ring=8, f=351.0, rig="HILTI_2022"),
 }
 
 
@@ -155,6 +157,125 @@ def run_reference(args, cfg, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def run_sharded(args, cfg, rank, world, local_rank):
+    """Camera-sharded multiframe pipeline (BASELINE config 4): camera c on rank c % world; per step every rank runs
+    detect+describe+back-project+M1 for its cameras on a batch of B multiframes, contributes its fixed-capacity feature
+    blocks to ONE NCCL all-gather, then stereo-matches (M4) the overlapping pairs it owns from the gathered device buffer."""
+    import torch
+    import torch.distributed as dist
+    from okvis2_b200 import lib as okl, rigs, sharding as sh
+    from okvis2_b200.frontend import Frontend, MultiFrame
+    from okvis2_b200.synth import synth_frame
+    L_ = okl.lib()
+    rig = getattr(rigs, cfg["rig"])
+    n_cams, W, H, B, ring = len(rig), cfg["W"], cfg["H"], cfg["batch"], cfg["ring"]
+    mine = sh.cameras_of(rank, world, n_cams)
+    overlaps = sh.rig_overlaps(rig)
+    pairs = sh.pairs_of(rank, world, overlaps)
+    warm = max(args.warmup, 3)
+    fe = Frontend(max(len(mine), 1), W, H, device=local_rank, max_batch=B)
+    fe.configure(threshold=cfg["threshold"], octaves=cfg["octaves"], max_keypoints=cfg["max_kp"])
+    ctx = fe.ctx
+    models = []
+    for c in range(n_cams):
+        m = okl.CameraModel(); r = rig[c]
+        m.model = Frontend.MODELS[r["distortion_type"]]; m.fu, m.fv = r["focal_length"]; m.cu, m.cv = r["principal_point"]
+        for i in range(4):
+            m.k[i] = r["distortion_coefficients"][i]
+        models.append(m)
+    for li, c in enumerate(mine):
+        fe.setCameraModel(li, rig[c]["distortion_type"], rig[c]["focal_length"], rig[c]["principal_point"], rig[c]["distortion_coefficients"])
+    T = [np.array(r["T_SC"]).reshape(4, 4) for r in rig]
+    C_WC = [np.ascontiguousarray(t[:3, :3]) for t in T]; r_WC = [np.ascontiguousarray(t[:3, 3]) for t in T]
+    cap = C.c_int(0); L_.okb_device_features(ctx, 0, None, None, None, C.byref(cap)); kp_cap = cap.value
+    # inputs: ring * B frames per local camera (distinct synthetic views), resident in HBM
+    n_frames = ring * B
+    d_img, maps, d_maps, d_m1 = [], [], [], []
+    for li, c in enumerate(mine):
+        base = [synth_frame(3000 + 17 * c + i, W, H) for i in range(4)]
+        frames = np.stack([np.roll(base[i % 4], (3 * (i // 4), 5 * (i // 4)), (0, 1)) for i in range(n_frames)])
+        d_img.append(torch.from_numpy(frames).cuda())
+        mf = MultiFrame(len(mine)); mf.setImage(li, frames[0]); fe.detectAndDescribe(li, mf)
+        m = make_map(cfg, mf.frames[li].keypoints, mf.frames[li].descriptors, 70 + c)
+        proj = np.broadcast_to(m["lm_proj"], (B,) + m["lm_proj"].shape).copy()
+        d_maps.append(dict(desc=torch.from_numpy(m["cand_desc"]).cuda(), lm=torch.from_numpy(m["cand_lm"]).cuda(),
+                           proj=torch.from_numpy(proj).cuda(), is3d=torch.from_numpy(m["lm_is3d"]).cuda()))
+        d_m1.append(dict(dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), lm=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda")))
+    slots = sh.slots_per_rank(world, n_cams)
+    o_c, o_k, o_d, blk = sh.block_layout(B, kp_cap)
+    assert blk == L_.okb_feature_block_bytes(B, kp_cap)
+    local = torch.zeros((slots, blk), dtype=torch.uint8, device="cuda")
+    gathered = torch.zeros((world, slots, blk), dtype=torch.uint8, device="cuda")
+    d_st = [dict(k1=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"),
+                 hp=torch.zeros((B, kp_cap, 4), dtype=torch.float64, device="cuda"), init=torch.zeros((B, kp_cap), dtype=torch.uint8, device="cuda"))
+            for _ in pairs]
+    cur = torch.cuda.current_stream()
+    cam_streams = [torch.cuda.ExternalStream(L_.okb_stream(ctx, li)) for li in range(len(mine))]
+
+    def step(s):
+        for li, c in enumerate(mine):
+            cam_streams[li].wait_stream(cur)      # the previous step's matchers have finished reading the features
+            frames = d_img[li][(s % ring) * B:(s % ring + 1) * B]
+            okl.check(L_.okb_detect_describe_batch_device(ctx, li, B, frames.data_ptr()))
+            dm = d_maps[li]
+            okl.check(L_.okb_match_map3d_device(ctx, li, B, len(dm["lm"]), dm["desc"].data_ptr(), dm["lm"].data_ptr(), len(dm["is3d"]),
+                                                dm["proj"].data_ptr(), dm["is3d"].data_ptr(), 20.0, 60, d_m1[li]["dist"].data_ptr(),
+                                                d_m1[li]["lm"].data_ptr()))
+            okl.check(L_.okb_export_features(ctx, li, B, local[c // world].data_ptr()))
+            cur.wait_stream(cam_streams[li])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), local.view(-1))      # the one collective of the path
+        else:
+            gathered[0].copy_(local)
+        for pi, (i, j) in enumerate(pairs):
+            bi = gathered.data_ptr() + (sh.slot_of(i, world)[0] * slots + sh.slot_of(i, world)[1]) * blk
+            bj = gathered.data_ptr() + (sh.slot_of(j, world)[0] * slots + sh.slot_of(j, world)[1]) * blk
+            o = d_st[pi]
+            okl.check(L_.okb_match_stereo_device_ptr(ctx, B, kp_cap, bi + o_k, bi + o_d, bi + o_c, C.byref(models[i]), C_WC[i].ctypes.data,
+                                                     r_WC[i].ctypes.data, kp_cap, bj + o_k, bj + o_d, bj + o_c, C.byref(models[j]),
+                                                     C_WC[j].ctypes.data, r_WC[j].ctypes.data, 60, cur.cuda_stream, o["k1"].data_ptr(),
+                                                     o["dist"].data_ptr(), o["hp"].data_ptr(), o["init"].data_ptr()))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(warm):
+        step(s)
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    launches0 = L_.okb_launch_count(ctx)
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(cur)
+    for s in range(args.steps):
+        step(warm + s)
+    for st in cam_streams:
+        cur.wait_stream(st)
+    ev1.record(cur)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = L_.okb_launch_count(ctx) - launches0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    n_match = int(sum((o["k1"] >= 0).sum().item() for o in d_st))
+    if rank == 0:
+        line = {"metric": "multiframes/sec detect+describe+match (5-camera rig)", "value": B * args.steps / (ms * 1e-3), "unit": "multiframes/s",
+                "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": args.config, "multiframes_per_step": B, "cameras": n_cams, "overlapping_pairs": overlaps,
+                           "parallelism": f"camera c on GPU c % {world}; one NCCL all-gather of {slots} x {blk} B feature blocks per rank per step",
+                           "l2_policy": f"inputs larger than L2: ring of {ring} batches",
+                           **{k: cfg[k] for k in ("W", "H", "max_kp", "threshold", "octaves", "n_lm")}},
+                "roofline": None, "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+                "stereo_matches_rank0_last_step": n_match}
+        print(json.dumps(line))
+    fe.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,6 +302,11 @@ def main():
     from okvis2_b200 import lib as okl
     from okvis2_b200.frontend import Frontend, MultiFrame
     L_ = okl.lib()
+    if "rig" in cfg:
+        run_sharded(args, cfg, rank, world, local_rank)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     W, H, B, ring = cfg["W"], cfg["H"], cfg["batch"], cfg["ring"]
     warm = max(args.warmup, 3)

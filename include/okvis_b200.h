@@ -88,6 +88,13 @@ int okb_fetch_features(okb_context_t* ctx, int cam, int frame, okb_keypoint_t* k
 int okb_device_features(okb_context_t* ctx, int cam, const okb_keypoint_t** d_kp, const uint8_t** d_desc,
                         const int32_t** d_count, int* capacity);
 
+/* Fixed-capacity feature block of a batch, the unit the camera-sharded multi-GPU mode all-gathers:
+ *   [counts: n_frames x int32, padded to 256 B][keypoints: n_frames x capacity x 28 B][descriptors: n_frames x capacity x 64 B]
+ * okb_export_features packs the last result of camera `cam` into the caller's DEVICE buffer (asynchronous on the camera
+ * stream; capacity = okb_device_features). The block layout is what okb_match_stereo_device_ptr consumes. */
+size_t okb_feature_block_bytes(int n_frames, int capacity);
+int okb_export_features(okb_context_t* ctx, int cam, int n_frames, void* d_block);
+
 /* inspection hooks used by the parity tests: layer geometry, layer images and the dense AGAST score maps
  * (b0 = largest threshold at which the pixel is still a 9-16 corner, 0 in the 3-pixel margin) of the last call */
 int okb_num_layers(okb_context_t* ctx, int cam);

@@ -209,6 +209,28 @@ int okb_device_features(okb_context_t* ctx, int cam, const okb_keypoint_t** d_kp
   return OKB_OK;
 }
 
+size_t okb_feature_block_bytes(int n_frames, int capacity)
+{
+  const size_t counts = ((size_t)n_frames * 4 + 255) & ~(size_t)255;
+  return counts + (size_t)n_frames * capacity * (sizeof(okb_keypoint_t) + 64);
+}
+
+int okb_export_features(okb_context_t* ctx, int cam, int n_frames, void* d_block)
+{
+  int rc = check_cam(ctx, cam, "okb_export_features");
+  if (rc) return rc;
+  CamWorkspace& ws = ctx->cams[cam];
+  if (!d_block || n_frames < 1 || n_frames > ws.cfg.max_batch) { set_error("okb_export_features: bad arguments"); return OKB_ERR_ARGUMENT; }
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  uint8_t* p = (uint8_t*)d_block;
+  const size_t counts = ((size_t)n_frames * 4 + 255) & ~(size_t)255;
+  const size_t kp_bytes = (size_t)n_frames * ws.kp_cap * sizeof(okb_keypoint_t);
+  OKB_CUDA(cudaMemcpyAsync(p, ws.d_count, (size_t)n_frames * 4, cudaMemcpyDeviceToDevice, ws.stream));
+  OKB_CUDA(cudaMemcpyAsync(p + counts, ws.d_kp, kp_bytes, cudaMemcpyDeviceToDevice, ws.stream));
+  OKB_CUDA(cudaMemcpyAsync(p + counts + kp_bytes, ws.d_desc, (size_t)n_frames * ws.kp_cap * 64, cudaMemcpyDeviceToDevice, ws.stream));
+  return OKB_OK;
+}
+
 int okb_num_layers(okb_context_t* ctx, int cam) { return check_cam(ctx, cam, "okb_num_layers") ? -1 : ctx->cams[cam].n_layers; }
 
 int okb_layer_info(okb_context_t* ctx, int cam, int layer, int* width, int* height, float* scale, float* offset)

@@ -65,6 +65,8 @@ _PROTOS = {
     "okb_detect_describe_batch_device": (i32, [vp, i32, i32, vp]),
     "okb_fetch_features": (i32, [vp, i32, i32, vp, vp, i32, vp]),
     "okb_device_features": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]),
+    "okb_feature_block_bytes": (C.c_size_t, [i32, i32]),
+    "okb_export_features": (i32, [vp, i32, i32, vp]),
     "okb_num_layers": (i32, [vp, i32]),
     "okb_layer_info": (i32, [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "okb_fetch_layer": (i32, [vp, i32, i32, i32, vp, vp]),
