@@ -382,10 +382,12 @@ def main():
     launches = L_.okb_launch_count(ctx) - launches0
     clocks = sampler.stop()
     ps_ms = C.c_double(); ps_l = C.c_int64(); tot = C.c_double()
-    ps_total_ms, ps_total_launches = 0.0, 0
+    ps_total_ms, ps_total_launches, score_total_ms = 0.0, 0, 0.0
+    sc_ms = C.c_double()
     for c in range(2):
         L_.okb_get_timers(ctx, c, C.byref(ps_ms), C.byref(ps_l), C.byref(tot))
-        ps_total_ms += ps_ms.value; ps_total_launches += ps_l.value
+        L_.okb_get_score_kernel_ms(ctx, c, C.byref(sc_ms))
+        ps_total_ms += ps_ms.value; ps_total_launches += ps_l.value; score_total_ms += sc_ms.value
     L_.okb_enable_timers(ctx, 0)
     if world > 1:
         t = torch.tensor([dev_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
@@ -401,8 +403,14 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = ps_bytes * B * passes / (ps_total_ms * 1e-3) / 1e9 if ps_total_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "kernel": "pyramid+score pass (k_resize x3 + k_score)", "bytes_per_image": int(ps_bytes),
+    # DRAM traffic of the dominant kernel (k_score_nms, one launch = B images) from the committed ncu --set full capture
+    # profiles/r01_ncu_full_score_refine_describe_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum), euroc config
+    traffic = 22.16e6 if args.config == "euroc" and B == 32 else None
+    ach_k = ps_bytes * B * passes / (score_total_ms * 1e-3) / 1e9 if score_total_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "kernel": "pyramid+score pass (k_resize launches + k_score_nms, TMA-staged tiles)", "bytes_per_image": int(ps_bytes),
+                "dominant_kernel": {"name": "k_score_nms", "ms_per_launch": score_total_ms / passes, "achieved_GBps": ach_k,
+                                    "frac": ach_k / peak, "limiter": "ALU pipe (~74% busy: 80 VIMNMX3.U16x2 per pixel pair), not HBM"},
                 "images_per_pass": B, "ms_per_pass": ps_total_ms / passes, "launches_per_pass": ps_total_launches / passes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
 

@@ -48,7 +48,7 @@ extern "C" int okb_e2e_run(okb_context_t* ctx, int n_frames, int warmup, int W, 
   std::vector<okb_keypoint_t> kp[2]; std::vector<uint8_t> desc[2]; int n[2] = {0, 0}; int rc2[2] = {0, 0};
   for (int c = 0; c < 2; c++) { kp[c].resize(cap); desc[c].resize((size_t)cap * 64); }
   std::vector<double> e[2], sof[2], xy[2]; std::vector<uint8_t> valid[2];
-  std::vector<int32_t> k1(cap), lm(cap); std::vector<uint32_t> dist(cap); std::vector<double> hp((size_t)cap * 4); std::vector<uint8_t> init(cap);
+  std::vector<int32_t> k1(cap), lm(cap), lm_b(cap); std::vector<uint32_t> dist_b(cap); std::vector<uint32_t> dist(cap); std::vector<double> hp((size_t)cap * 4); std::vector<uint8_t> init(cap);
   const double r0[3] = {0, 0, 0}, r1[3] = {0.11, 0, 0};
   const double T0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}, T1[12] = {1, 0, 0, -0.11, 0, 1, 0, 0, 0, 0, 1, 0};
   Worker w; w.start();
@@ -61,7 +61,8 @@ extern "C" int okb_e2e_run(okb_context_t* ctx, int n_frames, int warmup, int W, 
     if (rc2[0] || rc2[1]) return rc2[0] ? rc2[0] : rc2[1];
     for (int c = 0; c < 2; c++) {  // Frame::computeBackProjections on the device, then the packing the matchers need
       e[c].resize((size_t)n[c] * 3); sof[c].resize(n[c]); xy[c].resize((size_t)n[c] * 2); valid[c].resize(n[c]);
-      const int rcb = okb_back_project(ctx, c, n[c], kp[c].data(), e[c].data(), valid[c].data());
+      int nr = 0;   // rays were computed on the device during okb_detect_describe (camera model set)
+      const int rcb = okb_last_back_projections(ctx, c, 0, n[c], e[c].data(), valid[c].data(), &nr);
       if (rcb) return rcb;
       for (int k = 0; k < n[c]; k++) {   // e_W = (C_WC * e_C).normalized() with C_WC = I
         const double x = e[c][3 * k], y = e[c][3 * k + 1], z = e[c][3 * k + 2];
@@ -69,18 +70,28 @@ extern "C" int okb_e2e_run(okb_context_t* ctx, int n_frames, int warmup, int W, 
         e[c][3 * k] = x / nn; e[c][3 * k + 1] = y / nn; e[c][3 * k + 2] = z / nn;
         sof[c][k] = (double)kp[c][k].size / f; xy[c][2 * k] = kp[c][k].x; xy[c][2 * k + 1] = kp[c][k].y;
       }
-      h2d += (long long)n[c] * 28; d2h += (long long)n[c] * 25;
+      d2h += (long long)n[c] * 25;
     }
+    // map matching of camera 1 on the worker thread (its own matcher slot/stream), stereo + camera 0 on this thread
+    std::vector<int32_t>& lm1 = lm_b; std::vector<uint32_t>& dist1 = dist_b;
+    int rc_m1 = 0;
+    w.submit([&] {
+      rc_m1 = okb_match_map3d(ctx, 64, n[1], desc[1].data(), xy[1].data(), nullptr, n_cand[1], cand_desc[1], cand_lm[1], n_lm[1],
+                              lm_proj[1], lm_is3d[1], 20.0, 60, dist1.data(), lm1.data());
+    });
     int rc = okb_match_stereo(ctx, 64, n[0], desc[0].data(), valid[0].data(), e[0].data(), sof[0].data(), n[1], desc[1].data(),
                               valid[1].data(), e[1].data(), sof[1].data(), r0, r1, T0, T1, 60, k1.data(), dist.data(), hp.data(), init.data());
-    if (rc) return rc;
-    for (int k = 0; k < n[0]; k++) nm += k1[k] >= 0;
+    if (!rc) {
+      for (int k = 0; k < n[0]; k++) nm += k1[k] >= 0;
+      rc = okb_match_map3d(ctx, 64, n[0], desc[0].data(), xy[0].data(), nullptr, n_cand[0], cand_desc[0], cand_lm[0], n_lm[0],
+                           lm_proj[0], lm_is3d[0], 20.0, 60, dist.data(), lm.data());
+    }
+    w.wait();
+    if (rc || rc_m1) return rc ? rc : rc_m1;
+    for (int k = 0; k < n[0]; k++) nm += lm[k] >= 0;
+    for (int k = 0; k < n[1]; k++) nm += lm1[k] >= 0;
     h2d += (long long)(n[0] + n[1]) * (64 + 24 + 8 + 2 * 8 + 1); d2h += (long long)n[0] * (4 + 4 + 32 + 1);
     for (int c = 0; c < 2; c++) {
-      rc = okb_match_map3d(ctx, 64, n[c], desc[c].data(), xy[c].data(), nullptr, n_cand[c], cand_desc[c], cand_lm[c], n_lm[c],
-                           lm_proj[c], lm_is3d[c], 20.0, 60, dist.data(), lm.data());
-      if (rc) return rc;
-      for (int k = 0; k < n[c]; k++) nm += lm[k] >= 0;
       h2d += (long long)W * H + (long long)n[c] * (64 + 16) + (long long)n_cand[c] * 68 + (long long)n_lm[c] * 17;
       d2h += (long long)n[c] * (28 + 64 + 8);
       nkp += n[c];

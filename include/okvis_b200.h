@@ -112,6 +112,8 @@ int okb_enable_timers(okb_context_t* ctx, int on);
 int okb_reset_timers(okb_context_t* ctx);
 int okb_get_timers(okb_context_t* ctx, int cam, double* pyramid_score_ms, int64_t* pyramid_score_launches,
                    double* total_ms);
+/* accumulated device time of the fused score + non-max kernel alone (the dominant kernel of the pass) */
+int okb_get_score_kernel_ms(okb_context_t* ctx, int cam, double* score_ms);
 
 /* ---- D4: back-projection. Replaces okvis::Frame::computeBackProjections (okvis_cv/include/okvis/implementation/Frame.hpp:
  *      178-193) -> PinholeCamera<D>::backProject (cameras/implementation/PinholeCamera.hpp:574-592) -> Distortion::undistort.
@@ -125,6 +127,11 @@ typedef struct {
 int okb_set_camera_model(okb_context_t* ctx, int cam, const okb_camera_model_t* model);
 /* rays_out: n x 3 doubles (x, y, 1); valid_out: n success flags (Frame::backProjectionsValid_). Host buffers. */
 int okb_back_project(okb_context_t* ctx, int cam, int n, const okb_keypoint_t* kp, double* rays_out, uint8_t* valid_out);
+
+/* When a camera model is set, okb_detect_describe* also back-projects the keypoints it returns (same kernel as
+ * okb_back_project) and keeps the rays in pinned host memory: this call only copies them out (frame = index inside the
+ * last batch of camera `cam`). It is how the adapter fills Frame::backProjections_ without a second device round trip. */
+int okb_last_back_projections(okb_context_t* ctx, int cam, int frame, int cap, double* rays_out, uint8_t* valid_out, int* n_out);
 
 /* ---- matchers. Descriptors are n x D u8, D in {48, 64}. "First in the reference's iteration order wins ties"
  *      (strict <) is honoured bit-exactly; geometric gates are evaluated on the device in fp64 without FMA

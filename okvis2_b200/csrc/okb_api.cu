@@ -88,7 +88,7 @@ int64_t okb_launch_count(const okb_context_t* ctx) { return ctx ? ctx->launches 
 void* okb_stream(okb_context_t* ctx, int cam)
 {
   if (!ctx) return nullptr;
-  if (cam < 0 || cam >= ctx->n_cams) return (void*)ctx->match.stream;
+  if (cam < 0 || cam >= ctx->n_cams) return (void*)ctx->match_slots[0].stream;
   return (void*)ctx->cams[cam].stream;
 }
 int okb_sync(okb_context_t* ctx)
@@ -96,7 +96,7 @@ int okb_sync(okb_context_t* ctx)
   if (!ctx) return OKB_ERR_ARGUMENT;
   OKB_CUDA(cudaSetDevice(ctx->device));
   for (int i = 0; i < ctx->n_cams; i++) OKB_CUDA(cudaStreamSynchronize(ctx->cams[i].stream));
-  OKB_CUDA(cudaStreamSynchronize(ctx->match.stream));
+  for (int i = 0; i < kMatchSlots; i++) OKB_CUDA(cudaStreamSynchronize(ctx->match_slots[i].stream));
   return OKB_OK;
 }
 
@@ -111,7 +111,7 @@ static int status_to_error(const CamWorkspace& ws, int n_frames)
   for (int b = 0; b < n_frames; b++)
     if (ws.h_status[b]) {
       set_error("detect: device capacity exceeded on frame %d (flags 0x%x: 1=candidates>%d, 2=ties, 4=keypoints>sort cap, "
-                "8=keypoints>output cap %d)", b, ws.h_status[b], ws.cand_cap, ws.kp_cap);
+                "8=keypoints>output cap %d, 16=TMA tile load timed out)", b, ws.h_status[b], ws.cand_cap, ws.kp_cap);
       return OKB_ERR_CAPACITY;
     }
   return OKB_OK;
@@ -148,6 +148,13 @@ int okb_detect_describe_batch(okb_context_t* ctx, int cam, int n_frames, const u
     OKB_CUDA(cudaMemcpyAsync(ws.h_kp, ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t) * n_frames, cudaMemcpyDeviceToHost, st));
     OKB_CUDA(cudaMemcpyAsync(ws.h_desc, ws.d_desc, (size_t)ws.kp_cap * 64 * n_frames, cudaMemcpyDeviceToHost, st));
   }
+  ws.h_rays_frames = 0;
+  if (ws.has_model) {   // the rays of D4 ride along (okb_last_back_projections): no second round trip for computeBackProjections
+    const size_t nr = n_frames == 1 ? (size_t)rows : (size_t)ws.kp_cap * n_frames;
+    OKB_CUDA(cudaMemcpyAsync(ws.h_rays, ws.d_rays, nr * 24, cudaMemcpyDeviceToHost, st));
+    OKB_CUDA(cudaMemcpyAsync(ws.h_rays_valid, ws.d_rays_valid, nr, cudaMemcpyDeviceToHost, st));
+    ws.h_rays_frames = n_frames;
+  }
   OKB_CUDA(cudaStreamSynchronize(st));
   rc = status_to_error(ws, n_frames);
   if (rc) return rc;
@@ -175,6 +182,23 @@ int okb_detect_describe_batch_device(okb_context_t* ctx, int cam, int n_frames, 
   if (!d_images || n_frames < 1 || n_frames > ws.cfg.max_batch) { set_error("okb_detect_describe_batch_device: bad arguments"); return OKB_ERR_ARGUMENT; }
   OKB_CUDA(cudaSetDevice(ctx->device));
   return detect_run_device(ctx, cam, n_frames, d_images, ws.cfg.width);
+}
+
+int okb_last_back_projections(okb_context_t* ctx, int cam, int frame, int cap, double* rays_out, uint8_t* valid_out, int* n_out)
+{
+  int rc = check_cam(ctx, cam, "okb_last_back_projections");
+  if (rc) return rc;
+  CamWorkspace& ws = ctx->cams[cam];
+  if (!rays_out || !valid_out || !n_out || frame < 0 || frame >= ws.h_rays_frames) {
+    set_error("okb_last_back_projections: no back-projections for frame %d (camera model set before okb_detect_describe?)", frame);
+    return OKB_ERR_ARGUMENT;
+  }
+  const int n = ws.h_count[frame];
+  if (n > cap) { set_error("okb_last_back_projections: %d rays > capacity %d", n, cap); return OKB_ERR_CAPACITY; }
+  memcpy(rays_out, ws.h_rays + (size_t)frame * ws.kp_cap * 3, (size_t)n * 24);
+  memcpy(valid_out, ws.h_rays_valid + (size_t)frame * ws.kp_cap, (size_t)n);
+  *n_out = n;
+  return OKB_OK;
 }
 
 int okb_fetch_features(okb_context_t* ctx, int cam, int frame, okb_keypoint_t* kp_out, uint8_t* desc_out, int cap, int* n_out)
@@ -280,9 +304,18 @@ int okb_enable_timers(okb_context_t* ctx, int on) { if (!ctx) return OKB_ERR_ARG
 int okb_reset_timers(okb_context_t* ctx)
 {
   if (!ctx) return OKB_ERR_ARGUMENT;
-  for (auto& ws : ctx->cams) { if (ws.pending_timing) { cudaEventSynchronize(ws.ev[3]); ws.pending_timing = 0; } ws.ps_ms = ws.total_ms = 0; ws.ps_launches = 0; }
+  for (auto& ws : ctx->cams) { if (ws.pending_timing) { cudaEventSynchronize(ws.ev[3]); ws.pending_timing = 0; } ws.ps_ms = ws.total_ms = ws.score_ms = 0; ws.ps_launches = 0; }
   return OKB_OK;
 }
+int okb_get_score_kernel_ms(okb_context_t* ctx, int cam, double* score_ms)
+{
+  int rc = check_cam(ctx, cam, "okb_get_score_kernel_ms");
+  if (rc) return rc;
+  detect_collect_timing(ctx, cam);
+  if (score_ms) *score_ms = ctx->cams[cam].score_ms;
+  return OKB_OK;
+}
+
 int okb_get_timers(okb_context_t* ctx, int cam, double* pyramid_score_ms, int64_t* pyramid_score_launches, double* total_ms)
 {
   int rc = check_cam(ctx, cam, "okb_get_timers");

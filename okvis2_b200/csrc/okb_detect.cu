@@ -13,7 +13,9 @@
 //   k_finalize      order by (layer, y, x), keep the N strongest, drop border keypoints, pattern scale index
 //   k_integral_*    int32 integral image
 //   k_describe      one warp per keypoint: 2 x 60 smoothed samples, orientation, 512 bits via ballot
+#include <cuda.h>   // CUtensorMap type and enums only; the encoder is resolved through cudaGetDriverEntryPoint
 #include <stdio.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -153,6 +155,35 @@ __device__ __forceinline__ uint32_t b0_pair(const uint32_t (&v)[16], uint32_t p)
   return __vminu2(__vmaxu2(t, 0x00010001u) - 0x00010001u, 0x00FE00FEu);
 }
 
+// ---- TMA (cp.async.bulk.tensor) staging of the image tiles -----------------------------------------------------
+// One 3-D tensor map per layer: (x: w bytes, y: h rows of `pitch` bytes, frame). A single elected thread issues one
+// bulk tensor copy of the kImgW x kImgH box per CTA; out-of-image elements are zero-filled by the hardware, the
+// completion is signalled on a shared-memory mbarrier.
+struct alignas(64) TmaMaps { CUtensorMap m[kMaxLayers]; int use[kMaxLayers]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // Fused score + non-max suppression. Tile = kTileW x kTileH pixels of one layer of one frame, 256 threads.
 //   1. the image tile with a 4-pixel halo (3 for the ring + 1 because candidates need their neighbours' scores) is
 //      staged in shared memory as 32-bit words, zero outside the image;
@@ -167,11 +198,13 @@ constexpr int kScW = kTileW + 8;     // score tile row: x0-4 .. x0+67
 constexpr int kScH = kTileH + 2;     // rows y0-1 .. y0+32
 constexpr int kScoreThreads = 256;
 
-__global__ void __launch_bounds__(kScoreThreads) k_score_nms(DeviceLayers dl, TileMap tm, const uint8_t* in0, int in_pitch,
-                                                   size_t in_frame_stride, uint8_t* img_block, uint8_t* score_block,
-                                                   uint32_t* cand, int32_t* cand_count, int cand_cap, int threshold)
+__global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_constant__ TmaMaps maps, DeviceLayers dl, TileMap tm,
+                                                             const uint8_t* in0, int in_pitch, size_t in_frame_stride,
+                                                             uint8_t* img_block, uint8_t* score_block, uint32_t* cand,
+                                                             int32_t* cand_count, int cand_cap, int threshold, int32_t* status)
 {
-  __shared__ __align__(16) uint8_t tile[kImgH][kImgW];
+  __shared__ __align__(128) uint8_t tile[kImgH][kImgW];
+  __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(16) uint8_t sc[kScH][kScW];
   const int frame = blockIdx.y;
   const int layer = find_layer(tm, blockIdx.x);
@@ -183,22 +216,39 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(DeviceLayers dl, Ti
   else { img = img_block + (size_t)frame * dl.frame_stride + d.offset; pitch = d.pitch; }
   uint8_t* score = score_block + (size_t)frame * dl.frame_stride + d.offset;
   const int x0 = tx * kTileW, y0 = ty * kTileH;
-  const bool word_ok = ((pitch & 3) == 0) && ((((uintptr_t)img) & 3) == 0);
-  for (int i = threadIdx.x; i < kImgH * (kImgW / 4); i += kScoreThreads) {
-    const int r = i / (kImgW / 4), c = i % (kImgW / 4);
-    const int y = y0 - 4 + r, x = x0 - 8 + c * 4;
-    uint32_t w = 0;
-    if (y >= 0 && y < d.h) {
-      const uint8_t* row = img + (size_t)y * pitch;
-      if (word_ok && x >= 0 && x + 3 < d.w) w = *reinterpret_cast<const uint32_t*>(row + x);
-      else {
-#pragma unroll
-        for (int b = 0; b < 4; b++) { const int xx = x + b; if (xx >= 0 && xx < d.w) w |= (uint32_t)row[xx] << (8 * b); }
+  if (maps.use[layer]) {
+    // TMA: one bulk tensor copy per CTA; out-of-image bytes arrive as zeros
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, kImgH * kImgW);
+      tma_load_3d(&tile[0][0], &maps.m[layer], &bar, x0 - 8, y0 - 4, frame);
+    }
+    const long long t_start = clock64();
+    while (!mbar_try_wait(&bar, 0)) {
+      if (clock64() - t_start > 400000000ll) {   // ~0.2 s: never spin forever on a broken descriptor
+        if (threadIdx.x == 0) atomicOr(&status[frame], 16);
+        return;
       }
     }
-    *reinterpret_cast<uint32_t*>(&tile[r][c * 4]) = w;
+  } else {
+    const bool word_ok = ((pitch & 3) == 0) && ((((uintptr_t)img) & 3) == 0);
+    for (int i = threadIdx.x; i < kImgH * (kImgW / 4); i += kScoreThreads) {
+      const int r = i / (kImgW / 4), c = i % (kImgW / 4);
+      const int y = y0 - 4 + r, x = x0 - 8 + c * 4;
+      uint32_t w = 0;
+      if (y >= 0 && y < d.h) {
+        const uint8_t* row = img + (size_t)y * pitch;
+        if (word_ok && x >= 0 && x + 3 < d.w) w = *reinterpret_cast<const uint32_t*>(row + x);
+        else {
+#pragma unroll
+          for (int b = 0; b < 4; b++) { const int xx = x + b; if (xx >= 0 && xx < d.w) w |= (uint32_t)row[xx] << (8 * b); }
+        }
+      }
+      *reinterpret_cast<uint32_t*>(&tile[r][c * 4]) = w;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 #pragma unroll 1
   for (int item = threadIdx.x; item < kScH * (kScW / 4); item += kScoreThreads) {
     const int rr = item / (kScW / 4), g = item % (kScW / 4);
@@ -990,7 +1040,10 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMallocHost(&ws.h_desc, (size_t)ws.kp_cap * 64 * B));
   OKB_CUDA(cudaMallocHost(&ws.h_count, 4 * B));
   OKB_CUDA(cudaMallocHost(&ws.h_status, 4 * B));
+  OKB_CUDA(cudaMallocHost(&ws.h_rays, (size_t)ws.kp_cap * 24 * B));
+  OKB_CUDA(cudaMallocHost(&ws.h_rays_valid, (size_t)ws.kp_cap * B));
   for (int i = 0; i < 4; i++) OKB_CUDA(cudaEventCreate(&ws.ev[i]));
+  OKB_CUDA(cudaEventCreate(&ws.ev_mid));
   OKB_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalizeSmem));
   OKB_CUDA(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, kResolveSmem));
   return OKB_OK;
@@ -1007,8 +1060,9 @@ void detect_free_camera(okb_context* ctx, int cam)
   cudaFree(ws.d_cand_count); cudaFree(ws.d_rec); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
   cudaFree(ws.d_count); cudaFree(ws.d_status); cudaFree(ws.d_m1_cell_off); cudaFree(ws.d_m1_cell_list); cudaFree(ws.d_m1_best); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);
   if (ws.ev_done) cudaEventDestroy(ws.ev_done);
-  cudaFreeHost(ws.h_img); cudaFreeHost(ws.h_kp); cudaFreeHost(ws.h_desc); cudaFreeHost(ws.h_count); cudaFreeHost(ws.h_status);
+  cudaFreeHost(ws.h_img); cudaFreeHost(ws.h_kp); cudaFreeHost(ws.h_desc); cudaFreeHost(ws.h_count); cudaFreeHost(ws.h_status); cudaFreeHost(ws.h_rays); cudaFreeHost(ws.h_rays_valid);
   for (int i = 0; i < 4; i++) if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
+  if (ws.ev_mid) cudaEventDestroy(ws.ev_mid);
   if (ws.stream) cudaStreamDestroy(ws.stream);
 }
 
@@ -1017,11 +1071,54 @@ static void collect_timing(okb_context* ctx, CamWorkspace& ws)
   if (!ws.pending_timing) return;
   cudaEventSynchronize(ws.ev[3]);
   float a = 0, b = 0;
+  float cth = 0;
   cudaEventElapsedTime(&a, ws.ev[0], ws.ev[1]);
   cudaEventElapsedTime(&b, ws.ev[0], ws.ev[3]);
-  ws.ps_ms += a; ws.total_ms += b;
+  cudaEventElapsedTime(&cth, ws.ev_mid, ws.ev[1]);
+  ws.ps_ms += a; ws.total_ms += b; ws.score_ms += cth;
   ws.pending_timing = 0;
   (void)ctx;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_encode_tried = 0;
+
+static bool encode_map(CUtensorMap* m, const void* base, int w, int h, size_t pitch, size_t frame_stride, int frames)
+{
+  if (!g_encode) return false;
+  if ((((uintptr_t)base) & 15) || (pitch & 15) || (frame_stride & 15) || pitch == 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+  const cuuint32_t box[3] = {(cuuint32_t)kImgW, (cuuint32_t)kImgH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// tensor maps of all layers for this call (layer 0 lives in the caller's buffer, so its map is re-encoded per call;
+// the others are cached in the workspace). Layers whose geometry TMA cannot address fall back to plain loads.
+static int build_tma_maps(CamWorkspace& ws, const uint8_t* d_images, int src_pitch, size_t in_stride, int frames, TmaMaps& maps)
+{
+  if (!g_encode_tried) {
+    g_encode_tried = 1;
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      g_encode = (EncodeTiledFn)fn;
+  }
+  memset(&maps, 0, sizeof(maps));
+  if (!ws.tma_ready) {
+    for (int i = 1; i < ws.n_layers; i++) {
+      const LayerGeom& g = ws.geom[i];
+      ws.tma_use[i] = encode_map(&ws.tma[i], ws.d_img + g.offset, g.w, g.h, (size_t)g.pitch, (size_t)ws.dl.frame_stride, ws.cfg.max_batch) ? 1 : 0;
+    }
+    ws.tma_ready = 1;
+  }
+  for (int i = 1; i < ws.n_layers; i++) { maps.m[i] = ws.tma[i]; maps.use[i] = ws.tma_use[i]; }
+  maps.use[0] = encode_map(&maps.m[0], d_images, ws.geom[0].w, ws.geom[0].h, (size_t)src_pitch, in_stride, frames) ? 1 : 0;
+  return OKB_OK;
 }
 
 // all frames are device resident: d_images = n_frames x H x src_pitch
@@ -1063,6 +1160,7 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
     ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
     i += 2;
   }
+  if (ctx->timers_on) cudaEventRecord(ws.ev_mid, st);
   // ---- scores
   TileMap tm; tm.n_layers = ws.n_layers; tm.tile_prefix[0] = 0;
   for (int i = 0; i < ws.n_layers; i++) {
@@ -1073,8 +1171,10 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   const int n_tiles = tm.tile_prefix[ws.n_layers];
   OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, 4 * B, st));
   OKB_CUDA(cudaMemsetAsync(ws.d_status, 0, 4 * B, st));
-  k_score_nms<<<dim3(n_tiles, B), kScoreThreads, 0, st>>>(ws.dl, tm, d_images, src_pitch, in_stride, ws.d_img, ws.d_score, ws.d_cand,
-                                                ws.d_cand_count, ws.cand_cap, c.threshold);
+  TmaMaps maps;
+  { int rc = build_tma_maps(ws, d_images, src_pitch, in_stride, c.max_batch, maps); if (rc) return rc; }
+  k_score_nms<<<dim3(n_tiles, B), kScoreThreads, 0, st>>>(maps, ws.dl, tm, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
+                                                          ws.d_cand, ws.d_cand_count, ws.cand_cap, c.threshold, ws.d_status);
   ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
   if (ctx->timers_on) cudaEventRecord(ws.ev[1], st);
   // ---- candidates, refinement, tie resolution, selection

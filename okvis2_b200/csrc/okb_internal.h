@@ -1,7 +1,10 @@
 // okb_internal.h -- context / workspace definitions shared by the translation units of libokvis_b200.so
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -82,6 +85,8 @@ struct CamWorkspace {
   okb_camera_model_t model; int has_model = 0;
   double* d_rays = nullptr; uint8_t* d_rays_valid = nullptr;
   cudaEvent_t ev_done = nullptr;
+  // TMA tensor maps of the internal layers (layer 0 is encoded per call)
+  CUtensorMap tma[kMaxLayers]; int tma_use[kMaxLayers] = {0}; int tma_ready = 0;
   long long* d_dbg = nullptr;   // per-frame cycle stamps of the single-CTA kernels (okb_debug_stamps)
   int32_t* d_m1_cell_off = nullptr; int32_t* d_m1_cell_list = nullptr; unsigned long long* d_m1_best = nullptr;
   // pinned staging
@@ -90,18 +95,25 @@ struct CamWorkspace {
   uint8_t* h_desc = nullptr;
   int32_t* h_count = nullptr;
   int32_t* h_status = nullptr;
+  double* h_rays = nullptr; uint8_t* h_rays_valid = nullptr; int h_rays_frames = 0;
   // timers
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  double ps_ms = 0, total_ms = 0;
+  cudaEvent_t ev_mid = nullptr;
+  double ps_ms = 0, total_ms = 0, score_ms = 0;
   int64_t ps_launches = 0;
   int pending_timing = 0;
   int64_t ps_bytes = 0;
 };
 
+// staging arena + stream of the host-buffer matchers. There are kMatchSlots of them; a calling thread is bound to one
+// slot (round robin at its first call) and holds the slot's mutex during a call, so that e.g. the map matching of two
+// cameras can be issued concurrently from two host threads (the reference spawns num_matching_threads workers).
+constexpr int kMatchSlots = 4;
 struct MatchWorkspace {
   cudaStream_t stream = nullptr;
   void* d_buf = nullptr; size_t d_cap = 0;
   void* h_buf = nullptr; size_t h_cap = 0;
+  std::mutex* mtx = nullptr;
 };
 
 }  // namespace okb
@@ -110,7 +122,8 @@ struct okb_context {
   int device = 0;
   int n_cams = 0;
   std::vector<okb::CamWorkspace> cams;
-  okb::MatchWorkspace match;
+  okb::MatchWorkspace match_slots[okb::kMatchSlots];
+  std::atomic<int> next_slot{0};
   // static tables
   okb::PatternPoint* d_pattern = nullptr;  // [scale][rot][point]
   uint32_t* d_short_pairs = nullptr;       // packed (i | j << 8)
@@ -132,6 +145,7 @@ int camera_backproject_batch(okb_context* ctx, int cam, int n_frames);
 int camera_stereo_prep(okb_context* ctx, const okb_camera_model_t& model, const double C_WC[9], const okb_keypoint_t* d_kp,
                        const int32_t* d_count, int cap, int n_frames, double* d_rays, uint8_t* d_valid, double* d_eW, double* d_sof,
                        double* d_c26, double* d_c6, cudaStream_t st);
+MatchWorkspace& match_ws(okb_context* ctx);   // the calling thread's slot
 int tables_init(okb_context* ctx, float pattern_scale);
 void tables_free(okb_context* ctx);
 }  // namespace okb

@@ -515,7 +515,7 @@ struct Arena {
 
 static int ensure(okb_context* ctx, size_t bytes)
 {
-  MatchWorkspace& m = ctx->match;
+  MatchWorkspace& m = match_ws(ctx);
   if (bytes <= m.d_cap) return OKB_OK;
   OKB_CUDA(cudaStreamSynchronize(m.stream));
   if (m.d_buf) cudaFree(m.d_buf);
@@ -528,16 +528,31 @@ static int ensure(okb_context* ctx, size_t bytes)
   return OKB_OK;
 }
 
+MatchWorkspace& match_ws(okb_context* ctx)
+{
+  static thread_local const okb_context* bound_ctx = nullptr;
+  static thread_local int slot = 0;
+  if (bound_ctx != ctx) { slot = ctx->next_slot.fetch_add(1) % kMatchSlots; bound_ctx = ctx; }
+  return ctx->match_slots[slot];
+}
+
 int match_init(okb_context* ctx)
 {
-  OKB_CUDA(cudaStreamCreateWithFlags(&ctx->match.stream, cudaStreamNonBlocking));
-  return ensure(ctx, 8 << 20);
+  for (int i = 0; i < kMatchSlots; i++) {
+    OKB_CUDA(cudaStreamCreateWithFlags(&ctx->match_slots[i].stream, cudaStreamNonBlocking));
+    ctx->match_slots[i].mtx = new std::mutex();
+  }
+  return OKB_OK;
 }
 void match_free(okb_context* ctx)
 {
-  if (ctx->match.d_buf) cudaFree(ctx->match.d_buf);
-  if (ctx->match.h_buf) cudaFreeHost(ctx->match.h_buf);
-  if (ctx->match.stream) cudaStreamDestroy(ctx->match.stream);
+  for (int i = 0; i < kMatchSlots; i++) {
+    MatchWorkspace& w = ctx->match_slots[i];
+    if (w.d_buf) cudaFree(w.d_buf);
+    if (w.h_buf) cudaFreeHost(w.h_buf);
+    if (w.stream) cudaStreamDestroy(w.stream);
+    delete w.mtx;
+  }
 }
 
 static bool bad_D(int D) { return D != 48 && D != 64; }
@@ -545,6 +560,9 @@ static bool bad_D(int D) { return D != 48 && D != 64; }
 }  // namespace okb
 
 using namespace okb;
+
+#define MW (match_ws(ctx))
+#define OKB_LOCK_SLOT std::lock_guard<std::mutex> slot_lock__(*MW.mtx)
 
 #define OKB_CHECK_ARGS(cond, who)                                  \
   if (!(cond)) { set_error("%s: bad arguments", who); return OKB_ERR_ARGUMENT; }
@@ -568,7 +586,8 @@ int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc,
   OKB_CHECK_ARGS(reprojection_threshold >= 0.0 && reprojection_threshold < 1e6, "okb_match_map3d");
   if (n_kp == 0) return OKB_OK;
   OKB_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->match.stream;
+  OKB_LOCK_SLOT;
+  cudaStream_t st = MW.stream;
   double max_x = 0, max_y = 0;   // extent of the keypoint cloud (sizes the grid; not part of the arithmetic)
   for (int k = 0; k < n_kp; k++) { if (kp_xy[2 * k] > max_x) max_x = kp_xy[2 * k]; if (kp_xy[2 * k + 1] > max_y) max_y = kp_xy[2 * k + 1]; }
   if (!(max_x < 1e6)) max_x = 1e6; if (!(max_y < 1e6)) max_y = 1e6;
@@ -576,7 +595,7 @@ int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc,
   m1_grid(reprojection_threshold, max_x, max_y, a.cell, a.gx, a.gy);
   size_t o_dist = 0, o_idx = 0, in_end = 0;
   for (int pass = 0; pass < 2; pass++) {
-    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
+    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)MW.h_buf; A.d = (uint8_t*)MW.d_buf;
     a.q_desc = A.in(kp_desc, (size_t)n_kp * D); a.q_xy = A.in(kp_xy, (size_t)n_kp * 2);
     a.q_use = kp_use ? A.in(kp_use, (size_t)n_kp) : nullptr;
     a.c_desc = A.in(cand_desc, (size_t)n_cand * D); a.c_lm = A.in(cand_lm, (size_t)n_cand);
@@ -588,10 +607,10 @@ int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc,
     if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
   }
   a.nq = n_kp; a.nc = n_cand; a.thr = match_threshold; a.thr_sq = reprojection_threshold * reprojection_threshold;
-  OKB_CUDA(cudaMemcpyAsync(ctx->match.d_buf, ctx->match.h_buf, in_end, cudaMemcpyHostToDevice, st));
+  OKB_CUDA(cudaMemcpyAsync(MW.d_buf, MW.h_buf, in_end, cudaMemcpyHostToDevice, st));
   int rc = m1_launch(ctx, a, D, 1, st);
   if (rc) return rc;
-  uint8_t* h = (uint8_t*)ctx->match.h_buf; uint8_t* d = (uint8_t*)ctx->match.d_buf;
+  uint8_t* h = (uint8_t*)MW.h_buf; uint8_t* d = (uint8_t*)MW.d_buf;
   OKB_CUDA(cudaMemcpyAsync(h + o_dist, d + o_dist, (o_idx - o_dist) + (size_t)n_kp * 4, cudaMemcpyDeviceToHost, st));
   OKB_CUDA(cudaStreamSynchronize(st));
   memcpy(out_dist, h + o_dist, (size_t)n_kp * 4); memcpy(out_lm, h + o_idx, (size_t)n_kp * 4);
@@ -602,8 +621,8 @@ static int run_gated(okb_context_t* ctx, int mode, int D, MatchArgs& a, size_t i
                      size_t o_idx, size_t o_hp, size_t o_init, size_t o_ctr, uint32_t* out_dist, int32_t* out_idx,
                      double* out_hp, uint8_t* out_init, int32_t* out_ctr)
 {
-  cudaStream_t st = ctx->match.stream;
-  uint8_t* h = (uint8_t*)ctx->match.h_buf; uint8_t* d = (uint8_t*)ctx->match.d_buf;
+  cudaStream_t st = MW.stream;
+  uint8_t* h = (uint8_t*)MW.h_buf; uint8_t* d = (uint8_t*)MW.d_buf;
   OKB_CUDA(cudaMemcpyAsync(d, h, in_end, cudaMemcpyHostToDevice, st));
   if (a.out_ctr) OKB_CUDA(cudaMemsetAsync(a.out_ctr, 0, 4, st));
   const int grid = (a.nq + 7) / 8;
@@ -640,10 +659,11 @@ int okb_match_map_uninit(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_
   if (out_ctr) *out_ctr = 0;
   if (n_kp == 0) return OKB_OK;
   OKB_CUDA(cudaSetDevice(ctx->device));
+  OKB_LOCK_SLOT;
   MatchArgs a; memset(&a, 0, sizeof(a));
   size_t o_dist = 0, o_idx = 0, o_hp = 0, o_ctr = 0, in_end = 0, o_end = 0;
   for (int pass = 0; pass < 2; pass++) {
-    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
+    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)MW.h_buf; A.d = (uint8_t*)MW.d_buf;
     a.q_desc = A.in(kp_desc, (size_t)n_kp * D); a.q_e = A.in(kp_e_W, (size_t)n_kp * 3);
     a.q_use = kp_use ? A.in(kp_use, (size_t)n_kp) : nullptr;
     a.q_prev_lm = kp_prev_lm ? A.in(kp_prev_lm, (size_t)n_kp) : nullptr;
@@ -673,6 +693,7 @@ static int stereo_like(okb_context_t* ctx, int mode, int D, int n0, const uint8_
   OKB_CHECK_ARGS(n1 == 0 || (desc1 && e1_W && valid1 && (mode == MODE_M3 || sof1)), who);
   if (n0 == 0) return OKB_OK;
   OKB_CUDA(cudaSetDevice(ctx->device));
+  OKB_LOCK_SLOT;
   // per-keypoint cos(2.6 sigma), cos(6 sigma) tables with the host libm (sigma = size/f * 0.125)
   std::vector<double> c26_0(n0), c6_0(n0), c26_1, c6_1;
   for (int i = 0; i < n0; i++) { const double s = sof0[i] * 0.125; c26_0[i] = cos(2.6 * s); c6_0[i] = cos(6.0 * s); }
@@ -683,7 +704,7 @@ static int stereo_like(okb_context_t* ctx, int mode, int D, int n0, const uint8_
   MatchArgs a; memset(&a, 0, sizeof(a));
   size_t o_dist = 0, o_idx = 0, o_hp = 0, o_init = 0, in_end = 0, o_end = 0;
   for (int pass = 0; pass < 2; pass++) {
-    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
+    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)MW.h_buf; A.d = (uint8_t*)MW.d_buf;
     a.q_desc = A.in(desc0, (size_t)n0 * D); a.q_e = A.in(e0_W, (size_t)n0 * 3);
     a.q_use = use0 ? A.in(use0, (size_t)n0) : nullptr;
     a.q_sof = A.in(sof0, (size_t)n0); a.q_cos26 = A.in(c26_0.data(), (size_t)n0); a.q_cos6 = A.in(c6_0.data(), (size_t)n0);
@@ -762,7 +783,7 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
                  d_count1 && model1 && C_WC0 && r_WC0 && C_WC1 && r_WC1 && d_out_k1 && d_out_dist && d_out_hp_W && d_out_initialisable,
                  "okb_match_stereo_device_ptr");
   OKB_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->match.stream;
+  cudaStream_t st = stream ? (cudaStream_t)stream : MW.stream;
   // scratch: per side rays(3) eW(3) sof c26 c6 doubles + valid bytes
   const size_t n0 = (size_t)n_frames * cap0, n1 = (size_t)n_frames * cap1;
   const size_t need = (n0 + n1) * (9 * 8 + 8);
@@ -826,17 +847,18 @@ int okb_match_place(okb_context_t* ctx, int D, int n_lm, const int32_t* lm_offse
   const int n_desc = lm_offsets[n_lm];
   for (int i = 0; i < n_lm; i++) OKB_CHECK_ARGS(lm_offsets[i + 1] >= lm_offsets[i] && lm_offsets[i + 1] - lm_offsets[i] < 4096, "okb_match_place");
   OKB_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->match.stream;
+  OKB_LOCK_SLOT;
+  cudaStream_t st = MW.stream;
   const int32_t* d_off = nullptr; const uint8_t *d_ld = nullptr, *d_kd = nullptr; int32_t* d_ok = nullptr; uint32_t* d_od = nullptr;
   size_t o_k = 0, o_d = 0, in_end = 0, o_end = 0;
   for (int pass = 0; pass < 2; pass++) {
-    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
+    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)MW.h_buf; A.d = (uint8_t*)MW.d_buf;
     d_off = A.in(lm_offsets, (size_t)n_lm + 1); d_ld = A.in(lm_desc, (size_t)n_desc * D); d_kd = A.in(kp_desc, (size_t)n_kp * D);
     in_end = A.off;
     d_ok = A.out<int32_t>(n_lm, &o_k); d_od = A.out<uint32_t>(n_lm, &o_d); o_end = A.off;
     if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
   }
-  uint8_t* h = (uint8_t*)ctx->match.h_buf; uint8_t* d = (uint8_t*)ctx->match.d_buf;
+  uint8_t* h = (uint8_t*)MW.h_buf; uint8_t* d = (uint8_t*)MW.d_buf;
   OKB_CUDA(cudaMemcpyAsync(d, h, in_end, cudaMemcpyHostToDevice, st));
   const int grid = (n_lm + 7) / 8;
   if (D == 64) k_match_place<4><<<grid, 256, 0, st>>>(n_lm, d_off, d_ld, n_kp, d_kd, match_threshold, d_ok, d_od);
@@ -855,15 +877,16 @@ int okb_hamming_matrix(okb_context_t* ctx, int D, int n_a, const uint8_t* a, int
   if (n_a == 0 || n_b == 0) return OKB_OK;
   OKB_CHECK_ARGS(a && b, "okb_hamming_matrix");
   OKB_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->match.stream;
+  OKB_LOCK_SLOT;
+  cudaStream_t st = MW.stream;
   const uint8_t *da = nullptr, *db = nullptr; uint16_t* dout = nullptr; size_t o_out = 0, in_end = 0, o_end = 0;
   for (int pass = 0; pass < 2; pass++) {
-    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)ctx->match.h_buf; A.d = (uint8_t*)ctx->match.d_buf;
+    Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)MW.h_buf; A.d = (uint8_t*)MW.d_buf;
     da = A.in(a, (size_t)n_a * D); db = A.in(b, (size_t)n_b * D); in_end = A.off;
     dout = A.out<uint16_t>((size_t)n_a * n_b, &o_out); o_end = A.off;
     if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
   }
-  uint8_t* h = (uint8_t*)ctx->match.h_buf; uint8_t* d = (uint8_t*)ctx->match.d_buf;
+  uint8_t* h = (uint8_t*)MW.h_buf; uint8_t* d = (uint8_t*)MW.d_buf;
   OKB_CUDA(cudaMemcpyAsync(d, h, in_end, cudaMemcpyHostToDevice, st));
   k_hamming_matrix<<<dim3((n_b + 255) / 256, n_a), 256, 0, st>>>(D / 16, n_a, da, n_b, db, dout);
   ctx->launches++;

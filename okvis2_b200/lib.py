@@ -74,6 +74,7 @@ _PROTOS = {
     "okb_pyramid_score_bytes": (C.c_int64, [vp, i32]),
     "okb_enable_timers": (i32, [vp, i32]),
     "okb_reset_timers": (i32, [vp]),
+    "okb_get_score_kernel_ms": (i32, [vp, i32, C.POINTER(f64)]),
     "okb_get_timers": (i32, [vp, i32, C.POINTER(f64), C.POINTER(C.c_int64), C.POINTER(f64)]),
     "okb_match_map3d": (i32, [vp, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, f64, u32, vp, vp]),
     "okb_match_map_uninit": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, f64, u32, vp, vp, vp, vp]),
@@ -82,6 +83,7 @@ _PROTOS = {
     "okb_match_place": (i32, [vp, i32, i32, vp, vp, i32, vp, u32, vp, vp]),
     "okb_hamming_matrix": (i32, [vp, i32, i32, vp, i32, vp, vp]),
     "okb_set_camera_model": (i32, [vp, i32, vp]),
+    "okb_last_back_projections": (i32, [vp, i32, i32, i32, vp, vp, vp]),
     "okb_back_project": (i32, [vp, i32, i32, vp, vp, vp]),
     "okb_match_stereo_device": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
     "okb_match_stereo_device_ptr": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]),
