@@ -1009,6 +1009,9 @@ int detect_init_camera(okb_context* ctx, int cam)
   ws.cand_cap = std::max(16384, (W * H / 32 + 1023) / 1024 * 1024);
   ws.kp_cap = c.max_keypoints > 0 ? (int)align_up((size_t)c.max_keypoints, 64) : kSortCap;
   OKB_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+  OKB_CUDA(cudaStreamCreateWithFlags(&ws.stream2, cudaStreamNonBlocking));
+  OKB_CUDA(cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming));
+  OKB_CUDA(cudaEventCreateWithFlags(&ws.ev_join, cudaEventDisableTiming));
   OKB_CUDA(cudaMalloc(&ws.d_in, (size_t)W * H * B));
   OKB_CUDA(cudaMalloc(&ws.d_img, off * B));
   OKB_CUDA(cudaMalloc(&ws.d_score, off * B));
@@ -1063,6 +1066,9 @@ void detect_free_camera(okb_context* ctx, int cam)
   cudaFreeHost(ws.h_img); cudaFreeHost(ws.h_kp); cudaFreeHost(ws.h_desc); cudaFreeHost(ws.h_count); cudaFreeHost(ws.h_status); cudaFreeHost(ws.h_rays); cudaFreeHost(ws.h_rays_valid);
   for (int i = 0; i < 4; i++) if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
   if (ws.ev_mid) cudaEventDestroy(ws.ev_mid);
+  if (ws.ev_fork) cudaEventDestroy(ws.ev_fork);
+  if (ws.ev_join) cudaEventDestroy(ws.ev_join);
+  if (ws.stream2) cudaStreamDestroy(ws.stream2);
   if (ws.stream) cudaStreamDestroy(ws.stream);
 }
 
@@ -1135,6 +1141,14 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
     ws.epoch = 1;
   }
   const size_t in_stride = (size_t)src_pitch * H;
+  // ---- fork: the integral image only needs the input frames; it runs on a side stream underneath the detection
+  //      kernels (several of which are latency-bound single-CTA-per-frame kernels that leave most SMs idle)
+  const int ipitch = W + 1;
+  OKB_CUDA(cudaEventRecord(ws.ev_fork, st));
+  OKB_CUDA(cudaStreamWaitEvent(ws.stream2, ws.ev_fork, 0));
+  k_integral_rows<<<dim3((H + 7) / 8, B), 256, 0, ws.stream2>>>(d_images, src_pitch, in_stride, W, H, ws.d_integral, ipitch);
+  k_integral_cols<<<dim3((W + 31) / 32, B), 1024, 0, ws.stream2>>>(W, H, ws.d_integral, ipitch);
+  OKB_CUDA(cudaEventRecord(ws.ev_join, ws.stream2));
   // ---- pyramid: layers whose parents are complete can share a launch
   for (int i = 1; i < ws.n_layers;) {
     ResizeJobs jobs; jobs.n = 0;
@@ -1187,10 +1201,8 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
                                             W, H, c.max_keypoints, ws.kp_cap, ws.d_kp, ws.d_kscale, ws.d_count, ws.d_status, ws.d_dbg);
   ctx->launches += 3;
   if (ctx->timers_on) cudaEventRecord(ws.ev[2], st);
-  // ---- descriptors
-  const int ipitch = W + 1;
-  k_integral_rows<<<dim3((H + 7) / 8, B), 256, 0, st>>>(d_images, src_pitch, in_stride, W, H, ws.d_integral, ipitch);
-  k_integral_cols<<<dim3((W + 31) / 32, B), 1024, 0, st>>>(W, H, ws.d_integral, ipitch);
+  // ---- descriptors (the integral image was produced on the side stream, see the fork above)
+  OKB_CUDA(cudaStreamWaitEvent(st, ws.ev_join, 0));
   k_describe<<<dim3((ws.kp_cap + 3) / 4, B), 128, 0, st>>>(d_images, src_pitch, in_stride, H, ws.d_integral, ipitch,
                                                            ctx->d_pattern, ctx->d_short_pairs, ctx->d_long_pairs, ws.d_kp,
                                                            ws.d_kscale, ws.d_count, ws.kp_cap, ws.d_desc);

@@ -60,6 +60,8 @@ struct CandRecord {
 struct CamWorkspace {
   okb_camera_config_t cfg;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;            // side stream (integral image)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_layers = 0;
   LayerGeom geom[kMaxLayers];
   DeviceLayers dl;

@@ -141,3 +141,50 @@ def test_properties_at_full_size():
     ham = np.array([np.unpackbits(np.frombuffer(a[k], np.uint8) ^ np.frombuffer(b[k], np.uint8)).sum() for k in common])
     assert (ham == 0).mean() > 0.8 and ham.max() <= 24, (float((ham == 0).mean()), int(ham.max()))
     fe.close()
+
+
+@pytest.mark.parametrize("octv,thr,W,H", [(1, 20, 400, 300), (4, 25, 640, 480), (2, 60, 333, 222)])
+def test_other_octave_counts_equal_oracle(octv, thr, W, H):
+    img = synth_frame(40 + octv, W, H)
+    fe = Frontend(1, W, H)
+    fe.configure(threshold=thr, octaves=octv, max_keypoints=0)
+    kp, d = run(fe, img)
+    rk, rd = oracle.Brisk(thr, octv).detect_and_compute(img)
+    assert len(rk) > 50
+    assert_same_features(kp, d, rk, rd, f"octaves {octv}")
+    fe.close()
+
+
+def test_concurrent_cameras_from_two_host_threads():
+    """Frontend::detectAndDescribe is documented thread-safe per camera (Frontend.hpp:87; ThreadedSlam.cpp:432-448)."""
+    import threading
+    fe = Frontend(2, 752, 480)
+    fe.configure(threshold=30, octaves=3, max_keypoints=1000)
+    o = oracle.Brisk(30, 3)
+    frames = [synth_stereo(800 + t, 752, 480) for t in range(4)]
+    refs = [[o.detect_and_compute(f[c], 1000) for c in range(2)] for f in frames]
+    for t, f in enumerate(frames):
+        mf = MultiFrame(2)
+        mf.setImage(0, f[0]); mf.setImage(1, f[1])
+        th = threading.Thread(target=fe.detectAndDescribe, args=(1, mf))
+        th.start(); fe.detectAndDescribe(0, mf); th.join()
+        for c in range(2):
+            assert_same_features(mf.frames[c].keypoints, mf.frames[c].descriptors, refs[t][c][0], refs[t][c][1], f"t{t} cam{c}")
+    fe.close()
+
+
+def test_capacity_errors_are_reported_not_truncated():
+    import ctypes as C
+    from okvis2_b200 import lib as okl
+    fe = Frontend(1, 752, 480)
+    fe.configure(threshold=30, octaves=3, max_keypoints=0)
+    img = synth_frame(1000, 752, 480)
+    kp = np.zeros(100, okl.KP_DTYPE); desc = np.zeros((100, 64), np.uint8); n = C.c_int(0)
+    rc = okl.lib().okb_detect_describe(fe.ctx, 0, img.ctypes.data, 752, kp.ctypes.data, desc.ctypes.data, 100, C.byref(n))
+    assert rc == okl.OKB_ERR_CAPACITY and b"capacity" in okl.lib().okb_last_error()
+    rc = okl.lib().okb_detect_describe(fe.ctx, 3, img.ctypes.data, 752, kp.ctypes.data, desc.ctypes.data, 100, C.byref(n))
+    assert rc == okl.OKB_ERR_ARGUMENT
+    fe.close()
+    with pytest.raises(okl.OkbError) as e:
+        Frontend(1, 752, 480, descriptor_bytes=48)   # the 48-byte BRISK2 extractor is not built (DESIGN.md §2)
+    assert e.value.status == okl.OKB_ERR_UNSUPPORTED

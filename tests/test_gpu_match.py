@@ -128,3 +128,37 @@ def test_matcher_argument_errors(fe):
     from okvis2_b200.lib import OkbError
     with pytest.raises(OkbError):
         fe.hammingMatrix(np.zeros((2, 32), np.uint8), np.zeros((2, 32), np.uint8))  # D must be 48 or 64
+
+
+def test_m1_degenerate_projections_follow_the_reference(fe):
+    """NaN projections are not gated by `reprDist.dot(reprDist) > thr` (false for NaN), infinite ones always are."""
+    rng = np.random.default_rng(4)
+    kd = rng.integers(0, 256, (50, 64), dtype=np.uint8)
+    kp_xy = rng.uniform(0, 700, (50, 2))
+    cand = np.concatenate([kd[:10], kd[10:20], kd[20:30]])          # exact copies -> distance 0 where allowed
+    cand_lm = np.arange(30, dtype=np.int32)
+    proj = np.zeros((30, 2)); proj[:10] = np.nan; proj[10:20] = np.inf; proj[20:30] = kp_xy[20:30] + 3.0
+    is3d = np.ones(30, np.uint8)
+    got = fe.matchToMapByThread(kd, kp_xy, None, cand, cand_lm, proj, is3d, True)
+    ref = oracle.match_map3d(kd, kp_xy, None, cand, cand_lm, proj, is3d, 20.0, 60)
+    eq(got, ref, "M1 degenerate")
+    assert (ref[1][:10] == np.arange(10)).all() and (ref[1][10:20] == -1).all() and (ref[1][20:30] == np.arange(20, 30)).all()
+
+
+def test_matchers_from_two_host_threads(fe):
+    import threading
+    s = [stereo_scene(70 + i, 500, 480) for i in range(2)]
+    out = [None, None]
+
+    def work(i):
+        x = s[i]
+        for _ in range(5):
+            out[i] = fe.matchStereo(x["desc0"], x["valid0"], x["e0_W"], x["sof0"], x["desc1"], x["valid1"], x["e1_W"], x["sof1"],
+                                    x["r_WC0"], x["r_WC1"], x["T_CW0"], x["T_CW1"])
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for i in range(2):
+        x = s[i]
+        ref = oracle.match_stereo(x["desc0"], x["valid0"], x["e0_W"], x["sof0"], x["desc1"], x["valid1"], x["e1_W"], x["sof1"],
+                                  x["r_WC0"], x["r_WC1"], x["T_CW0"], x["T_CW1"], 60)
+        eq(out[i], ref, f"thread {i}")
