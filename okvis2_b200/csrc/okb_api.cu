@@ -110,7 +110,7 @@ static int status_to_error(const CamWorkspace& ws, int n_frames)
 {
   for (int b = 0; b < n_frames; b++)
     if (ws.h_status[b]) {
-      set_error("detect: device capacity exceeded on frame %d (flags 0x%x: 1=candidates>%d, 2=ties, 4=keypoints>sort cap, "
+      set_error("detect: device capacity exceeded on frame %d (flags 0x%x: 1=a layer overflowed its share of the %d candidate slots, 2=ties, 4=keypoints>sort cap, "
                 "8=keypoints>output cap %d, 16=TMA tile load timed out)", b, ws.h_status[b], ws.cand_cap, ws.kp_cap);
       return OKB_ERR_CAPACITY;
     }

@@ -63,7 +63,7 @@ struct ResizeJob {
 };
 struct ResizeJobs { ResizeJob j[2]; int n; int tiles_x[2], tiles_y[2]; };
 
-__global__ void __launch_bounds__(256) k_resize(ResizeJobs jobs)
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ ResizeJobs jobs)
 {
   int t = blockIdx.x, ji = 0;
   const int n0 = jobs.tiles_x[0] * jobs.tiles_y[0];
@@ -114,6 +114,18 @@ __global__ void __launch_bounds__(256) k_resize(ResizeJobs jobs)
 // ---------------------------------------------------------------------------------------------------------------
 // score map tiling
 constexpr int kTileW = 56, kTileH = 30;   // (30 + 2) rows x (56 / 4 + 2) groups = 512 score items = 2 per thread
+
+// per-layer regions of the candidate list (so that a warp of the refinement kernel sees candidates of ONE layer and
+// follows one code path); cand_count is [frames][kMaxLayers]
+struct CandRegions { int off[kMaxLayers + 1]; };
+__device__ __forceinline__ int cand_total(const CandRegions& cr, const int32_t* count, int n_layers, int* prefix /*kMaxLayers+1*/)
+{
+  int acc = 0;
+#pragma unroll
+  for (int l = 0; l < kMaxLayers; l++) { prefix[l] = acc; if (l < n_layers) acc += min(count[l], cr.off[l + 1] - cr.off[l]); }
+  prefix[kMaxLayers] = acc;
+  return acc;
+}
 
 struct TileMap { int n_layers; int tile_prefix[kMaxLayers + 1]; int tiles_x[kMaxLayers]; };
 
@@ -198,10 +210,12 @@ constexpr int kScW = kTileW + 8;     // score tile row: x0-4 .. x0+67
 constexpr int kScH = kTileH + 2;     // rows y0-1 .. y0+32
 constexpr int kScoreThreads = 256;
 
-__global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_constant__ TmaMaps maps, DeviceLayers dl, TileMap tm,
+__global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_constant__ TmaMaps maps, const __grid_constant__ DeviceLayers dl,
+                                                             const __grid_constant__ TileMap tm,
                                                              const uint8_t* in0, int in_pitch, size_t in_frame_stride,
                                                              uint8_t* img_block, uint8_t* score_block, uint32_t* cand,
-                                                             int32_t* cand_count, int cand_cap, int threshold, int32_t* status)
+                                                             int32_t* cand_count, int cand_cap, const __grid_constant__ CandRegions cr,
+                                                             int threshold, int32_t* status)
 {
   __shared__ __align__(128) uint8_t tile[kImgH][kImgW];
   __shared__ __align__(8) uint64_t bar;
@@ -316,11 +330,12 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
       if (m) {
         int base = 0;
         const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(&cand_count[frame], __popc(m));
+        if (lane == leader) base = atomicAdd(&cand_count[frame * kMaxLayers + layer], __popc(m));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (is_c) {
           const int pos = base + __popc(m & ((1u << lane) - 1u));
-          if (pos < cand_cap) cand[(size_t)frame * cand_cap + pos] = time_key(layer, xb + px, y) | (tie ? 0x80000000u : 0u);
+          if (pos < cr.off[layer + 1] - cr.off[layer])
+            cand[(size_t)frame * cand_cap + cr.off[layer] + pos] = time_key(layer, xb + px, y) | (tie ? 0x80000000u : 0u);
         }
       }
     }
@@ -357,13 +372,14 @@ __device__ __forceinline__ void emit_touches_warp(const DeviceLayers& dl, uint32
   }
 }
 
-__global__ void __launch_bounds__(128) k_refine(DeviceLayers dl, const uint8_t* in0, int in_pitch, size_t in_frame_stride,
+__global__ void __launch_bounds__(128) k_refine(const __grid_constant__ DeviceLayers dl, const uint8_t* in0, int in_pitch, size_t in_frame_stride,
                                                 uint8_t* img_block, uint8_t* score_block, uint32_t* touch_block,
                                                 const uint32_t* cand, const int32_t* cand_count, int cand_cap,
-                                                CandRecord* rec, int threshold, uint32_t epoch)
+                                                const __grid_constant__ CandRegions cr, CandRecord* rec, int threshold, uint32_t epoch)
 {
   const int frame = blockIdx.y;
-  const int n = min(cand_count[frame], cand_cap);
+  int prefix[kMaxLayers + 1];
+  const int n = cand_total(cr, cand_count + frame * kMaxLayers, dl.n, prefix);
   if (blockIdx.x * blockDim.x >= n) return;
   __shared__ FrameViews v;  // dynamically indexed by layer: keep it out of local memory
   if (threadIdx.x == 0) make_views(dl, in0, in_pitch, in_frame_stride, img_block, score_block, touch_block, frame, v);
@@ -375,7 +391,10 @@ __global__ void __launch_bounds__(128) k_refine(DeviceLayers dl, const uint8_t* 
   RefineResult r;
   r.keep = 0; r.own_touch = 0; r.has_above = 0; r.above.n_queries = 0; r.above.exited = 1; r.above.max_x = r.above.max_y = 0;
   if (have) {
-    const uint32_t c = cand[(size_t)frame * cand_cap + i];
+    int l = 0;   // records are dense and layer-major: record i is candidate i - prefix[l] of layer l
+#pragma unroll
+    for (int j = 1; j < kMaxLayers; j++) if (i >= prefix[j]) l = j;
+    const uint32_t c = cand[(size_t)frame * cand_cap + cr.off[l] + (i - prefix[l])];
     key = c & 0x7fffffffu; tie = (int)(c >> 31);
     refine_candidate(v.L, v.n, (int)(key >> 22), (int)(key & 2047), (int)((key >> 11) & 2047), threshold, r);
     CandRecord out;
@@ -436,9 +455,9 @@ struct TieInfo {  // what a tie's cache touches look like if it turns out to be 
 // from shared memory: a tie waits only for the earlier ties whose touches can reach its 5x5 window (same layer within
 // 4 px, or the layer below through the window of its above-scan), listed once; when they are all decided it ORs the
 // footprint of the winners among them into its 25-bit "touched" mask and evaluates the reference's isMax2D.
-__global__ void __launch_bounds__(512) k_resolve(DeviceLayers dl, const uint8_t* score_block, const uint32_t* touch_block,
-                                                 const int32_t* cand_count, int cand_cap, CandRecord* rec,
-                                                 uint32_t epoch, int threshold, int32_t* status, long long* dbg)
+__global__ void __launch_bounds__(512) k_resolve(const __grid_constant__ DeviceLayers dl, const uint8_t* score_block, const uint32_t* touch_block,
+                                                 const int32_t* cand_count, int cand_cap, const __grid_constant__ CandRegions cr,
+                                                 CandRecord* rec, uint32_t epoch, int threshold, int32_t* status, long long* dbg)
 {
 #define OKB_STAMP(i) if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + (i)] = clock64()
   OKB_STAMP(0);
@@ -452,7 +471,8 @@ __global__ void __launch_bounds__(512) k_resolve(DeviceLayers dl, const uint8_t*
   int8_t* n_block = state + kMaxTies;                                        // -1: list overflowed, scan instead
   __shared__ int n_ties, n_unresolved, layer_start[kMaxLayers + 1];
   const int frame = blockIdx.x;
-  const int n = min(cand_count[frame], cand_cap);
+  int prefix_[kMaxLayers + 1];
+  const int n = cand_total(cr, cand_count + frame * kMaxLayers, dl.n, prefix_);
   CandRecord* R = rec + (size_t)frame * cand_cap;
   if (threadIdx.x == 0) n_ties = 0;
   __syncthreads();
@@ -672,7 +692,8 @@ constexpr int kFinalizeSmem = kSortCap * 8 + kSortCap * 4 + (kMaxRows + 2) * 2 +
 // One CTA (1024 threads) per frame: order the surviving keypoints by (layer, y, x), keep the max_kp strongest
 // (ties: earlier first), drop the ones whose sampling pattern leaves the image, write cv::KeyPoint records.
 // Ordering is a counting sort by (layer, row) followed by a tiny in-place insertion sort inside every row group.
-__global__ void __launch_bounds__(1024) k_finalize(DeviceLayers dl, const int32_t* cand_count, int cand_cap, const CandRecord* rec,
+__global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ DeviceLayers dl, const int32_t* cand_count, int cand_cap,
+                                                   const __grid_constant__ CandRegions cr, const CandRecord* rec,
                                                    const float* scale_bounds, const uint32_t* size_list, int W, int H,
                                                    int max_kp, int kp_cap, okb_keypoint_t* kp_out, int32_t* kscale_out,
                                                    int32_t* count_out, int32_t* status, long long* dbg)
@@ -687,8 +708,10 @@ __global__ void __launch_bounds__(1024) k_finalize(DeviceLayers dl, const int32_
   __shared__ uint32_t sel_prefix;
   __shared__ int sel_remaining;
   const int frame = blockIdx.x;
-  const int n = min(cand_count[frame], cand_cap);
-  if (cand_count[frame] > cand_cap && threadIdx.x == 0) atomicOr(&status[frame], 1);
+  int prefix_[kMaxLayers + 1];
+  const int n = cand_total(cr, cand_count + frame * kMaxLayers, dl.n, prefix_);
+  if (threadIdx.x < dl.n && cand_count[frame * kMaxLayers + threadIdx.x] > cr.off[threadIdx.x + 1] - cr.off[threadIdx.x])
+    atomicOr(&status[frame], 1);   // a layer's region of the candidate list overflowed
   const CandRecord* R = rec + (size_t)frame * cand_cap;
   if (threadIdx.x == 0) {
     n_valid = 0;
@@ -1006,7 +1029,20 @@ int detect_init_camera(okb_context* ctx, int cam)
     ws.dl.l[i] = DeviceLayer{g.w, g.h, g.pitch, (uint32_t)g.offset, g.scale, g.offset_px};
   }
   const int B = c.max_batch;
-  ws.cand_cap = std::max(16384, (W * H / 32 + 1023) / 1024 * 1024);
+  {
+    // candidate list: one region per layer, sized by the layer's share of the pixels with 6x slack
+    const int base = std::max(16384, (W * H / 32 + 1023) / 1024 * 1024);
+    long long area = 0;
+    for (int i = 0; i < ws.n_layers; i++) area += (long long)ws.geom[i].w * ws.geom[i].h;
+    int acc = 0;
+    for (int i = 0; i < kMaxLayers; i++) {
+      ws.cand_off[i] = acc;
+      if (i < ws.n_layers)   // coarse layers carry more corners per pixel: generous floors, capped at the single-layer size
+        acc += (int)align_up((size_t)std::min((long long)base, std::max(4096LL, 6LL * base * ws.geom[i].w * ws.geom[i].h / area)), 128);
+    }
+    ws.cand_off[kMaxLayers] = acc;
+    ws.cand_cap = acc;
+  }
   ws.kp_cap = c.max_keypoints > 0 ? (int)align_up((size_t)c.max_keypoints, 64) : kSortCap;
   OKB_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
   OKB_CUDA(cudaStreamCreateWithFlags(&ws.stream2, cudaStreamNonBlocking));
@@ -1021,7 +1057,7 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMemset(ws.d_img, 0, off * B));
   OKB_CUDA(cudaMalloc(&ws.d_integral, (size_t)(W + 1) * (H + 1) * 4 * B));
   OKB_CUDA(cudaMalloc(&ws.d_cand, (size_t)ws.cand_cap * 4 * B));
-  OKB_CUDA(cudaMalloc(&ws.d_cand_count, 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_cand_count, 4 * kMaxLayers * B));
   OKB_CUDA(cudaMalloc(&ws.d_rec, (size_t)ws.cand_cap * sizeof(CandRecord) * B));
   OKB_CUDA(cudaMalloc(&ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t) * B));
   OKB_CUDA(cudaMalloc(&ws.d_kscale, (size_t)ws.kp_cap * 4 * B));
@@ -1183,21 +1219,22 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   }
   for (int i = ws.n_layers + 1; i <= kMaxLayers; i++) tm.tile_prefix[i] = tm.tile_prefix[ws.n_layers];
   const int n_tiles = tm.tile_prefix[ws.n_layers];
-  OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, 4 * B, st));
+  OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, 4 * kMaxLayers * B, st));
+  CandRegions cr; for (int i = 0; i <= kMaxLayers; i++) cr.off[i] = ws.cand_off[i];
   OKB_CUDA(cudaMemsetAsync(ws.d_status, 0, 4 * B, st));
   TmaMaps maps;
   { int rc = build_tma_maps(ws, d_images, src_pitch, in_stride, c.max_batch, maps); if (rc) return rc; }
   k_score_nms<<<dim3(n_tiles, B), kScoreThreads, 0, st>>>(maps, ws.dl, tm, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
-                                                          ws.d_cand, ws.d_cand_count, ws.cand_cap, c.threshold, ws.d_status);
+                                                          ws.d_cand, ws.d_cand_count, ws.cand_cap, cr, c.threshold, ws.d_status);
   ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
   if (ctx->timers_on) cudaEventRecord(ws.ev[1], st);
   // ---- candidates, refinement, tie resolution, selection
   k_refine<<<dim3((ws.cand_cap + 127) / 128, B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
-                                                               ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap,
+                                                               ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap, cr,
                                                                ws.d_rec, c.threshold, ws.epoch);
-  k_resolve<<<B, 512, kResolveSmem, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_cand_count, ws.cand_cap, ws.d_rec, ws.epoch, c.threshold,
+  k_resolve<<<B, 512, kResolveSmem, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_cand_count, ws.cand_cap, cr, ws.d_rec, ws.epoch, c.threshold,
                                           ws.d_status, ws.d_dbg);
-  k_finalize<<<B, 1024, kFinalizeSmem, st>>>(ws.dl, ws.d_cand_count, ws.cand_cap, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,
+  k_finalize<<<B, 1024, kFinalizeSmem, st>>>(ws.dl, ws.d_cand_count, ws.cand_cap, cr, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,
                                             W, H, c.max_keypoints, ws.kp_cap, ws.d_kp, ws.d_kscale, ws.d_count, ws.d_status, ws.d_dbg);
   ctx->launches += 3;
   if (ctx->timers_on) cudaEventRecord(ws.ev[2], st);

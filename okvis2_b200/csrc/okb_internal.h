@@ -65,7 +65,8 @@ struct CamWorkspace {
   int n_layers = 0;
   LayerGeom geom[kMaxLayers];
   DeviceLayers dl;
-  int cand_cap = 0;   // candidate capacity per frame
+  int cand_cap = 0;   // candidate capacity per frame (sum of the per-layer regions)
+  int cand_off[kMaxLayers + 1] = {0};
   int kp_cap = 0;     // keypoint capacity per frame (output rows)
   uint32_t epoch = 0;
   // device buffers ([max_batch] leading dimension)
