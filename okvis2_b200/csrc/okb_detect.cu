@@ -520,6 +520,7 @@ __global__ void __launch_bounds__(512) k_resolve(const __grid_constant__ DeviceL
     tmask[i] = mask;
   }
   __syncthreads();
+  OKB_STAMP(7);
   // enumerate the possible blockers of tie ti (earlier ties whose touches can reach its window); F(u) true = stop
   auto for_each_blocker = [&](int ti, auto F) {
     const uint32_t key = (uint32_t)(ties[ti] >> 32);
@@ -556,6 +557,7 @@ __global__ void __launch_bounds__(512) k_resolve(const __grid_constant__ DeviceL
     n_block[ti] = (int8_t)nb;
   }
   __syncthreads();
+  OKB_STAMP(15);
   // the boxes are no longer needed unless a list overflowed (then the scan above is reused every round, with boxes):
   // keep them in that (rare) case and read the touch info from the records instead
   __shared__ int any_overflow;
