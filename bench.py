@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -192,7 +192,9 @@ def run_sharded(args, cfg, rank, world, local_rank):
     n_frames = ring * B
     d_img, maps, d_maps, d_m1 = [], [], [], []
     for li, c in enumerate(mine):
-        base = [synth_frame(3000 + 17 * c + i, W, H) for i in range(4)]
+        # every camera sees the same four scenes, displaced horizontally by 14 px per camera index (so that overlapping
+        # pairs share content and the stereo matcher's gates run on real candidates), then drifting frame to frame
+        base = [np.roll(synth_frame(3000 + i, W, H), 14 * c, 1) for i in range(4)]
         frames = np.stack([np.roll(base[i % 4], (3 * (i // 4), 5 * (i // 4)), (0, 1)) for i in range(n_frames)])
         d_img.append(torch.from_numpy(frames).cuda())
         mf = MultiFrame(len(mine)); mf.setImage(li, frames[0]); fe.detectAndDescribe(li, mf)
@@ -242,9 +244,9 @@ def run_sharded(args, cfg, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank); sampler.start()
     for s in range(warm):
         step(s)
-    sampler = ClockSampler(local_rank); sampler.start()
     barrier()
     launches0 = L_.okb_launch_count(ctx)
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
@@ -367,10 +369,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-resident, device-timed
+    sampler = ClockSampler(local_rank); sampler.start()   # samples clocks through the warm-up, value, roofline and e2e legs
     for s in range(warm):
         device_step(s)
     okl.check(L_.okb_sync(ctx))
-    sampler = ClockSampler(local_rank); sampler.start()
     barrier()
     launches0 = L_.okb_launch_count(ctx)
     ev0 = torch.cuda.Event(enable_timing=True); ev0.record(streams[0])
@@ -382,7 +384,6 @@ def main():
     barrier()
     dev_ms = max(ev0.elapsed_time(e) for e in ends)
     launches = L_.okb_launch_count(ctx) - launches0
-    clocks = sampler.stop()
     # ---- kernel-level timing for the roofline: a few extra steps with the two camera streams serialized, so that the
     #      CUDA events around the pyramid+score launches (recorded on the launching stream inside the library) time those
     #      kernels alone and not whatever the other camera's stream runs next to them
@@ -449,11 +450,53 @@ def main():
     e2e_s = sec.value
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
-    e2e = {"value": world * e2e_frames / e2e_s, "unit": "stereo frames/s", "h2d_bytes_per_step": int(h2d.value / e2e_frames),
-           "d2h_bytes_per_step": int(d2h.value / e2e_frames), "ms_per_stereo_frame": 1e3 * e2e_s / e2e_frames,
-           "step": "one stereo frame: 2x okb_detect_describe (one host thread per camera) + okb_match_stereo + 2x okb_match_map3d, host buffers",
-           "frames": e2e_frames, "keypoints_per_frame": nkp.value / e2e_frames / 2, "matches_per_frame": nm.value / e2e_frames}
+    streaming = {"value": world * e2e_frames / e2e_s, "unit": "stereo frames/s", "h2d_bytes_per_frame": int(h2d.value / e2e_frames),
+                 "d2h_bytes_per_frame": int(d2h.value / e2e_frames), "ms_per_stereo_frame": 1e3 * e2e_s / e2e_frames,
+                 "step": "one stereo frame per call (live use): 2x okb_detect_describe (one host thread per camera) + okb_match_stereo + 2x okb_match_map3d, host buffers",
+                 "frames": e2e_frames, "keypoints_per_frame": nkp.value / e2e_frames / 2, "matches_per_frame": nm.value / e2e_frames}
 
+    # ---- e2e proper: the SAME step as `value` (a batch of B stereo frames: detect+describe both cameras, M1 per camera,
+    #      M4) through the host-buffer C ABI (okb_detect_describe_batch / okb_match_map3d_batch / okb_match_stereo_batch)
+    #      from page-locked host memory; every H2D / D2H copy of the step is inside the timed region
+    class ReplayIO(C.Structure):
+        _fields_ = [("n_steps", C.c_int32), ("warmup", C.c_int32), ("batch", C.c_int32), ("ring", C.c_int32), ("W", C.c_int32),
+                    ("H", C.c_int32), ("cap", C.c_int32), ("pad_", C.c_int32),
+                    ("img", C.c_void_p * 2), ("kp", C.c_void_p * 2), ("desc", C.c_void_p * 2), ("n", C.c_void_p * 2),
+                    ("n_cand", C.c_int32 * 2), ("n_lm", C.c_int32 * 2),
+                    ("cand_desc", C.c_void_p * 2), ("cand_lm", C.c_void_p * 2), ("lm_proj", C.c_void_p * 2), ("lm_is3d", C.c_void_p * 2),
+                    ("m1_dist", C.c_void_p * 2), ("m1_lm", C.c_void_p * 2),
+                    ("k1", C.c_void_p), ("sdist", C.c_void_p), ("hp", C.c_void_p), ("init", C.c_void_p),
+                    ("seconds", C.c_double), ("h2d", C.c_longlong), ("d2h", C.c_longlong), ("nkp", C.c_longlong), ("nm", C.c_longlong)]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    pz = lambda n, dt: torch.zeros(n, dtype=dt).pin_memory()
+    hold = dict(img=[pin(Lh), pin(Rh)], kp=[pz(B * kp_cap * 28, torch.uint8) for _ in range(2)],
+                desc=[pz(B * kp_cap * 64, torch.uint8) for _ in range(2)], n=[pz(B, torch.int32) for _ in range(2)],
+                cand_desc=[pin(m["cand_desc"]) for m in maps], cand_lm=[pin(m["cand_lm"]) for m in maps],
+                lm_proj=[pin(np.broadcast_to(m["lm_proj"], (B,) + m["lm_proj"].shape)) for m in maps],
+                lm_is3d=[pin(m["lm_is3d"]) for m in maps],
+                m1_dist=[pz(B * kp_cap, torch.int32) for _ in range(2)], m1_lm=[pz(B * kp_cap, torch.int32) for _ in range(2)],
+                k1=pz(B * kp_cap, torch.int32), sdist=pz(B * kp_cap, torch.int32), hp=pz(B * kp_cap * 4, torch.float64),
+                init=pz(B * kp_cap, torch.uint8))
+    io = ReplayIO(n_steps=args.steps, warmup=warm, batch=B, ring=ring, W=W, H=H, cap=kp_cap)
+    for k in ("img", "kp", "desc", "n", "cand_desc", "cand_lm", "lm_proj", "lm_is3d", "m1_dist", "m1_lm"):
+        for c in range(2):
+            getattr(io, k)[c] = hold[k][c].data_ptr()
+    for c in range(2):
+        io.n_cand[c] = len(maps[c]["cand_lm"]); io.n_lm[c] = len(maps[c]["lm_is3d"])
+    io.k1, io.sdist, io.hp, io.init = (hold[k].data_ptr() for k in ("k1", "sdist", "hp", "init"))
+    drv.okb_e2e_replay.argtypes = [C.c_void_p, C.c_void_p]
+    barrier()
+    okl.check(drv.okb_e2e_replay(ctx, C.byref(io)))
+    rep_s = io.seconds
+    if world > 1:
+        t = torch.tensor([rep_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); rep_s = float(t.item())
+    e2e = {"value": world * B * args.steps / rep_s, "unit": "stereo frames/s", "h2d_bytes_per_step": int(io.h2d),
+           "d2h_bytes_per_step": int(io.d2h), "ms_per_step": 1e3 * rep_s / args.steps,
+           "step": f"the value leg's step ({B} stereo frames) from page-locked HOST buffers: per camera (one host thread each) "
+                   "okb_detect_describe_batch + okb_match_map3d_batch, then okb_match_stereo_batch; results in host memory",
+           "keypoints_per_frame": io.nkp / (2 * B), "matches_per_stereo_frame": io.nm / B, "streaming": streaming}
+
+    clocks = sampler.stop()
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

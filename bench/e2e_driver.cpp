@@ -6,6 +6,8 @@
 // Only the C ABI of include/okvis_b200.h is used.
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -108,5 +110,84 @@ extern "C" int okb_e2e_run(okb_context_t* ctx, int n_frames, int warmup, int W, 
   w.stop();
   *seconds = std::chrono::duration<double>(t1 - t0).count();
   *h2d_bytes = h2d; *d2h_bytes = d2h; *total_kp = nkp; *total_matches = nm;
+  return rc;
+}
+
+// ---- replay step (the same step as bench.py's device-resident `value` leg, but HOST buffers in and out): a batch of stereo
+// frames per call, one host thread per camera: okb_detect_describe_batch + okb_match_map3d_batch, then
+// okb_match_stereo_batch. All buffers are caller-provided (bench.py allocates them page-locked).
+struct okb_replay_io {
+  int32_t n_steps, warmup, batch, ring, W, H, cap, pad_;
+  const uint8_t* img[2];                                  // ring * batch frames per camera
+  okb_keypoint_t* kp[2]; uint8_t* desc[2]; int32_t* n[2];  // batch x cap
+  int32_t n_cand[2]; int32_t n_lm[2];
+  const uint8_t* cand_desc[2]; const int32_t* cand_lm[2]; const double* lm_proj[2]; const uint8_t* lm_is3d[2];
+  uint32_t* m1_dist[2]; int32_t* m1_lm[2];
+  int32_t* k1; uint32_t* sdist; double* hp; uint8_t* init;
+  double seconds; long long h2d, d2h, nkp, nm;             // results
+};
+
+extern "C" int okb_e2e_replay(okb_context_t* ctx, okb_replay_io* io)
+{
+  const double C0[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, r0[3] = {0, 0, 0}, r1[3] = {0.11, 0, 0};
+  const int B = io->batch, cap = io->cap;
+  const size_t frame = (size_t)io->W * io->H;
+  int rcs[2] = {0, 0};
+  const bool trace = getenv("OKB_E2E_TRACE") != nullptr;
+  double t_det[2] = {0, 0}, t_m1[2] = {0, 0}, t_m4 = 0;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  auto camera = [&](int c, int s) {
+    const uint8_t* imgs = io->img[c] + (size_t)(s % io->ring) * B * frame;
+    const auto ta = now();
+    int rc = okb_detect_describe_batch(ctx, c, B, imgs, (size_t)io->W, io->kp[c], io->desc[c], cap, io->n[c]);
+    const auto tb = now();
+    t_det[c] += ms(ta, tb);
+    if (!rc) rc = okb_match_map3d_batch(ctx, c, B, io->n_cand[c], io->cand_desc[c], io->cand_lm[c], io->n_lm[c], io->lm_proj[c],
+                                        io->lm_is3d[c], 20.0, 60, cap, io->m1_dist[c], io->m1_lm[c]);
+    t_m1[c] += ms(tb, now());
+    rcs[c] = rc;
+  };
+  Worker w; w.start();
+  auto step = [&](int s) -> int {
+    w.submit([&, s] { camera(1, s); });
+    camera(0, s);
+    w.wait();
+    if (rcs[0] || rcs[1]) return rcs[0] ? rcs[0] : rcs[1];
+    const auto ta = now();
+    const int rc4 = okb_match_stereo_batch(ctx, 0, 1, B, C0, r0, C0, r1, 60, cap, io->k1, io->sdist, io->hp, io->init);
+    t_m4 += ms(ta, now());
+    return rc4;
+  };
+  int rc = 0;
+  for (int s = 0; s < io->warmup && !rc; s++) rc = step(s);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int s = 0; s < io->n_steps && !rc; s++) rc = step(io->warmup + s);
+  if (!rc) rc = okb_sync(ctx);
+  const auto t1 = std::chrono::steady_clock::now();
+  w.stop();
+  io->seconds = std::chrono::duration<double>(t1 - t0).count();
+  if (trace) {
+    const int n = io->n_steps + io->warmup;
+    fprintf(stderr, "[okb_e2e_replay] per step (ms): detect %.3f / %.3f  map3d %.3f / %.3f  stereo %.3f\n", t_det[0] / n, t_det[1] / n,
+            t_m1[0] / n, t_m1[1] / n, t_m4 / n);
+  }
+  // bytes per step, counted from the copies the three calls issue (row stride = cap)
+  long long h2d = 0, d2h = 0;
+  for (int c = 0; c < 2; c++) {
+    h2d += (long long)B * frame + (long long)io->n_cand[c] * 68 + (long long)B * io->n_lm[c] * 16 + io->n_lm[c];
+    d2h += (long long)B * cap * (28 + 64 + 25) + 8LL * B + (long long)B * cap * 8;
+  }
+  d2h += (long long)B * cap * 41;
+  io->h2d = h2d; io->d2h = d2h;
+  long long nkp = 0, nm = 0;   // of the last step (sanity numbers for the bench line)
+  for (int c = 0; c < 2; c++)
+    for (int b = 0; b < B; b++) {
+      nkp += io->n[c][b];
+      for (int k = 0; k < io->n[c][b]; k++) nm += io->m1_lm[c][(size_t)b * cap + k] >= 0;
+    }
+  for (int b = 0; b < B; b++)
+    for (int k = 0; k < io->n[0][b]; k++) nm += io->k1[(size_t)b * cap + k] >= 0;
+  io->nkp = nkp; io->nm = nm;
   return rc;
 }

@@ -199,6 +199,25 @@ int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand
                            double reprojection_threshold, uint32_t match_threshold, uint32_t* d_out_dist,
                            int32_t* d_out_lm);
 
+/* Host-buffer, batched M1 (replay use; benchmark "e2e" leg): same queries as okb_match_map3d_device -- the features
+ * the last okb_detect_describe[_batch] call of camera `cam` left on the device -- matched against a landmark pool given in
+ * HOST memory (Frontend.cpp:1515-1590; pool layout Frontend.cpp:1221-1223,1259,1267). lm_proj: n_frames x n_lm x 2
+ * doubles (one projection table per frame). out_*: n_frames x cap entries in host memory; rows k >= n_out[b] of frame b
+ * are unspecified. Page-locked caller buffers are read / written by the copy engines directly, pageable ones go through
+ * the library's pinned staging. Synchronous (returns when the outputs are in place). */
+int okb_match_map3d_batch(okb_context_t* ctx, int cam, int n_frames, int n_cand, const uint8_t* cand_desc,
+                          const int32_t* cand_lm, int n_lm, const double* lm_proj, const uint8_t* lm_is3d,
+                          double reprojection_threshold, uint32_t match_threshold, int cap, uint32_t* out_dist,
+                          int32_t* out_lm);
+
+/* Host-buffer, batched M4 (Frontend.cpp:2016-2074): okb_match_stereo_device with the outputs delivered to HOST memory
+ * (n_frames x cap entries each; out_hp_W n_frames x cap x 4 doubles). Queries = camera cam0, candidates = camera cam1,
+ * both as left on the device by the last okb_detect_describe[_batch]; camera models from okb_set_camera_model.
+ * Synchronous. */
+int okb_match_stereo_batch(okb_context_t* ctx, int cam0, int cam1, int n_frames, const double C_WC0[9], const double r_WC0[3],
+                           const double C_WC1[9], const double r_WC1[3], uint32_t match_threshold, int cap, int32_t* out_k1,
+                           uint32_t* out_dist, double* out_hp_W, uint8_t* out_initialisable);
+
 /* Device-resident, batched M4 for the benchmark "value" leg and the camera-sharded multi-GPU mode: stereo-matches the
  * features of camera cam0 (queries) against camera cam1 left on the device by okb_detect_describe_batch_device, frame by
  * frame. Back-projection (D4, camera models from okb_set_camera_model), e_W = (C_WC * e_C).normalized(), size/f and the

@@ -130,18 +130,33 @@ int okb_detect_describe_batch(okb_context_t* ctx, int cam, int n_frames, const u
   }
   OKB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ws.stream;
-  // host -> pinned -> device (the caller's buffer is pageable cv::Mat memory)
-  for (int b = 0; b < n_frames; b++)
-    for (int y = 0; y < H; y++) memcpy(ws.h_img + ((size_t)b * H + y) * W, images + ((size_t)b * H + y) * stride_bytes, (size_t)W);
   static_assert(sizeof(okb_keypoint_t) == 28, "cv::KeyPoint layout");
-  OKB_CUDA(cudaMemcpyAsync(ws.d_in, ws.h_img, (size_t)W * H * n_frames, cudaMemcpyHostToDevice, st));
+  // host -> device: pageable caller memory (cv::Mat) is staged through the pinned buffer; page-locked caller memory
+  // (cudaHostAlloc / cudaHostRegister) is read by the copy engine directly
+  const bool in_pinned = host_pinned(images);
+  if (in_pinned && stride_bytes == (size_t)W) {
+    OKB_CUDA(cudaMemcpyAsync(ws.d_in, images, (size_t)W * H * n_frames, cudaMemcpyHostToDevice, st));
+  } else if (in_pinned) {   // row-by-row DMA: correct for padded images, much slower than the dense copy
+    OKB_CUDA(cudaMemcpy2DAsync(ws.d_in, (size_t)W, images, stride_bytes, (size_t)W, (size_t)H * n_frames, cudaMemcpyHostToDevice, st));
+  } else {
+    for (int b = 0; b < n_frames; b++)
+      for (int y = 0; y < H; y++) memcpy(ws.h_img + ((size_t)b * H + y) * W, images + ((size_t)b * H + y) * stride_bytes, (size_t)W);
+    OKB_CUDA(cudaMemcpyAsync(ws.d_in, ws.h_img, (size_t)W * H * n_frames, cudaMemcpyHostToDevice, st));
+  }
   rc = detect_run_device(ctx, cam, n_frames, ws.d_in, W);
   if (rc) return rc;
   OKB_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, 4 * n_frames, cudaMemcpyDeviceToHost, st));
   OKB_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, 4 * n_frames, cudaMemcpyDeviceToHost, st));
-  // keypoint / descriptor payload: copy the capacity-bounded blocks, then trim on the host
+  // keypoint / descriptor payload: capacity-bounded blocks. Page-locked caller buffers receive them directly (rows
+  // k >= n_out[b] are then unspecified); otherwise they land in the pinned staging and are trimmed on the host.
   const int rows = cap < ws.kp_cap ? cap : ws.kp_cap;
-  if (n_frames == 1) {
+  const bool out_pinned = rows > 0 && host_pinned(kp_out) && host_pinned(desc_out);
+  if (out_pinned) {
+    OKB_CUDA(cudaMemcpy2DAsync(kp_out, (size_t)cap * sizeof(okb_keypoint_t), ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t),
+                               (size_t)rows * sizeof(okb_keypoint_t), n_frames, cudaMemcpyDeviceToHost, st));
+    OKB_CUDA(cudaMemcpy2DAsync(desc_out, (size_t)cap * 64, ws.d_desc, (size_t)ws.kp_cap * 64, (size_t)rows * 64, n_frames,
+                               cudaMemcpyDeviceToHost, st));
+  } else if (n_frames == 1) {
     OKB_CUDA(cudaMemcpyAsync(ws.h_kp, ws.d_kp, (size_t)rows * sizeof(okb_keypoint_t), cudaMemcpyDeviceToHost, st));
     OKB_CUDA(cudaMemcpyAsync(ws.h_desc, ws.d_desc, (size_t)rows * 64, cudaMemcpyDeviceToHost, st));
   } else {
@@ -162,6 +177,7 @@ int okb_detect_describe_batch(okb_context_t* ctx, int cam, int n_frames, const u
     int n = ws.h_count[b];
     if (n > cap) { set_error("okb_detect_describe: %d keypoints do not fit the caller's capacity %d", n, cap); return OKB_ERR_CAPACITY; }
     n_out[b] = n;
+    if (out_pinned) continue;
     memcpy(kp_out + (size_t)b * cap, ws.h_kp + (size_t)b * ws.kp_cap, (size_t)n * sizeof(okb_keypoint_t));
     memcpy(desc_out + (size_t)b * cap * 64, ws.h_desc + (size_t)b * ws.kp_cap * 64, (size_t)n * 64);
   }

@@ -92,6 +92,8 @@ struct CamWorkspace {
   CUtensorMap tma[kMaxLayers]; int tma_use[kMaxLayers] = {0}; int tma_ready = 0;
   long long* d_dbg = nullptr;   // per-frame cycle stamps of the single-CTA kernels (okb_debug_stamps)
   int32_t* d_m1_cell_off = nullptr; int32_t* d_m1_cell_list = nullptr; unsigned long long* d_m1_best = nullptr;
+  // staging of the host-buffer batch matchers (okb_match_map3d_batch / okb_match_stereo_batch), grown on demand
+  uint8_t* m_d = nullptr; uint8_t* m_h = nullptr; size_t m_cap = 0;
   // pinned staging
   uint8_t* h_img = nullptr;
   okb_keypoint_t* h_kp = nullptr;
@@ -149,6 +151,13 @@ int camera_stereo_prep(okb_context* ctx, const okb_camera_model_t& model, const 
                        const int32_t* d_count, int cap, int n_frames, double* d_rays, uint8_t* d_valid, double* d_eW, double* d_sof,
                        double* d_c26, double* d_c6, cudaStream_t st);
 MatchWorkspace& match_ws(okb_context* ctx);   // the calling thread's slot
+// true when `p` is page-locked host memory the copy engines can address (cudaHostAlloc / cudaHostRegister)
+inline bool host_pinned(const void* p)
+{
+  cudaPointerAttributes at;
+  if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
 int tables_init(okb_context* ctx, float pattern_scale);
 void tables_free(okb_context* ctx);
 }  // namespace okb

@@ -838,6 +838,113 @@ int okb_match_stereo_device(okb_context_t* ctx, int cam0, int cam1, int n_frames
   return OKB_OK;
 }
 
+// ---- host-buffer batch forms: the queries are the features the last okb_detect_describe[_batch] of the camera left on the
+// device, everything else comes from / goes to caller memory (page-locked buffers are used by the copy engines directly)
+namespace {
+struct CamStage {
+  CamWorkspace& ws; cudaStream_t st; size_t off = 0;
+  int reserve(size_t bytes)
+  {
+    if (bytes <= ws.m_cap) return OKB_OK;
+    OKB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(ws.m_d); if (ws.m_h) cudaFreeHost(ws.m_h);
+    ws.m_d = ws.m_h = nullptr; ws.m_cap = 0;
+    const size_t cap = bytes + bytes / 4 + (1 << 16);
+    OKB_CUDA(cudaMalloc(&ws.m_d, cap));
+    OKB_CUDA(cudaMallocHost(&ws.m_h, cap));
+    ws.m_cap = cap;
+    return OKB_OK;
+  }
+  size_t take(size_t bytes) { off = (off + 255) & ~(size_t)255; const size_t o = off; off += bytes; return o; }
+  int upload(size_t o, const void* src, size_t bytes)
+  {
+    if (!bytes) return OKB_OK;
+    if (host_pinned(src)) { OKB_CUDA(cudaMemcpyAsync(ws.m_d + o, src, bytes, cudaMemcpyHostToDevice, st)); return OKB_OK; }
+    memcpy(ws.m_h + o, src, bytes);
+    OKB_CUDA(cudaMemcpyAsync(ws.m_d + o, ws.m_h + o, bytes, cudaMemcpyHostToDevice, st));
+    return OKB_OK;
+  }
+  // rows of `row_bytes` (device stride src_rows * elem) into the caller's [n_frames][cap] array
+  int download(size_t o, void* dst, size_t elem, int rows, int src_rows, int cap, int n_frames, bool* staged)
+  {
+    *staged = !host_pinned(dst);
+    if (!*staged) {
+      OKB_CUDA(cudaMemcpy2DAsync(dst, (size_t)cap * elem, ws.m_d + o, (size_t)src_rows * elem, (size_t)rows * elem, n_frames, cudaMemcpyDeviceToHost, st));
+    } else {
+      OKB_CUDA(cudaMemcpyAsync(ws.m_h + o, ws.m_d + o, (size_t)src_rows * elem * n_frames, cudaMemcpyDeviceToHost, st));
+    }
+    return OKB_OK;
+  }
+  void unstage(size_t o, void* dst, size_t elem, int rows, int src_rows, int cap, int n_frames)
+  {
+    for (int b = 0; b < n_frames; b++)
+      memcpy((uint8_t*)dst + (size_t)b * cap * elem, ws.m_h + o + (size_t)b * src_rows * elem, (size_t)rows * elem);
+  }
+};
+}  // namespace
+
+int okb_match_map3d_batch(okb_context_t* ctx, int cam, int n_frames, int n_cand, const uint8_t* cand_desc, const int32_t* cand_lm,
+                          int n_lm, const double* lm_proj, const uint8_t* lm_is3d, double reprojection_threshold,
+                          uint32_t match_threshold, int cap, uint32_t* out_dist, int32_t* out_lm)
+{
+  OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams && n_cand >= 0 && n_lm >= 0 && cap > 0 && out_dist && out_lm, "okb_match_map3d_batch");
+  CamWorkspace& ws = ctx->cams[cam];
+  OKB_CHECK_ARGS(n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_map3d_batch");
+  OKB_CHECK_ARGS(n_cand == 0 || (cand_desc && cand_lm && lm_proj && lm_is3d), "okb_match_map3d_batch");
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  CamStage S{ws, ws.stream};
+  const size_t o_desc = S.take((size_t)n_cand * 64), o_lm = S.take((size_t)n_cand * 4);
+  const size_t o_proj = S.take((size_t)n_frames * n_lm * 16), o_3d = S.take((size_t)n_lm);
+  const size_t o_dist = S.take((size_t)n_frames * ws.kp_cap * 4), o_idx = S.take((size_t)n_frames * ws.kp_cap * 4);
+  int rc = S.reserve(S.off);
+  if (rc) return rc;
+  if ((rc = S.upload(o_desc, cand_desc, (size_t)n_cand * 64)) || (rc = S.upload(o_lm, cand_lm, (size_t)n_cand * 4)) ||
+      (rc = S.upload(o_proj, lm_proj, (size_t)n_frames * n_lm * 16)) || (rc = S.upload(o_3d, lm_is3d, (size_t)n_lm)))
+    return rc;
+  rc = okb_match_map3d_device(ctx, cam, n_frames, n_cand, ws.m_d + o_desc, (const int32_t*)(ws.m_d + o_lm), n_lm,
+                              (const double*)(ws.m_d + o_proj), ws.m_d + o_3d, reprojection_threshold, match_threshold,
+                              (uint32_t*)(ws.m_d + o_dist), (int32_t*)(ws.m_d + o_idx));
+  if (rc) return rc;
+  const int rows = cap < ws.kp_cap ? cap : ws.kp_cap;
+  bool s0, s1;
+  if ((rc = S.download(o_dist, out_dist, 4, rows, ws.kp_cap, cap, n_frames, &s0)) || (rc = S.download(o_idx, out_lm, 4, rows, ws.kp_cap, cap, n_frames, &s1)))
+    return rc;
+  OKB_CUDA(cudaStreamSynchronize(ws.stream));
+  if (s0) S.unstage(o_dist, out_dist, 4, rows, ws.kp_cap, cap, n_frames);
+  if (s1) S.unstage(o_idx, out_lm, 4, rows, ws.kp_cap, cap, n_frames);
+  return OKB_OK;
+}
+
+int okb_match_stereo_batch(okb_context_t* ctx, int cam0, int cam1, int n_frames, const double C_WC0[9], const double r_WC0[3],
+                           const double C_WC1[9], const double r_WC1[3], uint32_t match_threshold, int cap, int32_t* out_k1,
+                           uint32_t* out_dist, double* out_hp_W, uint8_t* out_initialisable)
+{
+  OKB_CHECK_ARGS(ctx && cam0 >= 0 && cam0 < ctx->n_cams && cap > 0 && out_k1 && out_dist && out_hp_W && out_initialisable, "okb_match_stereo_batch");
+  CamWorkspace& ws = ctx->cams[cam0];
+  OKB_CHECK_ARGS(n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_stereo_batch");
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  CamStage S{ws, ws.stream};
+  const size_t n = (size_t)n_frames * ws.kp_cap;
+  const size_t o_k1 = S.take(n * 4), o_dist = S.take(n * 4), o_hp = S.take(n * 32), o_init = S.take(n);
+  int rc = S.reserve(S.off);
+  if (rc) return rc;
+  rc = okb_match_stereo_device(ctx, cam0, cam1, n_frames, C_WC0, r_WC0, C_WC1, r_WC1, match_threshold, (int32_t*)(ws.m_d + o_k1),
+                               (uint32_t*)(ws.m_d + o_dist), (double*)(ws.m_d + o_hp), ws.m_d + o_init);
+  if (rc) return rc;
+  const int rows = cap < ws.kp_cap ? cap : ws.kp_cap;
+  bool s[4];
+  if ((rc = S.download(o_k1, out_k1, 4, rows, ws.kp_cap, cap, n_frames, &s[0])) || (rc = S.download(o_dist, out_dist, 4, rows, ws.kp_cap, cap, n_frames, &s[1])) ||
+      (rc = S.download(o_hp, out_hp_W, 32, rows, ws.kp_cap, cap, n_frames, &s[2])) ||
+      (rc = S.download(o_init, out_initialisable, 1, rows, ws.kp_cap, cap, n_frames, &s[3])))
+    return rc;
+  OKB_CUDA(cudaStreamSynchronize(ws.stream));
+  if (s[0]) S.unstage(o_k1, out_k1, 4, rows, ws.kp_cap, cap, n_frames);
+  if (s[1]) S.unstage(o_dist, out_dist, 4, rows, ws.kp_cap, cap, n_frames);
+  if (s[2]) S.unstage(o_hp, out_hp_W, 32, rows, ws.kp_cap, cap, n_frames);
+  if (s[3]) S.unstage(o_init, out_initialisable, 1, rows, ws.kp_cap, cap, n_frames);
+  return OKB_OK;
+}
+
 int okb_match_place(okb_context_t* ctx, int D, int n_lm, const int32_t* lm_offsets, const uint8_t* lm_desc, int n_kp,
                     const uint8_t* kp_desc, uint32_t match_threshold, int32_t* out_k, uint32_t* out_dist)
 {

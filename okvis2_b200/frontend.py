@@ -291,6 +291,33 @@ class Frontend:
         return self._stereo("stereo", desc0, valid0, e0_W, size_over_f0, desc1, valid1, e1_W, size_over_f1, r_WC0, r_WC1,
                             T_CW0, T_CW1)
 
+    def matchToMapBatch(self, cameraIndex, n_frames, cand_desc, cand_lm, lm_proj, lm_is3d, use_imu=True, out=None):
+        """Frontend::matchToMapByThread for every frame of the last detectAndDescribeBatch of `cameraIndex` (the queries
+        stay on the device); lm_proj is n_frames x n_lm x 2. `out` = (dist, lm) arrays to fill (e.g. page-locked)."""
+        cap = self._capacity(cameraIndex)
+        cand_desc = np.ascontiguousarray(cand_desc, np.uint8); cand_lm = np.ascontiguousarray(cand_lm, np.int32)
+        lm_proj = np.ascontiguousarray(lm_proj, np.float64); lm_is3d = np.ascontiguousarray(lm_is3d, np.uint8)
+        assert lm_proj.shape == (n_frames, len(lm_is3d), 2)
+        dist, lm = out if out is not None else (np.zeros((n_frames, cap), np.uint32), np.zeros((n_frames, cap), np.int32))
+        with self._locks[cameraIndex]:
+            check(_l.lib().okb_match_map3d_batch(self._ctx, cameraIndex, n_frames, len(cand_desc), ptr(cand_desc), ptr(cand_lm),
+                                                 len(lm_is3d), ptr(lm_proj), ptr(lm_is3d), 20.0 if use_imu else 150.0,
+                                                 int(self.briskMatchingThreshold_), dist.shape[1], ptr(dist), ptr(lm)))
+        return dist, lm
+
+    def matchStereoBatch(self, cam0, cam1, n_frames, C_WC0, r_WC0, C_WC1, r_WC1, out=None):
+        """Frontend::matchStereo k0/k1 loops for every frame of the last detectAndDescribeBatch of the two cameras."""
+        cap = self._capacity(cam0)
+        a = lambda x: np.ascontiguousarray(x, np.float64)
+        C0, r0, C1, r1 = a(C_WC0), a(r_WC0), a(C_WC1), a(r_WC1)
+        if out is None:
+            out = (np.zeros((n_frames, cap), np.int32), np.zeros((n_frames, cap), np.uint32),
+                   np.zeros((n_frames, cap, 4), np.float64), np.zeros((n_frames, cap), np.uint8))
+        k1, dist, hp, init = out
+        check(_l.lib().okb_match_stereo_batch(self._ctx, cam0, cam1, n_frames, ptr(C0), ptr(r0), ptr(C1), ptr(r1),
+                                              int(self.briskMatchingThreshold_), k1.shape[1], ptr(k1), ptr(dist), ptr(hp), ptr(init)))
+        return k1, dist, hp, init
+
     def verifyRecognisedPlaceMatch(self, lm_offsets, lm_desc, kp_desc):
         """Descriptor matching loop of Frontend::verifyRecognisedPlace (Frontend.cpp:329-355)."""
         lm_offsets = np.ascontiguousarray(lm_offsets, np.int32); lm_desc = np.ascontiguousarray(lm_desc, np.uint8)

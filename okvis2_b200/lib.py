@@ -88,6 +88,8 @@ _PROTOS = {
     "okb_match_stereo_device": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
     "okb_match_stereo_device_ptr": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]),
     "okb_match_map3d_device": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, vp, vp]),
+    "okb_match_map3d_batch": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, i32, vp, vp]),
+    "okb_match_stereo_batch": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, i32, vp, vp, vp, vp]),
 }
 
 

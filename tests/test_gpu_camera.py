@@ -114,3 +114,71 @@ def test_device_resident_stereo_pipeline_equals_oracle():
         total += (ref[0] >= 0).sum()
     assert total > 5
     fe.close()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_buffer_batch_pipeline_equals_oracle(pinned):
+    """Replay step through HOST buffers: okb_detect_describe_batch -> okb_match_map3d_batch -> okb_match_stereo_batch,
+    with pageable and with page-locked caller memory (the latter is copied by the DMA engines directly)."""
+    import torch
+    from okvis2_b200.synth import map_scene
+    B = 3
+    fe = Frontend(2, 752, 480, max_batch=B)
+    fe.configure(threshold=30, octaves=3, max_keypoints=1000)
+    for c in range(2):
+        fe.setCameraModel(c, **EUROC[c])
+    L_ = okl.lib()
+    cap = fe._capacity(0) + 24      # caller capacity differs from the device row stride on purpose
+
+    def buf(shape, dtype):
+        if not pinned:
+            return np.zeros(shape, dtype)
+        t = torch.zeros(int(np.prod(shape)) * np.dtype(dtype).itemsize, dtype=torch.uint8).pin_memory()
+        return t.numpy().view(dtype).reshape(shape)
+
+    imgs = []
+    for c in range(2):
+        a = buf((B, 480, 752), np.uint8)
+        for t in range(B):
+            a[t] = synth_stereo(900 + t, 752, 480)[c]
+        imgs.append(a)
+    kps, descs, ns = [], [], []
+    for c in range(2):
+        kp = buf((B, cap), okl.KP_DTYPE); d = buf((B, cap, 64), np.uint8); n = np.zeros(B, np.int32)
+        okl.check(L_.okb_detect_describe_batch(fe.ctx, c, B, imgs[c].ctypes.data, 752, kp.ctypes.data, d.ctypes.data, cap, n.ctypes.data))
+        kps.append(kp); descs.append(d); ns.append(n)
+    feats = [[oracle.Brisk(30, 3).detect_and_compute(imgs[c][b], 1000) for b in range(B)] for c in range(2)]
+    for c in range(2):
+        for b in range(B):
+            rk, rd = feats[c][b]
+            assert ns[c][b] == len(rk) and kps[c][b, :len(rk)].tobytes() == rk.tobytes() and np.array_equal(descs[c][b, :len(rk)], rd)
+    # M1: one landmark pool, one projection table per frame (shifted a little from frame to frame)
+    rk, rd = feats[0][0]
+    m = map_scene(5, np.stack([rk["x"], rk["y"]], 1).astype(np.float64), rd, 2000, W=752, H=480)
+    proj = buf((B,) + m["lm_proj"].shape, np.float64)
+    for b in range(B):
+        proj[b] = m["lm_proj"] + 1.5 * b
+    dist = buf((B, cap), np.uint32); lm = buf((B, cap), np.int32)
+    fe.matchToMapBatch(0, B, m["cand_desc"], m["cand_lm"], proj, m["lm_is3d"], out=(dist, lm))
+    hits = 0
+    for b in range(B):
+        rk, rd = feats[0][b]
+        ref = oracle.match_map3d(rd, np.stack([rk["x"], rk["y"]], 1).astype(np.float64), None, m["cand_desc"], m["cand_lm"], proj[b],
+                                 m["lm_is3d"], 20.0, 60)
+        assert np.array_equal(dist[b, :len(rk)], ref[0]) and np.array_equal(lm[b, :len(rk)], ref[1])
+        hits += (ref[1] >= 0).sum()
+    assert hits > 50
+    # M4
+    C0 = np.eye(3); r0 = np.zeros(3); C1 = np.eye(3); r1 = np.array([0.11, 0.0, 0.0])
+    out = (buf((B, cap), np.int32), buf((B, cap), np.uint32), buf((B, cap, 4), np.float64), buf((B, cap), np.uint8))
+    k1, sdist, hp, init = fe.matchStereoBatch(0, 1, B, C0, r0, C1, r1, out=out)
+    for b in range(B):
+        (kp0, d0), (kp1, d1) = feats[0][b], feats[1][b]
+        rays0, v0 = oracle_bp(EUROC[0], kp0); rays1, v1 = oracle_bp(EUROC[1], kp1)
+        f0 = 0.5 * sum(EUROC[0]["focal_length"]); f1 = 0.5 * sum(EUROC[1]["focal_length"])
+        ref = oracle.match_stereo(d0, v0, world_rays(C0, rays0), kp0["size"].astype(np.float64) / f0, d1, v1, world_rays(C1, rays1),
+                                  kp1["size"].astype(np.float64) / f1, r0, r1, T_CW(C0, r0), T_CW(C1, r1), 60)
+        n0 = len(kp0)
+        assert np.array_equal(k1[b, :n0], ref[0]) and np.array_equal(sdist[b, :n0], ref[1])
+        assert np.array_equal(hp[b, :n0].view(np.uint64), ref[2].view(np.uint64)) and np.array_equal(init[b, :n0], ref[3])
+    fe.close()
