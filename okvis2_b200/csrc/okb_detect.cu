@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ ResizeJo
 
 // ---------------------------------------------------------------------------------------------------------------
 // score map tiling
-constexpr int kTileW = 56, kTileH = 30;   // (30 + 2) rows x (56 / 4 + 2) groups = 512 score items = 2 per thread
+constexpr int kTileW = 64, kTileH = 32;   // one warp per tile row, one lane per horizontal pixel pair
 
 // per-layer regions of the candidate list (so that a warp of the refinement kernel sees candidates of ONE layer and
 // follows one code path); cand_count is [frames][kMaxLayers]
@@ -196,19 +196,28 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
-// Fused score + non-max suppression. Tile = kTileW x kTileH pixels of one layer of one frame, 256 threads.
-//   1. the image tile with a 4-pixel halo (3 for the ring + 1 because candidates need their neighbours' scores) is
-//      staged in shared memory as 32-bit words, zero outside the image;
-//   2. dense scores b0 for the tile + 1-pixel halo ((kTileH+2) rows x (kTileW/4+2) groups of 4 pixels = 512 items, two per
-//      thread) by 16x2 SIMD min/max, written to a
-//      shared score tile and (inner part) to the global score map;
-//   3. 3x3 non-max test (>= all neighbours, tie flag) on the inner pixels from shared memory, warp-ballot compaction of
-//      the candidates into the per-frame list: one u32 per candidate = time key | tie << 31.
-constexpr int kImgW = kTileW + 16;   // bytes per staged image row: x0-8 .. x0+71
-constexpr int kImgH = kTileH + 8;    // rows y0-4 .. y0+35
-constexpr int kScW = kTileW + 8;     // score tile row: x0-4 .. x0+67
-constexpr int kScH = kTileH + 2;     // rows y0-1 .. y0+32
+// Fused score + non-max suppression. Tile = kTileW x kTileH (64 x 32) pixels of one layer of one frame, 256 threads.
+//   1. the image tile with its ring halo (3 rows above/below, 16 bytes left/right: TMA wants 16-byte granular boxes
+//      AND box origins) arrives in shared memory by ONE TMA bulk tensor copy, zero outside the image;
+//   2. the bytes are expanded once into two 16x2 planes, E[r][k] = (p[2k], p[2k+1]) and O[r][k] = (p[2k+1], p[2k+2]):
+//      every ring sample of a horizontal pixel PAIR is then a single conflict-free LDS.32 (E for even dx, O for odd dx)
+//      and the main loop is nothing but the 81 VIMNMX3.U16x2 of b0_pair (the ALU pipe is this kernel's limiter);
+//   3. a warp owns a tile row per iteration (lane = pixel pair): dense scores b0 go to the global score map (64
+//      contiguous bytes per warp) and to a shared score tile; pixels with score >= threshold ("strong", a few per
+//      cent) are appended to a shared list;
+//   4. the strong pixels get the 3x3 non-max test from the shared score tile. A strong pixel ON the tile border whose
+//      in-tile neighbours do not already beat it is emitted with the PENDING flag (bit 30): its out-of-tile neighbours
+//      are scores of another CTA, so k_refine finishes the test from the global map (complete by then). There is no
+//      score halo, i.e. no pixel is scored twice.
+//   Candidate word: time key | tie << 31 | pending << 30; the tile's candidates are appended with one atomicAdd.
+constexpr int kHaloX = 16;           // measured on B200: the innermost TMA coordinate must be a multiple of 16 bytes
+                                     // (bench/tma_probe.cu: x = -8, 8, 376 raise "illegal instruction", -16, 0, 384 work)
+constexpr int kImgW = kTileW + 2 * kHaloX;   // bytes per staged image row: x0-16 .. x0+79
+constexpr int kImgH = kTileH + 6;    // rows y0-3 .. y0+34
+constexpr int kExp0 = 3, kExp1 = 21; // staged words (4 bytes) that are expanded: bytes 12 .. 83 cover x0-4 .. x0+67
+constexpr int kPlaneW = 2 * (kExp1 - kExp0);   // 16x2 words per plane row; plane word j holds staged bytes 2j+12 (E) / 2j+13 (O)
 constexpr int kScoreThreads = 256;
+constexpr uint32_t kCandTie = 0x80000000u, kCandPending = 0x40000000u, kCandKeyMask = 0x3fffffffu;
 
 __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_constant__ TmaMaps maps, const __grid_constant__ DeviceLayers dl,
                                                              const __grid_constant__ TileMap tm,
@@ -218,8 +227,13 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
                                                              int threshold, int32_t* status)
 {
   __shared__ __align__(128) uint8_t tile[kImgH][kImgW];
+  __shared__ __align__(16) uint32_t pe[kImgH][kPlaneW];
+  __shared__ __align__(16) uint32_t po[kImgH][kPlaneW];
+  __shared__ __align__(16) uint8_t sc[kTileH][kTileW];
+  __shared__ uint16_t strong[kTileH * kTileW];
+  __shared__ uint32_t out_list[kTileH * kTileW];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ __align__(16) uint8_t sc[kScH][kScW];
+  __shared__ int n_strong, n_out, out_base;
   const int frame = blockIdx.y;
   const int layer = find_layer(tm, blockIdx.x);
   const int t = blockIdx.x - tm.tile_prefix[layer];
@@ -230,13 +244,14 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
   else { img = img_block + (size_t)frame * dl.frame_stride + d.offset; pitch = d.pitch; }
   uint8_t* score = score_block + (size_t)frame * dl.frame_stride + d.offset;
   const int x0 = tx * kTileW, y0 = ty * kTileH;
+  if (threadIdx.x == 0) { n_strong = 0; n_out = 0; }
   if (maps.use[layer]) {
     // TMA: one bulk tensor copy per CTA; out-of-image bytes arrive as zeros
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
       mbar_expect_tx(&bar, kImgH * kImgW);
-      tma_load_3d(&tile[0][0], &maps.m[layer], &bar, x0 - 8, y0 - 4, frame);
+      tma_load_3d(&tile[0][0], &maps.m[layer], &bar, x0 - kHaloX, y0 - 3, frame);
     }
     const long long t_start = clock64();
     while (!mbar_try_wait(&bar, 0)) {
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
     const bool word_ok = ((pitch & 3) == 0) && ((((uintptr_t)img) & 3) == 0);
     for (int i = threadIdx.x; i < kImgH * (kImgW / 4); i += kScoreThreads) {
       const int r = i / (kImgW / 4), c = i % (kImgW / 4);
-      const int y = y0 - 4 + r, x = x0 - 8 + c * 4;
+      const int y = y0 - 3 + r, x = x0 - kHaloX + c * 4;
       uint32_t w = 0;
       if (y >= 0 && y < d.h) {
         const uint8_t* row = img + (size_t)y * pitch;
@@ -263,83 +278,80 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
     }
     __syncthreads();
   }
-#pragma unroll 1
-  for (int item = threadIdx.x; item < kScH * (kScW / 4); item += kScoreThreads) {
-    const int rr = item / (kScW / 4), g = item % (kScW / 4);
-    const int y = y0 - 1 + rr, x = x0 - 4 + 4 * g;
-    uint32_t out = 0;
-    if (y >= 3 && y < d.h - 3 && x + 3 >= 3 && x < d.w - 3) {   // warp-divergent only at the image border
-      uint32_t lo[16], hi[16];
-      uint32_t W[7][3];
-#pragma unroll
-      for (int r = 0; r < 7; r++) {
-        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(&tile[rr + r][4 * g]);
-        W[r][0] = rowp[0]; W[r][1] = rowp[1]; W[r][2] = rowp[2];
-      }
-#define OKB_RING(i, dx, dy)                                                                                            \
-      {                                                                                                                \
-        const uint32_t w = (dx) < 0 ? __funnelshift_r(W[(dy) + 3][0], W[(dy) + 3][1], 8 * (4 + (dx)))                  \
-                                    : ((dx) > 0 ? __funnelshift_r(W[(dy) + 3][1], W[(dy) + 3][2], 8 * (dx)) : W[(dy) + 3][1]); \
-        lo[i] = u16x2_lo(w); hi[i] = u16x2_hi(w);                                                                      \
-      }
-      OKB_RING(0, -3, 0) OKB_RING(1, -3, -1) OKB_RING(2, -2, -2) OKB_RING(3, -1, -3) OKB_RING(4, 0, -3) OKB_RING(5, 1, -3)
-      OKB_RING(6, 2, -2) OKB_RING(7, 3, -1) OKB_RING(8, 3, 0) OKB_RING(9, 3, 1) OKB_RING(10, 2, 2) OKB_RING(11, 1, 3)
-      OKB_RING(12, 0, 3) OKB_RING(13, -1, 3) OKB_RING(14, -2, 2) OKB_RING(15, -3, 1)
-#undef OKB_RING
-      const uint32_t c = W[3][1];
-      out = __byte_perm(b0_pair(lo, u16x2_lo(c)), b0_pair(hi, u16x2_hi(c)), 0x6420);
-      uint32_t mask = 0;
-#pragma unroll
-      for (int px = 0; px < 4; px++) if (x + px >= 3 && x + px < d.w - 3) mask |= 0xffu << (8 * px);
-      out &= mask;
-    }
-    *reinterpret_cast<uint32_t*>(&sc[rr][4 * g]) = out;
-    if (rr >= 1 && rr <= kTileH && g >= 1 && g <= kTileW / 4 && y < d.h && x < d.pitch)
-      *reinterpret_cast<uint32_t*>(score + (size_t)y * d.pitch + x) = out;   // pitch is a multiple of 64
+  // ---- expansion into the two 16x2 planes
+  for (int i = threadIdx.x; i < kImgH * (kExp1 - kExp0); i += kScoreThreads) {
+    const int r = i / (kExp1 - kExp0), m = i % (kExp1 - kExp0);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&tile[r][4 * (m + kExp0)]);
+    const uint32_t nx = *reinterpret_cast<const uint32_t*>(&tile[r][4 * (m + kExp0) + 4]);
+    uint2 e, o;
+    e.x = __byte_perm(w, 0, 0x4140); e.y = __byte_perm(w, 0, 0x4342);
+    o.x = __byte_perm(w, 0, 0x4241); o.y = __byte_perm(w, nx, 0x7473) & 0x00ff00ffu;   // (b3, nx.b0)
+    *reinterpret_cast<uint2*>(&pe[r][2 * m]) = e;
+    *reinterpret_cast<uint2*>(&po[r][2 * m]) = o;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  constexpr int kWords = kTileH * (kTileW / 4);                              // inner words of the tile
-  constexpr int kWordsPadded = (kWords + kScoreThreads - 1) / kScoreThreads * kScoreThreads;
+  // ---- dense scores: warp = tile row, lane = pixel pair (x0 + 2*lane, +1)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool edge_tile = x0 < 3 || y0 < 3 || x0 + kTileW > d.w - 3 || y0 + kTileH > d.h - 3;
+  const uint32_t thr2 = (uint32_t)(0x8000 - min(max(threshold, 1), 0x7fff)) * 0x00010001u;
 #pragma unroll 1
-  for (int wi = threadIdx.x; wi < kWordsPadded; wi += kScoreThreads) {        // whole warps iterate together (ballots below)
-    const bool in = wi < kWords;
-    const int r = in ? wi / (kTileW / 4) : 0, g = in ? wi % (kTileW / 4) : 0;  // inner word (row r, pixels 4g..4g+3)
-    const int y = y0 + r, xb = x0 + 4 * g;
-    const uint32_t w = in ? *reinterpret_cast<const uint32_t*>(&sc[r + 1][4 * g + 4]) : 0u;
-    const bool any_corner = ((w & 255u) >= (unsigned)threshold) | (((w >> 8) & 255u) >= (unsigned)threshold) |
-                            (((w >> 16) & 255u) >= (unsigned)threshold) | ((w >> 24) >= (unsigned)threshold);
-    if (!__any_sync(0xffffffffu, any_corner)) continue;
-    for (int px = 0; px < 4; px++) {
-      const int c = (w >> (8 * px)) & 255;
-      bool is_c = false, tie = false;
-      if (c >= threshold) {   // scores are zero in the margin and outside the image
-        const uint8_t* s = &sc[r + 1][4 * g + 4 + px];
-        is_c = true;
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-          for (int dx = -1; dx <= 1; dx++) {
-            if (dx == 0 && dy == 0) continue;
-            const int v = s[dy * kScW + dx];
-            if (v > c) is_c = false;
-            if (v == c) tie = true;
-          }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, is_c);
-      if (m) {
-        int base = 0;
-        const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(&cand_count[frame * kMaxLayers + layer], __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (is_c) {
-          const int pos = base + __popc(m & ((1u << lane) - 1u));
-          if (pos < cr.off[layer + 1] - cr.off[layer])
-            cand[(size_t)frame * cand_cap + cr.off[layer] + pos] = time_key(layer, xb + px, y) | (tie ? 0x80000000u : 0u);
-        }
-      }
+  for (int row = warp; row < kTileH; row += kScoreThreads / 32) {
+    const int y = y0 + row;
+    if (y >= d.h) break;                       // warp-uniform
+    const int k = 2 + lane;                    // plane word of this pair (staged byte 16 + 2*lane)
+    uint32_t v[16];
+    v[0] = po[row + 3][k - 2];  v[1] = po[row + 2][k - 2];  v[2] = pe[row + 1][k - 1];  v[3] = po[row][k - 1];
+    v[4] = pe[row][k];          v[5] = po[row][k];          v[6] = pe[row + 1][k + 1];  v[7] = po[row + 2][k + 1];
+    v[8] = po[row + 3][k + 1];  v[9] = po[row + 4][k + 1];  v[10] = pe[row + 5][k + 1]; v[11] = po[row + 6][k];
+    v[12] = pe[row + 6][k];     v[13] = po[row + 6][k - 1]; v[14] = pe[row + 5][k - 1]; v[15] = po[row + 4][k - 2];
+    uint32_t s = b0_pair(v, pe[row + 3][k]);
+    if (edge_tile) {                           // CTA-uniform: scores are zero in the 3-pixel margin of the layer
+      const int x = x0 + 2 * lane;
+      const bool yok = y >= 3 && y < d.h - 3;
+      if (!(yok && x >= 3 && x < d.w - 3)) s &= 0xffff0000u;
+      if (!(yok && x + 1 >= 3 && x + 1 < d.w - 3)) s &= 0x0000ffffu;
+    }
+    const uint16_t packed = (uint16_t)__byte_perm(s, 0, 0x4420);
+    *reinterpret_cast<uint16_t*>(&sc[row][2 * lane]) = packed;
+    *reinterpret_cast<uint16_t*>(score + (size_t)y * d.pitch + x0 + 2 * lane) = packed;   // pitch is a multiple of 64
+    const uint32_t hit = (s + thr2) & 0x80008000u;   // per half: score >= threshold (scores <= 254)
+    if (hit) {
+      if (hit & 0x8000u) strong[atomicAdd(&n_strong, 1)] = (uint16_t)(row * kTileW + 2 * lane);
+      if (hit & 0x80000000u) strong[atomicAdd(&n_strong, 1)] = (uint16_t)(row * kTileW + 2 * lane + 1);
     }
   }
+  __syncthreads();
+  // ---- 3x3 non-max test of the strong pixels
+  const int ns = n_strong;
+  for (int i = threadIdx.x; i < ns; i += kScoreThreads) {
+    const int r = strong[i] / kTileW, x = strong[i] % kTileW;
+    const int c = sc[r][x];
+    bool is_c = true, tie = false, pending = false;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+      for (int dx = -1; dx <= 1; dx++) {
+        if (dx == 0 && dy == 0) continue;
+        const int rr = r + dy, xx = x + dx;
+        if ((unsigned)rr < (unsigned)kTileH && (unsigned)xx < (unsigned)kTileW) {
+          const int v = sc[rr][xx];   // rows of the tile below the image hold stale data only when y >= h-3: c is 0 there
+          if (v > c) is_c = false;
+          if (v == c) tie = true;
+        } else pending = true;
+      }
+    if (is_c) {
+      const int pos = atomicAdd(&n_out, 1);
+      out_list[pos] = time_key(layer, x0 + x, y0 + r) | (pending ? kCandPending : (tie ? kCandTie : 0u));
+    }
+  }
+  __syncthreads();
+  const int no = n_out;
+  if (no == 0) return;
+  if (threadIdx.x == 0) out_base = atomicAdd(&cand_count[frame * kMaxLayers + layer], no);
+  __syncthreads();
+  const int base = out_base, room = cr.off[layer + 1] - cr.off[layer];
+  for (int i = threadIdx.x; i < no; i += kScoreThreads)
+    if (base + i < room) cand[(size_t)frame * cand_cap + cr.off[layer] + base + i] = out_list[i];
 }
 
 // Cache-touch events of one maximum, emitted by a full warp (all arguments warp-uniform): lanes take the positions of
@@ -395,8 +407,26 @@ __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ DeviceLa
 #pragma unroll
     for (int j = 1; j < kMaxLayers; j++) if (i >= prefix[j]) l = j;
     const uint32_t c = cand[(size_t)frame * cand_cap + cr.off[l] + (i - prefix[l])];
-    key = c & 0x7fffffffu; tie = (int)(c >> 31);
-    refine_candidate(v.L, v.n, (int)(key >> 22), (int)(key & 2047), (int)((key >> 11) & 2047), threshold, r);
+    key = c & kCandKeyMask; tie = (int)(c >> 31);
+    bool alive = true;
+    if (c & kCandPending) {
+      // a strong pixel on the border of its score tile: finish the 3x3 non-max test from the (now complete) dense map
+      const LayerView& lv = v.L[l];
+      const uint8_t* s = lv.b0 + (size_t)((key >> 11) & 2047) * lv.bpitch + (key & 2047);
+      const int cc = s[0];
+      tie = 0;
+#pragma unroll
+      for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+          if (dx == 0 && dy == 0) continue;
+          const int val = s[dy * lv.bpitch + dx];
+          if (val > cc) alive = false;
+          if (val == cc) tie = 1;
+        }
+      if (!alive) tie = 0;
+    }
+    if (alive) refine_candidate(v.L, v.n, (int)(key >> 22), (int)(key & 2047), (int)((key >> 11) & 2047), threshold, r);
     CandRecord out;
     out.x = r.x; out.y = r.y; out.size = r.size; out.response = r.response; out.key = key;
     out.keep = r.keep; out.own_touch = r.own_touch; out.has_above = r.has_above; out.tie = (int8_t)tie;
