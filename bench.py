@@ -339,6 +339,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="euroc", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-lanes", type=int, default=2, help="independent sequences replayed concurrently in the e2e leg")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -519,34 +520,69 @@ def main():
                     ("cand_desc", C.c_void_p * 2), ("cand_lm", C.c_void_p * 2), ("lm_proj", C.c_void_p * 2), ("lm_is3d", C.c_void_p * 2),
                     ("m1_dist", C.c_void_p * 2), ("m1_lm", C.c_void_p * 2),
                     ("k1", C.c_void_p), ("sdist", C.c_void_p), ("hp", C.c_void_p), ("init", C.c_void_p),
-                    ("seconds", C.c_double), ("h2d", C.c_longlong), ("d2h", C.c_longlong), ("nkp", C.c_longlong), ("nm", C.c_longlong)]
+                    ("seconds", C.c_double), ("h2d", C.c_longlong), ("d2h", C.c_longlong), ("nkp", C.c_longlong), ("nm", C.c_longlong),
+                    ("lane", C.c_int32), ("lanes", C.c_int32)]
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     pz = lambda n, dt: torch.zeros(n, dtype=dt).pin_memory()
-    hold = dict(img=[pin(Lh), pin(Rh)], kp=[pz(B * kp_cap * 28, torch.uint8) for _ in range(2)],
-                desc=[pz(B * kp_cap * 64, torch.uint8) for _ in range(2)], n=[pz(B, torch.int32) for _ in range(2)],
-                cand_desc=[pin(m["cand_desc"]) for m in maps], cand_lm=[pin(m["cand_lm"]) for m in maps],
-                lm_proj=[pin(np.broadcast_to(m["lm_proj"], (B,) + m["lm_proj"].shape)) for m in maps],
-                lm_is3d=[pin(m["lm_is3d"]) for m in maps],
-                m1_dist=[pz(B * kp_cap, torch.int32) for _ in range(2)], m1_lm=[pz(B * kp_cap, torch.int32) for _ in range(2)],
-                k1=pz(B * kp_cap, torch.int32), sdist=pz(B * kp_cap, torch.int32), hp=pz(B * kp_cap * 4, torch.float64),
-                init=pz(B * kp_cap, torch.uint8))
-    io = ReplayIO(n_steps=args.steps, warmup=warm, batch=B, ring=ring, W=W, H=H, cap=kp_cap)
-    for k in ("img", "kp", "desc", "n", "cand_desc", "cand_lm", "lm_proj", "lm_is3d", "m1_dist", "m1_lm"):
+    h_img = [pin(Lh), pin(Rh)]
+    h_map = dict(cand_desc=[pin(m["cand_desc"]) for m in maps], cand_lm=[pin(m["cand_lm"]) for m in maps],
+                 lm_proj=[pin(np.broadcast_to(m["lm_proj"], (B,) + m["lm_proj"].shape)) for m in maps],
+                 lm_is3d=[pin(m["lm_is3d"]) for m in maps])
+
+    def make_io(n_steps, lane, lanes):
+        hold = dict(img=h_img, kp=[pz(B * kp_cap * 28, torch.uint8) for _ in range(2)],
+                    desc=[pz(B * kp_cap * 64, torch.uint8) for _ in range(2)], n=[pz(B, torch.int32) for _ in range(2)],
+                    m1_dist=[pz(B * kp_cap, torch.int32) for _ in range(2)], m1_lm=[pz(B * kp_cap, torch.int32) for _ in range(2)],
+                    k1=pz(B * kp_cap, torch.int32), sdist=pz(B * kp_cap, torch.int32), hp=pz(B * kp_cap * 4, torch.float64),
+                    init=pz(B * kp_cap, torch.uint8), **h_map)
+        io = ReplayIO(n_steps=n_steps, warmup=warm, batch=B, ring=ring, W=W, H=H, cap=kp_cap, lane=lane, lanes=lanes)
+        for k in ("img", "kp", "desc", "n", "cand_desc", "cand_lm", "lm_proj", "lm_is3d", "m1_dist", "m1_lm"):
+            for c in range(2):
+                getattr(io, k)[c] = hold[k][c].data_ptr()
         for c in range(2):
-            getattr(io, k)[c] = hold[k][c].data_ptr()
-    for c in range(2):
-        io.n_cand[c] = len(maps[c]["cand_lm"]); io.n_lm[c] = len(maps[c]["lm_is3d"])
-    io.k1, io.sdist, io.hp, io.init = (hold[k].data_ptr() for k in ("k1", "sdist", "hp", "init"))
+            io.n_cand[c] = len(maps[c]["cand_lm"]); io.n_lm[c] = len(maps[c]["lm_is3d"])
+        io.k1, io.sdist, io.hp, io.init = (hold[k].data_ptr() for k in ("k1", "sdist", "hp", "init"))
+        return io, hold
+
+    # (i) one replay alone: every call returns its results before the next batch is submitted
+    io, hold = make_io(args.steps, 0, 0)
     drv.okb_e2e_replay.argtypes = [C.c_void_p, C.c_void_p]
     barrier()
     okl.check(drv.okb_e2e_replay(ctx, C.byref(io)))
     rep_s = io.seconds
+    # (ii) `lanes` independent sequences replayed concurrently on this GPU (BASELINE config 5 interleaves sequences), each
+    #      through its own library handle and host-thread pair: exactly args.steps steps in total, split over the lanes.
+    #      One lane's H2D / D2H copies overlap the other lane's kernels.
+    lanes = max(1, args.e2e_lanes)
+    fes = [fe]
+    for l in range(1, lanes):
+        f2 = Frontend(2, W, H, device=local_rank, max_batch=B)
+        f2.configure(threshold=cfg["threshold"], octaves=cfg["octaves"], max_keypoints=cfg["max_kp"])
+        for c in range(2):
+            f2.setCameraModel(c, "radialtangential", (cfg["f"], cfg["f"] * 0.997), (W / 2 - 8.8 + 12 * c, H / 2 + 8.4 + 7 * c),
+                              [-0.2834, 0.0740, 0.00019, 1.76e-05])
+        fes.append(f2)
+    per_lane = [args.steps // lanes + (1 if l < args.steps % lanes else 0) for l in range(lanes)]
+    ios = [make_io(per_lane[l], l, lanes) for l in range(lanes)]
+    ctx_arr = (C.c_void_p * lanes)(*[f.ctx for f in fes])
+    io_arr = (C.c_void_p * lanes)(*[C.addressof(x[0]) for x in ios])
+    lane_s = C.c_double()
+    drv.okb_e2e_replay_lanes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    barrier()
+    okl.check(drv.okb_e2e_replay_lanes(ctx_arr, io_arr, lanes, C.byref(lane_s)))
+    lanes_s = lane_s.value
     if world > 1:
-        t = torch.tensor([rep_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); rep_s = float(t.item())
-    e2e = {"value": world * B * args.steps / rep_s, "unit": "stereo frames/s", "h2d_bytes_per_step": int(io.h2d),
-           "d2h_bytes_per_step": int(io.d2h), "ms_per_step": 1e3 * rep_s / args.steps,
+        t = torch.tensor([rep_s, lanes_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); rep_s, lanes_s = (float(x) for x in t.tolist())
+    for f2 in fes[1:]:
+        f2.close()
+    e2e = {"value": world * B * args.steps / lanes_s, "unit": "stereo frames/s", "h2d_bytes_per_step": int(io.h2d),
+           "d2h_bytes_per_step": int(io.d2h), "ms_per_step": 1e3 * lanes_s / args.steps,
            "step": f"the value leg's step ({B} stereo frames) from page-locked HOST buffers: per camera (one host thread each) "
-                   "okb_detect_describe_batch + okb_match_map3d_batch, then okb_match_stereo_batch; results in host memory",
+                   "okb_detect_describe_batch + okb_match_map3d_batch, then okb_match_stereo_batch; results in host memory; "
+                   f"{lanes} independent sequences in flight on the GPU (one library handle + host-thread pair each), "
+                   f"{args.steps} steps in total",
+           "lanes": lanes,
+           "one_sequence_alone": {"value": world * B * args.steps / rep_s, "ms_per_step": 1e3 * rep_s / args.steps},
            "keypoints_per_frame": io.nkp / (2 * B), "matches_per_stereo_frame": io.nm / B, "streaming": streaming}
 
     clocks = sampler.stop()

@@ -125,9 +125,50 @@ struct okb_replay_io {
   uint32_t* m1_dist[2]; int32_t* m1_lm[2];
   int32_t* k1; uint32_t* sdist; double* hp; uint8_t* init;
   double seconds; long long h2d, d2h, nkp, nm;             // results
+  int32_t lane, lanes;                                     // this replay is sequence `lane` of `lanes` concurrent ones (0, 0 = alone)
 };
 
+namespace {
+struct StartGate {   // all lanes finish their warm-up, then start the timed region together
+  std::atomic<int> arrived{0}; int lanes = 1;
+  std::chrono::steady_clock::time_point t0;
+  std::mutex m; std::condition_variable cv;
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    if (++arrived == lanes) { t0 = std::chrono::steady_clock::now(); cv.notify_all(); }
+    else cv.wait(lk, [this] { return arrived.load() >= lanes; });
+  }
+};
+}  // namespace
+
+static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, std::chrono::steady_clock::time_point* t_end);
+
 extern "C" int okb_e2e_replay(okb_context_t* ctx, okb_replay_io* io)
+{
+  StartGate gate; std::chrono::steady_clock::time_point t1;
+  const int rc = replay_one(ctx, io, &gate, &t1);
+  io->seconds = std::chrono::duration<double>(t1 - gate.t0).count();
+  return rc;
+}
+
+// `lanes` independent sequences replayed concurrently on ONE GPU, each through its own library handle (own streams, own
+// workspaces) and its own pair of host threads: while one lane's batch is in its kernels, the other lane's images are on
+// the copy engine and its results on the way back. Wall clock from the common start to the last lane's okb_sync.
+extern "C" int okb_e2e_replay_lanes(okb_context_t** ctx, okb_replay_io** io, int lanes, double* seconds)
+{
+  StartGate gate; gate.lanes = lanes;
+  std::vector<std::thread> th; std::vector<int> rc(lanes, 0);
+  std::vector<std::chrono::steady_clock::time_point> t1(lanes);
+  for (int l = 0; l < lanes; l++) th.emplace_back([&, l] { rc[l] = replay_one(ctx[l], io[l], &gate, &t1[l]); });
+  for (auto& t : th) t.join();
+  auto last = t1[0];
+  for (int l = 1; l < lanes; l++) if (t1[l] > last) last = t1[l];
+  *seconds = std::chrono::duration<double>(last - gate.t0).count();
+  for (int l = 0; l < lanes; l++) if (rc[l]) return rc[l];
+  return 0;
+}
+
+static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, std::chrono::steady_clock::time_point* t_end)
 {
   const double C0[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, r0[3] = {0, 0, 0}, r1[3] = {0.11, 0, 0};
   const int B = io->batch, cap = io->cap;
@@ -138,7 +179,8 @@ extern "C" int okb_e2e_replay(okb_context_t* ctx, okb_replay_io* io)
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
   auto camera = [&](int c, int s) {
-    const uint8_t* imgs = io->img[c] + (size_t)(s % io->ring) * B * frame;
+    const int g = io->lanes > 1 ? s * io->lanes + io->lane : s;   // lanes replay interleaved parts of the ring
+    const uint8_t* imgs = io->img[c] + (size_t)(g % io->ring) * B * frame;
     const auto ta = now();
     int rc = okb_detect_describe_batch(ctx, c, B, imgs, (size_t)io->W, io->kp[c], io->desc[c], cap, io->n[c]);
     const auto tb = now();
@@ -161,10 +203,13 @@ extern "C" int okb_e2e_replay(okb_context_t* ctx, okb_replay_io* io)
   };
   int rc = 0;
   for (int s = 0; s < io->warmup && !rc; s++) rc = step(s);
-  const auto t0 = std::chrono::steady_clock::now();
+  if (!rc) rc = okb_sync(ctx);
+  gate->wait();
+  const auto t0 = gate->t0;
   for (int s = 0; s < io->n_steps && !rc; s++) rc = step(io->warmup + s);
   if (!rc) rc = okb_sync(ctx);
   const auto t1 = std::chrono::steady_clock::now();
+  *t_end = t1;
   w.stop();
   io->seconds = std::chrono::duration<double>(t1 - t0).count();
   if (trace) {

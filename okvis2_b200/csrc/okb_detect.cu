@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
   __shared__ uint16_t strong[kTileH * kTileW];
   __shared__ uint32_t out_list[kTileH * kTileW];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ int n_strong, n_out, out_base;
+  __shared__ int n_strong, n_out, out_base, tma_failed;
   const int frame = blockIdx.y;
   const int layer = find_layer(tm, blockIdx.x);
   const int t = blockIdx.x - tm.tile_prefix[layer];
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
   else { img = img_block + (size_t)frame * dl.frame_stride + d.offset; pitch = d.pitch; }
   uint8_t* score = score_block + (size_t)frame * dl.frame_stride + d.offset;
   const int x0 = tx * kTileW, y0 = ty * kTileH;
-  if (threadIdx.x == 0) { n_strong = 0; n_out = 0; }
+  if (threadIdx.x == 0) { n_strong = 0; n_out = 0; tma_failed = 0; }
   if (maps.use[layer]) {
     // TMA: one bulk tensor copy per CTA; out-of-image bytes arrive as zeros
     if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -253,13 +253,19 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
       mbar_expect_tx(&bar, kImgH * kImgW);
       tma_load_3d(&tile[0][0], &maps.m[layer], &bar, x0 - kHaloX, y0 - 3, frame);
     }
-    const long long t_start = clock64();
-    while (!mbar_try_wait(&bar, 0)) {
-      if (clock64() - t_start > 400000000ll) {   // ~0.2 s: never spin forever on a broken descriptor
-        if (threadIdx.x == 0) atomicOr(&status[frame], 16);
-        return;
+    // one warp polls the mbarrier (try_wait suspends in hardware), the others park at the CTA barrier and leave the
+    // issue slots to the resident CTAs that are computing
+    if (threadIdx.x < 32) {
+      const long long t_start = clock64();
+      while (!mbar_try_wait(&bar, 0)) {
+        if (clock64() - t_start > 400000000ll) {   // ~0.2 s: never spin forever on a broken descriptor
+          if (threadIdx.x == 0) { atomicOr(&status[frame], 16); tma_failed = 1; }
+          break;
+        }
       }
     }
+    __syncthreads();
+    if (tma_failed) return;
   } else {
     const bool word_ok = ((pitch & 3) == 0) && ((((uintptr_t)img) & 3) == 0);
     for (int i = threadIdx.x; i < kImgH * (kImgW / 4); i += kScoreThreads) {
