@@ -196,6 +196,32 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+// Tie-cell bitmap: one bit per 16x16-pixel cell of every layer, set when the 5x5 window of a tied (or still pending)
+// candidate intersects the cell. The touch-time map is only ever read inside those windows (k_resolve), so a maximum
+// whose touch footprint misses every flagged cell does not have to emit its touches at all (k_refine).
+constexpr int kCellShift = 4;
+constexpr int kCellWordsPerLayer = 512;                    // 16384 cells: layers up to 2048 x 2048
+constexpr int kCellWordsPerFrame = kMaxLayers * kCellWordsPerLayer;
+__device__ __forceinline__ void cells_flag(uint32_t* cells /*layer*/, int layer_w, int x_lo, int x_hi, int y_lo, int y_hi)
+{
+  const int cw = (layer_w + 15) >> kCellShift;
+  for (int cy = max(y_lo, 0) >> kCellShift; cy <= (y_hi >> kCellShift); cy++)
+    for (int cx = max(x_lo, 0) >> kCellShift; cx <= min(x_hi >> kCellShift, cw - 1); cx++) {
+      const int b = cy * cw + cx;
+      if (b < kCellWordsPerLayer * 32) atomicOr(&cells[b >> 5], 1u << (b & 31));
+    }
+}
+__device__ __forceinline__ bool cells_any(const uint32_t* cells /*layer*/, int layer_w, int x_lo, int x_hi, int y_lo, int y_hi)
+{
+  const int cw = (layer_w + 15) >> kCellShift;
+  for (int cy = max(y_lo, 0) >> kCellShift; cy <= (y_hi >> kCellShift); cy++)
+    for (int cx = max(x_lo, 0) >> kCellShift; cx <= min(x_hi >> kCellShift, cw - 1); cx++) {
+      const int b = cy * cw + cx;
+      if (b >= kCellWordsPerLayer * 32 || ((__ldg(&cells[b >> 5]) >> (b & 31)) & 1u)) return true;
+    }
+  return false;
+}
+
 // Fused score + non-max suppression. Tile = kTileW x kTileH (64 x 32) pixels of one layer of one frame, 256 threads.
 //   1. the image tile with its ring halo (3 rows above/below, 16 bytes left/right: TMA wants 16-byte granular boxes
 //      AND box origins) arrives in shared memory by ONE TMA bulk tensor copy, zero outside the image;
@@ -224,7 +250,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
                                                              const uint8_t* in0, int in_pitch, size_t in_frame_stride,
                                                              uint8_t* img_block, uint8_t* score_block, uint32_t* cand,
                                                              int32_t* cand_count, int cand_cap, const __grid_constant__ CandRegions cr,
-                                                             int threshold, int32_t* status)
+                                                             int threshold, int32_t* status, uint32_t* tie_cells)
 {
   __shared__ __align__(128) uint8_t tile[kImgH][kImgW];
   __shared__ __align__(16) uint32_t pe[kImgH][kPlaneW];
@@ -348,6 +374,9 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
     if (is_c) {
       const int pos = atomicAdd(&n_out, 1);
       out_list[pos] = time_key(layer, x0 + x, y0 + r) | (pending ? kCandPending : (tie ? kCandTie : 0u));
+      if (pending || tie)
+        cells_flag(tie_cells + (size_t)frame * kCellWordsPerFrame + layer * kCellWordsPerLayer, d.w, x0 + x - 2, x0 + x + 2,
+                   y0 + r - 2, y0 + r + 2);
     }
   }
   __syncthreads();
@@ -393,7 +422,8 @@ __device__ __forceinline__ void emit_touches_warp(const DeviceLayers& dl, uint32
 __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ DeviceLayers dl, const uint8_t* in0, int in_pitch, size_t in_frame_stride,
                                                 uint8_t* img_block, uint8_t* score_block, uint32_t* touch_block,
                                                 const uint32_t* cand, const int32_t* cand_count, int cand_cap,
-                                                const __grid_constant__ CandRegions cr, CandRecord* rec, int threshold, uint32_t epoch)
+                                                const __grid_constant__ CandRegions cr, CandRecord* rec, int threshold, uint32_t epoch,
+                                                const uint32_t* tie_cells)
 {
   const int frame = blockIdx.y;
   int prefix[kMaxLayers + 1];
@@ -441,7 +471,21 @@ __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ DeviceLa
   }
   // cache-touch events of the non-tied maxima, one maximum at a time by the whole warp
   uint32_t* touch_frame = touch_block + (size_t)frame * dl.frame_stride;
-  const bool emits = have && !tie && (r.own_touch || r.has_above);
+  bool emits = have && !tie && (r.own_touch || r.has_above);
+  if (emits) {
+    // the touches are only read inside the 5x5 windows of tied candidates: skip the emission when the footprint (own
+    // 4x4 patch; window of the above-layer scan with its bilinear / 3x3 margins) misses every flagged cell
+    const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+    const uint32_t* cells = tie_cells + (size_t)frame * kCellWordsPerFrame;
+    bool hit = false;
+    if (r.own_touch) hit = cells_any(cells + layer * kCellWordsPerLayer, dl.l[layer].w, x - 1, x + 2, y - 1, y + 2);
+    if (!hit && r.has_above) {
+      ScanIter it; above_window(layer, x, y, it);
+      hit = cells_any(cells + (layer + 1) * kCellWordsPerLayer, dl.l[layer + 1].w, (int)it.x_1 - 1, (int)it.x1 + 2, (int)it.y_1 - 1,
+                      (int)it.y1 + 2);
+    }
+    emits = hit;
+  }
   unsigned m = __ballot_sync(0xffffffffu, emits);
   const unsigned tr_a = (uint32_t)(uint16_t)r.above.n_queries | ((uint32_t)(uint16_t)r.above.exited << 16);
   const unsigned tr_b = (uint32_t)(uint16_t)r.above.max_x | ((uint32_t)(uint16_t)r.above.max_y << 16);
@@ -1091,6 +1135,7 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMalloc(&ws.d_score, off * B));
   OKB_CUDA(cudaMalloc(&ws.d_touch, off * B * 4));
   OKB_CUDA(cudaMemset(ws.d_touch, 0, off * B * 4));
+  OKB_CUDA(cudaMalloc(&ws.d_tie_cells, (size_t)kCellWordsPerFrame * B * 4));
   OKB_CUDA(cudaMemset(ws.d_score, 0, off * B));
   OKB_CUDA(cudaMemset(ws.d_img, 0, off * B));
   OKB_CUDA(cudaMalloc(&ws.d_integral, (size_t)(W + 1) * (H + 1) * 4 * B));
@@ -1133,7 +1178,7 @@ void detect_free_camera(okb_context* ctx, int cam)
     LayerGeom& g = ws.geom[i];
     cudaFree(g.d_xs); cudaFree(g.d_xn); cudaFree(g.d_xa); cudaFree(g.d_ys); cudaFree(g.d_yn); cudaFree(g.d_ya);
   }
-  cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
+  cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_tie_cells); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
   cudaFree(ws.d_cand_count); cudaFree(ws.d_rec); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
   cudaFree(ws.d_count); cudaFree(ws.d_status); cudaFree(ws.d_m1_cell_off); cudaFree(ws.d_m1_cell_list); cudaFree(ws.d_m1_best); cudaFree(ws.m_d); if (ws.m_h) cudaFreeHost(ws.m_h); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);
   if (ws.ev_done) cudaEventDestroy(ws.ev_done);
@@ -1260,16 +1305,17 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, 4 * kMaxLayers * B, st));
   CandRegions cr; for (int i = 0; i <= kMaxLayers; i++) cr.off[i] = ws.cand_off[i];
   OKB_CUDA(cudaMemsetAsync(ws.d_status, 0, 4 * B, st));
+  OKB_CUDA(cudaMemsetAsync(ws.d_tie_cells, 0, (size_t)kCellWordsPerFrame * B * 4, st));
   TmaMaps maps;
   { int rc = build_tma_maps(ws, d_images, src_pitch, in_stride, c.max_batch, maps); if (rc) return rc; }
   k_score_nms<<<dim3(n_tiles, B), kScoreThreads, 0, st>>>(maps, ws.dl, tm, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
-                                                          ws.d_cand, ws.d_cand_count, ws.cand_cap, cr, c.threshold, ws.d_status);
+                                                          ws.d_cand, ws.d_cand_count, ws.cand_cap, cr, c.threshold, ws.d_status, ws.d_tie_cells);
   ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
   if (ctx->timers_on) cudaEventRecord(ws.ev[1], st);
   // ---- candidates, refinement, tie resolution, selection
   k_refine<<<dim3((ws.cand_cap + 127) / 128, B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
                                                                ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap, cr,
-                                                               ws.d_rec, c.threshold, ws.epoch);
+                                                               ws.d_rec, c.threshold, ws.epoch, ws.d_tie_cells);
   k_resolve<<<B, 512, kResolveSmem, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_cand_count, ws.cand_cap, cr, ws.d_rec, ws.epoch, c.threshold,
                                           ws.d_status, ws.d_dbg);
   k_finalize<<<B, 1024, kFinalizeSmem, st>>>(ws.dl, ws.d_cand_count, ws.cand_cap, cr, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,

@@ -74,6 +74,7 @@ struct CamWorkspace {
   uint8_t* d_img = nullptr;     // layer images (layers >= 1)
   uint8_t* d_score = nullptr;   // thresholded score maps
   uint32_t* d_touch = nullptr;  // touch-time maps
+  uint32_t* d_tie_cells = nullptr;  // per frame: one bit per 16x16 cell of every layer, set around tied candidates
   int32_t* d_integral = nullptr;  // (w+1) x (h+1) per frame
   uint32_t* d_cand = nullptr;   // candidate keys
   int32_t* d_cand_count = nullptr;

@@ -154,6 +154,33 @@ __device__ __forceinline__ uint32_t hamming(const uint4 (&qd)[D16], uint4 (*s_de
   return d;
 }
 
+// Hamming distance with a warp-uniform early exit: POPC is the bound of the gated matchers (16 results/clk/SM), and a
+// candidate can only matter if its distance is < `best` (strict, as in the reference loops). The popcount of the first
+// half of the descriptor is a lower bound of the distance; when no lane of the warp is still below `best` after that
+// half, the second half is skipped for the whole warp. A skipped lane returns its partial count, which is >= best, so
+// every `d < best` test downstream decides exactly as with the full distance.
+template <int D16>
+__device__ __forceinline__ uint32_t hamming_bounded(const uint4 (&qd)[D16], uint4 (*s_desc)[kTile], int ci, bool valid, uint32_t best)
+{
+  constexpr int H = (D16 + 1) / 2;
+  uint32_t d = 0;
+#pragma unroll
+  for (int w = 0; w < H; w++) {
+    const uint4 c = s_desc[w][ci];
+    d += __popcll(((unsigned long long)(qd[w].x ^ c.x) << 32) | (qd[w].y ^ c.y));
+    d += __popcll(((unsigned long long)(qd[w].z ^ c.z) << 32) | (qd[w].w ^ c.w));
+  }
+  if (!valid) d = 0xffffu;
+  if (!__any_sync(0xffffffffu, d < best)) return d;
+#pragma unroll
+  for (int w = H; w < D16; w++) {
+    const uint4 c = s_desc[w][ci];
+    d += __popcll(((unsigned long long)(qd[w].x ^ c.x) << 32) | (qd[w].y ^ c.y));
+    d += __popcll(((unsigned long long)(qd[w].z ^ c.z) << 32) | (qd[w].w ^ c.w));
+  }
+  return valid ? d : 0xffffu;
+}
+
 // M1. The reprojection gate makes the problem sparse: a keypoint can only match landmarks that project within
 // `thr` pixels of it. Keypoints are binned into a grid of cells >= thr wide (k_m1_bin, one CTA per frame); every pooled
 // descriptor then visits the 3x3 cells around its landmark's projection, evaluates the reference's exact fp64 gate
@@ -397,12 +424,51 @@ __global__ void __launch_bounds__(256) k_match_gated(MatchArgs a)
     for (int j = 0; active && j < kTile / 32; j++) {
       const int ci = j * 32 + lane, c = tile0 + ci;
       if (tile0 + j * 32 >= nc) break;
-      uint32_t d = 0xffffu;
       int lm = -1;
-      if (c < nc) {
-        bool ok = true;
-        if (MODE == MODE_M2) { lm = a.c_lm[fc + c]; ok = !a.lm_is3d[lm]; }
-        if (ok) d = hamming<D16>(qd, s_desc, ci);
+      bool ok = c < nc;
+      if (MODE == MODE_M2 && ok) { lm = a.c_lm[fc + c]; ok = !a.lm_is3d[lm]; }
+      const uint32_t d = hamming_bounded<D16>(qd, s_desc, ci, ok, best);
+      if (MODE != MODE_M2) {
+        // M3 / M4: the gate is a pure function of the pair, so the sequential loop's result is "the smallest distance
+        // among the candidates that pass, first index on ties". Every lane whose distance beats the running best
+        // evaluates the gate of ITS candidate (the loads and the fp64 triangulation of up to 32 candidates overlap),
+        // then the warp takes the minimum of (distance, lane) over the lanes that passed.
+        bool pass = false, parallel = false;
+        V3 hp = V3{0, 0, 0};
+        if (d < best && a.c_valid[fc + c]) {
+          const V3 e1 = v3(a.c_e + 3 * (fc + c));
+          double c26 = q_c26, c6 = q_c6;
+          if (MODE == MODE_M4) { const double s1 = a.c_sof[fc + c]; if (q_sof < s1) { c26 = a.c_cos26[fc + c]; c6 = a.c_cos6[fc + c]; } }
+          if (MODE != MODE_M3 || !(dot(eq, e1) < 0.5)) {
+            const Tri t = triangulate_fast(r0, eq, r1, e1, c26, c6);
+            pass = t.valid; parallel = t.parallel; hp = t.p;
+            if (MODE == MODE_M3) {
+              if (pass) {
+                if (dot(eq, e1) < 0.8) pass = false;
+                if (!parallel) {
+                  if (depth_in(a.T0, hp) < 0.2) pass = false;
+                  if (depth_in(a.T1, hp) < 0.2) pass = false;
+                }
+              }
+            } else {
+              if (!parallel) {
+                if (depth_in(a.T0, hp) < 0.05) pass = false;
+                if (depth_in(a.T1, hp) < 0.05) pass = false;
+                if (dot(eq, e1) < 0.8) pass = false;
+              }
+            }
+          }
+        }
+        const unsigned key = pass ? ((d << 5) | (unsigned)lane) : 0xffffffffu;
+        const unsigned win = __reduce_min_sync(0xffffffffu, key);
+        if (win != 0xffffffffu) {
+          const int wl = (int)(win & 31u);
+          best = win >> 5; best_idx = tile0 + j * 32 + wl;
+          best_hp.x = __shfl_sync(0xffffffffu, hp.x, wl); best_hp.y = __shfl_sync(0xffffffffu, hp.y, wl);
+          best_hp.z = __shfl_sync(0xffffffffu, hp.z, wl);
+          have_hp = true; best_init = !__shfl_sync(0xffffffffu, (int)parallel, wl);
+        }
+        continue;
       }
       unsigned m = __ballot_sync(0xffffffffu, d < best);
       while (m) {
