@@ -236,6 +236,52 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
                                 const double r_WC1[3], uint32_t match_threshold, void* stream, int32_t* d_out_k1,
                                 uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_initialisable);
 
+/* ---- P1: landmark-candidate preparation. Replaces the serial host loop of Frontend::matchToMap that
+ *      builds landmarksToMatch / descriptorPool for one camera (okvis_frontend/src/Frontend.cpp:1196-1360; pose lookups
+ *      ViGraph.cpp:632-645): projection of every landmark into the current view (PinholeCamera::projectHomogeneous,
+ *      cameras/implementation/PinholeCamera.hpp:257-292,493-502), field-of-view gate +- reprThreshold, is3d decision,
+ *      viewpoint (0.6 rad) and scale (50 %) pruning of the observations walked newest first, "best 3" descriptor pool with
+ *      the loop's own bookkeeping (row `o` written, cropped to `o` rows; oracle/prepare_oracle.cpp states what survives).
+ *      Output = what M1/M2 take: cand_desc (pool rows), cand_lm (row -> output landmark), lm_proj, lm_is3d (+ e_W, r_W).
+ *
+ *      The descriptors / back-projections of the frames in the window live in a device-resident store:
+ *      okb_store_configure(n_slots, n_cams, D); okb_store_frame(slot, cam, ...) per (multiframe, camera), the slot being
+ *      the caller's index for the multiframe id (KeypointIdentifier::frameId). */
+int okb_store_configure(okb_context_t* ctx, int n_slots, int n_cams, int D);
+/* desc: n x D bytes (Frame::keypointDescriptor), rays: n x 3 doubles (Frame::getBackProjection); host pointers */
+int okb_store_frame(okb_context_t* ctx, int slot, int cam, int n, const uint8_t* desc, const double* rays);
+/* same, device to device from frame `batch_index` of the last okb_detect_describe[_batch] call of camera `cam`
+ * (needs okb_set_camera_model: the rays are the device D4 output) */
+int okb_store_frame_from_last(okb_context_t* ctx, int slot, int cam, int batch_index);
+
+typedef struct {
+  double T_WC1[12];            /* current camera pose T_WS1 * T_SC: C_WC row-major (9) then r_WC (3)  (Frontend.cpp:1214-1215) */
+  double T_CW1[12];            /* its inverse, same layout                                              (Frontend.cpp:1216) */
+  okb_camera_model_t model;    /* geometryAs<CAMERA_GEOMETRY>(im) */
+  int32_t width, height;
+  double repr_threshold;       /* 20.0 with IMU, 150.0 without (Frontend.cpp:1180) */
+  int32_t exclusive, reserved; /* 1 = loopClosureLandmarksToUseExclusively given: the caller passes only those landmarks
+                                  and the viewpoint / scale gates are off (Frontend.cpp:1300,1306) */
+} okb_prepare_view_t;
+
+/* Landmarks in ascending LandmarkId order (MapPoints is an ordered map): hp_W n_lm x 4, quality n_lm, observations of
+ * landmark i = obs[obs_begin[i] .. obs_begin[i+1]) in std::set<KeypointIdentifier> order (frame slot, camera, keypoint
+ * index; 3 x int32 each) -- the kernel walks them in reverse like the reference. T_WC_old: n_slots x n_cams x 12 doubles
+ * (T_WS_old * T_SC_old, layout as T_WC1). Outputs (host, caller-sized: n_lm landmarks, 2 * n_lm pool rows):
+ *   out_lm[j]         input index of output landmark j (ascending)          out_proj[j]  projection (2 doubles)
+ *   out_is3d[j], out_p_W[j] (3 doubles)                                    out_desc_begin[j .. j+1)  its pool rows
+ *   out_pool rows x D, out_cand_lm[row] = j, out_e_W / out_r_W rows x 3 doubles, out_kid rows x 3 int32.
+ * Any out_* may be NULL. The same arrays stay on the device for okb_prepared_device. Synchronous. */
+int okb_prepare_landmarks(okb_context_t* ctx, const okb_prepare_view_t* view, int n_lm, const double* hp_W, const double* quality,
+                          const int32_t* obs_begin, int n_obs, const int32_t* obs, const double* T_WC_old,
+                          int32_t* n_out, int32_t* n_rows, int32_t* out_lm, double* out_proj, uint8_t* out_is3d, double* out_p_W,
+                          int32_t* out_desc_begin, uint8_t* out_pool, int32_t* out_cand_lm, double* out_e_W, double* out_r_W,
+                          int32_t* out_kid);
+/* device pointers of the last okb_prepare_landmarks result, in the argument layout of okb_match_map3d_device (valid
+ * until the next okb_prepare_landmarks / okb_store_configure) */
+int okb_prepared_device(okb_context_t* ctx, const uint8_t** d_cand_desc, const int32_t** d_cand_lm, const double** d_lm_proj,
+                        const uint8_t** d_lm_is3d, int32_t* n_cand, int32_t* n_lm);
+
 #ifdef __cplusplus
 }
 #endif

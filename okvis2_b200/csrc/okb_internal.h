@@ -141,6 +141,8 @@ struct okb_context {
   int timers_on = 0;
   void* stereo_scratch = nullptr; size_t stereo_cap = 0;   // device scratch of okb_match_stereo_device*
   int64_t launches = 0;
+  void* prepare = nullptr;   // okb::PrepareState (okb_prepare.cu): keyframe feature store + P1 workspace
+  void* aux = nullptr;       // okb::AuxState (okb_aux.cu): keyframe-overlap / BoW workspaces
 };
 
 namespace okb {
@@ -159,6 +161,7 @@ inline bool host_pinned(const void* p)
   if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return at.type == cudaMemoryTypeHost;
 }
+void prepare_free(okb_context* ctx);
 int tables_init(okb_context* ctx, float pattern_scale);
 void tables_free(okb_context* ctx);
 }  // namespace okb

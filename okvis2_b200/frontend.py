@@ -149,6 +149,48 @@ class Frontend:
         fr.backProjections, fr.backProjectionsValid = rays, valid
         return int(valid.sum())
 
+    # ---- P1: landmark-candidate preparation (the loop of Frontend::matchToMap before the matching threads start)
+    def configureFeatureStore(self, n_slots, D=64):
+        """Device-resident store of the descriptors / back-projections of the multiframes in the window."""
+        check(_l.lib().okb_store_configure(self._ctx, int(n_slots), self.numCameras, int(D)))
+        self._store_D = int(D)
+
+    def storeFrame(self, slot, cameraIndex, descriptors, backProjections):
+        d = np.ascontiguousarray(descriptors, np.uint8); r = np.ascontiguousarray(backProjections, np.float64)
+        check(_l.lib().okb_store_frame(self._ctx, int(slot), int(cameraIndex), len(d), ptr(d), ptr(r)))
+
+    def storeLastFrame(self, slot, cameraIndex, batch_index=0):
+        check(_l.lib().okb_store_frame_from_last(self._ctx, int(slot), int(cameraIndex), int(batch_index)))
+
+    def prepareLandmarksToMatch(self, cameraIndex, T_WC1, T_CW1, width, height, hp_W, quality, obs_begin, obs, T_WC_old,
+                                reprThreshold=20.0, exclusive=False):
+        """landmarksToMatch / descriptorPool of one camera (Frontend.cpp:1196-1360). Poses are (C 3x3, r 3) pairs packed
+        as 12 doubles; returns a dict with the packed pool (cand_desc, cand_lm, lm_proj, lm_is3d, ...)."""
+        v = _l.PrepareView()
+        v.T_WC1[:] = list(np.asarray(T_WC1, np.float64).ravel()); v.T_CW1[:] = list(np.asarray(T_CW1, np.float64).ravel())
+        v.model = self._models[cameraIndex]; v.width, v.height = int(width), int(height)
+        v.repr_threshold = float(reprThreshold); v.exclusive = 1 if exclusive else 0
+        hp_W = np.ascontiguousarray(hp_W, np.float64); quality = np.ascontiguousarray(quality, np.float64)
+        obs_begin = np.ascontiguousarray(obs_begin, np.int32); obs = np.ascontiguousarray(obs, np.int32).reshape(-1, 3)
+        T_WC_old = np.ascontiguousarray(T_WC_old, np.float64)
+        n_lm = len(quality); D = self._store_D
+        out = dict(lm=np.zeros(n_lm, np.int32), lm_proj=np.zeros((n_lm, 2)), lm_is3d=np.zeros(n_lm, np.uint8), p_W=np.zeros((n_lm, 3)),
+                   desc_begin=np.zeros(n_lm + 1, np.int32), cand_desc=np.zeros((2 * n_lm, D), np.uint8),
+                   cand_lm=np.zeros(2 * n_lm, np.int32), e_W=np.zeros((2 * n_lm, 3)), r_W=np.zeros((2 * n_lm, 3)),
+                   kid=np.zeros((2 * n_lm, 3), np.int32))
+        n_out = C.c_int32(); n_rows = C.c_int32()
+        check(_l.lib().okb_prepare_landmarks(self._ctx, C.byref(v), n_lm, ptr(hp_W), ptr(quality), ptr(obs_begin), len(obs), ptr(obs),
+                                             ptr(T_WC_old), C.byref(n_out), C.byref(n_rows), ptr(out["lm"]), ptr(out["lm_proj"]),
+                                             ptr(out["lm_is3d"]), ptr(out["p_W"]), ptr(out["desc_begin"]), ptr(out["cand_desc"]),
+                                             ptr(out["cand_lm"]), ptr(out["e_W"]), ptr(out["r_W"]), ptr(out["kid"])))
+        nl, nr = n_out.value, n_rows.value
+        for k in ("lm", "lm_proj", "lm_is3d", "p_W"):
+            out[k] = out[k][:nl]
+        out["desc_begin"] = out["desc_begin"][:nl + 1]
+        for k in ("cand_desc", "cand_lm", "e_W", "r_W", "kid"):
+            out[k] = out[k][:nr]
+        return out
+
     def initialiseBriskFeatureDetectors(self):
         """Frontend::initialiseBriskFeatureDetectors (Frontend.cpp:2398-2417): (re)create the per-camera objects."""
         self.close()

@@ -90,7 +90,18 @@ _PROTOS = {
     "okb_match_map3d_device": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, vp, vp]),
     "okb_match_map3d_batch": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, i32, vp, vp]),
     "okb_match_stereo_batch": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, i32, vp, vp, vp, vp]),
+    "okb_store_configure": (i32, [vp, i32, i32, i32]),
+    "okb_store_frame": (i32, [vp, i32, i32, i32, vp, vp]),
+    "okb_store_frame_from_last": (i32, [vp, i32, i32, i32]),
+    "okb_prepare_landmarks": (i32, [vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "okb_prepared_device": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]),
 }
+
+
+class PrepareView(C.Structure):
+    """okb_prepare_view_t"""
+    _fields_ = [("T_WC1", C.c_double * 12), ("T_CW1", C.c_double * 12), ("model", CameraModel), ("width", C.c_int32),
+                ("height", C.c_int32), ("repr_threshold", C.c_double), ("exclusive", C.c_int32), ("reserved", C.c_int32)]
 
 
 def lib():

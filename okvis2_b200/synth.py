@@ -173,3 +173,47 @@ def stereo_scene(seed, n0, n1, D=64, f=458.0, baseline=0.11, flip_p=0.04, frac_m
 
     return dict(desc0=d0, e0_W=e0, sof0=sof0, valid0=v0, desc1=d1, e1_W=e1, sof1=sof1, valid1=v1, r_WC0=r0, r_WC1=r1,
                 T_CW0=T_CW(C0, r0), T_CW1=T_CW(C1, r1), idx0=i0, idx1=i1, f=f)
+
+
+def landmark_scene(seed, n_lm=2000, n_slots=10, n_cams=2, n_kp=600, D=64, W=752, H=480, f=458.0):
+    """Synthetic map for the landmark-candidate preparation (P1): a camera rig moving along x through a cloud of
+    landmarks, every landmark observed by a random subset of the (frame slot, camera) views. Poses are packed as 12
+    doubles (C_WC row-major, r_WC). Returns the inputs of Frontend.prepareLandmarksToMatch / oracle.prepare_landmarks."""
+    rng = np.random.default_rng(seed)
+
+    def rot(rx, ry, rz):
+        cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        return Rz @ Ry @ Rx
+
+    T_WC_old = np.zeros((n_slots, n_cams, 12))
+    for s in range(n_slots):
+        C = rot(*(0.05 * rng.standard_normal(3)))
+        r = np.array([0.35 * s, 0.0, 0.0]) + 0.05 * rng.standard_normal(3)
+        for c in range(n_cams):
+            Cc = C @ rot(0.0, 0.02 * c, 0.0)
+            T_WC_old[s, c, :9] = Cc.ravel(); T_WC_old[s, c, 9:] = r + C @ np.array([0.11 * c, 0.0, 0.0])
+    # current view: a little beyond the last slot
+    C1 = rot(*(0.05 * rng.standard_normal(3)))
+    r1 = np.array([0.35 * n_slots, 0.02, -0.01])
+    T_WC1 = np.concatenate([C1.ravel(), r1]); T_CW1 = np.concatenate([C1.T.ravel(), -(C1.T @ r1)])
+    # landmarks: mostly in front (z = 2..15 m), some behind / far off axis / at the w < 0 branch / near the singularity
+    p = np.stack([rng.uniform(-8, 12, n_lm), rng.uniform(-5, 5, n_lm), rng.uniform(1.0, 15.0, n_lm)], 1)
+    behind = rng.random(n_lm) < 0.1
+    p[behind, 2] = -rng.uniform(0.5, 10.0, behind.sum())
+    w = np.where(rng.random(n_lm) < 0.1, -1.0, 1.0) * rng.uniform(0.5, 2.0, n_lm)
+    hp_W = np.concatenate([p * w[:, None], w[:, None]], 1)
+    quality = 10.0 ** rng.uniform(-4.0, 0.0, n_lm)   # low-quality landmarks with parallax stay non-3d
+    # feature tables
+    desc_tab = [rng.integers(0, 256, (n_kp, D), dtype=np.uint8) for _ in range(n_slots * n_cams)]
+    ray_tab = [np.concatenate([rng.uniform(-0.8, 0.8, (n_kp, 2)), np.ones((n_kp, 1))], 1) for _ in range(n_slots * n_cams)]
+    obs_begin = [0]; obs = []
+    for i in range(n_lm):
+        k = int(rng.integers(0, 9))
+        views = rng.choice(n_slots * n_cams, size=min(k, n_slots * n_cams), replace=False)
+        ids = sorted((int(v) // n_cams, int(v) % n_cams, int(rng.integers(0, n_kp))) for v in views)  # std::set order
+        obs.extend(ids); obs_begin.append(len(obs))
+    return dict(hp_W=hp_W, quality=quality, obs_begin=np.array(obs_begin, np.int32), obs=np.array(obs, np.int32).reshape(-1, 3),
+                T_WC_old=T_WC_old, T_WC1=T_WC1, T_CW1=T_CW1, desc_tab=desc_tab, ray_tab=ray_tab, n_cams=n_cams, n_slots=n_slots,
+                D=D, W=W, H=H, intr=np.array([f, f * 0.997, W / 2 - 8.8, H / 2 + 8.4, -0.2834, 0.0740, 0.00019, 1.76e-05]))

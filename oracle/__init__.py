@@ -259,3 +259,34 @@ def back_project(model, fu, fv, cu, cv, k, kp):
     f.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     f(model, fu, fv, cu, cv, kk.ctypes.data, n, kp.ctypes.data, 7, rays.ctypes.data, valid.ctypes.data)
     return rays, valid
+
+
+def prepare_landmarks(hp_W, quality, obs_begin, obs, n_cams, T_WC_old, desc_tab, ray_tab, D, T_WC1, T_CW1, model, intr,
+                      width, height, repr_thr=20.0, exclusive=False):
+    """P1 oracle (prepare_oracle.cpp = Frontend.cpp:1196-1360). desc_tab / ray_tab: lists indexed slot * n_cams + cam."""
+    L = lib()
+    hp_W = _c(hp_W, np.float64); quality = _c(quality, np.float64); obs_begin = _c(obs_begin, np.int32)
+    obs = _c(np.asarray(obs).reshape(-1, 3), np.int32); T_WC_old = _c(T_WC_old, np.float64)
+    descs = [_c(d, np.uint8) for d in desc_tab]; rays = [_c(r, np.float64) for r in ray_tab]
+    dt = (C.c_void_p * len(descs))(*[d.ctypes.data for d in descs]); rt = (C.c_void_p * len(rays))(*[r.ctypes.data for r in rays])
+    n = len(quality)
+    out = dict(lm=np.zeros(n, np.int32), lm_proj=np.zeros((n, 2)), lm_is3d=np.zeros(n, np.uint8), p_W=np.zeros((n, 3)),
+               desc_begin=np.zeros(n + 1, np.int32), cand_desc=np.zeros((3 * n + 3, D), np.uint8), e_W=np.zeros((3 * n + 3, 3)),
+               r_W=np.zeros((3 * n + 3, 3)), kid=np.zeros((3 * n + 3, 3), np.int32))
+    n_rows = C.c_int32()
+    T1 = _c(T_WC1, np.float64); T2 = _c(T_CW1, np.float64); intr = _c(intr, np.float64)
+    L.okvo_prepare_landmarks.restype = C.c_int
+    L.okvo_prepare_landmarks.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + \
+        [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 10
+    nl = L.okvo_prepare_landmarks(n, _p(hp_W), _p(quality), _p(obs_begin), _p(obs), n_cams, _p(T_WC_old), dt, rt, D, _p(T1), _p(T2),
+                                  int(model), _p(intr), int(width), int(height), float(repr_thr), 1 if exclusive else 0,
+                                  _p(out["lm"]), _p(out["lm_proj"]), _p(out["lm_is3d"]), _p(out["p_W"]), _p(out["desc_begin"]),
+                                  _p(out["cand_desc"]), _p(out["e_W"]), _p(out["r_W"]), _p(out["kid"]), C.byref(n_rows))
+    nr = n_rows.value
+    for k in ("lm", "lm_proj", "lm_is3d", "p_W"):
+        out[k] = out[k][:nl]
+    out["desc_begin"] = out["desc_begin"][:nl + 1]
+    for k in ("cand_desc", "e_W", "r_W", "kid"):
+        out[k] = out[k][:nr]
+    out["cand_lm"] = np.repeat(np.arange(nl, dtype=np.int32), np.diff(out["desc_begin"]))
+    return out
