@@ -331,6 +331,33 @@ def run_sharded(args, cfg, rank, world, local_rank):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def bench_next_rows(fe, cfg):
+    """P1 (Frontend.cpp:1196-1360) on a 50 000-landmark map: the C-ABI call (H2D of the map, kernels, D2H of the pool)
+    against the oracle transcription on one host core; outputs compared."""
+    import oracle
+    from okvis2_b200.synth import landmark_scene
+    s = landmark_scene(77, n_lm=50000, n_slots=50, n_cams=2, n_kp=cfg["max_kp"], W=cfg["W"], H=cfg["H"], f=cfg["f"])
+    fe.configureFeatureStore(s["n_slots"], 64)
+    for t in range(s["n_slots"] * 2):
+        fe.storeFrame(t // 2, t % 2, s["desc_tab"][t], s["ray_tab"][t])
+    call = lambda: fe.prepareLandmarksToMatch(0, s["T_WC1"], s["T_CW1"], s["W"], s["H"], s["hp_W"], s["quality"], s["obs_begin"],
+                                              s["obs"], s["T_WC_old"])
+    got = call()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        got = call()
+    gpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+    intr = np.array([cfg["f"], cfg["f"] * 0.997, s["W"] / 2 - 8.8, s["H"] / 2 + 8.4, -0.2834, 0.0740, 0.00019, 1.76e-05])
+    t0 = time.perf_counter()
+    ref = oracle.prepare_landmarks(s["hp_W"], s["quality"], s["obs_begin"], s["obs"], 2, s["T_WC_old"], s["desc_tab"], s["ray_tab"], 64,
+                                   s["T_WC1"], s["T_CW1"], 1, intr, s["W"], s["H"])
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    same = all(np.array_equal(got[k], ref[k]) for k in ("lm", "lm_is3d", "desc_begin", "cand_desc", "kid", "lm_proj"))
+    return {"P1_prepare_landmarks": {"landmarks": 50000, "observations": int(len(s["obs"])), "kept": int(len(got["lm"])),
+                                     "pool_rows": int(len(got["cand_desc"])), "gpu_ms_host_buffers": gpu_ms, "cpu_port_ms_1_core": cpu_ms,
+                                     "identical_to_oracle": bool(same)}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -585,6 +612,15 @@ def main():
            "one_sequence_alone": {"value": world * B * args.steps / rep_s, "ms_per_step": 1e3 * rep_s / args.steps},
            "keypoints_per_frame": io.nkp / (2 * B), "matches_per_stereo_frame": io.nm / B, "streaming": streaming}
 
+    # ---- next rows of the scope table, measured beside the headline: P1 landmark-candidate preparation
+    #      (host buffers in, packed pool out; TUM-VI-sized map of 50 000 landmarks) against its oracle on one host core
+    next_rows = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            next_rows = bench_next_rows(fe, cfg)
+        except Exception as e:   # never lose the headline line to an auxiliary measurement
+            next_rows = {"error": repr(e)}
+
     clocks = sampler.stop()
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
     cpu = None
@@ -604,7 +640,8 @@ def main():
                 "config": {"workload": args.config, "stereo_frames_per_step_per_gpu": B, "l2_policy": f"inputs larger than L2: ring of {ring} batches = {in_bytes >> 20} MiB per GPU",
                            "parallelism": "replicas (independent sequences per GPU)" if world > 1 else "single GPU",
                            **{k: cfg[k] for k in ("W", "H", "max_kp", "threshold", "octaves", "n_lm")}},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "next_rows": next_rows}
         print(json.dumps(line))
     fe.close()
     if world > 1:

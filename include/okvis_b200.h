@@ -282,6 +282,19 @@ int okb_prepare_landmarks(okb_context_t* ctx, const okb_prepare_view_t* view, in
 int okb_prepared_device(okb_context_t* ctx, const uint8_t** d_cand_desc, const int32_t** d_cand_lm, const double** d_lm_proj,
                         const uint8_t** d_lm_is3d, int32_t* n_cand, int32_t* n_lm);
 
+/* ---- K1: keyframe-overlap masks. Replaces the mask painting and counting inside
+ *      Frontend::doWeNeedANewKeyframe (okvis_frontend/src/Frontend.cpp:1068-1101 for the current frame, :1117-1151 for
+ *      every keyframe of the window) and ViSlamBackend::overlapFraction (okvis_ceres/src/ViSlamBackend.cpp:2341-2426):
+ *      per view (one camera image of one multiframe) the "detections" mask gets cv::circle(mask, pt*0.1,
+ *      int(min(rows/10, cols/10) * kptrad), 255, FILLED) for every keypoint and the "matches" mask for every keypoint with
+ *      matched[k] != 0 (the caller evaluates `lmId != 0 [&& lmIds.count(lmId)]`); the outputs are
+ *      countNonZero(matches & detections) and countNonZero(matches | detections) per view. The caller sums them over
+ *      the cameras of a multiframe and divides, as the reference does (kptrad = 0.09, Frontend.cpp:104). */
+typedef struct { int32_t image_rows, image_cols, first_keypoint, n_keypoints; } okb_overlap_view_t;
+/* xy: n_keypoints x 2 floats (cv::KeyPoint::pt of all views, concatenated), matched: n_keypoints bytes. Synchronous. */
+int okb_overlap_counts(okb_context_t* ctx, int n_views, const okb_overlap_view_t* views, int n_keypoints, const float* xy,
+                       const uint8_t* matched, double kptrad, int32_t* out_intersection, int32_t* out_union);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,7 @@ void okb_destroy(okb_context_t* ctx)
   for (int i = 0; i < ctx->n_cams; i++) detect_free_camera(ctx, i);
   match_free(ctx);
   prepare_free(ctx);
+  aux_free(ctx);
   if (ctx->stereo_scratch) cudaFree(ctx->stereo_scratch);
   tables_free(ctx);
   delete ctx;

@@ -162,6 +162,7 @@ inline bool host_pinned(const void* p)
   return at.type == cudaMemoryTypeHost;
 }
 void prepare_free(okb_context* ctx);
+void aux_free(okb_context* ctx);
 int tables_init(okb_context* ctx, float pattern_scale);
 void tables_free(okb_context* ctx);
 }  // namespace okb

@@ -191,6 +191,76 @@ class Frontend:
             out[k] = out[k][:nr]
         return out
 
+    # ---- K1: keyframe-overlap masks (Frontend::doWeNeedANewKeyframe, ViSlamBackend::overlapFraction)
+    keyframeInsertionOverlapThreshold_ = np.float32(0.55)   # Frontend.cpp:145
+    kptrad = 0.09                                           # Frontend.cpp:104, ViSlamBackend.hpp:684
+
+    def _overlap_counts(self, views, kptrad=None):
+        """views: (image_rows, image_cols, xy (n, 2) float32, matched (n,) bool). One device call for all of them."""
+        vs = (_l.OverlapView * len(views))()
+        xy, m, first = [], [], 0
+        for i, (r, c, p, f) in enumerate(views):
+            vs[i] = _l.OverlapView(int(r), int(c), first, len(p)); first += len(p)
+            xy.append(np.asarray(p, np.float32).reshape(-1, 2)); m.append(np.asarray(f, np.uint8))
+        xy = np.ascontiguousarray(np.concatenate(xy)) if views else np.zeros((0, 2), np.float32)
+        m = np.ascontiguousarray(np.concatenate(m)) if views else np.zeros(0, np.uint8)
+        inter = np.zeros(len(views), np.int32); uni = np.zeros(len(views), np.int32)
+        check(_l.lib().okb_overlap_counts(self._ctx, len(views), vs, len(m), ptr(xy), ptr(m), self.kptrad if kptrad is None else kptrad,
+                                          ptr(inter), ptr(uni)))
+        return inter, uni
+
+    @staticmethod
+    def _views_of(mf, matched_of):
+        out = []
+        for fr in mf.frames:
+            xy = np.stack([fr.keypoints["x"], fr.keypoints["y"]], 1) if len(fr.keypoints) else np.zeros((0, 2), np.float32)
+            out.append((fr.image.shape[0], fr.image.shape[1], xy, matched_of(fr)))
+        return out
+
+    def doWeNeedANewKeyframe(self, numFramesInEstimator, currentFrame, otherFrames, isInitialized=True):
+        """Frontend::doWeNeedANewKeyframe (Frontend.cpp:1058-1167). otherFrames = the multiframes of estimator.keyFrames()
+        + loopClosureFrames() + keyframes in the IMU window (the caller's bookkeeping, :1105-1115)."""
+        if numFramesInEstimator < 4:
+            return True
+        if not isInitialized:
+            return False
+        lmIds = set()
+        for fr in currentFrame.frames:
+            lmIds.update(int(x) for x in fr.landmarkIds if x != 0)
+        ids = np.array(sorted(lmIds), np.uint64)
+        views = self._views_of(currentFrame, lambda fr: fr.landmarkIds != 0)
+        for mf in otherFrames:
+            views += self._views_of(mf, lambda fr: (fr.landmarkIds != 0) & np.isin(fr.landmarkIds, ids))
+        inter, uni = self._overlap_counts(views)
+        nc = currentFrame.numFrames()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            overlap = np.float64(inter[:nc].sum()) / np.float64(uni[:nc].sum())
+            overlapOthers = np.float64(0.0)
+            pos = nc
+            for mf in otherFrames:
+                n = mf.numFrames()
+                x = np.float64(inter[pos:pos + n].sum()) / np.float64(uni[pos:pos + n].sum()); pos += n
+                overlapOthers = x if overlapOthers < x else overlapOthers   # std::max(overlapOthers, x)
+        overlap = overlap if overlap < overlapOthers else overlapOthers     # std::min(overlapOthers, overlap)
+        if currentFrame.numKeypoints() < 7 * nc:
+            return False
+        return not (np.float32(overlap) > self.keyframeInsertionOverlapThreshold_)
+
+    def overlapFraction(self, frameA, frameB, kptradius=0.09):
+        """ViSlamBackend::overlapFraction (ViSlamBackend.cpp:2341-2426)."""
+        lm = [set(int(x) for fr in f.frames for x in fr.landmarkIds if x != 0) for f in (frameA, frameB)]
+        matches = np.array(sorted(lm[0] & lm[1]), np.uint64)
+        if len(matches) == 0:
+            return 0.0
+        views = []
+        for f in (frameA, frameB):
+            views += self._views_of(f, lambda fr: np.isin(fr.landmarkIds, matches))
+        inter, uni = self._overlap_counts(views, kptradius)
+        n = frameA.numFrames()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            o = [np.float64(inter[i * n:(i + 1) * n].sum()) / np.float64(uni[i * n:(i + 1) * n].sum()) for i in range(2)]
+        return float(o[1] if o[1] < o[0] else o[0])   # std::min(overlap[0], overlap[1])
+
     def initialiseBriskFeatureDetectors(self):
         """Frontend::initialiseBriskFeatureDetectors (Frontend.cpp:2398-2417): (re)create the per-camera objects."""
         self.close()

@@ -290,3 +290,25 @@ def prepare_landmarks(hp_W, quality, obs_begin, obs, n_cams, T_WC_old, desc_tab,
         out[k] = out[k][:nr]
     out["cand_lm"] = np.repeat(np.arange(nl, dtype=np.int32), np.diff(out["desc_begin"]))
     return out
+
+
+def circle_filled(img, cx, cy, radius):
+    """cv::circle(img, (cx, cy), radius, 255, FILLED) restated (overlap_oracle.cpp); img: u8 2-D, modified in place."""
+    assert img.dtype == np.uint8 and img.flags.c_contiguous
+    L = lib()
+    L.okvo_circle_filled.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.okvo_circle_filled(img.ctypes.data, img.shape[1], img.shape[0], int(cx), int(cy), int(radius))
+    return img
+
+
+def overlap_counts(image_rows, image_cols, xy, matched, kptrad=0.09, masks=False):
+    """K1 oracle: (intersection, union) pixel counts of the matches / detections masks of one camera image."""
+    L = lib()
+    xy = _c(np.asarray(xy, np.float32).reshape(-1, 2), np.float32); matched = _c(matched, np.uint8)
+    rows, cols = image_rows // 10, image_cols // 10
+    det = np.zeros((rows, cols), np.uint8); mat = np.zeros((rows, cols), np.uint8)
+    i = C.c_int32(); u = C.c_int32()
+    L.okvo_overlap_counts.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+    L.okvo_overlap_counts(image_rows, image_cols, len(xy), _p(xy), _p(matched), float(kptrad), C.byref(i), C.byref(u), _p(det), _p(mat))
+    return (i.value, u.value, det, mat) if masks else (i.value, u.value)
