@@ -336,7 +336,7 @@ def bench_next_rows(fe, cfg):
     against the oracle transcription on one host core; outputs compared."""
     import oracle
     from okvis2_b200.synth import landmark_scene
-    s = landmark_scene(77, n_lm=50000, n_slots=50, n_cams=2, n_kp=cfg["max_kp"], W=cfg["W"], H=cfg["H"], f=cfg["f"])
+    s = landmark_scene(77, n_lm=50000, n_slots=50, n_cams=2, n_kp=cfg["max_kp"], W=cfg["W"], H=cfg["H"], f=cfg["f"], step=0.05)
     fe.configureFeatureStore(s["n_slots"], 64)
     for t in range(s["n_slots"] * 2):
         fe.storeFrame(t // 2, t % 2, s["desc_tab"][t], s["ray_tab"][t])

@@ -295,6 +295,21 @@ typedef struct { int32_t image_rows, image_cols, first_keypoint, n_keypoints; } 
 int okb_overlap_counts(okb_context_t* ctx, int n_views, const okb_overlap_view_t* views, int n_keypoints, const float* xy,
                        const uint8_t* matched, double kptrad, int32_t* out_intersection, int32_t* out_union);
 
+/* ---- B1: DBoW2 vocabulary descent with the FBrisk distance. Replaces
+ *      TemplatedVocabulary<FBrisk::TDescriptor, FBrisk>::transform(feature, word_id, weight, nid, levelsup) as reached from
+ *      the loop-closure queries of the front-end (okvis_frontend/src/Frontend.cpp:661-672,756-760,896-899) with
+ *      FBrisk::distance = brisk::Hamming::PopcntofXORed (okvis_frontend/src/FBrisk.cpp:64-67). external/DBoW2 is an empty
+ *      submodule in the reference tree: the descent is restated from the published algorithm (oracle/bow_oracle.py).
+ *      Vocabulary as stored in resources/small_voc.yml.gz: nodes IN FILE ORDER (nodeId, parentId, weight, descriptor of D
+ *      bytes; ids 1..n_nodes, 0 = root), words (wordId, nodeId). */
+int okb_bow_load(okb_context_t* ctx, int D, int k, int L, int n_nodes, const int32_t* node_id, const int32_t* parent_id,
+                 const double* weight, const uint8_t* desc, int n_words, const int32_t* word_id, const int32_t* word_node);
+/* desc: n x D bytes. out_word[i] = word id of the leaf reached, out_weight[i] its weight, out_node[i] = id of the node on
+ * the path at level L - levelsup (0 when that is the root), as DBoW2's direct index wants it. out_weight / out_node may be
+ * NULL. Synchronous. */
+int okb_bow_transform(okb_context_t* ctx, int n, const uint8_t* desc, int levelsup, int32_t* out_word, double* out_weight,
+                      int32_t* out_node);
+
 #ifdef __cplusplus
 }
 #endif

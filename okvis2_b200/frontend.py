@@ -261,6 +261,21 @@ class Frontend:
             o = [np.float64(inter[i * n:(i + 1) * n].sum()) / np.float64(uni[i * n:(i + 1) * n].sum()) for i in range(2)]
         return float(o[1] if o[1] < o[0] else o[0])   # std::min(overlap[0], overlap[1])
 
+    # ---- B1: DBoW2 vocabulary descent with the FBrisk distance
+    def loadVocabulary(self, k, L, node_id, parent_id, weight, descriptors, word_id, word_node):
+        """The node / word lists of a DBoW2 vocabulary file, nodes in file order (resources/small_voc.yml.gz)."""
+        a = lambda x, t: np.ascontiguousarray(x, t)
+        d = a(descriptors, np.uint8)
+        ni, pi, w, wi, wn = a(node_id, np.int32), a(parent_id, np.int32), a(weight, np.float64), a(word_id, np.int32), a(word_node, np.int32)
+        check(_l.lib().okb_bow_load(self._ctx, d.shape[1], int(k), int(L), len(ni), ptr(ni), ptr(pi), ptr(w), ptr(d), len(wi), ptr(wi), ptr(wn)))
+
+    def bowTransform(self, descriptors, levelsup=0):
+        """TemplatedVocabulary::transform for every row: (word ids, weights, node ids `levelsup` levels above the leaves)."""
+        d = np.ascontiguousarray(descriptors, np.uint8)
+        word = np.zeros(len(d), np.int32); weight = np.zeros(len(d), np.float64); node = np.zeros(len(d), np.int32)
+        check(_l.lib().okb_bow_transform(self._ctx, len(d), ptr(d), int(levelsup), ptr(word), ptr(weight), ptr(node)))
+        return word, weight, node
+
     def initialiseBriskFeatureDetectors(self):
         """Frontend::initialiseBriskFeatureDetectors (Frontend.cpp:2398-2417): (re)create the per-camera objects."""
         self.close()

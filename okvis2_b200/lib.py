@@ -94,6 +94,8 @@ _PROTOS = {
     "okb_store_frame": (i32, [vp, i32, i32, i32, vp, vp]),
     "okb_store_frame_from_last": (i32, [vp, i32, i32, i32]),
     "okb_prepare_landmarks": (i32, [vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "okb_bow_load": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
+    "okb_bow_transform": (i32, [vp, i32, vp, i32, vp, vp, vp]),
     "okb_overlap_counts": (i32, [vp, i32, vp, i32, vp, vp, f64, vp, vp]),
     "okb_prepared_device": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]),
 }

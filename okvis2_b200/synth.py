@@ -175,7 +175,7 @@ def stereo_scene(seed, n0, n1, D=64, f=458.0, baseline=0.11, flip_p=0.04, frac_m
                 T_CW0=T_CW(C0, r0), T_CW1=T_CW(C1, r1), idx0=i0, idx1=i1, f=f)
 
 
-def landmark_scene(seed, n_lm=2000, n_slots=10, n_cams=2, n_kp=600, D=64, W=752, H=480, f=458.0):
+def landmark_scene(seed, n_lm=2000, n_slots=10, n_cams=2, n_kp=600, D=64, W=752, H=480, f=458.0, step=0.35):
     """Synthetic map for the landmark-candidate preparation (P1): a camera rig moving along x through a cloud of
     landmarks, every landmark observed by a random subset of the (frame slot, camera) views. Poses are packed as 12
     doubles (C_WC row-major, r_WC). Returns the inputs of Frontend.prepareLandmarksToMatch / oracle.prepare_landmarks."""
@@ -190,13 +190,13 @@ def landmark_scene(seed, n_lm=2000, n_slots=10, n_cams=2, n_kp=600, D=64, W=752,
     T_WC_old = np.zeros((n_slots, n_cams, 12))
     for s in range(n_slots):
         C = rot(*(0.05 * rng.standard_normal(3)))
-        r = np.array([0.35 * s, 0.0, 0.0]) + 0.05 * rng.standard_normal(3)
+        r = np.array([step * s, 0.0, 0.0]) + 0.05 * rng.standard_normal(3)
         for c in range(n_cams):
             Cc = C @ rot(0.0, 0.02 * c, 0.0)
             T_WC_old[s, c, :9] = Cc.ravel(); T_WC_old[s, c, 9:] = r + C @ np.array([0.11 * c, 0.0, 0.0])
     # current view: a little beyond the last slot
     C1 = rot(*(0.05 * rng.standard_normal(3)))
-    r1 = np.array([0.35 * n_slots, 0.02, -0.01])
+    r1 = np.array([step * n_slots, 0.02, -0.01])
     T_WC1 = np.concatenate([C1.ravel(), r1]); T_CW1 = np.concatenate([C1.T.ravel(), -(C1.T @ r1)])
     # landmarks: mostly in front (z = 2..15 m), some behind / far off axis / at the w < 0 branch / near the singularity
     p = np.stack([rng.uniform(-8, 12, n_lm), rng.uniform(-5, 5, n_lm), rng.uniform(1.0, 15.0, n_lm)], 1)

@@ -1,0 +1,52 @@
+"""oracle/bow_oracle.py -- TEST INFRASTRUCTURE ONLY (CPU oracle of B1; never on the product path).
+
+Restatement of DBoW2::TemplatedVocabulary<FBrisk::TDescriptor, FBrisk>::transform(feature, word_id, weight, nid, levelsup)
+with F::distance = FBrisk::distance (reference okvis_frontend/src/FBrisk.cpp:64-67: popcount of the XOR over L/16 128-bit
+words). external/DBoW2 (dorian3d/DBoW2, patched by external/patches/DBoW2) is an EMPTY submodule in /root/reference; the
+descent below follows the published TemplatedVocabulary.h: start at the root, `final_id = children[0]`, replace it by a
+later child only when its distance is strictly smaller, repeat until a leaf; `nid` is the node at level L - levelsup.
+Children are in the order the nodes are listed in the vocabulary file (load() appends them to their parent in that order).
+PARITY UNPINNED against DBoW2 itself (no golden word ids exist in the reference tree); pinned facts: node descriptors,
+parents, weights and word ids of resources/small_voc.yml.gz (tests/golden/voc_tree.npz, voc_descriptors.npy)."""
+import numpy as np
+
+_PC = np.array([bin(i).count("1") for i in range(256)], np.int32)
+
+
+class Vocabulary:
+    def __init__(self, k, L, node_id, parent_id, weight, desc, word_id, word_node):
+        self.k, self.L = int(k), int(L)
+        n = int(max(node_id))
+        self.children = [[] for _ in range(n + 1)]
+        self.desc = np.zeros((n + 1, desc.shape[1]), np.uint8)
+        self.weight = np.zeros(n + 1)
+        self.word = -np.ones(n + 1, np.int64)
+        for i, (nid, pid) in enumerate(zip(node_id, parent_id)):
+            self.children[int(pid)].append(int(nid))
+            self.desc[int(nid)] = desc[i]; self.weight[int(nid)] = weight[i]
+        for w, nid in zip(word_id, word_node):
+            self.word[int(nid)] = int(w)
+
+    def distance(self, a, b):
+        return float(_PC[np.bitwise_xor(a, b)].sum())
+
+    def transform(self, feature, levelsup=0):
+        nid_level = self.L - levelsup
+        nid = 0
+        final_id = 0
+        current_level = 0
+        while True:
+            current_level += 1
+            nodes = self.children[final_id]
+            final_id = nodes[0]
+            best_d = self.distance(feature, self.desc[final_id])
+            for cid in nodes[1:]:
+                d = self.distance(feature, self.desc[cid])
+                if d < best_d:
+                    best_d = d
+                    final_id = cid
+            if current_level == nid_level:
+                nid = final_id
+            if not self.children[final_id]:
+                break
+        return int(self.word[final_id]), float(self.weight[final_id]), nid
