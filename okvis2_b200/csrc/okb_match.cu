@@ -162,10 +162,13 @@ __device__ __forceinline__ uint32_t hamming(const uint4 (&qd)[D16], uint4 (*s_de
 template <int D16>
 __device__ __forceinline__ uint32_t hamming_bounded(const uint4 (&qd)[D16], uint4 (*s_desc)[kTile], int ci, bool valid, uint32_t best)
 {
-  constexpr int H = (D16 + 1) / 2;
+  // The LAST 32 bytes go first: BRISK's later short pairs discriminate better (measured on the synthetic stereo set:
+  // a 32-candidate chunk still holds a partial distance < 60 in 2 % of the cases after bytes 32..63, in 48 % after
+  // bytes 0..31), so the early exit almost always saves half of the popcounts.
+  constexpr int H = D16 / 2;
   uint32_t d = 0;
 #pragma unroll
-  for (int w = 0; w < H; w++) {
+  for (int w = H; w < D16; w++) {
     const uint4 c = s_desc[w][ci];
     d += __popcll(((unsigned long long)(qd[w].x ^ c.x) << 32) | (qd[w].y ^ c.y));
     d += __popcll(((unsigned long long)(qd[w].z ^ c.z) << 32) | (qd[w].w ^ c.w));
@@ -173,7 +176,7 @@ __device__ __forceinline__ uint32_t hamming_bounded(const uint4 (&qd)[D16], uint
   if (!valid) d = 0xffffu;
   if (!__any_sync(0xffffffffu, d < best)) return d;
 #pragma unroll
-  for (int w = H; w < D16; w++) {
+  for (int w = 0; w < H; w++) {
     const uint4 c = s_desc[w][ci];
     d += __popcll(((unsigned long long)(qd[w].x ^ c.x) << 32) | (qd[w].y ^ c.y));
     d += __popcll(((unsigned long long)(qd[w].z ^ c.z) << 32) | (qd[w].w ^ c.w));
@@ -200,6 +203,7 @@ struct M1Args {
   int cell, gx, gy;             // grid
   int32_t* cell_off;            // [frames][kMaxCells + 1]
   int32_t* cell_list;           // [frames][nq]
+  double2* cell_xy;             // [frames][nq]: keypoint coordinates in cell-list order (one 16-byte load per gate test)
   unsigned long long* best;     // [frames][nq]
   uint32_t* out_dist; int32_t* out_idx;
 };
@@ -252,7 +256,10 @@ __global__ void __launch_bounds__(256) k_m1_bin(M1Args a)
   for (int k = threadIdx.x; k < nq; k += blockDim.x) {
     if (a.q_use == nullptr || a.q_use[k]) {
       double x, y; m1_kp_xy(a, fq, k, x, y);
-      if (x == x && y == y) list[atomicAdd(&cnt[m1_cell_of(a, x, y)], 1)] = k;
+      if (x == x && y == y) {
+        const int pos = atomicAdd(&cnt[m1_cell_of(a, x, y)], 1);
+        list[pos] = k; a.cell_xy[fq + pos] = make_double2(x, y);
+      }
     }
   }
 }
@@ -283,11 +290,11 @@ __global__ void __launch_bounds__(128) k_m1_match(M1Args a)
     if (cx0 > cx1) break;
     const int beg = off[cy * a.gx + cx0], end = off[cy * a.gx + cx1 + 1];   // cells of one row are contiguous
     for (int i = beg; i < end; i++) {
-      const int k = list[i];
-      double kx, ky; m1_kp_xy(a, fq, k, kx, ky);
-      const double dx = px - kx, dy = py - ky;
+      const double2 kxy = __ldg(&a.cell_xy[fq + i]);
+      const double dx = px - kxy.x, dy = py - kxy.y;
       const double d2 = dx * dx + dy * dy;
       if (d2 > a.thr_sq) continue;
+      const int k = list[i];
       if (!loaded) { load_query<D16>(a.c_desc, c, cd); loaded = true; }
       const uint4* qp = reinterpret_cast<const uint4*>(a.q_desc) + (fq + k) * D16;
       uint32_t d = 0;
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(256) k_match_place(int n_lm, const int32_t* lm
 
 // M2 / M3 / M4: sequential-order replay with gates
 template <int D16, int MODE>
-__global__ void __launch_bounds__(256) k_match_gated(MatchArgs a)
+__global__ void __launch_bounds__(256, 4) k_match_gated(MatchArgs a)
 {
   __shared__ uint4 s_desc2[2][D16][kTile];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -668,7 +675,7 @@ int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc,
     a.lm_proj = A.in(lm_proj, (size_t)n_lm * 2); a.lm_is3d = A.in(lm_is3d, (size_t)n_lm);
     in_end = A.off;
     a.cell_off = A.out<int32_t>(kMaxCells + 1, nullptr); a.cell_list = A.out<int32_t>(n_kp, nullptr);
-    a.best = A.out<unsigned long long>(n_kp, nullptr);
+    a.best = A.out<unsigned long long>(n_kp, nullptr); a.cell_xy = A.out<double2>(n_kp, nullptr);
     a.out_dist = A.out<uint32_t>(n_kp, &o_dist); a.out_idx = A.out<int32_t>(n_kp, &o_idx);
     if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
   }
@@ -824,7 +831,7 @@ int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand
   a.q_desc = ws.d_desc; a.q_kp = ws.d_kp;
   a.nc = n_cand; a.c_desc = d_cand_desc; a.c_lm = d_cand_lm; a.lm_proj = d_lm_proj; a.lm_is3d = d_lm_is3d;
   a.thr = match_threshold; a.thr_sq = reprojection_threshold * reprojection_threshold;
-  a.cell_off = ws.d_m1_cell_off; a.cell_list = ws.d_m1_cell_list; a.best = ws.d_m1_best;
+  a.cell_off = ws.d_m1_cell_off; a.cell_list = ws.d_m1_cell_list; a.best = ws.d_m1_best; a.cell_xy = ws.d_m1_cell_xy;
   a.out_dist = d_out_dist; a.out_idx = d_out_lm;
   return m1_launch(ctx, a, 64, n_frames, ws.stream);
 }
