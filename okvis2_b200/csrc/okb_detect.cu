@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ ResizeJo
 
 // ---------------------------------------------------------------------------------------------------------------
 // score map tiling
-constexpr int kTileW = 64, kTileH = 32;   // one warp per tile row, one lane per horizontal pixel pair
+constexpr int kTileW = 64, kTileH = 64;   // one warp per tile row (8 rows per warp), one lane per horizontal pixel pair
 
 // per-layer regions of the candidate list (so that a warp of the refinement kernel sees candidates of ONE layer and
 // follows one code path); cand_count is [frames][kMaxLayers]
@@ -222,7 +222,7 @@ __device__ __forceinline__ bool cells_any(const uint32_t* cells /*layer*/, int l
   return false;
 }
 
-// Fused score + non-max suppression. Tile = kTileW x kTileH (64 x 32) pixels of one layer of one frame, 256 threads.
+// Fused score + non-max suppression. Tile = kTileW x kTileH (64 x 64) pixels of one layer of one frame, 256 threads.
 //   1. the image tile with its ring halo (3 rows above/below, 16 bytes left/right: TMA wants 16-byte granular boxes
 //      AND box origins) arrives in shared memory by ONE TMA bulk tensor copy, zero outside the image;
 //   2. the bytes are expanded once into two 16x2 planes, E[r][k] = (p[2k], p[2k+1]) and O[r][k] = (p[2k+1], p[2k+2]):
@@ -253,12 +253,16 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
                                                              int threshold, int32_t* status, uint32_t* tie_cells)
 {
   __shared__ __align__(128) uint8_t tile[kImgH][kImgW];
-  __shared__ __align__(16) uint32_t pe[kImgH][kPlaneW];
-  __shared__ __align__(16) uint32_t po[kImgH][kPlaneW];
+  __shared__ __align__(16) uint32_t planes[2][kImgH][kPlaneW];   // E and O; reused as the candidate list after the scoring
   __shared__ __align__(16) uint8_t sc[kTileH][kTileW];
-  __shared__ uint16_t strong[kTileH * kTileW];
-  __shared__ uint32_t out_list[kTileH * kTileW];
+  uint32_t (*pe)[kPlaneW] = planes[0];
+  uint32_t (*po)[kPlaneW] = planes[1];
+  uint32_t* out_list = &planes[0][0][0];   // kTileH * kTileW entries <= 2 * kImgH * kPlaneW; first written after the
+                                           // __syncthreads() that ends the scoring loop (the planes are dead by then)
+  static_assert(kTileH * kTileW <= 2 * kImgH * kPlaneW, "candidate list must fit into the planes");
   __shared__ __align__(8) uint64_t bar;
+  __shared__ uint16_t strong[kTileH * kTileW];
+  __shared__ uint32_t smask[kTileH][2];            // per tile row: ballots of the strong even / odd pixels
   __shared__ int n_strong, n_out, out_base, tma_failed;
   const int frame = blockIdx.y;
   const int layer = find_layer(tm, blockIdx.x);
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
   uint8_t* score = score_block + (size_t)frame * dl.frame_stride + d.offset;
   const int x0 = tx * kTileW, y0 = ty * kTileH;
   if (threadIdx.x == 0) { n_strong = 0; n_out = 0; tma_failed = 0; }
+  if (threadIdx.x < 2 * kTileH) (&smask[0][0])[threadIdx.x] = 0u;
   if (maps.use[layer]) {
     // TMA: one bulk tensor copy per CTA; out-of-image bytes arrive as zeros
     if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -322,38 +327,50 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
     *reinterpret_cast<uint2*>(&po[r][2 * m]) = o;
   }
   __syncthreads();
-  // ---- dense scores: warp = tile row, lane = pixel pair (x0 + 2*lane, +1)
+  // ---- dense scores: warp = tile row, lane = pixel pair (x0 + 2*lane, +1). Every ring sample is one LDS.32 at a
+  //      compile-time offset from a single per-lane pointer (the two planes are one array).
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool edge_tile = x0 < 3 || y0 < 3 || x0 + kTileW > d.w - 3 || y0 + kTileH > d.h - 3;
+  constexpr int PW = kPlaneW, OO = kImgH * kPlaneW;          // row pitch of a plane, offset of the O plane (words)
+  const int xg = x0 + 2 * lane;
+  // scores are zero in the 3-pixel margin of the layer: per-lane column mask, per-row on/off
+  const uint32_t colmask = ((xg >= 3 && xg < d.w - 3) ? 0x0000ffffu : 0u) | ((xg + 1 >= 3 && xg + 1 < d.w - 3) ? 0xffff0000u : 0u);
+  const int rows_here = min(kTileH, d.h - y0);
   const uint32_t thr2 = (uint32_t)(0x8000 - min(max(threshold, 1), 0x7fff)) * 0x00010001u;
+  {
+    const uint32_t* p = &planes[0][warp][2 + lane];          // plane word of this pair (staged byte 16 + 2*lane), tile row `warp`
+    uint8_t* gout = score + (size_t)(y0 + warp) * d.pitch + xg;   // pitch is a multiple of 64
+    uint8_t* sout = &sc[warp][2 * lane];
 #pragma unroll 1
-  for (int row = warp; row < kTileH; row += kScoreThreads / 32) {
-    const int y = y0 + row;
-    if (y >= d.h) break;                       // warp-uniform
-    const int k = 2 + lane;                    // plane word of this pair (staged byte 16 + 2*lane)
-    uint32_t v[16];
-    v[0] = po[row + 3][k - 2];  v[1] = po[row + 2][k - 2];  v[2] = pe[row + 1][k - 1];  v[3] = po[row][k - 1];
-    v[4] = pe[row][k];          v[5] = po[row][k];          v[6] = pe[row + 1][k + 1];  v[7] = po[row + 2][k + 1];
-    v[8] = po[row + 3][k + 1];  v[9] = po[row + 4][k + 1];  v[10] = pe[row + 5][k + 1]; v[11] = po[row + 6][k];
-    v[12] = pe[row + 6][k];     v[13] = po[row + 6][k - 1]; v[14] = pe[row + 5][k - 1]; v[15] = po[row + 4][k - 2];
-    uint32_t s = b0_pair(v, pe[row + 3][k]);
-    if (edge_tile) {                           // CTA-uniform: scores are zero in the 3-pixel margin of the layer
-      const int x = x0 + 2 * lane;
-      const bool yok = y >= 3 && y < d.h - 3;
-      if (!(yok && x >= 3 && x < d.w - 3)) s &= 0xffff0000u;
-      if (!(yok && x + 1 >= 3 && x + 1 < d.w - 3)) s &= 0x0000ffffu;
-    }
-    const uint16_t packed = (uint16_t)__byte_perm(s, 0, 0x4420);
-    *reinterpret_cast<uint16_t*>(&sc[row][2 * lane]) = packed;
-    *reinterpret_cast<uint16_t*>(score + (size_t)y * d.pitch + x0 + 2 * lane) = packed;   // pitch is a multiple of 64
-    const uint32_t hit = (s + thr2) & 0x80008000u;   // per half: score >= threshold (scores <= 254)
-    if (hit) {
-      if (hit & 0x8000u) strong[atomicAdd(&n_strong, 1)] = (uint16_t)(row * kTileW + 2 * lane);
-      if (hit & 0x80000000u) strong[atomicAdd(&n_strong, 1)] = (uint16_t)(row * kTileW + 2 * lane + 1);
+    for (int row = warp; row < rows_here; row += kScoreThreads / 32) {
+      uint32_t v[16];
+      v[0] = p[OO + 3 * PW - 2];  v[1] = p[OO + 2 * PW - 2];  v[2] = p[1 * PW - 1];       v[3] = p[OO - 1];
+      v[4] = p[0];                v[5] = p[OO];               v[6] = p[1 * PW + 1];       v[7] = p[OO + 2 * PW + 1];
+      v[8] = p[OO + 3 * PW + 1];  v[9] = p[OO + 4 * PW + 1];  v[10] = p[5 * PW + 1];      v[11] = p[OO + 6 * PW];
+      v[12] = p[6 * PW];          v[13] = p[OO + 6 * PW - 1]; v[14] = p[5 * PW - 1];      v[15] = p[OO + 4 * PW - 2];
+      uint32_t s = b0_pair(v, p[3 * PW]);
+      const int y = y0 + row;
+      s &= (y >= 3 && y < d.h - 3) ? colmask : 0u;
+      const uint16_t packed = (uint16_t)__byte_perm(s, 0, 0x4420);
+      *reinterpret_cast<uint16_t*>(sout) = packed;
+      *reinterpret_cast<uint16_t*>(gout) = packed;
+      // strong pixels (score >= threshold; scores <= 254 so the 16-bit adds cannot carry): two ballots per row
+      const uint32_t hit = s + thr2;
+      const unsigned m_even = __ballot_sync(0xffffffffu, hit & 0x8000u), m_odd = __ballot_sync(0xffffffffu, hit & 0x80000000u);
+      if (lane == 0) { smask[row][0] = m_even; smask[row][1] = m_odd; }
+      p += (kScoreThreads / 32) * PW; gout += (size_t)(kScoreThreads / 32) * d.pitch; sout += (kScoreThreads / 32) * kTileW;
     }
   }
   __syncthreads();
-  // ---- 3x3 non-max test of the strong pixels
+  // ---- the strong pixels (a few per cent) are compacted into a dense list, then get the 3x3 non-max test one per thread
+  if (threadIdx.x < 2 * kTileH) {
+    uint32_t m = (&smask[0][0])[threadIdx.x];
+    if (m) {
+      int pos = atomicAdd(&n_strong, __popc(m));
+      const int r = threadIdx.x >> 1, odd = threadIdx.x & 1;
+      while (m) { const int b = __ffs(m) - 1; m &= m - 1; strong[pos++] = (uint16_t)(r * kTileW + 2 * b + odd); }
+    }
+  }
+  __syncthreads();
   const int ns = n_strong;
   for (int i = threadIdx.x; i < ns; i += kScoreThreads) {
     const int r = strong[i] / kTileW, x = strong[i] % kTileW;
@@ -366,7 +383,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_consta
         if (dx == 0 && dy == 0) continue;
         const int rr = r + dy, xx = x + dx;
         if ((unsigned)rr < (unsigned)kTileH && (unsigned)xx < (unsigned)kTileW) {
-          const int v = sc[rr][xx];   // rows of the tile below the image hold stale data only when y >= h-3: c is 0 there
+          const int v = sc[rr][xx];   // rows at / below the image end are never neighbours of a strong pixel (y < h - 3)
           if (v > c) is_c = false;
           if (v == c) tie = true;
         } else pending = true;
