@@ -1008,8 +1008,18 @@ __global__ void __launch_bounds__(1024) k_integral_cols(int W, int H, int32_t* i
   const int rows = (H + 31) / 32;
   const int y0 = 1 + warp * rows, y1 = min(y0 + rows, H + 1);
   int32_t* I = integral + (size_t)frame * ipitch * (H + 1);
+  constexpr int kKeep = 32;   // rows of a band kept in registers (H <= 1024): the band is read once, not twice
+  int vals[kKeep];
   int sum = 0;
-  if (x <= W) for (int y = y0; y < y1; y++) sum += I[(size_t)y * ipitch + x];
+  const bool in_regs = rows <= kKeep;
+  if (x <= W) {
+    if (in_regs) {
+#pragma unroll
+      for (int i = 0; i < kKeep; i++) { vals[i] = (y0 + i < y1) ? I[(size_t)(y0 + i) * ipitch + x] : 0; sum += vals[i]; }
+    } else {
+      for (int y = y0; y < y1; y++) sum += I[(size_t)y * ipitch + x];
+    }
+  }
   band[warp][lane] = sum;
   __syncthreads();
   if (warp == 0) {
@@ -1019,7 +1029,12 @@ __global__ void __launch_bounds__(1024) k_integral_cols(int W, int H, int32_t* i
   __syncthreads();
   if (x > W) return;
   int acc = band[warp][lane];
-  for (int y = y0; y < y1; y++) { acc += I[(size_t)y * ipitch + x]; I[(size_t)y * ipitch + x] = acc; }
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < kKeep; i++) if (y0 + i < y1) { acc += vals[i]; I[(size_t)(y0 + i) * ipitch + x] = acc; }
+  } else {
+    for (int y = y0; y < y1; y++) { acc += I[(size_t)y * ipitch + x]; I[(size_t)y * ipitch + x] = acc; }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
