@@ -499,13 +499,13 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = ps_bytes * B * passes / (ps_total_ms * 1e-3) / 1e9 if ps_total_ms > 0 else 0.0
     # DRAM traffic of the dominant kernel (k_score_nms, one launch = B images) from the committed ncu --set full capture
-    # profiles/r01_ncu_full_v7_score_nms_raw.csv (dram__bytes_read.sum 22.159 MB + dram__bytes_write.sum 0.241 MB), euroc config
-    traffic = 22.40e6 if args.config == "euroc" and B == 32 else None
+    # profiles/r01_ncu_full_v10_score_nms_raw.csv (dram__bytes_read.sum 22.218 MB + dram__bytes_write.sum 0.077 MB), euroc config
+    traffic = 22.30e6 if args.config == "euroc" and B == 32 else None
     ach_k = ps_bytes * B * passes / (score_total_ms * 1e-3) / 1e9 if score_total_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "kernel": "pyramid+score pass (k_resize launches + k_score_nms, TMA-staged tiles)", "bytes_per_image": int(ps_bytes),
                 "dominant_kernel": {"name": "k_score_nms", "ms_per_launch": score_total_ms / passes, "achieved_GBps": ach_k,
-                                    "frac": ach_k / peak, "limiter": "ALU pipe (73% busy, 64 lanes/clk/SM: 81 VIMNMX3.U16x2 per pixel pair = 49 us floor), not HBM"},
+                                    "frac": ach_k / peak, "limiter": "ALU pipe (79% busy, 64 lanes/clk/SM: 81 VIMNMX3.U16x2 per pixel pair = 49 us floor per 32 frames), not HBM"},
                 "images_per_pass": B, "ms_per_pass": ps_total_ms / passes, "launches_per_pass": ps_total_launches / passes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                 "measured": f"CUDA events on the launching stream, {roof_steps} extra steps right after the timed region with the two camera streams serialized (they overlap in the timed region)"}
