@@ -353,9 +353,27 @@ def bench_next_rows(fe, cfg):
                                    s["T_WC1"], s["T_CW1"], 1, intr, s["W"], s["H"])
     cpu_ms = (time.perf_counter() - t0) * 1e3
     same = all(np.array_equal(got[k], ref[k]) for k in ("lm", "lm_is3d", "desc_begin", "cand_desc", "kid", "lm_proj"))
-    return {"P1_prepare_landmarks": {"landmarks": 50000, "observations": int(len(s["obs"])), "kept": int(len(got["lm"])),
+    rows = {"P1_prepare_landmarks": {"landmarks": 50000, "observations": int(len(s["obs"])), "kept": int(len(got["lm"])),
                                      "pool_rows": int(len(got["cand_desc"])), "gpu_ms_host_buffers": gpu_ms, "cpu_port_ms_1_core": cpu_ms,
                                      "identical_to_oracle": bool(same)}}
+    # K1 (Frontend.cpp:1058-1167): the masks of the current frame + 10 keyframes, 2 cameras each, max_kp keypoints per view
+    rng = np.random.default_rng(3)
+    views = []
+    for _ in range(22):
+        xy = np.stack([rng.uniform(0, cfg["W"], cfg["max_kp"]), rng.uniform(0, cfg["H"], cfg["max_kp"])], 1).astype(np.float32)
+        views.append((cfg["H"], cfg["W"], xy, rng.random(cfg["max_kp"]) < 0.5))
+    inter, uni = fe._overlap_counts(views)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        inter, uni = fe._overlap_counts(views)
+    k1_gpu = (time.perf_counter() - t0) / 10 * 1e3
+    t0 = time.perf_counter()
+    ref = [oracle.overlap_counts(r, c, xy, m) for (r, c, xy, m) in views]
+    k1_cpu = (time.perf_counter() - t0) * 1e3
+    rows["K1_keyframe_overlap"] = {"views": len(views), "keypoints_per_view": cfg["max_kp"], "gpu_ms_host_buffers": k1_gpu,
+                                   "cpu_port_ms_1_core": k1_cpu,
+                                   "identical_to_oracle": bool(all((inter[i], uni[i]) == ref[i] for i in range(len(views))))}
+    return rows
 
 
 def main():
@@ -366,7 +384,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="euroc", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-lanes", type=int, default=2, help="independent sequences replayed concurrently in the e2e leg")
+    ap.add_argument("--e2e-lanes", "--lanes", dest="e2e_lanes", type=int, default=3,
+                    help="independent sequences in flight per GPU (own library handle each) in the value and e2e legs")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -399,6 +418,17 @@ def main():
         fe.setCameraModel(c, "radialtangential", (cfg["f"], cfg["f"] * 0.997), (W / 2 - 8.8 + 12 * c, H / 2 + 8.4 + 7 * c),
                           [-0.2834, 0.0740, 0.00019, 1.76e-05])
     ctx = fe.ctx
+    # further sequences in flight on this GPU: one library handle (own streams and workspaces) each. The single-CTA-per-frame
+    # kernels of one sequence (tie resolution, selection: 200 us on 32 SMs) leave most SMs to the others.
+    lanes = max(1, args.e2e_lanes)
+    fes = [fe]
+    for l in range(1, lanes):
+        f2 = Frontend(2, W, H, device=local_rank, max_batch=B)
+        f2.configure(threshold=cfg["threshold"], octaves=cfg["octaves"], max_keypoints=cfg["max_kp"])
+        for c in range(2):
+            f2.setCameraModel(c, "radialtangential", (cfg["f"], cfg["f"] * 0.997), (W / 2 - 8.8 + 12 * c, H / 2 + 8.4 + 7 * c),
+                              [-0.2834, 0.0740, 0.00019, 1.76e-05])
+        fes.append(f2)
     C_WC = [np.eye(3), np.eye(3)]; r_WC = [np.zeros(3), np.array([0.11, 0.0, 0.0])]
     # ---- synthetic inputs: ring * B stereo frames per rank (ring * B * 2 * W * H bytes > L2 so steps do not hit in L2)
     n_frames = ring * B
@@ -417,29 +447,32 @@ def main():
     cap = C.c_int(0)
     L_.okb_device_features(ctx, 0, None, None, None, C.byref(cap))
     kp_cap = cap.value
-    d_out = [dict(dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), lm=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda")) for _ in range(2)]
-    d_st = dict(k1=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"),
-                hp=torch.zeros((B, kp_cap, 4), dtype=torch.float64, device="cuda"), init=torch.zeros((B, kp_cap), dtype=torch.uint8, device="cuda"))
-    streams = [torch.cuda.ExternalStream(L_.okb_stream(ctx, c)) for c in range(2)]
+    mk_out = lambda: [dict(dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), lm=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda")) for _ in range(2)]
+    mk_st = lambda: dict(k1=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"),
+                         hp=torch.zeros((B, kp_cap, 4), dtype=torch.float64, device="cuda"), init=torch.zeros((B, kp_cap), dtype=torch.uint8, device="cuda"))
+    lane_out = [mk_out() for _ in range(lanes)]; lane_st = [mk_st() for _ in range(lanes)]
+    lane_streams = [[torch.cuda.ExternalStream(L_.okb_stream(f.ctx, c)) for c in range(2)] for f in fes]
+    streams = lane_streams[0]
 
     chain = [torch.cuda.Event() for _ in range(2)]
     serialize = [False]
 
-    def device_step(s):
+    def device_step(s, lane=0):
+        cx = fes[lane].ctx; d_out = lane_out[lane]; d_st = lane_st[lane]; st = lane_streams[lane]
         for c in range(2):
             # the two camera streams run concurrently: the latency-bound single-CTA-per-frame kernels of one camera
             # (tie resolution, selection) leave SMs free for the other camera's wide kernels
             if serialize[0]:
-                streams[c].wait_event(chain[1 - c])
+                st[c].wait_event(chain[1 - c])
             frames = d_img[c][(s % ring) * B:(s % ring + 1) * B]
-            okl.check(L_.okb_detect_describe_batch_device(ctx, c, B, frames.data_ptr()))
+            okl.check(L_.okb_detect_describe_batch_device(cx, c, B, frames.data_ptr()))
             dm = d_maps[c]
-            okl.check(L_.okb_match_map3d_device(ctx, c, B, len(dm["lm"]), dm["desc"].data_ptr(), dm["lm"].data_ptr(),
+            okl.check(L_.okb_match_map3d_device(cx, c, B, len(dm["lm"]), dm["desc"].data_ptr(), dm["lm"].data_ptr(),
                                                 len(dm["is3d"]), dm["proj"].data_ptr(), dm["is3d"].data_ptr(), 20.0, 60,
                                                 d_out[c]["dist"].data_ptr(), d_out[c]["lm"].data_ptr()))
-            chain[c].record(streams[c])
+            chain[c].record(st[c])
         # M4: stereo matching camera 0 -> camera 1 of every frame of the batch (back-projection on the device)
-        okl.check(L_.okb_match_stereo_device(ctx, 0, 1, B, C_WC[0].ctypes.data, r_WC[0].ctypes.data, C_WC[1].ctypes.data,
+        okl.check(L_.okb_match_stereo_device(cx, 0, 1, B, C_WC[0].ctypes.data, r_WC[0].ctypes.data, C_WC[1].ctypes.data,
                                              r_WC[1].ctypes.data, 60, d_st["k1"].data_ptr(), d_st["dist"].data_ptr(),
                                              d_st["hp"].data_ptr(), d_st["init"].data_ptr()))
 
@@ -451,20 +484,24 @@ def main():
 
     # ---- value: device-resident, device-timed
     sampler = ClockSampler(local_rank); sampler.start()   # samples clocks through the warm-up, value, roofline and e2e legs
-    for s in range(warm):
-        device_step(s)
-    okl.check(L_.okb_sync(ctx))
+    for s in range(warm * lanes):
+        device_step(s, s % lanes)
+    for f in fes:
+        okl.check(L_.okb_sync(f.ctx))
     barrier()
-    launches0 = L_.okb_launch_count(ctx)
+    launches0 = sum(L_.okb_launch_count(f.ctx) for f in fes)
+    # all streams are idle here: the event on lane 0 precedes every kernel of the timed region; step s is the next batch of
+    # sequence s % lanes (exactly args.steps steps in total)
     ev0 = torch.cuda.Event(enable_timing=True); ev0.record(streams[0])
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(2 * lanes)]
     for s in range(args.steps):
-        device_step(warm + s)
-    for c in range(2):
-        ends[c].record(streams[c])
+        device_step(warm * lanes + s, s % lanes)
+    for l in range(lanes):
+        for c in range(2):
+            ends[2 * l + c].record(lane_streams[l][c])
     barrier()
     dev_ms = max(ev0.elapsed_time(e) for e in ends)
-    launches = L_.okb_launch_count(ctx) - launches0
+    launches = sum(L_.okb_launch_count(f.ctx) for f in fes) - launches0
     # ---- kernel-level timing for the roofline: a few extra steps with the two camera streams serialized, so that the
     #      CUDA events around the pyramid+score launches (recorded on the launching stream inside the library) time those
     #      kernels alone and not whatever the other camera's stream runs next to them
@@ -580,15 +617,6 @@ def main():
     # (ii) `lanes` independent sequences replayed concurrently on this GPU (BASELINE config 5 interleaves sequences), each
     #      through its own library handle and host-thread pair: exactly args.steps steps in total, split over the lanes.
     #      One lane's H2D / D2H copies overlap the other lane's kernels.
-    lanes = max(1, args.e2e_lanes)
-    fes = [fe]
-    for l in range(1, lanes):
-        f2 = Frontend(2, W, H, device=local_rank, max_batch=B)
-        f2.configure(threshold=cfg["threshold"], octaves=cfg["octaves"], max_keypoints=cfg["max_kp"])
-        for c in range(2):
-            f2.setCameraModel(c, "radialtangential", (cfg["f"], cfg["f"] * 0.997), (W / 2 - 8.8 + 12 * c, H / 2 + 8.4 + 7 * c),
-                              [-0.2834, 0.0740, 0.00019, 1.76e-05])
-        fes.append(f2)
     per_lane = [args.steps // lanes + (1 if l < args.steps % lanes else 0) for l in range(lanes)]
     ios = [make_io(per_lane[l], l, lanes) for l in range(lanes)]
     ctx_arr = (C.c_void_p * lanes)(*[f.ctx for f in fes])
@@ -639,6 +667,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": args.config, "stereo_frames_per_step_per_gpu": B, "l2_policy": f"inputs larger than L2: ring of {ring} batches = {in_bytes >> 20} MiB per GPU",
                            "parallelism": "replicas (independent sequences per GPU)" if world > 1 else "single GPU",
+                           "sequences_in_flight_per_gpu": lanes,
                            **{k: cfg[k] for k in ("W", "H", "max_kp", "threshold", "octaves", "n_lm")}},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "next_rows": next_rows}
