@@ -101,6 +101,8 @@ struct MatchArgs {
   size_t q_stride, proj_stride, c_stride;
   const int32_t* q_count; const int32_t* c_count;   // per-frame counts (device) or nullptr
   uint32_t* out_dist; int32_t* out_idx; double* out_hp; uint8_t* out_init; int32_t* out_ctr;
+  // M4 scan/gate split: when set, k_match_gated only runs for frames whose hit list overflowed (hit_cnt[frame] > hit_cap)
+  const int32_t* hit_cnt; int hit_cap;
 };
 
 constexpr int kTile = 256;
@@ -397,6 +399,7 @@ template <int D16, int MODE>
 __global__ void __launch_bounds__(256, 4) k_match_gated(MatchArgs a)
 {
   __shared__ uint4 s_desc2[2][D16][kTile];
+  if (a.hit_cnt && a.hit_cnt[blockIdx.y] <= a.hit_cap) return;   // this frame was handled by the scan/gate split
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 8 + warp;
   // batched device form: blockIdx.y = frame, per-frame strides (elements) and counts; all zero/null for the host form
@@ -547,6 +550,125 @@ __global__ void __launch_bounds__(256, 4) k_match_gated(MatchArgs a)
     else { hp[0] = hp[1] = hp[2] = hp[3] = 0.0; }
     if (a.out_init) a.out_init[fq + q] = best_init ? 1 : 0;
     if (MODE == MODE_M2 && a.out_ctr && ctr) atomicAdd(a.out_ctr, ctr);
+  }
+}
+
+// ---- M4, device-resident batched form, as scan + gate ------------------------------------------------------------------
+// The gate of M4 is a pure function of the pair, so the loop's result per query is min (distance, candidate index) over
+// the candidates with distance < threshold that pass the gate. Pairs below the threshold are rare (a handful per query),
+// which splits the work into
+//   k_m4_scan    Hamming only, register blocked: a thread keeps ONE candidate descriptor in registers, the queries of the
+//                frame stream through shared memory (broadcast LDS); the better-discriminating half of the descriptor is
+//                popcounted first and the other half only when some lane of the warp is still below the threshold. Hits
+//                (distance < threshold) are appended to a per-frame list. ~30 instructions per (warp, query), 48 registers.
+//   k_m4_gate    one thread per hit: the reference's gate (triangulateFast etc., fp64), 64-bit atomicMin of
+//                (distance << 32 | candidate) per query = first minimum in candidate order;
+//   k_m4_finish  one thread per query: outputs; the triangulated point of the winner is recomputed (same function, same
+//                inputs, same result).
+// A frame whose list overflows (hit_cnt > hit_cap; pathological inputs) is redone by the sequential-replay kernel
+// k_match_gated, which is launched behind and returns at once for all other frames.
+struct M4Gate { bool pass, parallel; V3 hp; };
+__device__ __forceinline__ M4Gate m4_gate(const MatchArgs& a, size_t fq, size_t fc, int q, int c)
+{
+  M4Gate g; g.pass = false; g.parallel = false; g.hp = V3{0, 0, 0};
+  if (!a.c_valid[fc + c]) return g;
+  const V3 eq = v3(a.q_e + 3 * (fq + q)), e1 = v3(a.c_e + 3 * (fc + c));
+  double c26 = a.q_cos26[fq + q], c6 = a.q_cos6[fq + q];
+  const double s1 = a.c_sof[fc + c];
+  if (a.q_sof[fq + q] < s1) { c26 = a.c_cos26[fc + c]; c6 = a.c_cos6[fc + c]; }
+  const Tri t = triangulate_fast(v3(a.r0), eq, v3(a.r1), e1, c26, c6);
+  g.pass = t.valid; g.parallel = t.parallel; g.hp = t.p;
+  if (!g.parallel) {
+    if (depth_in(a.T0, g.hp) < 0.05) g.pass = false;
+    if (depth_in(a.T1, g.hp) < 0.05) g.pass = false;
+    if (dot(eq, e1) < 0.8) g.pass = false;
+  }
+  return g;
+}
+
+template <int D16>
+__global__ void __launch_bounds__(256) k_m4_scan(MatchArgs a, uint2* hits, int32_t* hit_cnt)
+{
+  constexpr int kQT = 128, H = D16 / 2;
+  __shared__ uint4 sq[kQT][D16];
+  __shared__ uint8_t s_act[kQT];
+  const int frame = blockIdx.y;
+  const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
+  const int nq = min(a.q_count[frame], a.nq), nc = min(a.c_count[frame], a.nc);
+  if ((int)(blockIdx.x * blockDim.x) >= nc) return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid_c = c < nc && a.c_valid[fc + c];
+  uint4 cd[D16];
+#pragma unroll
+  for (int w = 0; w < D16; w++) cd[w] = valid_c ? __ldg(reinterpret_cast<const uint4*>(a.c_desc) + (fc + c) * D16 + w) : make_uint4(0, 0, 0, 0);
+  {
+    const int q0 = blockIdx.z * kQT;   // one chunk of queries per CTA: (candidate tile, frame, query chunk) fills the GPU
+    if (q0 >= nq) return;
+    for (int i = threadIdx.x; i < kQT * D16; i += blockDim.x) {
+      const int j = i / D16, w = i % D16;
+      sq[j][w] = q0 + j < nq ? __ldg(reinterpret_cast<const uint4*>(a.q_desc) + (fq + q0 + j) * D16 + w) : make_uint4(0, 0, 0, 0);
+    }
+    if (threadIdx.x < kQT) s_act[threadIdx.x] = (q0 + (int)threadIdx.x < nq && (a.q_use == nullptr || a.q_use[fq + q0 + threadIdx.x])) ? 1 : 0;
+    __syncthreads();
+    const int jn = min(kQT, nq - q0);
+    for (int j = 0; j < jn; j++) {
+      if (!s_act[j]) continue;   // CTA-uniform
+      uint32_t d = 0;
+#pragma unroll
+      for (int w = H; w < D16; w++) {
+        const uint4 qv = sq[j][w];
+        d += __popcll(((unsigned long long)(qv.x ^ cd[w].x) << 32) | (qv.y ^ cd[w].y));
+        d += __popcll(((unsigned long long)(qv.z ^ cd[w].z) << 32) | (qv.w ^ cd[w].w));
+      }
+      if (!valid_c) d = 0xffffu;
+      if (!__any_sync(0xffffffffu, d < a.thr)) continue;
+#pragma unroll
+      for (int w = 0; w < H; w++) {
+        const uint4 qv = sq[j][w];
+        d += __popcll(((unsigned long long)(qv.x ^ cd[w].x) << 32) | (qv.y ^ cd[w].y));
+        d += __popcll(((unsigned long long)(qv.z ^ cd[w].z) << 32) | (qv.w ^ cd[w].w));
+      }
+      if (valid_c && d < a.thr) {
+        const int pos = atomicAdd(&hit_cnt[frame], 1);
+        if (pos < a.hit_cap) hits[(size_t)frame * a.hit_cap + pos] = make_uint2((uint32_t)(q0 + j), (d << 16) | (uint32_t)c);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_m4_gate(MatchArgs a, const uint2* hits, unsigned long long* best)
+{
+  const int frame = blockIdx.y;
+  const int n = min(a.hit_cnt[frame], a.hit_cap);
+  if (a.hit_cnt[frame] > a.hit_cap) return;   // redone by k_match_gated
+  const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint2 e = hits[(size_t)frame * a.hit_cap + i];
+    const int q = (int)e.x, c = (int)(e.y & 0xffffu);
+    const uint32_t d = e.y >> 16;
+    if (m4_gate(a, fq, fc, q, c).pass) atomicMin(&best[fq + q], ((unsigned long long)d << 32) | (unsigned)c);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_m4_finish(MatchArgs a, const unsigned long long* best)
+{
+  const int frame = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.nq || a.hit_cnt[frame] > a.hit_cap) return;
+  const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
+  const unsigned long long b = best[fq + q];
+  const uint32_t d = (uint32_t)(b >> 32);
+  double* hp = a.out_hp + 4 * (fq + q);
+  if (d < a.thr) {
+    const int c = (int)(uint32_t)b;
+    const M4Gate g = m4_gate(a, fq, fc, q, c);
+    a.out_dist[fq + q] = d; a.out_idx[fq + q] = c;
+    hp[0] = g.hp.x; hp[1] = g.hp.y; hp[2] = g.hp.z; hp[3] = 1.0;
+    a.out_init[fq + q] = g.parallel ? 0 : 1;
+  } else {
+    a.out_dist[fq + q] = a.thr; a.out_idx[fq + q] = -1;
+    hp[0] = hp[1] = hp[2] = hp[3] = 0.0;
+    a.out_init[fq + q] = 0;
   }
 }
 
@@ -859,7 +981,9 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
   cudaStream_t st = stream ? (cudaStream_t)stream : MW.stream;
   // scratch: per side rays(3) eW(3) sof c26 c6 doubles + valid bytes
   const size_t n0 = (size_t)n_frames * cap0, n1 = (size_t)n_frames * cap1;
-  const size_t need = (n0 + n1) * (9 * 8 + 8);
+  const int hit_cap = 16 * cap0;   // hits (distance < threshold) per frame kept for the gate pass; more -> sequential replay
+  const size_t need_prep = ((n0 + n1) * (9 * 8 + 8) + 255) & ~(size_t)255;
+  const size_t need = need_prep + n0 * 8 + (size_t)n_frames * hit_cap * 8 + (size_t)n_frames * 4 + 256;
   if (need > ctx->stereo_cap) {
     OKB_CUDA(cudaDeviceSynchronize());
     if (ctx->stereo_scratch) cudaFree(ctx->stereo_scratch);
@@ -883,8 +1007,17 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
   invert_pose(C_WC0, r_WC0, a.T0); invert_pose(C_WC1, r_WC1, a.T1);
   a.thr = match_threshold;
   a.out_dist = d_out_dist; a.out_idx = d_out_k1; a.out_hp = d_out_hp_W; a.out_init = d_out_initialisable;
-  k_match_gated<4, MODE_M4><<<dim3((cap0 + 7) / 8, n_frames), 256, 0, st>>>(a);
-  ctx->launches++;
+  unsigned long long* best = (unsigned long long*)((uint8_t*)ctx->stereo_scratch + need_prep);
+  uint2* hits = (uint2*)(best + n0);
+  int32_t* hit_cnt = (int32_t*)(hits + (size_t)n_frames * hit_cap);
+  a.hit_cnt = hit_cnt; a.hit_cap = hit_cap;
+  OKB_CUDA(cudaMemsetAsync(best, 0xff, n0 * 8, st));
+  OKB_CUDA(cudaMemsetAsync(hit_cnt, 0, (size_t)n_frames * 4, st));
+  k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, (cap0 + 127) / 128), 256, 0, st>>>(a, hits, hit_cnt);
+  k_m4_gate<<<dim3(8, n_frames), 128, 0, st>>>(a, hits, best);
+  k_m4_finish<<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(a, best);
+  k_match_gated<4, MODE_M4><<<dim3((cap0 + 7) / 8, n_frames), 256, 0, st>>>(a);   // only frames whose hit list overflowed
+  ctx->launches += 4;
   OKB_CUDA(cudaGetLastError());
   return OKB_OK;
 }

@@ -182,3 +182,74 @@ def test_host_buffer_batch_pipeline_equals_oracle(pinned):
         assert np.array_equal(k1[b, :n0], ref[0]) and np.array_equal(sdist[b, :n0], ref[1])
         assert np.array_equal(hp[b, :n0].view(np.uint64), ref[2].view(np.uint64)) and np.array_equal(init[b, :n0], ref[3])
     fe.close()
+
+
+def test_stereo_scan_gate_split_with_dense_hits_and_overflow():
+    """M4 device form on crafted feature blocks: frame 0 holds near-duplicate descriptors (every pair is below the matching
+    threshold: the hit list overflows and the sequential-replay kernel redoes the frame), frame 1 a normal mix with many
+    hits per query, frame 2 is empty on the query side. All three must equal the oracle's transcription of the loop."""
+    import torch
+    rng = np.random.default_rng(42)
+    B, cap = 3, 320
+    fe = Frontend(0)
+    L_ = okl.lib()
+    models = []
+    for c in range(2):
+        m = okl.CameraModel(); m.model = 1
+        m.fu, m.fv = EUROC[c]["focal_length"]; m.cu, m.cv = EUROC[c]["principal_point"]
+        for i in range(4):
+            m.k[i] = EUROC[c]["distortion_coefficients"][i]
+        models.append(m)
+    base = rng.integers(0, 256, 64, dtype=np.uint8)
+
+    def near(n, flips):
+        d = np.tile(base, (n, 1))
+        for i in range(n):
+            for b in rng.choice(512, flips, replace=False):
+                d[i, b // 8] ^= 1 << (b % 8)
+        return d
+
+    counts = [[300, 250, 0], [310, 280, 100]]
+    kps = [np.zeros((B, cap), okl.KP_DTYPE) for _ in range(2)]
+    descs = [np.zeros((B, cap, 64), np.uint8) for _ in range(2)]
+    for c in range(2):
+        for b in range(B):
+            n = counts[c][b]
+            kps[c][b]["x"][:n] = rng.uniform(40, 700, n); kps[c][b]["y"][:n] = rng.uniform(40, 440, n)
+            kps[c][b]["size"][:n] = rng.choice([12.0, 18.0, 24.0, 36.0], n)
+            if b == 0:
+                descs[c][b, :n] = near(n, 8)                                          # all pairs < 60
+            else:
+                descs[c][b, :n] = rng.integers(0, 256, (n, 64), dtype=np.uint8)
+                descs[c][b, : n // 3] = near(n // 3, 20)                               # a third of them: dense hits
+    # stereo geometry: points in front of both cameras so that many gates pass: camera 1 keypoints = camera 0 shifted
+    for b in range(B):
+        n = min(counts[0][b], counts[1][b])
+        kps[1][b]["x"][:n] = kps[0][b]["x"][:n] - rng.uniform(2, 30, n).astype(np.float32)
+        kps[1][b]["y"][:n] = kps[0][b]["y"][:n] + rng.uniform(-0.3, 0.3, n).astype(np.float32)
+    d_kp = [torch.from_numpy(k.view(np.uint8).reshape(B, cap * 28)).cuda() for k in kps]
+    d_desc = [torch.from_numpy(d).cuda() for d in descs]
+    d_cnt = [torch.tensor(c, dtype=torch.int32).cuda() for c in counts]
+    C0 = np.eye(3); r0 = np.zeros(3); C1 = np.eye(3); r1 = np.array([0.11, 0.0, 0.0])
+    k1 = torch.zeros((B, cap), dtype=torch.int32, device="cuda"); dist = torch.zeros((B, cap), dtype=torch.int32, device="cuda")
+    hp = torch.zeros((B, cap, 4), dtype=torch.float64, device="cuda"); init = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
+    okl.check(L_.okb_match_stereo_device_ptr(fe.ctx, B, cap, d_kp[0].data_ptr(), d_desc[0].data_ptr(), d_cnt[0].data_ptr(),
+                                             C.addressof(models[0]), C0.ctypes.data, r0.ctypes.data, cap, d_kp[1].data_ptr(),
+                                             d_desc[1].data_ptr(), d_cnt[1].data_ptr(), C.addressof(models[1]), C1.ctypes.data,
+                                             r1.ctypes.data, 60, None, k1.data_ptr(), dist.data_ptr(), hp.data_ptr(), init.data_ptr()))
+    okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    k1, dist, hp, init = k1.cpu().numpy(), dist.cpu().numpy().view(np.uint32), hp.cpu().numpy(), init.cpu().numpy()
+    matched = []
+    for b in range(B):
+        n0, n1 = counts[0][b], counts[1][b]
+        kp0, kp1 = kps[0][b][:n0], kps[1][b][:n1]
+        rays0, v0 = oracle_bp(EUROC[0], kp0); rays1, v1 = oracle_bp(EUROC[1], kp1)
+        f0 = 0.5 * sum(EUROC[0]["focal_length"]); f1 = 0.5 * sum(EUROC[1]["focal_length"])
+        ref = oracle.match_stereo(descs[0][b, :n0], v0, world_rays(C0, rays0), kp0["size"].astype(np.float64) / f0, descs[1][b, :n1], v1,
+                                  world_rays(C1, rays1), kp1["size"].astype(np.float64) / f1, r0, r1, T_CW(C0, r0), T_CW(C1, r1), 60)
+        assert np.array_equal(k1[b, :n0], ref[0]) and np.array_equal(dist[b, :n0], ref[1]), b
+        assert np.array_equal(hp[b, :n0].view(np.uint64), ref[2].view(np.uint64)) and np.array_equal(init[b, :n0], ref[3]), b
+        assert (k1[b, n0:] == -1).all()
+        matched.append(int((ref[0] >= 0).sum()))
+    assert matched[0] > 100 and matched[1] > 30 and matched[2] == 0
+    fe.close()
