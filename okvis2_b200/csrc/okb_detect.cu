@@ -196,15 +196,15 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
-// Tie-cell bitmap: one bit per 16x16-pixel cell of every layer, set when the 5x5 window of a tied (or still pending)
+// Tie-cell bitmap: one bit per 8x8-pixel cell of every layer, set when the 5x5 window of a tied (or still pending)
 // candidate intersects the cell. The touch-time map is only ever read inside those windows (k_resolve), so a maximum
 // whose touch footprint misses every flagged cell does not have to emit its touches at all (k_refine).
-constexpr int kCellShift = 4;
-constexpr int kCellWordsPerLayer = 512;                    // 16384 cells: layers up to 2048 x 2048
+constexpr int kCellShift = 3;
+constexpr int kCellWordsPerLayer = 2048;                   // 65536 cells: layers up to 2048 x 2048
 constexpr int kCellWordsPerFrame = kMaxLayers * kCellWordsPerLayer;
 __device__ __forceinline__ void cells_flag(uint32_t* cells /*layer*/, int layer_w, int x_lo, int x_hi, int y_lo, int y_hi)
 {
-  const int cw = (layer_w + 15) >> kCellShift;
+  const int cw = (layer_w + (1 << kCellShift) - 1) >> kCellShift;
   for (int cy = max(y_lo, 0) >> kCellShift; cy <= (y_hi >> kCellShift); cy++)
     for (int cx = max(x_lo, 0) >> kCellShift; cx <= min(x_hi >> kCellShift, cw - 1); cx++) {
       const int b = cy * cw + cx;
@@ -213,7 +213,7 @@ __device__ __forceinline__ void cells_flag(uint32_t* cells /*layer*/, int layer_
 }
 __device__ __forceinline__ bool cells_any(const uint32_t* cells /*layer*/, int layer_w, int x_lo, int x_hi, int y_lo, int y_hi)
 {
-  const int cw = (layer_w + 15) >> kCellShift;
+  const int cw = (layer_w + (1 << kCellShift) - 1) >> kCellShift;
   for (int cy = max(y_lo, 0) >> kCellShift; cy <= (y_hi >> kCellShift); cy++)
     for (int cx = max(x_lo, 0) >> kCellShift; cx <= min(x_hi >> kCellShift, cw - 1); cx++) {
       const int b = cy * cw + cx;
