@@ -1184,10 +1184,6 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaEventCreateWithFlags(&ws.ev_done, cudaEventDisableTiming));
   OKB_CUDA(cudaMalloc(&ws.d_dbg, (size_t)16 * 8 * B));
   OKB_CUDA(cudaMemset(ws.d_dbg, 0, (size_t)16 * 8 * B));
-  OKB_CUDA(cudaMalloc(&ws.d_m1_cell_off, (size_t)4097 * 4 * B));
-  OKB_CUDA(cudaMalloc(&ws.d_m1_cell_list, (size_t)ws.kp_cap * 4 * B));
-  OKB_CUDA(cudaMalloc(&ws.d_m1_cell_xy, (size_t)ws.kp_cap * 16 * B));
-  OKB_CUDA(cudaMalloc(&ws.d_m1_best, (size_t)ws.kp_cap * 8 * B));
   OKB_CUDA(cudaMemset(ws.d_count, 0, 4 * B));
   OKB_CUDA(cudaMemset(ws.d_status, 0, 4 * B));
   OKB_CUDA(cudaMallocHost(&ws.h_img, (size_t)W * H * B));
@@ -1213,7 +1209,7 @@ void detect_free_camera(okb_context* ctx, int cam)
   }
   cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_tie_cells); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
   cudaFree(ws.d_cand_count); cudaFree(ws.d_rec); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
-  cudaFree(ws.d_count); cudaFree(ws.d_status); cudaFree(ws.d_m1_cell_off); cudaFree(ws.d_m1_cell_list); cudaFree(ws.d_m1_cell_xy); cudaFree(ws.d_m1_best); cudaFree(ws.m_d); if (ws.m_h) cudaFreeHost(ws.m_h); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);
+  cudaFree(ws.d_count); cudaFree(ws.d_status); cudaFree(ws.d_m1_rows); cudaFree(ws.m_d); if (ws.m_h) cudaFreeHost(ws.m_h); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);
   if (ws.ev_done) cudaEventDestroy(ws.ev_done);
   cudaFreeHost(ws.h_img); cudaFreeHost(ws.h_kp); cudaFreeHost(ws.h_desc); cudaFreeHost(ws.h_count); cudaFreeHost(ws.h_status); cudaFreeHost(ws.h_rays); cudaFreeHost(ws.h_rays_valid);
   for (int i = 0; i < 4; i++) if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);

@@ -92,7 +92,7 @@ struct CamWorkspace {
   // TMA tensor maps of the internal layers (layer 0 is encoded per call)
   CUtensorMap tma[kMaxLayers]; int tma_use[kMaxLayers] = {0}; int tma_ready = 0;
   long long* d_dbg = nullptr;   // per-frame cycle stamps of the single-CTA kernels (okb_debug_stamps)
-  int32_t* d_m1_cell_off = nullptr; int32_t* d_m1_cell_list = nullptr; double2* d_m1_cell_xy = nullptr; unsigned long long* d_m1_best = nullptr;
+  uint8_t* d_m1_rows = nullptr; size_t m1_rows_cap = 0;   // M1 row bins of the device-resident form (grown on demand)
   // staging of the host-buffer batch matchers (okb_match_map3d_batch / okb_match_stereo_batch), grown on demand
   uint8_t* m_d = nullptr; uint8_t* m_h = nullptr; size_t m_cap = 0;
   // pinned staging

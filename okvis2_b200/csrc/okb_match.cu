@@ -186,12 +186,15 @@ __device__ __forceinline__ uint32_t hamming_bounded(const uint4 (&qd)[D16], uint
   return valid ? d : 0xffffu;
 }
 
-// M1. The reprojection gate makes the problem sparse: a keypoint can only match landmarks that project within
-// `thr` pixels of it. Keypoints are binned into a grid of cells >= thr wide (k_m1_bin, one CTA per frame); every pooled
-// descriptor then visits the 3x3 cells around its landmark's projection, evaluates the reference's exact fp64 gate
-// (reprDist.dot(reprDist) > thr^2 -> skip) and the Hamming distance, and merges (distance, candidate index) into the
-// keypoint's slot with a 64-bit atomicMin. The lexicographic minimum is exactly "first strict minimum in ascending
-// LandmarkId / descriptor order" of the sequential loop, and it is order independent, so the result is bit-identical.
+// M1. The reprojection gate makes the problem sparse: a keypoint can only match pooled descriptors whose landmark projects
+// within `thr` pixels of it. Per frame the pool ROWS of 3-D landmarks are binned by their projection into a grid of cells
+// >= thr wide (k_m1_rowbin: one CTA per frame, counting sort in shared memory; rows that project more than thr + 1 px
+// outside the keypoint extent cannot pass the gate and are dropped; NaN projections -- which the reference's gate does NOT
+// reject -- go to an extra cell every keypoint visits). Then one WARP per keypoint (k_m1_match) walks the 3x3 cells around
+// it, lanes over the rows: coalesced (projection, row) records, the reference's exact fp64 gate
+// (reprDist.dot(reprDist) > thr^2 -> skip), Hamming distance for the rows that pass, and a warp reduction of
+// (distance << 32 | row). The lexicographic minimum is exactly "first strict minimum in ascending LandmarkId / descriptor
+// order" of the sequential loop, and it is order independent, so the result is bit-identical.
 constexpr int kMaxCells = 4096;
 
 struct M1Args {
@@ -202,11 +205,11 @@ struct M1Args {
   size_t q_stride, proj_stride; // per-frame strides (elements) for the batched device form
   int nc; const uint8_t* c_desc; const int32_t* c_lm; const double* lm_proj; const uint8_t* lm_is3d;
   double thr_sq; uint32_t thr;
+  double thr_px, min_x, min_y, max_x, max_y;   // gate radius and extent of the keypoint cloud (row pre-filter)
   int cell, gx, gy;             // grid
-  int32_t* cell_off;            // [frames][kMaxCells + 1]
-  int32_t* cell_list;           // [frames][nq]
-  double2* cell_xy;             // [frames][nq]: keypoint coordinates in cell-list order (one 16-byte load per gate test)
-  unsigned long long* best;     // [frames][nq]
+  int32_t* row_off;             // [frames][kMaxCells + 2]: cell offsets into row_list; cell gx*gy = rows with NaN projections
+  int32_t* row_list;            // [frames][nc]
+  double2* row_xy;              // [frames][nc]: projection of the row's landmark, in row_list order
   uint32_t* out_dist; int32_t* out_idx;
 };
 
@@ -215,119 +218,132 @@ __device__ __forceinline__ void m1_kp_xy(const M1Args& a, size_t fq, int k, doub
   if (a.q_kp) { x = (double)a.q_kp[fq + k].x; y = (double)a.q_kp[fq + k].y; }  // MultiFrame::getKeypoint: float -> double
   else { x = a.q_xy[2 * k]; y = a.q_xy[2 * k + 1]; }
 }
-__device__ __forceinline__ int m1_cell_of(const M1Args& a, double x, double y)
+__device__ __forceinline__ int m1_cell_of(const M1Args& a, double x, double y, int& cx, int& cy)
 {
-  int cx = (int)floor(x / a.cell), cy = (int)floor(y / a.cell);
-  cx = min(max(cx, 0), a.gx - 1); cy = min(max(cy, 0), a.gy - 1);
+  const double fx = floor((x - a.min_x) / a.cell), fy = floor((y - a.min_y) / a.cell);
+  cx = fx < 0.0 ? 0 : (fx > (double)(a.gx - 1) ? a.gx - 1 : (int)fx);
+  cy = fy < 0.0 ? 0 : (fy > (double)(a.gy - 1) ? a.gy - 1 : (int)fy);
   return cy * a.gx + cx;
 }
-
-__global__ void __launch_bounds__(256) k_m1_bin(M1Args a)
+// cell of a pool row for this frame: -1 = cannot match (not 3-D, or farther than thr outside the keypoint extent),
+// n_cells = NaN projection (passes the reference's gate against every keypoint)
+__device__ __forceinline__ int m1_row_cell(const M1Args& a, int frame, int r, double& px, double& py)
 {
-  __shared__ int cnt[kMaxCells + 1];
+  const int lm = __ldg(&a.c_lm[r]);
+  if (!a.lm_is3d[lm]) return -1;
+  const double* lp = a.lm_proj + (size_t)frame * a.proj_stride + 2 * (size_t)lm;
+  px = lp[0]; py = lp[1];
+  if (!(px == px) || !(py == py)) return a.gx * a.gy;
+  const double m = a.thr_px + 1.0;
+  if (!(px >= a.min_x - m && px <= a.max_x + m && py >= a.min_y - m && py <= a.max_y + m)) return -1;   // also +-inf
+  int cx, cy;
+  return m1_cell_of(a, px, py, cx, cy);
+}
+
+__global__ void __launch_bounds__(1024) k_m1_rowbin(M1Args a)
+{
+  __shared__ int cnt[kMaxCells + 2];
   const int frame = blockIdx.x;
-  const size_t fq = (size_t)frame * a.q_stride;
-  const int nq = a.q_count ? min(a.q_count[frame], a.nq) : a.nq;
   const int n_cells = a.gx * a.gy;
-  for (int i = threadIdx.x; i <= n_cells; i += blockDim.x) cnt[i] = 0;
+  for (int i = threadIdx.x; i <= n_cells + 1; i += blockDim.x) cnt[i] = 0;
   __syncthreads();
-  for (int k = threadIdx.x; k < a.nq; k += blockDim.x) {
-    a.best[fq + k] = ((unsigned long long)a.thr << 32) | 0xffffffffull;
-    if (k < nq && (a.q_use == nullptr || a.q_use[k])) {
-      double x, y; m1_kp_xy(a, fq, k, x, y);
-      if (x == x && y == y) atomicAdd(&cnt[m1_cell_of(a, x, y)], 1);
-    }
+  for (int r = threadIdx.x; r < a.nc; r += blockDim.x) {
+    double px, py;
+    const int c = m1_row_cell(a, frame, r, px, py);
+    if (c >= 0) atomicAdd(&cnt[c], 1);
   }
   __syncthreads();
-  // exclusive scan of the cell counts (<= 4096 cells): one warp, 128 cells per lane
+  // exclusive scan of the cell counts (<= 4097 cells): one warp, a contiguous chunk per lane
   if (threadIdx.x < 32) {
-    const int per = (n_cells + 31) / 32, beg = min((int)threadIdx.x * per, n_cells), end = min(beg + per, n_cells);
-    int s = 0;
-    for (int i = beg; i < end; i++) s += cnt[i];
-    int incl = s;
+    const int n = n_cells + 1;
+    const int per = (n + 31) / 32, beg = min((int)threadIdx.x * per, n), end = min(beg + per, n);
+    int sum = 0;
+    for (int i = beg; i < end; i++) sum += cnt[i];
+    int incl = sum;
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
-    int run = incl - s;
+    int run = incl - sum;
     for (int i = beg; i < end; i++) { const int c = cnt[i]; cnt[i] = run; run += c; }
-    if (threadIdx.x == 31) cnt[n_cells] = incl;
+    if (threadIdx.x == 31) cnt[n] = incl;
   }
   __syncthreads();
-  int32_t* off = a.cell_off + (size_t)frame * (kMaxCells + 1);
-  for (int i = threadIdx.x; i <= n_cells; i += blockDim.x) off[i] = cnt[i];
+  int32_t* off = a.row_off + (size_t)frame * (kMaxCells + 2);
+  for (int i = threadIdx.x; i <= n_cells + 1; i += blockDim.x) off[i] = cnt[i];
   __syncthreads();
-  int32_t* list = a.cell_list + fq;
-  for (int k = threadIdx.x; k < nq; k += blockDim.x) {
-    if (a.q_use == nullptr || a.q_use[k]) {
-      double x, y; m1_kp_xy(a, fq, k, x, y);
-      if (x == x && y == y) {
-        const int pos = atomicAdd(&cnt[m1_cell_of(a, x, y)], 1);
-        list[pos] = k; a.cell_xy[fq + pos] = make_double2(x, y);
-      }
-    }
+  int32_t* list = a.row_list + (size_t)frame * a.nc;
+  double2* xy = a.row_xy + (size_t)frame * a.nc;
+  for (int r = threadIdx.x; r < a.nc; r += blockDim.x) {
+    double px, py;
+    const int c = m1_row_cell(a, frame, r, px, py);
+    if (c >= 0) { const int pos = atomicAdd(&cnt[c], 1); list[pos] = r; xy[pos] = make_double2(px, py); }
   }
 }
 
 template <int D16>
-__global__ void __launch_bounds__(128) k_m1_match(M1Args a)
+__global__ void __launch_bounds__(256) k_m1_match(M1Args a)
 {
   const int frame = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.nc) return;
-  const int lm = __ldg(&a.c_lm[c]);
-  if (!a.lm_is3d[lm]) return;
-  const double* lp = a.lm_proj + (size_t)frame * a.proj_stride + 2 * (size_t)lm;
-  const double px = lp[0], py = lp[1];
-  const size_t fq = (size_t)frame * a.q_stride;
-  const int32_t* off = a.cell_off + (size_t)frame * (kMaxCells + 1);
-  const int32_t* list = a.cell_list + fq;
-  int cx0 = 0, cx1 = a.gx - 1, cy0 = 0, cy1 = a.gy - 1;   // NaN projections are not gated by the reference: visit all
-  if (px == px && py == py) {
-    const double fx = floor(px / a.cell), fy = floor(py / a.cell);
-    if (!(fabs(fx) < 1e8) || !(fabs(fy) < 1e8)) return;   // infinitely far away: every gate fails
-    cx0 = max((int)fx - 1, 0); cx1 = min((int)fx + 1, a.gx - 1);
-    cy0 = max((int)fy - 1, 0); cy1 = min((int)fy + 1, a.gy - 1);
-  }
-  uint4 cd[D16];
-  bool loaded = false;
-  for (int cy = cy0; cy <= cy1; cy++) {
-    if (cx0 > cx1) break;
-    const int beg = off[cy * a.gx + cx0], end = off[cy * a.gx + cx1 + 1];   // cells of one row are contiguous
-    for (int i = beg; i < end; i++) {
-      const double2 kxy = __ldg(&a.cell_xy[fq + i]);
-      const double dx = px - kxy.x, dy = py - kxy.y;
-      const double d2 = dx * dx + dy * dy;
-      if (d2 > a.thr_sq) continue;
-      const int k = list[i];
-      if (!loaded) { load_query<D16>(a.c_desc, c, cd); loaded = true; }
-      const uint4* qp = reinterpret_cast<const uint4*>(a.q_desc) + (fq + k) * D16;
-      uint32_t d = 0;
-#pragma unroll
-      for (int w = 0; w < D16; w++) {
-        const uint4 qv = __ldg(qp + w);
-        d += __popcll(((unsigned long long)(qv.x ^ cd[w].x) << 32) | (qv.y ^ cd[w].y));
-        d += __popcll(((unsigned long long)(qv.z ^ cd[w].z) << 32) | (qv.w ^ cd[w].w));
-      }
-      if (d < a.thr) atomicMin(&a.best[fq + k], ((unsigned long long)d << 32) | (unsigned)c);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) k_m1_unpack(M1Args a)
-{
-  const int frame = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + warp;
   if (k >= a.nq) return;
   const size_t fq = (size_t)frame * a.q_stride;
-  const unsigned long long b = a.best[fq + k];
-  const uint32_t d = (uint32_t)(b >> 32);
-  if (d < a.thr) { a.out_dist[fq + k] = d; a.out_idx[fq + k] = a.c_lm[(uint32_t)b]; }
-  else { a.out_dist[fq + k] = a.thr; a.out_idx[fq + k] = -1; }
+  const int nq = a.q_count ? min(a.q_count[frame], a.nq) : a.nq;
+  unsigned long long best = ((unsigned long long)a.thr << 32) | 0xffffffffull;
+  double x = 0, y = 0;
+  bool active = k < nq && (a.q_use == nullptr || a.q_use[k]) && a.nc > 0;
+  if (active) { m1_kp_xy(a, fq, k, x, y); active = x == x && y == y; }
+  if (active) {
+    const int32_t* off = a.row_off + (size_t)frame * (kMaxCells + 2);
+    const int32_t* list = a.row_list + (size_t)frame * a.nc;
+    const double2* xy = a.row_xy + (size_t)frame * a.nc;
+    uint4 qd[D16];
+    load_query<D16>(a.q_desc, (int)(fq + k), qd);
+    int cx, cy;
+    m1_cell_of(a, x, y, cx, cy);
+    const int cx0 = max(cx - 1, 0), cx1 = min(cx + 1, a.gx - 1), n_cells = a.gx * a.gy;
+    for (int pass = 0; pass < 4; pass++) {
+      int beg, end;
+      if (pass < 3) {
+        const int cyy = cy - 1 + pass;
+        if (cyy < 0 || cyy >= a.gy) continue;
+        beg = off[cyy * a.gx + cx0]; end = off[cyy * a.gx + cx1 + 1];   // cells of one grid row are contiguous
+      } else { beg = off[n_cells]; end = off[n_cells + 1]; }             // NaN projections: the gate never rejects them
+      for (int i = beg + lane; i < end; i += 32) {
+        const double2 p = __ldg(&xy[i]);
+        const double dx = p.x - x, dy = p.y - y;
+        const double d2 = dx * dx + dy * dy;
+        if (d2 > a.thr_sq) continue;
+        const int r = __ldg(&list[i]);
+        const uint4* cp = reinterpret_cast<const uint4*>(a.c_desc) + (size_t)r * D16;
+        uint32_t d = 0;
+#pragma unroll
+        for (int w = 0; w < D16; w++) {
+          const uint4 cv = __ldg(cp + w);
+          d += __popcll(((unsigned long long)(qd[w].x ^ cv.x) << 32) | (qd[w].y ^ cv.y));
+          d += __popcll(((unsigned long long)(qd[w].z ^ cv.z) << 32) | (qd[w].w ^ cv.w));
+        }
+        const unsigned long long key = ((unsigned long long)d << 32) | (unsigned)r;
+        if (key < best) best = key;
+      }
+    }
+  }
+  // warp minimum of the 64-bit keys (inactive warps keep the "no match" key)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    if (other < best) best = other;
+  }
+  if (lane == 0) {
+    const uint32_t d = (uint32_t)(best >> 32);
+    if (d < a.thr) { a.out_dist[fq + k] = d; a.out_idx[fq + k] = a.c_lm[(uint32_t)best]; }
+    else { a.out_dist[fq + k] = a.thr; a.out_idx[fq + k] = -1; }
+  }
 }
 
-static void m1_grid(double thr, double max_x, double max_y, int& cell, int& gx, int& gy)
+static void m1_grid(double thr, double ext_x, double ext_y, int& cell, int& gx, int& gy)
 {
   cell = (int)ceil(thr); if (cell < 8) cell = 8;
   for (;;) {
-    gx = (int)(max_x / cell) + 1; gy = (int)(max_y / cell) + 1;
+    gx = (int)(ext_x / cell) + 1; gy = (int)(ext_y / cell) + 1;
     if ((long long)gx * gy <= kMaxCells) break;
     cell *= 2;
   }
@@ -335,13 +351,10 @@ static void m1_grid(double thr, double max_x, double max_y, int& cell, int& gx, 
 
 static int m1_launch(okb_context* ctx, M1Args& a, int D, int n_frames, cudaStream_t st)
 {
-  k_m1_bin<<<n_frames, 256, 0, st>>>(a);
-  if (a.nc > 0) {
-    if (D == 64) k_m1_match<4><<<dim3((a.nc + 127) / 128, n_frames), 128, 0, st>>>(a);
-    else k_m1_match<3><<<dim3((a.nc + 127) / 128, n_frames), 128, 0, st>>>(a);
-  }
-  k_m1_unpack<<<dim3((a.nq + 255) / 256, n_frames), 256, 0, st>>>(a);
-  ctx->launches += a.nc > 0 ? 3 : 2;
+  if (a.nc > 0) k_m1_rowbin<<<n_frames, 1024, 0, st>>>(a);
+  if (D == 64) k_m1_match<4><<<dim3((a.nq + 7) / 8, n_frames), 256, 0, st>>>(a);
+  else k_m1_match<3><<<dim3((a.nq + 7) / 8, n_frames), 256, 0, st>>>(a);
+  ctx->launches += a.nc > 0 ? 2 : 1;
   OKB_CUDA(cudaGetLastError());
   return OKB_OK;
 }
@@ -783,11 +796,19 @@ int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc,
   OKB_CUDA(cudaSetDevice(ctx->device));
   OKB_LOCK_SLOT;
   cudaStream_t st = MW.stream;
-  double max_x = 0, max_y = 0;   // extent of the keypoint cloud (sizes the grid; not part of the arithmetic)
-  for (int k = 0; k < n_kp; k++) { if (kp_xy[2 * k] > max_x) max_x = kp_xy[2 * k]; if (kp_xy[2 * k + 1] > max_y) max_y = kp_xy[2 * k + 1]; }
-  if (!(max_x < 1e6)) max_x = 1e6; if (!(max_y < 1e6)) max_y = 1e6;
+  // extent of the keypoint cloud (sizes the grid and the row pre-filter; not part of the arithmetic)
+  double min_x = 0, min_y = 0, max_x = 0, max_y = 0; bool first = true;
+  for (int k = 0; k < n_kp; k++) {
+    const double x = kp_xy[2 * k], y = kp_xy[2 * k + 1];
+    if (!(x == x) || !(y == y)) continue;
+    if (first) { min_x = max_x = x; min_y = max_y = y; first = false; }
+    if (x < min_x) min_x = x; if (x > max_x) max_x = x; if (y < min_y) min_y = y; if (y > max_y) max_y = y;
+  }
+  if (!(max_x - min_x < 1e6)) { min_x = -5e5; max_x = 5e5; }
+  if (!(max_y - min_y < 1e6)) { min_y = -5e5; max_y = 5e5; }
   M1Args a; memset(&a, 0, sizeof(a));
-  m1_grid(reprojection_threshold, max_x, max_y, a.cell, a.gx, a.gy);
+  m1_grid(reprojection_threshold, max_x - min_x, max_y - min_y, a.cell, a.gx, a.gy);
+  a.thr_px = reprojection_threshold; a.min_x = min_x; a.min_y = min_y; a.max_x = max_x; a.max_y = max_y;
   size_t o_dist = 0, o_idx = 0, in_end = 0;
   for (int pass = 0; pass < 2; pass++) {
     Arena A; A.ctx = ctx; A.dry = pass == 0; A.h = (uint8_t*)MW.h_buf; A.d = (uint8_t*)MW.d_buf;
@@ -796,8 +817,8 @@ int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc,
     a.c_desc = A.in(cand_desc, (size_t)n_cand * D); a.c_lm = A.in(cand_lm, (size_t)n_cand);
     a.lm_proj = A.in(lm_proj, (size_t)n_lm * 2); a.lm_is3d = A.in(lm_is3d, (size_t)n_lm);
     in_end = A.off;
-    a.cell_off = A.out<int32_t>(kMaxCells + 1, nullptr); a.cell_list = A.out<int32_t>(n_kp, nullptr);
-    a.best = A.out<unsigned long long>(n_kp, nullptr); a.cell_xy = A.out<double2>(n_kp, nullptr);
+    a.row_off = A.out<int32_t>(kMaxCells + 2, nullptr); a.row_list = A.out<int32_t>((size_t)n_cand + 1, nullptr);
+    a.row_xy = A.out<double2>((size_t)n_cand + 1, nullptr);
     a.out_dist = A.out<uint32_t>(n_kp, &o_dist); a.out_idx = A.out<int32_t>(n_kp, &o_idx);
     if (pass == 0) { int rc = ensure(ctx, A.off); if (rc) return rc; }
   }
@@ -953,7 +974,20 @@ int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand
   a.q_desc = ws.d_desc; a.q_kp = ws.d_kp;
   a.nc = n_cand; a.c_desc = d_cand_desc; a.c_lm = d_cand_lm; a.lm_proj = d_lm_proj; a.lm_is3d = d_lm_is3d;
   a.thr = match_threshold; a.thr_sq = reprojection_threshold * reprojection_threshold;
-  a.cell_off = ws.d_m1_cell_off; a.cell_list = ws.d_m1_cell_list; a.best = ws.d_m1_best; a.cell_xy = ws.d_m1_cell_xy;
+  a.thr_px = reprojection_threshold; a.min_x = 0.0; a.min_y = 0.0; a.max_x = ws.cfg.width; a.max_y = ws.cfg.height;
+  {
+    // per-frame row bins: [n_frames][kMaxCells + 2] offsets, [n_frames][n_cand] rows and projections; grown on demand
+    const size_t off_b = (((size_t)n_frames * (kMaxCells + 2) * 4) + 255) & ~(size_t)255;
+    const size_t list_b = (((size_t)n_frames * ((size_t)n_cand + 1) * 4) + 255) & ~(size_t)255;
+    const size_t need = off_b + list_b + (size_t)n_frames * ((size_t)n_cand + 1) * 16;
+    if (need > ws.m1_rows_cap) {
+      OKB_CUDA(cudaStreamSynchronize(ws.stream));
+      cudaFree(ws.d_m1_rows); ws.d_m1_rows = nullptr; ws.m1_rows_cap = 0;
+      OKB_CUDA(cudaMalloc(&ws.d_m1_rows, need + need / 4));
+      ws.m1_rows_cap = need + need / 4;
+    }
+    a.row_off = (int32_t*)ws.d_m1_rows; a.row_list = (int32_t*)(ws.d_m1_rows + off_b); a.row_xy = (double2*)(ws.d_m1_rows + off_b + list_b);
+  }
   a.out_dist = d_out_dist; a.out_idx = d_out_lm;
   return m1_launch(ctx, a, 64, n_frames, ws.stream);
 }
