@@ -50,6 +50,31 @@ def test_m1_match_to_map(fe, D, n_kp, n_lm, use_imu):
         assert (ref[1] >= 0).sum() > 10 and (ref[1][use == 0] == -1).all()
 
 
+def test_m1_at_tumvi_size(fe):
+    """BASELINE config 2 at full size: 2000 keypoints against the pool of a 50 000-landmark map (~100 000 rows), both
+    reprojection thresholds, exact equality with the oracle; plus the size-independent property that dropping every
+    pool row outside the gate radius of all keypoints changes nothing."""
+    rng = np.random.default_rng(7)
+    n_kp = 2000
+    kp_xy = rng.uniform(0, 1024, (n_kp, 2))
+    kd = rng.integers(0, 256, (n_kp, 64), dtype=np.uint8)
+    m = map_scene(3, kp_xy, kd, 50000, W=1024, H=1024, frac_near=0.1)
+    assert len(m["cand_lm"]) > 90000
+    for use_imu in (True, False):
+        thr = 20.0 if use_imu else 150.0
+        got = fe.matchToMapByThread(kd, kp_xy, None, m["cand_desc"], m["cand_lm"], m["lm_proj"], m["lm_is3d"], use_imu)
+        ref = oracle.match_map3d(kd, kp_xy, None, m["cand_desc"], m["cand_lm"], m["lm_proj"], m["lm_is3d"], thr, 60)
+        eq(got, ref, "M1 full size")
+        assert (ref[1] >= 0).sum() > 500
+    # rows whose landmark projects farther than 20 px from every keypoint cannot matter
+    from scipy.spatial import cKDTree
+    near = np.array([len(x) > 0 for x in cKDTree(kp_xy).query_ball_point(np.nan_to_num(m["lm_proj"], nan=-1e9, posinf=1e9, neginf=-1e9), 20.0 + 1e-6)])
+    keep = near[m["cand_lm"]] | ~np.isfinite(m["lm_proj"][m["cand_lm"]]).all(1)
+    got2 = fe.matchToMapByThread(kd, kp_xy, None, m["cand_desc"][keep], m["cand_lm"][keep], m["lm_proj"], m["lm_is3d"], True)
+    ref = oracle.match_map3d(kd, kp_xy, None, m["cand_desc"], m["cand_lm"], m["lm_proj"], m["lm_is3d"], 20.0, 60)
+    eq(got2, ref, "M1 pruned pool")
+
+
 def test_m1_ties_first_in_order_wins(fe):
     # identical descriptors everywhere: every candidate has distance 0 -> the lowest landmark passing the gate must win
     kd = np.zeros((40, 64), np.uint8)
