@@ -547,6 +547,11 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                 "measured": f"CUDA events on the launching stream, {roof_steps} extra steps right after the timed region with the two camera streams serialized (they overlap in the timed region)"}
 
+    # more waiting host threads than cores (many ranks per box): sleep instead of spinning while a batch is on the device
+    host_threads = world * lanes * 3
+    blocking = host_threads > (os.cpu_count() or 1)
+    for f in fes:
+        L_.okb_set_blocking_sync(f.ctx, 1 if blocking else 0)
     # ---- e2e: HOST buffers through the C ABI, per stereo frame (streaming use), driven by the C++ host loop of
     #      bench/e2e_driver.cpp (what an integrator of the library writes; one host thread per camera for detection,
     #      ThreadedSlam.cpp:432-448; then okb_match_stereo and okb_match_map3d). All H2D/D2H copies are inside.
@@ -636,7 +641,7 @@ def main():
                    "okb_detect_describe_batch + okb_match_map3d_batch, then okb_match_stereo_batch; results in host memory; "
                    f"{lanes} independent sequences in flight on the GPU (one library handle + host-thread pair each), "
                    f"{args.steps} steps in total",
-           "lanes": lanes,
+           "lanes": lanes, "host_wait": "blocking event" if blocking else "spin",
            "one_sequence_alone": {"value": world * B * args.steps / rep_s, "ms_per_step": 1e3 * rep_s / args.steps},
            "keypoints_per_frame": io.nkp / (2 * B), "matches_per_stereo_frame": io.nm / B, "streaming": streaming}
 

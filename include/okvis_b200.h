@@ -63,6 +63,10 @@ int64_t okb_launch_count(const okb_context_t* ctx);
 /* the CUDA stream (cudaStream_t as void*) camera `cam` works on; okb_sync waits for all of them */
 void* okb_stream(okb_context_t* ctx, int cam);
 int okb_sync(okb_context_t* ctx);
+/* How the host-buffer entry points (okb_detect_describe[_batch], okb_match_map3d_batch, okb_match_stereo_batch) wait for
+ * the device: 0 (default) = spin, lowest latency; 1 = sleep on a blocking event, for hosts that run more waiting threads than
+ * cores (many ranks x sequences per box). The reference has no counterpart: its calls are synchronous CPU code. */
+int okb_set_blocking_sync(okb_context_t* ctx, int on);
 
 /* ---- detect + describe: replaces okvis::Frame::detect + okvis::Frame::describe, i.e. the calls
  *      detector_->detect(image_, keypoints_) and extractor_->compute(image_, keypoints_, descriptors_)

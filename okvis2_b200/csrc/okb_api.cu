@@ -87,6 +87,7 @@ void okb_destroy(okb_context_t* ctx)
 }
 
 int64_t okb_launch_count(const okb_context_t* ctx) { return ctx ? ctx->launches : 0; }
+int okb_set_blocking_sync(okb_context_t* ctx, int on) { if (!ctx) return OKB_ERR_ARGUMENT; ctx->blocking_sync = on ? 1 : 0; return OKB_OK; }
 void* okb_stream(okb_context_t* ctx, int cam)
 {
   if (!ctx) return nullptr;
@@ -172,7 +173,7 @@ int okb_detect_describe_batch(okb_context_t* ctx, int cam, int n_frames, const u
     OKB_CUDA(cudaMemcpyAsync(ws.h_rays_valid, ws.d_rays_valid, nr, cudaMemcpyDeviceToHost, st));
     ws.h_rays_frames = n_frames;
   }
-  OKB_CUDA(cudaStreamSynchronize(st));
+  OKB_CUDA(wait_stream(ctx, st));
   rc = status_to_error(ws, n_frames);
   if (rc) return rc;
   for (int b = 0; b < n_frames; b++) {

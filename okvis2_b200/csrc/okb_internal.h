@@ -141,6 +141,7 @@ struct okb_context {
   int timers_on = 0;
   void* stereo_scratch = nullptr; size_t stereo_cap = 0;   // device scratch of okb_match_stereo_device*
   int64_t launches = 0;
+  int blocking_sync = 0;     // 1: host-buffer entry points wait on a cudaEventBlockingSync event (the thread sleeps) instead of spinning
   void* prepare = nullptr;   // okb::PrepareState (okb_prepare.cu): keyframe feature store + P1 workspace
   void* aux = nullptr;       // okb::AuxState (okb_aux.cu): keyframe-overlap / BoW workspaces
 };
@@ -160,6 +161,24 @@ inline bool host_pinned(const void* p)
   cudaPointerAttributes at;
   if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return at.type == cudaMemoryTypeHost;
+}
+// wait for `st` from a host-buffer entry point: spin (lowest latency) or sleep on a blocking event (okb_set_blocking_sync: for
+// hosts with more waiting threads than cores, e.g. 8 ranks x 3 sequences x 3 threads)
+inline cudaError_t wait_stream(okb_context* ctx, cudaStream_t st)
+{
+  if (!ctx->blocking_sync) return cudaStreamSynchronize(st);
+  static thread_local cudaEvent_t ev = nullptr;
+  static thread_local int ev_device = -1;
+  if (ev_device != ctx->device) {
+    if (ev) cudaEventDestroy(ev);
+    ev = nullptr;
+    const cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    ev_device = ctx->device;
+  }
+  const cudaError_t e = cudaEventRecord(ev, st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ev);
 }
 void prepare_free(okb_context* ctx);
 void aux_free(okb_context* ctx);

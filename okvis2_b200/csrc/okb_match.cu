@@ -1149,7 +1149,7 @@ int okb_match_map3d_batch(okb_context_t* ctx, int cam, int n_frames, int n_cand,
   bool s0, s1;
   if ((rc = S.download(o_dist, out_dist, 4, rows, ws.kp_cap, cap, n_frames, &s0)) || (rc = S.download(o_idx, out_lm, 4, rows, ws.kp_cap, cap, n_frames, &s1)))
     return rc;
-  OKB_CUDA(cudaStreamSynchronize(ws.stream));
+  OKB_CUDA(wait_stream(ctx, ws.stream));
   if (s0) S.unstage(o_dist, out_dist, 4, rows, ws.kp_cap, cap, n_frames);
   if (s1) S.unstage(o_idx, out_lm, 4, rows, ws.kp_cap, cap, n_frames);
   return OKB_OK;
@@ -1177,7 +1177,7 @@ int okb_match_stereo_batch(okb_context_t* ctx, int cam0, int cam1, int n_frames,
       (rc = S.download(o_hp, out_hp_W, 32, rows, ws.kp_cap, cap, n_frames, &s[2])) ||
       (rc = S.download(o_init, out_initialisable, 1, rows, ws.kp_cap, cap, n_frames, &s[3])))
     return rc;
-  OKB_CUDA(cudaStreamSynchronize(ws.stream));
+  OKB_CUDA(wait_stream(ctx, ws.stream));
   if (s[0]) S.unstage(o_k1, out_k1, 4, rows, ws.kp_cap, cap, n_frames);
   if (s[1]) S.unstage(o_dist, out_dist, 4, rows, ws.kp_cap, cap, n_frames);
   if (s[2]) S.unstage(o_hp, out_hp_W, 32, rows, ws.kp_cap, cap, n_frames);

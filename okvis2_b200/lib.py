@@ -60,6 +60,7 @@ _PROTOS = {
     "okb_launch_count": (C.c_int64, [vp]),
     "okb_stream": (vp, [vp, i32]),
     "okb_sync": (i32, [vp]),
+    "okb_set_blocking_sync": (i32, [vp, i32]),
     "okb_detect_describe": (i32, [vp, i32, vp, C.c_size_t, vp, vp, i32, vp]),
     "okb_detect_describe_batch": (i32, [vp, i32, i32, vp, C.c_size_t, vp, vp, i32, vp]),
     "okb_detect_describe_batch_device": (i32, [vp, i32, i32, vp]),
