@@ -551,6 +551,33 @@ OKB_HDN void refine_candidate(const LayerView* L, int n_layers, int layer, int x
   if (max > (float)threshold) { r.x = x; r.y = y; r.size = basicSize * scale; r.response = max; r.keep = 1; }
 }
 
+// ---- tie-cell bitmap -------------------------------------------------------------------------------------------
+// One bit per 8x8-pixel cell of a layer, set when the 5x5 window of a tied (or not yet decided, "pending") candidate
+// intersects the cell. The touch-time map is only ever read inside those windows, so a maximum whose touch footprint
+// misses every flagged cell does not have to emit its touches. for_each_cell visits the bit indices of the cells that the
+// pixel box [x_lo, x_hi] x [y_lo, y_hi] covers (clipped to the layer on the low side and in x); f returns true to stop.
+constexpr int kCellShift = 3;
+constexpr int kCellWordsPerLayer = 2048;                   // 65536 cells: layers up to 2048 x 2048
+template <class F>
+OKB_HD bool for_each_cell(int layer_w, int x_lo, int x_hi, int y_lo, int y_hi, F f)
+{
+  const int cw = (layer_w + (1 << kCellShift) - 1) >> kCellShift;
+  for (int cy = imax(y_lo, 0) >> kCellShift; cy <= (y_hi >> kCellShift); cy++)
+    for (int cx = imax(x_lo, 0) >> kCellShift; cx <= imin(x_hi >> kCellShift, cw - 1); cx++)
+      if (f(cy * cw + cx)) return true;
+  return false;
+}
+// footprint boxes of a maximum's cache touches: own layer (x-1..x+2, y-1..y+2 covers both the 3x3 and the 4x4 patch) and
+// the window of its above-layer scan with the bilinear / 3x3 margins, in coordinates of layer + 1
+struct TouchBox { int x_lo, x_hi, y_lo, y_hi; };
+OKB_HD TouchBox own_touch_box(int x, int y) { return TouchBox{x - 1, x + 2, y - 1, y + 2}; }
+
+OKB_HD TouchBox above_touch_box(int layer, int x, int y)
+{
+  ScanIter it; above_window(layer, x, y, it);
+  return TouchBox{(int)it.x_1 - 1, (int)it.x1 + 2, (int)it.y_1 - 1, (int)it.y1 + 2};
+}
+
 // ---- touch-time map (state of the reference's lazily filled score cache) --------------------------------------
 // time key of a candidate = its position in the sequential processing order (layer, y, x)
 OKB_HD uint32_t time_key(int layer, int x, int y) { return ((uint32_t)layer << 22) | ((uint32_t)y << 11) | (uint32_t)x; }

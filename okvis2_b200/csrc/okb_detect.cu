@@ -196,30 +196,20 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
-// Tie-cell bitmap: one bit per 8x8-pixel cell of every layer, set when the 5x5 window of a tied (or still pending)
-// candidate intersects the cell. The touch-time map is only ever read inside those windows (k_resolve), so a maximum
-// whose touch footprint misses every flagged cell does not have to emit its touches at all (k_refine).
-constexpr int kCellShift = 3;
-constexpr int kCellWordsPerLayer = 2048;                   // 65536 cells: layers up to 2048 x 2048
+// Tie-cell bitmap (okb_core.h: for_each_cell): flagged by the score kernel around tied / pending candidates, tested by
+// k_refine before it emits the touches of a maximum.
 constexpr int kCellWordsPerFrame = kMaxLayers * kCellWordsPerLayer;
 __device__ __forceinline__ void cells_flag(uint32_t* cells /*layer*/, int layer_w, int x_lo, int x_hi, int y_lo, int y_hi)
 {
-  const int cw = (layer_w + (1 << kCellShift) - 1) >> kCellShift;
-  for (int cy = max(y_lo, 0) >> kCellShift; cy <= (y_hi >> kCellShift); cy++)
-    for (int cx = max(x_lo, 0) >> kCellShift; cx <= min(x_hi >> kCellShift, cw - 1); cx++) {
-      const int b = cy * cw + cx;
-      if (b < kCellWordsPerLayer * 32) atomicOr(&cells[b >> 5], 1u << (b & 31));
-    }
+  for_each_cell(layer_w, x_lo, x_hi, y_lo, y_hi, [&](int b) {
+    if (b < kCellWordsPerLayer * 32) atomicOr(&cells[b >> 5], 1u << (b & 31));
+    return false;
+  });
 }
-__device__ __forceinline__ bool cells_any(const uint32_t* cells /*layer*/, int layer_w, int x_lo, int x_hi, int y_lo, int y_hi)
+__device__ __forceinline__ bool cells_any(const uint32_t* cells /*layer*/, int layer_w, const TouchBox& t)
 {
-  const int cw = (layer_w + (1 << kCellShift) - 1) >> kCellShift;
-  for (int cy = max(y_lo, 0) >> kCellShift; cy <= (y_hi >> kCellShift); cy++)
-    for (int cx = max(x_lo, 0) >> kCellShift; cx <= min(x_hi >> kCellShift, cw - 1); cx++) {
-      const int b = cy * cw + cx;
-      if (b >= kCellWordsPerLayer * 32 || ((__ldg(&cells[b >> 5]) >> (b & 31)) & 1u)) return true;
-    }
-  return false;
+  return for_each_cell(layer_w, t.x_lo, t.x_hi, t.y_lo, t.y_hi,
+                       [&](int b) { return b >= kCellWordsPerLayer * 32 || ((__ldg(&cells[b >> 5]) >> (b & 31)) & 1u); });
 }
 
 // Fused score + non-max suppression. Tile = kTileW x kTileH (64 x 64) pixels of one layer of one frame, 256 threads.
@@ -495,12 +485,8 @@ __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ DeviceLa
     const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
     const uint32_t* cells = tie_cells + (size_t)frame * kCellWordsPerFrame;
     bool hit = false;
-    if (r.own_touch) hit = cells_any(cells + layer * kCellWordsPerLayer, dl.l[layer].w, x - 1, x + 2, y - 1, y + 2);
-    if (!hit && r.has_above) {
-      ScanIter it; above_window(layer, x, y, it);
-      hit = cells_any(cells + (layer + 1) * kCellWordsPerLayer, dl.l[layer + 1].w, (int)it.x_1 - 1, (int)it.x1 + 2, (int)it.y_1 - 1,
-                      (int)it.y1 + 2);
-    }
+    if (r.own_touch) hit = cells_any(cells + layer * kCellWordsPerLayer, dl.l[layer].w, own_touch_box(x, y));
+    if (!hit && r.has_above) hit = cells_any(cells + (layer + 1) * kCellWordsPerLayer, dl.l[layer + 1].w, above_touch_box(layer, x, y));
     emits = hit;
   }
   unsigned m = __ballot_sync(0xffffffffu, emits);

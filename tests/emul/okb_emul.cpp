@@ -38,7 +38,7 @@ static void resize_layer(const HostLayer& s, HostLayer& d)
 struct Cand { uint32_t key; int layer, x, y; bool tie; RefineResult r; int state; };
 
 extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int threshold, int octaves, int max_kp,
-                                        Kp* kp_out, uint8_t* desc_out, int cap, int* stats /*[4]: cands, ties, rounds, raw*/)
+                                        Kp* kp_out, uint8_t* desc_out, int cap, int* stats /*[5]: cands, ties, rounds, raw, skipped emissions*/)
 {
   if (!g_tables) { g_tables = new HostTables(); if (!build_host_tables(1.0f, *g_tables)) return -1; }
   const HostTables& T = *g_tables;
@@ -82,6 +82,59 @@ extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int th
       C.push_back(cd);
     }
   }
+  // phase (as the device does it): the same candidates from 64x64 score tiles. A strong pixel is tested against its
+  // in-tile neighbours only; one on the tile border that they do not beat is "pending" and finished from the complete
+  // map (k_refine). The result must be the candidate set above, tie flags included.
+  {
+    constexpr int TW = 64, TH = 64;
+    std::vector<std::pair<uint32_t, bool>> tiled;
+    for (int i = 0; i < n_layers; i++) {
+      const HostLayer& l = HL[i];
+      for (int y0 = 0; y0 < l.h; y0 += TH) for (int x0 = 0; x0 < l.w; x0 += TW)
+        for (int y = y0; y < std::min(y0 + TH, l.h); y++) for (int x = x0; x < std::min(x0 + TW, l.w); x++) {
+          const int c = l.score[(size_t)y * l.pitch + x];
+          if (c < threshold) continue;
+          bool is_c = true, tie = false, pending = false;
+          for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
+            if (!dx && !dy) continue;
+            const int xx = x + dx, yy = y + dy;
+            if (xx >= x0 && xx < x0 + TW && yy >= y0 && yy < y0 + TH) {
+              const int v = l.score[(size_t)yy * l.pitch + xx];
+              if (v > c) is_c = false;
+              if (v == c) tie = true;
+            } else pending = true;
+          }
+          if (!is_c) continue;
+          if (pending) {   // completion from the global map
+            tie = false;
+            for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
+              if (!dx && !dy) continue;
+              const int v = l.score[(size_t)(y + dy) * l.pitch + x + dx];
+              if (v > c) is_c = false;
+              if (v == c) tie = true;
+            }
+            if (!is_c) continue;
+          }
+          tiled.push_back({time_key(i, x, y), tie});
+        }
+    }
+    std::vector<std::pair<uint32_t, bool>> dense;
+    for (const Cand& c : C) dense.push_back({c.key, c.tie});
+    std::sort(tiled.begin(), tiled.end()); std::sort(dense.begin(), dense.end());
+    if (tiled != dense) return -2000;
+  }
+  // tie-cell bitmap: cells around tied candidates and around candidates on a tile border (pending when the score kernel
+  // flags them); non-tied maxima whose touch footprint misses every flagged cell do not emit
+  std::vector<std::vector<uint32_t>> cells(n_layers, std::vector<uint32_t>(kCellWordsPerLayer, 0u));
+  for (const Cand& c : C) {
+    const bool on_tile_border = c.x % 64 == 0 || c.x % 64 == 63 || c.y % 64 == 0 || c.y % 64 == 63;
+    if (c.tie || on_tile_border)
+      for_each_cell(HL[c.layer].w, c.x - 2, c.x + 2, c.y - 2, c.y + 2, [&](int b) { cells[c.layer][b >> 5] |= 1u << (b & 31); return false; });
+  }
+  auto any_cell = [&](int layer, const TouchBox& t) {
+    return for_each_cell(HL[layer].w, t.x_lo, t.x_hi, t.y_lo, t.y_hi, [&](int b) { return ((cells[layer][b >> 5] >> (b & 31)) & 1u) != 0; });
+  };
+  int emissions_skipped = 0;
   const uint32_t epoch = 1;
   auto touch = [&](int layer, int x, int y, uint32_t time) {
     HostLayer& l = HL[layer];
@@ -110,7 +163,13 @@ extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int th
     }
   };
   // phase: refine (pure) + touches of the non-tie maxima
-  for (auto& c : C) { refine_candidate(L, n_layers, c.layer, c.x, c.y, threshold, c.r); if (!c.tie) emit(c); }
+  for (auto& c : C) {
+    refine_candidate(L, n_layers, c.layer, c.x, c.y, threshold, c.r);
+    if (c.tie || !(c.r.own_touch || c.r.has_above)) continue;
+    bool hit = c.r.own_touch && any_cell(c.layer, own_touch_box(c.x, c.y));
+    if (!hit && c.r.has_above) hit = any_cell(c.layer + 1, above_touch_box(c.layer, c.x, c.y));
+    if (hit) emit(c); else emissions_skipped++;
+  }
   // phase: resolve ties in dependency rounds
   std::vector<int> ties;
   for (size_t i = 0; i < C.size(); i++) if (C[i].tie) ties.push_back((int)i);
@@ -205,6 +264,6 @@ extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int th
     kp_out[k] = p;
   }
   if (closed_form_mismatches) return -1000 - closed_form_mismatches;
-  if (stats) { stats[0] = (int)C.size(); stats[1] = (int)ties.size(); stats[2] = rounds; stats[3] = raw; }
+  if (stats) { stats[0] = (int)C.size(); stats[1] = (int)ties.size(); stats[2] = rounds; stats[3] = raw; stats[4] = emissions_skipped; }
   return (int)kps.size();
 }

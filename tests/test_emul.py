@@ -1,6 +1,7 @@
 """CPU suite: the *parallel formulation* implemented by the CUDA kernels (same per-element code, okvis2_b200/csrc/okb_core.h,
 executed serially by tests/emul/okb_emul.cpp) must reproduce the oracle bit for bit, including the order-dependent
-tie-breaks of the reference's lazily cached score map."""
+tie-breaks of the reference's lazily cached score map, the 64x64-tile candidate generation with "pending" border candidates
+(the emulator returns -2000 when it differs from the dense 3x3 test) and the tie-cell filter that skips touch emissions."""
 import ctypes as C
 import os
 import subprocess
@@ -26,7 +27,7 @@ def emul():
 
     def run(img, thr, octv, max_kp=0, cap=1 << 16):
         img = np.ascontiguousarray(img)
-        kp = np.zeros(cap, oracle.KP_DTYPE); d = np.zeros((cap, 64), np.uint8); st = np.zeros(4, np.int32)
+        kp = np.zeros(cap, oracle.KP_DTYPE); d = np.zeros((cap, 64), np.uint8); st = np.zeros(5, np.int32)
         n = lib.okb_emul_detect_describe(img.ctypes.data, img.shape[1], img.shape[0], thr, octv, max_kp, kp.ctypes.data,
                                          d.ctypes.data, cap, st.ctypes.data)
         return kp[:n], d[:n], st
@@ -40,6 +41,7 @@ def test_parallel_formulation_equals_oracle(emul, seed, W, H, thr, octv, max_kp)
     rk, rd = oracle.Brisk(thr, octv).detect_and_compute(img, max_kp)
     kp, d, st = emul(img, thr, octv, max_kp)
     assert st[1] > 0, "the case must exercise tied maxima"
+    assert st[4] > 0, "the tie-cell filter must have skipped some touch emissions"
     assert_same_features(kp, d, rk, rd, f"seed {seed}")
 
 
