@@ -873,6 +873,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Devic
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
       const uint32_t prefix = sel_prefix;
+      const int rem = sel_remaining;   // read here, a barrier away from the owner lane's update below (racecheck-clean)
       const uint32_t himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
       for (int i = threadIdx.x; i < V; i += blockDim.x) {
         const uint32_t rb = resp[i];
@@ -885,7 +886,6 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Devic
         int mine = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) mine += hist[lane * 8 + j];
-        const int rem = sel_remaining;
         int suffix = mine;   // inclusive suffix sum over the lanes (higher lanes own higher bins)
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, suffix, o); if (lane + o < 32) suffix += t; }
