@@ -218,10 +218,11 @@ __device__ __forceinline__ bool cells_any(const uint32_t* cells /*layer*/, int l
 //   2. the bytes are expanded once into two 16x2 planes, E[r][k] = (p[2k], p[2k+1]) and O[r][k] = (p[2k+1], p[2k+2]):
 //      every ring sample of a horizontal pixel PAIR is then a single conflict-free LDS.32 (E for even dx, O for odd dx)
 //      and the main loop is nothing but the 81 VIMNMX3.U16x2 of b0_pair (the ALU pipe is this kernel's limiter);
-//   3. a warp owns a tile row per iteration (lane = pixel pair): dense scores b0 go to the global score map (64
-//      contiguous bytes per warp) and to a shared score tile; pixels with score >= threshold ("strong", a few per
-//      cent) are appended to a shared list;
-//   4. the strong pixels get the 3x3 non-max test from the shared score tile. A strong pixel ON the tile border whose
+//   3. a warp owns a tile row per iteration (lane = pixel pair, 8 rows per warp): dense scores b0 go to the global score
+//      map (64 contiguous bytes per warp) and to a shared score tile; the pixels with score >= threshold ("strong", a few
+//      per cent) of a row leave the loop as two ballots (even / odd pixels), no atomics inside the loop;
+//   4. the ballots are compacted into a dense list and the strong pixels get the 3x3 non-max test from the shared score
+//      tile, one per thread. A strong pixel ON the tile border whose
 //      in-tile neighbours do not already beat it is emitted with the PENDING flag (bit 30): its out-of-tile neighbours
 //      are scores of another CTA, so k_refine finishes the test from the global map (complete by then). There is no
 //      score halo, i.e. no pixel is scored twice.
@@ -229,7 +230,7 @@ __device__ __forceinline__ bool cells_any(const uint32_t* cells /*layer*/, int l
 constexpr int kHaloX = 16;           // measured on B200: the innermost TMA coordinate must be a multiple of 16 bytes
                                      // (bench/tma_probe.cu: x = -8, 8, 376 raise "illegal instruction", -16, 0, 384 work)
 constexpr int kImgW = kTileW + 2 * kHaloX;   // bytes per staged image row: x0-16 .. x0+79
-constexpr int kImgH = kTileH + 6;    // rows y0-3 .. y0+34
+constexpr int kImgH = kTileH + 6;    // rows y0-3 .. y0+66
 constexpr int kExp0 = 3, kExp1 = 21; // staged words (4 bytes) that are expanded: bytes 12 .. 83 cover x0-4 .. x0+67
 constexpr int kPlaneW = 2 * (kExp1 - kExp0);   // 16x2 words per plane row; plane word j holds staged bytes 2j+12 (E) / 2j+13 (O)
 constexpr int kScoreThreads = 256;
