@@ -539,10 +539,16 @@ def main():
     # profiles/r01_ncu_full_v10_score_nms_raw.csv (dram__bytes_read.sum 22.218 MB + dram__bytes_write.sum 0.077 MB), euroc config
     traffic = 22.30e6 if args.config == "euroc" and B == 32 else None
     ach_k = ps_bytes * B * passes / (score_total_ms * 1e-3) / 1e9 if score_total_ms > 0 else 0.0
+    # the limiter that actually binds k_score_nms: 81 VIMNMX3.U16x2 per pixel pair on the ALU pipe, which issues one warp
+    # instruction per 2 cycles per SM sub-partition (bench/ubench_pipes.cu) -> floor time per launch at the sampled SM clock
+    sm_hz = 1.965e9
+    pairs_per_launch = (ps_bytes / 2) / 2 * B           # scored pixels of all layers / 2
+    alu_floor_ms = 81 * (pairs_per_launch / 32) * 2 / (148 * 4) / sm_hz * 1e3
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "kernel": "pyramid+score pass (k_resize launches + k_score_nms, TMA-staged tiles)", "bytes_per_image": int(ps_bytes),
                 "dominant_kernel": {"name": "k_score_nms", "ms_per_launch": score_total_ms / passes, "achieved_GBps": ach_k,
-                                    "frac": ach_k / peak, "limiter": "ALU pipe (79% busy, 64 lanes/clk/SM: 81 VIMNMX3.U16x2 per pixel pair = 49 us floor per 32 frames), not HBM"},
+                                    "frac": ach_k / peak, "alu_floor_ms": alu_floor_ms,
+                                    "alu_frac": (alu_floor_ms / (score_total_ms / passes)) if score_total_ms > 0 else None, "limiter": "ALU pipe (79% busy, 64 lanes/clk/SM: 81 VIMNMX3.U16x2 per pixel pair = 49 us floor per 32 frames), not HBM"},
                 "images_per_pass": B, "ms_per_pass": ps_total_ms / passes, "launches_per_pass": ps_total_launches / passes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                 "measured": f"CUDA events on the launching stream, {roof_steps} extra steps right after the timed region with the two camera streams serialized (they overlap in the timed region)"}

@@ -236,7 +236,7 @@ constexpr int kPlaneW = 2 * (kExp1 - kExp0);   // 16x2 words per plane row; plan
 constexpr int kScoreThreads = 256;
 constexpr uint32_t kCandTie = 0x80000000u, kCandPending = 0x40000000u, kCandKeyMask = 0x3fffffffu;
 
-__global__ void __launch_bounds__(kScoreThreads, 5) k_score_nms(const __grid_constant__ TmaMaps maps, const __grid_constant__ DeviceLayers dl,
+__global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_constant__ TmaMaps maps, const __grid_constant__ DeviceLayers dl,
                                                              const __grid_constant__ TileMap tm,
                                                              const uint8_t* in0, int in_pitch, size_t in_frame_stride,
                                                              uint8_t* img_block, uint8_t* score_block, uint32_t* cand,
