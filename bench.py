@@ -551,6 +551,7 @@ def main():
                                     "alu_frac": (alu_floor_ms / (score_total_ms / passes)) if score_total_ms > 0 else None, "limiter": "ALU pipe (79% busy, 64 lanes/clk/SM: 81 VIMNMX3.U16x2 per pixel pair = 49 us floor per 32 frames), not HBM"},
                 "images_per_pass": B, "ms_per_pass": ps_total_ms / passes, "launches_per_pass": ps_total_launches / passes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                "frac_of_nominal_8000_GBps": ach / 8000.0,
                 "measured": f"CUDA events on the launching stream, {roof_steps} extra steps right after the timed region with the two camera streams serialized (they overlap in the timed region)"}
 
     # more waiting host threads than cores (many ranks per box): sleep instead of spinning while a batch is on the device
