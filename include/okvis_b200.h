@@ -232,7 +232,8 @@ int okb_match_stereo_device(okb_context_t* ctx, int cam0, int cam1, int n_frames
                             uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_initialisable);
 /* Same on explicit device feature blocks (e.g. a peer camera's block received by NCCL all-gather): keypoints
  * [n_frames][cap], descriptors [n_frames][cap][64], counts [n_frames]. `stream` = cudaStream_t (NULL: the context's
- * match stream); the caller orders it after the producers of the inputs. */
+ * match stream); the caller orders it after the producers of the inputs. The call uses one scratch area per context:
+ * calls of one context must be issued on streams that serialise them (different contexts are independent). */
 int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, const okb_keypoint_t* d_kp0, const uint8_t* d_desc0,
                                 const int32_t* d_count0, const okb_camera_model_t* model0, const double C_WC0[9],
                                 const double r_WC0[3], int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
