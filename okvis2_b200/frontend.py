@@ -191,6 +191,32 @@ class Frontend:
             out[k] = out[k][:nr]
         return out
 
+    def matchToMap(self, cameraIndex, T_WC1, T_CW1, width, height, hp_W, quality, obs_begin, obs, T_WC_old,
+                   reprThreshold=20.0, exclusive=False):
+        """The device part of Frontend::matchToMap for one camera (Frontend.cpp:1196-1408): prepare the landmark pool
+        (P1), then match the keypoints of the LAST detectAndDescribe of this camera against it (M1) without the pool leaving
+        the device. Returns (distances, landmark index per keypoint row into the caller's hp_W order or -1, the prepared pool);
+        the arrays have one entry per keypoint ROW of the device block (capacity), the first numKeypoints are the frame's."""
+        pool = self.prepareLandmarksToMatch(cameraIndex, T_WC1, T_CW1, width, height, hp_W, quality, obs_begin, obs, T_WC_old,
+                                            reprThreshold, exclusive)
+        L = _l.lib()
+        p = [C.c_void_p() for _ in range(4)]; nc = C.c_int32(); nl = C.c_int32()
+        check(L.okb_prepared_device(self._ctx, *[C.byref(x) for x in p], C.byref(nc), C.byref(nl)))
+        d_kp = C.c_void_p(); d_desc = C.c_void_p(); d_cnt = C.c_void_p(); cap = C.c_int(0)
+        check(L.okb_device_features(self._ctx, cameraIndex, C.byref(d_kp), C.byref(d_desc), C.byref(d_cnt), C.byref(cap)))
+        import torch   # device buffers for the M1 outputs (plumbing only)
+        dist = torch.zeros(cap.value, dtype=torch.int32, device=f"cuda:{self._device}")
+        lm = torch.zeros(cap.value, dtype=torch.int32, device=f"cuda:{self._device}")
+        check(L.okb_match_map3d_device(self._ctx, cameraIndex, 1, nc.value, p[0], p[1], nl.value, p[2], p[3], float(reprThreshold),
+                                       int(self.briskMatchingThreshold_), dist.data_ptr(), lm.data_ptr()))
+        check(L.okb_sync(self._ctx))
+        dist = dist.cpu().numpy().view(np.uint32); lm = lm.cpu().numpy()   # rows >= the frame's keypoint count: "no match"
+        idx = np.full(len(lm), -1, np.int32)
+        if len(pool["lm"]):
+            hit = lm >= 0
+            idx[hit] = pool["lm"][lm[hit]]
+        return dist, idx, pool
+
     # ---- K1: keyframe-overlap masks (Frontend::doWeNeedANewKeyframe, ViSlamBackend::overlapFraction)
     keyframeInsertionOverlapThreshold_ = np.float32(0.55)   # Frontend.cpp:145
     kptrad = 0.09                                           # Frontend.cpp:104, ViSlamBackend.hpp:684

@@ -125,10 +125,14 @@ def test_prepared_pool_feeds_device_m1():
         d_dist = torch.zeros(cap.value, dtype=torch.int32, device="cuda"); d_lm = torch.zeros(cap.value, dtype=torch.int32, device="cuda")
         L.check(lib.okb_match_map3d_device(fe.ctx, 0, 1, nc.value, p[0], p[1], nl.value, p[2], p[3], 20.0, 60, d_dist.data_ptr(), d_lm.data_ptr()))
         L.check(lib.okb_sync(fe.ctx))
+        # the same through the mirror's one-call form
+        mdist, midx, _ = fe.matchToMap(0, s["T_WC1"], s["T_CW1"], W, H, s["hp_W"], s["quality"], s["obs_begin"], s["obs"], s["T_WC_old"])
         n = len(fr.keypoints)
         xy = np.stack([fr.keypoints["x"], fr.keypoints["y"]], 1).astype(np.float64)
         rdist, rlm = oracle.match_map3d(fr.descriptors, xy, None, ref["cand_desc"], ref["cand_lm"], ref["lm_proj"], ref["lm_is3d"], 20.0, 60)
         assert np.array_equal(d_dist.cpu().numpy()[:n].astype(np.uint32), rdist.astype(np.uint32))
         assert np.array_equal(d_lm.cpu().numpy()[:n], rlm)
+        assert np.array_equal(mdist[:n], rdist.astype(np.uint32))
+        assert np.array_equal(midx[:n], np.where(rlm >= 0, ref["lm"][np.clip(rlm, 0, None)], -1))
     finally:
         fe.close()
