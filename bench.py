@@ -384,7 +384,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="euroc", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-lanes", "--lanes", dest="e2e_lanes", type=int, default=3,
+    ap.add_argument("--e2e-lanes", "--lanes", dest="e2e_lanes", type=int, default=4,
                     help="independent sequences in flight per GPU (own library handle each) in the value and e2e legs")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
