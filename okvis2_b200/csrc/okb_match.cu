@@ -626,12 +626,22 @@ __global__ void __launch_bounds__(256) k_m4_scan(MatchArgs a, uint2* hits, int32
     const int jn = min(kQT, nq - q0);
     for (int j = 0; j < jn; j++) {
       if (!s_act[j]) continue;   // CTA-uniform
-      uint32_t d = 0;
-#pragma unroll
-      for (int w = H; w < D16; w++) {
-        const uint4 qv = sq[j][w];
-        d += __popcll(((unsigned long long)(qv.x ^ cd[w].x) << 32) | (qv.y ^ cd[w].y));
-        d += __popcll(((unsigned long long)(qv.z ^ cd[w].z) << 32) | (qv.w ^ cd[w].w));
+      // popcount of the 256 bits of the second descriptor half through a carry-save adder tree: 8 words -> ones / twos /
+      // fours / eights planes (14 LOP3 on the ALU pipe), then 4 POPC instead of 8 -- POPC (XU pipe) is this kernel's bound
+      static_assert(D16 == 4, "the adder tree below is written for 2 x uint4 per half");
+      uint32_t d;
+      {
+        const uint4 q0v = sq[j][H], q1v = sq[j][H + 1];
+        const uint32_t x0 = q0v.x ^ cd[H].x, x1 = q0v.y ^ cd[H].y, x2 = q0v.z ^ cd[H].z, x3 = q0v.w ^ cd[H].w;
+        const uint32_t x4 = q1v.x ^ cd[H + 1].x, x5 = q1v.y ^ cd[H + 1].y, x6 = q1v.z ^ cd[H + 1].z, x7 = q1v.w ^ cd[H + 1].w;
+        const uint32_t s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | (x2 & (x0 | x1));
+        const uint32_t s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | (x5 & (x3 | x4));
+        const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 | s2));
+        const uint32_t ones = s3 ^ x7, c4 = s3 & x7;
+        const uint32_t t1 = c1 ^ c2 ^ c3, f1 = (c1 & c2) | (c3 & (c1 | c2));
+        const uint32_t twos = t1 ^ c4, f2 = t1 & c4;
+        const uint32_t fours = f1 ^ f2, eights = f1 & f2;
+        d = __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
       }
       if (!valid_c) d = 0xffffu;
       if (!__any_sync(0xffffffffu, d < a.thr)) continue;
