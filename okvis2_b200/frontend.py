@@ -302,6 +302,38 @@ class Frontend:
         check(_l.lib().okb_bow_transform(self._ctx, len(d), ptr(d), int(levelsup), ptr(word), ptr(weight), ptr(node)))
         return word, weight, node
 
+    def bowTransformImage(self, descriptors, levelsup=0):
+        """TemplatedVocabulary::transform(features, bowVector, featureVector, levelsup) for TF_IDF weighting + L1 scoring: the
+        per-feature descents run on the device (okb_bow_transform), the accumulation into the sparse vectors -- DBoW2's own
+        bookkeeping -- on the host in feature order. Returns (sorted [(word, weight)], {node: [feature indices]})."""
+        word, weight, node = self.bowTransform(descriptors, levelsup)
+        v, fv = {}, {}
+        for i in range(len(word)):
+            if weight[i] > 0:
+                w = int(word[i])
+                v[w] = v.get(w, 0.0) + float(weight[i])
+                fv.setdefault(int(node[i]), []).append(i)
+        items = sorted(v.items())
+        norm = 0.0
+        for _, w in items:
+            norm += abs(w)
+        if norm > 0.0:
+            items = [(k, w / norm) for k, w in items]
+        return items, fv
+
+    @staticmethod
+    def bowScoreL1(v1, v2):
+        """DBoW2::L1Scoring::score of two normalised BowVectors."""
+        score, i, j = 0.0, 0, 0
+        while i < len(v1) and j < len(v2):
+            if v1[i][0] == v2[j][0]:
+                score += abs(v1[i][1] - v2[j][1]) - abs(v1[i][1]) - abs(v2[j][1]); i += 1; j += 1
+            elif v1[i][0] < v2[j][0]:
+                i += 1
+            else:
+                j += 1
+        return -score / 2.0
+
     def initialiseBriskFeatureDetectors(self):
         """Frontend::initialiseBriskFeatureDetectors (Frontend.cpp:2398-2417): (re)create the per-camera objects."""
         self.close()

@@ -50,3 +50,40 @@ class Vocabulary:
             if not self.children[final_id]:
                 break
         return int(self.word[final_id]), float(self.weight[final_id]), nid
+
+
+def transform_image(voc, features, levelsup=0):
+    """TemplatedVocabulary::transform(features, BowVector, FeatureVector, levelsup) for TF_IDF weighting and L1 scoring (the
+    types stored in small_voc.yml.gz: weightingType 0, scoringType 0), restated from the published DBoW2 source: every
+    feature adds its leaf's weight to its word (skipped when the weight is 0 = stopped word) and its index to the node
+    `levelsup` levels above the leaves; L1 scoring normalises the vector by the sum of its weights (words in id order).
+    Returns (sorted [(word id, weight)], {node id: [feature indices]})."""
+    v, fv = {}, {}
+    for i, f in enumerate(features):
+        word, w, nid = voc.transform(f, levelsup)
+        if w > 0:
+            v[word] = v.get(word, 0.0) + w
+            fv.setdefault(nid, []).append(i)
+    items = sorted(v.items())
+    norm = 0.0
+    for _, w in items:
+        norm += abs(w)
+    if norm > 0.0:
+        items = [(k, w / norm) for k, w in items]
+    return items, fv
+
+
+def score_l1(v1, v2):
+    """DBoW2::L1Scoring::score on two normalised BowVectors (sorted (word, weight) lists): 1 - 0.5 * ||v1 - v2||_1, summed
+    over the common words as |a - b| - |a| - |b| in word order."""
+    score, i, j = 0.0, 0, 0
+    while i < len(v1) and j < len(v2):
+        if v1[i][0] == v2[j][0]:
+            a, b = v1[i][1], v2[j][1]
+            score += abs(a - b) - abs(a) - abs(b)
+            i += 1; j += 1
+        elif v1[i][0] < v2[j][0]:
+            i += 1
+        else:
+            j += 1
+    return -score / 2.0

@@ -8,7 +8,7 @@ import pytest
 from conftest import ROOT
 from okvis2_b200 import formats
 from okvis2_b200.lib import KP_DTYPE
-from oracle.bow_oracle import Vocabulary
+from oracle.bow_oracle import Vocabulary, score_l1, transform_image
 
 
 @pytest.fixture(scope="module")
@@ -32,6 +32,19 @@ def test_oracle_descent_on_the_vocabulary_itself(voc, voc_desc):
     assert hits > 600
     # levelsup = L: the root
     assert v.transform(voc_desc[20], levelsup=3)[2] == 0
+
+
+def test_oracle_image_vectors(voc, voc_desc):
+    t, v = voc
+    rng = np.random.default_rng(2)
+    a = voc_desc[rng.choice(819, 300)]; b = a.copy(); b[:150] = voc_desc[rng.choice(819, 150)]
+    va, fa = transform_image(v, a, levelsup=2)
+    vb, _ = transform_image(v, b, levelsup=2)
+    assert abs(sum(w for _, w in va) - 1.0) < 1e-12 and all(w > 0 for _, w in va) and [k for k, _ in va] == sorted(k for k, _ in va)
+    assert sorted(i for idx in fa.values() for i in idx) == [i for i in range(300) if v.transform(a[i])[1] > 0]
+    assert all(n in range(1, 10) for n in fa)                       # levelsup = 2 of L = 3: the 9 first-level nodes
+    assert abs(score_l1(va, va) - 1.0) < 1e-12 and 0.0 < score_l1(va, vb) < 1.0
+    assert score_l1(va, []) == 0.0
 
 
 def test_fbrisk_string_round_trip(voc_desc):
@@ -71,5 +84,12 @@ def test_device_descent_equals_oracle(voc, voc_desc):
                 assert (word[i], weight[i], node[i]) == v.transform(feats[i], levelsup), (i, levelsup)
         w0, _, _ = fe.bowTransform(feats[:0])
         assert len(w0) == 0
+        # image-level vectors (BowVector / FeatureVector) and the L1 score
+        va, fa = fe.bowTransformImage(feats[:400], levelsup=2)
+        ra, rfa = transform_image(v, feats[:400], levelsup=2)
+        assert va == ra and fa == rfa
+        vb, _ = fe.bowTransformImage(feats[819:1300], levelsup=2)
+        rb, _ = transform_image(v, feats[819:1300], levelsup=2)
+        assert fe.bowScoreL1(va, vb) == score_l1(ra, rb) and 0.0 < score_l1(ra, rb) < 1.0
     finally:
         fe.close()
