@@ -620,8 +620,10 @@ OKB_HDN void for_each_above_touch(int layer, int x_layer, int y_layer, const Sca
 OKB_HD void above_query_pos(const ScanIter& it, int q, int& X, int& Y, bool& block2x2)
 {
   const int nx = imax(it.xb - it.xa + 1, 0), ny = imax(it.yb - it.ya + 1, 0);
-  const int rowlen = nx + 2;
-  const int r = q / rowlen, c = q % rowlen;
+  const int rowlen = nx + 2;   // 2, 3 or 4 for the 4/3x and 3/2x windows; q < 32
+  // q / rowlen without the emulated integer division ((q * 11) >> 5 == q / 3 for q < 32)
+  const int r = rowlen == 2 ? (q >> 1) : (rowlen == 4 ? (q >> 2) : (rowlen == 3 && q < 32 ? (q * 11) >> 5 : q / rowlen));
+  const int c = q - r * rowlen;
   X = c == 0 ? (int)it.x_1 : (c == rowlen - 1 ? (int)it.x1 : it.xa + c - 1);
   Y = r == 0 ? (int)it.y_1 : (r == ny + 1 ? (int)it.y1 : it.ya + r - 1);
   block2x2 = (r == 0) || (r == ny + 1) || (c == 0) || (c == rowlen - 1);
