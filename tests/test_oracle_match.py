@@ -65,3 +65,24 @@ def test_m4_true_matches_and_gates():
     assert (s["idx1"][k1[m]] == s["idx0"][m]).mean() > 0.99
     assert (dist[~m] == 60).all() and (hp[~m] == 0).all()
     assert (s["valid0"][m] == 1).all() and (s["valid1"][k1[m]] == 1).all()
+
+
+def test_triangulate_fast_equals_least_squares_midpoint():
+    """Independent check of the G1 restatement (stereo_triangulation.cpp:50-132): in the regular branch the result is the
+    midpoint of the common perpendicular of the two rays, which numpy's least-squares solver gives directly."""
+    rng = np.random.default_rng(9)
+    n_regular = 0
+    for _ in range(300):
+        p1 = rng.normal(0, 0.2, 3); p2 = p1 + rng.normal(0, 0.3, 3)
+        X = rng.normal(0, 1.0, 3) + np.array([0, 0, 6.0])
+        e1 = X - p1 + rng.normal(0, 0.01, 3); e1 /= np.linalg.norm(e1)
+        e2 = X - p2 + rng.normal(0, 0.01, 3); e2 /= np.linalg.norm(e2)
+        hp, valid, parallel = oracle.triangulate_fast(p1, e1, p2, e2, 0.01)
+        lam = np.linalg.lstsq(np.stack([e1, -e2], 1), p2 - p1, rcond=None)[0]
+        if lam[0] < 0.01 or lam[1] < 0.01:
+            assert parallel
+            continue
+        mid = 0.5 * ((p1 + lam[0] * e1) + (p2 + lam[1] * e2))
+        assert np.allclose(hp[:3], mid, rtol=0, atol=1e-9) and hp[3] == 1.0
+        n_regular += 1
+    assert n_regular > 250
