@@ -273,7 +273,7 @@ def run_sharded(args, cfg, rank, world, local_rank):
             frames = d_img[li][(s % ring) * B:(s % ring + 1) * B]
             okl.check(L_.okb_detect_describe_batch_device(ctx, li, B, frames.data_ptr()))
             dm = d_maps[li]
-            okl.check(L_.okb_match_map3d_device(ctx, li, B, len(dm["lm"]), dm["desc"].data_ptr(), dm["lm"].data_ptr(), len(dm["is3d"]),
+            okl.check(L_.okb_match_map3d_device(ctx, li, 64, B, len(dm["lm"]), dm["desc"].data_ptr(), dm["lm"].data_ptr(), len(dm["is3d"]),
                                                 dm["proj"].data_ptr(), dm["is3d"].data_ptr(), 20.0, 60, d_m1[li]["dist"].data_ptr(),
                                                 d_m1[li]["lm"].data_ptr()))
             okl.check(L_.okb_export_features(ctx, li, B, local[c // world].data_ptr()))
@@ -467,7 +467,7 @@ def main():
             frames = d_img[c][(s % ring) * B:(s % ring + 1) * B]
             okl.check(L_.okb_detect_describe_batch_device(cx, c, B, frames.data_ptr()))
             dm = d_maps[c]
-            okl.check(L_.okb_match_map3d_device(cx, c, B, len(dm["lm"]), dm["desc"].data_ptr(), dm["lm"].data_ptr(),
+            okl.check(L_.okb_match_map3d_device(cx, c, 64, B, len(dm["lm"]), dm["desc"].data_ptr(), dm["lm"].data_ptr(),
                                                 len(dm["is3d"]), dm["proj"].data_ptr(), dm["is3d"].data_ptr(), 20.0, 60,
                                                 d_out[c]["dist"].data_ptr(), d_out[c]["lm"].data_ptr()))
             chain[c].record(st[c])

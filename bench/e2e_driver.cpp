@@ -185,7 +185,7 @@ static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, st
     int rc = okb_detect_describe_batch(ctx, c, B, imgs, (size_t)io->W, io->kp[c], io->desc[c], cap, io->n[c]);
     const auto tb = now();
     t_det[c] += ms(ta, tb);
-    if (!rc) rc = okb_match_map3d_batch(ctx, c, B, io->n_cand[c], io->cand_desc[c], io->cand_lm[c], io->n_lm[c], io->lm_proj[c],
+    if (!rc) rc = okb_match_map3d_batch(ctx, c, 64, B, io->n_cand[c], io->cand_desc[c], io->cand_lm[c], io->n_lm[c], io->lm_proj[c],
                                         io->lm_is3d[c], 20.0, 60, cap, io->m1_dist[c], io->m1_lm[c]);
     t_m1[c] += ms(tb, now());
     rcs[c] = rc;

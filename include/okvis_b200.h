@@ -58,6 +58,11 @@ int okb_create(int device, int n_cams, const okb_camera_config_t* cfgs, okb_cont
 void okb_destroy(okb_context_t* ctx);
 const char* okb_last_error(void);
 const char* okb_version(void);
+/* 1 when the cos() the matchers' gates use (cos(2.6 sigma), cos(6 sigma) of triangulateFast, okvis_frontend/src/
+ * stereo_triangulation.cpp:82-127) was verified at okb_create to return exactly what this machine's libm returns on 65 536
+ * arguments. It is one function for the host-buffer and the device-resident matcher forms (a restatement of glibc's
+ * algorithm, csrc/okb_gatecos.h), so those agree by construction either way. */
+int okb_gate_cos_exact(const okb_context_t* ctx);
 /* number of kernels of this library launched on this context so far (bench.py's gpu_launches) */
 int64_t okb_launch_count(const okb_context_t* ctx);
 /* the CUDA stream (cudaStream_t as void*) camera `cam` works on; okb_sync waits for all of them */
@@ -197,8 +202,10 @@ int okb_hamming_matrix(okb_context_t* ctx, int D, int n_a, const uint8_t* a, int
  * okb_detect_describe_batch_device call left on the device for frames 0..n_frames-1 of camera `cam` against a
  * device-resident landmark pool. d_lm_proj holds one projection table per frame (n_frames x n_lm x 2 doubles: the
  * camera moves between frames). d_out_* hold n_frames x capacity entries (capacity from okb_device_features).
+ * D = bytes per pool row; it must equal the camera's descriptor_bytes (e.g. a D = 48 pool from okb_prepare_landmarks
+ * against a 64-byte camera is OKB_ERR_ARGUMENT, not a stride mismatch).
  * All d_* pointers are device pointers. Asynchronous on okb_stream(ctx, cam). */
-int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand, const uint8_t* d_cand_desc,
+int okb_match_map3d_device(okb_context_t* ctx, int cam, int D, int n_frames, int n_cand, const uint8_t* d_cand_desc,
                            const int32_t* d_cand_lm, int n_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
                            double reprojection_threshold, uint32_t match_threshold, uint32_t* d_out_dist,
                            int32_t* d_out_lm);
@@ -209,7 +216,7 @@ int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand
  * doubles (one projection table per frame). out_*: n_frames x cap entries in host memory; rows k >= n_out[b] of frame b
  * are unspecified. Page-locked caller buffers are read / written by the copy engines directly, pageable ones go through
  * the library's pinned staging. Synchronous (returns when the outputs are in place). */
-int okb_match_map3d_batch(okb_context_t* ctx, int cam, int n_frames, int n_cand, const uint8_t* cand_desc,
+int okb_match_map3d_batch(okb_context_t* ctx, int cam, int D, int n_frames, int n_cand, const uint8_t* cand_desc,
                           const int32_t* cand_lm, int n_lm, const double* lm_proj, const uint8_t* lm_is3d,
                           double reprojection_threshold, uint32_t match_threshold, int cap, uint32_t* out_dist,
                           int32_t* out_lm);
@@ -225,7 +232,7 @@ int okb_match_stereo_batch(okb_context_t* ctx, int cam0, int cam1, int n_frames,
 /* Device-resident, batched M4 for the benchmark "value" leg and the camera-sharded multi-GPU mode: stereo-matches the
  * features of camera cam0 (queries) against camera cam1 left on the device by okb_detect_describe_batch_device, frame by
  * frame. Back-projection (D4, camera models from okb_set_camera_model), e_W = (C_WC * e_C).normalized(), size/f and the
- * cos tables are computed on the device (cos within 1 ulp of libm). C_WC: row-major 3x3 rotation, r_WC: position.
+ * cos tables are computed on the device (by the same function as the host-buffer form: csrc/okb_gatecos.h, equal to libm). C_WC: row-major 3x3 rotation, r_WC: position.
  * Outputs: n_frames x capacity(cam0) entries, device pointers. */
 int okb_match_stereo_device(okb_context_t* ctx, int cam0, int cam1, int n_frames, const double C_WC0[9], const double r_WC0[3],
                             const double C_WC1[9], const double r_WC1[3], uint32_t match_threshold, int32_t* d_out_k1,

@@ -7,6 +7,7 @@
 #include <mutex>
 
 #include "okb_internal.h"
+#include "okb_gatecos.h"
 
 namespace okb {
 static thread_local char g_err[512] = "";
@@ -48,6 +49,10 @@ int okb_create(int device, int n_cams, const okb_camera_config_t* cfgs, okb_cont
   ctx->device = device; ctx->n_cams = n_cams; ctx->cams.resize(n_cams);
   float ps = n_cams > 0 ? cfgs[0].pattern_scale : 1.0f;
   if (ps <= 0.f) ps = 1.0f;
+  for (int i = 1; i < n_cams; i++) {   // the sampling-pattern tables are per context
+    const float pi = cfgs[i].pattern_scale <= 0.f ? 1.0f : cfgs[i].pattern_scale;
+    if (pi != ps) { set_error("okb_create: camera %d has pattern_scale %g, camera 0 has %g (one pattern table per context)", i, pi, ps); delete ctx; return OKB_ERR_ARGUMENT; }
+  }
   int rc = tables_init(ctx, ps);
   if (rc != OKB_OK) { delete ctx; return rc; }
   for (int i = 0; i < n_cams; i++) {
@@ -61,13 +66,28 @@ int okb_create(int device, int n_cams, const okb_camera_config_t* cfgs, okb_cont
                 i, c.descriptor_bytes);
       okb_destroy(ctx); return OKB_ERR_UNSUPPORTED;
     }
+    if (c.octaves < 0 || c.max_keypoints < 0 || c.max_keypoints >= (1 << 20)) {
+      set_error("camera %d: octaves %d / max_keypoints %d out of range", i, c.octaves, c.max_keypoints); okb_destroy(ctx); return OKB_ERR_ARGUMENT;
+    }
     if (c.threshold < 1 || c.threshold > 254) { set_error("camera %d: threshold %d", i, c.threshold); okb_destroy(ctx); return OKB_ERR_ARGUMENT; }
     rc = detect_init_camera(ctx, i);
     if (rc != OKB_OK) { okb_destroy(ctx); return rc; }
   }
   rc = match_init(ctx);
   if (rc != OKB_OK) { okb_destroy(ctx); return rc; }
-  OKB_CUDA(cudaDeviceSynchronize());
+  {
+    // self-check of the gate constants: gate_cos must return what THIS machine's libm returns (it restates glibc's
+    // algorithm, okb_gatecos.h); 65 536 arguments over the gate's range
+    uint64_t s = 88172645463325252ull; int bad = 0;
+    for (int i = 0; i < 65536; i++) {
+      s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+      const double x = (double)(s >> 11) / 9007199254740992.0 * ((i & 3) ? 0.5 : 0.855);
+      bad += gate_cos(x) != cos(x);
+    }
+    ctx->gate_cos_exact = bad == 0;
+  }
+  { const cudaError_t e2 = cudaDeviceSynchronize();
+    if (e2 != cudaSuccess) { set_error("okb_create: %s", cudaGetErrorString(e2)); okb_destroy(ctx); return OKB_ERR_CUDA; } }
   *out = ctx;
   return OKB_OK;
 }
@@ -86,6 +106,7 @@ void okb_destroy(okb_context_t* ctx)
   delete ctx;
 }
 
+int okb_gate_cos_exact(const okb_context_t* ctx) { return ctx ? ctx->gate_cos_exact : 0; }
 int64_t okb_launch_count(const okb_context_t* ctx) { return ctx ? ctx->launches : 0; }
 int okb_set_blocking_sync(okb_context_t* ctx, int on) { if (!ctx) return OKB_ERR_ARGUMENT; ctx->blocking_sync = on ? 1 : 0; return OKB_OK; }
 void* okb_stream(okb_context_t* ctx, int cam)

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "okb_internal.h"
+#include "okb_gatecos.h"
 
 namespace okb {
 
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(128) k_stereo_prep(PrepArgs p, const okb_keypo
   const double s = (double)kp[i].size / p.f;
   sof[i] = s;
   const double sigma = s * 0.125;
-  c26[i] = cos(2.6 * sigma); c6[i] = cos(6.0 * sigma);
+  c26[i] = gate_cos(2.6 * sigma); c6[i] = gate_cos(6.0 * sigma);   // == host libm, okb_gatecos.h
 }
 
 static Model to_model(const okb_camera_model_t& c)

@@ -141,6 +141,7 @@ struct okb_context {
   int timers_on = 0;
   void* stereo_scratch = nullptr; size_t stereo_cap = 0;   // device scratch of okb_match_stereo_device*
   int64_t launches = 0;
+  int gate_cos_exact = 0;    // okb_create's self-check: gate_cos == this machine's libm cos on 65 536 arguments
   int blocking_sync = 0;     // 1: host-buffer entry points wait on a cudaEventBlockingSync event (the thread sleeps) instead of spinning
   void* prepare = nullptr;   // okb::PrepareState (okb_prepare.cu): keyframe feature store + P1 workspace
   void* aux = nullptr;       // okb::AuxState (okb_aux.cu): keyframe-overlap / BoW workspaces

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include "okb_internal.h"
+#include "okb_gatecos.h"
 
 namespace okb {
 
@@ -36,7 +37,7 @@ __device__ __forceinline__ V3 normalized(V3 a)
 
 struct Tri { V3 p; bool valid, parallel; };
 
-// triangulation::triangulateFast; cos26 = cos(2.6 sigma), cos6 = cos(6 sigma) come from the host libm
+// triangulation::triangulateFast; cos26 = cos(2.6 sigma), cos6 = cos(6 sigma) come from gate_cos (okb_gatecos.h)
 __device__ Tri triangulate_fast(V3 p1, V3 e1, V3 p2, V3 e2, double cos26, double cos6)
 {
   Tri r; r.parallel = false; r.valid = true;
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(256) k_m4_scan(MatchArgs a, uint2* hits, int32
       }
       if (valid_c && d < a.thr) {
         const int pos = atomicAdd(&hit_cnt[frame], 1);
-        if (pos < a.hit_cap) hits[(size_t)frame * a.hit_cap + pos] = make_uint2((uint32_t)(q0 + j), (d << 16) | (uint32_t)c);
+        if (pos < a.hit_cap) hits[(size_t)frame * a.hit_cap + pos] = make_uint2((d << 20) | (uint32_t)(q0 + j), (uint32_t)c);   // d <= 512, q < 2^20
       }
     }
   }
@@ -667,8 +668,8 @@ __global__ void __launch_bounds__(128) k_m4_gate(MatchArgs a, const uint2* hits,
   const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint2 e = hits[(size_t)frame * a.hit_cap + i];
-    const int q = (int)e.x, c = (int)(e.y & 0xffffu);
-    const uint32_t d = e.y >> 16;
+    const int q = (int)(e.x & 0xfffffu), c = (int)e.y;
+    const uint32_t d = e.x >> 20;
     if (m4_gate(a, fq, fc, q, c).pass) atomicMin(&best[fq + q], ((unsigned long long)d << 32) | (unsigned)c);
   }
 }
@@ -775,6 +776,22 @@ void match_free(okb_context* ctx)
 
 static bool bad_D(int D) { return D != 48 && D != 64; }
 
+// host-side validation of a landmark pool (LandmarkToMatch order, Frontend.cpp:1221-1223): cand_lm indexes lm_* and is
+// non-decreasing; a bad index would otherwise become an out-of-bounds device read
+static int check_pool(int n_cand, const int32_t* cand_lm, int n_lm, const char* who)
+{
+  int prev = 0;
+  for (int c = 0; c < n_cand; c++) {
+    const int lm = cand_lm[c];
+    if (lm < 0 || lm >= n_lm || lm < prev) {
+      set_error("%s: cand_lm[%d] = %d is out of range [0, %d) or decreasing", who, c, lm, n_lm);
+      return OKB_ERR_ARGUMENT;
+    }
+    prev = lm;
+  }
+  return OKB_OK;
+}
+
 }  // namespace okb
 
 using namespace okb;
@@ -802,6 +819,7 @@ int okb_match_map3d(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_desc,
   OKB_CHECK_ARGS(n_kp == 0 || (kp_desc && kp_xy), "okb_match_map3d");
   OKB_CHECK_ARGS(n_cand == 0 || (cand_desc && cand_lm && lm_proj && lm_is3d), "okb_match_map3d");
   OKB_CHECK_ARGS(reprojection_threshold >= 0.0 && reprojection_threshold < 1e6, "okb_match_map3d");
+  { int rcv = check_pool(n_cand, cand_lm, n_lm, "okb_match_map3d"); if (rcv) return rcv; }
   if (n_kp == 0) return OKB_OK;
   OKB_CUDA(cudaSetDevice(ctx->device));
   OKB_LOCK_SLOT;
@@ -882,6 +900,8 @@ int okb_match_map_uninit(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_
   OKB_CHECK_ARGS(ctx && !bad_D(D) && n_kp >= 0 && n_cand >= 0 && out_dist && out_lm && out_hp_W && r_WC1, "okb_match_map_uninit");
   OKB_CHECK_ARGS(n_kp == 0 || (kp_desc && kp_e_W), "okb_match_map_uninit");
   OKB_CHECK_ARGS(n_cand == 0 || (cand_desc && cand_lm && cand_e_W && cand_r_W && lm_is3d), "okb_match_map_uninit");
+  OKB_CHECK_ARGS(n_lm >= 0, "okb_match_map_uninit");
+  { int rcv = check_pool(n_cand, cand_lm, n_lm, "okb_match_map_uninit"); if (rcv) return rcv; }
   if (out_ctr) *out_ctr = 0;
   if (n_kp == 0) return OKB_OK;
   OKB_CUDA(cudaSetDevice(ctx->device));
@@ -904,7 +924,7 @@ int okb_match_map_uninit(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_
   }
   a.nq = n_kp; a.nc = n_cand; a.thr = match_threshold;
   for (int i = 0; i < 3; i++) a.r1[i] = r_WC1[i];
-  a.cos26 = cos(2.6 * sigma); a.cos6 = cos(6.0 * sigma);  // host libm, as in the reference
+  a.cos26 = gate_cos(2.6 * sigma); a.cos6 = gate_cos(6.0 * sigma);  // the libm algorithm, same function as on the device (okb_gatecos.h)
   return run_gated(ctx, MODE_M2, D, a, in_end, o_dist, o_end, o_idx, o_hp, 0, o_ctr, out_dist, out_lm, out_hp_W, nullptr, out_ctr);
 }
 
@@ -920,12 +940,13 @@ static int stereo_like(okb_context_t* ctx, int mode, int D, int n0, const uint8_
   if (n0 == 0) return OKB_OK;
   OKB_CUDA(cudaSetDevice(ctx->device));
   OKB_LOCK_SLOT;
-  // per-keypoint cos(2.6 sigma), cos(6 sigma) tables with the host libm (sigma = size/f * 0.125)
+  // per-keypoint cos(2.6 sigma), cos(6 sigma) tables (sigma = size/f * 0.125) by gate_cos: the libm algorithm, the very
+  // function k_stereo_prep runs for the device-resident form, so both forms use identical constants by construction
   std::vector<double> c26_0(n0), c6_0(n0), c26_1, c6_1;
-  for (int i = 0; i < n0; i++) { const double s = sof0[i] * 0.125; c26_0[i] = cos(2.6 * s); c6_0[i] = cos(6.0 * s); }
+  for (int i = 0; i < n0; i++) { const double s = sof0[i] * 0.125; c26_0[i] = gate_cos(2.6 * s); c6_0[i] = gate_cos(6.0 * s); }
   if (mode == MODE_M4) {
     c26_1.resize(n1); c6_1.resize(n1);
-    for (int i = 0; i < n1; i++) { const double s = sof1[i] * 0.125; c26_1[i] = cos(2.6 * s); c6_1[i] = cos(6.0 * s); }
+    for (int i = 0; i < n1; i++) { const double s = sof1[i] * 0.125; c26_1[i] = gate_cos(2.6 * s); c6_1[i] = gate_cos(6.0 * s); }
   }
   MatchArgs a; memset(&a, 0, sizeof(a));
   size_t o_dist = 0, o_idx = 0, o_hp = 0, o_init = 0, in_end = 0, o_end = 0;
@@ -968,12 +989,17 @@ int okb_match_stereo(okb_context_t* ctx, int D, int n0, const uint8_t* desc0, co
                      r_WC1, T_CW0, T_CW1, match_threshold, out_k1, out_dist, out_hp_W, out_initialisable, "okb_match_stereo");
 }
 
-int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand, const uint8_t* d_cand_desc,
+int okb_match_map3d_device(okb_context_t* ctx, int cam, int D, int n_frames, int n_cand, const uint8_t* d_cand_desc,
                            const int32_t* d_cand_lm, int n_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
                            double reprojection_threshold, uint32_t match_threshold, uint32_t* d_out_dist, int32_t* d_out_lm)
 {
   OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams && n_cand >= 0 && n_lm >= 0 && d_out_dist && d_out_lm, "okb_match_map3d_device");
   CamWorkspace& ws = ctx->cams[cam];
+  if (D != ws.cfg.descriptor_bytes) {   // the pool rows must have the stride of the camera's own descriptors (the queries)
+    set_error("okb_match_map3d_device: pool descriptors of %d bytes against camera %d, which describes with %d bytes", D, cam,
+              ws.cfg.descriptor_bytes);
+    return OKB_ERR_ARGUMENT;
+  }
   OKB_CHECK_ARGS(n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_map3d_device");
   OKB_CHECK_ARGS(n_cand == 0 || (d_cand_desc && d_cand_lm && d_lm_proj && d_lm_is3d), "okb_match_map3d_device");
   OKB_CHECK_ARGS(reprojection_threshold >= 0.0 && reprojection_threshold < 1e6, "okb_match_map3d_device");
@@ -999,7 +1025,7 @@ int okb_match_map3d_device(okb_context_t* ctx, int cam, int n_frames, int n_cand
     a.row_off = (int32_t*)ws.d_m1_rows; a.row_list = (int32_t*)(ws.d_m1_rows + off_b); a.row_xy = (double2*)(ws.d_m1_rows + off_b + list_b);
   }
   a.out_dist = d_out_dist; a.out_idx = d_out_lm;
-  return m1_launch(ctx, a, 64, n_frames, ws.stream);
+  return m1_launch(ctx, a, D, n_frames, ws.stream);
 }
 
 // T_CW = T_WC.inverse() = [C^T | -(C^T r)] as row-major 3x4 (kinematics/implementation/Transformation.hpp:207-209)
@@ -1021,6 +1047,7 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
   OKB_CHECK_ARGS(ctx && n_frames >= 1 && cap0 > 0 && cap1 > 0 && d_kp0 && d_desc0 && d_count0 && model0 && d_kp1 && d_desc1 &&
                  d_count1 && model1 && C_WC0 && r_WC0 && C_WC1 && r_WC1 && d_out_k1 && d_out_dist && d_out_hp_W && d_out_initialisable,
                  "okb_match_stereo_device_ptr");
+  OKB_CHECK_ARGS(cap0 < (1 << 20) && cap1 < (1 << 20), "okb_match_stereo_device_ptr (capacity >= 2^20 keypoints per frame)");
   OKB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : MW.stream;
   // scratch: per side rays(3) eW(3) sof c26 c6 doubles + valid bytes
@@ -1133,7 +1160,7 @@ struct CamStage {
 };
 }  // namespace
 
-int okb_match_map3d_batch(okb_context_t* ctx, int cam, int n_frames, int n_cand, const uint8_t* cand_desc, const int32_t* cand_lm,
+int okb_match_map3d_batch(okb_context_t* ctx, int cam, int D, int n_frames, int n_cand, const uint8_t* cand_desc, const int32_t* cand_lm,
                           int n_lm, const double* lm_proj, const uint8_t* lm_is3d, double reprojection_threshold,
                           uint32_t match_threshold, int cap, uint32_t* out_dist, int32_t* out_lm)
 {
@@ -1143,15 +1170,17 @@ int okb_match_map3d_batch(okb_context_t* ctx, int cam, int n_frames, int n_cand,
   OKB_CHECK_ARGS(n_cand == 0 || (cand_desc && cand_lm && lm_proj && lm_is3d), "okb_match_map3d_batch");
   OKB_CUDA(cudaSetDevice(ctx->device));
   CamStage S{ws, ws.stream};
-  const size_t o_desc = S.take((size_t)n_cand * 64), o_lm = S.take((size_t)n_cand * 4);
+  OKB_CHECK_ARGS(!bad_D(D), "okb_match_map3d_batch");
+  { int rcv = check_pool(n_cand, cand_lm, n_lm, "okb_match_map3d_batch"); if (rcv) return rcv; }
+  const size_t o_desc = S.take((size_t)n_cand * D), o_lm = S.take((size_t)n_cand * 4);
   const size_t o_proj = S.take((size_t)n_frames * n_lm * 16), o_3d = S.take((size_t)n_lm);
   const size_t o_dist = S.take((size_t)n_frames * ws.kp_cap * 4), o_idx = S.take((size_t)n_frames * ws.kp_cap * 4);
   int rc = S.reserve(S.off);
   if (rc) return rc;
-  if ((rc = S.upload(o_desc, cand_desc, (size_t)n_cand * 64)) || (rc = S.upload(o_lm, cand_lm, (size_t)n_cand * 4)) ||
+  if ((rc = S.upload(o_desc, cand_desc, (size_t)n_cand * D)) || (rc = S.upload(o_lm, cand_lm, (size_t)n_cand * 4)) ||
       (rc = S.upload(o_proj, lm_proj, (size_t)n_frames * n_lm * 16)) || (rc = S.upload(o_3d, lm_is3d, (size_t)n_lm)))
     return rc;
-  rc = okb_match_map3d_device(ctx, cam, n_frames, n_cand, ws.m_d + o_desc, (const int32_t*)(ws.m_d + o_lm), n_lm,
+  rc = okb_match_map3d_device(ctx, cam, D, n_frames, n_cand, ws.m_d + o_desc, (const int32_t*)(ws.m_d + o_lm), n_lm,
                               (const double*)(ws.m_d + o_proj), ws.m_d + o_3d, reprojection_threshold, match_threshold,
                               (uint32_t*)(ws.m_d + o_dist), (int32_t*)(ws.m_d + o_idx));
   if (rc) return rc;

@@ -3,8 +3,10 @@
 * DBoW2::FBrisk::toString / fromString (reference okvis_frontend/src/FBrisk.cpp:71-95): the bytes as decimal integers,
   each followed by a space -- the `descriptor:"..."` strings of resources/small_voc.yml.gz.
 * `FRAME:KEYPOINT <stateId> <cameraIdx> <pt.x> <pt.y> <size> BRISK2 <hex>` records of a saved map
-  (writer okvis_ceres/src/Component.cpp:449-460, reader :235-258): two lower-case hex digits per descriptor byte, floats in
-  the default ostream format (6 significant digits, %g).
+  (writer okvis_ceres/src/Component.cpp:449-460, reader :235-258): two lower-case hex digits per descriptor byte. The
+  stream was given std::setprecision(17) BEFORE init.copyfmt(file) (Component.cpp:407-411), so the "default format" that
+  file.copyfmt(init) restores after every record still carries 17 significant digits: the float fields are promoted to
+  double and printed as %.17g, which round-trips every float32 exactly.
 """
 import numpy as np
 
@@ -21,7 +23,7 @@ def fbrisk_from_string(s, L=48):
 
 
 def _g(x):
-    return format(float(x), ".6g")
+    return format(float(np.float32(x)), ".17g")   # operator<<(float) -> double, precision 17
 
 
 def write_frame_keypoints(state_id, camera_idx, keypoints, descriptors):

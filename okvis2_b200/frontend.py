@@ -207,7 +207,7 @@ class Frontend:
         import torch   # device buffers for the M1 outputs (plumbing only)
         dist = torch.zeros(cap.value, dtype=torch.int32, device=f"cuda:{self._device}")
         lm = torch.zeros(cap.value, dtype=torch.int32, device=f"cuda:{self._device}")
-        check(L.okb_match_map3d_device(self._ctx, cameraIndex, 1, nc.value, p[0], p[1], nl.value, p[2], p[3], float(reprThreshold),
+        check(L.okb_match_map3d_device(self._ctx, cameraIndex, self._store_D, 1, nc.value, p[0], p[1], nl.value, p[2], p[3], float(reprThreshold),
                                        int(self.briskMatchingThreshold_), dist.data_ptr(), lm.data_ptr()))
         check(L.okb_sync(self._ctx))
         dist = dist.cpu().numpy().view(np.uint32); lm = lm.cpu().numpy()   # rows >= the frame's keypoint count: "no match"
@@ -485,7 +485,7 @@ class Frontend:
         assert lm_proj.shape == (n_frames, len(lm_is3d), 2)
         dist, lm = out if out is not None else (np.zeros((n_frames, cap), np.uint32), np.zeros((n_frames, cap), np.int32))
         with self._locks[cameraIndex]:
-            check(_l.lib().okb_match_map3d_batch(self._ctx, cameraIndex, n_frames, len(cand_desc), ptr(cand_desc), ptr(cand_lm),
+            check(_l.lib().okb_match_map3d_batch(self._ctx, cameraIndex, cand_desc.shape[1], n_frames, len(cand_desc), ptr(cand_desc), ptr(cand_lm),
                                                  len(lm_is3d), ptr(lm_proj), ptr(lm_is3d), 20.0 if use_imu else 150.0,
                                                  int(self.briskMatchingThreshold_), dist.shape[1], ptr(dist), ptr(lm)))
         return dist, lm

@@ -58,6 +58,7 @@ _PROTOS = {
     "okb_last_error": (C.c_char_p, []),
     "okb_version": (C.c_char_p, []),
     "okb_launch_count": (C.c_int64, [vp]),
+    "okb_gate_cos_exact": (i32, [vp]),
     "okb_stream": (vp, [vp, i32]),
     "okb_sync": (i32, [vp]),
     "okb_set_blocking_sync": (i32, [vp, i32]),
@@ -88,8 +89,8 @@ _PROTOS = {
     "okb_back_project": (i32, [vp, i32, i32, vp, vp, vp]),
     "okb_match_stereo_device": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
     "okb_match_stereo_device_ptr": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]),
-    "okb_match_map3d_device": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, vp, vp]),
-    "okb_match_map3d_batch": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, i32, vp, vp]),
+    "okb_match_map3d_device": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, vp, vp]),
+    "okb_match_map3d_batch": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, i32, vp, vp]),
     "okb_match_stereo_batch": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, i32, vp, vp, vp, vp]),
     "okb_store_configure": (i32, [vp, i32, i32, i32]),
     "okb_store_frame": (i32, [vp, i32, i32, i32, vp, vp]),

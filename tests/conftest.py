@@ -30,6 +30,18 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
+def build_emul():
+    """tests/emul/libokb_emul.so: the kernels' per-element code compiled for the host (test infrastructure)."""
+    import subprocess
+    so = os.path.join(ROOT, "tests", "emul", "libokb_emul.so")
+    src = os.path.join(ROOT, "tests", "emul", "okb_emul.cpp")
+    csrc = os.path.join(ROOT, "okvis2_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
+    return so
+
+
 @pytest.fixture(scope="session")
 def golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "brisk_cv2_4_13.npz"))

@@ -267,3 +267,33 @@ extern "C" int okb_emul_detect_describe(const uint8_t* img, int W, int H, int th
   if (stats) { stats[0] = (int)C.size(); stats[1] = (int)ties.size(); stats[2] = rounds; stats[3] = raw; stats[4] = emissions_skipped; }
   return (int)kps.size();
 }
+
+// ---- gate constants: okb::gate_cos (csrc/okb_gatecos.h, the function the matchers use on host and device) against the
+//      libm of this machine. Returns the number of arguments on which they differ.
+#include <math.h>
+#include "../../okvis2_b200/csrc/okb_gatecos.h"
+extern "C" double okb_emul_gate_cos(double x) { return okb::gate_cos(x); }
+extern "C" long okb_emul_gate_cos_mismatches(long n, unsigned long long seed, double range)
+{
+  unsigned long long s = seed ? seed : 88172645463325252ull; long bad = 0;
+  for (long i = 0; i < n; i++) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    double x = (double)(s >> 11) / 9007199254740992.0 * range;
+    if (i % 5 == 0) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x *= (double)(s >> 11) / 9007199254740992.0; }   // more small arguments
+    if (i % 7 == 0) x = -x;
+    bad += okb::gate_cos(x) != cos(x);
+  }
+  return bad;
+}
+// every keypoint size (float) of a binade range at focal length f: sigma = size / f * 0.125 -> cos(2.6 sigma), cos(6 sigma)
+extern "C" long okb_emul_gate_cos_sizes(double f, unsigned first_bits, unsigned last_bits, unsigned stride)
+{
+  long bad = 0;
+  for (unsigned b = first_bits; b < last_bits; b += stride) {
+    float size; memcpy(&size, &b, 4);
+    const double sg = ((double)size / f) * 0.125;
+    bad += okb::gate_cos(2.6 * sg) != cos(2.6 * sg);
+    bad += okb::gate_cos(6.0 * sg) != cos(6.0 * sg);
+  }
+  return bad;
+}

@@ -58,10 +58,13 @@ def test_brisk2_record_round_trip(voc_desc):
     kp["x"] = [12.5, 700.123474, 0.000123456789]; kp["y"] = [3.0, 479.999969, 1e6]; kp["size"] = [12.0, 18.0, 8.48528]
     lines = formats.write_frame_keypoints(17, 1, kp, voc_desc[:3])
     assert lines[0] == "FRAME:KEYPOINT 17 1 12.5 3 12 BRISK2 " + "".join(f"{b:02x}" for b in voc_desc[0])
-    assert lines[1].split()[3:6] == ["700.123", "480", "18"] and lines[2].split()[3:5] == ["0.000123457", "1e+06"]
+    # precision 17 (Component.cpp:407-411): the float32 value promoted to double, %.17g
+    assert lines[1].split()[3:6] == ["700.12347412109375", "479.99996948242188", "18"]
+    assert lines[2].split()[3:5] == ["0.00012345678987912834", "1000000"]
     k2, d2, n = formats.read_frame_keypoints(lines + ["FRAME 18 0"], 17, 1)
     assert n == 3 and np.array_equal(d2, voc_desc[:3])
-    assert np.allclose(k2["x"], kp["x"], rtol=1e-5) and np.array_equal(k2["size"][:2], kp["size"][:2])
+    for f in ("x", "y", "size"):   # exact float32 round trip
+        assert np.array_equal(k2[f].view(np.uint32), kp[f].view(np.uint32)), f
     with pytest.raises(ValueError):
         formats.read_frame_keypoints(lines, 18, 1)
     with pytest.raises(ValueError):

@@ -16,12 +16,8 @@ from okvis2_b200.synth import synth_frame
 
 @pytest.fixture(scope="module")
 def emul():
-    so = os.path.join(ROOT, "tests", "emul", "libokb_emul.so")
-    src = os.path.join(ROOT, "tests", "emul", "okb_emul.cpp")
-    deps = [src, os.path.join(ROOT, "okvis2_b200", "csrc", "okb_core.h"), os.path.join(ROOT, "okvis2_b200", "csrc", "okb_tables.h")]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
-    lib = C.CDLL(so)
+    from conftest import build_emul
+    lib = C.CDLL(build_emul())
     lib.okb_emul_detect_describe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_int, C.c_void_p]
 

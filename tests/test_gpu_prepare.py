@@ -123,7 +123,7 @@ def test_prepared_pool_feeds_device_m1():
         cap = C.c_int(0)
         lib.okb_device_features(fe.ctx, 0, None, None, None, C.byref(cap))
         d_dist = torch.zeros(cap.value, dtype=torch.int32, device="cuda"); d_lm = torch.zeros(cap.value, dtype=torch.int32, device="cuda")
-        L.check(lib.okb_match_map3d_device(fe.ctx, 0, 1, nc.value, p[0], p[1], nl.value, p[2], p[3], 20.0, 60, d_dist.data_ptr(), d_lm.data_ptr()))
+        L.check(lib.okb_match_map3d_device(fe.ctx, 0, 64, 1, nc.value, p[0], p[1], nl.value, p[2], p[3], 20.0, 60, d_dist.data_ptr(), d_lm.data_ptr()))
         L.check(lib.okb_sync(fe.ctx))
         # the same through the mirror's one-call form
         mdist, midx, _ = fe.matchToMap(0, s["T_WC1"], s["T_CW1"], W, H, s["hp_W"], s["quality"], s["obs_begin"], s["obs"], s["T_WC_old"])
