@@ -13,13 +13,13 @@
 //   k_finalize      order by (layer, y, x), keep the N strongest, drop border keypoints, pattern scale index
 //   k_integral_*    int32 integral image
 //   k_describe      one warp per keypoint: 2 x 60 smoothed samples, orientation, 512 bits via ballot
-#include <cuda.h>   // CUtensorMap type and enums only; the encoder is resolved through cudaGetDriverEntryPoint
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 
-#include "okb_internal.h"
+#include "okb_detect.h"
 
 namespace okb {
 
@@ -51,350 +51,6 @@ __device__ __forceinline__ void make_views(const DeviceLayers& dl, const uint8_t
       v.touch[i] = tb ? tb + d.offset : nullptr;
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// pyramid
-struct ResizeJob {
-  const uint8_t* src; int src_pitch; size_t src_frame_stride;
-  uint8_t* dst; int dst_pitch; size_t dst_frame_stride;
-  int dw, dh, fast2;
-  const int *xs, *xn, *ys, *yn; const float *xa, *ya;
-};
-struct ResizeJobs { ResizeJob j[2]; int n; int tiles_x[2], tiles_y[2]; };
-
-__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ ResizeJobs jobs)
-{
-  int t = blockIdx.x, ji = 0;
-  const int n0 = jobs.tiles_x[0] * jobs.tiles_y[0];
-  if (t >= n0) { t -= n0; ji = 1; }
-  const ResizeJob& J = jobs.j[ji];
-  const int tx = t % jobs.tiles_x[ji], ty = t / jobs.tiles_x[ji];
-  const int frame = blockIdx.y;
-  const uint8_t* src = J.src + (size_t)frame * J.src_frame_stride;
-  uint8_t* dst = J.dst + (size_t)frame * J.dst_frame_stride;
-  if (J.fast2) {
-    // tile = 128 x 8 destination pixels; a thread makes 4 of them from two 8-byte source loads
-    const int x = tx * 128 + (threadIdx.x & 31) * 4, y = ty * 8 + (threadIdx.x >> 5);
-    if (x >= J.dw || y >= J.dh) return;
-    const uint8_t* r0 = src + (size_t)(2 * y) * J.src_pitch + 2 * x;
-    const bool vec = ((J.src_pitch & 7) == 0) && ((((uintptr_t)src) & 7) == 0) && (x + 3 < J.dw) && ((J.dst_pitch & 3) == 0);
-    if (vec) {
-      const uint2 a = *reinterpret_cast<const uint2*>(r0), b = *reinterpret_cast<const uint2*>(r0 + J.src_pitch);
-      auto px = [](uint32_t u, uint32_t v, int sh) {
-        return (((u >> sh) & 255u) + ((u >> (sh + 8)) & 255u) + ((v >> sh) & 255u) + ((v >> (sh + 8)) & 255u) + 2u) >> 2;
-      };
-      const uint32_t out = px(a.x, b.x, 0) | (px(a.x, b.x, 16) << 8) | (px(a.y, b.y, 0) << 16) | (px(a.y, b.y, 16) << 24);
-      *reinterpret_cast<uint32_t*>(dst + (size_t)y * J.dst_pitch + x) = out;
-    } else {
-      for (int i = 0; i < 4 && x + i < J.dw; i++) dst[(size_t)y * J.dst_pitch + x + i] = half_pixel(src, J.src_pitch, x + i, y);
-    }
-  } else {
-    // tile = 32 x 32 destination pixels, 4 rows per thread
-    const int x = tx * 32 + (threadIdx.x & 31);
-    const int y0 = ty * 32 + (threadIdx.x >> 5) * 4;
-    if (x >= J.dw) return;
-    const int xs = J.xs[x], xn = J.xn[x];
-    float xa[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) xa[i] = J.xa[x * 4 + i];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const int y = y0 + r;
-      if (y < J.dh) {
-        float ya[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) ya[i] = J.ya[y * 4 + i];
-        dst[(size_t)y * J.dst_pitch + x] = area_pixel(src, J.src_pitch, xs, xn, xa, J.ys[y], J.yn[y], ya);
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// score map tiling
-constexpr int kTileW = 64, kTileH = 64;   // one warp per tile row (8 rows per warp), one lane per horizontal pixel pair
-
-// per-layer regions of the candidate list (so that a warp of the refinement kernel sees candidates of ONE layer and
-// follows one code path); cand_count is [frames][kMaxLayers]
-struct CandRegions { int off[kMaxLayers + 1]; };
-__device__ __forceinline__ int cand_total(const CandRegions& cr, const int32_t* count, int n_layers, int* prefix /*kMaxLayers+1*/)
-{
-  int acc = 0;
-#pragma unroll
-  for (int l = 0; l < kMaxLayers; l++) { prefix[l] = acc; if (l < n_layers) acc += min(count[l], cr.off[l + 1] - cr.off[l]); }
-  prefix[kMaxLayers] = acc;
-  return acc;
-}
-
-struct TileMap { int n_layers; int tile_prefix[kMaxLayers + 1]; int tiles_x[kMaxLayers]; };
-
-__device__ __forceinline__ int find_layer(const TileMap& tm, int tile)
-{
-  int l = 0;
-#pragma unroll
-  for (int i = 1; i < kMaxLayers; i++) if (i < tm.n_layers && tile >= tm.tile_prefix[i]) l = i;
-  return l;
-}
-
-// Dense AGAST 9-16 score b0 = clamp(B*, 0, 254) of four horizontally adjacent pixels, two at a time in 16x2 SIMD
-// (VIMNMX3.U16x2): B* = max(max_arcs min_arc(ring) - p, p - min_arcs max_arc(ring)) - 1 over the 16 arcs of 9 pixels.
-__device__ __forceinline__ uint32_t u16x2_lo(uint32_t w) { return __byte_perm(w, 0, 0x4140); }  // (b0, b1)
-__device__ __forceinline__ uint32_t u16x2_hi(uint32_t w) { return __byte_perm(w, 0, 0x4342); }  // (b2, b3)
-
-__device__ __forceinline__ uint32_t b0_pair(const uint32_t (&v)[16], uint32_t p)
-{
-  uint32_t m3[16], M3[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    m3[i] = __vimin3_u16x2(v[i], v[(i + 1) & 15], v[(i + 2) & 15]);
-    M3[i] = __vimax3_u16x2(v[i], v[(i + 1) & 15], v[(i + 2) & 15]);
-  }
-  uint32_t m9[16], M9[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    m9[i] = __vimin3_u16x2(m3[i], m3[(i + 3) & 15], m3[(i + 6) & 15]);
-    M9[i] = __vimax3_u16x2(M3[i], M3[(i + 3) & 15], M3[(i + 6) & 15]);
-  }
-  uint32_t bb = __vimax3_u16x2(m9[0], m9[1], m9[2]), bd = __vimin3_u16x2(M9[0], M9[1], M9[2]);
-#pragma unroll
-  for (int i = 3; i < 15; i += 2) { bb = __vimax3_u16x2(bb, m9[i], m9[i + 1]); bd = __vimin3_u16x2(bd, M9[i], M9[i + 1]); }
-  bb = __vmaxu2(bb, m9[15]); bd = __vminu2(bd, M9[15]);
-  // per half: t = max(bb - p, p - bd, 0) computed without borrows; b0 = min(max(t, 1) - 1, 254)
-  const uint32_t tb = __vmaxu2(bb, p) - p;
-  const uint32_t td = p - __vminu2(bd, p);
-  const uint32_t t = __vmaxu2(tb, td);
-  return __vminu2(__vmaxu2(t, 0x00010001u) - 0x00010001u, 0x00FE00FEu);
-}
-
-// ---- TMA (cp.async.bulk.tensor) staging of the image tiles -----------------------------------------------------
-// One 3-D tensor map per layer: (x: w bytes, y: h rows of `pitch` bytes, frame). A single elected thread issues one
-// bulk tensor copy of the kImgW x kImgH box per CTA; out-of-image elements are zero-filled by the hardware, the
-// completion is signalled on a shared-memory mbarrier.
-struct alignas(64) TmaMaps { CUtensorMap m[kMaxLayers]; int use[kMaxLayers]; };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
-{
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z)
-{
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
-}
-
-// Tie-cell bitmap (okb_core.h: for_each_cell): flagged by the score kernel around tied / pending candidates, tested by
-// k_refine before it emits the touches of a maximum.
-constexpr int kCellWordsPerFrame = kMaxLayers * kCellWordsPerLayer;
-__device__ __forceinline__ void cells_flag(uint32_t* cells /*layer*/, int layer_w, int x_lo, int x_hi, int y_lo, int y_hi)
-{
-  for_each_cell(layer_w, x_lo, x_hi, y_lo, y_hi, [&](int b) {
-    if (b < kCellWordsPerLayer * 32) atomicOr(&cells[b >> 5], 1u << (b & 31));
-    return false;
-  });
-}
-__device__ __forceinline__ bool cells_any(const uint32_t* cells /*layer*/, int layer_w, const TouchBox& t)
-{
-  return for_each_cell(layer_w, t.x_lo, t.x_hi, t.y_lo, t.y_hi,
-                       [&](int b) { return b >= kCellWordsPerLayer * 32 || ((__ldg(&cells[b >> 5]) >> (b & 31)) & 1u); });
-}
-
-// Fused score + non-max suppression. Tile = kTileW x kTileH (64 x 64) pixels of one layer of one frame, 256 threads.
-//   1. the image tile with its ring halo (3 rows above/below, 16 bytes left/right: TMA wants 16-byte granular boxes
-//      AND box origins) arrives in shared memory by ONE TMA bulk tensor copy, zero outside the image;
-//   2. the bytes are expanded once into two 16x2 planes, E[r][k] = (p[2k], p[2k+1]) and O[r][k] = (p[2k+1], p[2k+2]):
-//      every ring sample of a horizontal pixel PAIR is then a single conflict-free LDS.32 (E for even dx, O for odd dx)
-//      and the main loop is nothing but the 81 VIMNMX3.U16x2 of b0_pair (the ALU pipe is this kernel's limiter);
-//   3. a warp owns a tile row per iteration (lane = pixel pair, 8 rows per warp): dense scores b0 go to the global score
-//      map (64 contiguous bytes per warp) and to a shared score tile; the pixels with score >= threshold ("strong", a few
-//      per cent) of a row leave the loop as two ballots (even / odd pixels), no atomics inside the loop;
-//   4. the ballots are compacted into a dense list and the strong pixels get the 3x3 non-max test from the shared score
-//      tile, one per thread. A strong pixel ON the tile border whose
-//      in-tile neighbours do not already beat it is emitted with the PENDING flag (bit 30): its out-of-tile neighbours
-//      are scores of another CTA, so k_refine finishes the test from the global map (complete by then). There is no
-//      score halo, i.e. no pixel is scored twice.
-//   Candidate word: time key | tie << 31 | pending << 30; the tile's candidates are appended with one atomicAdd.
-constexpr int kHaloX = 16;           // measured on B200: the innermost TMA coordinate must be a multiple of 16 bytes
-                                     // (bench/tma_probe.cu: x = -8, 8, 376 raise "illegal instruction", -16, 0, 384 work)
-constexpr int kImgW = kTileW + 2 * kHaloX;   // bytes per staged image row: x0-16 .. x0+79
-constexpr int kImgH = kTileH + 6;    // rows y0-3 .. y0+66
-constexpr int kExp0 = 3, kExp1 = 21; // staged words (4 bytes) that are expanded: bytes 12 .. 83 cover x0-4 .. x0+67
-constexpr int kPlaneW = 2 * (kExp1 - kExp0);   // 16x2 words per plane row; plane word j holds staged bytes 2j+12 (E) / 2j+13 (O)
-constexpr int kScoreThreads = 256;
-constexpr uint32_t kCandTie = 0x80000000u, kCandPending = 0x40000000u, kCandKeyMask = 0x3fffffffu;
-
-__global__ void __launch_bounds__(kScoreThreads) k_score_nms(const __grid_constant__ TmaMaps maps, const __grid_constant__ DeviceLayers dl,
-                                                             const __grid_constant__ TileMap tm,
-                                                             const uint8_t* in0, int in_pitch, size_t in_frame_stride,
-                                                             uint8_t* img_block, uint8_t* score_block, uint32_t* cand,
-                                                             int32_t* cand_count, int cand_cap, const __grid_constant__ CandRegions cr,
-                                                             int threshold, int32_t* status, uint32_t* tie_cells)
-{
-  __shared__ __align__(128) uint8_t tile[kImgH][kImgW];
-  __shared__ __align__(16) uint32_t planes[2][kImgH][kPlaneW];   // E and O; reused as the candidate list after the scoring
-  __shared__ __align__(16) uint8_t sc[kTileH][kTileW];
-  uint32_t (*pe)[kPlaneW] = planes[0];
-  uint32_t (*po)[kPlaneW] = planes[1];
-  uint32_t* out_list = &planes[0][0][0];   // kTileH * kTileW entries <= 2 * kImgH * kPlaneW; first written after the
-                                           // __syncthreads() that ends the scoring loop (the planes are dead by then)
-  static_assert(kTileH * kTileW <= 2 * kImgH * kPlaneW, "candidate list must fit into the planes");
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint16_t strong[kTileH * kTileW];
-  __shared__ uint32_t smask[kTileH][2];            // per tile row: ballots of the strong even / odd pixels
-  __shared__ int n_strong, n_out, out_base, tma_failed;
-  const int frame = blockIdx.y;
-  const int layer = find_layer(tm, blockIdx.x);
-  const int t = blockIdx.x - tm.tile_prefix[layer];
-  const int tx = t % tm.tiles_x[layer], ty = t / tm.tiles_x[layer];
-  const DeviceLayer d = dl.l[layer];
-  const uint8_t* img; int pitch;
-  if (layer == 0) { img = in0 + (size_t)frame * in_frame_stride; pitch = in_pitch; }
-  else { img = img_block + (size_t)frame * dl.frame_stride + d.offset; pitch = d.pitch; }
-  uint8_t* score = score_block + (size_t)frame * dl.frame_stride + d.offset;
-  const int x0 = tx * kTileW, y0 = ty * kTileH;
-  if (threadIdx.x == 0) { n_strong = 0; n_out = 0; tma_failed = 0; }
-  if (threadIdx.x < 2 * kTileH) (&smask[0][0])[threadIdx.x] = 0u;
-  if (maps.use[layer]) {
-    // TMA: one bulk tensor copy per CTA; out-of-image bytes arrive as zeros
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(&bar, kImgH * kImgW);
-      tma_load_3d(&tile[0][0], &maps.m[layer], &bar, x0 - kHaloX, y0 - 3, frame);
-    }
-    // one warp polls the mbarrier (try_wait suspends in hardware), the others park at the CTA barrier and leave the
-    // issue slots to the resident CTAs that are computing
-    if (threadIdx.x < 32) {
-      const long long t_start = clock64();
-      while (!mbar_try_wait(&bar, 0)) {
-        if (clock64() - t_start > 400000000ll) {   // ~0.2 s: never spin forever on a broken descriptor
-          if (threadIdx.x == 0) { atomicOr(&status[frame], 16); tma_failed = 1; }
-          break;
-        }
-      }
-    }
-    __syncthreads();
-    if (tma_failed) return;
-  } else {
-    const bool word_ok = ((pitch & 3) == 0) && ((((uintptr_t)img) & 3) == 0);
-    for (int i = threadIdx.x; i < kImgH * (kImgW / 4); i += kScoreThreads) {
-      const int r = i / (kImgW / 4), c = i % (kImgW / 4);
-      const int y = y0 - 3 + r, x = x0 - kHaloX + c * 4;
-      uint32_t w = 0;
-      if (y >= 0 && y < d.h) {
-        const uint8_t* row = img + (size_t)y * pitch;
-        if (word_ok && x >= 0 && x + 3 < d.w) w = *reinterpret_cast<const uint32_t*>(row + x);
-        else {
-#pragma unroll
-          for (int b = 0; b < 4; b++) { const int xx = x + b; if (xx >= 0 && xx < d.w) w |= (uint32_t)row[xx] << (8 * b); }
-        }
-      }
-      *reinterpret_cast<uint32_t*>(&tile[r][c * 4]) = w;
-    }
-    __syncthreads();
-  }
-  // ---- expansion into the two 16x2 planes
-  for (int i = threadIdx.x; i < kImgH * (kExp1 - kExp0); i += kScoreThreads) {
-    const int r = i / (kExp1 - kExp0), m = i % (kExp1 - kExp0);
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(&tile[r][4 * (m + kExp0)]);
-    const uint32_t nx = *reinterpret_cast<const uint32_t*>(&tile[r][4 * (m + kExp0) + 4]);
-    uint2 e, o;
-    e.x = __byte_perm(w, 0, 0x4140); e.y = __byte_perm(w, 0, 0x4342);
-    o.x = __byte_perm(w, 0, 0x4241); o.y = __byte_perm(w, nx, 0x7473) & 0x00ff00ffu;   // (b3, nx.b0)
-    *reinterpret_cast<uint2*>(&pe[r][2 * m]) = e;
-    *reinterpret_cast<uint2*>(&po[r][2 * m]) = o;
-  }
-  __syncthreads();
-  // ---- dense scores: warp = tile row, lane = pixel pair (x0 + 2*lane, +1). Every ring sample is one LDS.32 at a
-  //      compile-time offset from a single per-lane pointer (the two planes are one array).
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int PW = kPlaneW, OO = kImgH * kPlaneW;          // row pitch of a plane, offset of the O plane (words)
-  const int xg = x0 + 2 * lane;
-  // scores are zero in the 3-pixel margin of the layer: per-lane column mask, per-row on/off
-  const uint32_t colmask = ((xg >= 3 && xg < d.w - 3) ? 0x0000ffffu : 0u) | ((xg + 1 >= 3 && xg + 1 < d.w - 3) ? 0xffff0000u : 0u);
-  const int rows_here = min(kTileH, d.h - y0);
-  const uint32_t thr2 = (uint32_t)(0x8000 - min(max(threshold, 1), 0x7fff)) * 0x00010001u;
-  {
-    const uint32_t* p = &planes[0][warp][2 + lane];          // plane word of this pair (staged byte 16 + 2*lane), tile row `warp`
-    uint8_t* gout = score + (size_t)(y0 + warp) * d.pitch + xg;   // pitch is a multiple of 64
-    uint8_t* sout = &sc[warp][2 * lane];
-#pragma unroll 1
-    for (int row = warp; row < rows_here; row += kScoreThreads / 32) {
-      uint32_t v[16];
-      v[0] = p[OO + 3 * PW - 2];  v[1] = p[OO + 2 * PW - 2];  v[2] = p[1 * PW - 1];       v[3] = p[OO - 1];
-      v[4] = p[0];                v[5] = p[OO];               v[6] = p[1 * PW + 1];       v[7] = p[OO + 2 * PW + 1];
-      v[8] = p[OO + 3 * PW + 1];  v[9] = p[OO + 4 * PW + 1];  v[10] = p[5 * PW + 1];      v[11] = p[OO + 6 * PW];
-      v[12] = p[6 * PW];          v[13] = p[OO + 6 * PW - 1]; v[14] = p[5 * PW - 1];      v[15] = p[OO + 4 * PW - 2];
-      uint32_t s = b0_pair(v, p[3 * PW]);
-      const int y = y0 + row;
-      s &= (y >= 3 && y < d.h - 3) ? colmask : 0u;
-      const uint16_t packed = (uint16_t)__byte_perm(s, 0, 0x4420);
-      *reinterpret_cast<uint16_t*>(sout) = packed;
-      *reinterpret_cast<uint16_t*>(gout) = packed;
-      // strong pixels (score >= threshold; scores <= 254 so the 16-bit adds cannot carry): two ballots per row
-      const uint32_t hit = s + thr2;
-      const unsigned m_even = __ballot_sync(0xffffffffu, hit & 0x8000u), m_odd = __ballot_sync(0xffffffffu, hit & 0x80000000u);
-      if (lane == 0) { smask[row][0] = m_even; smask[row][1] = m_odd; }
-      p += (kScoreThreads / 32) * PW; gout += (size_t)(kScoreThreads / 32) * d.pitch; sout += (kScoreThreads / 32) * kTileW;
-    }
-  }
-  __syncthreads();
-  // ---- the strong pixels (a few per cent) are compacted into a dense list, then get the 3x3 non-max test one per thread
-  if (threadIdx.x < 2 * kTileH) {
-    uint32_t m = (&smask[0][0])[threadIdx.x];
-    if (m) {
-      int pos = atomicAdd(&n_strong, __popc(m));
-      const int r = threadIdx.x >> 1, odd = threadIdx.x & 1;
-      while (m) { const int b = __ffs(m) - 1; m &= m - 1; strong[pos++] = (uint16_t)(r * kTileW + 2 * b + odd); }
-    }
-  }
-  __syncthreads();
-  const int ns = n_strong;
-  for (int i = threadIdx.x; i < ns; i += kScoreThreads) {
-    const int r = strong[i] / kTileW, x = strong[i] % kTileW;
-    const int c = sc[r][x];
-    bool is_c = true, tie = false, pending = false;
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-      for (int dx = -1; dx <= 1; dx++) {
-        if (dx == 0 && dy == 0) continue;
-        const int rr = r + dy, xx = x + dx;
-        if ((unsigned)rr < (unsigned)kTileH && (unsigned)xx < (unsigned)kTileW) {
-          const int v = sc[rr][xx];   // rows at / below the image end are never neighbours of a strong pixel (y < h - 3)
-          if (v > c) is_c = false;
-          if (v == c) tie = true;
-        } else pending = true;
-      }
-    if (is_c) {
-      const int pos = atomicAdd(&n_out, 1);
-      out_list[pos] = time_key(layer, x0 + x, y0 + r) | (pending ? kCandPending : (tie ? kCandTie : 0u));
-      if (pending || tie)
-        cells_flag(tie_cells + (size_t)frame * kCellWordsPerFrame + layer * kCellWordsPerLayer, d.w, x0 + x - 2, x0 + x + 2,
-                   y0 + r - 2, y0 + r + 2);
-    }
-  }
-  __syncthreads();
-  const int no = n_out;
-  if (no == 0) return;
-  if (threadIdx.x == 0) out_base = atomicAdd(&cand_count[frame * kMaxLayers + layer], no);
-  __syncthreads();
-  const int base = out_base, room = cr.off[layer + 1] - cr.off[layer];
-  for (int i = threadIdx.x; i < no; i += kScoreThreads)
-    if (base + i < room) cand[(size_t)frame * cand_cap + cr.off[layer] + base + i] = out_list[i];
 }
 
 // Cache-touch events of one maximum, emitted by a full warp (all arguments warp-uniform): lanes take the positions of
@@ -1113,6 +769,7 @@ int detect_init_camera(okb_context* ctx, int cam)
       g.fast2 = (sx == 2.0 && sy == 2.0) ? 1 : 0;
       if (!g.fast2) {
         AreaAxis ax, ay; build_area_axis(p.w, g.w, ax); build_area_axis(p.h, g.h, ay);
+        g.max_taps = std::max(*std::max_element(ax.count.begin(), ax.count.end()), *std::max_element(ay.count.begin(), ay.count.end()));
         OKB_CUDA(cudaMalloc(&g.d_xs, g.w * 4)); OKB_CUDA(cudaMalloc(&g.d_xn, g.w * 4)); OKB_CUDA(cudaMalloc(&g.d_xa, g.w * 16));
         OKB_CUDA(cudaMalloc(&g.d_ys, g.h * 4)); OKB_CUDA(cudaMalloc(&g.d_yn, g.h * 4)); OKB_CUDA(cudaMalloc(&g.d_ya, g.h * 16));
         OKB_CUDA(cudaMemcpy(g.d_xs, ax.start.data(), g.w * 4, cudaMemcpyHostToDevice));
@@ -1144,6 +801,7 @@ int detect_init_camera(okb_context* ctx, int cam)
     ws.cand_off[kMaxLayers] = acc;
     ws.cand_cap = acc;
   }
+  if (const char* e = getenv("OKB_SCORE_TILE_H")) ws.score_tile_h = atoi(e) == 64 ? 64 : 32;   // tuning hook
   ws.kp_cap = c.max_keypoints > 0 ? (int)align_up((size_t)c.max_keypoints, 64) : kSortCap;
   OKB_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
   OKB_CUDA(cudaStreamCreateWithFlags(&ws.stream2, cudaStreamNonBlocking));
@@ -1154,25 +812,30 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMalloc(&ws.d_score, off * B));
   OKB_CUDA(cudaMalloc(&ws.d_touch, off * B * 4));
   OKB_CUDA(cudaMemset(ws.d_touch, 0, off * B * 4));
-  OKB_CUDA(cudaMalloc(&ws.d_tie_cells, (size_t)kCellWordsPerFrame * B * 4));
   OKB_CUDA(cudaMemset(ws.d_score, 0, off * B));
   OKB_CUDA(cudaMemset(ws.d_img, 0, off * B));
   OKB_CUDA(cudaMalloc(&ws.d_integral, (size_t)(W + 1) * (H + 1) * 4 * B));
   OKB_CUDA(cudaMalloc(&ws.d_cand, (size_t)ws.cand_cap * 4 * B));
-  OKB_CUDA(cudaMalloc(&ws.d_cand_count, 4 * kMaxLayers * B));
+  {
+    // per-call counters in one block (one memset per call): candidate counts, status words, tie-cell bitmaps
+    const size_t cc = align_up((size_t)4 * kMaxLayers * B, 256), stb = align_up((size_t)4 * B, 256);
+    ws.zero_bytes = cc + stb + (size_t)kCellWordsPerFrame * B * 4;
+    uint8_t* blk = nullptr;
+    OKB_CUDA(cudaMalloc(&blk, ws.zero_bytes));
+    OKB_CUDA(cudaMemset(blk, 0, ws.zero_bytes));
+    ws.d_cand_count = (int32_t*)blk; ws.d_status = (int32_t*)(blk + cc); ws.d_tie_cells = (uint32_t*)(blk + cc + stb);
+  }
   OKB_CUDA(cudaMalloc(&ws.d_rec, (size_t)ws.cand_cap * sizeof(CandRecord) * B));
   OKB_CUDA(cudaMalloc(&ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t) * B));
   OKB_CUDA(cudaMalloc(&ws.d_kscale, (size_t)ws.kp_cap * 4 * B));
   OKB_CUDA(cudaMalloc(&ws.d_desc, (size_t)ws.kp_cap * 64 * B));
   OKB_CUDA(cudaMalloc(&ws.d_count, 4 * B));
-  OKB_CUDA(cudaMalloc(&ws.d_status, 4 * B));
   OKB_CUDA(cudaMalloc(&ws.d_rays, (size_t)ws.kp_cap * 24 * B));
   OKB_CUDA(cudaMalloc(&ws.d_rays_valid, (size_t)ws.kp_cap * B));
   OKB_CUDA(cudaEventCreateWithFlags(&ws.ev_done, cudaEventDisableTiming));
   OKB_CUDA(cudaMalloc(&ws.d_dbg, (size_t)16 * 8 * B));
   OKB_CUDA(cudaMemset(ws.d_dbg, 0, (size_t)16 * 8 * B));
   OKB_CUDA(cudaMemset(ws.d_count, 0, 4 * B));
-  OKB_CUDA(cudaMemset(ws.d_status, 0, 4 * B));
   OKB_CUDA(cudaMallocHost(&ws.h_img, (size_t)W * H * B));
   OKB_CUDA(cudaMallocHost(&ws.h_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t) * B));
   OKB_CUDA(cudaMallocHost(&ws.h_desc, (size_t)ws.kp_cap * 64 * B));
@@ -1194,9 +857,10 @@ void detect_free_camera(okb_context* ctx, int cam)
     LayerGeom& g = ws.geom[i];
     cudaFree(g.d_xs); cudaFree(g.d_xn); cudaFree(g.d_xa); cudaFree(g.d_ys); cudaFree(g.d_yn); cudaFree(g.d_ya);
   }
-  cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_tie_cells); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
+  cudaFree(ws.d_tiles);
+  cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
   cudaFree(ws.d_cand_count); cudaFree(ws.d_rec); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
-  cudaFree(ws.d_count); cudaFree(ws.d_status); cudaFree(ws.d_m1_rows); cudaFree(ws.m_d); if (ws.m_h) cudaFreeHost(ws.m_h); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);
+  cudaFree(ws.d_count); cudaFree(ws.d_m1_rows); cudaFree(ws.m_d); if (ws.m_h) cudaFreeHost(ws.m_h); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);
   if (ws.ev_done) cudaEventDestroy(ws.ev_done);
   cudaFreeHost(ws.h_img); cudaFreeHost(ws.h_kp); cudaFreeHost(ws.h_desc); cudaFreeHost(ws.h_count); cudaFreeHost(ws.h_status); cudaFreeHost(ws.h_rays); cudaFreeHost(ws.h_rays_valid);
   for (int i = 0; i < 4; i++) if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
@@ -1221,47 +885,6 @@ static void collect_timing(okb_context* ctx, CamWorkspace& ws)
   (void)ctx;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn g_encode = nullptr;
-static int g_encode_tried = 0;
-
-static bool encode_map(CUtensorMap* m, const void* base, int w, int h, size_t pitch, size_t frame_stride, int frames)
-{
-  if (!g_encode) return false;
-  if ((((uintptr_t)base) & 15) || (pitch & 15) || (frame_stride & 15) || pitch == 0) return false;
-  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
-  const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
-  const cuuint32_t box[3] = {(cuuint32_t)kImgW, (cuuint32_t)kImgH, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// tensor maps of all layers for this call (layer 0 lives in the caller's buffer, so its map is re-encoded per call;
-// the others are cached in the workspace). Layers whose geometry TMA cannot address fall back to plain loads.
-static int build_tma_maps(CamWorkspace& ws, const uint8_t* d_images, int src_pitch, size_t in_stride, int frames, TmaMaps& maps)
-{
-  if (!g_encode_tried) {
-    g_encode_tried = 1;
-    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      g_encode = (EncodeTiledFn)fn;
-  }
-  memset(&maps, 0, sizeof(maps));
-  if (!ws.tma_ready) {
-    for (int i = 1; i < ws.n_layers; i++) {
-      const LayerGeom& g = ws.geom[i];
-      ws.tma_use[i] = encode_map(&ws.tma[i], ws.d_img + g.offset, g.w, g.h, (size_t)g.pitch, (size_t)ws.dl.frame_stride, ws.cfg.max_batch) ? 1 : 0;
-    }
-    ws.tma_ready = 1;
-  }
-  for (int i = 1; i < ws.n_layers; i++) { maps.m[i] = ws.tma[i]; maps.use[i] = ws.tma_use[i]; }
-  maps.use[0] = encode_map(&maps.m[0], d_images, ws.geom[0].w, ws.geom[0].h, (size_t)src_pitch, in_stride, frames) ? 1 : 0;
-  return OKB_OK;
-}
-
 // all frames are device resident: d_images = n_frames x H x src_pitch
 int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch)
 {
@@ -1276,57 +899,18 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
     ws.epoch = 1;
   }
   const size_t in_stride = (size_t)src_pitch * H;
-  // ---- fork: the integral image only needs the input frames; it runs on a side stream underneath the detection
-  //      kernels (several of which are latency-bound single-CTA-per-frame kernels that leave most SMs idle)
   const int ipitch = W + 1;
+  // ---- pyramid + dense scores + non-max candidates (okb_score.cu)
+  CandRegions cr; for (int i = 0; i <= kMaxLayers; i++) cr.off[i] = ws.cand_off[i];
+  { int rc = pyramid_score_run(ctx, ws, d_images, src_pitch, in_stride, B, cr); if (rc) return rc; }
+  // ---- fork: the integral image only needs the input frames. It runs on a side stream underneath the refinement / tie
+  //      resolution / selection kernels (latency-bound, two of them one CTA per frame: they leave most SMs idle), not
+  //      underneath the pyramid + score pass, which fills the GPU by itself
   OKB_CUDA(cudaEventRecord(ws.ev_fork, st));
   OKB_CUDA(cudaStreamWaitEvent(ws.stream2, ws.ev_fork, 0));
   k_integral_rows<<<dim3((H + 7) / 8, B), 256, 0, ws.stream2>>>(d_images, src_pitch, in_stride, W, H, ws.d_integral, ipitch);
   k_integral_cols<<<dim3((W + 31) / 32, B), 1024, 0, ws.stream2>>>(W, H, ws.d_integral, ipitch);
   OKB_CUDA(cudaEventRecord(ws.ev_join, ws.stream2));
-  // ---- pyramid: layers whose parents are complete can share a launch
-  for (int i = 1; i < ws.n_layers;) {
-    ResizeJobs jobs; jobs.n = 0;
-    int total = 0;
-    auto add = [&](int li) {
-      const LayerGeom& g = ws.geom[li]; const LayerGeom& p = ws.geom[g.parent];
-      ResizeJob& J = jobs.j[jobs.n];
-      if (g.parent == 0) { J.src = d_images; J.src_pitch = src_pitch; J.src_frame_stride = in_stride; }
-      else { J.src = ws.d_img + p.offset; J.src_pitch = p.pitch; J.src_frame_stride = ws.dl.frame_stride; }
-      J.dst = ws.d_img + g.offset; J.dst_pitch = g.pitch; J.dst_frame_stride = ws.dl.frame_stride;
-      J.dw = g.w; J.dh = g.h; J.fast2 = g.fast2;
-      J.xs = g.d_xs; J.xn = g.d_xn; J.ys = g.d_ys; J.yn = g.d_yn; J.xa = g.d_xa; J.ya = g.d_ya;
-      if (g.fast2) { jobs.tiles_x[jobs.n] = (g.w + 127) / 128; jobs.tiles_y[jobs.n] = (g.h + 7) / 8; }
-      else { jobs.tiles_x[jobs.n] = (g.w + 31) / 32; jobs.tiles_y[jobs.n] = (g.h + 31) / 32; }
-      total += jobs.tiles_x[jobs.n] * jobs.tiles_y[jobs.n];
-      jobs.n++;
-    };
-    // layer i (odd, from i-2 or 0) and layer i+1 (even, from i-1): both parents have index < i
-    add(i);
-    if (i + 1 < ws.n_layers) add(i + 1);
-    if (jobs.n == 1) { jobs.tiles_x[1] = jobs.tiles_y[1] = 0; }
-    k_resize<<<dim3(total, B), 256, 0, st>>>(jobs);
-    ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
-    i += 2;
-  }
-  if (ctx->timers_on) cudaEventRecord(ws.ev_mid, st);
-  // ---- scores
-  TileMap tm; tm.n_layers = ws.n_layers; tm.tile_prefix[0] = 0;
-  for (int i = 0; i < ws.n_layers; i++) {
-    tm.tiles_x[i] = (ws.geom[i].w + kTileW - 1) / kTileW;
-    tm.tile_prefix[i + 1] = tm.tile_prefix[i] + tm.tiles_x[i] * ((ws.geom[i].h + kTileH - 1) / kTileH);
-  }
-  for (int i = ws.n_layers + 1; i <= kMaxLayers; i++) tm.tile_prefix[i] = tm.tile_prefix[ws.n_layers];
-  const int n_tiles = tm.tile_prefix[ws.n_layers];
-  OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, 4 * kMaxLayers * B, st));
-  CandRegions cr; for (int i = 0; i <= kMaxLayers; i++) cr.off[i] = ws.cand_off[i];
-  OKB_CUDA(cudaMemsetAsync(ws.d_status, 0, 4 * B, st));
-  OKB_CUDA(cudaMemsetAsync(ws.d_tie_cells, 0, (size_t)kCellWordsPerFrame * B * 4, st));
-  TmaMaps maps;
-  { int rc = build_tma_maps(ws, d_images, src_pitch, in_stride, c.max_batch, maps); if (rc) return rc; }
-  k_score_nms<<<dim3(n_tiles, B), kScoreThreads, 0, st>>>(maps, ws.dl, tm, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
-                                                          ws.d_cand, ws.d_cand_count, ws.cand_cap, cr, c.threshold, ws.d_status, ws.d_tie_cells);
-  ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
   if (ctx->timers_on) cudaEventRecord(ws.ev[1], st);
   // ---- candidates, refinement, tie resolution, selection
   k_refine<<<dim3((ws.cand_cap + 127) / 128, B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,

@@ -31,6 +31,7 @@ struct LayerGeom {
   float scale, offset_px;
   int parent;     // layer it is sampled from (-1 for layer 0)
   int fast2;      // 1 = exact 2x2 mean, 0 = general area tables
+  int max_taps = 0;   // general: largest tap count per axis (3 for the 2/3-sample layer)
   // device copies of the area tables (general path)
   int *d_xs = nullptr, *d_xn = nullptr, *d_ys = nullptr, *d_yn = nullptr;
   float *d_xa = nullptr, *d_ya = nullptr;
@@ -77,7 +78,8 @@ struct CamWorkspace {
   uint32_t* d_tie_cells = nullptr;  // per frame: one bit per 16x16 cell of every layer, set around tied candidates
   int32_t* d_integral = nullptr;  // (w+1) x (h+1) per frame
   uint32_t* d_cand = nullptr;   // candidate keys
-  int32_t* d_cand_count = nullptr;
+  int32_t* d_cand_count = nullptr;   // start of the per-call zero block: counts | status | tie cells (zero_bytes in total)
+  size_t zero_bytes = 0;
   CandRecord* d_rec = nullptr;
   okb_keypoint_t* d_kp = nullptr;
   int32_t* d_kscale = nullptr;
@@ -91,6 +93,8 @@ struct CamWorkspace {
   cudaEvent_t ev_done = nullptr;
   // TMA tensor maps of the internal layers (layer 0 is encoded per call)
   CUtensorMap tma[kMaxLayers]; int tma_use[kMaxLayers] = {0}; int tma_ready = 0;
+  int score_tile_h = 32;          // rows per score tile: 32 (128-thread CTAs, default) or 64 (256-thread CTAs)
+  void* d_tiles = nullptr; int n_tiles = 0;   // (layer, x0, y0) of every score tile of a frame
   long long* d_dbg = nullptr;   // per-frame cycle stamps of the single-CTA kernels (okb_debug_stamps)
   uint8_t* d_m1_rows = nullptr; size_t m1_rows_cap = 0;   // M1 row bins of the device-resident form (grown on demand)
   // staging of the host-buffer batch matchers (okb_match_map3d_batch / okb_match_stereo_batch), grown on demand
