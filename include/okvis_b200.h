@@ -248,6 +248,39 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
                                 const double r_WC1[3], uint32_t match_threshold, void* stream, int32_t* d_out_k1,
                                 uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_initialisable);
 
+
+/* M3 as a device-resident SEQUENCE over the older keyframes: replaces the loop of Frontend::matchMotionStereo over
+ * matchFrameIds for one camera (okvis_frontend/src/Frontend.cpp:1775-1958): per older keyframe the worker loop (:1809-1895), the
+ * 4 px re-projection check (:1897-1904; PinholeCamera::projectHomogeneous of T_WC1.inverse() * hp_W with the camera model of
+ * okb_set_camera_model) and the serial insertion (:1915-1954: ascending k0, the first k0 that claims a current keypoint wins),
+ * whose result -- the current keypoints that now carry a landmark -- shrinks the candidate set k1s of the NEXT older keyframe
+ * (:1789-1801). All of it stays on the device, batched over the n_frames current frames of the last detect call of `cam`.
+ * older[b * n_older + v]: view v of current frame b (device blocks; the estimator-state tests :1813-1821,1840,1923-1932 are the
+ * caller's d_use flags). T_WC1 / T_CW1: n_frames x 12 doubles, pose of the current camera and its inverse as
+ * okvis::kinematics::Transformation gives them (C row-major, then r). d_matched1: n_frames x capacity bytes, IN: 1 = the current
+ * keypoint already has a landmark (e.g. from M1), OUT: after the insertions of all views. Outputs: n_frames x n_older x cap0
+ * entries (d_out_hp_W x 4 doubles); flags bit 0 = matching (matchInfos[k0].matching), bit 1 = initialisable, bit 2 = inserted.
+ * `quality` (acos, :1888) only feeds estimator.setLandmark and stays with the caller. Asynchronous on okb_stream(ctx, cam). */
+typedef struct {
+  const uint8_t* d_desc;   /* n x 64 descriptors (device) */
+  const double* d_rays;    /* n x 3 back-projections (x, y, 1), Frame::getBackProjection */
+  const uint8_t* d_valid;  /* n: back-projection succeeded */
+  const float* d_size;     /* n: cv::KeyPoint::size */
+  const uint8_t* d_use;    /* n eligibility flags, or NULL = all eligible */
+  int32_t n, reserved;
+  double T_WC[12], T_CW[12];   /* pose of this camera in the older frame and its inverse */
+} okb_older_view_t;
+int okb_match_motion_stereo_device(okb_context_t* ctx, int cam, int n_frames, const double* T_WC1, const double* T_CW1, int n_older,
+                                   const okb_older_view_t* older, int cap0, uint32_t match_threshold, uint8_t* d_matched1,
+                                   int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags);
+/* Same on explicit device feature blocks of the current frames (keypoints [n_frames][cap1], descriptors [n_frames][cap1][64],
+ * counts [n_frames]); `stream` = cudaStream_t or NULL. */
+int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
+                                       const int32_t* d_count1, const okb_camera_model_t* model, int width, int height,
+                                       const double* T_WC1, const double* T_CW1, int n_older, const okb_older_view_t* older, int cap0,
+                                       uint32_t match_threshold, void* stream, uint8_t* d_matched1, int32_t* d_out_k1,
+                                       uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags);
+
 /* ---- P1: landmark-candidate preparation. Replaces the serial host loop of Frontend::matchToMap that
  *      builds landmarksToMatch / descriptorPool for one camera (okvis_frontend/src/Frontend.cpp:1196-1360; pose lookups
  *      ViGraph.cpp:632-645): projection of every landmark into the current view (PinholeCamera::projectHomogeneous,

@@ -102,6 +102,7 @@ void okb_destroy(okb_context_t* ctx)
   prepare_free(ctx);
   aux_free(ctx);
   if (ctx->stereo_scratch) cudaFree(ctx->stereo_scratch);
+  if (ctx->motion_scratch) cudaFree(ctx->motion_scratch);
   tables_free(ctx);
   delete ctx;
 }

@@ -144,6 +144,7 @@ struct okb_context {
   float pattern_scale = 1.0f;
   int timers_on = 0;
   void* stereo_scratch = nullptr; size_t stereo_cap = 0;   // device scratch of okb_match_stereo_device*
+  void* motion_scratch = nullptr; size_t motion_cap = 0;   // device scratch of okb_match_motion_stereo_device*
   int64_t launches = 0;
   int gate_cos_exact = 0;    // okb_create's self-check: gate_cos == this machine's libm cos on 65 536 arguments
   int blocking_sync = 0;     // 1: host-buffer entry points wait on a cudaEventBlockingSync event (the thread sleeps) instead of spinning
@@ -156,6 +157,9 @@ int detect_init_camera(okb_context* ctx, int cam);
 void detect_free_camera(okb_context* ctx, int cam);
 int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch);
 int camera_backproject_batch(okb_context* ctx, int cam, int n_frames);
+struct Model;
+void k_backproject_ext(const Model& m, const okb_keypoint_t* d_kp, const int32_t* d_count, int cap, int n_frames, double* d_rays,
+                       uint8_t* d_valid, cudaStream_t st);   // D4 on explicit device blocks (okb_camera.cu)
 int camera_stereo_prep(okb_context* ctx, const okb_camera_model_t& model, const double C_WC[9], const okb_keypoint_t* d_kp,
                        const int32_t* d_count, int cap, int n_frames, double* d_rays, uint8_t* d_valid, double* d_eW, double* d_sof,
                        double* d_c26, double* d_c6, cudaStream_t st);

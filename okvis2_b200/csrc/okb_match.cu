@@ -16,6 +16,7 @@
 
 #include "okb_internal.h"
 #include "okb_gatecos.h"
+#include "okb_camdev.h"
 
 namespace okb {
 
@@ -104,7 +105,16 @@ struct MatchArgs {
   uint32_t* out_dist; int32_t* out_idx; double* out_hp; uint8_t* out_init; int32_t* out_ctr;
   // M4 scan/gate split: when set, k_match_gated only runs for frames whose hit list overflowed (hit_cnt[frame] > hit_cap)
   const int32_t* hit_cnt; int hit_cap;
+  // M3 sequence (okb_match_motion_stereo_device*): the queries of frame b are the keypoints of the older view
+  // views[b * view_stride + view_index]; poses per frame
+  const struct M3View* views; int view_stride, view_index; const struct M3Frame* frames;
 };
+
+// one older keyframe view (device pointers) and the per-frame pose of the current camera, as uploaded by the M3 sequence
+struct M3View { const uint8_t* desc; const double* rays; const uint8_t* valid; const float* size; const uint8_t* use; int n, pad; double Twc[12], Tcw[12]; };
+struct M3Frame { double Twc[12], Tcw[12]; };
+// z of T * (p, 1) for a pose stored as (C row-major 9, r 3): Transformation::operator*(Vector4d) = C * head + r * s
+__device__ __forceinline__ double depth_cr(const double* T, V3 p) { return (((T[6] * p.x + T[7] * p.y) + T[8] * p.z) + T[11] * 1.0) / 1.0; }
 
 constexpr int kTile = 256;
 
@@ -418,7 +428,8 @@ __global__ void __launch_bounds__(256, 4) k_match_gated(MatchArgs a)
   const int q = blockIdx.x * 8 + warp;
   // batched device form: blockIdx.y = frame, per-frame strides (elements) and counts; all zero/null for the host form
   const size_t fq = (size_t)blockIdx.y * a.q_stride, fc = (size_t)blockIdx.y * a.c_stride;
-  const int nq = a.q_count ? min(a.q_count[blockIdx.y], a.nq) : a.nq;
+  const M3View* view = (MODE == MODE_M3 && a.views) ? &a.views[(size_t)blockIdx.y * a.view_stride + a.view_index] : nullptr;
+  const int nq = view ? min(view->n, a.nq) : (a.q_count ? min(a.q_count[blockIdx.y], a.nq) : a.nq);
   const int nc = a.c_count ? min(a.c_count[blockIdx.y], a.nc) : a.nc;
   const uint8_t* c_desc = a.c_desc + fc * (D16 * 16);
   const bool active = q < nq && (a.q_use == nullptr || a.q_use[fq + q]);
@@ -427,7 +438,7 @@ __global__ void __launch_bounds__(256, 4) k_match_gated(MatchArgs a)
   double q_c26 = 0, q_c6 = 0, q_sof = 0;
   int prev_lm = -1;
   if (active) {
-    load_query<D16>(a.q_desc, (int)(fq + q), qd);
+    if (view) load_query<D16>(view->desc, q, qd); else load_query<D16>(a.q_desc, (int)(fq + q), qd);
     eq = v3(a.q_e + 3 * (fq + q));
     if (MODE == MODE_M2) { q_c26 = a.cos26; q_c6 = a.cos6; if (a.q_prev_lm) prev_lm = a.q_prev_lm[fq + q]; }
     else { q_c26 = a.q_cos26[fq + q]; q_c6 = a.q_cos6[fq + q]; q_sof = a.q_sof[fq + q]; }
@@ -436,7 +447,9 @@ __global__ void __launch_bounds__(256, 4) k_match_gated(MatchArgs a)
   int best_idx = -1;
   V3 best_hp = V3{0, 0, 0}; bool have_hp = false; bool best_init = false;
   int ctr = 0, skip_lm = -1;
-  const V3 r0 = v3(a.r0), r1 = v3(a.r1);
+  V3 r0 = v3(a.r0), r1 = v3(a.r1);
+  const double* Tcw0 = nullptr; const double* Tcw1 = nullptr;   // M3 sequence: (C, r) poses of this frame
+  if (view) { r0 = v3(view->Twc + 9); r1 = v3(a.frames[blockIdx.y].Twc + 9); Tcw0 = view->Tcw; Tcw1 = a.frames[blockIdx.y].Tcw; }
   const int n_tiles = (nc + kTile - 1) / kTile;
   if (n_tiles > 0) stage_tile_async<D16>(c_desc, nc, 0, s_desc2[0]);
   for (int tt = 0; tt < n_tiles; tt++) {
@@ -470,8 +483,8 @@ __global__ void __launch_bounds__(256, 4) k_match_gated(MatchArgs a)
               if (pass) {
                 if (dot(eq, e1) < 0.8) pass = false;
                 if (!parallel) {
-                  if (depth_in(a.T0, hp) < 0.2) pass = false;
-                  if (depth_in(a.T1, hp) < 0.2) pass = false;
+                  if ((Tcw0 ? depth_cr(Tcw0, hp) : depth_in(a.T0, hp)) < 0.2) pass = false;
+                  if ((Tcw1 ? depth_cr(Tcw1, hp) : depth_in(a.T1, hp)) < 0.2) pass = false;
                 }
               }
             } else {
@@ -558,6 +571,7 @@ __global__ void __launch_bounds__(256, 4) k_match_gated(MatchArgs a)
   }
   if (q >= a.nq) return;
   if (lane == 0) {
+    if (MODE == MODE_M3 && view && best_idx < 0) best = a.thr;
     a.out_dist[fq + q] = best; a.out_idx[fq + q] = best_idx;
     double* hp = a.out_hp + 4 * (fq + q);
     if (have_hp) { hp[0] = best_hp.x; hp[1] = best_hp.y; hp[2] = best_hp.z; hp[3] = 1.0; }
@@ -694,6 +708,105 @@ __global__ void __launch_bounds__(128) k_m4_finish(MatchArgs a, const unsigned l
     hp[0] = hp[1] = hp[2] = hp[3] = 0.0;
     a.out_init[fq + q] = 0;
   }
+}
+
+
+// ---- M3 as a device-resident sequence over the older keyframes (Frontend::matchMotionStereo, Frontend.cpp:1775-1958) ----
+// Per older keyframe index v, for all frames of the batch at once:
+//   k_m3_prep    world rays / sigma tables of the view's keypoints (e0_W = (C_WC0 e_C).normalized(), cos(2.6 s), cos(6 s) by
+//                gate_cos, use = eligible && back-projection valid) and the candidate mask of the current frame
+//                (valid && not yet matched: the reference's compacted set k1s, :1789-1801, in the same ascending order);
+//   k_match_gated<., M3>  the worker loop (:1809-1895);
+//   k_m3_check   the 4 px re-projection check (:1897-1904, PinholeCamera::projectHomogeneous of T_CW1 * hp_W) and the claim
+//                of the matched current keypoint: atomicMin of k0 = "first k0 in ascending order wins" (:1915-1954);
+//   k_m3_commit  flags (matching / initialisable / inserted) and the update of the matched mask for the next older keyframe.
+struct M3Prep {
+  const M3View* views; int view_stride, view_index; const M3Frame* frames;
+  int cap0, cap1; size_t q_stride;   // scratch / output stride per frame (keypoints): n_older * cap0
+  double f0;
+  double* e0; double* c26; double* c6; uint8_t* use0;            // [frames][n_older][cap0] (base already offset by view_index * cap0)
+  const double* rays1; const uint8_t* valid1; const int32_t* count1; const uint8_t* matched1; double* e1; uint8_t* cvalid;   // [frames][cap1]
+  int first;   // 1: also compute e1 (once per call)
+};
+
+__global__ void __launch_bounds__(128) k_m3_prep(const __grid_constant__ M3Prep p)
+{
+  const int frame = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const M3View& V = p.views[(size_t)frame * p.view_stride + p.view_index];
+  if (k < p.cap0) {
+    const size_t i = (size_t)frame * p.q_stride + k;
+    bool use = false;
+    if (k < V.n) {
+      use = V.valid[k] && (V.use == nullptr || V.use[k]);
+      const double x = V.rays[3 * (size_t)k], y = V.rays[3 * (size_t)k + 1], z = V.rays[3 * (size_t)k + 2];
+      const double* C = V.Twc;
+      const V3 w = V3{(C[0] * x + C[1] * y) + C[2] * z, (C[3] * x + C[4] * y) + C[5] * z, (C[6] * x + C[7] * y) + C[8] * z};
+      const V3 e = normalized(w);
+      p.e0[3 * i] = e.x; p.e0[3 * i + 1] = e.y; p.e0[3 * i + 2] = e.z;
+      const double sigma = (double)V.size[k] / p.f0 * 0.125;
+      p.c26[i] = gate_cos(2.6 * sigma); p.c6[i] = gate_cos(6.0 * sigma);
+    }
+    p.use0[i] = use ? 1 : 0;
+  }
+  if (k < p.cap1) {
+    const size_t j = (size_t)frame * p.cap1 + k;
+    const bool in = k < min(p.count1[frame], p.cap1);
+    if (p.first && in) {
+      const double x = p.rays1[3 * j], y = p.rays1[3 * j + 1], z = p.rays1[3 * j + 2];
+      const double* C = p.frames[frame].Twc;
+      const V3 e = normalized(V3{(C[0] * x + C[1] * y) + C[2] * z, (C[3] * x + C[4] * y) + C[5] * z, (C[6] * x + C[7] * y) + C[8] * z});
+      p.e1[3 * j] = e.x; p.e1[3 * j + 1] = e.y; p.e1[3 * j + 2] = e.z;
+    }
+    p.cvalid[j] = (in && p.valid1[j] && !p.matched1[j]) ? 1 : 0;
+  }
+}
+
+struct M3Check {
+  const M3View* views; int view_stride, view_index; const M3Frame* frames;
+  int cap0, cap1; size_t q_stride;
+  Model cam; int width, height; uint32_t thr;
+  const okb_keypoint_t* kp1;                     // [frames][cap1]
+  const int32_t* k1; const uint32_t* dist; const double* hp; const uint8_t* init;   // matcher outputs (offset by view_index * cap0)
+  uint8_t* flags; int32_t* claim; uint8_t* matched1;
+};
+
+__global__ void __launch_bounds__(128) k_m3_check(const __grid_constant__ M3Check c)
+{
+  const int frame = blockIdx.y;
+  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k0 >= c.cap0) return;
+  const size_t i = (size_t)frame * c.q_stride + k0;
+  uint8_t fl = 0;
+  const int k1 = c.k1[i];
+  if (k1 >= 0 && c.dist[i] < c.thr) {
+    const double* T = c.frames[frame].Tcw;
+    const double x = c.hp[4 * i], y = c.hp[4 * i + 1], z = c.hp[4 * i + 2];
+    const double px = ((T[0] * x + T[1] * y) + T[2] * z) + T[9] * 1.0;
+    const double py = ((T[3] * x + T[4] * y) + T[5] * z) + T[10] * 1.0;
+    const double pz = ((T[6] * x + T[7] * y) + T[8] * z) + T[11] * 1.0;
+    double kx, ky;
+    const int st = project(c.cam, c.width, c.height, px, py, pz, kx, ky);
+    const okb_keypoint_t kp = c.kp1[(size_t)frame * c.cap1 + k1];
+    const double dx = (double)kp.x - kx, dy = (double)kp.y - ky;
+    const bool matching = st == kProjSuccessful && sqrt(dx * dx + dy * dy) < 4.0;
+    fl = (uint8_t)((matching ? 1 : 0) | (c.init[i] ? 2 : 0));
+    if (matching) atomicMin(&c.claim[(size_t)frame * c.cap1 + k1], k0);
+  }
+  c.flags[i] = fl;
+}
+
+__global__ void __launch_bounds__(128) k_m3_commit(const __grid_constant__ M3Check c)
+{
+  const int frame = blockIdx.y;
+  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k0 >= c.cap0) return;
+  const size_t i = (size_t)frame * c.q_stride + k0;
+  const uint8_t fl = c.flags[i];
+  if (!(fl & 1)) return;
+  const size_t j = (size_t)frame * c.cap1 + c.k1[i];
+  // cvalid excluded the keypoints matched before this view, so every claim is on an unmatched keypoint: the lowest k0 inserts
+  if (c.claim[j] == k0) { c.flags[i] = fl | 4; c.matched1[j] = 1; }
 }
 
 __global__ void __launch_bounds__(256) k_hamming_matrix(int D16, int na, const uint8_t* A, int nb, const uint8_t* B, uint16_t* out)
@@ -1113,6 +1226,96 @@ int okb_match_stereo_device(okb_context_t* ctx, int cam0, int cam1, int n_frames
   OKB_CUDA(cudaEventRecord(w0.ev_done, w0.stream));
   OKB_CUDA(cudaStreamWaitEvent(w1.stream, w0.ev_done, 0));
   return OKB_OK;
+}
+
+
+int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
+                                       const int32_t* d_count1, const okb_camera_model_t* model, int width, int height,
+                                       const double* T_WC1, const double* T_CW1, int n_older, const okb_older_view_t* older, int cap0,
+                                       uint32_t match_threshold, void* stream, uint8_t* d_matched1, int32_t* d_out_k1,
+                                       uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags)
+{
+  OKB_CHECK_ARGS(ctx && n_frames >= 1 && cap1 > 0 && cap1 < (1 << 20) && d_kp1 && d_desc1 && d_count1 && model && T_WC1 && T_CW1 &&
+                 n_older >= 0 && (n_older == 0 || older) && cap0 > 0 && cap0 < (1 << 20) && d_matched1 && d_out_k1 && d_out_dist &&
+                 d_out_hp_W && d_out_flags && width > 0 && height > 0, "okb_match_motion_stereo_device_ptr");
+  for (int i = 0; i < n_frames * n_older; i++)
+    OKB_CHECK_ARGS(older[i].n >= 0 && older[i].n <= cap0 && (older[i].n == 0 || (older[i].d_desc && older[i].d_rays && older[i].d_valid && older[i].d_size)),
+                   "okb_match_motion_stereo_device_ptr (older view)");
+  if (n_older == 0) return OKB_OK;
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : MW.stream;
+  const size_t nq = (size_t)n_frames * n_older * cap0, n1 = (size_t)n_frames * cap1;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t b_views = al(sizeof(M3View) * n_frames * n_older), b_frames = al(sizeof(M3Frame) * n_frames);
+  const size_t need = b_views + b_frames + al(nq * 24) + 2 * al(nq * 8) + al(nq) + al(nq) /*init*/ + al(n1 * 24) + al(n1 * 24) + 2 * al(n1) + al(n1 * 4);
+  if (need > ctx->motion_cap) {
+    OKB_CUDA(cudaDeviceSynchronize());
+    if (ctx->motion_scratch) cudaFree(ctx->motion_scratch);
+    ctx->motion_scratch = nullptr; ctx->motion_cap = 0;
+    OKB_CUDA(cudaMalloc(&ctx->motion_scratch, need + need / 4));
+    ctx->motion_cap = need + need / 4;
+  }
+  uint8_t* base = (uint8_t*)ctx->motion_scratch; size_t o = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base + o; o += al(bytes); return p; };
+  M3View* d_views = (M3View*)take(sizeof(M3View) * n_frames * n_older);
+  M3Frame* d_frames = (M3Frame*)take(sizeof(M3Frame) * n_frames);
+  double* e0 = (double*)take(nq * 24); double* c26 = (double*)take(nq * 8); double* c6 = (double*)take(nq * 8);
+  uint8_t* use0 = take(nq); uint8_t* init = take(nq);
+  double* rays1 = (double*)take(n1 * 24); double* e1 = (double*)take(n1 * 24);
+  uint8_t* valid1 = take(n1); uint8_t* cvalid = take(n1); int32_t* claim = (int32_t*)take(n1 * 4);
+  // descriptors of the views and poses: pageable host staging (cudaMemcpyAsync copies it before returning)
+  std::vector<M3View> hv((size_t)n_frames * n_older); std::vector<M3Frame> hf(n_frames);
+  for (size_t i = 0; i < hv.size(); i++) {
+    const okb_older_view_t& s = older[i];
+    hv[i].desc = s.d_desc; hv[i].rays = s.d_rays; hv[i].valid = s.d_valid; hv[i].size = s.d_size; hv[i].use = s.d_use; hv[i].n = s.n; hv[i].pad = 0;
+    memcpy(hv[i].Twc, s.T_WC, sizeof(hv[i].Twc)); memcpy(hv[i].Tcw, s.T_CW, sizeof(hv[i].Tcw));
+  }
+  for (int b = 0; b < n_frames; b++) { memcpy(hf[b].Twc, T_WC1 + 12 * (size_t)b, 96); memcpy(hf[b].Tcw, T_CW1 + 12 * (size_t)b, 96); }
+  OKB_CUDA(cudaMemcpyAsync(d_views, hv.data(), sizeof(M3View) * hv.size(), cudaMemcpyHostToDevice, st));
+  OKB_CUDA(cudaMemcpyAsync(d_frames, hf.data(), sizeof(M3Frame) * hf.size(), cudaMemcpyHostToDevice, st));
+  const Model cam = to_model(*model);
+  // D4 of the current keypoints (Frame::computeBackProjections)
+  k_backproject_ext(cam, d_kp1, d_count1, cap1, n_frames, rays1, valid1, st);
+  ctx->launches++;
+  const int gmax = (std::max(cap0, cap1) + 127) / 128;
+  for (int v = 0; v < n_older; v++) {
+    const size_t vo = (size_t)v * cap0;
+    M3Prep p; memset(&p, 0, sizeof(p));
+    p.views = d_views; p.view_stride = n_older; p.view_index = v; p.frames = d_frames; p.cap0 = cap0; p.cap1 = cap1;
+    p.q_stride = (size_t)n_older * cap0; p.f0 = 0.5 * (model->fu + model->fv);
+    p.e0 = e0 + 3 * vo; p.c26 = c26 + vo; p.c6 = c6 + vo; p.use0 = use0 + vo;
+    p.rays1 = rays1; p.valid1 = valid1; p.count1 = d_count1; p.matched1 = d_matched1; p.e1 = e1; p.cvalid = cvalid; p.first = v == 0;
+    k_m3_prep<<<dim3(gmax, n_frames), 128, 0, st>>>(p);
+    MatchArgs a; memset(&a, 0, sizeof(a));
+    a.nq = cap0; a.nc = cap1; a.q_stride = p.q_stride; a.c_stride = (size_t)cap1; a.c_count = d_count1;
+    a.c_desc = d_desc1; a.q_use = p.use0; a.q_e = p.e0; a.q_sof = p.c26 /* unused by M3 */; a.q_cos26 = p.c26; a.q_cos6 = p.c6;
+    a.c_valid = cvalid; a.c_e = e1; a.thr = match_threshold;
+    a.views = d_views; a.view_stride = n_older; a.view_index = v; a.frames = d_frames;
+    a.out_dist = d_out_dist + vo; a.out_idx = d_out_k1 + vo; a.out_hp = d_out_hp_W + 4 * vo; a.out_init = init + vo;
+    k_match_gated<4, MODE_M3><<<dim3((cap0 + 7) / 8, n_frames), 256, 0, st>>>(a);
+    OKB_CUDA(cudaMemsetAsync(claim, 0x7f, n1 * 4, st));
+    M3Check c; memset(&c, 0, sizeof(c));
+    c.views = d_views; c.view_stride = n_older; c.view_index = v; c.frames = d_frames; c.cap0 = cap0; c.cap1 = cap1; c.q_stride = p.q_stride;
+    c.cam = cam; c.width = width; c.height = height; c.thr = match_threshold; c.kp1 = d_kp1;
+    c.k1 = a.out_idx; c.dist = a.out_dist; c.hp = a.out_hp; c.init = a.out_init; c.flags = d_out_flags + vo; c.claim = claim; c.matched1 = d_matched1;
+    k_m3_check<<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(c);
+    k_m3_commit<<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(c);
+    ctx->launches += 4;
+  }
+  OKB_CUDA(cudaGetLastError());
+  return OKB_OK;
+}
+
+int okb_match_motion_stereo_device(okb_context_t* ctx, int cam, int n_frames, const double* T_WC1, const double* T_CW1, int n_older,
+                                   const okb_older_view_t* older, int cap0, uint32_t match_threshold, uint8_t* d_matched1,
+                                   int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags)
+{
+  OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams, "okb_match_motion_stereo_device");
+  CamWorkspace& ws = ctx->cams[cam];
+  OKB_CHECK_ARGS(ws.has_model && n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_motion_stereo_device (camera model set? okb_set_camera_model)");
+  return okb_match_motion_stereo_device_ptr(ctx, n_frames, ws.kp_cap, ws.d_kp, ws.d_desc, ws.d_count, &ws.model, ws.cfg.width, ws.cfg.height,
+                                            T_WC1, T_CW1, n_older, older, cap0, match_threshold, (void*)ws.stream, d_matched1, d_out_k1,
+                                            d_out_dist, d_out_hp_W, d_out_flags);
 }
 
 // ---- host-buffer batch forms: the queries are the features the last okb_detect_describe[_batch] of the camera left on the

@@ -89,6 +89,8 @@ _PROTOS = {
     "okb_back_project": (i32, [vp, i32, i32, vp, vp, vp]),
     "okb_match_stereo_device": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
     "okb_match_stereo_device_ptr": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]),
+    "okb_match_motion_stereo_device": (i32, [vp, i32, i32, vp, vp, i32, vp, i32, u32, vp, vp, vp, vp, vp]),
+    "okb_match_motion_stereo_device_ptr": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, i32, u32, vp, vp, vp, vp, vp, vp]),
     "okb_match_map3d_device": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, vp, vp]),
     "okb_match_map3d_batch": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, i32, vp, vp]),
     "okb_match_stereo_batch": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, i32, vp, vp, vp, vp]),
@@ -101,6 +103,12 @@ _PROTOS = {
     "okb_overlap_counts": (i32, [vp, i32, vp, i32, vp, vp, f64, vp, vp]),
     "okb_prepared_device": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]),
 }
+
+
+class OlderView(C.Structure):
+    """okb_older_view_t: one older keyframe view of the M3 sequence (device pointers)"""
+    _fields_ = [("d_desc", C.c_void_p), ("d_rays", C.c_void_p), ("d_valid", C.c_void_p), ("d_size", C.c_void_p), ("d_use", C.c_void_p),
+                ("n", C.c_int32), ("reserved", C.c_int32), ("T_WC", C.c_double * 12), ("T_CW", C.c_double * 12)]
 
 
 class OverlapView(C.Structure):

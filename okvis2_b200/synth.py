@@ -217,3 +217,67 @@ def landmark_scene(seed, n_lm=2000, n_slots=10, n_cams=2, n_kp=600, D=64, W=752,
     return dict(hp_W=hp_W, quality=quality, obs_begin=np.array(obs_begin, np.int32), obs=np.array(obs, np.int32).reshape(-1, 3),
                 T_WC_old=T_WC_old, T_WC1=T_WC1, T_CW1=T_CW1, desc_tab=desc_tab, ray_tab=ray_tab, n_cams=n_cams, n_slots=n_slots,
                 D=D, W=W, H=H, intr=np.array([f, f * 0.997, W / 2 - 8.8, H / 2 + 8.4, -0.2834, 0.0740, 0.00019, 1.76e-05]))
+
+
+def radtan_project(p_C, fu, fv, cu, cv, k):
+    """PinholeCamera<RadialTangentialDistortion>::project of camera-frame points (n x 3) -> pixel coordinates (n x 2), float64."""
+    u0, u1 = p_C[:, 0] / p_C[:, 2], p_C[:, 1] / p_C[:, 2]
+    k1, k2, p1, p2 = k
+    mx, my, mxy = u0 * u0, u1 * u1, u0 * u1
+    rho = mx + my
+    rad = k1 * rho + k2 * rho * rho
+    d0 = u0 + u0 * rad + 2.0 * p1 * mxy + p2 * (rho + 2.0 * mx)
+    d1 = u1 + u1 * rad + 2.0 * p2 * mxy + p1 * (rho + 2.0 * my)
+    return np.stack([fu * d0 + cu, fv * d1 + cv], 1)
+
+
+def pose12(Cm, r):
+    """(C row-major 9, r 3) packing of a pose and of its inverse, the layout of okb_prepare_view_t / okb_older_view_t."""
+    Cm = np.asarray(Cm, np.float64); r = np.asarray(r, np.float64)
+    return np.concatenate([Cm.ravel(), r]), np.concatenate([Cm.T.ravel(), -(Cm.T @ r)])
+
+
+def motion_scene(seed, n_views=5, n0=600, n1=900, W=752, H=480, f=458.0, k=(-0.2834, 0.0740, 0.00019, 1.76e-05), flip_p=0.04,
+                 frac_seen=0.7, premated=0.2):
+    """A camera moving through a cloud of 3-D points for the M3 sequence (Frontend::matchMotionStereo): the current view and
+    `n_views` older keyframe views, each with keypoints (pixels, float32), descriptors (noisy copies of the points' descriptors,
+    so that several older views compete for the same current keypoint), keypoint sizes, eligibility flags and poses.
+    Returns dict(cur=dict(kp xy, desc, size, matched), views=[dict(xy, desc, size, use, T_WC, T_CW)], T_WC1, T_CW1, intr)."""
+    rng = np.random.default_rng(seed)
+    fu, fv, cu, cv = f, f * 0.997, W / 2 - 8.8, H / 2 + 8.4
+    n_pts = max(n0, n1) * 2
+    P = np.stack([rng.uniform(-6, 6, n_pts), rng.uniform(-4, 4, n_pts), rng.uniform(0.15, 30.0, n_pts)], 1)
+    desc_pts = random_descriptors(rng, n_pts, 64)
+
+    def view(Cm, r, n, noise_seed):
+        g = np.random.default_rng(noise_seed)
+        pc = (P - r) @ Cm          # C_CW = C_WC^T applied to row vectors
+        ok = pc[:, 2] > 0.05
+        px = np.full((n_pts, 2), -1.0)
+        px[ok] = radtan_project(pc[ok], fu, fv, cu, cv, k)
+        inside = ok & (px[:, 0] > 20) & (px[:, 0] < W - 20) & (px[:, 1] > 20) & (px[:, 1] < H - 20)
+        idx = np.nonzero(inside)[0]
+        idx = idx[g.permutation(len(idx))[:int(n * frac_seen)]]
+        xy = px[idx] + g.normal(0, 0.4, (len(idx), 2))
+        bits = np.unpackbits(desc_pts[idx], axis=1)
+        d = np.packbits(bits ^ (g.random(bits.shape) < flip_p).astype(np.uint8), axis=1)
+        n_out = n - len(idx)            # outliers: random pixels, random descriptors
+        xy = np.concatenate([xy, np.stack([g.uniform(20, W - 20, n_out), g.uniform(20, H - 20, n_out)], 1)])
+        d = np.concatenate([d, random_descriptors(g, n_out, 64)])
+        perm = g.permutation(n)
+        size = (g.choice([12.0, 18.0, 24.0, 36.0], n) * g.uniform(0.9, 1.1, n)).astype(np.float32)
+        return np.ascontiguousarray(xy[perm].astype(np.float32)), np.ascontiguousarray(d[perm]), size
+
+    C1 = rot((0, 1, 0), 0.03) @ rot((1, 0, 0), -0.02); r1 = np.array([0.4, 0.02, 0.05])
+    T_WC1, T_CW1 = pose12(C1, r1)
+    xy1, d1, s1 = view(C1, r1, n1, seed * 11 + 1)
+    views = []
+    for v in range(n_views):
+        Cv = rot((0, 1, 0), 0.03 - 0.015 * (v + 1)) @ rot((0, 0, 1), 0.004 * v)
+        rv = r1 - np.array([0.12 * (v + 1), 0.01 * v, 0.02])
+        xy, d, sz = view(Cv, rv, n0, seed * 11 + 2 + v)
+        Tw, Tc = pose12(Cv, rv)
+        views.append(dict(xy=xy, desc=d, size=sz, use=(rng.random(n0) > 0.1).astype(np.uint8), T_WC=Tw, T_CW=Tc))
+    matched = (rng.random(n1) < premated).astype(np.uint8)
+    return dict(cur=dict(xy=xy1, desc=d1, size=s1, matched=matched), views=views, T_WC1=T_WC1, T_CW1=T_CW1,
+                intr=np.array([fu, fv, cu, cv, *k]), W=W, H=H)

@@ -235,6 +235,40 @@ def match_motion_stereo(desc0, use0, e0, sof0, desc1, valid1, e1, r0, r1, T0, T1
     return _stereo("okvo_match_motion_stereo", desc0, use0, e0, sof0, desc1, valid1, e1, None, r0, r1, T0, T1, match_thr, n_threads)
 
 
+def match_motion_stereo_sequence(views, desc1, rays1, valid1, xy1, T_WC1, T_CW1, model, intr, width, height, match_thr,
+                                 matched1, n_threads=1):
+    """Frontend::matchMotionStereo over the older keyframes of one camera (Frontend.cpp:1775-1958).
+    views: list of dicts(desc, rays, valid, size, use (or None), T_WC (12), T_CW (12)). Returns (list of per-view
+    (k1, dist, hp_W, flags), matched1 after the sequence). flags: 1 matching, 2 initialisable, 4 inserted."""
+    D = desc1.shape[1]
+    n0 = np.array([len(v["desc"]) for v in views], np.int32)
+    off = np.concatenate([[0], np.cumsum(n0)[:-1]]).astype(np.int32) if len(views) else np.zeros(0, np.int32)
+    tot = int(n0.sum())
+    cat = lambda k, t, shape: (np.ascontiguousarray(np.concatenate([np.asarray(v[k], t).reshape((-1,) + shape) for v in views]), t)
+                               if views else np.zeros((0,) + shape, t))
+    d0, r0, v0, s0 = cat("desc", np.uint8, (D,)), cat("rays", np.float64, (3,)), cat("valid", np.uint8, ()), cat("size", np.float32, ())
+    use = None
+    if any(v.get("use") is not None for v in views):
+        use = np.ascontiguousarray(np.concatenate([np.ones(len(v["desc"]), np.uint8) if v.get("use") is None else np.asarray(v["use"], np.uint8)
+                                                   for v in views]))
+    Tw = np.ascontiguousarray(np.stack([np.asarray(v["T_WC"], np.float64).reshape(12) for v in views])) if views else np.zeros((0, 12))
+    Tc = np.ascontiguousarray(np.stack([np.asarray(v["T_CW"], np.float64).reshape(12) for v in views])) if views else np.zeros((0, 12))
+    desc1 = _c(desc1, np.uint8); rays1 = _c(rays1, np.float64); valid1 = _c(valid1, np.uint8); xy1 = _c(xy1, np.float32)
+    T_WC1 = _c(np.asarray(T_WC1).reshape(12), np.float64); T_CW1 = _c(np.asarray(T_CW1).reshape(12), np.float64)
+    intr = _c(intr, np.float64)
+    m1 = np.ascontiguousarray(matched1, np.uint8).copy()
+    k1 = np.zeros(tot, np.int32); dist = np.zeros(tot, np.uint32); hp = np.zeros((tot, 4), np.float64); fl = np.zeros(tot, np.uint8)
+    f = lib().okvo_match_motion_stereo_sequence
+    f.restype = None
+    f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint32] + \
+                 [C.c_void_p] * 5 + [C.c_int]
+    f(D, len(views), _p(n0), _p(off), _p(d0), _p(r0), _p(v0), _p(s0), _p(use), _p(Tw), _p(Tc), len(desc1), _p(desc1), _p(rays1), _p(valid1),
+      _p(xy1), _p(T_WC1), _p(T_CW1), int(model), _p(intr), int(width), int(height), int(match_thr), _p(m1), _p(k1), _p(dist), _p(hp), _p(fl),
+      n_threads)
+    out = [(k1[o:o + n], dist[o:o + n], hp[o:o + n], fl[o:o + n]) for o, n in zip(off, n0)]
+    return out, m1
+
+
 def match_stereo(desc0, valid0, e0, sof0, desc1, valid1, e1, sof1, r0, r1, T0, T1, match_thr, n_threads=1):
     return _stereo("okvo_match_stereo", desc0, valid0, e0, sof0, desc1, valid1, e1, sof1, r0, r1, T0, T1, match_thr, n_threads)
 

@@ -24,6 +24,8 @@
 #include <thread>
 #include <vector>
 
+#include "camera_project.h"
+
 namespace {
 
 struct V3 { double x, y, z; };
@@ -229,6 +231,97 @@ void okvo_match_motion_stereo(int D, int n0, const uint8_t* desc0, const uint8_t
       out_dist[k0] = distances;
     }
   });
+}
+
+
+// M3 as a sequence over the older keyframes of one camera (Frontend::matchMotionStereo, Frontend.cpp:1775-1958): per older
+// frame the worker loop (:1809-1907, including the 4 px re-projection check :1897-1904) and then the serial insertion
+// (:1915-1954): ascending k0, a match is inserted unless its k1 already carries a landmark -- from before the call or from
+// an earlier k0 of this loop -- and the inserted k1 drop out of the candidate set `k1s` of the next older frame (:1789-1801).
+// The estimator-state tests (:1813-1821, :1840, :1923-1932) are the caller's `use0` flags; `quality` (acos, :1888) only
+// feeds estimator.setLandmark and stays with the caller.
+// view i: n0[i] keypoints, arrays at offset off[i] (in keypoints) of desc0 / rays0 / valid0 / size0 / use0; poses T_WC0[i] and
+// its inverse T_CW0[i] = T_WC0[i].inverse() as the caller's Transformation gives them (12 doubles each: C row-major, then r);
+// outputs at the same offsets. flags: bit 0 matching (matchInfos[k0].matching), bit 1 initialisable, bit 2 inserted.
+void okvo_match_motion_stereo_sequence(int D, int n_views, const int32_t* n0, const int32_t* off, const uint8_t* desc0,
+                                       const double* rays0, const uint8_t* valid0, const float* size0, const uint8_t* use0,
+                                       const double* T_WC0, const double* T_CW0, int n1, const uint8_t* desc1, const double* rays1,
+                                       const uint8_t* valid1, const float* xy1 /* n1 x 2 keypoint pt */, const double T_WC1[12],
+                                       const double T_CW1_in[12],
+                                       int model, const double* intr /* fu fv cu cv k0..k3 */, int width, int height,
+                                       uint32_t matchThreshold, uint8_t* matched1 /* n1, in/out */, int32_t* out_k1,
+                                       uint32_t* out_dist, double* out_hp_W, uint8_t* out_flags, int n_threads)
+{
+  const double f0 = 0.5 * (intr[0] + intr[1]);
+  auto rot = [](const double* C, V3 v) {
+    return V3{(C[0] * v.x + C[1] * v.y) + C[2] * v.z, (C[3] * v.x + C[4] * v.y) + C[5] * v.z, (C[6] * v.x + C[7] * v.y) + C[8] * v.z};
+  };
+  auto as3x4 = [](const double* T, double* out) {   // (C row-major, r) -> row-major 3x4 [C | r], the layout depth() reads
+    for (int i = 0; i < 3; i++) { out[4 * i] = T[3 * i]; out[4 * i + 1] = T[3 * i + 1]; out[4 * i + 2] = T[3 * i + 2]; out[4 * i + 3] = T[9 + i]; }
+  };
+  double T_CW1[12]; as3x4(T_CW1_in, T_CW1);
+  const V3 r1 = V3{T_WC1[9], T_WC1[10], T_WC1[11]};
+  std::vector<double> e1_W((size_t)n1 * 3);
+  for (int k = 0; k < n1; k++) { const V3 e = normalized(rot(T_WC1, ld(rays1 + 3 * (size_t)k))); e1_W[3 * k] = e.x; e1_W[3 * k + 1] = e.y; e1_W[3 * k + 2] = e.z; }
+  for (int v = 0; v < n_views; v++) {
+    const int n = n0[v]; const size_t o = (size_t)off[v];
+    const double* Tw0 = T_WC0 + 12 * (size_t)v;
+    double T_CW0v[12]; as3x4(T_CW0 + 12 * (size_t)v, T_CW0v);
+    const V3 r0 = V3{Tw0[9], Tw0[10], Tw0[11]};
+    // the compacted unmatched set k1s and its descriptors (Frontend.cpp:1789-1801)
+    std::vector<int> k1s; k1s.reserve(n1);
+    for (int k1 = 0; k1 < n1; k1++) if (!matched1[k1]) k1s.push_back(k1);
+    run_threads(n_threads, [&](int t, int T) {
+      for (int k0 = t; k0 < n; k0 += T) {
+        out_k1[o + k0] = -1; out_dist[o + k0] = matchThreshold; out_flags[o + k0] = 0;
+        for (int i = 0; i < 4; i++) out_hp_W[4 * (o + k0) + i] = 0.0;
+        if (use0 && !use0[o + k0]) continue;
+        if (!valid0[o + k0]) continue;
+        uint32_t distances = matchThreshold;
+        bool initialisable = false;
+        V3 hps = V3{0, 0, 0};
+        int k1_max = -1;
+        const V3 e0 = normalized(rot(Tw0, ld(rays0 + 3 * (o + k0))));
+        const double sigma = (double)size0[o + k0] / f0 * 0.125;
+        for (size_t kk = 0; kk < k1s.size(); kk++) {
+          const int k1 = k1s[kk];
+          const uint32_t dist = popcnt_xored(desc0 + (o + k0) * D, desc1 + (size_t)k1 * D, D / 16);
+          if (dist < distances) {
+            bool isValid = false, isParallel = false;
+            if (!valid1[k1]) continue;
+            const V3 e1 = ld(&e1_W[3 * (size_t)k1]);
+            if (dot(e0, e1) < 0.5) continue;
+            V3 hp = triangulateFast(r0, e0, r1, e1, sigma, isValid, isParallel);
+            if (!isValid) continue;
+            const double z0 = depth(T_CW0v, hp), z1 = depth(T_CW1, hp);
+            if (dot(e0, e1) < 0.8) isValid = false;
+            if (!isParallel) { if (z0 < 0.2) isValid = false; if (z1 < 0.2) isValid = false; }
+            if (isValid) { k1_max = k1; distances = dist; hps = hp; initialisable = !isParallel; }
+          }
+        }
+        out_dist[o + k0] = distances;
+        if (distances < matchThreshold) {
+          out_k1[o + k0] = k1_max;
+          out_hp_W[4 * (o + k0)] = hps.x; out_hp_W[4 * (o + k0) + 1] = hps.y; out_hp_W[4 * (o + k0) + 2] = hps.z; out_hp_W[4 * (o + k0) + 3] = 1.0;
+          // re-projection into the current view (:1897-1904): T_WC1.inverse() * hps_W, projectHomogeneous (w = 1 > 0)
+          const V3 c = rot(T_CW1_in, hps);   // Transformation::operator*(Vector4d): C * head + r * s
+          const okvo_cam::P3 pc{c.x + T_CW1_in[9] * 1.0, c.y + T_CW1_in[10] * 1.0, c.z + T_CW1_in[11] * 1.0};
+          double pt1p[2];
+          const auto st = okvo_cam::project(model, intr, width, height, pc, pt1p);
+          const double dx = (double)xy1[2 * k1_max] - pt1p[0], dy = (double)xy1[2 * k1_max + 1] - pt1p[1];
+          if (st == okvo_cam::Successful && sqrt(dx * dx + dy * dy) < 4.0) out_flags[o + k0] = (uint8_t)(1 | (initialisable ? 2 : 0));
+          else if (initialisable) out_flags[o + k0] = 2;
+        }
+      }
+    });
+    for (int k0 = 0; k0 < n; k0++) {   // serial insertion
+      if (!(out_flags[o + k0] & 1)) continue;
+      const int k1 = out_k1[o + k0];
+      if (matched1[k1]) continue;      // already matched
+      matched1[k1] = 1;
+      out_flags[o + k0] |= 4;
+    }
+  }
 }
 
 // M4 (single-threaded in the reference; n_threads > 1 splits k0 for the all-cores baseline)

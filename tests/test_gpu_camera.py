@@ -253,3 +253,81 @@ def test_stereo_scan_gate_split_with_dense_hits_and_overflow():
         matched.append(int((ref[0] >= 0).sum()))
     assert matched[0] > 100 and matched[1] > 30 and matched[2] == 0
     fe.close()
+
+
+def test_gate_cos_is_libm_and_both_m4_forms_agree():
+    """The gate constants cos(2.6 sigma) / cos(6 sigma) come from ONE function on host and device (csrc/okb_gatecos.h) that
+    okb_create verified against this machine's libm; the host-buffer M4 (okb_match_stereo) and the device-resident M4
+    (okb_match_stereo_device_ptr) must therefore return identical bits on the same features."""
+    import torch
+    rng = np.random.default_rng(7)
+    fe = Frontend(0)
+    L_ = okl.lib()
+    assert L_.okb_gate_cos_exact(fe.ctx) == 1
+    B, cap, n0, n1 = 1, 512, 480, 500
+    models = []
+    for c in range(2):
+        m = okl.CameraModel(); m.model = 1
+        m.fu, m.fv = EUROC[c]["focal_length"]; m.cu, m.cv = EUROC[c]["principal_point"]
+        for i in range(4):
+            m.k[i] = EUROC[c]["distortion_coefficients"][i]
+        models.append(m)
+    kps = [np.zeros((B, cap), okl.KP_DTYPE) for _ in range(2)]
+    descs = [np.zeros((B, cap, 64), np.uint8) for _ in range(2)]
+    base = rng.integers(0, 256, (n0, 64), dtype=np.uint8)
+    for c, n in enumerate((n0, n1)):
+        kps[c][0]["x"][:n] = rng.uniform(40, 700, n); kps[c][0]["y"][:n] = rng.uniform(40, 440, n)
+        kps[c][0]["size"][:n] = (rng.uniform(8.4, 108.0, n)).astype(np.float32)     # continuous sizes: many distinct sigmas
+        descs[c][0, :n] = rng.integers(0, 256, (n, 64), dtype=np.uint8)
+    m = min(n0, n1)
+    kps[1][0]["x"][:m] = kps[0][0]["x"][:m] - rng.uniform(2, 30, m).astype(np.float32)
+    kps[1][0]["y"][:m] = kps[0][0]["y"][:m] + rng.uniform(-0.3, 0.3, m).astype(np.float32)
+    flips = rng.random((m, 512)) < 0.03
+    descs[0][0, :m] = base[:m]; descs[1][0, :m] = base[:m] ^ np.packbits(flips, axis=1)
+    counts = [[n0], [n1]]
+    d_kp = [torch.from_numpy(k.view(np.uint8).reshape(B, cap * 28)).cuda() for k in kps]
+    d_desc = [torch.from_numpy(d).cuda() for d in descs]
+    d_cnt = [torch.tensor(c, dtype=torch.int32).cuda() for c in counts]
+    C0 = np.eye(3); r0 = np.zeros(3); C1 = np.eye(3); r1 = np.array([0.11, 0.0, 0.0])
+    k1 = torch.zeros((B, cap), dtype=torch.int32, device="cuda"); dist = torch.zeros((B, cap), dtype=torch.int32, device="cuda")
+    hp = torch.zeros((B, cap, 4), dtype=torch.float64, device="cuda"); init = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
+    okl.check(L_.okb_match_stereo_device_ptr(fe.ctx, B, cap, d_kp[0].data_ptr(), d_desc[0].data_ptr(), d_cnt[0].data_ptr(),
+                                             C.addressof(models[0]), C0.ctypes.data, r0.ctypes.data, cap, d_kp[1].data_ptr(),
+                                             d_desc[1].data_ptr(), d_cnt[1].data_ptr(), C.addressof(models[1]), C1.ctypes.data,
+                                             r1.ctypes.data, 60, None, k1.data_ptr(), dist.data_ptr(), hp.data_ptr(), init.data_ptr()))
+    okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    kp0, kp1 = kps[0][0][:n0], kps[1][0][:n1]
+    rays0, v0 = oracle_bp(EUROC[0], kp0); rays1, v1 = oracle_bp(EUROC[1], kp1)
+    f0 = 0.5 * sum(EUROC[0]["focal_length"]); f1 = 0.5 * sum(EUROC[1]["focal_length"])
+    host = fe.matchStereo(descs[0][0, :n0], v0, world_rays(C0, rays0), kp0["size"].astype(np.float64) / f0, descs[1][0, :n1], v1,
+                          world_rays(C1, rays1), kp1["size"].astype(np.float64) / f1, r0, r1, T_CW(C0, r0), T_CW(C1, r1))
+    ref = oracle.match_stereo(descs[0][0, :n0], v0, world_rays(C0, rays0), kp0["size"].astype(np.float64) / f0, descs[1][0, :n1], v1,
+                              world_rays(C1, rays1), kp1["size"].astype(np.float64) / f1, r0, r1, T_CW(C0, r0), T_CW(C1, r1), 60)
+    dev = (k1.cpu().numpy()[0, :n0], dist.cpu().numpy().view(np.uint32)[0, :n0], hp.cpu().numpy()[0, :n0], init.cpu().numpy()[0, :n0])
+    for a, b, r in zip(dev, host, ref):
+        assert np.array_equal(np.asarray(a).view(np.uint8), np.asarray(b).view(np.uint8)), "device-resident and host-buffer M4 differ"
+        assert np.array_equal(np.asarray(b).view(np.uint8), np.asarray(r).view(np.uint8)), "M4 differs from the oracle (libm cos)"
+    assert (ref[0] >= 0).sum() > 100
+    fe.close()
+
+
+def test_export_features_block_layout():
+    """okb_export_features: [counts | keypoints | descriptors] of a batch, the unit the camera-sharded mode all-gathers."""
+    import torch
+    from okvis2_b200 import sharding as sh
+    B = 2
+    fe = Frontend(1, 752, 480, max_batch=B)
+    fe.configure(threshold=30, octaves=3, max_keypoints=600)
+    L_ = okl.lib()
+    imgs = np.stack([synth_stereo(40 + t, 752, 480)[0] for t in range(B)])
+    feats = fe.detectAndDescribeBatch(0, imgs)
+    cap = C.c_int(0); L_.okb_device_features(fe.ctx, 0, None, None, None, C.byref(cap)); cap = cap.value
+    nbytes = L_.okb_feature_block_bytes(B, cap)
+    assert nbytes == sh.block_layout(B, cap)[3]
+    blk = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    okl.check(L_.okb_export_features(fe.ctx, 0, B, blk.data_ptr()))
+    okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    counts, kps, descs = sh.unpack_block(blk.cpu().numpy(), B, cap, okl.KP_DTYPE)
+    for b in range(B):
+        assert counts[b] == len(feats[b][0]) and kps[b].tobytes() == feats[b][0].tobytes() and np.array_equal(descs[b], feats[b][1])
+    fe.close()

@@ -187,3 +187,28 @@ def test_matchers_from_two_host_threads(fe):
         ref = oracle.match_stereo(x["desc0"], x["valid0"], x["e0_W"], x["sof0"], x["desc1"], x["valid1"], x["e1_W"], x["sof1"],
                                   x["r_WC0"], x["r_WC1"], x["T_CW0"], x["T_CW1"], 60)
         eq(out[i], ref, f"thread {i}")
+
+
+def test_pool_validation_and_descriptor_width_mismatch():
+    """Bad pool indices and a pool whose descriptor width differs from the camera's are argument errors, not device faults."""
+    import ctypes as C
+    from okvis2_b200 import lib as okl
+    from okvis2_b200.lib import OkbError
+    fe = Frontend(1, 752, 480)
+    try:
+        rng = np.random.default_rng(1)
+        d = rng.integers(0, 256, (10, 64), dtype=np.uint8); xy = rng.uniform(0, 400, (10, 2))
+        cd = rng.integers(0, 256, (4, 64), dtype=np.uint8)
+        proj = rng.uniform(0, 400, (2, 2)); is3d = np.ones(2, np.uint8)
+        for bad in ([0, 1, 2, 1], [0, 0, 1, 0], [-1, 0, 1, 1]):
+            with pytest.raises(OkbError) as e:
+                fe.matchToMapByThread(d, xy, None, cd, np.array(bad, np.int32), proj, is3d)
+            assert e.value.status == okl.OKB_ERR_ARGUMENT
+        # D = 48 pool against a camera that describes with 64 bytes
+        L_ = okl.lib()
+        import torch
+        z = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+        rc = L_.okb_match_map3d_device(fe.ctx, 0, 48, 1, 4, z.data_ptr(), z.data_ptr(), 2, z.data_ptr(), z.data_ptr(), 20.0, 60, z.data_ptr(), z.data_ptr())
+        assert rc == okl.OKB_ERR_ARGUMENT and b"48 bytes" in L_.okb_last_error()
+    finally:
+        fe.close()
