@@ -42,11 +42,20 @@ struct Worker {  // persistent detection thread of one camera
 };
 }  // namespace
 
+// M3 inputs of the streaming loop (one camera): views + poses of ONE frame, list capacity
+struct okb_stream_m3 { int32_t n_older, cap0, cap_m, pad_; const okb_older_view_t* older[2]; const double* T_WC1[2]; const double* T_CW1[2]; };
+
 extern "C" int okb_e2e_run(okb_context_t* ctx, int n_frames, int warmup, int W, int H, const uint8_t* left, const uint8_t* right,
                            int cap, double f, const int* n_cand, const uint8_t* const* cand_desc, const int32_t* const* cand_lm,
-                           const int* n_lm, const double* const* lm_proj, const uint8_t* const* lm_is3d, double* seconds,
-                           long long* h2d_bytes, long long* d2h_bytes, long long* total_kp, long long* total_matches)
+                           const int* n_lm, const double* const* lm_proj, const uint8_t* const* lm_is3d, const okb_stream_m3* m3,
+                           double* seconds, long long* h2d_bytes, long long* d2h_bytes, long long* total_kp, long long* total_matches)
 {
+  std::vector<uint8_t> matched[2]; std::vector<int32_t> m_n[2], m_k0[2], m_k1[2]; std::vector<uint8_t> m_fl[2]; std::vector<double> m_hp[2];
+  const int n_older = m3 ? m3->n_older : 0;
+  for (int c = 0; c < 2 && n_older > 0; c++) {
+    matched[c].resize(cap); m_n[c].resize(n_older); m_k0[c].resize((size_t)n_older * m3->cap_m); m_k1[c].resize((size_t)n_older * m3->cap_m);
+    m_fl[c].resize((size_t)n_older * m3->cap_m); m_hp[c].resize((size_t)n_older * m3->cap_m * 4);
+  }
   std::vector<okb_keypoint_t> kp[2]; std::vector<uint8_t> desc[2]; int n[2] = {0, 0}; int rc2[2] = {0, 0};
   for (int c = 0; c < 2; c++) { kp[c].resize(cap); desc[c].resize((size_t)cap * 64); }
   std::vector<double> e[2], sof[2], xy[2]; std::vector<uint8_t> valid[2];
@@ -92,6 +101,22 @@ extern "C" int okb_e2e_run(okb_context_t* ctx, int n_frames, int warmup, int W, 
     if (rc || rc_m1) return rc ? rc : rc_m1;
     for (int k = 0; k < n[0]; k++) nm += lm[k] >= 0;
     for (int k = 0; k < n[1]; k++) nm += lm1[k] >= 0;
+    if (n_older > 0) {   // M3 of both cameras (camera 1 on the worker thread), candidate set = keypoints without a landmark from M1
+      auto motion = [&](int c, const int32_t* lmv) -> int {
+        for (int k = 0; k < cap; k++) matched[c][k] = (k < n[c] && lmv[k] >= 0) ? 1 : 0;
+        return okb_match_motion_stereo_batch(ctx, c, 1, m3->T_WC1[c], m3->T_CW1[c], n_older, m3->older[c], m3->cap0, 60, cap, matched[c].data(),
+                                             m3->cap_m, m_n[c].data(), m_k0[c].data(), m_k1[c].data(), m_fl[c].data(), m_hp[c].data());
+      };
+      int rc_b = 0;
+      w.submit([&] { rc_b = motion(1, lm1.data()); });
+      const int rc_a = motion(0, lm.data());
+      w.wait();
+      if (rc_a || rc_b) return rc_a ? rc_a : rc_b;
+      for (int c = 0; c < 2; c++) {
+        for (int v = 0; v < n_older; v++) for (int j = 0; j < m_n[c][v]; j++) nm += (m_fl[c][(size_t)v * m3->cap_m + j] & 4) != 0;
+        h2d += 192 + cap + (long long)n_older * (long long)sizeof(okb_older_view_t); d2h += (long long)n_older * (4 + (long long)m3->cap_m * 41) + cap;
+      }
+    }
     h2d += (long long)(n[0] + n[1]) * (64 + 24 + 8 + 2 * 8 + 1); d2h += (long long)n[0] * (4 + 4 + 32 + 1);
     for (int c = 0; c < 2; c++) {
       h2d += (long long)W * H + (long long)n[c] * (64 + 16) + (long long)n_cand[c] * 68 + (long long)n_lm[c] * 17;
@@ -126,6 +151,14 @@ struct okb_replay_io {
   int32_t* k1; uint32_t* sdist; double* hp; uint8_t* init;
   double seconds; long long h2d, d2h, nkp, nm;             // results
   int32_t lane, lanes;                                     // this replay is sequence `lane` of `lanes` concurrent ones (0, 0 = alone)
+  // M3 (Frontend::matchMotionStereo): per camera the older keyframe views (device blocks: the keyframe feature store), poses,
+  // the matched mask (host, derived from the M1 result) and the compact match lists
+  int32_t n_older, cap0, cap_m, pad2_;
+  const okb_older_view_t* older[2];                        // batch * n_older entries
+  const double* T_WC1[2]; const double* T_CW1[2];          // batch x 12
+  uint8_t* matched[2];                                     // batch x cap
+  int32_t* n_match[2]; int32_t* m_k0[2]; int32_t* m_k1[2]; uint8_t* m_flags[2]; double* m_hp[2];
+  long long n_m3;                                          // inserted M3 matches of the last step
 };
 
 namespace {
@@ -175,7 +208,7 @@ static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, st
   const size_t frame = (size_t)io->W * io->H;
   int rcs[2] = {0, 0};
   const bool trace = getenv("OKB_E2E_TRACE") != nullptr;
-  double t_det[2] = {0, 0}, t_m1[2] = {0, 0}, t_m4 = 0;
+  double t_det[2] = {0, 0}, t_m1[2] = {0, 0}, t_m3[2] = {0, 0}, t_m4 = 0;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
   auto camera = [&](int c, int s) {
@@ -187,7 +220,16 @@ static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, st
     t_det[c] += ms(ta, tb);
     if (!rc) rc = okb_match_map3d_batch(ctx, c, 64, B, io->n_cand[c], io->cand_desc[c], io->cand_lm[c], io->n_lm[c], io->lm_proj[c],
                                         io->lm_is3d[c], 20.0, 60, cap, io->m1_dist[c], io->m1_lm[c]);
-    t_m1[c] += ms(tb, now());
+    const auto tc = now();
+    t_m1[c] += ms(tb, tc);
+    if (!rc && io->n_older > 0) {
+      // the keypoints that M1 gave a landmark leave the candidate set of M3 (Frontend.cpp:1792-1795)
+      for (int b = 0; b < B; b++)
+        for (int k = 0; k < cap; k++) io->matched[c][(size_t)b * cap + k] = (k < io->n[c][b] && io->m1_lm[c][(size_t)b * cap + k] >= 0) ? 1 : 0;
+      rc = okb_match_motion_stereo_batch(ctx, c, B, io->T_WC1[c], io->T_CW1[c], io->n_older, io->older[c], io->cap0, 60, cap, io->matched[c],
+                                         io->cap_m, io->n_match[c], io->m_k0[c], io->m_k1[c], io->m_flags[c], io->m_hp[c]);
+      t_m3[c] += ms(tc, now());
+    }
     rcs[c] = rc;
   };
   Worker w; w.start();
@@ -214,8 +256,8 @@ static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, st
   io->seconds = std::chrono::duration<double>(t1 - t0).count();
   if (trace) {
     const int n = io->n_steps + io->warmup;
-    fprintf(stderr, "[okb_e2e_replay] per step (ms): detect %.3f / %.3f  map3d %.3f / %.3f  stereo %.3f\n", t_det[0] / n, t_det[1] / n,
-            t_m1[0] / n, t_m1[1] / n, t_m4 / n);
+    fprintf(stderr, "[okb_e2e_replay] per step (ms): detect %.3f / %.3f  map3d %.3f / %.3f  motion %.3f / %.3f  stereo %.3f\n", t_det[0] / n, t_det[1] / n,
+            t_m1[0] / n, t_m1[1] / n, t_m3[0] / n, t_m3[1] / n, t_m4 / n);
   }
   // bytes per step, counted from the copies the three calls issue (row stride = cap)
   long long h2d = 0, d2h = 0;
@@ -224,6 +266,11 @@ static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, st
     d2h += (long long)B * cap * (28 + 64 + 25) + 8LL * B + (long long)B * cap * 8;
   }
   d2h += (long long)B * cap * 41;
+  if (io->n_older > 0)
+    for (int c = 0; c < 2; c++) {
+      h2d += (long long)B * 192 + (long long)B * cap + (long long)B * io->n_older * (long long)sizeof(okb_older_view_t);
+      d2h += (long long)B * io->n_older * (4 + (long long)io->cap_m * 41) + (long long)B * cap;
+    }
   io->h2d = h2d; io->d2h = d2h;
   long long nkp = 0, nm = 0;   // of the last step (sanity numbers for the bench line)
   for (int c = 0; c < 2; c++)
@@ -233,6 +280,11 @@ static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, st
     }
   for (int b = 0; b < B; b++)
     for (int k = 0; k < io->n[0][b]; k++) nm += io->k1[(size_t)b * cap + k] >= 0;
-  io->nkp = nkp; io->nm = nm;
+  long long n_m3 = 0;
+  if (io->n_older > 0)
+    for (int c = 0; c < 2; c++)
+      for (int i = 0; i < B * io->n_older; i++)
+        for (int j = 0; j < io->n_match[c][i] && j < io->cap_m; j++) n_m3 += (io->m_flags[c][(size_t)i * io->cap_m + j] & 4) != 0;
+  io->nkp = nkp; io->nm = nm + n_m3; io->n_m3 = n_m3;
   return rc;
 }

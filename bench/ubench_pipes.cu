@@ -18,6 +18,10 @@ template <int OP> __device__ __forceinline__ uint32_t op(uint32_t a, uint32_t b,
   if constexpr (OP == 9) { uint32_t r; asm volatile("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
   if constexpr (OP == 10) return a * b + c;   // IMAD
   if constexpr (OP == 11) return __vimax3_s16x2_relu(a, b, c);
+  if constexpr (OP == 12) return (uint32_t)__popc(a ^ b) + c;          // POPC.b32 (+ 1 IADD/LOP on another pipe)
+  if constexpr (OP == 13) return (uint32_t)__popcll(((unsigned long long)(a ^ b) << 32) | (a ^ c));   // popc.b64 = 2 POPC + add
+  if constexpr (OP == 14) return __viaddmax_s16x2_relu(a, b, c);
+  if constexpr (OP == 15) return __vadd2(a, b);
   return 0;
 }
 template <int OP, int OP2> __global__ void k(uint32_t* out, uint32_t seed, long long* cyc)
@@ -41,6 +45,7 @@ template <int OP, int OP2> __global__ void k(uint32_t* out, uint32_t seed, long 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
+static double g_last_rate = 0;
 template <int OP, int OP2> void run(const char* name, uint32_t* d, long long* dc)
 {
   const int threads = 1024;   // 32 warps / SM = 8 per SMSP
@@ -50,6 +55,7 @@ template <int OP, int OP2> void run(const char* name, uint32_t* d, long long* dc
   cudaDeviceSynchronize();
   long long c; cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
   double warp_instr_per_sm = (double)ITERS * 8 * (threads / 32);
+  g_last_rate = warp_instr_per_sm / c;
   printf("%-34s cycles %8lld  warp-instr/clk/SM %.3f  (cycles per warp-instr per SMSP %.2f)  %s\n", name, c, warp_instr_per_sm / c,
          c / (warp_instr_per_sm / 4), cudaGetErrorString(cudaGetLastError()));
 }
@@ -74,5 +80,18 @@ int main()
   run<0, 10>("vimin3_u16x2 + imad (1:1)", d, dc);
   run<3, 6>("hmin2 + hfma2.relu (1:1)", d, dc);
   run<0, 4>("vimin3_u16x2 + fmnmx3 (1:1)", d, dc);
+  run<14, -1>("viaddmax_s16x2_relu", d, dc);
+  run<15, -1>("vadd2 (VIADD.16x2)", d, dc);
+  run<12, -1>("popc.b32 (+ iadd)", d, dc);
+  const double popc32 = g_last_rate;   // warp instructions (each = one POPC) per clk per SM
+  run<13, -1>("popcll (2 x popc.b32 + add)", d, dc);
+  // the matchers' roofline denominator: POPC.b32 lanes per clock per SM (written where bench.py reads it)
+  FILE* f = fopen("gpurun_out/popc_rate.json", "w");
+  if (f) {
+    fprintf(f, "{\"popc_b32_lanes_per_clk_per_sm\": %.3f, \"popc_b32_warp_instr_per_clk_per_sm\": %.4f, \"popcll_warp_instr_per_clk_per_sm\": %.4f, "
+               "\"how\": \"bench/ubench_pipes.cu on the B200: 148 x 1024 threads, 8 independent chains per thread, clock64 around 4096 iterations\"}\n",
+            popc32 * 32, popc32, g_last_rate);
+    fclose(f);
+  }
   return 0;
 }

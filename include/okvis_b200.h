@@ -97,6 +97,10 @@ int okb_fetch_features(okb_context_t* ctx, int cam, int frame, okb_keypoint_t* k
 int okb_device_features(okb_context_t* ctx, int cam, const okb_keypoint_t** d_kp, const uint8_t** d_desc,
                         const int32_t** d_count, int* capacity);
 
+/* device pointers of the back-projections (D4) of the last detect call of camera `cam` (camera model set):
+ * rays [max_batch][capacity][3] doubles (x, y, 1), valid [max_batch][capacity]; valid until the next detect call on it */
+int okb_device_back_projections(okb_context_t* ctx, int cam, const double** d_rays, const uint8_t** d_valid);
+
 /* Fixed-capacity feature block of a batch, the unit the camera-sharded multi-GPU mode all-gathers:
  *   [counts: n_frames x int32, padded to 256 B][keypoints: n_frames x capacity x 28 B][descriptors: n_frames x capacity x 64 B]
  * okb_export_features packs the last result of camera `cam` into the caller's DEVICE buffer (asynchronous on the camera
@@ -136,6 +140,25 @@ typedef struct {
 int okb_set_camera_model(okb_context_t* ctx, int cam, const okb_camera_model_t* model);
 /* rays_out: n x 3 doubles (x, y, 1); valid_out: n success flags (Frame::backProjectionsValid_). Host buffers. */
 int okb_back_project(okb_context_t* ctx, int cam, int n, const okb_keypoint_t* kp, double* rays_out, uint8_t* valid_out);
+
+
+/* ---- D5: camera-awareness maps. Replaces PinholeCamera<D>::initialiseCameraAwarenessMaps (okvis_cv/include/okvis/cameras/
+ *      implementation/PinholeCamera.hpp:179-208, called once per camera at configuration load, ViParametersReader.cpp:105): for
+ *      every pixel the normalised back-projection (rays: height x width x 3 floats, CV_32FC3; zero where backProject fails) and the
+ *      2 x 3 Jacobian of the projection at that ray (jac: height x width x 6 floats, CV_32FC(6), row-major; zero where the
+ *      projection is not Successful -- the reference leaves those entries uninitialised). Uses the model of okb_set_camera_model
+ *      and the camera's width / height; the maps also stay on the device for the camera-aware extractor. Either output may be
+ *      NULL. Synchronous. */
+int okb_camera_awareness_maps(okb_context_t* ctx, int cam, float* rays_out, float* jac_out);
+
+/* ---- NCameraSystem::computeOverlaps (okvis_cv/src/NCameraSystem.cpp:48-118): for every ordered camera pair (seenBy, cam) every
+ *      pixel of `cam` is back-projected, rotated into `seenBy` (C_rel[(seenBy * n + cam) * 9 ..]: the rotation
+ *      (T_SC[seenBy]->inverse() * *T_SC[cam]).C(), row-major), projected, and verified by a back-projection of the image point
+ *      (|cos - 1| < 1e-10). overlaps_out: n x n bytes = NCameraSystem::hasOverlap(seenBy, cam), the test Frontend::matchStereo
+ *      uses to pick its camera pairs (Frontend.cpp:1990-2000). mats_out: NULL, or n x n host pointers (NULL entries allowed) that
+ *      receive overlapMats_[seenBy][cam] (height[cam] x width[cam] bytes). Synchronous. */
+int okb_compute_overlaps(okb_context_t* ctx, int n_cams, const okb_camera_model_t* models, const int32_t* widths, const int32_t* heights,
+                         const double* C_rel, uint8_t* overlaps_out, uint8_t* const* mats_out);
 
 /* When a camera model is set, okb_detect_describe* also back-projects the keypoints it returns (same kernel as
  * okb_back_project) and keeps the rays in pinned host memory: this call only copies them out (frame = index inside the
@@ -273,6 +296,16 @@ typedef struct {
 int okb_match_motion_stereo_device(okb_context_t* ctx, int cam, int n_frames, const double* T_WC1, const double* T_CW1, int n_older,
                                    const okb_older_view_t* older, int cap0, uint32_t match_threshold, uint8_t* d_matched1,
                                    int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags);
+/* d_matched[b][k] = (d_lm[b][k] >= 0) for the keypoints of frame b of the last detect call of `cam`, 0 beyond its count: the
+ * `landmarkId != 0` test (Frontend.cpp:1792-1795) on the output of okb_match_map3d_device. Asynchronous on okb_stream(ctx, cam). */
+int okb_matched_mask_device(okb_context_t* ctx, int cam, int n_frames, const int32_t* d_lm, uint8_t* d_matched);
+/* Host-buffer form (replay use; benchmark "e2e" leg): the older views stay device blocks (the keyframe feature store), poses and
+ * the matched mask come from / go to HOST memory (matched1: n_frames x cap bytes, in/out), and only the MATCHING entries return:
+ * per (frame, view) n_match and, in ascending k0 (the order of the insertion loop, Frontend.cpp:1915), up to cap_m entries of
+ * m_k0, m_k1, m_flags, m_hp_W (x 4). More than cap_m matches of a view -> OKB_ERR_CAPACITY. Synchronous. */
+int okb_match_motion_stereo_batch(okb_context_t* ctx, int cam, int n_frames, const double* T_WC1, const double* T_CW1, int n_older,
+                                  const okb_older_view_t* older, int cap0, uint32_t match_threshold, int cap, uint8_t* matched1,
+                                  int cap_m, int32_t* n_match, int32_t* m_k0, int32_t* m_k1, uint8_t* m_flags, double* m_hp_W);
 /* Same on explicit device feature blocks of the current frames (keypoints [n_frames][cap1], descriptors [n_frames][cap1][64],
  * counts [n_frames]); `stream` = cudaStream_t or NULL. */
 int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,

@@ -274,6 +274,17 @@ int okb_device_features(okb_context_t* ctx, int cam, const okb_keypoint_t** d_kp
   return OKB_OK;
 }
 
+int okb_device_back_projections(okb_context_t* ctx, int cam, const double** d_rays, const uint8_t** d_valid)
+{
+  int rc = check_cam(ctx, cam, "okb_device_back_projections");
+  if (rc) return rc;
+  CamWorkspace& ws = ctx->cams[cam];
+  if (!ws.has_model) { set_error("okb_device_back_projections: camera %d has no model (okb_set_camera_model)", cam); return OKB_ERR_ARGUMENT; }
+  if (d_rays) *d_rays = ws.d_rays;
+  if (d_valid) *d_valid = ws.d_rays_valid;
+  return OKB_OK;
+}
+
 size_t okb_feature_block_bytes(int n_frames, int capacity)
 {
   const size_t counts = ((size_t)n_frames * 4 + 255) & ~(size_t)255;

@@ -12,6 +12,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "okb_internal.h"
 #include "okb_gatecos.h"
 #include "okb_camdev.h"
@@ -31,6 +33,71 @@ __global__ void __launch_bounds__(128) k_backproject(Model m, const okb_keypoint
   const bool ok = back_project(m, (double)kp[i].x, (double)kp[i].y, rx, ry);
   rays[3 * i] = rx; rays[3 * i + 1] = ry; rays[3 * i + 2] = 1.0;
   valid[i] = ok ? 1 : 0;
+}
+
+
+// D5: PinholeCamera::initialiseCameraAwarenessMaps (cameras/implementation/PinholeCamera.hpp:179-208), one thread per pixel
+__device__ __forceinline__ int project_jac(const Model& m, int width, int height, double px, double py, double pz, double& kx, double& ky, double (&J)[2][3])
+{
+  if (fabs(pz) < 1.0e-12) return kProjInvalid;
+  const double rz = 1.0 / pz;
+  const double rz2 = rz * rz;
+  const double u0 = px * rz, u1 = py * rz;
+  double d0, d1, D[2][2];
+  if (m.model == 1) distort_radtan(m, u0, u1, d0, d1, D);
+  else if (m.model == 2) distort_equi(m, u0, u1, d0, d1, D);
+  else { d0 = u0; d1 = u1; D[0][0] = 1; D[0][1] = 0; D[1][0] = 0; D[1][1] = 1; }
+  J[0][0] = m.fu * D[0][0] * rz;
+  J[0][1] = m.fu * D[0][1] * rz;
+  J[0][2] = -m.fu * (px * D[0][0] + py * D[0][1]) * rz2;
+  J[1][0] = m.fv * D[1][0] * rz;
+  J[1][1] = m.fv * D[1][1] * rz;
+  J[1][2] = -m.fv * (px * D[1][0] + py * D[1][1]) * rz2;
+  kx = m.fu * d0 + m.cu; ky = m.fv * d1 + m.cv;
+  if (kx < 0.0 || ky < 0.0 || kx >= width || ky >= height) return kProjOutside;
+  return pz > 0.0 ? kProjSuccessful : kProjBehind;
+}
+
+__global__ void __launch_bounds__(128) k_awareness_maps(Model m, int width, int height, float* rays, float* jac)
+{
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= width) return;
+  double rx, ry, rz = 1.0;
+  if (back_project(m, (double)u, (double)v, rx, ry)) {
+    const double n = sqrt((rx * rx + ry * ry) + rz * rz);
+    rx /= n; ry /= n; rz /= n;
+  } else { rx = ry = rz = 0.0; }
+  const size_t i = (size_t)v * width + u;
+  rays[3 * i] = (float)rx; rays[3 * i + 1] = (float)ry; rays[3 * i + 2] = (float)rz;
+  double kx, ky, J[2][3];
+  const bool ok = project_jac(m, width, height, rx, ry, rz, kx, ky, J) == kProjSuccessful;
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) jac[6 * i + 3 * r + k] = ok ? (float)J[r][k] : 0.f;   // the reference leaves non-Successful entries uninitialised
+}
+
+// NCameraSystem::computeOverlaps (okvis_cv/src/NCameraSystem.cpp:48-118) for one (seenBy, cam) pair, one thread per pixel of `cam`
+struct OverlapPair { Model cam, other; int w, h, ow, oh; double C[9]; uint8_t* mat; uint8_t* flag; };
+__global__ void __launch_bounds__(128) k_compute_overlaps(const __grid_constant__ OverlapPair p)
+{
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= p.w) return;
+  double rx, ry;
+  back_project(p.cam, (double)u, (double)v, rx, ry);   // the success flag is ignored, as in the reference
+  const double ox = (p.C[0] * rx + p.C[1] * ry) + p.C[2] * 1.0, oy = (p.C[3] * rx + p.C[4] * ry) + p.C[5] * 1.0,
+               oz = (p.C[6] * rx + p.C[7] * ry) + p.C[8] * 1.0;
+  double kx, ky;
+  uint8_t hit = 0;
+  if (project(p.other, p.ow, p.oh, ox, oy, oz, kx, ky) == kProjSuccessful) {
+    double vx, vy;
+    back_project(p.other, kx, ky, vx, vy);
+    const double n0 = sqrt((ox * ox + oy * oy) + oz * oz), n1 = sqrt((vx * vx + vy * vy) + 1.0 * 1.0);
+    const double d = ((ox / n0) * (vx / n1) + (oy / n0) * (vy / n1)) + (oz / n0) * (1.0 / n1);
+    if (fabs(d - 1.0) < 1.0e-10) hit = 1;
+  }
+  if (p.mat) p.mat[(size_t)v * p.w + u] = hit;
+  if (hit) *p.flag = 1;
 }
 
 // world-frame inputs of the stereo matcher: e_W = (C_WC * e_C).normalized(), size/f, cos(2.6 sigma), cos(6 sigma)
@@ -99,6 +166,64 @@ int okb_set_camera_model(okb_context_t* ctx, int cam, const okb_camera_model_t* 
   }
   ctx->cams[cam].model = *model; ctx->cams[cam].has_model = 1;
   return OKB_OK;
+}
+
+
+int okb_camera_awareness_maps(okb_context_t* ctx, int cam, float* rays_out, float* jac_out)
+{
+  if (!ctx || cam < 0 || cam >= ctx->n_cams) { set_error("okb_camera_awareness_maps: bad camera"); return OKB_ERR_ARGUMENT; }
+  CamWorkspace& ws = ctx->cams[cam];
+  if (!ws.has_model) { set_error("okb_camera_awareness_maps: camera %d has no model (okb_set_camera_model)", cam); return OKB_ERR_ARGUMENT; }
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  const int W = ws.cfg.width, H = ws.cfg.height;
+  const size_t n = (size_t)W * H;
+  if (!ws.d_ray_map) { OKB_CUDA(cudaMalloc(&ws.d_ray_map, n * 12)); OKB_CUDA(cudaMalloc(&ws.d_jac_map, n * 24)); }
+  k_awareness_maps<<<dim3((W + 127) / 128, H), 128, 0, ws.stream>>>(to_model(ws.model), W, H, ws.d_ray_map, ws.d_jac_map);
+  ctx->launches++;
+  OKB_CUDA(cudaGetLastError());
+  if (rays_out) OKB_CUDA(cudaMemcpyAsync(rays_out, ws.d_ray_map, n * 12, cudaMemcpyDeviceToHost, ws.stream));
+  if (jac_out) OKB_CUDA(cudaMemcpyAsync(jac_out, ws.d_jac_map, n * 24, cudaMemcpyDeviceToHost, ws.stream));
+  OKB_CUDA(cudaStreamSynchronize(ws.stream));
+  ws.maps_ready = 1;
+  return OKB_OK;
+}
+
+int okb_compute_overlaps(okb_context_t* ctx, int n_cams, const okb_camera_model_t* models, const int32_t* widths, const int32_t* heights,
+                         const double* C_rel, uint8_t* overlaps_out, uint8_t* const* mats_out)
+{
+  if (!ctx || n_cams < 1 || n_cams > 64 || !models || !widths || !heights || !C_rel || !overlaps_out) { set_error("okb_compute_overlaps: bad arguments"); return OKB_ERR_ARGUMENT; }
+  for (int i = 0; i < n_cams; i++)
+    if (widths[i] < 1 || heights[i] < 1 || models[i].model < 0 || models[i].model > 2 || !(models[i].fu > 0) || !(models[i].fv > 0)) {
+      set_error("okb_compute_overlaps: camera %d", i); return OKB_ERR_ARGUMENT;
+    }
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->match_slots[0].stream;
+  size_t max_px = 0; for (int i = 0; i < n_cams; i++) max_px = std::max(max_px, (size_t)widths[i] * heights[i]);
+  uint8_t* d_flags = nullptr; uint8_t* d_mat = nullptr;
+  OKB_CUDA(cudaMalloc(&d_flags, (size_t)n_cams * n_cams));
+  OKB_CUDA(cudaMemsetAsync(d_flags, 0, (size_t)n_cams * n_cams, st));
+  if (mats_out) OKB_CUDA(cudaMalloc(&d_mat, max_px));
+  int rc = OKB_OK;
+  for (int s = 0; s < n_cams && rc == OKB_OK; s++)
+    for (int c = 0; c < n_cams && rc == OKB_OK; c++) {
+      uint8_t* host_mat = mats_out ? mats_out[s * n_cams + c] : nullptr;
+      if (s == c) { if (host_mat) memset(host_mat, 1, (size_t)widths[c] * heights[c]); continue; }   // self-visibility is trivial
+      OverlapPair p; memset(&p, 0, sizeof(p));
+      p.cam = to_model(models[c]); p.other = to_model(models[s]); p.w = widths[c]; p.h = heights[c]; p.ow = widths[s]; p.oh = heights[s];
+      for (int i = 0; i < 9; i++) p.C[i] = C_rel[9 * (size_t)(s * n_cams + c) + i];
+      p.mat = host_mat ? d_mat : nullptr; p.flag = d_flags + s * n_cams + c;
+      k_compute_overlaps<<<dim3((p.w + 127) / 128, p.h), 128, 0, st>>>(p);
+      ctx->launches++;
+      if (cudaGetLastError() != cudaSuccess) { set_error("okb_compute_overlaps: launch failed"); rc = OKB_ERR_CUDA; break; }
+      if (host_mat && cudaMemcpyAsync(host_mat, d_mat, (size_t)p.w * p.h, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = OKB_ERR_CUDA;
+      if (host_mat && cudaStreamSynchronize(st) != cudaSuccess) rc = OKB_ERR_CUDA;
+    }
+  if (rc == OKB_OK && cudaMemcpyAsync(overlaps_out, d_flags, (size_t)n_cams * n_cams, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = OKB_ERR_CUDA;
+  if (cudaStreamSynchronize(st) != cudaSuccess) rc = OKB_ERR_CUDA;
+  cudaFree(d_flags); cudaFree(d_mat);
+  if (rc == OKB_OK) for (int i = 0; i < n_cams; i++) overlaps_out[i * n_cams + i] = 1;
+  if (rc == OKB_ERR_CUDA) set_error("okb_compute_overlaps: CUDA error");
+  return rc;
 }
 
 int okb_back_project(okb_context_t* ctx, int cam, int n, const okb_keypoint_t* kp, double* rays_out, uint8_t* valid_out)

@@ -90,6 +90,7 @@ struct CamWorkspace {
   // D4: camera model and the rays of the last batch
   okb_camera_model_t model; int has_model = 0;
   double* d_rays = nullptr; uint8_t* d_rays_valid = nullptr;
+  float* d_ray_map = nullptr; float* d_jac_map = nullptr; int maps_ready = 0;   // D5: camera-awareness maps (H x W x 3, H x W x 6)
   cudaEvent_t ev_done = nullptr;
   // TMA tensor maps of the internal layers (layer 0 is encoded per call)
   CUtensorMap tma[kMaxLayers]; int tma_use[kMaxLayers] = {0}; int tma_ready = 0;
@@ -99,6 +100,7 @@ struct CamWorkspace {
   uint8_t* d_m1_rows = nullptr; size_t m1_rows_cap = 0;   // M1 row bins of the device-resident form (grown on demand)
   // staging of the host-buffer batch matchers (okb_match_map3d_batch / okb_match_stereo_batch), grown on demand
   uint8_t* m_d = nullptr; uint8_t* m_h = nullptr; size_t m_cap = 0;
+  uint8_t* m3_d = nullptr; uint8_t* m3_h = nullptr; size_t m3_cap = 0;   // staging of okb_match_motion_stereo_batch
   // pinned staging
   uint8_t* h_img = nullptr;
   okb_keypoint_t* h_kp = nullptr;

@@ -809,6 +809,46 @@ __global__ void __launch_bounds__(128) k_m3_commit(const __grid_constant__ M3Che
   if (c.claim[j] == k0) { c.flags[i] = fl | 4; c.matched1[j] = 1; }
 }
 
+// matched[b][k] = lm[b][k] >= 0 (the `landmarkId != 0` test of Frontend.cpp:1792-1795 on the M1 result)
+__global__ void __launch_bounds__(256) k_matched_mask(const int32_t* lm, const int32_t* count, int cap, uint8_t* matched)
+{
+  const int frame = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cap) return;
+  const size_t i = (size_t)frame * cap + k;
+  matched[i] = (k < min(count[frame], cap) && lm[i] >= 0) ? 1 : 0;
+}
+
+// ordered compaction of the matching entries (flags bit 0) of one (frame, view): k0 ascending, as the serial insertion
+// loop of Frontend.cpp:1915 walks them. One CTA of 256 threads per (view, frame).
+__global__ void __launch_bounds__(256) k_m3_compact(int cap0, int n_older, int cap_m, const int32_t* k1, const double* hp, const uint8_t* flags,
+                                                    int32_t* n_match, int32_t* m_k0, int32_t* m_k1, uint8_t* m_flags, double* m_hp)
+{
+  __shared__ int warp_tot[8], base;
+  const int v = blockIdx.x, frame = blockIdx.y;
+  const size_t in0 = ((size_t)frame * n_older + v) * cap0, out0 = ((size_t)frame * n_older + v) * cap_m;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < cap0; c0 += 256) {
+    const int k0 = c0 + threadIdx.x;
+    const bool m = k0 < cap0 && (flags[in0 + k0] & 1);
+    const unsigned bal = __ballot_sync(0xffffffffu, m);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int before = base;
+    for (int w = 0; w < warp; w++) before += warp_tot[w];
+    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+    if (m && pos < cap_m) {
+      m_k0[out0 + pos] = k0; m_k1[out0 + pos] = k1[in0 + k0]; m_flags[out0 + pos] = flags[in0 + k0];
+      for (int i = 0; i < 4; i++) m_hp[4 * (out0 + pos) + i] = hp[4 * (in0 + k0) + i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += warp_tot[w]; base += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_match[(size_t)frame * n_older + v] = base;
+}
+
 __global__ void __launch_bounds__(256) k_hamming_matrix(int D16, int na, const uint8_t* A, int nb, const uint8_t* B, uint16_t* out)
 {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
@@ -1316,6 +1356,84 @@ int okb_match_motion_stereo_device(okb_context_t* ctx, int cam, int n_frames, co
   return okb_match_motion_stereo_device_ptr(ctx, n_frames, ws.kp_cap, ws.d_kp, ws.d_desc, ws.d_count, &ws.model, ws.cfg.width, ws.cfg.height,
                                             T_WC1, T_CW1, n_older, older, cap0, match_threshold, (void*)ws.stream, d_matched1, d_out_k1,
                                             d_out_dist, d_out_hp_W, d_out_flags);
+}
+
+int okb_matched_mask_device(okb_context_t* ctx, int cam, int n_frames, const int32_t* d_lm, uint8_t* d_matched)
+{
+  OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams && d_lm && d_matched, "okb_matched_mask_device");
+  CamWorkspace& ws = ctx->cams[cam];
+  OKB_CHECK_ARGS(n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_matched_mask_device");
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  k_matched_mask<<<dim3((ws.kp_cap + 255) / 256, n_frames), 256, 0, ws.stream>>>(d_lm, ws.d_count, ws.kp_cap, d_matched);
+  ctx->launches++;
+  OKB_CUDA(cudaGetLastError());
+  return OKB_OK;
+}
+
+int okb_match_motion_stereo_batch(okb_context_t* ctx, int cam, int n_frames, const double* T_WC1, const double* T_CW1, int n_older,
+                                  const okb_older_view_t* older, int cap0, uint32_t match_threshold, int cap, uint8_t* matched1,
+                                  int cap_m, int32_t* n_match, int32_t* m_k0, int32_t* m_k1, uint8_t* m_flags, double* m_hp_W)
+{
+  OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams && matched1 && cap > 0 && cap_m > 0 && n_match && m_k0 && m_k1 && m_flags && m_hp_W &&
+                 n_older >= 1 && cap0 > 0, "okb_match_motion_stereo_batch");
+  CamWorkspace& ws = ctx->cams[cam];
+  OKB_CHECK_ARGS(n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_motion_stereo_batch");
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  // device side: mask [frames][kp_cap], dense results, compact lists (own scratch: the camera's m_d staging holds the M1 / M4 results)
+  const size_t nq = (size_t)n_frames * n_older * cap0, nm = (size_t)n_frames * n_older * cap_m, n1 = (size_t)n_frames * ws.kp_cap;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t need = al(n1) + al(nq * 4) * 2 + al(nq * 32) + al(nq) + al((size_t)n_frames * n_older * 4) + al(nm * 4) * 2 + al(nm) + al(nm * 32);
+  if (need > ws.m3_cap) {
+    OKB_CUDA(cudaStreamSynchronize(ws.stream));
+    cudaFree(ws.m3_d); if (ws.m3_h) cudaFreeHost(ws.m3_h);
+    ws.m3_d = ws.m3_h = nullptr; ws.m3_cap = 0;
+    OKB_CUDA(cudaMalloc(&ws.m3_d, need + need / 4));
+    OKB_CUDA(cudaMallocHost(&ws.m3_h, need + need / 4));
+    ws.m3_cap = need + need / 4;
+  }
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t r = o; o += al(bytes); return r; };
+  const size_t o_mask = take(n1), o_k1 = take(nq * 4), o_dist = take(nq * 4), o_hp = take(nq * 32), o_fl = take(nq);
+  const size_t o_n = take((size_t)n_frames * n_older * 4), o_mk0 = take(nm * 4), o_mk1 = take(nm * 4), o_mf = take(nm), o_mhp = take(nm * 32);
+  uint8_t* d = ws.m3_d; uint8_t* h = ws.m3_h;
+  cudaStream_t st = ws.stream;
+  const int rows = cap < ws.kp_cap ? cap : ws.kp_cap;
+  // mask in: the caller's [n_frames][cap] rows -> [n_frames][kp_cap]
+  OKB_CUDA(cudaMemsetAsync(d + o_mask, 0, n1, st));
+  const bool pin_mask = host_pinned(matched1);
+  if (pin_mask) OKB_CUDA(cudaMemcpy2DAsync(d + o_mask, ws.kp_cap, matched1, cap, rows, n_frames, cudaMemcpyHostToDevice, st));
+  else {
+    for (int b = 0; b < n_frames; b++) memcpy(h + o_mask + (size_t)b * ws.kp_cap, matched1 + (size_t)b * cap, rows);
+    OKB_CUDA(cudaMemcpyAsync(d + o_mask, h + o_mask, n1, cudaMemcpyHostToDevice, st));
+  }
+  int rc = okb_match_motion_stereo_device(ctx, cam, n_frames, T_WC1, T_CW1, n_older, older, cap0, match_threshold, d + o_mask,
+                                          (int32_t*)(d + o_k1), (uint32_t*)(d + o_dist), (double*)(d + o_hp), d + o_fl);
+  if (rc) return rc;
+  k_m3_compact<<<dim3(n_older, n_frames), 256, 0, st>>>(cap0, n_older, cap_m, (const int32_t*)(d + o_k1), (const double*)(d + o_hp), d + o_fl,
+                                                       (int32_t*)(d + o_n), (int32_t*)(d + o_mk0), (int32_t*)(d + o_mk1), d + o_mf, (double*)(d + o_mhp));
+  ctx->launches++;
+  OKB_CUDA(cudaGetLastError());
+  // results: counts + compact lists + mask, through the pinned mirror (or straight into page-locked caller buffers)
+  auto out = [&](size_t off, void* dst, size_t bytes) -> int {
+    if (host_pinned(dst)) { OKB_CUDA(cudaMemcpyAsync(dst, d + off, bytes, cudaMemcpyDeviceToHost, st)); return 0; }
+    OKB_CUDA(cudaMemcpyAsync(h + off, d + off, bytes, cudaMemcpyDeviceToHost, st)); return 1;
+  };
+  int s_n, s_k0, s_k1, s_f, s_hp;
+  if ((s_n = out(o_n, n_match, (size_t)n_frames * n_older * 4)) < 0 || (s_k0 = out(o_mk0, m_k0, nm * 4)) < 0 || (s_k1 = out(o_mk1, m_k1, nm * 4)) < 0 ||
+      (s_f = out(o_mf, m_flags, nm)) < 0 || (s_hp = out(o_mhp, m_hp_W, nm * 32)) < 0)
+    return OKB_ERR_CUDA;
+  if (pin_mask) OKB_CUDA(cudaMemcpy2DAsync(matched1, cap, d + o_mask, ws.kp_cap, rows, n_frames, cudaMemcpyDeviceToHost, st));
+  else OKB_CUDA(cudaMemcpyAsync(h + o_mask, d + o_mask, n1, cudaMemcpyDeviceToHost, st));
+  OKB_CUDA(wait_stream(ctx, st));
+  if (s_n) memcpy(n_match, h + o_n, (size_t)n_frames * n_older * 4);
+  if (s_k0) memcpy(m_k0, h + o_mk0, nm * 4);
+  if (s_k1) memcpy(m_k1, h + o_mk1, nm * 4);
+  if (s_f) memcpy(m_flags, h + o_mf, nm);
+  if (s_hp) memcpy(m_hp_W, h + o_mhp, nm * 32);
+  if (!pin_mask) for (int b = 0; b < n_frames; b++) memcpy(matched1 + (size_t)b * cap, h + o_mask + (size_t)b * ws.kp_cap, rows);
+  for (int i = 0; i < n_frames * n_older; i++)
+    if (n_match[i] > cap_m) { set_error("okb_match_motion_stereo_batch: %d matches of view %d exceed the list capacity %d", n_match[i], i, cap_m); return OKB_ERR_CAPACITY; }
+  return OKB_OK;
 }
 
 // ---- host-buffer batch forms: the queries are the features the last okb_detect_describe[_batch] of the camera left on the

@@ -86,9 +86,14 @@ _PROTOS = {
     "okb_hamming_matrix": (i32, [vp, i32, i32, vp, i32, vp, vp]),
     "okb_set_camera_model": (i32, [vp, i32, vp]),
     "okb_last_back_projections": (i32, [vp, i32, i32, i32, vp, vp, vp]),
+    "okb_camera_awareness_maps": (i32, [vp, i32, vp, vp]),
+    "okb_compute_overlaps": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
     "okb_back_project": (i32, [vp, i32, i32, vp, vp, vp]),
     "okb_match_stereo_device": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
     "okb_match_stereo_device_ptr": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]),
+    "okb_device_back_projections": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp)]),
+    "okb_matched_mask_device": (i32, [vp, i32, i32, vp, vp]),
+    "okb_match_motion_stereo_batch": (i32, [vp, i32, i32, vp, vp, i32, vp, i32, u32, i32, vp, i32, vp, vp, vp, vp, vp]),
     "okb_match_motion_stereo_device": (i32, [vp, i32, i32, vp, vp, i32, vp, i32, u32, vp, vp, vp, vp, vp]),
     "okb_match_motion_stereo_device_ptr": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, i32, u32, vp, vp, vp, vp, vp, vp]),
     "okb_match_map3d_device": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, f64, u32, vp, vp]),

@@ -346,3 +346,34 @@ def overlap_counts(image_rows, image_cols, xy, matched, kptrad=0.09, masks=False
                                       C.c_void_p, C.c_void_p]
     L.okvo_overlap_counts(image_rows, image_cols, len(xy), _p(xy), _p(matched), float(kptrad), C.byref(i), C.byref(u), _p(det), _p(mat))
     return (i.value, u.value, det, mat) if masks else (i.value, u.value)
+
+
+def camera_awareness_maps(model, intr, width, height):
+    """PinholeCamera::initialiseCameraAwarenessMaps (PinholeCamera.hpp:179-208): (rays H x W x 3 f32, jacobians H x W x 6 f32)."""
+    intr = _c(intr, np.float64)
+    rays = np.zeros((height, width, 3), np.float32); jac = np.zeros((height, width, 6), np.float32)
+    f = lib().okvo_camera_awareness_maps
+    f.restype = None; f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    f(int(model), _p(intr), int(width), int(height), _p(rays), _p(jac))
+    return rays, jac
+
+
+def compute_overlaps(models, intr, widths, heights, C_rel, masks=False):
+    """NCameraSystem::computeOverlaps (NCameraSystem.cpp:48-118). C_rel: n x n x 3 x 3 relative rotations
+    (T_SC[seenBy]^-1 * T_SC[cam]).C(). Returns the n x n boolean matrix (and the per-pair masks when asked)."""
+    n = len(models)
+    models = _c(models, np.int32); intr = _c(intr, np.float64); widths = _c(widths, np.int32); heights = _c(heights, np.int32)
+    C_rel = _c(np.asarray(C_rel).reshape(n, n, 9), np.float64)
+    out = np.zeros((n, n), np.uint8)
+    offs = data = None
+    if masks:
+        sizes = np.array([[int(widths[c]) * int(heights[c]) for c in range(n)] for _ in range(n)], np.int64).reshape(-1)
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        data = np.zeros(int(sizes.sum()), np.uint8)
+    f = lib().okvo_compute_overlaps
+    f.restype = None; f.argtypes = [C.c_int] + [C.c_void_p] * 8
+    f(n, _p(models), _p(intr), _p(widths), _p(heights), _p(C_rel), _p(out), _p(offs), _p(data))
+    if not masks:
+        return out.astype(bool)
+    mats = [[data[offs[s * n + c]:offs[s * n + c] + int(widths[c]) * int(heights[c])].reshape(int(heights[c]), int(widths[c])) for c in range(n)] for s in range(n)]
+    return out.astype(bool), mats
