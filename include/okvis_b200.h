@@ -108,6 +108,29 @@ int okb_device_back_projections(okb_context_t* ctx, int cam, const double** d_ra
 size_t okb_feature_block_bytes(int n_frames, int capacity);
 int okb_export_features(okb_context_t* ctx, int cam, int n_frames, void* d_block);
 
+
+/* ---- multi-GPU: the cameras of an NCameraSystem sharded over the GPUs. detect / describe / M1 / M3 are
+ *      independent per camera (the reference runs one thread per camera, ThreadedSlam.cpp:432-448); only Frontend::matchStereo
+ *      couples cameras, pairwise and only where NCameraSystem::hasOverlap (Frontend.cpp:1990-2000). The exchange is ONE NCCL
+ *      all-gather of the fixed-capacity feature blocks (okb_export_features) per batch. NCCL is loaded at run time (dlopen),
+ *      errors are OKB_ERR_NCCL.
+ *      okb_comm_init_all : one process drives all GPUs (the reference is a single process): ncclCommInitAll.
+ *      okb_comm_init_rank: one process per GPU; rank 0 makes a 128-byte id with okb_comm_unique_id and shares it out of band. */
+typedef struct okb_comm okb_comm_t;
+int okb_comm_unique_id(void* id128);
+int okb_comm_init_all(int n_devices, const int* devices, okb_comm_t** out);
+int okb_comm_init_rank(int world, int rank, const void* id128, int device, okb_comm_t** out);
+void okb_comm_destroy(okb_comm_t* comm);
+int okb_comm_world(const okb_comm_t* comm);
+int okb_comm_local_ranks(const okb_comm_t* comm);   /* n_devices of okb_comm_init_all, 1 for okb_comm_init_rank */
+/* All-gather of bytes_per_rank bytes per rank: d_send[i] (device i) -> d_recv[i] (world x bytes_per_rank, device i) for the
+ * n_local local ranks of the communicator (one call covers them all: ncclGroupStart / End). It is enqueued on the stream of
+ * camera cams[i] of context ctxs[i], i.e. right behind that camera's okb_export_features, so it overlaps the matchers of the other
+ * cameras; okb_comm_wait makes `stream` (e.g. the stereo matcher's) wait for the gathered data of local rank i. Asynchronous. */
+int okb_allgather_features(okb_comm_t* comm, int n_local, okb_context_t* const* ctxs, const int* cams, const void* const* d_send,
+                           void* const* d_recv, size_t bytes_per_rank);
+int okb_comm_wait(okb_comm_t* comm, int local_rank, void* stream);
+
 /* inspection hooks used by the parity tests: layer geometry, layer images and the dense AGAST score maps
  * (b0 = largest threshold at which the pixel is still a 9-16 corner, 0 in the 3-pixel margin) of the last call */
 int okb_num_layers(okb_context_t* ctx, int cam);

@@ -614,6 +614,33 @@ __device__ __forceinline__ M4Gate m4_gate(const MatchArgs& a, size_t fq, size_t 
   return g;
 }
 
+// the gate of the M3 worker loop for one (older keypoint, current keypoint) pair (Frontend.cpp:1849-1884)
+__device__ __forceinline__ M4Gate m3_gate(const MatchArgs& a, size_t fq, size_t fc, int q, int c)
+{
+  M4Gate g; g.pass = false; g.parallel = false; g.hp = V3{0, 0, 0};
+  if (!a.c_valid[fc + c]) return g;
+  const M3View& view = a.views[(size_t)(fc / a.c_stride) * a.view_stride + a.view_index];
+  const M3Frame& fr = a.frames[fc / a.c_stride];
+  const V3 eq = v3(a.q_e + 3 * (fq + q)), e1 = v3(a.c_e + 3 * (fc + c));
+  if (dot(eq, e1) < 0.5) return g;
+  const Tri t = triangulate_fast(v3(view.Twc + 9), eq, v3(fr.Twc + 9), e1, a.q_cos26[fq + q], a.q_cos6[fq + q]);
+  g.pass = t.valid; g.parallel = t.parallel; g.hp = t.p;
+  if (g.pass) {
+    if (dot(eq, e1) < 0.8) g.pass = false;
+    if (!g.parallel) {
+      if (depth_cr(view.Tcw, g.hp) < 0.2) g.pass = false;
+      if (depth_cr(fr.Tcw, g.hp) < 0.2) g.pass = false;
+    }
+  }
+  return g;
+}
+template <int MODE>
+__device__ __forceinline__ M4Gate pair_gate(const MatchArgs& a, size_t fq, size_t fc, int q, int c)
+{
+  if (MODE == MODE_M3) return m3_gate(a, fq, fc, q, c);
+  return m4_gate(a, fq, fc, q, c);
+}
+
 template <int D16>
 __global__ void __launch_bounds__(256) k_m4_scan(MatchArgs a, uint2* hits, int32_t* hit_cnt)
 {
@@ -622,7 +649,9 @@ __global__ void __launch_bounds__(256) k_m4_scan(MatchArgs a, uint2* hits, int32
   __shared__ uint8_t s_act[kQT];
   const int frame = blockIdx.y;
   const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
-  const int nq = min(a.q_count[frame], a.nq), nc = min(a.c_count[frame], a.nc);
+  const M3View* view = a.views ? &a.views[(size_t)frame * a.view_stride + a.view_index] : nullptr;   // M3: queries = an older view
+  const int nq = view ? min(view->n, a.nq) : min(a.q_count[frame], a.nq), nc = min(a.c_count[frame], a.nc);
+  const uint4* q_desc = view ? reinterpret_cast<const uint4*>(view->desc) : reinterpret_cast<const uint4*>(a.q_desc) + fq * D16;
   if ((int)(blockIdx.x * blockDim.x) >= nc) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid_c = c < nc && a.c_valid[fc + c];
@@ -634,7 +663,7 @@ __global__ void __launch_bounds__(256) k_m4_scan(MatchArgs a, uint2* hits, int32
     if (q0 >= nq) return;
     for (int i = threadIdx.x; i < kQT * D16; i += blockDim.x) {
       const int j = i / D16, w = i % D16;
-      sq[j][w] = q0 + j < nq ? __ldg(reinterpret_cast<const uint4*>(a.q_desc) + (fq + q0 + j) * D16 + w) : make_uint4(0, 0, 0, 0);
+      sq[j][w] = q0 + j < nq ? __ldg(q_desc + (size_t)(q0 + j) * D16 + w) : make_uint4(0, 0, 0, 0);
     }
     if (threadIdx.x < kQT) s_act[threadIdx.x] = (q0 + (int)threadIdx.x < nq && (a.q_use == nullptr || a.q_use[fq + q0 + threadIdx.x])) ? 1 : 0;
     __syncthreads();
@@ -674,6 +703,7 @@ __global__ void __launch_bounds__(256) k_m4_scan(MatchArgs a, uint2* hits, int32
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(128) k_m4_gate(MatchArgs a, const uint2* hits, unsigned long long* best)
 {
   const int frame = blockIdx.y;
@@ -684,10 +714,11 @@ __global__ void __launch_bounds__(128) k_m4_gate(MatchArgs a, const uint2* hits,
     const uint2 e = hits[(size_t)frame * a.hit_cap + i];
     const int q = (int)(e.x & 0xfffffu), c = (int)e.y;
     const uint32_t d = e.x >> 20;
-    if (m4_gate(a, fq, fc, q, c).pass) atomicMin(&best[fq + q], ((unsigned long long)d << 32) | (unsigned)c);
+    if (pair_gate<MODE>(a, fq, fc, q, c).pass) atomicMin(&best[fq + q], ((unsigned long long)d << 32) | (unsigned)c);
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(128) k_m4_finish(MatchArgs a, const unsigned long long* best)
 {
   const int frame = blockIdx.y;
@@ -699,7 +730,7 @@ __global__ void __launch_bounds__(128) k_m4_finish(MatchArgs a, const unsigned l
   double* hp = a.out_hp + 4 * (fq + q);
   if (d < a.thr) {
     const int c = (int)(uint32_t)b;
-    const M4Gate g = m4_gate(a, fq, fc, q, c);
+    const M4Gate g = pair_gate<MODE>(a, fq, fc, q, c);
     a.out_dist[fq + q] = d; a.out_idx[fq + q] = c;
     hp[0] = g.hp.x; hp[1] = g.hp.y; hp[2] = g.hp.z; hp[3] = 1.0;
     a.out_init[fq + q] = g.parallel ? 0 : 1;
@@ -1238,8 +1269,8 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
   OKB_CUDA(cudaMemsetAsync(best, 0xff, n0 * 8, st));
   OKB_CUDA(cudaMemsetAsync(hit_cnt, 0, (size_t)n_frames * 4, st));
   k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, (cap0 + 127) / 128), 256, 0, st>>>(a, hits, hit_cnt);
-  k_m4_gate<<<dim3(8, n_frames), 128, 0, st>>>(a, hits, best);
-  k_m4_finish<<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(a, best);
+  k_m4_gate<MODE_M4><<<dim3(8, n_frames), 128, 0, st>>>(a, hits, best);
+  k_m4_finish<MODE_M4><<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(a, best);
   k_match_gated<4, MODE_M4><<<dim3((cap0 + 7) / 8, n_frames), 256, 0, st>>>(a);   // only frames whose hit list overflowed
   ctx->launches += 4;
   OKB_CUDA(cudaGetLastError());
@@ -1287,7 +1318,9 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
   const size_t nq = (size_t)n_frames * n_older * cap0, n1 = (size_t)n_frames * cap1;
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t b_views = al(sizeof(M3View) * n_frames * n_older), b_frames = al(sizeof(M3Frame) * n_frames);
-  const size_t need = b_views + b_frames + al(nq * 24) + 2 * al(nq * 8) + al(nq) + al(nq) /*init*/ + al(n1 * 24) + al(n1 * 24) + 2 * al(n1) + al(n1 * 4);
+  const int hit_cap = 16 * cap0;   // hits (distance < threshold) per frame and view kept for the gate pass
+  const size_t need = b_views + b_frames + al(nq * 24) + 2 * al(nq * 8) + al(nq) + al(nq) /*init*/ + al(n1 * 24) + al(n1 * 24) + 2 * al(n1) + al(n1 * 4) +
+                      al(nq * 8) + al((size_t)n_frames * hit_cap * 8) + al((size_t)n_frames * 4);
   if (need > ctx->motion_cap) {
     OKB_CUDA(cudaDeviceSynchronize());
     if (ctx->motion_scratch) cudaFree(ctx->motion_scratch);
@@ -1303,6 +1336,8 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
   uint8_t* use0 = take(nq); uint8_t* init = take(nq);
   double* rays1 = (double*)take(n1 * 24); double* e1 = (double*)take(n1 * 24);
   uint8_t* valid1 = take(n1); uint8_t* cvalid = take(n1); int32_t* claim = (int32_t*)take(n1 * 4);
+  unsigned long long* best = (unsigned long long*)take(nq * 8); uint2* hits = (uint2*)take((size_t)n_frames * hit_cap * 8);
+  int32_t* hit_cnt = (int32_t*)take((size_t)n_frames * 4);
   // descriptors of the views and poses: pageable host staging (cudaMemcpyAsync copies it before returning)
   std::vector<M3View> hv((size_t)n_frames * n_older); std::vector<M3Frame> hf(n_frames);
   for (size_t i = 0; i < hv.size(); i++) {
@@ -1332,7 +1367,18 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
     a.c_valid = cvalid; a.c_e = e1; a.thr = match_threshold;
     a.views = d_views; a.view_stride = n_older; a.view_index = v; a.frames = d_frames;
     a.out_dist = d_out_dist + vo; a.out_idx = d_out_k1 + vo; a.out_hp = d_out_hp_W + 4 * vo; a.out_init = init + vo;
+    // the gate is a pure function of the pair: result per query = min (distance, k1) over the pairs below the threshold that
+    // pass it. Register-blocked Hamming scan -> hit list -> gate per hit -> outputs; a frame whose hit list overflows is redone
+    // by the sequential-replay kernel (which returns at once for all other frames)
+    a.hit_cnt = hit_cnt; a.hit_cap = hit_cap;
+    OKB_CUDA(cudaMemsetAsync(best, 0xff, (size_t)n_frames * p.q_stride * 8, st));
+    OKB_CUDA(cudaMemsetAsync(hit_cnt, 0, (size_t)n_frames * 4, st));
+    unsigned long long* best_v = best + vo;
+    k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, (cap0 + 127) / 128), 256, 0, st>>>(a, hits, hit_cnt);
+    k_m4_gate<MODE_M3><<<dim3(8, n_frames), 128, 0, st>>>(a, hits, best_v);
+    k_m4_finish<MODE_M3><<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(a, best_v);
     k_match_gated<4, MODE_M3><<<dim3((cap0 + 7) / 8, n_frames), 256, 0, st>>>(a);
+    ctx->launches += 3;
     OKB_CUDA(cudaMemsetAsync(claim, 0x7f, n1 * 4, st));
     M3Check c; memset(&c, 0, sizeof(c));
     c.views = d_views; c.view_stride = n_older; c.view_index = v; c.frames = d_frames; c.cap0 = cap0; c.cap1 = cap1; c.q_stride = p.q_stride;

@@ -149,6 +149,35 @@ class Frontend:
         fr.backProjections, fr.backProjectionsValid = rays, valid
         return int(valid.sum())
 
+
+    # ---- D5 / rig overlaps
+    def cameraAwarenessMaps(self, cameraIndex):
+        """PinholeCamera::initialiseCameraAwarenessMaps (PinholeCamera.hpp:179-208) for the camera model set with setCameraModel:
+        (rays H x W x 3 float32, imageJacobians H x W x 6 float32). The maps also stay on the device."""
+        w, h = self._geom[cameraIndex]
+        rays = np.zeros((h, w, 3), np.float32); jac = np.zeros((h, w, 6), np.float32)
+        check(_l.lib().okb_camera_awareness_maps(self._ctx, cameraIndex, ptr(rays), ptr(jac)))
+        return rays, jac
+
+    def computeOverlaps(self, models, intrinsics, widths, heights, C_rel, masks=False):
+        """NCameraSystem::computeOverlaps (NCameraSystem.cpp:48-118). models: 0 none / 1 radtan / 2 equidistant; intrinsics: per
+        camera fu fv cu cv k0..k3; C_rel[s][c] = (T_SC[s]^-1 * T_SC[c]).C(). Returns hasOverlap (n x n bool) [and the masks]."""
+        n = len(models)
+        ms = (CameraModel * n)()
+        for i in range(n):
+            ms[i].model = int(models[i]); ms[i].fu, ms[i].fv, ms[i].cu, ms[i].cv = (float(x) for x in intrinsics[i][:4])
+            for k in range(4):
+                ms[i].k[k] = float(intrinsics[i][4 + k]) if 4 + k < len(intrinsics[i]) else 0.0
+        W = np.ascontiguousarray(widths, np.int32); H = np.ascontiguousarray(heights, np.int32)
+        Cr = np.ascontiguousarray(np.asarray(C_rel, np.float64).reshape(n, n, 9))
+        out = np.zeros((n, n), np.uint8)
+        mats = ptrs = None
+        if masks:
+            mats = [[np.zeros((int(H[c]), int(W[c])), np.uint8) for c in range(n)] for _ in range(n)]
+            ptrs = (C.c_void_p * (n * n))(*[mats[s][c].ctypes.data for s in range(n) for c in range(n)])
+        check(_l.lib().okb_compute_overlaps(self._ctx, n, ms, ptr(W), ptr(H), ptr(Cr), ptr(out), ptrs))
+        return (out.astype(bool), mats) if masks else out.astype(bool)
+
     # ---- P1: landmark-candidate preparation (the loop of Frontend::matchToMap before the matching threads start)
     def configureFeatureStore(self, n_slots, D=64):
         """Device-resident store of the descriptors / back-projections of the multiframes in the window."""

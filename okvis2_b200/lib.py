@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, "libokvis_b200.so")
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                      ("octave", "<i4"), ("class_id", "<i4")])
 
-OKB_OK, OKB_ERR_NO_DEVICE, OKB_ERR_CUDA, OKB_ERR_ARGUMENT, OKB_ERR_CAPACITY, OKB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+OKB_OK, OKB_ERR_NO_DEVICE, OKB_ERR_CUDA, OKB_ERR_ARGUMENT, OKB_ERR_CAPACITY, OKB_ERR_UNSUPPORTED, OKB_ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
 
 
 class OkbError(RuntimeError):
@@ -69,6 +69,14 @@ _PROTOS = {
     "okb_device_features": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]),
     "okb_feature_block_bytes": (C.c_size_t, [i32, i32]),
     "okb_export_features": (i32, [vp, i32, i32, vp]),
+    "okb_comm_unique_id": (i32, [vp]),
+    "okb_comm_init_all": (i32, [i32, vp, C.POINTER(vp)]),
+    "okb_comm_init_rank": (i32, [i32, i32, vp, i32, C.POINTER(vp)]),
+    "okb_comm_destroy": (None, [vp]),
+    "okb_comm_world": (i32, [vp]),
+    "okb_comm_local_ranks": (i32, [vp]),
+    "okb_allgather_features": (i32, [vp, i32, vp, vp, vp, vp, C.c_size_t]),
+    "okb_comm_wait": (i32, [vp, i32, vp]),
     "okb_num_layers": (i32, [vp, i32]),
     "okb_layer_info": (i32, [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "okb_fetch_layer": (i32, [vp, i32, i32, i32, vp, vp]),

@@ -63,6 +63,20 @@ def test_motion_stereo_sequence_equals_oracle():
         scenes[1]["views"][2] = dict(xy=np.zeros((0, 2), np.float32), desc=np.zeros((0, 64), np.uint8), size=np.zeros(0, np.float32),
                                      use=np.zeros(0, np.uint8), T_WC=scenes[1]["views"][2]["T_WC"], T_CW=scenes[1]["views"][2]["T_CW"])
         scenes[2]["views"][0]["use"][:] = 0
+        # near-duplicate descriptors in frame 1 (every pair is below the threshold): the hit list of the Hamming scan overflows and
+        # the sequential-replay kernel redoes that frame
+        rng = np.random.default_rng(3)
+        base = rng.integers(0, 256, 64, dtype=np.uint8)
+
+        def near(n):
+            d = np.tile(base, (n, 1))
+            for i in range(n):
+                for b in rng.choice(512, 6, replace=False):
+                    d[i, b // 8] ^= 1 << (b % 8)
+            return d
+        scenes[1]["cur"]["desc"] = near(len(scenes[1]["cur"]["desc"]))
+        for v in (0, 1):
+            scenes[1]["views"][v]["desc"] = near(len(scenes[1]["views"][v]["desc"]))
         cap0, cap1, n_older = 640, 704, 5
         k1, dist, hp, fl, m1 = run_device(fe, scenes, cap0, cap1, n_older)
         inserted = 0
