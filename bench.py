@@ -801,12 +801,23 @@ def run_sharded(args, name, cfg, rank, world, local_rank, steps):
     rig = getattr(rigs, cfg["rig"])
     n_cams, W, H, B, ring = len(rig), cfg["W"], cfg["H"], cfg["batch"], cfg["ring"]
     mine = sh.cameras_of(rank, world, n_cams)
-    overlaps = sh.rig_overlaps(rig)
-    pairs = sh.pairs_of(rank, world, overlaps)
     warm = max(args.warmup, 3)
     fe = Frontend(max(len(mine), 1), W, H, device=local_rank, max_batch=B)
     fe.configure(threshold=cfg["threshold"], octaves=cfg["octaves"], max_keypoints=cfg["max_kp"])
     ctx = fe.ctx
+    # NCameraSystem::computeOverlaps on the device (exact, NCameraSystem.cpp:48-118): which pairs Frontend::matchStereo visits
+    overlaps = rig_overlaps_exact(rig, fe.computeOverlaps)
+    pairs = sh.pairs_of(rank, world, overlaps)
+    # the collective behind the C ABI: one process per GPU -> okb_comm_init_rank, the id travels through torch.distributed
+    comm = C.c_void_p()
+    ident = (C.c_uint8 * 128)()
+    if rank == 0:
+        okl.check(L_.okb_comm_unique_id(ident))
+    if world > 1:
+        obj = [bytes(ident)]
+        dist.broadcast_object_list(obj, src=0)
+        C.memmove(ident, obj[0], 128)
+    okl.check(L_.okb_comm_init_rank(world, rank, ident, local_rank, C.byref(comm)))
     models = []
     for c in range(n_cams):
         m = okl.CameraModel(); r = rig[c]
@@ -867,11 +878,17 @@ def run_sharded(args, name, cfg, rank, world, local_rank, steps):
                                                 dm["proj"].data_ptr(), dm["is3d"].data_ptr(), 20.0, 60, d_m1[li]["dist"].data_ptr(),
                                                 d_m1[li]["lm"].data_ptr()))
             okl.check(L_.okb_export_features(ctx, li, B, local[c // world].data_ptr()))
-            cur.wait_stream(cam_streams[li])
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), local.view(-1))      # the one collective of the path
-        else:
-            gathered[0].copy_(local)
+        # the one collective of the path: NCCL all-gather behind the C ABI, enqueued on the LAST local camera's stream (which first
+        # waits for the exports of the other local cameras); the stereo matchers' stream waits on its event
+        if mine:
+            last = len(mine) - 1
+            for li in range(last):
+                cam_streams[last].wait_stream(cam_streams[li])
+            okl.check(L_.okb_allgather_features(comm, 1, (C.c_void_p * 1)(ctx), (C.c_int * 1)(last), (C.c_void_p * 1)(local.data_ptr()),
+                                                (C.c_void_p * 1)(gathered.data_ptr()), local.numel()))
+            okl.check(L_.okb_comm_wait(comm, 0, cur.cuda_stream))
+            for li in range(len(mine)):
+                cur.wait_stream(cam_streams[li])      # M1 of every local camera is part of the step
         for pi, (i, j) in enumerate(pairs):
             bi = gathered.data_ptr() + (sh.slot_of(i, world)[0] * slots + sh.slot_of(i, world)[1]) * blk
             bj = gathered.data_ptr() + (sh.slot_of(j, world)[0] * slots + sh.slot_of(j, world)[1]) * blk
@@ -949,7 +966,7 @@ def run_sharded(args, name, cfg, rank, world, local_rank, steps):
         rec = {"metric": "multiframes/sec detect+describe+match (5-camera rig)", "value": B * steps / (ms * 1e-3), "unit": "multiframes/s",
                "n_gpus": world, "steps": steps, "ms_per_step": ms / steps, "scaling": "strong",
                "config": {"workload": name, "multiframes_per_step": B, "cameras": n_cams, "overlapping_pairs": [list(p) for p in overlaps],
-                          "parallelism": f"camera c on GPU c % {world}; one NCCL all-gather of {slots} x {blk} B feature blocks per rank per step",
+                          "parallelism": f"camera c on GPU c % {world}; one NCCL all-gather (okb_allgather_features, C ABI) of {slots} x {blk} B feature blocks per rank per step",
                           "l2_policy": f"inputs larger than L2: ring of {ring} batches",
                           "W": W, "H": H, "keypoints_per_frame": cfg["kpts"], "detector_max_keypoints": cfg["max_kp"], "threshold": cfg["threshold"],
                           "octaves": cfg["octaves"], "n_lm": cfg["n_lm"]},
@@ -961,8 +978,23 @@ def run_sharded(args, name, cfg, rank, world, local_rank, steps):
                "gpu_launches": int(launches), "stereo_matches_rank0_last_step": n_match}
     torch.cuda.synchronize()
     del h_img, h_blk, h_m1, h_st, cam_streams
+    L_.okb_comm_destroy(comm)
     fe.close()
     return rec
+
+
+def rig_overlaps_exact(rig, compute):
+    """the overlapping camera pairs (i < j) of a rig by NCameraSystem::computeOverlaps; `compute` = Frontend.computeOverlaps (device)
+    or oracle.compute_overlaps (CPU arm)"""
+    from okvis2_b200.frontend import Frontend
+    n = len(rig)
+    models = [Frontend.MODELS[r["distortion_type"]] for r in rig]
+    intr = [list(r["focal_length"]) + list(r["principal_point"]) + (list(r["distortion_coefficients"]) + [0.0] * 4)[:4] for r in rig]
+    Wd = [r["image_dimension"][0] for r in rig]; Hd = [r["image_dimension"][1] for r in rig]
+    Cs = [np.array(r["T_SC"]).reshape(4, 4)[:3, :3] for r in rig]
+    C_rel = np.array([[Cs[s].T @ Cs[c] for c in range(n)] for s in range(n)])
+    ov = compute(models, intr, Wd, Hd, C_rel)
+    return [(i, j) for i in range(n) for j in range(i + 1, n) if ov[i][j]]
 
 
 def cpu_sharded_baseline(cfg):
@@ -974,7 +1006,7 @@ def cpu_sharded_baseline(cfg):
     from okvis2_b200.synth import synth_frame
     rig = getattr(rigs, cfg["rig"])
     W, H = cfg["W"], cfg["H"]
-    overlaps = sh.rig_overlaps(rig)
+    overlaps = rig_overlaps_exact(rig, oracle.compute_overlaps)
     cores = os.cpu_count() or 1
     n = max(2, min(8, cores // 2))
     local = threading.local()
