@@ -288,3 +288,64 @@ static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, st
   io->nkp = nkp; io->nm = nm + n_m3; io->n_m3 = n_m3;
   return rc;
 }
+
+// ---- live use through okb_process_multiframe: one call per stereo frame (detect both cameras, M1, M3 sequence, M4), replayed
+// as a CUDA graph from the second frame on. Host buffers in and out.
+extern "C" int okb_e2e_multiframe(okb_context_t* ctx, int n_frames, int warmup, int W, int H, const uint8_t* left, const uint8_t* right, int cap,
+                                  const int* n_cand, const uint8_t* const* cand_desc, const int32_t* const* cand_lm, const int* n_lm,
+                                  const double* const* lm_proj, const uint8_t* const* lm_is3d, const okb_stream_m3* m3, double* seconds,
+                                  double* worst_ms, long long* h2d_bytes, long long* d2h_bytes, long long* total_kp, long long* total_matches)
+{
+  const int n_older = m3 ? m3->n_older : 0, cap_m = m3 ? m3->cap_m : 1;
+  std::vector<okb_keypoint_t> kp[2]; std::vector<uint8_t> desc[2], valid[2], m3f[2], init(cap);
+  std::vector<double> rays[2], m3hp[2], hp((size_t)cap * 4);
+  std::vector<uint32_t> m1d[2], sdist(cap); std::vector<int32_t> m1l[2], m3n[2], m3k0[2], m3k1[2], k1(cap);
+  okb_multiframe_cam_t io[2]; memset(io, 0, sizeof(io));
+  const uint8_t* imgs[2] = {left, right};
+  for (int c = 0; c < 2; c++) {
+    kp[c].resize(cap); desc[c].resize((size_t)cap * 64); rays[c].resize((size_t)cap * 3); valid[c].resize(cap); m1d[c].resize(cap); m1l[c].resize(cap);
+    m3n[c].resize(n_older + 1); m3k0[c].resize((size_t)(n_older + 1) * cap_m); m3k1[c].resize((size_t)(n_older + 1) * cap_m);
+    m3f[c].resize((size_t)(n_older + 1) * cap_m); m3hp[c].resize((size_t)(n_older + 1) * cap_m * 4);
+    okb_multiframe_cam_t& q = io[c];
+    q.stride_bytes = W; q.n_cand = n_cand[c]; q.n_lm = n_lm[c]; q.cand_desc = cand_desc[c]; q.cand_lm = cand_lm[c]; q.lm_is3d = lm_is3d[c]; q.lm_proj = lm_proj[c];
+    if (n_older > 0) { q.T_WC1 = m3->T_WC1[c]; q.T_CW1 = m3->T_CW1[c]; q.n_older = n_older; q.cap0 = m3->cap0; q.older = m3->older[c]; }
+    q.cap = cap; q.kp = kp[c].data(); q.desc = desc[c].data(); q.rays = rays[c].data(); q.rays_valid = valid[c].data();
+    q.m1_dist = m1d[c].data(); q.m1_lm = m1l[c].data(); q.cap_m = cap_m; q.m3_n = m3n[c].data(); q.m3_k0 = m3k0[c].data(); q.m3_k1 = m3k1[c].data();
+    q.m3_flags = m3f[c].data(); q.m3_hp_W = m3hp[c].data();
+  }
+  okb_multiframe_stereo_t st; memset(&st, 0, sizeof(st));
+  st.cam0 = 0; st.cam1 = 1; st.C_WC0[0] = st.C_WC0[4] = st.C_WC0[8] = 1.0; st.C_WC1[0] = st.C_WC1[4] = st.C_WC1[8] = 1.0; st.r_WC1[0] = 0.11;
+  st.k1 = k1.data(); st.dist = sdist.data(); st.hp_W = hp.data(); st.initialisable = init.data();
+  long long nkp = 0, nm = 0; double worst = 0;
+  auto frame = [&](int i, bool first) -> int {
+    for (int c = 0; c < 2; c++) { io[c].image = imgs[c] + (size_t)i * W * H; io[c].pool_changed = first ? 1 : 0; }
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = okb_process_multiframe(ctx, 2, io, 1, &st, 20.0, 60);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ms > worst) worst = ms;
+    if (rc) return rc;
+    for (int c = 0; c < 2; c++) {
+      nkp += io[c].n;
+      for (int k = 0; k < io[c].n; k++) nm += m1l[c][k] >= 0;
+      for (int v = 0; v < n_older; v++) for (int j = 0; j < m3n[c][v]; j++) nm += (m3f[c][(size_t)v * cap_m + j] & 4) != 0;
+    }
+    for (int k = 0; k < io[0].n; k++) nm += k1[k] >= 0;
+    return 0;
+  };
+  int rc = 0;
+  for (int i = 0; i < warmup && !rc; i++) rc = frame(i % n_frames, i == 0);
+  nkp = nm = 0; worst = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < n_frames && !rc; i++) rc = frame(i, false);
+  const auto t1 = std::chrono::steady_clock::now();
+  *seconds = std::chrono::duration<double>(t1 - t0).count(); *worst_ms = worst;
+  // bytes per frame of the copies inside okb_process_multiframe (row strides = device capacity `cap`)
+  long long h2d = 0, d2h = 0;
+  for (int c = 0; c < 2; c++) {
+    h2d += (long long)W * H + (long long)n_lm[c] * 16 + (n_older > 0 ? 192 + (long long)n_older * (long long)sizeof(okb_older_view_t) : 0);
+    d2h += 8 + (long long)cap * (28 + 64 + 25 + 8) + (n_older > 0 ? (long long)n_older * (4 + (long long)cap_m * 41) : 0);
+  }
+  d2h += (long long)cap * 41;
+  *h2d_bytes = h2d * n_frames; *d2h_bytes = d2h * n_frames; *total_kp = nkp; *total_matches = nm;
+  return rc;
+}

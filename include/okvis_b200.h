@@ -337,6 +337,43 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
                                        uint32_t match_threshold, void* stream, uint8_t* d_matched1, int32_t* d_out_k1,
                                        uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags);
 
+
+/* ---- live use: ONE call per multiframe. Replaces the per-frame sequence of ThreadedSlam::processFrame
+ *      (okvis_multisensor_processing/src/ThreadedSlam.cpp:429-463,512-533): Frontend::detectAndDescribe for every camera
+ *      (Frontend.cpp:221-269), then inside dataAssociationAndInitialization the matchers M1 (matchToMapByThread), M3
+ *      (matchMotionStereo) per camera and M4 (matchStereo) per overlapping pair. Everything is enqueued at once (one stream per
+ *      camera, the pairs behind them), the results come back in one synchronisation, and from the second call with the same
+ *      shapes on the launch sequence is replayed as a captured CUDA graph. HOST buffers in and out; the M1 landmark pool is
+ *      re-uploaded only when pool_changed is set, the M3 views are device blocks (the keyframe feature store).
+ *      One okb_multiframe_cam_t per camera of the context, in camera order. Synchronous. */
+typedef struct {
+  /* in */
+  const uint8_t* image; size_t stride_bytes;
+  int32_t n_cand, n_lm, pool_changed, reserved;           /* M1 pool; n_cand = 0: no M1. pool_changed: (re)upload cand_desc / cand_lm / lm_is3d */
+  const uint8_t* cand_desc; const int32_t* cand_lm; const uint8_t* lm_is3d;
+  const double* lm_proj;                                   /* n_lm x 2, every frame */
+  const double* T_WC1; const double* T_CW1;                /* 12 doubles each (C row-major, r): pose of the camera and its inverse */
+  int32_t n_older, cap0; const okb_older_view_t* older;    /* M3: n_older views with at most cap0 keypoints; n_older = 0: no M3 */
+  /* out */
+  int32_t cap, n;                                          /* caller capacity of the rows below; n = keypoints of this frame */
+  okb_keypoint_t* kp; uint8_t* desc;                       /* cap rows (desc: x 64) */
+  double* rays; uint8_t* rays_valid;                       /* may be NULL; back-projections (camera model set) */
+  uint32_t* m1_dist; int32_t* m1_lm;                       /* cap entries */
+  int32_t cap_m, reserved2;                                /* M3: list capacity per view */
+  int32_t* m3_n;                                           /* n_older counts */
+  int32_t* m3_k0; int32_t* m3_k1; uint8_t* m3_flags; double* m3_hp_W;   /* n_older x cap_m entries (hp x 4), ascending k0 */
+} okb_multiframe_cam_t;
+typedef struct {
+  int32_t cam0, cam1;                                      /* im0 < im1 with NCameraSystem::hasOverlap */
+  double C_WC0[9], r_WC0[3], C_WC1[9], r_WC1[3];
+  int32_t* k1; uint32_t* dist; double* hp_W; uint8_t* initialisable;   /* capacity of camera cam0's rows (cams[cam0].cap) */
+} okb_multiframe_stereo_t;
+int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t* cams, int n_pairs, okb_multiframe_stereo_t* pairs,
+                           double reprojection_threshold, uint32_t match_threshold);
+/* 0 = always submit the launches directly (default 1: CUDA-graph replay); counters of both kinds of submissions */
+int okb_stream_use_graph(okb_context_t* ctx, int on);
+int okb_stream_stats(okb_context_t* ctx, long long* graph_launches, long long* direct_calls);
+
 /* ---- P1: landmark-candidate preparation. Replaces the serial host loop of Frontend::matchToMap that
  *      builds landmarksToMatch / descriptorPool for one camera (okvis_frontend/src/Frontend.cpp:1196-1360; pose lookups
  *      ViGraph.cpp:632-645): projection of every landmark into the current view (PinholeCamera::projectHomogeneous,

@@ -99,10 +99,12 @@ void okb_destroy(okb_context_t* ctx)
   cudaDeviceSynchronize();
   for (int i = 0; i < ctx->n_cams; i++) detect_free_camera(ctx, i);
   match_free(ctx);
+  stream_free(ctx);
   prepare_free(ctx);
   aux_free(ctx);
   if (ctx->stereo_scratch) cudaFree(ctx->stereo_scratch);
-  if (ctx->motion_scratch) cudaFree(ctx->motion_scratch);
+  if (ctx->motion.d) cudaFree(ctx->motion.d);
+  if (ctx->motion.h) cudaFreeHost(ctx->motion.h);
   tables_free(ctx);
   delete ctx;
 }

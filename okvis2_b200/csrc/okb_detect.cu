@@ -86,13 +86,14 @@ __device__ __forceinline__ void emit_touches_warp(const DeviceLayers& dl, uint32
 __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ DeviceLayers dl, const uint8_t* in0, int in_pitch, size_t in_frame_stride,
                                                 uint8_t* img_block, uint8_t* score_block, uint32_t* touch_block,
                                                 const uint32_t* cand, const int32_t* cand_count, int cand_cap,
-                                                const __grid_constant__ CandRegions cr, CandRecord* rec, int threshold, uint32_t epoch,
+                                                const __grid_constant__ CandRegions cr, CandRecord* rec, int threshold, const uint32_t* d_epoch,
                                                 const uint32_t* tie_cells)
 {
   const int frame = blockIdx.y;
   int prefix[kMaxLayers + 1];
   const int n = cand_total(cr, cand_count + frame * kMaxLayers, dl.n, prefix);
   if (blockIdx.x * blockDim.x >= n) return;
+  const uint32_t epoch = *d_epoch;
   __shared__ FrameViews v;  // dynamically indexed by layer: keep it out of local memory
   if (threadIdx.x == 0) make_views(dl, in0, in_pitch, in_frame_stride, img_block, score_block, touch_block, frame, v);
   __syncthreads();
@@ -197,8 +198,9 @@ struct TieInfo {  // what a tie's cache touches look like if it turns out to be 
 // footprint of the winners among them into its 25-bit "touched" mask and evaluates the reference's isMax2D.
 __global__ void __launch_bounds__(512) k_resolve(const __grid_constant__ DeviceLayers dl, const uint8_t* score_block, const uint32_t* touch_block,
                                                  const int32_t* cand_count, int cand_cap, const __grid_constant__ CandRegions cr,
-                                                 CandRecord* rec, uint32_t epoch, int threshold, int32_t* status, long long* dbg)
+                                                 CandRecord* rec, const uint32_t* d_epoch, int threshold, int32_t* status, long long* dbg)
 {
+  const uint32_t epoch = *d_epoch;
 #define OKB_STAMP(i) if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + (i)] = clock64()
   OKB_STAMP(0);
   extern __shared__ unsigned long long resolve_smem[];
@@ -833,6 +835,8 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMalloc(&ws.d_rays, (size_t)ws.kp_cap * 24 * B));
   OKB_CUDA(cudaMalloc(&ws.d_rays_valid, (size_t)ws.kp_cap * B));
   OKB_CUDA(cudaEventCreateWithFlags(&ws.ev_done, cudaEventDisableTiming));
+  OKB_CUDA(cudaMalloc(&ws.d_epoch, 8));
+  OKB_CUDA(cudaMemset(ws.d_epoch, 0, 8));
   OKB_CUDA(cudaMalloc(&ws.d_dbg, (size_t)16 * 8 * B));
   OKB_CUDA(cudaMemset(ws.d_dbg, 0, (size_t)16 * 8 * B));
   OKB_CUDA(cudaMemset(ws.d_count, 0, 4 * B));
@@ -857,10 +861,10 @@ void detect_free_camera(okb_context* ctx, int cam)
     LayerGeom& g = ws.geom[i];
     cudaFree(g.d_xs); cudaFree(g.d_xn); cudaFree(g.d_xa); cudaFree(g.d_ys); cudaFree(g.d_yn); cudaFree(g.d_ya);
   }
-  cudaFree(ws.d_tiles); cudaFree(ws.d_ray_map); cudaFree(ws.d_jac_map);
+  cudaFree(ws.d_epoch); cudaFree(ws.d_tiles); cudaFree(ws.d_ray_map); cudaFree(ws.d_jac_map);
   cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
   cudaFree(ws.d_cand_count); cudaFree(ws.d_rec); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
-  cudaFree(ws.d_count); cudaFree(ws.d_m1_rows); cudaFree(ws.m_d); if (ws.m_h) cudaFreeHost(ws.m_h); cudaFree(ws.m3_d); if (ws.m3_h) cudaFreeHost(ws.m3_h); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);
+  cudaFree(ws.d_count); cudaFree(ws.d_m1_rows); cudaFree(ws.m_d); if (ws.m_h) cudaFreeHost(ws.m_h); cudaFree(ws.m3_d); if (ws.m3_h) cudaFreeHost(ws.m3_h); cudaFree(ws.motion.d); if (ws.motion.h) cudaFreeHost(ws.motion.h); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);
   if (ws.ev_done) cudaEventDestroy(ws.ev_done);
   cudaFreeHost(ws.h_img); cudaFreeHost(ws.h_kp); cudaFreeHost(ws.h_desc); cudaFreeHost(ws.h_count); cudaFreeHost(ws.h_status); cudaFreeHost(ws.h_rays); cudaFreeHost(ws.h_rays_valid);
   for (int i = 0; i < 4; i++) if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
@@ -885,6 +889,21 @@ static void collect_timing(okb_context* ctx, CamWorkspace& ws)
   (void)ctx;
 }
 
+// epoch[0] = current epoch (1..126), epoch[1] = 1 when this call wrapped it (the touch maps must be cleared)
+__global__ void k_epoch_tick(uint32_t* epoch)
+{
+  if (threadIdx.x == 0) {
+    const uint32_t e = epoch[0] + 1;
+    const bool wrap = e >= 127;
+    epoch[0] = wrap ? 1u : e; epoch[1] = wrap ? 1u : 0u;
+  }
+}
+__global__ void __launch_bounds__(256) k_touch_clear(const uint32_t* epoch, uint32_t* touch, size_t n)
+{
+  if (!epoch[1]) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) touch[i] = 0u;
+}
+
 // all frames are device resident: d_images = n_frames x H x src_pitch
 int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch)
 {
@@ -892,12 +911,13 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   const okb_camera_config_t& c = ws.cfg;
   const int W = c.width, H = c.height, B = n_frames;
   cudaStream_t st = ws.stream;
-  if (ctx->timers_on) { collect_timing(ctx, ws); cudaEventRecord(ws.ev[0], st); }
-  ws.epoch++;
-  if (ws.epoch >= 127) {  // epoch field is 7 bits: recycle
-    OKB_CUDA(cudaMemsetAsync(ws.d_touch, 0, (size_t)ws.dl.frame_stride * c.max_batch * 4, st));
-    ws.epoch = 1;
-  }
+  if (ctx->timers_on) collect_timing(ctx, ws);
+  // the touch-map epoch lives on the device (a captured CUDA graph replays the same launches: nothing per call may be a kernel
+  // argument): one thread advances it, the map is cleared when the 7-bit field wraps
+  k_epoch_tick<<<1, 32, 0, st>>>(ws.d_epoch);
+  k_touch_clear<<<296, 256, 0, st>>>(ws.d_epoch, ws.d_touch, (size_t)ws.dl.frame_stride * c.max_batch);
+  ctx->launches += 2;
+  if (ctx->timers_on) cudaEventRecord(ws.ev[0], st);
   const size_t in_stride = (size_t)src_pitch * H;
   const int ipitch = W + 1;
   // ---- pyramid + dense scores + non-max candidates (okb_score.cu)
@@ -915,8 +935,8 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   // ---- candidates, refinement, tie resolution, selection
   k_refine<<<dim3((ws.cand_cap + 127) / 128, B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
                                                                ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap, cr,
-                                                               ws.d_rec, c.threshold, ws.epoch, ws.d_tie_cells);
-  k_resolve<<<B, 512, kResolveSmem, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_cand_count, ws.cand_cap, cr, ws.d_rec, ws.epoch, c.threshold,
+                                                               ws.d_rec, c.threshold, ws.d_epoch, ws.d_tie_cells);
+  k_resolve<<<B, 512, kResolveSmem, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_cand_count, ws.cand_cap, cr, ws.d_rec, ws.d_epoch, c.threshold,
                                           ws.d_status, ws.d_dbg);
   k_finalize<<<B, 1024, kFinalizeSmem, st>>>(ws.dl, ws.d_cand_count, ws.cand_cap, cr, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,
                                             W, H, c.max_keypoints, ws.kp_cap, ws.d_kp, ws.d_kscale, ws.d_count, ws.d_status, ws.d_dbg);

@@ -58,6 +58,9 @@ struct CandRecord {
   int8_t pad[3];
 };
 
+// device scratch + page-locked table mirror of one M3 sequence (okb_match_motion_stereo_device*)
+struct MotionScratch { void* d = nullptr; size_t cap = 0; void* h = nullptr; size_t h_cap = 0; int pinned_staging = 0; };
+
 struct CamWorkspace {
   okb_camera_config_t cfg;
   cudaStream_t stream = nullptr;
@@ -69,7 +72,7 @@ struct CamWorkspace {
   int cand_cap = 0;   // candidate capacity per frame (sum of the per-layer regions)
   int cand_off[kMaxLayers + 1] = {0};
   int kp_cap = 0;     // keypoint capacity per frame (output rows)
-  uint32_t epoch = 0;
+  uint32_t* d_epoch = nullptr;   // [0] touch-map epoch (1..126), [1] wrap flag of the current call; advanced on the device
   // device buffers ([max_batch] leading dimension)
   uint8_t* d_in = nullptr;      // input frames (pitch = width) of the host-buffer entry points
   uint8_t* d_img = nullptr;     // layer images (layers >= 1)
@@ -101,6 +104,7 @@ struct CamWorkspace {
   // staging of the host-buffer batch matchers (okb_match_map3d_batch / okb_match_stereo_batch), grown on demand
   uint8_t* m_d = nullptr; uint8_t* m_h = nullptr; size_t m_cap = 0;
   uint8_t* m3_d = nullptr; uint8_t* m3_h = nullptr; size_t m3_cap = 0;   // staging of okb_match_motion_stereo_batch
+  MotionScratch motion;
   // pinned staging
   uint8_t* h_img = nullptr;
   okb_keypoint_t* h_kp = nullptr;
@@ -146,12 +150,13 @@ struct okb_context {
   float pattern_scale = 1.0f;
   int timers_on = 0;
   void* stereo_scratch = nullptr; size_t stereo_cap = 0;   // device scratch of okb_match_stereo_device*
-  void* motion_scratch = nullptr; size_t motion_cap = 0;   // device scratch of okb_match_motion_stereo_device*
+  okb::MotionScratch motion;   // scratch of okb_match_motion_stereo_device_ptr (one per context)
   int64_t launches = 0;
   int gate_cos_exact = 0;    // okb_create's self-check: gate_cos == this machine's libm cos on 65 536 arguments
   int blocking_sync = 0;     // 1: host-buffer entry points wait on a cudaEventBlockingSync event (the thread sleeps) instead of spinning
   void* prepare = nullptr;   // okb::PrepareState (okb_prepare.cu): keyframe feature store + P1 workspace
   void* aux = nullptr;       // okb::AuxState (okb_aux.cu): keyframe-overlap / BoW workspaces
+  void* stream_state = nullptr;   // okb::StreamState (okb_stream.cu): arenas + CUDA graph of okb_process_multiframe
 };
 
 namespace okb {
@@ -191,7 +196,15 @@ inline cudaError_t wait_stream(okb_context* ctx, cudaStream_t st)
   if (e != cudaSuccess) return e;
   return cudaEventSynchronize(ev);
 }
+// M3 sequence over the older keyframes with an explicit scratch area (okb_match.cu); the compaction of its matching entries
+int motion_sequence(okb_context* ctx, MotionScratch& ms, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
+                    const int32_t* d_count1, const okb_camera_model_t* model, int width, int height, const double* T_WC1, const double* T_CW1,
+                    int n_older, const okb_older_view_t* older, int cap0, uint32_t match_threshold, cudaStream_t st, uint8_t* d_matched1,
+                    int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags);
+void m3_compact_launch(int n_frames, int cap0, int n_older, int cap_m, const int32_t* k1, const double* hp, const uint8_t* flags, int32_t* n_match,
+                       int32_t* m_k0, int32_t* m_k1, uint8_t* m_flags, double* m_hp, cudaStream_t st);
 void prepare_free(okb_context* ctx);
+void stream_free(okb_context* ctx);
 void aux_free(okb_context* ctx);
 int tables_init(okb_context* ctx, float pattern_scale);
 void tables_free(okb_context* ctx);

@@ -880,6 +880,12 @@ __global__ void __launch_bounds__(256) k_m3_compact(int cap0, int n_older, int c
   if (threadIdx.x == 0) n_match[(size_t)frame * n_older + v] = base;
 }
 
+void m3_compact_launch(int n_frames, int cap0, int n_older, int cap_m, const int32_t* k1, const double* hp, const uint8_t* flags, int32_t* n_match,
+                       int32_t* m_k0, int32_t* m_k1, uint8_t* m_flags, double* m_hp, cudaStream_t st)
+{
+  k_m3_compact<<<dim3(n_older, n_frames), 256, 0, st>>>(cap0, n_older, cap_m, k1, hp, flags, n_match, m_k0, m_k1, m_flags, m_hp);
+}
+
 __global__ void __launch_bounds__(256) k_hamming_matrix(int D16, int na, const uint8_t* A, int nb, const uint8_t* B, uint16_t* out)
 {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
@@ -1306,6 +1312,19 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
                                        uint32_t match_threshold, void* stream, uint8_t* d_matched1, int32_t* d_out_k1,
                                        uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags)
 {
+  OKB_CHECK_ARGS(ctx, "okb_match_motion_stereo_device_ptr");
+  // one scratch area per context for this form: calls of one context must be issued on streams that serialise them
+  return okb::motion_sequence(ctx, ctx->motion, n_frames, cap1, d_kp1, d_desc1, d_count1, model, width, height, T_WC1, T_CW1, n_older, older, cap0,
+                              match_threshold, stream ? (cudaStream_t)stream : MW.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags);
+}
+
+}  // extern "C"
+
+int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
+                         const int32_t* d_count1, const okb_camera_model_t* model, int width, int height, const double* T_WC1, const double* T_CW1,
+                         int n_older, const okb_older_view_t* older, int cap0, uint32_t match_threshold, cudaStream_t st, uint8_t* d_matched1,
+                         int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags)
+{
   OKB_CHECK_ARGS(ctx && n_frames >= 1 && cap1 > 0 && cap1 < (1 << 20) && d_kp1 && d_desc1 && d_count1 && model && T_WC1 && T_CW1 &&
                  n_older >= 0 && (n_older == 0 || older) && cap0 > 0 && cap0 < (1 << 20) && d_matched1 && d_out_k1 && d_out_dist &&
                  d_out_hp_W && d_out_flags && width > 0 && height > 0, "okb_match_motion_stereo_device_ptr");
@@ -1314,21 +1333,27 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
                    "okb_match_motion_stereo_device_ptr (older view)");
   if (n_older == 0) return OKB_OK;
   OKB_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : MW.stream;
   const size_t nq = (size_t)n_frames * n_older * cap0, n1 = (size_t)n_frames * cap1;
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t b_views = al(sizeof(M3View) * n_frames * n_older), b_frames = al(sizeof(M3Frame) * n_frames);
   const int hit_cap = 16 * cap0;   // hits (distance < threshold) per frame and view kept for the gate pass
   const size_t need = b_views + b_frames + al(nq * 24) + 2 * al(nq * 8) + al(nq) + al(nq) /*init*/ + al(n1 * 24) + al(n1 * 24) + 2 * al(n1) + al(n1 * 4) +
                       al(nq * 8) + al((size_t)n_frames * hit_cap * 8) + al((size_t)n_frames * 4);
-  if (need > ctx->motion_cap) {
+  if (need > ms.cap) {
     OKB_CUDA(cudaDeviceSynchronize());
-    if (ctx->motion_scratch) cudaFree(ctx->motion_scratch);
-    ctx->motion_scratch = nullptr; ctx->motion_cap = 0;
-    OKB_CUDA(cudaMalloc(&ctx->motion_scratch, need + need / 4));
-    ctx->motion_cap = need + need / 4;
+    if (ms.d) cudaFree(ms.d);
+    if (ms.h) cudaFreeHost(ms.h);
+    ms.d = nullptr; ms.h = nullptr; ms.cap = 0;
+    OKB_CUDA(cudaMalloc(&ms.d, need + need / 4));
+    OKB_CUDA(cudaMallocHost(&ms.h, b_views + b_frames));
+    ms.cap = need + need / 4; ms.h_cap = b_views + b_frames;
   }
-  uint8_t* base = (uint8_t*)ctx->motion_scratch; size_t o = 0;
+  if (b_views + b_frames > ms.h_cap) {
+    OKB_CUDA(cudaDeviceSynchronize());
+    if (ms.h) cudaFreeHost(ms.h);
+    OKB_CUDA(cudaMallocHost(&ms.h, b_views + b_frames)); ms.h_cap = b_views + b_frames;
+  }
+  uint8_t* base = (uint8_t*)ms.d; size_t o = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base + o; o += al(bytes); return p; };
   M3View* d_views = (M3View*)take(sizeof(M3View) * n_frames * n_older);
   M3Frame* d_frames = (M3Frame*)take(sizeof(M3Frame) * n_frames);
@@ -1338,16 +1363,20 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
   uint8_t* valid1 = take(n1); uint8_t* cvalid = take(n1); int32_t* claim = (int32_t*)take(n1 * 4);
   unsigned long long* best = (unsigned long long*)take(nq * 8); uint2* hits = (uint2*)take((size_t)n_frames * hit_cap * 8);
   int32_t* hit_cnt = (int32_t*)take((size_t)n_frames * 4);
-  // descriptors of the views and poses: pageable host staging (cudaMemcpyAsync copies it before returning)
-  std::vector<M3View> hv((size_t)n_frames * n_older); std::vector<M3Frame> hf(n_frames);
-  for (size_t i = 0; i < hv.size(); i++) {
+  // descriptors of the views and poses. Asynchronous callers: pageable host staging (cudaMemcpyAsync copies it before it
+  // returns, so back-to-back calls cannot overwrite each other's tables). Streaming / CUDA-graph callers (ms.pinned_staging: one
+  // call in flight, synchronised per multiframe): the scratch's page-locked mirror, which a captured copy node re-reads at replay
+  std::vector<M3View> hv_((size_t)(ms.pinned_staging ? 0 : n_frames * n_older)); std::vector<M3Frame> hf_(ms.pinned_staging ? 0 : n_frames);
+  M3View* hv = ms.pinned_staging ? (M3View*)ms.h : hv_.data();
+  M3Frame* hf = ms.pinned_staging ? (M3Frame*)((uint8_t*)ms.h + b_views) : hf_.data();
+  for (size_t i = 0; i < (size_t)n_frames * n_older; i++) {
     const okb_older_view_t& s = older[i];
     hv[i].desc = s.d_desc; hv[i].rays = s.d_rays; hv[i].valid = s.d_valid; hv[i].size = s.d_size; hv[i].use = s.d_use; hv[i].n = s.n; hv[i].pad = 0;
     memcpy(hv[i].Twc, s.T_WC, sizeof(hv[i].Twc)); memcpy(hv[i].Tcw, s.T_CW, sizeof(hv[i].Tcw));
   }
   for (int b = 0; b < n_frames; b++) { memcpy(hf[b].Twc, T_WC1 + 12 * (size_t)b, 96); memcpy(hf[b].Tcw, T_CW1 + 12 * (size_t)b, 96); }
-  OKB_CUDA(cudaMemcpyAsync(d_views, hv.data(), sizeof(M3View) * hv.size(), cudaMemcpyHostToDevice, st));
-  OKB_CUDA(cudaMemcpyAsync(d_frames, hf.data(), sizeof(M3Frame) * hf.size(), cudaMemcpyHostToDevice, st));
+  OKB_CUDA(cudaMemcpyAsync(d_views, hv, sizeof(M3View) * (size_t)n_frames * n_older, cudaMemcpyHostToDevice, st));
+  OKB_CUDA(cudaMemcpyAsync(d_frames, hf, sizeof(M3Frame) * (size_t)n_frames, cudaMemcpyHostToDevice, st));
   const Model cam = to_model(*model);
   // D4 of the current keypoints (Frame::computeBackProjections)
   k_backproject_ext(cam, d_kp1, d_count1, cap1, n_frames, rays1, valid1, st);
@@ -1392,6 +1421,8 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
   return OKB_OK;
 }
 
+extern "C" {
+
 int okb_match_motion_stereo_device(okb_context_t* ctx, int cam, int n_frames, const double* T_WC1, const double* T_CW1, int n_older,
                                    const okb_older_view_t* older, int cap0, uint32_t match_threshold, uint8_t* d_matched1,
                                    int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags)
@@ -1399,9 +1430,9 @@ int okb_match_motion_stereo_device(okb_context_t* ctx, int cam, int n_frames, co
   OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams, "okb_match_motion_stereo_device");
   CamWorkspace& ws = ctx->cams[cam];
   OKB_CHECK_ARGS(ws.has_model && n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_motion_stereo_device (camera model set? okb_set_camera_model)");
-  return okb_match_motion_stereo_device_ptr(ctx, n_frames, ws.kp_cap, ws.d_kp, ws.d_desc, ws.d_count, &ws.model, ws.cfg.width, ws.cfg.height,
-                                            T_WC1, T_CW1, n_older, older, cap0, match_threshold, (void*)ws.stream, d_matched1, d_out_k1,
-                                            d_out_dist, d_out_hp_W, d_out_flags);
+  // per-camera scratch: the sequences of different cameras run concurrently on their own streams
+  return okb::motion_sequence(ctx, ws.motion, n_frames, ws.kp_cap, ws.d_kp, ws.d_desc, ws.d_count, &ws.model, ws.cfg.width, ws.cfg.height, T_WC1, T_CW1,
+                              n_older, older, cap0, match_threshold, ws.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags);
 }
 
 int okb_matched_mask_device(okb_context_t* ctx, int cam, int n_frames, const int32_t* d_lm, uint8_t* d_matched)

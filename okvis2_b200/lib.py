@@ -99,6 +99,9 @@ _PROTOS = {
     "okb_back_project": (i32, [vp, i32, i32, vp, vp, vp]),
     "okb_match_stereo_device": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, u32, vp, vp, vp, vp]),
     "okb_match_stereo_device_ptr": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]),
+    "okb_process_multiframe": (i32, [vp, i32, vp, i32, vp, f64, u32]),
+    "okb_stream_use_graph": (i32, [vp, i32]),
+    "okb_stream_stats": (i32, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "okb_device_back_projections": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp)]),
     "okb_matched_mask_device": (i32, [vp, i32, i32, vp, vp]),
     "okb_match_motion_stereo_batch": (i32, [vp, i32, i32, vp, vp, i32, vp, i32, u32, i32, vp, i32, vp, vp, vp, vp, vp]),
@@ -122,6 +125,22 @@ class OlderView(C.Structure):
     """okb_older_view_t: one older keyframe view of the M3 sequence (device pointers)"""
     _fields_ = [("d_desc", C.c_void_p), ("d_rays", C.c_void_p), ("d_valid", C.c_void_p), ("d_size", C.c_void_p), ("d_use", C.c_void_p),
                 ("n", C.c_int32), ("reserved", C.c_int32), ("T_WC", C.c_double * 12), ("T_CW", C.c_double * 12)]
+
+
+class MultiframeCam(C.Structure):
+    """okb_multiframe_cam_t"""
+    _fields_ = [("image", C.c_void_p), ("stride_bytes", C.c_size_t), ("n_cand", C.c_int32), ("n_lm", C.c_int32), ("pool_changed", C.c_int32),
+                ("reserved", C.c_int32), ("cand_desc", C.c_void_p), ("cand_lm", C.c_void_p), ("lm_is3d", C.c_void_p), ("lm_proj", C.c_void_p),
+                ("T_WC1", C.c_void_p), ("T_CW1", C.c_void_p), ("n_older", C.c_int32), ("cap0", C.c_int32), ("older", C.c_void_p),
+                ("cap", C.c_int32), ("n", C.c_int32), ("kp", C.c_void_p), ("desc", C.c_void_p), ("rays", C.c_void_p), ("rays_valid", C.c_void_p),
+                ("m1_dist", C.c_void_p), ("m1_lm", C.c_void_p), ("cap_m", C.c_int32), ("reserved2", C.c_int32), ("m3_n", C.c_void_p),
+                ("m3_k0", C.c_void_p), ("m3_k1", C.c_void_p), ("m3_flags", C.c_void_p), ("m3_hp_W", C.c_void_p)]
+
+
+class MultiframeStereo(C.Structure):
+    """okb_multiframe_stereo_t"""
+    _fields_ = [("cam0", C.c_int32), ("cam1", C.c_int32), ("C_WC0", C.c_double * 9), ("r_WC0", C.c_double * 3), ("C_WC1", C.c_double * 9),
+                ("r_WC1", C.c_double * 3), ("k1", C.c_void_p), ("dist", C.c_void_p), ("hp_W", C.c_void_p), ("initialisable", C.c_void_p)]
 
 
 class OverlapView(C.Structure):
