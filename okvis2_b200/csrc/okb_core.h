@@ -633,18 +633,25 @@ OKB_HD void above_query_pos(const ScanIter& it, int q, int& X, int& Y, bool& blo
 // m[5][5] = effective scores around the candidate (m[2][2] = centre). Returns true if it is a maximum.
 OKB_HD bool is_max_2d_5x5(const int m[5][5])
 {
+  // fixed trip counts, no early return: the window stays in registers on the device
   const int center = m[2][2];
-  for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) if (center < m[2 + dy][2 + dx]) return false;
+  bool ok = true;
+OKB_UNROLL
+  for (int dy = -1; dy <= 1; dy++)
+OKB_UNROLL
+    for (int dx = -1; dx <= 1; dx++) if (center < m[2 + dy][2 + dx]) ok = false;
   const int smoothedcenter = 4 * center + 2 * (m[2][1] + m[2][3] + m[1][2] + m[3][2]) + m[1][1] + m[1][3] + m[3][1] + m[3][3];
-  for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
-    if (dx == 0 && dy == 0) continue;
-    if (m[2 + dy][2 + dx] != center) continue;
-    const int cy = 2 + dy, cx = 2 + dx;
-    const int other = m[cy - 1][cx - 1] + 2 * m[cy - 1][cx] + m[cy - 1][cx + 1] + 2 * m[cy][cx - 1] + 4 * m[cy][cx] +
-                      2 * m[cy][cx + 1] + m[cy + 1][cx - 1] + 2 * m[cy + 1][cx] + m[cy + 1][cx + 1];
-    if (other > smoothedcenter) return false;
-  }
-  return true;
+OKB_UNROLL
+  for (int dy = -1; dy <= 1; dy++)
+OKB_UNROLL
+    for (int dx = -1; dx <= 1; dx++) {
+      if (dx == 0 && dy == 0) continue;
+      const int cy = 2 + dy, cx = 2 + dx;
+      const int other = m[cy - 1][cx - 1] + 2 * m[cy - 1][cx] + m[cy - 1][cx + 1] + 2 * m[cy][cx - 1] + 4 * m[cy][cx] +
+                        2 * m[cy][cx + 1] + m[cy + 1][cx - 1] + 2 * m[cy + 1][cx] + m[cy + 1][cx + 1];
+      if (m[cy][cx] == center && other > smoothedcenter) ok = false;
+    }
+  return ok;
 }
 
 // ---- descriptor ---------------------------------------------------------------------------------------------

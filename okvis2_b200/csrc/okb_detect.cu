@@ -83,11 +83,13 @@ __device__ __forceinline__ void emit_touches_warp(const DeviceLayers& dl, uint32
   }
 }
 
+constexpr int kMaxTies = 4096;   // per frame (k_resolve keeps them in shared memory)
+
 __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ DeviceLayers dl, const uint8_t* in0, int in_pitch, size_t in_frame_stride,
                                                 uint8_t* img_block, uint8_t* score_block, uint32_t* touch_block,
                                                 const uint32_t* cand, const int32_t* cand_count, int cand_cap,
-                                                const __grid_constant__ CandRegions cr, CandRecord* rec, int threshold, const uint32_t* d_epoch,
-                                                const uint32_t* tie_cells)
+                                                const __grid_constant__ CandRegions cr, uint32_t* fkey, float4* fval, int threshold, const uint32_t* d_epoch,
+                                                const uint32_t* tie_cells, TieEntry* tie_list, int32_t* tie_count)
 {
   const int frame = blockIdx.y;
   int prefix[kMaxLayers + 1];
@@ -128,11 +130,20 @@ __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ DeviceLa
       if (!alive) tie = 0;
     }
     if (alive) refine_candidate(v.L, v.n, (int)(key >> 22), (int)(key & 2047), (int)((key >> 11) & 2047), threshold, r);
-    CandRecord out;
-    out.x = r.x; out.y = r.y; out.size = r.size; out.response = r.response; out.key = key;
-    out.keep = r.keep; out.own_touch = r.own_touch; out.has_above = r.has_above; out.tie = (int8_t)tie;
-    out.above = r.above; out.state = tie ? 0 : 1; out.pad[0] = out.pad[1] = out.pad[2] = 0;
-    rec[(size_t)frame * cand_cap + i] = out;
+    // what the selection kernel reads, field by field: key | keep << 30 | decided-maximum << 31 (ties: set by k_resolve), values
+    fkey[(size_t)frame * cand_cap + i] = key | ((uint32_t)(r.keep != 0) << 30) | ((uint32_t)(tie == 0) << 31);
+    fval[(size_t)frame * cand_cap + i] = make_float4(r.x, r.y, r.size, r.response);
+    if (tie) {
+      // the tie resolution works on a compact list of its own (order irrelevant: it sorts by time key)
+      const int p = atomicAdd(&tie_count[frame], 1);
+      if (p < kMaxTies) {
+        TieEntry e;
+        e.key = key; e.rec = (uint32_t)i;
+        e.info.own_touch = r.own_touch; e.info.has_above = r.has_above; e.info.exited = (int8_t)r.above.exited;
+        e.info.n_queries = (int8_t)r.above.n_queries; e.info.max_x = r.above.max_x; e.info.max_y = r.above.max_y;
+        tie_list[(size_t)frame * kMaxTies + p] = e;
+      }
+    }
   }
   // cache-touch events of the non-tied maxima, one maximum at a time by the whole warp
   uint32_t* touch_frame = touch_block + (size_t)frame * dl.frame_stride;
@@ -164,235 +175,317 @@ __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ DeviceLa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// block-wide bitonic sort of n (power of two) 64-bit keys in shared memory, ascending
-__device__ void bitonic_sort_u64(unsigned long long* a, int n)
+constexpr int kMaxBlockers = 12;
+constexpr int kResolveThreads = 1024;
+constexpr int kResolveSmem = 232448 - 2048;   // all of an SM's shared memory: per-tie state (50 B) + score windows (28 B) while they fit
+constexpr int kResolvePerTie = 4 + 2 * kMaxBlockers + 8 + 4 + 4 + 4 + 2;
+static_assert(kMaxTies * kResolvePerTie <= kResolveSmem, "k_resolve shared memory");
+
+// 5x5 dense scores around a tie, one byte each, packed into 7 words
+struct TieWindow { uint32_t w[7]; };
+// the reference's isMax2D on the map the sequential algorithm would see: a pixel below the threshold reads 0 unless an
+// earlier maximum's cache touch (bit j of `mask`) had filled it in
+__device__ __forceinline__ bool tie_is_max(const TieWindow& t, uint32_t mask, int threshold)
 {
-  for (int k = 2; k <= n; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long x = a[i], y = a[ixj];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
-        }
-      }
-      __syncthreads();
-    }
+  int m[5][5];
+#pragma unroll
+  for (int j = 0; j < 25; j++) {
+    int val = (int)((t.w[j >> 2] >> (8 * (j & 3))) & 255u);
+    if (val < threshold && !((mask >> j) & 1u)) val = 0;
+    m[j / 5][j % 5] = val;
+  }
+  return is_max_2d_5x5(m);
 }
 
-constexpr int kMaxTies = 4096;
-constexpr int kMaxBlockers = 12;
-constexpr int kResolveSmem = kMaxTies * (8 + 2 * kMaxBlockers + 2 + 8 + 4);
+// 5x5 pixel masks: bit 5 r + c is pixel (origin.x + c, origin.y + r). A mask with origin o re-based to origin n
+// (d = o - n per axis); bits that leave the 5x5 frame are dropped.
+__device__ __forceinline__ uint32_t rebase5x5(uint32_t m, int dx, int dy)
+{
+  if (dx <= -5 || dx >= 5 || dy <= -5 || dy >= 5) return 0u;
+  uint32_t out = 0;
+#pragma unroll
+  for (int r = 0; r < 5; r++) {
+    const int sr = r - dy;
+    uint32_t row = (sr >= 0 && sr < 5) ? ((m >> (5 * sr)) & 31u) : 0u;
+    row = dx >= 0 ? (row << dx) : (row >> (-dx));
+    out |= (row & 31u) << (5 * r);
+  }
+  return out;
+}
+constexpr uint32_t kPatch3x3 = 0x1CE7u, kPatch4x4 = 0x7BDEFu;   // rows of 3 (4) set bits, origin (x - 1, y - 1)
 
-struct TieInfo {  // what a tie's cache touches look like if it turns out to be a maximum (8 bytes)
-  int8_t own_touch, has_above, exited, n_queries;
-  int16_t max_x, max_y;
+// The ties of one frame in time order, one array per field (what k_tie_gather writes and k_resolve reads, coalesced)
+struct TieSorted {
+  uint32_t* key;     // time key (layer, y, x)
+  uint32_t* rec;     // candidate record index
+  uint32_t* tmask;   // bits 0..24: 5x5 window pixels touched by non-tied maxima before this tie; bits 25..26: the outcome (1 maximum,
+                     // 2 rejected) if no earlier tie touches a sensitive pixel
+  uint32_t* sens;    // window pixels whose visibility matters: 0 < score < threshold and not in tmask
+  uint32_t* fp;      // cache touches of this tie if it is a maximum: bits 0..24 = pixels of layer + 1 relative to the box of its
+                     // above-layer scan, bits 25..26 = own-layer patch (0 none, 1 = 3x3, 2 = 4x4 around x-1, y-1)
+  uint32_t* win;     // [7][kMaxTies] packed 5x5 score bytes
 };
+constexpr size_t kTieSortedWords = (size_t)kMaxTies * (5 + 7);
+__device__ __host__ __forceinline__ TieSorted tie_sorted(uint32_t* base, int frame)
+{
+  uint32_t* p = base + (size_t)frame * kTieSortedWords;
+  return TieSorted{p, p + kMaxTies, p + 2 * kMaxTies, p + 3 * kMaxTies, p + 4 * kMaxTies, p + 5 * kMaxTies};
+}
+
+// Per tie, spread over the GPU (grid: tiles of 128 ties x frames): its rank in time order (count of smaller keys: the list
+// k_refine appended is unordered), everything the dependency rounds need from global memory -- the touch-time words and the
+// dense scores of its 5x5 window (50 scattered loads, the reason this is not done by the one CTA that resolves the frame) --
+// and the footprint of its own touches as bit masks. Results are written to position `rank` of the per-field arrays.
+__global__ void __launch_bounds__(128) k_tie_gather(const __grid_constant__ DeviceLayers dl, const uint8_t* score_block, const uint32_t* touch_block,
+                                                    const TieEntry* tie_list, const int32_t* tie_count, const uint32_t* d_epoch, int threshold,
+                                                    uint32_t* sorted_base)
+{
+  __shared__ uint32_t keys[kMaxTies];
+  const int frame = blockIdx.y;
+  const int T = min(tie_count[frame], kMaxTies);
+  if ((int)(blockIdx.x * blockDim.x) >= T) return;
+  const TieEntry* E = tie_list + (size_t)frame * kMaxTies;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) keys[j] = E[j].key;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  const TieEntry e = E[i];
+  const uint32_t key = e.key, epoch = *d_epoch;
+  const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+  const DeviceLayer d = dl.l[layer];
+  const uint32_t* tm = touch_block + (size_t)frame * dl.frame_stride + d.offset;
+  const uint8_t* sc = score_block + (size_t)frame * dl.frame_stride + d.offset;
+  uint32_t te[25], sv[25];
+#pragma unroll
+  for (int j = 0; j < 25; j++) {
+    const size_t o = (size_t)(y + j / 5 - 2) * d.pitch + (x + j % 5 - 2);
+    te[j] = __ldcg(&tm[o]); sv[j] = __ldcg(&sc[o]);
+  }
+  int rank = 0;
+  for (int j = 0; j < T; j++) rank += keys[j] < key;   // keys are distinct pixels
+  uint32_t mask = 0, sens = 0;
+  TieWindow w;
+#pragma unroll
+  for (int j = 0; j < 7; j++) w.w[j] = 0;
+#pragma unroll
+  for (int j = 0; j < 25; j++) {
+    if (touched_before(te[j], epoch, key)) mask |= 1u << j;
+    else if (sv[j] > 0u && (int)sv[j] < threshold) sens |= 1u << j;
+    w.w[j >> 2] |= sv[j] << (8 * (j & 3));
+  }
+  // the outcome as long as no earlier tie makes a sensitive pixel visible: the common case, decided here by all SMs
+  const uint32_t r0 = tie_is_max(w, mask, threshold) ? 1u : 2u;
+  uint32_t fp = (uint32_t)e.info.own_touch << 25;
+  if (e.info.has_above) {
+    ScanIter it; above_window(layer, x, y, it);
+    const int ox = (int)it.x_1 - 1, oy = (int)it.y_1 - 1;
+    auto mark = [&](int px, int py) {
+      const int c = px - ox, r = py - oy;
+      if ((unsigned)c < 5u && (unsigned)r < 5u) fp |= 1u << (5 * r + c);
+    };
+    for (int q = 0; q < e.info.n_queries; q++) {
+      int X, Y; bool blk; above_query_pos(it, q, X, Y, blk);
+      mark(X, Y);
+      if (blk) { mark(X + 1, Y); mark(X, Y + 1); mark(X + 1, Y + 1); }
+    }
+    if (!e.info.exited) for (int j = 0; j < 9; j++) mark(e.info.max_x + j % 3 - 1, e.info.max_y + j / 3 - 1);
+  }
+  const TieSorted S = tie_sorted(sorted_base, frame);
+  S.key[rank] = key; S.rec[rank] = e.rec; S.tmask[rank] = mask | (r0 << 25); S.sens[rank] = sens; S.fp[rank] = fp;
+#pragma unroll
+  for (int j = 0; j < 7; j++) S.win[(size_t)j * kMaxTies + rank] = w.w[j];
+}
+
+// shared-memory state of k_resolve
+struct ResolveCtx {
+  uint32_t* ties;                       // time keys, ascending
+  uint16_t (*blockers)[kMaxBlockers];
+  short4* box;                          // above-scan window (layer+1 coords)
+  uint32_t* tmask; uint32_t* fpm; uint32_t* sens;
+  int8_t* state;                        // 0 unresolved, 1 maximum, 2 rejected
+  int8_t* n_block;                      // -1: list overflowed, enumerate instead
+  int* layer_start;
+  const uint32_t* win; int win_stride;  // packed 5x5 score windows, word j of tie i at win[j * win_stride + i] (shared memory while they fit)
+};
+
+// window pixels of the tie at (layer, x, y) that winner u would have touched
+__device__ __noinline__ uint32_t tie_footprint(const ResolveCtx c, int u, int layer, int x, int y)
+{
+  const uint32_t uk = c.ties[u], f = c.fpm[u];
+  const int ul = (int)(uk >> 22), uy = (int)((uk >> 11) & 2047), ux = (int)(uk & 2047);
+  if (ul == layer) {
+    const uint32_t own = f >> 25;
+    return own ? rebase5x5(own == 2 ? kPatch4x4 : kPatch3x3, (ux - 1) - (x - 2), (uy - 1) - (y - 2)) : 0u;
+  }
+  const short4 bx = c.box[u];
+  return rebase5x5(f & 0x1ffffffu, (int)bx.x - (x - 2), (int)bx.z - (y - 2));
+}
+
+// Enumerates the possible blockers of tie ti: earlier ties whose touches can reach its window (same layer within 4 px, or the
+// layer below through the box of its above-scan). mode 0: append them to blockers[ti] (returns the count, -1 on overflow);
+// mode 1: returns 1 + the first undecided one (0 if none); mode 2: ORs the footprints of the winners among them into `add`.
+__device__ __noinline__ int tie_enumerate(const ResolveCtx c, int ti, int mode, uint32_t& add)
+{
+  const uint32_t key = c.ties[ti];
+  const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+  int nb = 0;
+  // part 0: own layer, rows y-4 .. y before ti; part 1: the layer below, rows whose above-scan box (rows 2/3 uy - 2.5 .. 2/3 uy + 2.2
+  // for a 3:2 step, 3/4 uy - 2.5 .. 3/4 uy + 2.3 for a 4:3 step) can reach [y-2, y+2]: +-8 rows around y times the ratio (the box
+  // test is the exact filter)
+#pragma unroll 1
+  for (int part = 0; part < 2; part++) {
+    if (part == 1 && layer == 0) break;
+    const int uc = (layer & 1) ? (3 * y) / 2 : (4 * y) / 3;
+    const int row_lo = part == 0 ? max(y - 4, 0) : max(uc - 8, 0), row_hi = part == 0 ? 2047 : uc + 8;
+    const uint32_t lo_key = time_key(layer - part, 0, min(row_lo, 2047));
+    int lo = c.layer_start[layer - part], hi = part == 0 ? ti : c.layer_start[layer];
+    const int end = hi;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (c.ties[mid] < lo_key) lo = mid + 1; else hi = mid; }
+#pragma unroll 1
+    for (int u = lo; u < end; u++) {
+      const uint32_t uk = c.ties[u];
+      bool hit;
+      if (part == 0) hit = abs((int)(uk & 2047) - x) <= 4;   // |dy| <= 4 by the key range
+      else {
+        if ((int)((uk >> 11) & 2047) > row_hi) break;
+        const short4 bx = c.box[u];
+        hit = !(x + 2 < bx.x || x - 2 > bx.y || y + 2 < bx.z || y - 2 > bx.w);
+      }
+      if (!hit) continue;
+      if (mode == 0) { if (nb >= kMaxBlockers) return -1; c.blockers[ti][nb++] = (uint16_t)u; }
+      else if (mode == 1) { if (c.state[u] == 0) return 1 + u; }
+      else if (c.state[u] == 1) add |= tie_footprint(c, u, layer, x, y);
+    }
+  }
+  return mode == 0 ? nb : 0;
+}
 
 // One CTA per frame. Resolves, in dependency rounds, the candidates whose 2-D maximum test ties with a neighbour:
 // their outcome depends on which sub-threshold scores the sequential algorithm had already cached when it reached them.
-// Touches by NON-tied maxima are already in the touch-time map (k_refine); touches by EARLIER TIES are applied here
-// from shared memory: a tie waits only for the earlier ties whose touches can reach its 5x5 window (same layer within
-// 4 px, or the layer below through the window of its above-scan), listed once; when they are all decided it ORs the
-// footprint of the winners among them into its 25-bit "touched" mask and evaluates the reference's isMax2D.
-__global__ void __launch_bounds__(512) k_resolve(const __grid_constant__ DeviceLayers dl, const uint8_t* score_block, const uint32_t* touch_block,
-                                                 const int32_t* cand_count, int cand_cap, const __grid_constant__ CandRegions cr,
-                                                 CandRecord* rec, const uint32_t* d_epoch, int threshold, int32_t* status, long long* dbg)
+// Touches by NON-tied maxima are already in the touch-time map (k_refine -> tmask, gathered by k_tie_gather); touches by
+// EARLIER TIES are applied here from shared memory: a tie waits only for the earlier ties whose touches can reach its 5x5
+// window, listed once; when they are all decided it ORs the footprint masks of the winners among them (re-based to its
+// window) into its "touched" mask. Only if that makes a SENSITIVE pixel visible (0 < score < threshold, TieSorted::sens) does
+// the reference's isMax2D have to be evaluated again; otherwise the outcome k_tie_gather computed stands. The kernel sees only
+// the ties, in time order, reads global memory coalesced and once; the rounds run out of shared memory. It is latency-bound on
+// one SM, instruction fetch included: the code is kept small (helpers not inlined, loops rolled).
+__global__ void __launch_bounds__(kResolveThreads) k_resolve(uint32_t* sorted_base, const int32_t* tie_count, uint32_t* fkey, int cand_cap,
+                                                             int threshold, int32_t* status, long long* dbg)
 {
-  const uint32_t epoch = *d_epoch;
 #define OKB_STAMP(i) if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + (i)] = clock64()
   OKB_STAMP(0);
+  if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + 15] = 0;
   extern __shared__ unsigned long long resolve_smem[];
-  unsigned long long* ties = resolve_smem;                                   // key << 32 | record index, sorted
-  uint16_t (*blockers)[kMaxBlockers] = reinterpret_cast<uint16_t (*)[kMaxBlockers]>(ties + kMaxTies);
-  short4* box = reinterpret_cast<short4*>(blockers + kMaxTies);              // above-scan window (layer+1 coords) ...
-  TieInfo* info = reinterpret_cast<TieInfo*>(box);                           // ... replaced by the touch info after the lists are built
-  uint32_t* tmask = reinterpret_cast<uint32_t*>(box + kMaxTies);             // window pixels touched before this tie
-  int8_t* state = reinterpret_cast<int8_t*>(tmask + kMaxTies);               // 0 unresolved, 1 maximum, 2 rejected
-  int8_t* n_block = state + kMaxTies;                                        // -1: list overflowed, scan instead
-  __shared__ int n_ties, n_unresolved, layer_start[kMaxLayers + 1];
+  __shared__ int layer_start[kMaxLayers + 1];
   const int frame = blockIdx.x;
-  int prefix_[kMaxLayers + 1];
-  const int n = cand_total(cr, cand_count + frame * kMaxLayers, dl.n, prefix_);
-  CandRecord* R = rec + (size_t)frame * cand_cap;
-  if (threadIdx.x == 0) n_ties = 0;
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    if (R[i].tie) {
-      const int p = atomicAdd(&n_ties, 1);
-      if (p < kMaxTies) ties[p] = ((unsigned long long)R[i].key << 32) | (unsigned)i;
-    }
-  __syncthreads();
-  int T = n_ties;
+  int T = tie_count[frame];
   if (T > kMaxTies) { if (threadIdx.x == 0) atomicOr(&status[frame], 2); T = kMaxTies; }
   if (T == 0) return;
-  int P = 1; while (P < T) P <<= 1;
-  for (int i = T + threadIdx.x; i < P; i += blockDim.x) ties[i] = ~0ull;
+  const int Tp = (T + 31) & ~31;   // array stride: the arrays are laid out for this frame's tie count
+  ResolveCtx c;
+  c.ties = reinterpret_cast<uint32_t*>(resolve_smem);
+  c.box = reinterpret_cast<short4*>(c.ties + Tp);
+  c.tmask = reinterpret_cast<uint32_t*>(c.box + Tp);
+  c.fpm = c.tmask + Tp;
+  c.sens = c.fpm + Tp;
+  c.blockers = reinterpret_cast<uint16_t (*)[kMaxBlockers]>(c.sens + Tp);
+  c.state = reinterpret_cast<int8_t*>(c.blockers + Tp);
+  c.n_block = c.state + Tp;
+  c.layer_start = layer_start;
+  uint32_t* swin = reinterpret_cast<uint32_t*>(c.n_block + Tp);
+  const bool win_in_smem = (size_t)Tp * (kResolvePerTie + 28) <= (size_t)kResolveSmem;
+  const TieSorted S = tie_sorted(sorted_base, frame);
+  c.win = win_in_smem ? swin : S.win; c.win_stride = win_in_smem ? Tp : kMaxTies;
+  uint32_t* FK = fkey + (size_t)frame * cand_cap;
+  if (win_in_smem) {
+#pragma unroll 1
+    for (int i = threadIdx.x; i < 7 * Tp; i += blockDim.x) { const int j = i / Tp, t = i - j * Tp; swin[i] = t < T ? S.win[(size_t)j * kMaxTies + t] : 0u; }
+  }
+#pragma unroll 1
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    const uint32_t key = S.key[i];
+    const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
+    c.ties[i] = key; c.tmask[i] = S.tmask[i]; c.fpm[i] = S.fp[i]; c.sens[i] = S.sens[i]; c.state[i] = 0;
+    ScanIter it; above_window(layer, x, y, it);
+    c.box[i] = make_short4((short)((int)it.x_1 - 1), (short)((int)it.x1 + 2), (short)((int)it.y_1 - 1), (short)((int)it.y1 + 2));
+  }
   __syncthreads();
-  OKB_STAMP(1);
-  bitonic_sort_u64(ties, P);
-  OKB_STAMP(2);
   if (threadIdx.x <= kMaxLayers) {
-    // first tie index of every layer (ties are sorted by key, layer is the top field)
+    // first tie index of every layer (layer is the top field of the key)
     const int l = threadIdx.x;
     int lo = 0, hi = T;
-    const unsigned long long target = (unsigned long long)time_key(l, 0, 0) << 32;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < target) lo = mid + 1; else hi = mid; }
+    const uint32_t target = time_key(l, 0, 0);
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (c.ties[mid] < target) lo = mid + 1; else hi = mid; }
     layer_start[l] = (l >= kMaxLayers) ? T : lo;
   }
-  if (threadIdx.x == 0) n_unresolved = T;
-  const uint8_t* score_frame = score_block + (size_t)frame * dl.frame_stride;
-  const uint32_t* touch_frame = touch_block + (size_t)frame * dl.frame_stride;
-  for (int i = threadIdx.x; i < T; i += blockDim.x) {
-    const uint32_t key = (uint32_t)(ties[i] >> 32);
-    const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
-    state[i] = 0;
-    ScanIter it; above_window(layer, x, y, it);
-    box[i] = make_short4((short)((int)it.x_1 - 1), (short)((int)it.x1 + 2), (short)((int)it.y_1 - 1), (short)((int)it.y1 + 2));
-    // touches by the non-tied maxima (all emitted before this kernel started)
-    const DeviceLayer d = dl.l[layer];
-    const uint32_t* tm = touch_frame + d.offset;
-    uint32_t mask = 0;
-#pragma unroll
-    for (int j = 0; j < 25; j++) {
-      const uint32_t e = __ldcg(&tm[(size_t)(y + j / 5 - 2) * d.pitch + (x + j % 5 - 2)]);
-      if (touched_before(e, epoch, key)) mask |= 1u << j;
-    }
-    tmask[i] = mask;
-  }
   __syncthreads();
-  OKB_STAMP(7);
-  // enumerate the possible blockers of tie ti (earlier ties whose touches can reach its window); F(u) true = stop
-  auto for_each_blocker = [&](int ti, auto F) {
-    const uint32_t key = (uint32_t)(ties[ti] >> 32);
-    const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
-    {
-      const unsigned long long lo_key = (unsigned long long)time_key(layer, 0, max(y - 4, 0)) << 32;
-      int lo = layer_start[layer], hi = ti;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < lo_key) lo = mid + 1; else hi = mid; }
-      for (int u = lo; u < ti; u++) {
-        const int ux = (int)((uint32_t)(ties[u] >> 32) & 2047);
-        if (abs(ux - x) <= 4) if (F(u)) return;   // |dy| <= 4 by the key range
-      }
-    }
-    if (layer > 0) {
-      // rows of the layer below that can map into [y-2, y+2] (+ scan margins); the ratio is 3/2 or 4/3
-      const int uy_lo = max((y - 5) * 4 / 3 - 3, 0), uy_hi = (y + 5) * 3 / 2 + 4;
-      const unsigned long long lo_key = (unsigned long long)time_key(layer - 1, 0, min(uy_lo, 2047)) << 32;
-      int lo = layer_start[layer - 1], hi = layer_start[layer];
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (ties[mid] < lo_key) lo = mid + 1; else hi = mid; }
-      for (int u = lo; u < layer_start[layer]; u++) {
-        const int uy = (int)(((uint32_t)(ties[u] >> 32) >> 11) & 2047);
-        if (uy > uy_hi) break;
-        const short4 bx = box[u];
-        if (!(x + 2 < bx.x || x - 2 > bx.y || y + 2 < bx.z || y - 2 > bx.w)) if (F(u)) return;
-      }
-    }
-  };
+  OKB_STAMP(1);
+  uint32_t unused = 0;
+#pragma unroll 1
   for (int ti = threadIdx.x; ti < T; ti += blockDim.x) {
-    int nb = 0;
-    for_each_blocker(ti, [&](int u) {
-      if (nb < kMaxBlockers) { blockers[ti][nb++] = (uint16_t)u; return false; }
-      nb = -1; return true;
-    });
-    n_block[ti] = (int8_t)nb;
+    const int nb = tie_enumerate(c, ti, 0, unused);
+    c.n_block[ti] = (int8_t)nb;
+    if (nb == 0) c.state[ti] = (int8_t)(c.tmask[ti] >> 25);   // nothing earlier can reach its window: k_tie_gather's outcome stands
+    if (nb < 0 && dbg) atomicAdd((unsigned long long*)&dbg[blockIdx.x * 16 + 15], 1ull);
   }
   __syncthreads();
-  OKB_STAMP(15);
-  // the boxes are no longer needed unless a list overflowed (then the scan above is reused every round, with boxes):
-  // keep them in that (rare) case and read the touch info from the records instead
-  __shared__ int any_overflow;
-  if (threadIdx.x == 0) any_overflow = 0;
-  __syncthreads();
-  for (int ti = threadIdx.x; ti < T; ti += blockDim.x) if (n_block[ti] < 0) any_overflow = 1;
-  __syncthreads();
-  const bool use_info = !any_overflow;
-  if (use_info)
-    for (int i = threadIdx.x; i < T; i += blockDim.x) {
-      const CandRecord& c = R[(int)(ties[i] & 0xffffffffu)];
-      TieInfo ti; ti.own_touch = c.own_touch; ti.has_above = c.has_above; ti.exited = (int8_t)c.above.exited;
-      ti.n_queries = (int8_t)c.above.n_queries; ti.max_x = c.above.max_x; ti.max_y = c.above.max_y;
-      info[i] = ti;
-    }
-  __syncthreads();
-  OKB_STAMP(3);
-  auto get_info = [&](int u) {
-    if (use_info) return info[u];
-    const CandRecord& c = R[(int)(ties[u] & 0xffffffffu)];
-    TieInfo ti; ti.own_touch = c.own_touch; ti.has_above = c.has_above; ti.exited = (int8_t)c.above.exited;
-    ti.n_queries = (int8_t)c.above.n_queries; ti.max_x = c.above.max_x; ti.max_y = c.above.max_y;
-    return ti;
-  };
-  // window pixels of tie (layer, x, y) that winner u would have touched
-  auto footprint = [&](int u, int layer, int x, int y) {
-    const uint32_t uk = (uint32_t)(ties[u] >> 32);
-    const int ul = (int)(uk >> 22), uy = (int)((uk >> 11) & 2047), ux = (int)(uk & 2047);
-    const TieInfo f = get_info(u);
-    uint32_t mask = 0;
-    auto mark = [&](int px, int py) {
-      const int dx = px - x + 2, dy = py - y + 2;
-      if ((unsigned)dx < 5u && (unsigned)dy < 5u) mask |= 1u << (dy * 5 + dx);
-    };
-    if (ul == layer) {
-      if (f.own_touch) {
-        const int hi = f.own_touch == 2 ? 2 : 1;
-        for (int dy = -1; dy <= hi; dy++) for (int dx = -1; dx <= hi; dx++) mark(ux + dx, uy + dy);
-      }
-    } else if (f.has_above) {
-      ScanIter it; above_window(ul, ux, uy, it);
-      for (int q = 0; q < f.n_queries; q++) {
-        int X, Y; bool blk; above_query_pos(it, q, X, Y, blk);
-        mark(X, Y);
-        if (blk) { mark(X + 1, Y); mark(X, Y + 1); mark(X + 1, Y + 1); }
-      }
-      if (!f.exited) for (int j = 0; j < 9; j++) mark(f.max_x + j % 3 - 1, f.max_y + j / 3 - 1);
-    }
-    return mask;
-  };
+  OKB_STAMP(2);
   int rounds = 0;
+  const int K = (T + kResolveThreads - 1) / kResolveThreads;   // ties per thread (<= 4)
+  uint32_t done = 0;   // bit k: tie threadIdx.x + k * kResolveThreads is decided
+  int wait_on[kMaxTies / kResolveThreads];   // the undecided blocker tie k was last seen waiting for (-1: none)
+#pragma unroll 1
+  for (int k = 0; k < K; k++) { const int ti = threadIdx.x + k * kResolveThreads; wait_on[k] = -1; if (ti >= T || c.state[ti] != 0) done |= 1u << k; }
   while (true) {
-    int8_t decided[(kMaxTies + 511) / 512];
-    int nd = 0;
-    for (int ti = threadIdx.x; ti < T; ti += blockDim.x, nd++) {
-      decided[nd] = 0;
-      if (state[ti] != 0) continue;
-      const uint32_t key = (uint32_t)(ties[ti] >> 32);
+    uint32_t decided = 0;   // 2 bits per k: 0 = still blocked, 1 = maximum, 2 = rejected
+    bool pending = false;
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+      if ((done >> k) & 1u) continue;
+      if (wait_on[k] >= 0 && c.state[wait_on[k]] == 0) { pending = true; continue; }   // still waiting for the same tie: O(1)
+      const int ti = threadIdx.x + k * kResolveThreads;
+      const uint32_t key = c.ties[ti];
       const int layer = (int)(key >> 22), y = (int)((key >> 11) & 2047), x = (int)(key & 2047);
-      bool blocked = false;
-      uint32_t mask = tmask[ti];
-      const int nb = n_block[ti];
+      int blocker = -1;
+      uint32_t add = 0;   // window pixels the winners among the blockers have touched
+      const int nb = c.n_block[ti];
       if (nb >= 0) {
-        for (int i = 0; i < nb; i++) if (state[blockers[ti][i]] == 0) { blocked = true; break; }
-        if (!blocked) for (int i = 0; i < nb; i++) { const int u = blockers[ti][i]; if (state[u] == 1) mask |= footprint(u, layer, x, y); }
-      } else {
-        for_each_blocker(ti, [&](int u) { if (state[u] == 0) { blocked = true; return true; } return false; });
-        if (!blocked) for_each_blocker(ti, [&](int u) { if (state[u] == 1) mask |= footprint(u, layer, x, y); return false; });
-      }
-      if (blocked) continue;
-      const DeviceLayer d = dl.l[layer];
-      const uint8_t* sc = score_frame + d.offset;
-      int m[5][5];
-#pragma unroll
-      for (int dy = -2; dy <= 2; dy++)
-#pragma unroll
-        for (int dx = -2; dx <= 2; dx++) {
-          int val = sc[(size_t)(y + dy) * d.pitch + (x + dx)];  // dense b0 = what the cache holds once the pixel was touched
-          if (val < threshold && !((mask >> ((dy + 2) * 5 + dx + 2)) & 1u)) val = 0;
-          m[dy + 2][dx + 2] = val;
+#pragma unroll 1
+        for (int i = 0; i < nb; i++) { const int u = c.blockers[ti][i]; if (c.state[u] == 0) { blocker = u; break; } }
+        if (blocker < 0) {
+#pragma unroll 1
+          for (int i = 0; i < nb; i++) { const int u = c.blockers[ti][i]; if (c.state[u] == 1) add |= tie_footprint(c, u, layer, x, y); }
         }
-      decided[nd] = is_max_2d_5x5(m) ? 1 : 2;
+      } else {
+        blocker = tie_enumerate(c, ti, 1, add) - 1;
+        if (blocker < 0) tie_enumerate(c, ti, 2, add);
+      }
+      if (blocker >= 0) { wait_on[k] = blocker; pending = true; continue; }
+      const uint32_t tm = c.tmask[ti];
+      uint32_t r = tm >> 25;
+      // an earlier tie made a sub-threshold score of the window visible: evaluate the test on the new map (rare)
+      if (add & c.sens[ti]) {
+        TieWindow t;
+#pragma unroll
+        for (int j = 0; j < 7; j++) t.w[j] = c.win[(size_t)j * c.win_stride + ti];
+        r = tie_is_max(t, (tm | add) & 0x1ffffffu, threshold) ? 1u : 2u;
+      }
+      decided |= r << (2 * k);
     }
     __syncthreads();   // every thread has read the states of this round
-    nd = 0;
-    for (int ti = threadIdx.x; ti < T; ti += blockDim.x, nd++)
-      if (decided[nd]) { state[ti] = decided[nd]; atomicSub(&n_unresolved, 1); }
-    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+      const uint32_t r = (decided >> (2 * k)) & 3u;
+      if (r) { c.state[threadIdx.x + k * kResolveThreads] = (int8_t)r; done |= 1u << k; }
+    }
     rounds++;
-    if (n_unresolved <= 0) break;
+    const int more = __syncthreads_or(pending);
+    if (rounds == 1) { OKB_STAMP(3); } else if (rounds == 2) { OKB_STAMP(7); } else if (rounds == 3) { OKB_STAMP(9); }
+    if (!more) break;
   }
   OKB_STAMP(4);
-  for (int ti = threadIdx.x; ti < T; ti += blockDim.x) R[(int)(ties[ti] & 0xffffffffu)].state = state[ti];
+#pragma unroll 1
+  for (int ti = threadIdx.x; ti < T; ti += blockDim.x) if (c.state[ti] == 1) FK[S.rec[ti]] |= 0x80000000u;   // one owner per record
   if (dbg && threadIdx.x == 0) { dbg[blockIdx.x * 16 + 5] = rounds; dbg[blockIdx.x * 16 + 6] = T; }
 #undef OKB_STAMP
 }
@@ -407,7 +500,7 @@ __device__ __forceinline__ uint32_t float_order_bits(float f)
 }
 
 // exclusive scan of one int per thread across the block (blockDim.x == 1024); returns the total in `total`
-__device__ int block_exclusive_scan_1024(int val, int* sh /*33 ints*/, int& total)
+__device__ __noinline__ int block_exclusive_scan_1024(int val, int* sh /*33 ints*/, int& total)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = val;
@@ -435,76 +528,95 @@ constexpr int kFinalizeSmem = kSortCap * 8 + kSortCap * 4 + (kMaxRows + 2) * 2 +
 
 // One CTA (1024 threads) per frame: order the surviving keypoints by (layer, y, x), keep the max_kp strongest
 // (ties: earlier first), drop the ones whose sampling pattern leaves the image, write cv::KeyPoint records.
-// Ordering is a counting sort by (layer, row) followed by a tiny in-place insertion sort inside every row group.
+// Ordering is a counting sort by (layer, row) followed by a tiny in-place insertion sort inside every row group. The kernel is
+// a chain of short block-wide phases: every global read is coalesced (field arrays written by k_refine) or an independent
+// gather issued in batches, and the candidates are read once (the slot a candidate takes inside its row comes back from the
+// counting atomic and waits in a register for the row offsets).
 __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ DeviceLayers dl, const int32_t* cand_count, int cand_cap,
-                                                   const __grid_constant__ CandRegions cr, const CandRecord* rec,
+                                                   const __grid_constant__ CandRegions cr, const uint32_t* fkey, const float4* fval, uint32_t* fslot,
                                                    const float* scale_bounds, const uint32_t* size_list, int W, int H,
                                                    int max_kp, int kp_cap, okb_keypoint_t* kp_out, int32_t* kscale_out,
                                                    int32_t* count_out, int32_t* status, long long* dbg)
 {
 #define OKB_STAMP(i) if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + (i)] = clock64()
   OKB_STAMP(8);
-  extern __shared__ unsigned long long keys[];  // kSortCap (key << 32 | record index), ordered
+  extern __shared__ unsigned long long keys[];  // kSortCap (key << 32 | candidate index), ordered
   uint32_t* resp = reinterpret_cast<uint32_t*>(keys + kSortCap);          // kSortCap response bits
   uint16_t* rowoff = reinterpret_cast<uint16_t*>(resp + kSortCap);        // kMaxRows + 1 group offsets
   uint8_t* flag = reinterpret_cast<uint8_t*>(rowoff + kMaxRows + 2);      // kSortCap keep flags
   __shared__ int n_valid, hist[256], sh_scan[33], rowbase[kMaxLayers + 1];
   __shared__ uint32_t sel_prefix;
   __shared__ int sel_remaining;
+  __shared__ float s_bounds[kScales];
+  __shared__ uint32_t s_sizes[kScales];
   const int frame = blockIdx.x;
   int prefix_[kMaxLayers + 1];
   const int n = cand_total(cr, cand_count + frame * kMaxLayers, dl.n, prefix_);
   if (threadIdx.x < dl.n && cand_count[frame * kMaxLayers + threadIdx.x] > cr.off[threadIdx.x + 1] - cr.off[threadIdx.x])
     atomicOr(&status[frame], 1);   // a layer's region of the candidate list overflowed
-  const CandRecord* R = rec + (size_t)frame * cand_cap;
+  const uint32_t* FK = fkey + (size_t)frame * cand_cap;
+  const float4* FV = fval + (size_t)frame * cand_cap;
+  uint32_t* FS = fslot + (size_t)frame * cand_cap;
   if (threadIdx.x == 0) {
     n_valid = 0;
     int acc = 0;
     for (int l = 0; l < kMaxLayers; l++) { rowbase[l] = acc; if (l < dl.n) acc += dl.l[l].h; }
     rowbase[kMaxLayers] = acc;
   }
+  if (threadIdx.x < kScales) { s_bounds[threadIdx.x] = threadIdx.x < kScales - 1 ? scale_bounds[threadIdx.x] : 0.f; s_sizes[threadIdx.x] = size_list[threadIdx.x]; }
   __syncthreads();
   const int n_rows = rowbase[kMaxLayers];
-  uint32_t* rowcnt = reinterpret_cast<uint32_t*>(keys);   // counts live in the (still unused) key array during pass 1
+  if (n_rows > kMaxRows) { if (threadIdx.x == 0) { atomicOr(&status[frame], 4); count_out[frame] = 0; } return; }
+  uint32_t* rowcnt = reinterpret_cast<uint32_t*>(keys);   // counts live in the (still unused) key array during the counting pass
   for (int i = threadIdx.x; i <= n_rows; i += blockDim.x) rowcnt[i] = 0;
   __syncthreads();
-  auto row_of = [&](uint32_t key) { return rowbase[key >> 22] + (int)((key >> 11) & 2047); };
-  // pass 1: count the valid keypoints per (layer, row)
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const CandRecord& c = R[i];
-    if (c.state == 1 && c.keep) { atomicAdd(&rowcnt[row_of(c.key)], 1u); atomicAdd(&n_valid, 1); }
+  auto row_of = [&](uint32_t key) { return rowbase[(key >> 22) & 7u] + (int)((key >> 11) & 2047); };
+  // pass 1: count the valid keypoints per (layer, row); the atomic returns the candidate's slot inside its row group, which
+  // waits in the slot array for the row offsets (four independent loads in flight per thread; rolled loops: this CTA pays for
+  // every instruction it fetches)
+  int my_valid = 0;
+#pragma unroll 1
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * 1024) {
+    uint32_t k[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = i0 + u * 1024; k[u] = i < n ? __ldcg(&FK[i]) : 0u; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * 1024;
+      if (i >= n) continue;
+      uint32_t w = 0;
+      if ((k[u] >> 30) == 3u) { w = 0x80000000u | atomicAdd(&rowcnt[row_of(k[u])], 1u); my_valid++; }
+      FS[i] = w;
+    }
   }
+  if (my_valid) atomicAdd(&n_valid, my_valid);
   __syncthreads();
-  int V = n_valid;
-  const bool overflow = V > kSortCap || n_rows > kMaxRows;
-  if (overflow) { if (threadIdx.x == 0) { atomicOr(&status[frame], 4); count_out[frame] = 0; } return; }
+  const int V = n_valid;
+  if (V > kSortCap) { if (threadIdx.x == 0) { atomicOr(&status[frame], 4); count_out[frame] = 0; } return; }
   // exclusive scan of the row counts -> group offsets (16 bit: V <= 16384)
   {
     const int chunk = (n_rows + (int)blockDim.x - 1) / (int)blockDim.x;
     const int beg = min((int)threadIdx.x * chunk, n_rows), end = min(beg + chunk, n_rows);
+    int cnts[8];   // chunk <= 8 for kMaxRows = 8192
     int sum = 0;
-    for (int i = beg; i < end; i++) sum += (int)rowcnt[i];
+    for (int i = beg, j = 0; i < end; i++, j++) { cnts[j] = (int)rowcnt[i]; sum += cnts[j]; }
     int total = 0;
-    int run = block_exclusive_scan_1024(sum, sh_scan, total);
-    // the counts must be consumed before the offsets overwrite anything: stage this thread's counts in registers
-    // (chunk <= 8 for kMaxRows = 8192)
-    int cnts[8];
-    for (int i = beg, j = 0; i < end; i++, j++) cnts[j] = (int)rowcnt[i];
-    __syncthreads();
+    int run = block_exclusive_scan_1024(sum, sh_scan, total);   // (its barriers separate the reads above from the writes below)
     for (int i = beg, j = 0; i < end; i++, j++) { rowoff[i] = (uint16_t)run; run += cnts[j]; }
-    if (threadIdx.x == blockDim.x - 1) rowoff[n_rows] = (uint16_t)V;
-    if (end == n_rows && beg < end) rowoff[n_rows] = (uint16_t)run;
+    if (threadIdx.x == 0) rowoff[n_rows] = (uint16_t)V;
   }
   __syncthreads();
-  // pass 2: scatter into the row groups (fill counters reuse flag[] as 8-bit counters is too small: use resp[] as 32-bit)
-  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) resp[i] = 0;   // n_rows <= kMaxRows <= kSortCap
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const CandRecord& c = R[i];
-    if (c.state == 1 && c.keep) {
-      const int row = row_of(c.key);
-      const int slot = (int)rowoff[row] + (int)atomicAdd(&resp[row], 1u);
-      keys[slot] = ((unsigned long long)c.key << 32) | (unsigned)i;
+  // pass 2: scatter into the row groups
+#pragma unroll 1
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * 1024) {
+    uint32_t w[4], k[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = i0 + u * 1024; w[u] = i < n ? FS[i] : 0u; k[u] = i < n ? __ldcg(&FK[i]) : 0u; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (!(w[u] >> 31)) continue;
+      const uint32_t key = k[u] & 0x1ffffffu;
+      keys[(int)rowoff[row_of(key)] + (int)(w[u] & 0x7fffffffu)] = ((unsigned long long)key << 32) | (unsigned)(i0 + u * 1024);
     }
   }
   __syncthreads();
@@ -520,7 +632,14 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Devic
   }
   __syncthreads();
   OKB_STAMP(10);
-  for (int i = threadIdx.x; i < V; i += blockDim.x) resp[i] = float_order_bits(R[(int)(keys[i] & 0xffffffffu)].response);
+  // responses of the ordered keypoints (independent gathers, four in flight per thread)
+  for (int i0 = threadIdx.x; i0 < V; i0 += 4 * 1024) {
+    float rv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = i0 + u * 1024; rv[u] = i < V ? __ldcg(&FV[(int)(keys[i] & 0xffffffffu)].w) : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = i0 + u * 1024; if (i < V) resp[i] = float_order_bits(rv[u]); }
+  }
   __syncthreads();
   // ---- strongest max_kp: radix select of the max_kp-th largest response
   const bool capped = max_kp > 0 && V > max_kp;
@@ -579,28 +698,41 @@ __global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ Devic
   } else {
     for (int i = beg; i < end; i++) flag[i] = 1;
   }
+  // values of the kept keypoints of this thread's chunk (chunk <= 16: V <= 16384), gathered four at a time before they are used
   int my_keep = 0;
-  for (int i = beg; i < end; i++) {
-    if (!flag[i]) continue;
-    const CandRecord& c = R[(int)(keys[i] & 0xffffffffu)];
-    const int sc = kscale_from_bounds(scale_bounds, c.size);
-    const int bd = (int)size_list[sc];
-    const bool out = c.x < (float)bd || c.x >= (float)(W - bd) || c.y < (float)bd || c.y >= (float)(H - bd);
-    flag[i] = out ? 0 : (uint8_t)(sc + 1);
-    my_keep += !out;
+  for (int j0 = beg; j0 < end; j0 += 4) {
+    float4 val[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = j0 + u; if (i < end && flag[i]) val[u] = __ldcg(&FV[(int)(keys[i] & 0xffffffffu)]); }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = j0 + u;
+      if (i >= end || !flag[i]) continue;
+      const int sc = kscale_from_bounds(s_bounds, val[u].z);
+      const int bd = (int)s_sizes[sc];
+      const bool out = val[u].x < (float)bd || val[u].x >= (float)(W - bd) || val[u].y < (float)bd || val[u].y >= (float)(H - bd);
+      flag[i] = out ? 0 : (uint8_t)(sc + 1);
+      my_keep += !out;
+    }
   }
   int pos = block_exclusive_scan_1024(my_keep, sh_scan, total);
-  for (int i = beg; i < end; i++) {
-    if (!flag[i]) continue;
-    if (pos < kp_cap) {
-      const CandRecord& c = R[(int)(keys[i] & 0xffffffffu)];
-      okb_keypoint_t k;
-      k.x = c.x; k.y = c.y; k.size = c.size; k.angle = -1.f; k.response = c.response;
-      k.octave = (int)(c.key >> 22); k.class_id = -1;
-      kp_out[(size_t)frame * kp_cap + pos] = k;
-      kscale_out[(size_t)frame * kp_cap + pos] = (int)flag[i] - 1;
+  for (int j0 = beg; j0 < end; j0 += 4) {
+    float4 val[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = j0 + u; if (i < end && flag[i]) val[u] = __ldcg(&FV[(int)(keys[i] & 0xffffffffu)]); }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = j0 + u;
+      if (i >= end || !flag[i]) continue;
+      if (pos < kp_cap) {
+        okb_keypoint_t k;
+        k.x = val[u].x; k.y = val[u].y; k.size = val[u].z; k.angle = -1.f; k.response = val[u].w;
+        k.octave = (int)((uint32_t)(keys[i] >> 32) >> 22); k.class_id = -1;
+        kp_out[(size_t)frame * kp_cap + pos] = k;
+        kscale_out[(size_t)frame * kp_cap + pos] = (int)flag[i] - 1;
+      }
+      pos++;
     }
-    pos++;
   }
   if (threadIdx.x == 0) {
     if (total > kp_cap) atomicOr(&status[frame], 8);
@@ -821,13 +953,18 @@ int detect_init_camera(okb_context* ctx, int cam)
   {
     // per-call counters in one block (one memset per call): candidate counts, status words, tie-cell bitmaps
     const size_t cc = align_up((size_t)4 * kMaxLayers * B, 256), stb = align_up((size_t)4 * B, 256);
-    ws.zero_bytes = cc + stb + (size_t)kCellWordsPerFrame * B * 4;
+    ws.zero_bytes = cc + 2 * stb + (size_t)kCellWordsPerFrame * B * 4;
     uint8_t* blk = nullptr;
     OKB_CUDA(cudaMalloc(&blk, ws.zero_bytes));
     OKB_CUDA(cudaMemset(blk, 0, ws.zero_bytes));
-    ws.d_cand_count = (int32_t*)blk; ws.d_status = (int32_t*)(blk + cc); ws.d_tie_cells = (uint32_t*)(blk + cc + stb);
+    ws.d_cand_count = (int32_t*)blk; ws.d_status = (int32_t*)(blk + cc); ws.d_tie_count = (int32_t*)(blk + cc + stb);
+    ws.d_tie_cells = (uint32_t*)(blk + cc + 2 * stb);
+    OKB_CUDA(cudaMalloc(&ws.d_ties, (size_t)kMaxTies * sizeof(TieEntry) * B));
+    OKB_CUDA(cudaMalloc(&ws.d_tie_sorted, kTieSortedWords * 4 * B));
   }
-  OKB_CUDA(cudaMalloc(&ws.d_rec, (size_t)ws.cand_cap * sizeof(CandRecord) * B));
+  OKB_CUDA(cudaMalloc(&ws.d_fkey, (size_t)ws.cand_cap * 4 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_fval, (size_t)ws.cand_cap * 16 * B));
+  OKB_CUDA(cudaMalloc(&ws.d_fslot, (size_t)ws.cand_cap * 4 * B));
   OKB_CUDA(cudaMalloc(&ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t) * B));
   OKB_CUDA(cudaMalloc(&ws.d_kscale, (size_t)ws.kp_cap * 4 * B));
   OKB_CUDA(cudaMalloc(&ws.d_desc, (size_t)ws.kp_cap * 64 * B));
@@ -861,9 +998,9 @@ void detect_free_camera(okb_context* ctx, int cam)
     LayerGeom& g = ws.geom[i];
     cudaFree(g.d_xs); cudaFree(g.d_xn); cudaFree(g.d_xa); cudaFree(g.d_ys); cudaFree(g.d_yn); cudaFree(g.d_ya);
   }
-  cudaFree(ws.d_epoch); cudaFree(ws.d_tiles); cudaFree(ws.d_ray_map); cudaFree(ws.d_jac_map);
+  cudaFree(ws.d_epoch); cudaFree(ws.d_ties); cudaFree(ws.d_tie_sorted); cudaFree(ws.d_tiles); cudaFree(ws.d_ray_map); cudaFree(ws.d_jac_map);
   cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
-  cudaFree(ws.d_cand_count); cudaFree(ws.d_rec); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
+  cudaFree(ws.d_cand_count); cudaFree(ws.d_fkey); cudaFree(ws.d_fval); cudaFree(ws.d_fslot); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
   cudaFree(ws.d_count); cudaFree(ws.d_m1_rows); cudaFree(ws.m_d); if (ws.m_h) cudaFreeHost(ws.m_h); cudaFree(ws.m3_d); if (ws.m3_h) cudaFreeHost(ws.m3_h); cudaFree(ws.motion.d); if (ws.motion.h) cudaFreeHost(ws.motion.h); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);
   if (ws.ev_done) cudaEventDestroy(ws.ev_done);
   cudaFreeHost(ws.h_img); cudaFreeHost(ws.h_kp); cudaFreeHost(ws.h_desc); cudaFreeHost(ws.h_count); cudaFreeHost(ws.h_status); cudaFreeHost(ws.h_rays); cudaFreeHost(ws.h_rays_valid);
@@ -935,10 +1072,12 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   // ---- candidates, refinement, tie resolution, selection
   k_refine<<<dim3((ws.cand_cap + 127) / 128, B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
                                                                ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap, cr,
-                                                               ws.d_rec, c.threshold, ws.d_epoch, ws.d_tie_cells);
-  k_resolve<<<B, 512, kResolveSmem, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_cand_count, ws.cand_cap, cr, ws.d_rec, ws.d_epoch, c.threshold,
-                                          ws.d_status, ws.d_dbg);
-  k_finalize<<<B, 1024, kFinalizeSmem, st>>>(ws.dl, ws.d_cand_count, ws.cand_cap, cr, ws.d_rec, ctx->d_scale_bounds, ctx->d_size_list,
+                                                               ws.d_fkey, (float4*)ws.d_fval, c.threshold, ws.d_epoch, ws.d_tie_cells, ws.d_ties, ws.d_tie_count);
+  k_tie_gather<<<dim3(kMaxTies / 128, B), 128, 0, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_ties, ws.d_tie_count, ws.d_epoch, c.threshold, ws.d_tie_sorted);
+  k_resolve<<<B, kResolveThreads, kResolveSmem, st>>>(ws.d_tie_sorted, ws.d_tie_count, ws.d_fkey, ws.cand_cap, c.threshold, ws.d_status, ws.d_dbg);
+  ctx->launches++;
+  k_finalize<<<B, 1024, kFinalizeSmem, st>>>(ws.dl, ws.d_cand_count, ws.cand_cap, cr, ws.d_fkey, (const float4*)ws.d_fval, ws.d_fslot,
+                                            ctx->d_scale_bounds, ctx->d_size_list,
                                             W, H, c.max_keypoints, ws.kp_cap, ws.d_kp, ws.d_kscale, ws.d_count, ws.d_status, ws.d_dbg);
   ctx->launches += 3;
   if (ctx->timers_on) cudaEventRecord(ws.ev[2], st);

@@ -49,14 +49,14 @@ struct DeviceLayers {
 };
 
 // refined candidate record kept on the device between the refine, resolve and finalize kernels
-struct CandRecord {
-  float x, y, size, response;
-  uint32_t key;       // time key (layer, y, x)
-  int8_t keep, own_touch, has_above, tie;
-  ScanTrace above;    // 8 bytes
-  int8_t state;       // ties: 0 unresolved, 1 = is a maximum, 2 = rejected; non-ties: 1
-  int8_t pad[3];
+
+// a candidate whose 2-D maximum test ties with a neighbour, appended by k_refine for k_resolve: what its cache touches look like
+// if it turns out to be a maximum (8 bytes) + its time key and record index
+struct TieInfo {
+  int8_t own_touch, has_above, exited, n_queries;
+  int16_t max_x, max_y;
 };
+struct TieEntry { uint32_t key, rec; TieInfo info; };
 
 // device scratch + page-locked table mirror of one M3 sequence (okb_match_motion_stereo_device*)
 struct MotionScratch { void* d = nullptr; size_t cap = 0; void* h = nullptr; size_t h_cap = 0; int pinned_staging = 0; };
@@ -78,12 +78,17 @@ struct CamWorkspace {
   uint8_t* d_img = nullptr;     // layer images (layers >= 1)
   uint8_t* d_score = nullptr;   // thresholded score maps
   uint32_t* d_touch = nullptr;  // touch-time maps
+  TieEntry* d_ties = nullptr;       // per frame: kMaxTies entries; d_tie_count (in the zero block) holds the fill
+  int32_t* d_tie_count = nullptr;
+  uint32_t* d_tie_sorted = nullptr; // per frame: the ties in time order, field by field (k_tie_gather -> k_resolve)
   uint32_t* d_tie_cells = nullptr;  // per frame: one bit per 16x16 cell of every layer, set around tied candidates
   int32_t* d_integral = nullptr;  // (w+1) x (h+1) per frame
   uint32_t* d_cand = nullptr;   // candidate keys
   int32_t* d_cand_count = nullptr;   // start of the per-call zero block: counts | status | tie cells (zero_bytes in total)
   size_t zero_bytes = 0;
-  CandRecord* d_rec = nullptr;
+  uint32_t* d_fkey = nullptr;   // per candidate: time key | keep << 30 | decided-maximum << 31 (k_refine, k_resolve -> k_finalize)
+  void* d_fval = nullptr;       // per candidate: float4 x, y, size, response
+  uint32_t* d_fslot = nullptr;  // k_finalize scratch for frames with more than 16384 candidates
   okb_keypoint_t* d_kp = nullptr;
   int32_t* d_kscale = nullptr;
   uint8_t* d_desc = nullptr;

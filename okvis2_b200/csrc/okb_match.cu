@@ -14,6 +14,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "okb_internal.h"
 #include "okb_gatecos.h"
 #include "okb_camdev.h"
@@ -108,6 +110,9 @@ struct MatchArgs {
   // M3 sequence (okb_match_motion_stereo_device*): the queries of frame b are the keypoints of the older view
   // views[b * view_stride + view_index]; poses per frame
   const struct M3View* views; int view_stride, view_index; const struct M3Frame* frames;
+  // k_m4_scan over several views at once (blockIdx.z = view * scan_chunks + query chunk): per-view slices of q_use (nq apart),
+  // of the hit lists (gridDim.y * hit_cap apart) and of hit_cnt (gridDim.y apart); scan_qt = queries per CTA (<= 128)
+  int scan_views, scan_chunks, scan_qt;
 };
 
 // one older keyframe view (device pointers) and the per-frame pose of the current camera, as uploaded by the M3 sequence
@@ -648,8 +653,11 @@ __global__ void __launch_bounds__(256) k_m4_scan(MatchArgs a, uint2* hits, int32
   __shared__ uint4 sq[kQT][D16];
   __shared__ uint8_t s_act[kQT];
   const int frame = blockIdx.y;
-  const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
-  const M3View* view = a.views ? &a.views[(size_t)frame * a.view_stride + a.view_index] : nullptr;   // M3: queries = an older view
+  const int vz = a.scan_views > 0 ? blockIdx.z / a.scan_chunks : 0, qz = a.scan_views > 0 ? blockIdx.z % a.scan_chunks : blockIdx.z;
+  const int qt = a.scan_qt > 0 ? a.scan_qt : kQT;
+  const size_t fq = (size_t)frame * a.q_stride + (size_t)vz * a.nq, fc = (size_t)frame * a.c_stride;
+  const M3View* view = a.views ? &a.views[(size_t)frame * a.view_stride + a.view_index + vz] : nullptr;   // M3: queries = an older view
+  hits += (size_t)vz * gridDim.y * a.hit_cap; hit_cnt += (size_t)vz * gridDim.y;
   const int nq = view ? min(view->n, a.nq) : min(a.q_count[frame], a.nq), nc = min(a.c_count[frame], a.nc);
   const uint4* q_desc = view ? reinterpret_cast<const uint4*>(view->desc) : reinterpret_cast<const uint4*>(a.q_desc) + fq * D16;
   if ((int)(blockIdx.x * blockDim.x) >= nc) return;
@@ -659,15 +667,15 @@ __global__ void __launch_bounds__(256) k_m4_scan(MatchArgs a, uint2* hits, int32
 #pragma unroll
   for (int w = 0; w < D16; w++) cd[w] = valid_c ? __ldg(reinterpret_cast<const uint4*>(a.c_desc) + (fc + c) * D16 + w) : make_uint4(0, 0, 0, 0);
   {
-    const int q0 = blockIdx.z * kQT;   // one chunk of queries per CTA: (candidate tile, frame, query chunk) fills the GPU
+    const int q0 = qz * qt;   // one chunk of queries per CTA: (candidate tile, frame, query chunk) fills the GPU
     if (q0 >= nq) return;
-    for (int i = threadIdx.x; i < kQT * D16; i += blockDim.x) {
+    for (int i = threadIdx.x; i < qt * D16; i += blockDim.x) {
       const int j = i / D16, w = i % D16;
       sq[j][w] = q0 + j < nq ? __ldg(q_desc + (size_t)(q0 + j) * D16 + w) : make_uint4(0, 0, 0, 0);
     }
-    if (threadIdx.x < kQT) s_act[threadIdx.x] = (q0 + (int)threadIdx.x < nq && (a.q_use == nullptr || a.q_use[fq + q0 + threadIdx.x])) ? 1 : 0;
+    if ((int)threadIdx.x < qt) s_act[threadIdx.x] = (q0 + (int)threadIdx.x < nq && (a.q_use == nullptr || a.q_use[fq + q0 + threadIdx.x])) ? 1 : 0;
     __syncthreads();
-    const int jn = min(kQT, nq - q0);
+    const int jn = min(qt, nq - q0);
     for (int j = 0; j < jn; j++) {
       if (!s_act[j]) continue;   // CTA-uniform
       // popcount of the 256 bits of the second descriptor half through a carry-save adder tree: 8 words -> ones / twos /
@@ -719,13 +727,9 @@ __global__ void __launch_bounds__(128) k_m4_gate(MatchArgs a, const uint2* hits,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128) k_m4_finish(MatchArgs a, const unsigned long long* best)
+__device__ __forceinline__ void m4_finish_one(const MatchArgs& a, const unsigned long long b, int frame, int q)
 {
-  const int frame = blockIdx.y;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= a.nq || a.hit_cnt[frame] > a.hit_cap) return;
   const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
-  const unsigned long long b = best[fq + q];
   const uint32_t d = (uint32_t)(b >> 32);
   double* hp = a.out_hp + 4 * (fq + q);
   if (d < a.thr) {
@@ -741,6 +745,15 @@ __global__ void __launch_bounds__(128) k_m4_finish(MatchArgs a, const unsigned l
   }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(128) k_m4_finish(MatchArgs a, const unsigned long long* best)
+{
+  const int frame = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.nq || a.hit_cnt[frame] > a.hit_cap) return;
+  m4_finish_one<MODE>(a, best[(size_t)frame * a.q_stride + q], frame, q);
+}
+
 
 // ---- M3 as a device-resident sequence over the older keyframes (Frontend::matchMotionStereo, Frontend.cpp:1775-1958) ----
 // Per older keyframe index v, for all frames of the batch at once:
@@ -752,21 +765,26 @@ __global__ void __launch_bounds__(128) k_m4_finish(MatchArgs a, const unsigned l
 //                of the matched current keypoint: atomicMin of k0 = "first k0 in ascending order wins" (:1915-1954);
 //   k_m3_commit  flags (matching / initialisable / inserted) and the update of the matched mask for the next older keyframe.
 struct M3Prep {
-  const M3View* views; int view_stride, view_index; const M3Frame* frames;
-  int cap0, cap1; size_t q_stride;   // scratch / output stride per frame (keypoints): n_older * cap0
+  const M3View* views; int n_views; const M3Frame* frames;
+  int cap0, cap1; size_t q_stride;   // scratch / output stride per frame (keypoints): n_views * cap0
   double f0;
-  double* e0; double* c26; double* c6; uint8_t* use0;            // [frames][n_older][cap0] (base already offset by view_index * cap0)
+  double* e0; double* c26; double* c6; uint8_t* use0;            // [frames][n_views][cap0]
   const double* rays1; const uint8_t* valid1; const int32_t* count1; const uint8_t* matched1; double* e1; uint8_t* cvalid;   // [frames][cap1]
-  int first;   // 1: also compute e1 (once per call)
+  unsigned long long* best;   // [frames][n_views][cap0] -> all ones
+  int32_t* claim;             // [n_views][frames][cap1] -> INT_MAX
+  int32_t* hit_cnt;           // [n_views][frames] -> 0
 };
 
+// one launch for the whole sequence: grid (keypoint tiles, frames, views). Tables of every view's keypoints, and (by the z = 0
+// slice) the world rays and the candidate mask of the current frame; resets the per-view reduction arrays
 __global__ void __launch_bounds__(128) k_m3_prep(const __grid_constant__ M3Prep p)
 {
-  const int frame = blockIdx.y;
+  const int frame = blockIdx.y, v = blockIdx.z;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const M3View& V = p.views[(size_t)frame * p.view_stride + p.view_index];
+  const M3View& V = p.views[(size_t)frame * p.n_views + v];
+  if (k == 0) p.hit_cnt[(size_t)v * gridDim.y + frame] = 0;
   if (k < p.cap0) {
-    const size_t i = (size_t)frame * p.q_stride + k;
+    const size_t i = (size_t)frame * p.q_stride + (size_t)v * p.cap0 + k;
     bool use = false;
     if (k < V.n) {
       use = V.valid[k] && (V.use == nullptr || V.use[k]);
@@ -779,17 +797,23 @@ __global__ void __launch_bounds__(128) k_m3_prep(const __grid_constant__ M3Prep 
       p.c26[i] = gate_cos(2.6 * sigma); p.c6[i] = gate_cos(6.0 * sigma);
     }
     p.use0[i] = use ? 1 : 0;
+    p.best[i] = ~0ull;
   }
   if (k < p.cap1) {
     const size_t j = (size_t)frame * p.cap1 + k;
-    const bool in = k < min(p.count1[frame], p.cap1);
-    if (p.first && in) {
-      const double x = p.rays1[3 * j], y = p.rays1[3 * j + 1], z = p.rays1[3 * j + 2];
-      const double* C = p.frames[frame].Twc;
-      const V3 e = normalized(V3{(C[0] * x + C[1] * y) + C[2] * z, (C[3] * x + C[4] * y) + C[5] * z, (C[6] * x + C[7] * y) + C[8] * z});
-      p.e1[3 * j] = e.x; p.e1[3 * j + 1] = e.y; p.e1[3 * j + 2] = e.z;
+    p.claim[((size_t)v * gridDim.y + frame) * p.cap1 + k] = 0x7fffffff;
+    if (v == 0) {
+      const bool in = k < min(p.count1[frame], p.cap1);
+      if (in) {
+        const double x = p.rays1[3 * j], y = p.rays1[3 * j + 1], z = p.rays1[3 * j + 2];
+        const double* C = p.frames[frame].Twc;
+        const V3 e = normalized(V3{(C[0] * x + C[1] * y) + C[2] * z, (C[3] * x + C[4] * y) + C[5] * z, (C[6] * x + C[7] * y) + C[8] * z});
+        p.e1[3 * j] = e.x; p.e1[3 * j + 1] = e.y; p.e1[3 * j + 2] = e.z;
+      }
+      // the reference's compacted candidate set k1s (:1789-1801): valid and not yet matched; k_m3_commit / k_m3_view clear the
+      // entries a view inserts, so every view sees the set as its predecessors left it
+      p.cvalid[j] = (in && p.valid1[j] && !p.matched1[j]) ? 1 : 0;
     }
-    p.cvalid[j] = (in && p.valid1[j] && !p.matched1[j]) ? 1 : 0;
   }
 }
 
@@ -799,14 +823,12 @@ struct M3Check {
   Model cam; int width, height; uint32_t thr;
   const okb_keypoint_t* kp1;                     // [frames][cap1]
   const int32_t* k1; const uint32_t* dist; const double* hp; const uint8_t* init;   // matcher outputs (offset by view_index * cap0)
-  uint8_t* flags; int32_t* claim; uint8_t* matched1;
+  uint8_t* flags; int32_t* claim; uint8_t* matched1; uint8_t* cvalid;
 };
 
-__global__ void __launch_bounds__(128) k_m3_check(const __grid_constant__ M3Check c)
+// re-projection check and claim of one (frame, k0): returns the flags (bit 0 matching, bit 1 initialisable)
+__device__ __forceinline__ uint8_t m3_check_one(const M3Check& c, int frame, int k0)
 {
-  const int frame = blockIdx.y;
-  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k0 >= c.cap0) return;
   const size_t i = (size_t)frame * c.q_stride + k0;
   uint8_t fl = 0;
   const int k1 = c.k1[i];
@@ -824,7 +846,15 @@ __global__ void __launch_bounds__(128) k_m3_check(const __grid_constant__ M3Chec
     fl = (uint8_t)((matching ? 1 : 0) | (c.init[i] ? 2 : 0));
     if (matching) atomicMin(&c.claim[(size_t)frame * c.cap1 + k1], k0);
   }
-  c.flags[i] = fl;
+  return fl;
+}
+
+__global__ void __launch_bounds__(128) k_m3_check(const __grid_constant__ M3Check c)
+{
+  const int frame = blockIdx.y;
+  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k0 >= c.cap0) return;
+  c.flags[(size_t)frame * c.q_stride + k0] = m3_check_one(c, frame, k0);
 }
 
 __global__ void __launch_bounds__(128) k_m3_commit(const __grid_constant__ M3Check c)
@@ -837,7 +867,63 @@ __global__ void __launch_bounds__(128) k_m3_commit(const __grid_constant__ M3Che
   if (!(fl & 1)) return;
   const size_t j = (size_t)frame * c.cap1 + c.k1[i];
   // cvalid excluded the keypoints matched before this view, so every claim is on an unmatched keypoint: the lowest k0 inserts
-  if (c.claim[j] == k0) { c.flags[i] = fl | 4; c.matched1[j] = 1; }
+  if (c.claim[j] == k0) { c.flags[i] = fl | 4; c.matched1[j] = 1; c.cvalid[j] = 0; }
+}
+
+// One older keyframe of the sequence in ONE launch, one CTA per frame (the low-latency form used for small batches, where ten
+// launches per view cost more than their work): gate of the view's hit list -> per-query minimum -> outputs -> 4 px check and
+// claim -> commit. Same device functions as k_m4_gate / k_m4_finish / k_m3_check / k_m3_commit; the phases are separated by block
+// barriers instead of kernel boundaries (the reductions go through L2 atomics and are read back with ld.cg). A frame whose hit
+// list overflowed is matched by brute force here (warp per query, candidates in ascending order by the min over (distance, k1)).
+template <int D16>
+__global__ void __launch_bounds__(512) k_m3_view(MatchArgs a, const __grid_constant__ M3Check c, const uint2* hits, unsigned long long* best)
+{
+  const int frame = blockIdx.x;
+  const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
+  const int n_hits = a.hit_cnt[frame];
+  if (n_hits <= a.hit_cap) {
+    for (int i = threadIdx.x; i < n_hits; i += blockDim.x) {
+      const uint2 e = hits[(size_t)frame * a.hit_cap + i];
+      const int q = (int)(e.x & 0xfffffu), cc = (int)e.y;
+      if (m3_gate(a, fq, fc, q, cc).pass) atomicMin(&best[fq + q], ((unsigned long long)(e.x >> 20) << 32) | (unsigned)cc);
+    }
+  } else {
+    const M3View& view = a.views[(size_t)frame * a.view_stride + a.view_index];
+    const int nq = min(view.n, a.nq), nc = min(a.c_count[frame], a.nc);
+    const int lane = threadIdx.x & 31;
+    for (int q = threadIdx.x >> 5; q < nq; q += blockDim.x >> 5) {
+      if (a.q_use && !a.q_use[fq + q]) continue;
+      uint4 qd[D16];
+#pragma unroll
+      for (int w = 0; w < D16; w++) qd[w] = __ldg(reinterpret_cast<const uint4*>(view.desc) + (size_t)q * D16 + w);
+      unsigned long long mine = ~0ull;
+      for (int cc = lane; cc < nc; cc += 32) {
+        if (!a.c_valid[fc + cc]) continue;
+        uint32_t d = 0;
+#pragma unroll
+        for (int w = 0; w < D16; w++) {
+          const uint4 cv = __ldg(reinterpret_cast<const uint4*>(a.c_desc) + (fc + cc) * D16 + w);
+          d += __popc(qd[w].x ^ cv.x) + __popc(qd[w].y ^ cv.y) + __popc(qd[w].z ^ cv.z) + __popc(qd[w].w ^ cv.w);
+        }
+        if (d < a.thr && m3_gate(a, fq, fc, q, cc).pass) mine = min(mine, ((unsigned long long)d << 32) | (unsigned)cc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+      if (lane == 0) best[fq + q] = mine;
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < a.nq; q += blockDim.x) {
+    m4_finish_one<MODE_M3>(a, __ldcg(&best[fq + q]), frame, q);
+    c.flags[fq + q] = m3_check_one(c, frame, q);   // reads the outputs this thread has just written
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < a.nq; q += blockDim.x) {
+    const uint8_t fl = c.flags[fq + q];
+    if (!(fl & 1)) continue;
+    const size_t j = fc + c.k1[fq + q];
+    if (__ldcg(&c.claim[j]) == q) { c.flags[fq + q] = fl | 4; c.matched1[j] = 1; c.cvalid[j] = 0; }
+  }
 }
 
 // matched[b][k] = lm[b][k] >= 0 (the `landmarkId != 0` test of Frontend.cpp:1792-1795 on the M1 result)
@@ -1320,6 +1406,10 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
 
 }  // extern "C"
 
+// -1: one launch per view (k_m3_view) for batches of up to 4 frames, separate kernels above; 0 / 1 force either form
+static std::atomic<int> g_m3_fused{-1};
+extern "C" void okb_m3_set_fused(int mode) { g_m3_fused.store(mode < 0 ? -1 : (mode ? 1 : 0)); }
+
 int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
                          const int32_t* d_count1, const okb_camera_model_t* model, int width, int height, const double* T_WC1, const double* T_CW1,
                          int n_older, const okb_older_view_t* older, int cap0, uint32_t match_threshold, cudaStream_t st, uint8_t* d_matched1,
@@ -1337,8 +1427,9 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t b_views = al(sizeof(M3View) * n_frames * n_older), b_frames = al(sizeof(M3Frame) * n_frames);
   const int hit_cap = 16 * cap0;   // hits (distance < threshold) per frame and view kept for the gate pass
-  const size_t need = b_views + b_frames + al(nq * 24) + 2 * al(nq * 8) + al(nq) + al(nq) /*init*/ + al(n1 * 24) + al(n1 * 24) + 2 * al(n1) + al(n1 * 4) +
-                      al(nq * 8) + al((size_t)n_frames * hit_cap * 8) + al((size_t)n_frames * 4);
+  const size_t n_hits = (size_t)n_older * n_frames * hit_cap;
+  const size_t need = b_views + b_frames + al(nq * 24) + 2 * al(nq * 8) + al(nq) + al(nq) /*init*/ + al(n1 * 24) + al(n1 * 24) + 2 * al(n1) +
+                      al(n1 * 4 * n_older) + al(nq * 8) + al(n_hits * 8) + al((size_t)n_older * n_frames * 4);
   if (need > ms.cap) {
     OKB_CUDA(cudaDeviceSynchronize());
     if (ms.d) cudaFree(ms.d);
@@ -1355,67 +1446,84 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
   }
   uint8_t* base = (uint8_t*)ms.d; size_t o = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base + o; o += al(bytes); return p; };
-  M3View* d_views = (M3View*)take(sizeof(M3View) * n_frames * n_older);
+  M3View* d_views = (M3View*)take(sizeof(M3View) * n_frames * n_older);   // views, then frames: one contiguous upload
   M3Frame* d_frames = (M3Frame*)take(sizeof(M3Frame) * n_frames);
   double* e0 = (double*)take(nq * 24); double* c26 = (double*)take(nq * 8); double* c6 = (double*)take(nq * 8);
   uint8_t* use0 = take(nq); uint8_t* init = take(nq);
   double* rays1 = (double*)take(n1 * 24); double* e1 = (double*)take(n1 * 24);
-  uint8_t* valid1 = take(n1); uint8_t* cvalid = take(n1); int32_t* claim = (int32_t*)take(n1 * 4);
-  unsigned long long* best = (unsigned long long*)take(nq * 8); uint2* hits = (uint2*)take((size_t)n_frames * hit_cap * 8);
-  int32_t* hit_cnt = (int32_t*)take((size_t)n_frames * 4);
+  uint8_t* valid1 = take(n1); uint8_t* cvalid = take(n1); int32_t* claim = (int32_t*)take(n1 * 4 * n_older);
+  unsigned long long* best = (unsigned long long*)take(nq * 8); uint2* hits = (uint2*)take(n_hits * 8);
+  int32_t* hit_cnt = (int32_t*)take((size_t)n_older * n_frames * 4);
   // descriptors of the views and poses. Asynchronous callers: pageable host staging (cudaMemcpyAsync copies it before it
   // returns, so back-to-back calls cannot overwrite each other's tables). Streaming / CUDA-graph callers (ms.pinned_staging: one
   // call in flight, synchronised per multiframe): the scratch's page-locked mirror, which a captured copy node re-reads at replay
-  std::vector<M3View> hv_((size_t)(ms.pinned_staging ? 0 : n_frames * n_older)); std::vector<M3Frame> hf_(ms.pinned_staging ? 0 : n_frames);
-  M3View* hv = ms.pinned_staging ? (M3View*)ms.h : hv_.data();
-  M3Frame* hf = ms.pinned_staging ? (M3Frame*)((uint8_t*)ms.h + b_views) : hf_.data();
+  std::vector<uint8_t> hbuf_(ms.pinned_staging ? 0 : b_views + b_frames);
+  uint8_t* hb = ms.pinned_staging ? (uint8_t*)ms.h : hbuf_.data();
+  M3View* hv = (M3View*)hb;
+  M3Frame* hf = (M3Frame*)(hb + b_views);
   for (size_t i = 0; i < (size_t)n_frames * n_older; i++) {
     const okb_older_view_t& s = older[i];
     hv[i].desc = s.d_desc; hv[i].rays = s.d_rays; hv[i].valid = s.d_valid; hv[i].size = s.d_size; hv[i].use = s.d_use; hv[i].n = s.n; hv[i].pad = 0;
     memcpy(hv[i].Twc, s.T_WC, sizeof(hv[i].Twc)); memcpy(hv[i].Tcw, s.T_CW, sizeof(hv[i].Tcw));
   }
   for (int b = 0; b < n_frames; b++) { memcpy(hf[b].Twc, T_WC1 + 12 * (size_t)b, 96); memcpy(hf[b].Tcw, T_CW1 + 12 * (size_t)b, 96); }
-  OKB_CUDA(cudaMemcpyAsync(d_views, hv, sizeof(M3View) * (size_t)n_frames * n_older, cudaMemcpyHostToDevice, st));
-  OKB_CUDA(cudaMemcpyAsync(d_frames, hf, sizeof(M3Frame) * (size_t)n_frames, cudaMemcpyHostToDevice, st));
+  OKB_CUDA(cudaMemcpyAsync(d_views, hb, b_views + sizeof(M3Frame) * (size_t)n_frames, cudaMemcpyHostToDevice, st));
   const Model cam = to_model(*model);
   // D4 of the current keypoints (Frame::computeBackProjections)
   k_backproject_ext(cam, d_kp1, d_count1, cap1, n_frames, rays1, valid1, st);
   ctx->launches++;
+  // ---- once per sequence: tables of all views + the candidate mask, then the Hamming scan of all views (the scan does not depend
+  //      on what earlier views insert: it keeps every pair below the threshold whose candidate is unmatched NOW; the gate of
+  //      view v re-tests the mask as views 0..v-1 left it)
   const int gmax = (std::max(cap0, cap1) + 127) / 128;
+  M3Prep p; memset(&p, 0, sizeof(p));
+  p.views = d_views; p.n_views = n_older; p.frames = d_frames; p.cap0 = cap0; p.cap1 = cap1;
+  p.q_stride = (size_t)n_older * cap0; p.f0 = 0.5 * (model->fu + model->fv);
+  p.e0 = e0; p.c26 = c26; p.c6 = c6; p.use0 = use0;
+  p.rays1 = rays1; p.valid1 = valid1; p.count1 = d_count1; p.matched1 = d_matched1; p.e1 = e1; p.cvalid = cvalid;
+  p.best = best; p.claim = claim; p.hit_cnt = hit_cnt;
+  k_m3_prep<<<dim3(gmax, n_frames, n_older), 128, 0, st>>>(p);
+  MatchArgs a; memset(&a, 0, sizeof(a));
+  a.nq = cap0; a.nc = cap1; a.q_stride = p.q_stride; a.c_stride = (size_t)cap1; a.c_count = d_count1;
+  a.c_desc = d_desc1; a.c_valid = cvalid; a.c_e = e1; a.thr = match_threshold;
+  a.views = d_views; a.view_stride = n_older; a.frames = d_frames; a.hit_cap = hit_cap;
+  {
+    MatchArgs s = a;
+    // small batches: short query chunks so that one frame's scan still spreads over the SMs
+    s.q_use = use0; s.view_index = 0; s.scan_views = n_older; s.scan_qt = n_frames >= 8 ? 128 : 32; s.scan_chunks = (cap0 + s.scan_qt - 1) / s.scan_qt;
+    s.hit_cnt = hit_cnt;
+    k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, n_older * s.scan_chunks), 256, 0, st>>>(s, hits, hit_cnt);
+  }
+  ctx->launches += 2;
+  // ---- per older keyframe, in order (what a view inserts is invisible to the next one's candidates)
+  const int fused_mode = g_m3_fused.load();
+  const bool fused = fused_mode >= 0 ? fused_mode != 0 : n_frames <= 4;
   for (int v = 0; v < n_older; v++) {
     const size_t vo = (size_t)v * cap0;
-    M3Prep p; memset(&p, 0, sizeof(p));
-    p.views = d_views; p.view_stride = n_older; p.view_index = v; p.frames = d_frames; p.cap0 = cap0; p.cap1 = cap1;
-    p.q_stride = (size_t)n_older * cap0; p.f0 = 0.5 * (model->fu + model->fv);
-    p.e0 = e0 + 3 * vo; p.c26 = c26 + vo; p.c6 = c6 + vo; p.use0 = use0 + vo;
-    p.rays1 = rays1; p.valid1 = valid1; p.count1 = d_count1; p.matched1 = d_matched1; p.e1 = e1; p.cvalid = cvalid; p.first = v == 0;
-    k_m3_prep<<<dim3(gmax, n_frames), 128, 0, st>>>(p);
-    MatchArgs a; memset(&a, 0, sizeof(a));
-    a.nq = cap0; a.nc = cap1; a.q_stride = p.q_stride; a.c_stride = (size_t)cap1; a.c_count = d_count1;
-    a.c_desc = d_desc1; a.q_use = p.use0; a.q_e = p.e0; a.q_sof = p.c26 /* unused by M3 */; a.q_cos26 = p.c26; a.q_cos6 = p.c6;
-    a.c_valid = cvalid; a.c_e = e1; a.thr = match_threshold;
-    a.views = d_views; a.view_stride = n_older; a.view_index = v; a.frames = d_frames;
+    a.view_index = v;
+    a.q_use = use0 + vo; a.q_e = e0 + 3 * vo; a.q_sof = c26 + vo /* unused by M3 */; a.q_cos26 = c26 + vo; a.q_cos6 = c6 + vo;
     a.out_dist = d_out_dist + vo; a.out_idx = d_out_k1 + vo; a.out_hp = d_out_hp_W + 4 * vo; a.out_init = init + vo;
-    // the gate is a pure function of the pair: result per query = min (distance, k1) over the pairs below the threshold that
-    // pass it. Register-blocked Hamming scan -> hit list -> gate per hit -> outputs; a frame whose hit list overflows is redone
-    // by the sequential-replay kernel (which returns at once for all other frames)
-    a.hit_cnt = hit_cnt; a.hit_cap = hit_cap;
-    OKB_CUDA(cudaMemsetAsync(best, 0xff, (size_t)n_frames * p.q_stride * 8, st));
-    OKB_CUDA(cudaMemsetAsync(hit_cnt, 0, (size_t)n_frames * 4, st));
+    a.hit_cnt = hit_cnt + (size_t)v * n_frames;
+    const uint2* hits_v = hits + (size_t)v * n_frames * hit_cap;
     unsigned long long* best_v = best + vo;
-    k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, (cap0 + 127) / 128), 256, 0, st>>>(a, hits, hit_cnt);
-    k_m4_gate<MODE_M3><<<dim3(8, n_frames), 128, 0, st>>>(a, hits, best_v);
-    k_m4_finish<MODE_M3><<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(a, best_v);
-    k_match_gated<4, MODE_M3><<<dim3((cap0 + 7) / 8, n_frames), 256, 0, st>>>(a);
-    ctx->launches += 3;
-    OKB_CUDA(cudaMemsetAsync(claim, 0x7f, n1 * 4, st));
     M3Check c; memset(&c, 0, sizeof(c));
     c.views = d_views; c.view_stride = n_older; c.view_index = v; c.frames = d_frames; c.cap0 = cap0; c.cap1 = cap1; c.q_stride = p.q_stride;
     c.cam = cam; c.width = width; c.height = height; c.thr = match_threshold; c.kp1 = d_kp1;
-    c.k1 = a.out_idx; c.dist = a.out_dist; c.hp = a.out_hp; c.init = a.out_init; c.flags = d_out_flags + vo; c.claim = claim; c.matched1 = d_matched1;
-    k_m3_check<<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(c);
-    k_m3_commit<<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(c);
-    ctx->launches += 4;
+    c.k1 = a.out_idx; c.dist = a.out_dist; c.hp = a.out_hp; c.init = a.out_init; c.flags = d_out_flags + vo;
+    c.claim = claim + (size_t)v * n1; c.matched1 = d_matched1; c.cvalid = cvalid;
+    if (fused) {
+      k_m3_view<4><<<n_frames, 512, 0, st>>>(a, c, hits_v, best_v);
+      ctx->launches++;
+    } else {
+      // gate per hit -> outputs; a frame whose hit list overflows is redone by the sequential-replay kernel (which returns at
+      // once for all other frames); then the re-projection check / claim and the commit
+      k_m4_gate<MODE_M3><<<dim3(8, n_frames), 128, 0, st>>>(a, hits_v, best_v);
+      k_m4_finish<MODE_M3><<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(a, best_v);
+      k_match_gated<4, MODE_M3><<<dim3((cap0 + 7) / 8, n_frames), 256, 0, st>>>(a);
+      k_m3_check<<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(c);
+      k_m3_commit<<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(c);
+      ctx->launches += 5;
+    }
   }
   OKB_CUDA(cudaGetLastError());
   return OKB_OK;

@@ -54,8 +54,11 @@ def run_device(fe, scenes, cap0, cap1, n_older):
             fl.cpu().numpy().reshape(sh), d_m.cpu().numpy())
 
 
-def test_motion_stereo_sequence_equals_oracle():
+@pytest.mark.parametrize("fused", [1, 0])
+def test_motion_stereo_sequence_equals_oracle(fused):
+    """both forms of the per-view step: one launch per view (k_m3_view, the small-batch default) and the separate kernels"""
     fe = Frontend(0)
+    okl.lib().okb_m3_set_fused(fused)
     try:
         scenes = [motion_scene(21, n_views=5, n0=500, n1=700), motion_scene(22, n_views=5, n0=640, n1=520, premated=0.5),
                   motion_scene(23, n_views=5, n0=100, n1=64, premated=0.0)]
@@ -96,4 +99,5 @@ def test_motion_stereo_sequence_equals_oracle():
             assert np.array_equal(m1[b, :len(rm)], rm)
         assert inserted > 150
     finally:
+        okl.lib().okb_m3_set_fused(-1)
         fe.close()
