@@ -683,6 +683,8 @@ class Replica:
                                         C.byref(d2), C.byref(nk2), C.byref(nm2))
             okl.check(rc)
             g_l = C.c_longlong(); d_l = C.c_longlong(); L_.okb_stream_stats(self.fes[0].ctx, C.byref(g_l), C.byref(d_l))
+            ph = (C.c_double * 4)(); L_.okb_stream_timing(self.fes[0].ctx, ph, 1)
+            calls = e2e_frames
             mf_s = self.allmax([sec2.value])[0]
             separate = {"value": self.world * e2e_frames / e2e_s, "ms_per_stereo_frame": 1e3 * e2e_s / e2e_frames,
                         "step": "the same frame as separate host-buffer calls: 2x okb_detect_describe (one host thread per camera) + okb_match_stereo + "
@@ -690,6 +692,8 @@ class Replica:
             out["streaming"] = {"value": self.world * e2e_frames / mf_s, "unit": "stereo frames/s", "h2d_bytes_per_frame": int(h2.value / e2e_frames),
                                 "d2h_bytes_per_frame": int(d2.value / e2e_frames), "ms_per_stereo_frame": 1e3 * mf_s / e2e_frames,
                                 "ms_worst_frame": worst.value,
+                                "host_ms_per_frame": {"stage_inputs": 1e3 * ph[0] / calls, "submit": 1e3 * ph[1] / calls, "wait_device": 1e3 * ph[2] / calls,
+                                                      "copy_results": 1e3 * ph[3] / calls},
                                 "step": "one stereo frame per call (live use, ThreadedSlam::processFrame): okb_process_multiframe = detect+describe both cameras, "
                                         "M1, M3 sequence, M4 enqueued at once from HOST buffers and replayed as a CUDA graph, one synchronisation per frame",
                                 "frames": e2e_frames, "cuda_graph_launches": int(g_l.value), "direct_submissions": int(d_l.value),

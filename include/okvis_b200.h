@@ -373,6 +373,8 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
 /* 0 = always submit the launches directly (default 1: CUDA-graph replay); counters of both kinds of submissions */
 int okb_stream_use_graph(okb_context_t* ctx, int on);
 int okb_stream_stats(okb_context_t* ctx, long long* graph_launches, long long* direct_calls);
+/* host seconds okb_process_multiframe has spent so far in: staging the inputs, submitting, waiting for the device, copying the results out */
+int okb_stream_timing(okb_context_t* ctx, double* seconds4, int reset);
 /* the per-older-keyframe step of the M3 sequence exists in two forms with identical results: one launch per view (one CTA per frame;
  * default for batches of up to 4 frames) and separate gate / finish / check / commit kernels (larger batches). mode: -1 default rule,
  * 0 separate kernels, 1 one launch per view. Process-wide; a testing / tuning hook. */

@@ -123,6 +123,65 @@ __global__ void __launch_bounds__(128) k_stereo_prep(PrepArgs p, const okb_keypo
   c26[i] = gate_cos(2.6 * sigma); c6[i] = gate_cos(6.0 * sigma);   // == host libm, okb_gatecos.h
 }
 
+// both sides of a stereo pair in one launch (grid: keypoint tiles x frames x 2): D4 + the preparation above, and the reset of the
+// matcher's reduction arrays (per-query best key, per-frame hit counter), which would otherwise be two more nodes in front of the scan
+struct PairPrep {
+  Model m[2]; PrepArgs p[2];
+  const okb_keypoint_t* kp[2]; const int32_t* count[2]; int cap[2];
+  double* rays[2]; uint8_t* valid[2]; double* e_W[2]; double* sof[2]; double* c26[2]; double* c6[2];
+  unsigned long long* best; int32_t* hit_cnt;
+};
+__global__ void __launch_bounds__(128) k_stereo_prep_pair(const __grid_constant__ PairPrep a)
+{
+  const int frame = blockIdx.y, s = blockIdx.z;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cap = a.cap[s];
+  if (s == 0) {
+    if (k == 0) a.hit_cnt[frame] = 0;
+    if (k < cap) a.best[(size_t)frame * cap + k] = ~0ull;
+  }
+  if (k >= min(a.count[s][frame], cap)) return;
+  const size_t i = (size_t)frame * cap + k;
+  const okb_keypoint_t kp = a.kp[s][i];
+  double x, y;
+  const bool ok = back_project(a.m[s], (double)kp.x, (double)kp.y, x, y);
+  const double z = 1.0;
+  a.rays[s][3 * i] = x; a.rays[s][3 * i + 1] = y; a.rays[s][3 * i + 2] = z;
+  a.valid[s][i] = ok ? 1 : 0;
+  const PrepArgs& p = a.p[s];
+  const double wx = (p.C[0] * x + p.C[1] * y) + p.C[2] * z;
+  const double wy = (p.C[3] * x + p.C[4] * y) + p.C[5] * z;
+  const double wz = (p.C[6] * x + p.C[7] * y) + p.C[8] * z;
+  const double n2 = (wx * wx + wy * wy) + wz * wz;
+  double ex = wx, ey = wy, ez = wz;
+  if (n2 > 0.0) { const double n = sqrt(n2); ex = wx / n; ey = wy / n; ez = wz / n; }
+  a.e_W[s][3 * i] = ex; a.e_W[s][3 * i + 1] = ey; a.e_W[s][3 * i + 2] = ez;
+  const double sz = (double)kp.size / p.f;
+  a.sof[s][i] = sz;
+  const double sigma = sz * 0.125;
+  a.c26[s][i] = gate_cos(2.6 * sigma); a.c6[s][i] = gate_cos(6.0 * sigma);   // == host libm, okb_gatecos.h
+}
+
+int camera_stereo_prep_pair(okb_context* ctx, const okb_camera_model_t* const model[2], const double* const C_WC[2], const okb_keypoint_t* const d_kp[2],
+                            const int32_t* const d_count[2], const int cap[2], int n_frames, double* const d_rays[2], uint8_t* const d_valid[2],
+                            double* const d_eW[2], double* const d_sof[2], double* const d_c26[2], double* const d_c6[2],
+                            unsigned long long* d_best, int32_t* d_hit_cnt, cudaStream_t st)
+{
+  PairPrep a;
+  for (int s = 0; s < 2; s++) {
+    a.m[s] = to_model(*model[s]);
+    for (int i = 0; i < 9; i++) a.p[s].C[i] = C_WC[s][i];
+    a.p[s].f = 0.5 * (model[s]->fu + model[s]->fv);
+    a.kp[s] = d_kp[s]; a.count[s] = d_count[s]; a.cap[s] = cap[s]; a.rays[s] = d_rays[s]; a.valid[s] = d_valid[s];
+    a.e_W[s] = d_eW[s]; a.sof[s] = d_sof[s]; a.c26[s] = d_c26[s]; a.c6[s] = d_c6[s];
+  }
+  a.best = d_best; a.hit_cnt = d_hit_cnt;
+  k_stereo_prep_pair<<<dim3((std::max(cap[0], cap[1]) + 127) / 128, n_frames, 2), 128, 0, st>>>(a);
+  ctx->launches++;
+  OKB_CUDA(cudaGetLastError());
+  return OKB_OK;
+}
+
 void k_backproject_ext(const Model& m, const okb_keypoint_t* d_kp, const int32_t* d_count, int cap, int n_frames, double* d_rays,
                        uint8_t* d_valid, cudaStream_t st)
 {

@@ -111,7 +111,7 @@ OKB_HD int b0_compute(const LayerView& l, int x, int y)
 // ... or read from the dense map the score pass has written (what refinement and tie resolution use)
 OKB_HD int b0(const LayerView& l, int x, int y)
 {
-  if (x < 3 || y < 3 || x >= l.w - 3 || y >= l.h - 3) return 0;
+  if ((unsigned)(x - 3) >= (unsigned)(l.w - 6) || (unsigned)(y - 3) >= (unsigned)(l.h - 6)) return 0;   // x < 3 || x >= w - 3 || ... (w, h >= 8)
   return l.b0[(size_t)y * l.bpitch + x];
 }
 OKB_HD int b0_58(const LayerView& l, int x, int y)

@@ -89,19 +89,21 @@ __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ DeviceLa
                                                 uint8_t* img_block, uint8_t* score_block, uint32_t* touch_block,
                                                 const uint32_t* cand, const int32_t* cand_count, int cand_cap,
                                                 const __grid_constant__ CandRegions cr, uint32_t* fkey, float4* fval, int threshold, const uint32_t* d_epoch,
-                                                const uint32_t* tie_cells, TieEntry* tie_list, int32_t* tie_count)
+                                                const uint32_t* tie_cells, TieEntry* tie_list, int32_t* tie_count, int cpw)
 {
+  // cpw candidates per warp (lanes cpw.. only help with the touch emission): 32 when the batch fills the GPU; fewer for a single
+  // frame, whose ~150 warps of 32 divergent candidates each would leave three quarters of the schedulers idle
   const int frame = blockIdx.y;
   int prefix[kMaxLayers + 1];
   const int n = cand_total(cr, cand_count + frame * kMaxLayers, dl.n, prefix);
-  if (blockIdx.x * blockDim.x >= n) return;
+  if ((int)blockIdx.x * 4 * cpw >= n) return;
   const uint32_t epoch = *d_epoch;
   __shared__ FrameViews v;  // dynamically indexed by layer: keep it out of local memory
   if (threadIdx.x == 0) make_views(dl, in0, in_pitch, in_frame_stride, img_block, score_block, touch_block, frame, v);
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const bool have = i < n;
+  const int i = ((int)blockIdx.x * 4 + (int)(threadIdx.x >> 5)) * cpw + lane;
+  const bool have = lane < cpw && i < n;
   uint32_t key = 0; int tie = 0;
   RefineResult r;
   r.keep = 0; r.own_touch = 0; r.has_above = 0; r.above.n_queries = 0; r.above.exited = 1; r.above.max_x = r.above.max_y = 0;
@@ -1042,7 +1044,7 @@ __global__ void __launch_bounds__(256) k_touch_clear(const uint32_t* epoch, uint
 }
 
 // all frames are device resident: d_images = n_frames x H x src_pitch
-int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch)
+int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch, cudaEvent_t input_ready)
 {
   CamWorkspace& ws = ctx->cams[cam];
   const okb_camera_config_t& c = ws.cfg;
@@ -1054,6 +1056,10 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   k_epoch_tick<<<1, 32, 0, st>>>(ws.d_epoch);
   k_touch_clear<<<296, 256, 0, st>>>(ws.d_epoch, ws.d_touch, (size_t)ws.dl.frame_stride * c.max_batch);
   ctx->launches += 2;
+  // one contiguous block holds the per-call counters: candidate counts, status words, tie counts, tie-cell bitmaps
+  OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, ws.zero_bytes, st));
+  // a caller that uploads the frames on another stream (okb_process_multiframe) lets the three nodes above run underneath the copy
+  if (input_ready) OKB_CUDA(cudaStreamWaitEvent(st, input_ready, 0));
   if (ctx->timers_on) cudaEventRecord(ws.ev[0], st);
   const size_t in_stride = (size_t)src_pitch * H;
   const int ipitch = W + 1;
@@ -1070,9 +1076,10 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   OKB_CUDA(cudaEventRecord(ws.ev_join, ws.stream2));
   if (ctx->timers_on) cudaEventRecord(ws.ev[1], st);
   // ---- candidates, refinement, tie resolution, selection
-  k_refine<<<dim3((ws.cand_cap + 127) / 128, B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
+  const int cpw = B >= 8 ? 32 : (B >= 4 ? 16 : 8);
+  k_refine<<<dim3((ws.cand_cap + 4 * cpw - 1) / (4 * cpw), B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
                                                                ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap, cr,
-                                                               ws.d_fkey, (float4*)ws.d_fval, c.threshold, ws.d_epoch, ws.d_tie_cells, ws.d_ties, ws.d_tie_count);
+                                                               ws.d_fkey, (float4*)ws.d_fval, c.threshold, ws.d_epoch, ws.d_tie_cells, ws.d_ties, ws.d_tie_count, cpw);
   k_tie_gather<<<dim3(kMaxTies / 128, B), 128, 0, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_ties, ws.d_tie_count, ws.d_epoch, c.threshold, ws.d_tie_sorted);
   k_resolve<<<B, kResolveThreads, kResolveSmem, st>>>(ws.d_tie_sorted, ws.d_tie_count, ws.d_fkey, ws.cand_cap, c.threshold, ws.d_status, ws.d_dbg);
   ctx->launches++;

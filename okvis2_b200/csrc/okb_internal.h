@@ -167,9 +167,13 @@ struct okb_context {
 namespace okb {
 int detect_init_camera(okb_context* ctx, int cam);
 void detect_free_camera(okb_context* ctx, int cam);
-int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch);
+int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch, cudaEvent_t input_ready = nullptr);
 int camera_backproject_batch(okb_context* ctx, int cam, int n_frames);
 struct Model;
+int camera_stereo_prep_pair(okb_context* ctx, const okb_camera_model_t* const model[2], const double* const C_WC[2], const okb_keypoint_t* const d_kp[2],
+                            const int32_t* const d_count[2], const int cap[2], int n_frames, double* const d_rays[2], uint8_t* const d_valid[2],
+                            double* const d_eW[2], double* const d_sof[2], double* const d_c26[2], double* const d_c6[2],
+                            unsigned long long* d_best, int32_t* d_hit_cnt, cudaStream_t st);
 void k_backproject_ext(const Model& m, const okb_keypoint_t* d_kp, const int32_t* d_count, int cap, int n_frames, double* d_rays,
                        uint8_t* d_valid, cudaStream_t st);   // D4 on explicit device blocks (okb_camera.cu)
 int camera_stereo_prep(okb_context* ctx, const okb_camera_model_t& model, const double C_WC[9], const okb_keypoint_t* d_kp,
@@ -202,10 +206,14 @@ inline cudaError_t wait_stream(okb_context* ctx, cudaStream_t st)
   return cudaEventSynchronize(ev);
 }
 // M3 sequence over the older keyframes with an explicit scratch area (okb_match.cu); the compaction of its matching entries
+int match_map3d_enqueue(okb_context* ctx, int cam, int D, int n_frames, int n_cand, const uint8_t* d_cand_desc, const int32_t* d_cand_lm, int n_lm,
+                        const double* d_lm_proj, const uint8_t* d_lm_is3d, double reprojection_threshold, uint32_t match_threshold,
+                        uint32_t* d_out_dist, int32_t* d_out_lm, cudaStream_t bin_stream, cudaEvent_t bin_done);
+int motion_restage(MotionScratch& ms, int n_frames, int n_older, const okb_older_view_t* older, int cap0, const double* T_WC1, const double* T_CW1);
 int motion_sequence(okb_context* ctx, MotionScratch& ms, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
                     const int32_t* d_count1, const okb_camera_model_t* model, int width, int height, const double* T_WC1, const double* T_CW1,
                     int n_older, const okb_older_view_t* older, int cap0, uint32_t match_threshold, cudaStream_t st, uint8_t* d_matched1,
-                    int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags);
+                    int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags, const double* d_rays1, const uint8_t* d_valid1);
 void m3_compact_launch(int n_frames, int cap0, int n_older, int cap_m, const int32_t* k1, const double* hp, const uint8_t* flags, int32_t* n_match,
                        int32_t* m_k0, int32_t* m_k1, uint8_t* m_flags, double* m_hp, cudaStream_t st);
 void prepare_free(okb_context* ctx);

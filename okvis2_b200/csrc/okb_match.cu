@@ -87,6 +87,10 @@ __device__ __forceinline__ double depth_in(const double* T, V3 p)
 // ---------------------------------------------------------------------------------------------------------------
 enum { MODE_M2 = 2, MODE_M3 = 3, MODE_M4 = 4 };
 
+// -1: small batches (up to 4 frames) run the gate / finish (/ check / commit) of M3 and M4 as ONE launch per view or pair
+// (k_pair_view, one CTA per frame); larger batches use the separate kernels. 0 / 1 force either form (okb_m3_set_fused).
+static std::atomic<int> g_m3_fused{-1};
+
 struct MatchArgs {
   int nq, nc;
   const uint8_t* q_desc; const uint8_t* c_desc;
@@ -241,19 +245,30 @@ __device__ __forceinline__ int m1_cell_of(const M1Args& a, double x, double y, i
   cy = fy < 0.0 ? 0 : (fy > (double)(a.gy - 1) ? a.gy - 1 : (int)fy);
   return cy * a.gx + cx;
 }
-// cell of a pool row for this frame: -1 = cannot match (not 3-D, or farther than thr outside the keypoint extent),
-// n_cells = NaN projection (passes the reference's gate against every keypoint)
-__device__ __forceinline__ int m1_row_cell(const M1Args& a, int frame, int r, double& px, double& py)
+// cell of a pool row for this frame from its landmark's projection: -1 = cannot match (farther than thr outside the keypoint
+// extent), n_cells = NaN projection (passes the reference's gate against every keypoint)
+__device__ __forceinline__ int m1_cell_from(const M1Args& a, double px, double py)
 {
-  const int lm = __ldg(&a.c_lm[r]);
-  if (!a.lm_is3d[lm]) return -1;
-  const double* lp = a.lm_proj + (size_t)frame * a.proj_stride + 2 * (size_t)lm;
-  px = lp[0]; py = lp[1];
   if (!(px == px) || !(py == py)) return a.gx * a.gy;
   const double m = a.thr_px + 1.0;
   if (!(px >= a.min_x - m && px <= a.max_x + m && py >= a.min_y - m && py <= a.max_y + m)) return -1;   // also +-inf
   int cx, cy;
   return m1_cell_of(a, px, py, cx, cy);
+}
+// cells and projections of four pool rows (r0, r0 + stride, ...): the three dependent loads of a row (landmark index -> is3d ->
+// projection) are issued for all four rows before any is consumed
+__device__ __forceinline__ void m1_rows4(const M1Args& a, int frame, int r0, int stride, int (&cell)[4], double (&px)[4], double (&py)[4])
+{
+  int lm[4]; bool ok[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++) { const int r = r0 + u * stride; lm[u] = r < a.nc ? __ldg(&a.c_lm[r]) : -1; }
+#pragma unroll
+  for (int u = 0; u < 4; u++) ok[u] = lm[u] >= 0 && a.lm_is3d[lm[u]] != 0;   // not 3-D: cannot match
+  const double* lp = a.lm_proj + (size_t)frame * a.proj_stride;
+#pragma unroll
+  for (int u = 0; u < 4; u++) { px[u] = ok[u] ? lp[2 * (size_t)lm[u]] : 0.0; py[u] = ok[u] ? lp[2 * (size_t)lm[u] + 1] : 0.0; }
+#pragma unroll
+  for (int u = 0; u < 4; u++) cell[u] = ok[u] ? m1_cell_from(a, px[u], py[u]) : -1;
 }
 
 __global__ void __launch_bounds__(1024) k_m1_rowbin(M1Args a)
@@ -263,10 +278,12 @@ __global__ void __launch_bounds__(1024) k_m1_rowbin(M1Args a)
   const int n_cells = a.gx * a.gy;
   for (int i = threadIdx.x; i <= n_cells + 1; i += blockDim.x) cnt[i] = 0;
   __syncthreads();
-  for (int r = threadIdx.x; r < a.nc; r += blockDim.x) {
-    double px, py;
-    const int c = m1_row_cell(a, frame, r, px, py);
-    if (c >= 0) atomicAdd(&cnt[c], 1);
+#pragma unroll 1
+  for (int r0 = threadIdx.x; r0 < a.nc; r0 += 4 * 1024) {
+    int c[4]; double px[4], py[4];
+    m1_rows4(a, frame, r0, 1024, c, px, py);
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (c[u] >= 0) atomicAdd(&cnt[c[u]], 1);
   }
   __syncthreads();
   // exclusive scan of the cell counts (<= 4097 cells): one warp, a contiguous chunk per lane
@@ -287,10 +304,13 @@ __global__ void __launch_bounds__(1024) k_m1_rowbin(M1Args a)
   __syncthreads();
   int32_t* list = a.row_list + (size_t)frame * a.nc;
   double2* xy = a.row_xy + (size_t)frame * a.nc;
-  for (int r = threadIdx.x; r < a.nc; r += blockDim.x) {
-    double px, py;
-    const int c = m1_row_cell(a, frame, r, px, py);
-    if (c >= 0) { const int pos = atomicAdd(&cnt[c], 1); list[pos] = r; xy[pos] = make_double2(px, py); }
+#pragma unroll 1
+  for (int r0 = threadIdx.x; r0 < a.nc; r0 += 4 * 1024) {
+    int c[4]; double px[4], py[4];
+    m1_rows4(a, frame, r0, 1024, c, px, py);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (c[u] >= 0) { const int pos = atomicAdd(&cnt[c[u]], 1); list[pos] = r0 + u * 1024; xy[pos] = make_double2(px[u], py[u]); }
   }
 }
 
@@ -365,9 +385,14 @@ static void m1_grid(double thr, double ext_x, double ext_y, int& cell, int& gx, 
   }
 }
 
-static int m1_launch(okb_context* ctx, M1Args& a, int D, int n_frames, cudaStream_t st)
+// bin_stream: the row binning only needs the pool and the projections, not the keypoints; a caller that has them early runs it
+// on a side stream (bin_done orders the match kernel behind it)
+static int m1_launch(okb_context* ctx, M1Args& a, int D, int n_frames, cudaStream_t st, cudaStream_t bin_stream = nullptr, cudaEvent_t bin_done = nullptr)
 {
-  if (a.nc > 0) k_m1_rowbin<<<n_frames, 1024, 0, st>>>(a);
+  if (a.nc > 0) {
+    k_m1_rowbin<<<n_frames, 1024, 0, bin_stream ? bin_stream : st>>>(a);
+    if (bin_stream) { OKB_CUDA(cudaEventRecord(bin_done, bin_stream)); OKB_CUDA(cudaStreamWaitEvent(st, bin_done, 0)); }
+  }
   if (D == 64) k_m1_match<4><<<dim3((a.nq + 7) / 8, n_frames), 256, 0, st>>>(a);
   else k_m1_match<3><<<dim3((a.nq + 7) / 8, n_frames), 256, 0, st>>>(a);
   ctx->launches += a.nc > 0 ? 2 : 1;
@@ -875,8 +900,8 @@ __global__ void __launch_bounds__(128) k_m3_commit(const __grid_constant__ M3Che
 // claim -> commit. Same device functions as k_m4_gate / k_m4_finish / k_m3_check / k_m3_commit; the phases are separated by block
 // barriers instead of kernel boundaries (the reductions go through L2 atomics and are read back with ld.cg). A frame whose hit
 // list overflowed is matched by brute force here (warp per query, candidates in ascending order by the min over (distance, k1)).
-template <int D16>
-__global__ void __launch_bounds__(512) k_m3_view(MatchArgs a, const __grid_constant__ M3Check c, const uint2* hits, unsigned long long* best)
+template <int D16, int MODE>
+__global__ void __launch_bounds__(512) k_pair_view(MatchArgs a, const __grid_constant__ M3Check c, const uint2* hits, unsigned long long* best)
 {
   const int frame = blockIdx.x;
   const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
@@ -885,17 +910,18 @@ __global__ void __launch_bounds__(512) k_m3_view(MatchArgs a, const __grid_const
     for (int i = threadIdx.x; i < n_hits; i += blockDim.x) {
       const uint2 e = hits[(size_t)frame * a.hit_cap + i];
       const int q = (int)(e.x & 0xfffffu), cc = (int)e.y;
-      if (m3_gate(a, fq, fc, q, cc).pass) atomicMin(&best[fq + q], ((unsigned long long)(e.x >> 20) << 32) | (unsigned)cc);
+      if (pair_gate<MODE>(a, fq, fc, q, cc).pass) atomicMin(&best[fq + q], ((unsigned long long)(e.x >> 20) << 32) | (unsigned)cc);
     }
   } else {
-    const M3View& view = a.views[(size_t)frame * a.view_stride + a.view_index];
-    const int nq = min(view.n, a.nq), nc = min(a.c_count[frame], a.nc);
+    const M3View* view = MODE == MODE_M3 ? &a.views[(size_t)frame * a.view_stride + a.view_index] : nullptr;
+    const int nq = view ? min(view->n, a.nq) : min(a.q_count[frame], a.nq), nc = min(a.c_count[frame], a.nc);
+    const uint4* q_desc = view ? reinterpret_cast<const uint4*>(view->desc) : reinterpret_cast<const uint4*>(a.q_desc) + fq * D16;
     const int lane = threadIdx.x & 31;
     for (int q = threadIdx.x >> 5; q < nq; q += blockDim.x >> 5) {
       if (a.q_use && !a.q_use[fq + q]) continue;
       uint4 qd[D16];
 #pragma unroll
-      for (int w = 0; w < D16; w++) qd[w] = __ldg(reinterpret_cast<const uint4*>(view.desc) + (size_t)q * D16 + w);
+      for (int w = 0; w < D16; w++) qd[w] = __ldg(q_desc + (size_t)q * D16 + w);
       unsigned long long mine = ~0ull;
       for (int cc = lane; cc < nc; cc += 32) {
         if (!a.c_valid[fc + cc]) continue;
@@ -905,7 +931,7 @@ __global__ void __launch_bounds__(512) k_m3_view(MatchArgs a, const __grid_const
           const uint4 cv = __ldg(reinterpret_cast<const uint4*>(a.c_desc) + (fc + cc) * D16 + w);
           d += __popc(qd[w].x ^ cv.x) + __popc(qd[w].y ^ cv.y) + __popc(qd[w].z ^ cv.z) + __popc(qd[w].w ^ cv.w);
         }
-        if (d < a.thr && m3_gate(a, fq, fc, q, cc).pass) mine = min(mine, ((unsigned long long)d << 32) | (unsigned)cc);
+        if (d < a.thr && pair_gate<MODE>(a, fq, fc, q, cc).pass) mine = min(mine, ((unsigned long long)d << 32) | (unsigned)cc);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
@@ -914,9 +940,10 @@ __global__ void __launch_bounds__(512) k_m3_view(MatchArgs a, const __grid_const
   }
   __syncthreads();
   for (int q = threadIdx.x; q < a.nq; q += blockDim.x) {
-    m4_finish_one<MODE_M3>(a, __ldcg(&best[fq + q]), frame, q);
-    c.flags[fq + q] = m3_check_one(c, frame, q);   // reads the outputs this thread has just written
+    m4_finish_one<MODE>(a, __ldcg(&best[fq + q]), frame, q);
+    if (MODE == MODE_M3) c.flags[fq + q] = m3_check_one(c, frame, q);   // reads the outputs this thread has just written
   }
+  if (MODE != MODE_M3) return;
   __syncthreads();
   for (int q = threadIdx.x; q < a.nq; q += blockDim.x) {
     const uint8_t fl = c.flags[fq + q];
@@ -1269,6 +1296,17 @@ int okb_match_map3d_device(okb_context_t* ctx, int cam, int D, int n_frames, int
                            const int32_t* d_cand_lm, int n_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
                            double reprojection_threshold, uint32_t match_threshold, uint32_t* d_out_dist, int32_t* d_out_lm)
 {
+  return okb::match_map3d_enqueue(ctx, cam, D, n_frames, n_cand, d_cand_desc, d_cand_lm, n_lm, d_lm_proj, d_lm_is3d, reprojection_threshold,
+                                  match_threshold, d_out_dist, d_out_lm, nullptr, nullptr);
+}
+
+}  // extern "C"
+
+int okb::match_map3d_enqueue(okb_context_t* ctx, int cam, int D, int n_frames, int n_cand, const uint8_t* d_cand_desc,
+                             const int32_t* d_cand_lm, int n_lm, const double* d_lm_proj, const uint8_t* d_lm_is3d,
+                             double reprojection_threshold, uint32_t match_threshold, uint32_t* d_out_dist, int32_t* d_out_lm,
+                             cudaStream_t bin_stream, cudaEvent_t bin_done)
+{
   OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams && n_cand >= 0 && n_lm >= 0 && d_out_dist && d_out_lm, "okb_match_map3d_device");
   CamWorkspace& ws = ctx->cams[cam];
   if (D != ws.cfg.descriptor_bytes) {   // the pool rows must have the stride of the camera's own descriptors (the queries)
@@ -1301,8 +1339,10 @@ int okb_match_map3d_device(okb_context_t* ctx, int cam, int D, int n_frames, int
     a.row_off = (int32_t*)ws.d_m1_rows; a.row_list = (int32_t*)(ws.d_m1_rows + off_b); a.row_xy = (double2*)(ws.d_m1_rows + off_b + list_b);
   }
   a.out_dist = d_out_dist; a.out_idx = d_out_lm;
-  return m1_launch(ctx, a, D, n_frames, ws.stream);
+  return m1_launch(ctx, a, D, n_frames, ws.stream, bin_stream, bin_done);
 }
+
+extern "C" {
 
 // T_CW = T_WC.inverse() = [C^T | -(C^T r)] as row-major 3x4 (kinematics/implementation/Transformation.hpp:207-209)
 static void invert_pose(const double C[9], const double r[3], double T[12])
@@ -1342,10 +1382,18 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
   double *rays0 = base, *eW0 = rays0 + 3 * n0, *sof0 = eW0 + 3 * n0, *c26_0 = sof0 + n0, *c6_0 = c26_0 + n0;
   double *rays1 = c6_0 + n0, *eW1 = rays1 + 3 * n1, *sof1 = eW1 + 3 * n1, *c26_1 = sof1 + n1, *c6_1 = c26_1 + n1;
   uint8_t* valid0 = (uint8_t*)(c6_1 + n1); uint8_t* valid1 = valid0 + ((n0 + 7) & ~(size_t)7);
-  int rc = okb::camera_stereo_prep(ctx, *model0, C_WC0, d_kp0, d_count0, cap0, n_frames, rays0, valid0, eW0, sof0, c26_0, c6_0, st);
-  if (rc) return rc;
-  rc = okb::camera_stereo_prep(ctx, *model1, C_WC1, d_kp1, d_count1, cap1, n_frames, rays1, valid1, eW1, sof1, c26_1, c6_1, st);
-  if (rc) return rc;
+  unsigned long long* best = (unsigned long long*)((uint8_t*)ctx->stereo_scratch + need_prep);
+  uint2* hits = (uint2*)(best + n0);
+  int32_t* hit_cnt = (int32_t*)(hits + (size_t)n_frames * hit_cap);
+  {
+    // D4 + world-frame tables of both sides and the reset of the reduction arrays: one launch
+    const okb_camera_model_t* const models[2] = {model0, model1}; const double* const Cs[2] = {C_WC0, C_WC1};
+    const okb_keypoint_t* const kps[2] = {d_kp0, d_kp1}; const int32_t* const counts[2] = {d_count0, d_count1}; const int caps[2] = {cap0, cap1};
+    double* const rays[2] = {rays0, rays1}; uint8_t* const valids[2] = {valid0, valid1}; double* const eWs[2] = {eW0, eW1};
+    double* const sofs[2] = {sof0, sof1}; double* const c26s[2] = {c26_0, c26_1}; double* const c6s[2] = {c6_0, c6_1};
+    const int rc = okb::camera_stereo_prep_pair(ctx, models, Cs, kps, counts, caps, n_frames, rays, valids, eWs, sofs, c26s, c6s, best, hit_cnt, st);
+    if (rc) return rc;
+  }
   MatchArgs a; memset(&a, 0, sizeof(a));
   a.nq = cap0; a.nc = cap1; a.q_stride = (size_t)cap0; a.c_stride = (size_t)cap1; a.q_count = d_count0; a.c_count = d_count1;
   a.q_desc = d_desc0; a.c_desc = d_desc1; a.q_use = valid0; a.q_e = eW0; a.q_sof = sof0; a.q_cos26 = c26_0; a.q_cos6 = c6_0;
@@ -1354,17 +1402,21 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
   invert_pose(C_WC0, r_WC0, a.T0); invert_pose(C_WC1, r_WC1, a.T1);
   a.thr = match_threshold;
   a.out_dist = d_out_dist; a.out_idx = d_out_k1; a.out_hp = d_out_hp_W; a.out_init = d_out_initialisable;
-  unsigned long long* best = (unsigned long long*)((uint8_t*)ctx->stereo_scratch + need_prep);
-  uint2* hits = (uint2*)(best + n0);
-  int32_t* hit_cnt = (int32_t*)(hits + (size_t)n_frames * hit_cap);
   a.hit_cnt = hit_cnt; a.hit_cap = hit_cap;
-  OKB_CUDA(cudaMemsetAsync(best, 0xff, n0 * 8, st));
-  OKB_CUDA(cudaMemsetAsync(hit_cnt, 0, (size_t)n_frames * 4, st));
-  k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, (cap0 + 127) / 128), 256, 0, st>>>(a, hits, hit_cnt);
-  k_m4_gate<MODE_M4><<<dim3(8, n_frames), 128, 0, st>>>(a, hits, best);
-  k_m4_finish<MODE_M4><<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(a, best);
-  k_match_gated<4, MODE_M4><<<dim3((cap0 + 7) / 8, n_frames), 256, 0, st>>>(a);   // only frames whose hit list overflowed
-  ctx->launches += 4;
+  const int fused_mode = g_m3_fused.load();
+  const bool fused = fused_mode >= 0 ? fused_mode != 0 : n_frames <= 4;
+  a.scan_qt = fused ? 32 : 128;   // small batches: short query chunks so that one frame's scan still spreads over the SMs
+  k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, (cap0 + a.scan_qt - 1) / a.scan_qt), 256, 0, st>>>(a, hits, hit_cnt);
+  if (fused) {
+    M3Check none; memset(&none, 0, sizeof(none));
+    k_pair_view<4, MODE_M4><<<n_frames, 512, 0, st>>>(a, none, hits, best);
+    ctx->launches += 2;
+  } else {
+    k_m4_gate<MODE_M4><<<dim3(8, n_frames), 128, 0, st>>>(a, hits, best);
+    k_m4_finish<MODE_M4><<<dim3((cap0 + 127) / 128, n_frames), 128, 0, st>>>(a, best);
+    k_match_gated<4, MODE_M4><<<dim3((cap0 + 7) / 8, n_frames), 256, 0, st>>>(a);   // only frames whose hit list overflowed
+    ctx->launches += 4;
+  }
   OKB_CUDA(cudaGetLastError());
   return OKB_OK;
 }
@@ -1401,19 +1453,42 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
   OKB_CHECK_ARGS(ctx, "okb_match_motion_stereo_device_ptr");
   // one scratch area per context for this form: calls of one context must be issued on streams that serialise them
   return okb::motion_sequence(ctx, ctx->motion, n_frames, cap1, d_kp1, d_desc1, d_count1, model, width, height, T_WC1, T_CW1, n_older, older, cap0,
-                              match_threshold, stream ? (cudaStream_t)stream : MW.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags);
+                              match_threshold, stream ? (cudaStream_t)stream : MW.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags, nullptr, nullptr);
 }
 
 }  // extern "C"
 
-// -1: one launch per view (k_m3_view) for batches of up to 4 frames, separate kernels above; 0 / 1 force either form
-static std::atomic<int> g_m3_fused{-1};
+static void fill_m3_tables(M3View* hv, M3Frame* hf, int n_frames, int n_older, const okb_older_view_t* older, const double* T_WC1, const double* T_CW1)
+{
+  for (size_t i = 0; i < (size_t)n_frames * n_older; i++) {
+    const okb_older_view_t& s = older[i];
+    hv[i].desc = s.d_desc; hv[i].rays = s.d_rays; hv[i].valid = s.d_valid; hv[i].size = s.d_size; hv[i].use = s.d_use; hv[i].n = s.n; hv[i].pad = 0;
+    memcpy(hv[i].Twc, s.T_WC, sizeof(hv[i].Twc)); memcpy(hv[i].Tcw, s.T_CW, sizeof(hv[i].Tcw));
+  }
+  for (int b = 0; b < n_frames; b++) { memcpy(hf[b].Twc, T_WC1 + 12 * (size_t)b, 96); memcpy(hf[b].Tcw, T_CW1 + 12 * (size_t)b, 96); }
+}
+
+// CUDA-graph callers (okb_process_multiframe): the captured copy node re-reads the scratch's page-locked tables at every replay,
+// so they are refreshed here, per multiframe, without enqueuing anything. Same argument checks as motion_sequence.
+int okb::motion_restage(MotionScratch& ms, int n_frames, int n_older, const okb_older_view_t* older, int cap0, const double* T_WC1, const double* T_CW1)
+{
+  if (n_older == 0) return OKB_OK;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t b_views = al(sizeof(M3View) * n_frames * n_older), b_frames = al(sizeof(M3Frame) * n_frames);
+  OKB_CHECK_ARGS(ms.h && ms.pinned_staging && b_views + b_frames <= ms.h_cap && older && T_WC1 && T_CW1, "motion_restage");
+  for (int i = 0; i < n_frames * n_older; i++)
+    OKB_CHECK_ARGS(older[i].n >= 0 && older[i].n <= cap0 && (older[i].n == 0 || (older[i].d_desc && older[i].d_rays && older[i].d_valid && older[i].d_size)),
+                   "okb_process_multiframe (older view)");
+  fill_m3_tables((M3View*)ms.h, (M3Frame*)((uint8_t*)ms.h + b_views), n_frames, n_older, older, T_WC1, T_CW1);
+  return OKB_OK;
+}
+
 extern "C" void okb_m3_set_fused(int mode) { g_m3_fused.store(mode < 0 ? -1 : (mode ? 1 : 0)); }
 
 int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
                          const int32_t* d_count1, const okb_camera_model_t* model, int width, int height, const double* T_WC1, const double* T_CW1,
                          int n_older, const okb_older_view_t* older, int cap0, uint32_t match_threshold, cudaStream_t st, uint8_t* d_matched1,
-                         int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags)
+                         int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags, const double* d_rays1, const uint8_t* d_valid1)
 {
   OKB_CHECK_ARGS(ctx && n_frames >= 1 && cap1 > 0 && cap1 < (1 << 20) && d_kp1 && d_desc1 && d_count1 && model && T_WC1 && T_CW1 &&
                  n_older >= 0 && (n_older == 0 || older) && cap0 > 0 && cap0 < (1 << 20) && d_matched1 && d_out_k1 && d_out_dist &&
@@ -1461,17 +1536,12 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
   uint8_t* hb = ms.pinned_staging ? (uint8_t*)ms.h : hbuf_.data();
   M3View* hv = (M3View*)hb;
   M3Frame* hf = (M3Frame*)(hb + b_views);
-  for (size_t i = 0; i < (size_t)n_frames * n_older; i++) {
-    const okb_older_view_t& s = older[i];
-    hv[i].desc = s.d_desc; hv[i].rays = s.d_rays; hv[i].valid = s.d_valid; hv[i].size = s.d_size; hv[i].use = s.d_use; hv[i].n = s.n; hv[i].pad = 0;
-    memcpy(hv[i].Twc, s.T_WC, sizeof(hv[i].Twc)); memcpy(hv[i].Tcw, s.T_CW, sizeof(hv[i].Tcw));
-  }
-  for (int b = 0; b < n_frames; b++) { memcpy(hf[b].Twc, T_WC1 + 12 * (size_t)b, 96); memcpy(hf[b].Tcw, T_CW1 + 12 * (size_t)b, 96); }
+  fill_m3_tables(hv, hf, n_frames, n_older, older, T_WC1, T_CW1);
   OKB_CUDA(cudaMemcpyAsync(d_views, hb, b_views + sizeof(M3Frame) * (size_t)n_frames, cudaMemcpyHostToDevice, st));
   const Model cam = to_model(*model);
-  // D4 of the current keypoints (Frame::computeBackProjections)
-  k_backproject_ext(cam, d_kp1, d_count1, cap1, n_frames, rays1, valid1, st);
-  ctx->launches++;
+  // D4 of the current keypoints (Frame::computeBackProjections), unless the caller has them already (the detector's own, same model)
+  if (d_rays1 && d_valid1) { rays1 = const_cast<double*>(d_rays1); valid1 = const_cast<uint8_t*>(d_valid1); }
+  else { k_backproject_ext(cam, d_kp1, d_count1, cap1, n_frames, rays1, valid1, st); ctx->launches++; }
   // ---- once per sequence: tables of all views + the candidate mask, then the Hamming scan of all views (the scan does not depend
   //      on what earlier views insert: it keeps every pair below the threshold whose candidate is unmatched NOW; the gate of
   //      view v re-tests the mask as views 0..v-1 left it)
@@ -1512,7 +1582,7 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
     c.k1 = a.out_idx; c.dist = a.out_dist; c.hp = a.out_hp; c.init = a.out_init; c.flags = d_out_flags + vo;
     c.claim = claim + (size_t)v * n1; c.matched1 = d_matched1; c.cvalid = cvalid;
     if (fused) {
-      k_m3_view<4><<<n_frames, 512, 0, st>>>(a, c, hits_v, best_v);
+      k_pair_view<4, MODE_M3><<<n_frames, 512, 0, st>>>(a, c, hits_v, best_v);
       ctx->launches++;
     } else {
       // gate per hit -> outputs; a frame whose hit list overflows is redone by the sequential-replay kernel (which returns at
@@ -1540,7 +1610,7 @@ int okb_match_motion_stereo_device(okb_context_t* ctx, int cam, int n_frames, co
   OKB_CHECK_ARGS(ws.has_model && n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_motion_stereo_device (camera model set? okb_set_camera_model)");
   // per-camera scratch: the sequences of different cameras run concurrently on their own streams
   return okb::motion_sequence(ctx, ws.motion, n_frames, ws.kp_cap, ws.d_kp, ws.d_desc, ws.d_count, &ws.model, ws.cfg.width, ws.cfg.height, T_WC1, T_CW1,
-                              n_older, older, cap0, match_threshold, ws.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags);
+                              n_older, older, cap0, match_threshold, ws.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags, ws.d_rays, ws.d_rays_valid);
 }
 
 int okb_matched_mask_device(okb_context_t* ctx, int cam, int n_frames, const int32_t* d_lm, uint8_t* d_matched)

@@ -638,8 +638,6 @@ int pyramid_score_run(okb_context* ctx, CamWorkspace& ws, const uint8_t* d_image
     OKB_CUDA(cudaMemcpy(ws.d_tiles, tab.data(), tab.size() * sizeof(TileEntry), cudaMemcpyHostToDevice));
   }
   const int n_items = ws.n_tiles * B;
-  // one contiguous block holds the per-call counters: candidate counts, status words, tie-cell bitmaps
-  OKB_CUDA(cudaMemsetAsync(ws.d_cand_count, 0, ws.zero_bytes, st));
   TmaMaps maps;
   build_tma_maps(ws, d_images, src_pitch, in_stride, c.max_batch, TH, maps);
   if (!g_sm_count) {

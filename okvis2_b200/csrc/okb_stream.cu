@@ -15,6 +15,8 @@
 
 #include <vector>
 
+#include <chrono>
+
 #include "okb_internal.h"
 
 namespace okb {
@@ -32,11 +34,14 @@ struct StreamState {
   std::vector<CamArena> cams;
   std::vector<PairArena> pairs;
   std::vector<cudaEvent_t> ev;       // fork / join events (per camera + 1)
+  std::vector<cudaStream_t> side;    // per camera: copies and the M1 row binning next to the detector; [n_cams]: the stereo pairs
+  std::vector<cudaEvent_t> ev_img, ev_bin, ev_det, ev_side;   // per camera: binning done, features ready, side stream done; ev_side[n_cams]: pairs done
   cudaGraphExec_t exec = nullptr;
   uint64_t sig = 0; int sig_seen = 0;
   int use_graph = 1;
   long long graph_launches = 0, direct_calls = 0;
   int64_t launches_per_graph = 0;
+  double t_stage = 0, t_submit = 0, t_wait = 0, t_out = 0;   // host seconds spent per phase (okb_stream_timing)
 };
 
 StreamState* state(okb_context* ctx)
@@ -61,7 +66,8 @@ void stream_free(okb_context* ctx)
   if (s->exec) cudaGraphExecDestroy(s->exec);
   for (auto& a : s->cams) { cudaFree(a.d); if (a.h) cudaFreeHost(a.h); }
   for (auto& a : s->pairs) { cudaFree(a.d); if (a.h) cudaFreeHost(a.h); }
-  for (auto e : s->ev) if (e) cudaEventDestroy(e);
+  for (auto* v : {&s->ev, &s->ev_img, &s->ev_bin, &s->ev_det, &s->ev_side}) for (auto e : *v) if (e) cudaEventDestroy(e);
+  for (auto st : s->side) if (st) cudaStreamDestroy(st);
   delete s;
   ctx->stream_state = nullptr;
 }
@@ -89,6 +95,15 @@ int okb_stream_stats(okb_context_t* ctx, long long* graph_launches, long long* d
   return OKB_OK;
 }
 
+int okb_stream_timing(okb_context_t* ctx, double* seconds4, int reset)
+{
+  if (!ctx || !seconds4) { set_error("okb_stream_timing: bad arguments"); return OKB_ERR_ARGUMENT; }
+  StreamState* s = state(ctx);
+  seconds4[0] = s->t_stage; seconds4[1] = s->t_submit; seconds4[2] = s->t_wait; seconds4[3] = s->t_out;
+  if (reset) s->t_stage = s->t_submit = s->t_wait = s->t_out = 0;
+  return OKB_OK;
+}
+
 int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t* io, int n_pairs, okb_multiframe_stereo_t* pairs,
                            double reprojection_threshold, uint32_t match_threshold)
 {
@@ -97,6 +112,9 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
   }
   OKB_CUDA(cudaSetDevice(ctx->device));
   StreamState* S = state(ctx);
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  const auto t0 = now();
   // ---- validation, arenas, staging of the inputs
   uint64_t sig = mix(mix(0x51ed270b, n_cams), n_pairs);
   sig = mix(mix(sig, match_threshold), (uint64_t)(reprojection_threshold * 1024.0));
@@ -117,8 +135,10 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       const int no = q.n_older > 0 ? q.n_older : 1, c0 = q.cap0 > 0 ? q.cap0 : 1, cm = q.cap_m > 0 ? q.cap_m : 1;
       size_t o = 0; auto take = [&](size_t b) { const size_t r = o; o += al(b); return r; };
       A.o_desc = take((size_t)q.n_cand * 64); A.o_lm = take((size_t)q.n_cand * 4); A.o_3d = take((size_t)q.n_lm); A.o_proj = take((size_t)q.n_lm * 16);
-      A.o_m1d = take((size_t)cap * 4); A.o_m1l = take((size_t)cap * 4); A.o_mask = take((size_t)cap);
+      A.o_mask = take((size_t)cap);
       A.o_k1 = take((size_t)no * c0 * 4); A.o_dist = take((size_t)no * c0 * 4); A.o_hp = take((size_t)no * c0 * 32); A.o_fl = take((size_t)no * c0);
+      // what the host reads back, contiguous (one copy): M1 results, M3 counts and compact lists
+      A.o_m1d = take((size_t)cap * 4); A.o_m1l = take((size_t)cap * 4);
       A.o_n = take((size_t)no * 4); A.o_mk0 = take((size_t)no * cm * 4); A.o_mk1 = take((size_t)no * cm * 4); A.o_mf = take((size_t)no * cm);
       A.o_mhp = take((size_t)no * cm * 32); A.o_pose = take(192); A.end = o;
       if (o > A.cap) {
@@ -170,72 +190,106 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
     sig = mix_bytes(sig, P.C_WC0, 72); sig = mix_bytes(sig, P.r_WC0, 24); sig = mix_bytes(sig, P.C_WC1, 72); sig = mix_bytes(sig, P.r_WC1, 24);
   }
   for (auto& e : S->ev) if (!e) OKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (S->side.empty()) {
+    S->side.resize(n_cams + 1, nullptr); S->ev_img.resize(n_cams, nullptr); S->ev_bin.resize(n_cams, nullptr); S->ev_det.resize(n_cams, nullptr); S->ev_side.resize(n_cams + 1, nullptr);
+    for (auto& st : S->side) OKB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto* v : {&S->ev_img, &S->ev_bin, &S->ev_det, &S->ev_side}) for (auto& e : *v) OKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   cudaStream_t origin = ctx->cams[0].stream;
 
   // ---- the launch sequence of one multiframe (identical in direct and in captured form)
+  // Streams: every camera's detector and matchers on its own stream; next to it a side stream that carries what is not on the
+  // critical path (the projections' upload and the M1 row binning while the detector runs, the download of the features while the
+  // matchers run); the stereo pairs on a stream of their own as soon as both cameras' features exist, next to M1 / M3.
   auto enqueue = [&]() -> int {
     OKB_CUDA(cudaEventRecord(S->ev[n_cams], origin));   // fork
     for (int c = 0; c < n_cams; c++) {
       okb_multiframe_cam_t& q = io[c];
       CamWorkspace& ws = ctx->cams[c];
       CamArena& A = S->cams[c];
-      cudaStream_t st = ws.stream;
+      cudaStream_t st = ws.stream, sd = S->side[c];
       const int W = ws.cfg.width, H = ws.cfg.height, cap = ws.kp_cap;
       if (c > 0) OKB_CUDA(cudaStreamWaitEvent(st, S->ev[n_cams], 0));
-      OKB_CUDA(cudaMemcpyAsync(ws.d_in, ws.h_img, (size_t)W * H, cudaMemcpyHostToDevice, st));
-      int rc = detect_run_device(ctx, c, 1, ws.d_in, W);
+      OKB_CUDA(cudaStreamWaitEvent(sd, S->ev[n_cams], 0));
+      // the frame goes up on the side stream while the detector's stream resets its counters
+      OKB_CUDA(cudaMemcpyAsync(ws.d_in, ws.h_img, (size_t)W * H, cudaMemcpyHostToDevice, sd));
+      OKB_CUDA(cudaEventRecord(S->ev_img[c], sd));
+      if (q.n_cand > 0) OKB_CUDA(cudaMemcpyAsync(A.d + A.o_proj, A.h + A.o_proj, (size_t)q.n_lm * 16, cudaMemcpyHostToDevice, sd));
+      int rc = detect_run_device(ctx, c, 1, ws.d_in, W, S->ev_img[c]);
       if (rc) return rc;
-      OKB_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, 4, cudaMemcpyDeviceToHost, st));
-      OKB_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, 4, cudaMemcpyDeviceToHost, st));
-      OKB_CUDA(cudaMemcpyAsync(ws.h_kp, ws.d_kp, (size_t)cap * sizeof(okb_keypoint_t), cudaMemcpyDeviceToHost, st));
-      OKB_CUDA(cudaMemcpyAsync(ws.h_desc, ws.d_desc, (size_t)cap * 64, cudaMemcpyDeviceToHost, st));
-      if (ws.has_model) {
-        OKB_CUDA(cudaMemcpyAsync(ws.h_rays, ws.d_rays, (size_t)cap * 24, cudaMemcpyDeviceToHost, st));
-        OKB_CUDA(cudaMemcpyAsync(ws.h_rays_valid, ws.d_rays_valid, (size_t)cap, cudaMemcpyDeviceToHost, st));
-      }
+      OKB_CUDA(cudaEventRecord(S->ev_det[c], st));
       if (q.n_cand > 0) {
-        OKB_CUDA(cudaMemcpyAsync(A.d + A.o_proj, A.h + A.o_proj, (size_t)q.n_lm * 16, cudaMemcpyHostToDevice, st));
-        rc = okb_match_map3d_device(ctx, c, 64, 1, q.n_cand, A.d + A.o_desc, (const int32_t*)(A.d + A.o_lm), q.n_lm, (const double*)(A.d + A.o_proj),
-                                    A.d + A.o_3d, reprojection_threshold, match_threshold, (uint32_t*)(A.d + A.o_m1d), (int32_t*)(A.d + A.o_m1l));
+        rc = match_map3d_enqueue(ctx, c, 64, 1, q.n_cand, A.d + A.o_desc, (const int32_t*)(A.d + A.o_lm), q.n_lm, (const double*)(A.d + A.o_proj),
+                                 A.d + A.o_3d, reprojection_threshold, match_threshold, (uint32_t*)(A.d + A.o_m1d), (int32_t*)(A.d + A.o_m1l), sd, S->ev_bin[c]);
         if (rc) return rc;
-        OKB_CUDA(cudaMemcpyAsync(A.h + A.o_m1d, A.d + A.o_m1d, (size_t)cap * 4, cudaMemcpyDeviceToHost, st));
-        OKB_CUDA(cudaMemcpyAsync(A.h + A.o_m1l, A.d + A.o_m1l, (size_t)cap * 4, cudaMemcpyDeviceToHost, st));
       }
+      // features to the host on the side stream, underneath the matchers
+      OKB_CUDA(cudaStreamWaitEvent(sd, S->ev_det[c], 0));
+      OKB_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, 4, cudaMemcpyDeviceToHost, sd));
+      OKB_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, 4, cudaMemcpyDeviceToHost, sd));
+      OKB_CUDA(cudaMemcpyAsync(ws.h_kp, ws.d_kp, (size_t)cap * sizeof(okb_keypoint_t), cudaMemcpyDeviceToHost, sd));
+      OKB_CUDA(cudaMemcpyAsync(ws.h_desc, ws.d_desc, (size_t)cap * 64, cudaMemcpyDeviceToHost, sd));
+      if (ws.has_model) {
+        OKB_CUDA(cudaMemcpyAsync(ws.h_rays, ws.d_rays, (size_t)cap * 24, cudaMemcpyDeviceToHost, sd));
+        OKB_CUDA(cudaMemcpyAsync(ws.h_rays_valid, ws.d_rays_valid, (size_t)cap, cudaMemcpyDeviceToHost, sd));
+      }
+      OKB_CUDA(cudaEventRecord(S->ev_side[c], sd));
       if (q.n_older > 0) {
         if (q.n_cand > 0) { rc = okb_matched_mask_device(ctx, c, 1, (const int32_t*)(A.d + A.o_m1l), A.d + A.o_mask); if (rc) return rc; }
         else OKB_CUDA(cudaMemsetAsync(A.d + A.o_mask, 0, (size_t)cap, st));
         ws.motion.pinned_staging = 1;   // tables through the page-locked mirror: a captured copy node re-reads it at every replay
         rc = motion_sequence(ctx, ws.motion, 1, cap, ws.d_kp, ws.d_desc, ws.d_count, &ws.model, W, H, (const double*)(A.h + A.o_pose),
                              (const double*)(A.h + A.o_pose + 96), q.n_older, q.older, q.cap0, match_threshold, st, A.d + A.o_mask,
-                             (int32_t*)(A.d + A.o_k1), (uint32_t*)(A.d + A.o_dist), (double*)(A.d + A.o_hp), A.d + A.o_fl);
+                             (int32_t*)(A.d + A.o_k1), (uint32_t*)(A.d + A.o_dist), (double*)(A.d + A.o_hp), A.d + A.o_fl, ws.d_rays, ws.d_rays_valid);
         if (rc) return rc;
         m3_compact_launch(1, q.cap0, q.n_older, q.cap_m, (const int32_t*)(A.d + A.o_k1), (const double*)(A.d + A.o_hp), A.d + A.o_fl,
                           (int32_t*)(A.d + A.o_n), (int32_t*)(A.d + A.o_mk0), (int32_t*)(A.d + A.o_mk1), A.d + A.o_mf, (double*)(A.d + A.o_mhp), st);
         ctx->launches++;
-        OKB_CUDA(cudaMemcpyAsync(A.h + A.o_n, A.d + A.o_n, A.o_pose - A.o_n, cudaMemcpyDeviceToHost, st));   // counts + compact lists (contiguous)
+      }
+      // M1 results + M3 counts and compact lists: contiguous in the arena, one copy
+      if (q.n_cand > 0 || q.n_older > 0) {
+        const size_t lo = q.n_cand > 0 ? A.o_m1d : A.o_n, hi = q.n_older > 0 ? A.o_pose : A.o_n;
+        OKB_CUDA(cudaMemcpyAsync(A.h + lo, A.d + lo, hi - lo, cudaMemcpyDeviceToHost, st));
       }
       OKB_CUDA(cudaEventRecord(S->ev[c], st));
     }
-    // M4 of the overlapping pairs on the first camera's stream (one scratch area per context), features stay on the device
-    for (int c = 1; c < n_cams; c++) OKB_CUDA(cudaStreamWaitEvent(origin, S->ev[c], 0));   // join (also orders the pairs behind every camera)
+    // M4 of the overlapping pairs on their own stream (one scratch area per context), features stay on the device
+    cudaStream_t sp = S->side[n_cams];
+    OKB_CUDA(cudaStreamWaitEvent(sp, S->ev[n_cams], 0));
     for (int p = 0; p < n_pairs; p++) {
       const okb_multiframe_stereo_t& P = pairs[p];
       CamWorkspace& w0 = ctx->cams[P.cam0]; CamWorkspace& w1 = ctx->cams[P.cam1];
       PairArena& A = S->pairs[p];
       const size_t n = (size_t)w0.kp_cap;
       uint8_t* d = A.d; const size_t o_k1 = 0, o_d = al(n * 4), o_hp = 2 * al(n * 4), o_in = o_hp + al(n * 32);
+      OKB_CUDA(cudaStreamWaitEvent(sp, S->ev_det[P.cam0], 0));
+      OKB_CUDA(cudaStreamWaitEvent(sp, S->ev_det[P.cam1], 0));
       int rc = okb_match_stereo_device_ptr(ctx, 1, w0.kp_cap, w0.d_kp, w0.d_desc, w0.d_count, &w0.model, P.C_WC0, P.r_WC0, w1.kp_cap, w1.d_kp, w1.d_desc,
-                                           w1.d_count, &w1.model, P.C_WC1, P.r_WC1, match_threshold, (void*)origin, (int32_t*)(d + o_k1),
+                                           w1.d_count, &w1.model, P.C_WC1, P.r_WC1, match_threshold, (void*)sp, (int32_t*)(d + o_k1),
                                            (uint32_t*)(d + o_d), (double*)(d + o_hp), d + o_in);
       if (rc) return rc;
-      OKB_CUDA(cudaMemcpyAsync(A.h, A.d, o_in + al(n), cudaMemcpyDeviceToHost, origin));
+      OKB_CUDA(cudaMemcpyAsync(A.h, A.d, o_in + al(n), cudaMemcpyDeviceToHost, sp));
     }
+    OKB_CUDA(cudaEventRecord(S->ev_side[n_cams], sp));
+    // join: every stream back into the origin
+    for (int c = 0; c < n_cams; c++) {
+      if (c > 0) OKB_CUDA(cudaStreamWaitEvent(origin, S->ev[c], 0));
+      OKB_CUDA(cudaStreamWaitEvent(origin, S->ev_side[c], 0));
+    }
+    OKB_CUDA(cudaStreamWaitEvent(origin, S->ev_side[n_cams], 0));
     return OKB_OK;
   };
 
   // ---- direct submission, capture on the second call with the same signature, replay afterwards
+  const auto t1 = now();
   const bool timers = ctx->timers_on != 0;
   if (S->exec && sig == S->sig) {
+    // the tables of the older views and the poses change with every multiframe: refresh the page-locked mirrors the graph copies from
+    for (int c = 0; c < n_cams; c++) {
+      const okb_multiframe_cam_t& q = io[c];
+      const int rc = motion_restage(ctx->cams[c].motion, 1, q.n_older, q.older, q.cap0, q.T_WC1, q.T_CW1);
+      if (rc) return rc;
+    }
     OKB_CUDA(cudaGraphLaunch(S->exec, origin));
     S->graph_launches++;
   } else {
@@ -273,7 +327,9 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
     }
   }
   if (S->exec && sig == S->sig && S->graph_launches > 1) ctx->launches += S->launches_per_graph;   // kernels the replay launched
+  const auto t2 = now();
   OKB_CUDA(wait_stream(ctx, origin));
+  const auto t3 = now();
 
   // ---- results to the caller
   for (int c = 0; c < n_cams; c++) {
@@ -308,6 +364,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
     const uint8_t* h = S->pairs[p].h; const size_t o_d = al(n * 4), o_hp = 2 * al(n * 4), o_in = o_hp + al(n * 32);
     memcpy(P.k1, h, (size_t)n0 * 4); memcpy(P.dist, h + o_d, (size_t)n0 * 4); memcpy(P.hp_W, h + o_hp, (size_t)n0 * 32); memcpy(P.initialisable, h + o_in, (size_t)n0);
   }
+  S->t_stage += secs(t0, t1); S->t_submit += secs(t1, t2); S->t_wait += secs(t2, t3); S->t_out += secs(t3, now());
   return OKB_OK;
 }
 

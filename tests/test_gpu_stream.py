@@ -40,6 +40,16 @@ def make_views(kp, desc, rays, valid, seed, T_WC1):
     return views
 
 
+def pose_at(c, t):
+    """the current camera pose of call t (moves a little every frame: the tables the graph copies must follow)"""
+    return pose12(np.eye(3), np.array([0.11 * c + 0.003 * t, 0.001 * t, 0.0]))
+
+
+def view_order(t):
+    """the older keyframes of call t: the window slides (their order changes every frame)"""
+    return [(v + t) % N_OLDER for v in range(N_OLDER)]
+
+
 def run(use_graph, n_calls=5):
     import torch
     fe = Frontend(2, W, H)
@@ -63,34 +73,34 @@ def run(use_graph, n_calls=5):
         cap0 = max(cap0, max(len(v["desc"]) for v in views[c]))
     cap0 = (cap0 + 63) // 64 * 64
     for c in range(2):
-        tab = (okl.OlderView * N_OLDER)()
-        for vi, v in enumerate(views[c]):
-            t = {k: torch.from_numpy(np.ascontiguousarray(v[k])).cuda() for k in ("desc", "rays", "valid", "size", "use")}
-            keep.append(t)
-            e = tab[vi]
-            e.d_desc, e.d_rays, e.d_valid, e.d_size, e.d_use = (t[k].data_ptr() for k in ("desc", "rays", "valid", "size", "use"))
-            e.n = len(v["desc"]); e.T_WC[:] = list(v["T_WC"]); e.T_CW[:] = list(v["T_CW"])
-        dviews.append(tab)
+        dviews.append([{k: torch.from_numpy(np.ascontiguousarray(v[k])).cuda() for k in ("desc", "rays", "valid", "size", "use")} for v in views[c]])
     cap = MAXKP
     results = []
     try:
         for t in range(n_calls):
-            io = (okl.MultiframeCam * 2)(); bufs = []
+            io = (okl.MultiframeCam * 2)(); bufs = []; tabs = []
             for c in range(2):
                 q = io[c]
+                tab = (okl.OlderView * N_OLDER)()
+                for vi, src in enumerate(view_order(t)):
+                    v, dv = views[c][src], dviews[c][src]
+                    e = tab[vi]
+                    e.d_desc, e.d_rays, e.d_valid, e.d_size, e.d_use = (dv[k].data_ptr() for k in ("desc", "rays", "valid", "size", "use"))
+                    e.n = len(v["desc"]); e.T_WC[:] = list(v["T_WC"]); e.T_CW[:] = list(v["T_CW"])
+                tabs.append(tab)
                 img = np.ascontiguousarray(frames[t][c]); m = maps[c]
                 proj = np.ascontiguousarray(m["lm_proj"] + 0.7 * t)    # the camera moves: projections change every frame
                 b = dict(img=img, proj=proj, kp=np.zeros(cap, okl.KP_DTYPE), desc=np.zeros((cap, 64), np.uint8), rays=np.zeros((cap, 3)),
                          valid=np.zeros(cap, np.uint8), m1d=np.zeros(cap, np.uint32), m1l=np.zeros(cap, np.int32), m3n=np.zeros(N_OLDER, np.int32),
                          k0=np.zeros((N_OLDER, CAP_M), np.int32), k1=np.zeros((N_OLDER, CAP_M), np.int32), fl=np.zeros((N_OLDER, CAP_M), np.uint8),
-                         hp=np.zeros((N_OLDER, CAP_M, 4)), Tw=np.ascontiguousarray(poses[c][0]), Tc=np.ascontiguousarray(poses[c][1]),
+                         hp=np.zeros((N_OLDER, CAP_M, 4)), Tw=np.ascontiguousarray(pose_at(c, t)[0]), Tc=np.ascontiguousarray(pose_at(c, t)[1]),
                          cd=np.ascontiguousarray(m["cand_desc"]), cl=np.ascontiguousarray(m["cand_lm"]), c3=np.ascontiguousarray(m["lm_is3d"]))
                 bufs.append(b)
                 q.image = img.ctypes.data; q.stride_bytes = W
                 q.n_cand = len(b["cl"]); q.n_lm = len(b["c3"]); q.pool_changed = 1 if t == 0 else 0
                 q.cand_desc, q.cand_lm, q.lm_is3d, q.lm_proj = b["cd"].ctypes.data, b["cl"].ctypes.data, b["c3"].ctypes.data, proj.ctypes.data
                 q.T_WC1, q.T_CW1 = b["Tw"].ctypes.data, b["Tc"].ctypes.data
-                q.n_older, q.cap0, q.older = N_OLDER, cap0, C.addressof(dviews[c])
+                q.n_older, q.cap0, q.older = N_OLDER, cap0, C.addressof(tab)
                 q.cap = cap; q.kp, q.desc, q.rays, q.rays_valid = (b[k].ctypes.data for k in ("kp", "desc", "rays", "valid"))
                 q.m1_dist, q.m1_lm = b["m1d"].ctypes.data, b["m1l"].ctypes.data
                 q.cap_m = CAP_M; q.m3_n, q.m3_k0, q.m3_k1, q.m3_flags, q.m3_hp_W = (b[k].ctypes.data for k in ("m3n", "k0", "k1", "fl", "hp"))
@@ -127,8 +137,8 @@ def test_process_multiframe_equals_oracle(use_graph):
             rdist, rlm = oracle.match_map3d(rd, xy, None, m["cand_desc"], m["cand_lm"], b["proj"], m["lm_is3d"], 20.0, 60)
             assert np.array_equal(b["m1d"][:n], rdist.astype(np.uint32)) and np.array_equal(b["m1l"][:n], rlm), (t, c)
             m1_total += int((rlm >= 0).sum())
-            ov = [dict(v) for v in views[c]]
-            ref, _ = oracle.match_motion_stereo_sequence(ov, rd, rays, valid, np.stack([rk["x"], rk["y"]], 1), poses[c][0], poses[c][1], 1, intr[c], W, H, 60,
+            ov = [dict(views[c][src]) for src in view_order(t)]
+            ref, _ = oracle.match_motion_stereo_sequence(ov, rd, rays, valid, np.stack([rk["x"], rk["y"]], 1), pose_at(c, t)[0], pose_at(c, t)[1], 1, intr[c], W, H, 60,
                                                          (rlm >= 0).astype(np.uint8))
             for v, (k1, dist, hp, fl) in enumerate(ref):
                 k0s = np.nonzero(fl & 1)[0]
