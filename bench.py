@@ -675,9 +675,13 @@ class Replica:
             # the same live use through ONE call per stereo frame (okb_process_multiframe), replayed as a CUDA graph
             sec2 = C.c_double(); worst = C.c_double(); h2 = C.c_longlong(); d2 = C.c_longlong(); nk2 = C.c_longlong(); nm2 = C.c_longlong()
             drv.okb_e2e_multiframe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 13
-            proj1 = [np.ascontiguousarray(m["lm_proj"]) for m in maps]
+            # inputs in page-locked host memory (the e2e contract's "pinned host memory"): the library reads them in place
+            pin_ = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            p_img = [pin_(wl["L"][:e2e_frames]), pin_(wl["R"][:e2e_frames])]
+            p_proj = [pin_(m["lm_proj"]) for m in maps]
+            proj1 = [x.numpy() for x in p_proj]
             self.barrier()
-            rc = drv.okb_e2e_multiframe(self.fes[0].ctx, e2e_frames, 6, W, H, wl["L"].ctypes.data, wl["R"].ctypes.data, kp_cap,
+            rc = drv.okb_e2e_multiframe(self.fes[0].ctx, e2e_frames, 6, W, H, p_img[0].data_ptr(), p_img[1].data_ptr(), kp_cap,
                                         arr_i([len(x) for x in keep[1]]), arr_p(keep[0]), arr_p(keep[1]), arr_i([len(x) for x in keep[3]]),
                                         arr_p(proj1), arr_p(keep[3]), C.byref(sm3) if self.n_older else None, C.byref(sec2), C.byref(worst), C.byref(h2),
                                         C.byref(d2), C.byref(nk2), C.byref(nm2))
@@ -686,6 +690,7 @@ class Replica:
             ph = (C.c_double * 4)(); L_.okb_stream_timing(self.fes[0].ctx, ph, 1)
             calls = e2e_frames
             mf_s = self.allmax([sec2.value])[0]
+            del p_img, p_proj
             separate = {"value": self.world * e2e_frames / e2e_s, "ms_per_stereo_frame": 1e3 * e2e_s / e2e_frames,
                         "step": "the same frame as separate host-buffer calls: 2x okb_detect_describe (one host thread per camera) + okb_match_stereo + "
                                 "2x okb_match_map3d + 2x okb_match_motion_stereo_batch"}
@@ -695,7 +700,8 @@ class Replica:
                                 "host_ms_per_frame": {"stage_inputs": 1e3 * ph[0] / calls, "submit": 1e3 * ph[1] / calls, "wait_device": 1e3 * ph[2] / calls,
                                                       "copy_results": 1e3 * ph[3] / calls},
                                 "step": "one stereo frame per call (live use, ThreadedSlam::processFrame): okb_process_multiframe = detect+describe both cameras, "
-                                        "M1, M3 sequence, M4 enqueued at once from HOST buffers and replayed as a CUDA graph, one synchronisation per frame",
+                                        "M1, M3 sequence, M4 enqueued at once from page-locked HOST buffers (results into pageable host buffers) and replayed "
+                                        "as a CUDA graph, one synchronisation per frame",
                                 "frames": e2e_frames, "cuda_graph_launches": int(g_l.value), "direct_submissions": int(d_l.value),
                                 "keypoints_per_frame": nk2.value / e2e_frames / 2, "matches_per_frame": nm2.value / e2e_frames,
                                 "separate_calls": separate}

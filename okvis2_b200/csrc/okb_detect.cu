@@ -234,11 +234,11 @@ __device__ __host__ __forceinline__ TieSorted tie_sorted(uint32_t* base, int fra
   return TieSorted{p, p + kMaxTies, p + 2 * kMaxTies, p + 3 * kMaxTies, p + 4 * kMaxTies, p + 5 * kMaxTies};
 }
 
-// Per tie, spread over the GPU (grid: tiles of 128 ties x frames): its rank in time order (count of smaller keys: the list
+// Per tie, spread over the GPU (grid: tiles of 64 ties x frames): its rank in time order (count of smaller keys: the list
 // k_refine appended is unordered), everything the dependency rounds need from global memory -- the touch-time words and the
 // dense scores of its 5x5 window (50 scattered loads, the reason this is not done by the one CTA that resolves the frame) --
 // and the footprint of its own touches as bit masks. Results are written to position `rank` of the per-field arrays.
-__global__ void __launch_bounds__(128) k_tie_gather(const __grid_constant__ DeviceLayers dl, const uint8_t* score_block, const uint32_t* touch_block,
+__global__ void __launch_bounds__(64) k_tie_gather(const __grid_constant__ DeviceLayers dl, const uint8_t* score_block, const uint32_t* touch_block,
                                                     const TieEntry* tie_list, const int32_t* tie_count, const uint32_t* d_epoch, int threshold,
                                                     uint32_t* sorted_base)
 {
@@ -1076,11 +1076,12 @@ int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   OKB_CUDA(cudaEventRecord(ws.ev_join, ws.stream2));
   if (ctx->timers_on) cudaEventRecord(ws.ev[1], st);
   // ---- candidates, refinement, tie resolution, selection
-  const int cpw = B >= 8 ? 32 : (B >= 4 ? 16 : 8);
+  static const int cpw_env = getenv("OKB_REFINE_CPW") ? atoi(getenv("OKB_REFINE_CPW")) : 0;   // tuning hook
+  const int cpw = cpw_env > 0 ? cpw_env : (B >= 8 ? 32 : (B >= 4 ? 16 : 8));
   k_refine<<<dim3((ws.cand_cap + 4 * cpw - 1) / (4 * cpw), B), 128, 0, st>>>(ws.dl, d_images, src_pitch, in_stride, ws.d_img, ws.d_score,
                                                                ws.d_touch, ws.d_cand, ws.d_cand_count, ws.cand_cap, cr,
                                                                ws.d_fkey, (float4*)ws.d_fval, c.threshold, ws.d_epoch, ws.d_tie_cells, ws.d_ties, ws.d_tie_count, cpw);
-  k_tie_gather<<<dim3(kMaxTies / 128, B), 128, 0, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_ties, ws.d_tie_count, ws.d_epoch, c.threshold, ws.d_tie_sorted);
+  k_tie_gather<<<dim3(kMaxTies / 64, B), 64, 0, st>>>(ws.dl, ws.d_score, ws.d_touch, ws.d_ties, ws.d_tie_count, ws.d_epoch, c.threshold, ws.d_tie_sorted);
   k_resolve<<<B, kResolveThreads, kResolveSmem, st>>>(ws.d_tie_sorted, ws.d_tie_count, ws.d_fkey, ws.cand_cap, c.threshold, ws.d_status, ws.d_dbg);
   ctx->launches++;
   k_finalize<<<B, 1024, kFinalizeSmem, st>>>(ws.dl, ws.d_cand_count, ws.cand_cap, cr, ws.d_fkey, (const float4*)ws.d_fval, ws.d_fslot,

@@ -1560,7 +1560,8 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
   {
     MatchArgs s = a;
     // small batches: short query chunks so that one frame's scan still spreads over the SMs
-    s.q_use = use0; s.view_index = 0; s.scan_views = n_older; s.scan_qt = n_frames >= 8 ? 128 : 32; s.scan_chunks = (cap0 + s.scan_qt - 1) / s.scan_qt;
+    s.q_use = use0; s.view_index = 0; s.scan_views = n_older; static const int qt_env = getenv("OKB_SCAN_QT") ? atoi(getenv("OKB_SCAN_QT")) : 0;   // tuning hook
+    s.scan_qt = qt_env > 0 ? qt_env : (n_frames >= 8 ? 128 : 32); s.scan_chunks = (cap0 + s.scan_qt - 1) / s.scan_qt;
     s.hit_cnt = hit_cnt;
     k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, n_older * s.scan_chunks), 256, 0, st>>>(s, hits, hit_cnt);
   }

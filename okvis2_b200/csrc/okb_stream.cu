@@ -37,12 +37,29 @@ struct StreamState {
   std::vector<cudaStream_t> side;    // per camera: copies and the M1 row binning next to the detector; [n_cams]: the stereo pairs
   std::vector<cudaEvent_t> ev_img, ev_bin, ev_det, ev_side;   // per camera: binning done, features ready, side stream done; ev_side[n_cams]: pairs done
   cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr;       // kept alive: its node handles address the upload nodes of `exec`
+  std::vector<cudaGraphNode_t> img_node, proj_node;   // per camera: the H2D nodes of the frame and of the projections
+  std::vector<const void*> img_bound, proj_bound;     // the host address each of them currently reads
   uint64_t sig = 0; int sig_seen = 0;
   int use_graph = 1;
   long long graph_launches = 0, direct_calls = 0;
   int64_t launches_per_graph = 0;
   double t_stage = 0, t_submit = 0, t_wait = 0, t_out = 0;   // host seconds spent per phase (okb_stream_timing)
 };
+
+void drop_graph(StreamState* s)
+{
+  if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
+  if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+}
+
+// page-locked (cudaMallocHost / cudaHostRegister) host memory can be read by the copy engine in place
+bool is_pinned(const void* p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
 
 StreamState* state(okb_context* ctx)
 {
@@ -63,7 +80,7 @@ void stream_free(okb_context* ctx)
 {
   if (!ctx->stream_state) return;
   StreamState* s = static_cast<StreamState*>(ctx->stream_state);
-  if (s->exec) cudaGraphExecDestroy(s->exec);
+  drop_graph(s);
   for (auto& a : s->cams) { cudaFree(a.d); if (a.h) cudaFreeHost(a.h); }
   for (auto& a : s->pairs) { cudaFree(a.d); if (a.h) cudaFreeHost(a.h); }
   for (auto* v : {&s->ev, &s->ev_img, &s->ev_bin, &s->ev_det, &s->ev_side}) for (auto e : *v) if (e) cudaEventDestroy(e);
@@ -82,7 +99,7 @@ int okb_stream_use_graph(okb_context_t* ctx, int on)
   if (!ctx) { set_error("okb_stream_use_graph: null context"); return OKB_ERR_ARGUMENT; }
   StreamState* s = state(ctx);
   s->use_graph = on ? 1 : 0;
-  if (!on && s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; s->sig_seen = 0; }
+  if (!on) { drop_graph(s); s->sig_seen = 0; }
   return OKB_OK;
 }
 
@@ -121,7 +138,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
   for (int c = 0; c < n_cams; c++) {
     okb_multiframe_cam_t& q = io[c];
     CamWorkspace& ws = ctx->cams[c];
-    const int W = ws.cfg.width, H = ws.cfg.height, cap = ws.kp_cap;
+    const int W = ws.cfg.width, cap = ws.kp_cap;
     if (!q.image || q.stride_bytes < (size_t)W || !q.kp || !q.desc || q.cap < 1 || q.n_cand < 0 || q.n_lm < 0 || q.n_older < 0 ||
         (q.n_cand > 0 && (!q.lm_proj || !q.m1_dist || !q.m1_lm)) ||
         (q.n_older > 0 && (!q.older || !q.T_WC1 || !q.T_CW1 || q.cap0 < 1 || q.cap_m < 1 || !q.m3_n || !q.m3_k0 || !q.m3_k1 || !q.m3_flags || !q.m3_hp_W)) ||
@@ -148,7 +165,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
         OKB_CUDA(cudaMalloc(&A.d, o + o / 4)); OKB_CUDA(cudaMallocHost(&A.h, o + o / 4)); A.cap = o + o / 4;
       }
       A.n_cand = q.n_cand; A.n_lm = q.n_lm; A.n_older = q.n_older; A.cap0 = q.cap0; A.cap_m = q.cap_m;
-      if (S->exec) { cudaGraphExecDestroy(S->exec); S->exec = nullptr; }
+      drop_graph(S);
       S->sig_seen = 0;
     }
     if ((q.pool_changed || layout_changed) && q.n_cand > 0) {   // outside the graph: the pool changes rarely
@@ -163,10 +180,6 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       OKB_CUDA(cudaMemcpy(A.d + A.o_lm, q.cand_lm, (size_t)q.n_cand * 4, cudaMemcpyHostToDevice));
       OKB_CUDA(cudaMemcpy(A.d + A.o_3d, q.lm_is3d, (size_t)q.n_lm, cudaMemcpyHostToDevice));
     }
-    // per-frame inputs -> page-locked staging
-    for (int y = 0; y < H; y++) memcpy(ws.h_img + (size_t)y * W, q.image + (size_t)y * q.stride_bytes, (size_t)W);
-    if (q.n_cand > 0) memcpy(A.h + A.o_proj, q.lm_proj, (size_t)q.n_lm * 16);
-    if (q.n_older > 0) { memcpy(A.h + A.o_pose, q.T_WC1, 96); memcpy(A.h + A.o_pose + 96, q.T_CW1, 96); }
     sig = mix(mix(mix(mix(mix(sig, q.n_cand), q.n_lm), q.n_older), q.cap0), q.cap_m);
     sig = mix(sig, q.rays ? 1 : 0);
   }
@@ -183,11 +196,42 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       OKB_CUDA(cudaDeviceSynchronize());
       cudaFree(A.d); if (A.h) cudaFreeHost(A.h);
       OKB_CUDA(cudaMalloc(&A.d, need)); OKB_CUDA(cudaMallocHost(&A.h, need)); A.cap = need;
-      if (S->exec) { cudaGraphExecDestroy(S->exec); S->exec = nullptr; }
+      drop_graph(S);
       S->sig_seen = 0;
     }
     sig = mix(mix(sig, P.cam0), P.cam1);
     sig = mix_bytes(sig, P.C_WC0, 72); sig = mix_bytes(sig, P.r_WC0, 24); sig = mix_bytes(sig, P.C_WC1, 72); sig = mix_bytes(sig, P.r_WC1, 24);
+  }
+  // ---- per-frame inputs. Pageable buffers go through the page-locked staging the copy nodes were captured with; a frame or a
+  //      projection table that is page-locked itself (and contiguous) is read in place: on replay its copy node is re-pointed
+  const bool replay = S->exec && sig == S->sig;
+  if (S->img_node.empty()) { S->img_node.assign(n_cams, nullptr); S->proj_node.assign(n_cams, nullptr); S->img_bound.assign(n_cams, nullptr); S->proj_bound.assign(n_cams, nullptr); }
+  for (int c = 0; c < n_cams; c++) {
+    okb_multiframe_cam_t& q = io[c];
+    CamWorkspace& ws = ctx->cams[c];
+    CamArena& A = S->cams[c];
+    const int W = ws.cfg.width, H = ws.cfg.height;
+    auto bind = [&](cudaGraphNode_t node, const void*& bound, void* dst, const void* staging, const void* user, size_t bytes, bool user_ok) -> int {
+      const void* src = (replay && node && user_ok && is_pinned(user)) ? user : staging;
+      if (replay && node && src != bound) {
+        const cudaError_t e = cudaGraphExecMemcpyNodeSetParams1D(S->exec, node, dst, src, bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error("okb_process_multiframe: cudaGraphExecMemcpyNodeSetParams1D -> %s", cudaGetErrorString(e)); return -1; }
+        bound = src;
+      }
+      return src == staging ? 1 : 0;   // 1: the caller has to fill the staging
+    };
+    const int st_img = bind(S->img_node[c], S->img_bound[c], ws.d_in, ws.h_img, q.image, (size_t)W * H, q.stride_bytes == (size_t)W);
+    if (st_img < 0) return OKB_ERR_CUDA;
+    if (st_img) {
+      if (q.stride_bytes == (size_t)W) memcpy(ws.h_img, q.image, (size_t)W * H);
+      else for (int y = 0; y < H; y++) memcpy(ws.h_img + (size_t)y * W, q.image + (size_t)y * q.stride_bytes, (size_t)W);
+    }
+    if (q.n_cand > 0) {
+      const int st_proj = bind(S->proj_node[c], S->proj_bound[c], A.d + A.o_proj, A.h + A.o_proj, q.lm_proj, (size_t)q.n_lm * 16, true);
+      if (st_proj < 0) return OKB_ERR_CUDA;
+      if (st_proj) memcpy(A.h + A.o_proj, q.lm_proj, (size_t)q.n_lm * 16);
+    }
+    if (q.n_older > 0) { memcpy(A.h + A.o_pose, q.T_WC1, 96); memcpy(A.h + A.o_pose + 96, q.T_CW1, 96); }
   }
   for (auto& e : S->ev) if (!e) OKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if (S->side.empty()) {
@@ -283,7 +327,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
   // ---- direct submission, capture on the second call with the same signature, replay afterwards
   const auto t1 = now();
   const bool timers = ctx->timers_on != 0;
-  if (S->exec && sig == S->sig) {
+  if (replay) {
     // the tables of the older views and the poses change with every multiframe: refresh the page-locked mirrors the graph copies from
     for (int c = 0; c < n_cams; c++) {
       const okb_multiframe_cam_t& q = io[c];
@@ -293,7 +337,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
     OKB_CUDA(cudaGraphLaunch(S->exec, origin));
     S->graph_launches++;
   } else {
-    if (S->exec) { cudaGraphExecDestroy(S->exec); S->exec = nullptr; }
+    drop_graph(S);
     const bool capture = S->use_graph && !timers && sig == S->sig && S->sig_seen >= 1;   // shapes are stable and every buffer has been sized
     if (sig != S->sig) { S->sig = sig; S->sig_seen = 0; }
     S->sig_seen++;
@@ -316,9 +360,27 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       } else {
         S->launches_per_graph = ctx->launches - launches_before;
         const cudaError_t e2 = cudaGraphInstantiate(&S->exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e2 != cudaSuccess) { S->exec = nullptr; S->use_graph = 0; cudaGetLastError(); rc = enqueue(); if (rc) return rc; S->direct_calls++; }
-        else { OKB_CUDA(cudaGraphLaunch(S->exec, origin)); S->graph_launches++; }
+        if (e2 != cudaSuccess) { cudaGraphDestroy(graph); S->exec = nullptr; S->use_graph = 0; cudaGetLastError(); rc = enqueue(); if (rc) return rc; S->direct_calls++; }
+        else {
+          // remember the upload nodes of the frames and projections (their sources are this call's staging buffers)
+          S->graph = graph;
+          size_t nn = 0;
+          std::vector<cudaGraphNode_t> nodes;
+          if (cudaGraphGetNodes(graph, nullptr, &nn) == cudaSuccess && nn > 0) { nodes.resize(nn); cudaGraphGetNodes(graph, nodes.data(), &nn); }
+          for (int c = 0; c < n_cams; c++) { S->img_node[c] = S->proj_node[c] = nullptr; S->img_bound[c] = ctx->cams[c].h_img; S->proj_bound[c] = S->cams[c].h + S->cams[c].o_proj; }
+          for (cudaGraphNode_t nd : nodes) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeMemcpy) continue;
+            cudaMemcpy3DParms mp;
+            if (cudaGraphMemcpyNodeGetParams(nd, &mp) != cudaSuccess) continue;
+            for (int c = 0; c < n_cams; c++) {
+              if (mp.srcPtr.ptr == (void*)ctx->cams[c].h_img) S->img_node[c] = nd;
+              if (io[c].n_cand > 0 && mp.srcPtr.ptr == (void*)(S->cams[c].h + S->cams[c].o_proj)) S->proj_node[c] = nd;
+            }
+          }
+          cudaGetLastError();
+          OKB_CUDA(cudaGraphLaunch(S->exec, origin)); S->graph_launches++;
+        }
       }
     } else {
       int rc = enqueue();
