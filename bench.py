@@ -776,19 +776,29 @@ def matcher_record(rep):
                    "Hamming distance (row binning), M3 and M4 scan every pair; a full 512-bit distance is 16 popc.b32, the scan kernel "
                    "spends 4 (carry-save tree over the better-discriminating half) and the other half only where a warp still has a pair below "
                    "the threshold, so frac_of_popc_issue_rate (which charges 16 per pair) can exceed 1"}
-    rate = None
+    rate = imma = None
     try:
         rate = json.load(open(os.path.join(ROOT, "profiles", "popc_rate.json")))["popc_b32_lanes_per_clk_per_sm"]
+        imma = json.load(open(os.path.join(ROOT, "profiles", "imma_rate.json")))["dot512_per_s"]
     except Exception:
         pass
-    rec["measured_popc_b32_lanes_per_clk_per_sm"] = rate
-    for key, pairs, ms in (("m3", m3_pairs, rec["m3_ms_per_step"]), ("m4", m4_pairs, rec["m4_ms_per_step"])):
+    rec = {"m1_ms_per_step": m1_ms, "m3_ms_per_step": m3_ms, "m4_ms_per_step": m4_ms,
+           "scan": "tensor cores: Hamming = popc(a) + popc(b) - 2 popc(a & b), popc(a & b) as a 0/1 dot product over bit planes on the integer MMA "
+                   "path (k_scan_mma: mma.sync.m16n8k32.u8 = IMMA.16832, 16 per 16x8 tile of 512-bit pairs; operands expanded in registers)",
+           "note": "device time of the match stages alone on the features of the last step (scan + gate + outputs + checks); M1 is gated by the "
+                   "re-projection radius before any Hamming distance (row binning), M3 and M4 scan every eligible pair. Two ceilings are "
+                   "quoted for the scan: the measured POPC issue rate (16 popc.b32 per pair; what the previous form of the scan ran at) and the "
+                   "measured IMMA.16832 issue rate (bench/ubench_imma.cu, 16 per 128 pairs)",
+           "measured_popc_b32_lanes_per_clk_per_sm": rate, "measured_imma_dot512_per_s": imma}
+    for key, ms in (("m3", m3_ms), ("m4", m4_ms)):
         if ms > 0:
-            pps = pairs / (ms * 1e-3)
-            rec[key] = {"pairs_per_step": pairs, "pairs_per_s": pps}
+            pps = pairs[key] / (ms * 1e-3)
+            rec[key] = {"pairs_per_step": pairs[key], "pairs_per_s": pps}
             if rate:
                 peak_pairs = rate * 148 * 1.965e9 / 16.0     # 16 popc.b32 per 512-bit pair
                 rec[key]["frac_of_popc_issue_rate"] = pps / peak_pairs
+            if imma:
+                rec[key]["frac_of_imma_issue_rate"] = pps / imma
     return rec
 
 

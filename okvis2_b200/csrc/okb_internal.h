@@ -213,7 +213,8 @@ int motion_restage(MotionScratch& ms, int n_frames, int n_older, const okb_older
 int motion_sequence(okb_context* ctx, MotionScratch& ms, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
                     const int32_t* d_count1, const okb_camera_model_t* model, int width, int height, const double* T_WC1, const double* T_CW1,
                     int n_older, const okb_older_view_t* older, int cap0, uint32_t match_threshold, cudaStream_t st, uint8_t* d_matched1,
-                    int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags, const double* d_rays1, const uint8_t* d_valid1);
+                    int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags, const double* d_rays1, const uint8_t* d_valid1,
+                    const int32_t* d_m1_lm = nullptr);
 void m3_compact_launch(int n_frames, int cap0, int n_older, int cap_m, const int32_t* k1, const double* hp, const uint8_t* flags, int32_t* n_match,
                        int32_t* m_k0, int32_t* m_k1, uint8_t* m_flags, double* m_hp, cudaStream_t st);
 void prepare_free(okb_context* ctx);

@@ -90,6 +90,8 @@ enum { MODE_M2 = 2, MODE_M3 = 3, MODE_M4 = 4 };
 // -1: small batches (up to 4 frames) run the gate / finish (/ check / commit) of M3 and M4 as ONE launch per view or pair
 // (k_pair_view, one CTA per frame); larger batches use the separate kernels. 0 / 1 force either form (okb_m3_set_fused).
 static std::atomic<int> g_m3_fused{-1};
+// 1 (default): the Hamming scans of the device-resident M3 / M4 run on the tensor cores (k_scan_mma); 0: the POPC scan (k_m4_scan)
+static std::atomic<int> g_scan_mma{1};
 
 struct MatchArgs {
   int nq, nc;
@@ -117,6 +119,9 @@ struct MatchArgs {
   // k_m4_scan over several views at once (blockIdx.z = view * scan_chunks + query chunk): per-view slices of q_use (nq apart),
   // of the hit lists (gridDim.y * hit_cap apart) and of hit_cnt (gridDim.y apart); scan_qt = queries per CTA (<= 128)
   int scan_views, scan_chunks, scan_qt;
+  // k_scan_mma: optional compacted list of the eligible queries per (view, frame) ([views][frames][nq] indices + [views][frames] counts);
+  // null = all queries below the frame's count, q_use tested per hit
+  const int32_t* q_list; const int32_t* q_list_cnt;
 };
 
 // one older keyframe view (device pointers) and the per-frame pose of the current camera, as uploaded by the M3 sequence
@@ -736,6 +741,137 @@ __global__ void __launch_bounds__(256) k_m4_scan(MatchArgs a, uint2* hits, int32
   }
 }
 
+// ---- the Hamming scan on the tensor cores (legacy integer path: mma.sync.m16n8k32.u8 -> IMMA.16832.U8.U8) -------------------
+// Hamming(a, b) = popc(a) + popc(b) - 2 popc(a & b), and popc(a & b) over 512 bits is a dot product of 0/1 vectors: 16 IMMAs of
+// k = 32 per 16 x 8 tile of pairs, the operands being the descriptor words with one bit plane selected per byte: the candidate
+// side keeps the bit where it is, w & (0x01010101 << i) (one LOP3: byte value 2^i), the query side moves it to bit 7 - i (byte
+// value 2^(7-i), expanded once per 16 queries), so every common bit adds 128 whatever its plane. The expansion stays in registers
+// (the same byte lane of the same word on both sides, so any consistent word assignment gives the exact count). bench/ubench_imma.cu measures 0.48 IMMA.16832 per clock per SM on the B200
+// (1.14 POPS): 3.8 pairs per clock per SM against 0.97 for the POPC scan above (profiles/popc_rate.json).
+// Layout: CTA = 4 warps x 64 candidates (8 column blocks whose raw words stay in registers); the queries of the CTA's chunk are
+// staged in shared memory (row stride 20 words: conflict-free fragment loads) and taken 16 at a time: their 64 plane words are
+// expanded once and reused for the 8 column blocks; the candidate planes are expanded per use (2 ALU ops per IMMA operand word).
+// Epilogue per tile: 4 distances per thread from the row / column popcounts, hits below the threshold appended as in k_m4_scan.
+__device__ __forceinline__ void imma_u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) k_scan_mma(MatchArgs a, uint2* hits, int32_t* hit_cnt)
+{
+  constexpr int kQT = 256, kRow = 20;
+  __shared__ uint32_t sq[kQT][kRow];
+  __shared__ uint32_t sc[4][64][kRow];   // per warp: 64 candidates x (16 words + popcount)
+  __shared__ int s_qid[kQT];
+  const int frame = blockIdx.y;
+  const int vz = a.scan_views > 0 ? blockIdx.z / a.scan_chunks : 0, qz = a.scan_views > 0 ? blockIdx.z % a.scan_chunks : blockIdx.z;
+  const int qt = a.scan_qt;
+  const size_t fq = (size_t)frame * a.q_stride + (size_t)vz * a.nq, fc = (size_t)frame * a.c_stride;
+  const M3View* view = a.views ? &a.views[(size_t)frame * a.view_stride + a.view_index + vz] : nullptr;   // M3: queries = an older view
+  hits += (size_t)vz * gridDim.y * a.hit_cap; hit_cnt += (size_t)vz * gridDim.y;
+  const int nq_all = view ? min(view->n, a.nq) : min(a.q_count[frame], a.nq), nc = min(a.c_count[frame], a.nc);
+  const int32_t* list = a.q_list ? a.q_list + ((size_t)vz * gridDim.y + frame) * a.nq : nullptr;
+  const int nq = list ? min(a.q_list_cnt[(size_t)vz * gridDim.y + frame], nq_all) : nq_all;
+  if ((int)(blockIdx.x * 256) >= nc) return;
+  const int q0 = qz * qt;
+  if (q0 >= nq) return;
+  const uint4* q_desc = view ? reinterpret_cast<const uint4*>(view->desc) : reinterpret_cast<const uint4*>(a.q_desc) + fq * 4;
+  // ---- stage the chunk's queries (through the eligible list, if there is one)
+  for (int i = threadIdx.x; i < qt * 4; i += blockDim.x) {
+    const int j = i >> 2, w = i & 3;
+    int qi = -1;
+    if (q0 + j < nq) qi = list ? __ldg(&list[q0 + j]) : q0 + j;
+    const uint4 v = qi >= 0 ? __ldg(q_desc + (size_t)qi * 4 + w) : make_uint4(0, 0, 0, 0);
+    sq[j][4 * w] = v.x; sq[j][4 * w + 1] = v.y; sq[j][4 * w + 2] = v.z; sq[j][4 * w + 3] = v.w;
+    if (w == 0) s_qid[j] = qi;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int c_base = blockIdx.x * 256 + warp * 64;
+  if (c_base >= nc) return;
+  // ---- this warp's 64 candidates: raw words and popcounts in shared memory (private to the warp)
+  {
+    const uint4* cd = reinterpret_cast<const uint4*>(a.c_desc) + fc * 4;
+    for (int i = lane; i < 64 * 4; i += 32) {
+      const int j = i >> 2, w = i & 3;
+      const uint4 v = c_base + j < nc ? __ldg(cd + (size_t)(c_base + j) * 4 + w) : make_uint4(0, 0, 0, 0);
+      uint32_t* row = sc[warp][j];
+      row[4 * w] = v.x; row[4 * w + 1] = v.y; row[4 * w + 2] = v.z; row[4 * w + 3] = v.w;
+    }
+    __syncwarp();
+    for (int j = lane; j < 64; j += 32) {
+      int pc = 0;
+#pragma unroll
+      for (int w = 0; w < 16; w++) pc += __popc(sc[warp][j][w]);
+      sc[warp][j][16] = (uint32_t)pc;
+    }
+    __syncwarp();
+  }
+  const int jn = min(qt, nq - q0);
+  constexpr uint32_t M = 0x01010101u;
+  const uint32_t* b_rows = &sc[warp][g][t];          // + n * 8 * kRow: words t + 4 j of column n * 8 + g
+  const uint32_t* b_pops = &sc[warp][2 * t][16];     // + n * 8 * kRow: popcounts of columns n * 8 + 2t, + kRow: 2t + 1
+  const int thr64 = 64 * (int)a.thr;
+#pragma unroll 1
+  for (int m0 = 0; m0 < jn; m0 += 16) {
+    // rows m0 + g and m0 + g + 8: words t + 4 j, their 8 bit planes, and the row popcounts
+    uint32_t A[2][4][8];   // [row half][word j][plane i]
+    int ra[2];             // 64 (popc(row) - thr): the hit test d < thr reads  128 popc(a & b) > 64 (popc(a) + popc(b) - thr)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      int pr = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t w = sq[m0 + g + 8 * h][t + 4 * j];
+        pr += __popc(w);
+#pragma unroll
+        for (int i = 0; i < 8; i++)   // bit i of every byte moved to bit 7 - i: byte value 2^(7-i)
+          A[h][j][i] = (i <= 3 ? (w << (7 - 2 * i)) : (w >> (2 * i - 7))) & (M << (7 - i));
+      }
+      pr += __shfl_xor_sync(0xffffffffu, pr, 1); pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+      ra[h] = 64 * pr - thr64;
+    }
+#pragma unroll 1
+    for (int n = 0; n < 8; n++) {
+      uint32_t Bw[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) Bw[j] = b_rows[n * 8 * kRow + 4 * j];
+      // two independent accumulator chains (a single chain of 16 dependent IMMAs is bound by the MMA latency)
+      int c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int jp = 0; jp < 2; jp++)   // word pairs (j, j + 1) feed (a0 | a2) / (b0 | b1)
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          imma_u8((i & 1) ? c1 : c0, A[0][2 * jp][i], A[1][2 * jp][i], A[0][2 * jp + 1][i], A[1][2 * jp + 1][i], Bw[2 * jp] & (M << i), Bw[2 * jp + 1] & (M << i));
+      // element e: row g + 8 (e >> 1), column 2t + (e & 1); every common bit contributed 2^(7-i) * 2^i = 128
+      const int cb0 = 64 * (int)b_pops[n * 8 * kRow], cb1 = 64 * (int)b_pops[n * 8 * kRow + kRow];
+      const int lim[4] = {ra[0] + cb0, ra[0] + cb1, ra[1] + cb0, ra[1] + cb1};
+      bool any = false;
+#pragma unroll
+      for (int e = 0; e < 4; e++) any |= (c0[e] + c1[e]) > lim[e];
+      if (any) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int raw = c0[e] + c1[e];
+          if (raw <= lim[e]) continue;
+          const int h = e >> 1, cc = e & 1;
+          const int j = m0 + g + 8 * h, col = c_base + n * 8 + 2 * t + cc;
+          if (j < jn && col < nc) {
+            const int q = s_qid[j];
+            if ((a.q_use == nullptr || a.q_use[fq + q]) && a.c_valid[fc + col]) {
+              // d = popc(a) + popc(b) - 2 popc(a & b), from the same integers: (lim + 64 thr - raw) / 64
+              const uint32_t d = (uint32_t)((lim[e] + thr64 - raw) >> 6);
+              const int pos = atomicAdd(&hit_cnt[frame], 1);
+              if (pos < a.hit_cap) hits[(size_t)frame * a.hit_cap + pos] = make_uint2((d << 20) | (uint32_t)q, (uint32_t)col);   // d <= 512, q < 2^20
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128) k_m4_gate(MatchArgs a, const uint2* hits, unsigned long long* best)
 {
@@ -794,10 +930,12 @@ struct M3Prep {
   int cap0, cap1; size_t q_stride;   // scratch / output stride per frame (keypoints): n_views * cap0
   double f0;
   double* e0; double* c26; double* c6; uint8_t* use0;            // [frames][n_views][cap0]
-  const double* rays1; const uint8_t* valid1; const int32_t* count1; const uint8_t* matched1; double* e1; uint8_t* cvalid;   // [frames][cap1]
+  const double* rays1; const uint8_t* valid1; const int32_t* count1; uint8_t* matched1; double* e1; uint8_t* cvalid;   // [frames][cap1]
+  const int32_t* m1_lm;       // optional [frames][cap1]: M1's landmark per keypoint; when set, matched1 is initialised from it here
   unsigned long long* best;   // [frames][n_views][cap0] -> all ones
   int32_t* claim;             // [n_views][frames][cap1] -> INT_MAX
   int32_t* hit_cnt;           // [n_views][frames] -> 0
+  int32_t* q_list; int32_t* q_list_cnt;   // [n_views][frames][cap0] eligible keypoints of the view (any order), [n_views][frames] counts (zeroed by the caller)
 };
 
 // one launch for the whole sequence: grid (keypoint tiles, frames, views). Tables of every view's keypoints, and (by the z = 0
@@ -823,6 +961,10 @@ __global__ void __launch_bounds__(128) k_m3_prep(const __grid_constant__ M3Prep 
     }
     p.use0[i] = use ? 1 : 0;
     p.best[i] = ~0ull;
+    if (use) {
+      const size_t vf = (size_t)v * gridDim.y + frame;
+      p.q_list[vf * p.cap0 + atomicAdd(&p.q_list_cnt[vf], 1)] = k;
+    }
   }
   if (k < p.cap1) {
     const size_t j = (size_t)frame * p.cap1 + k;
@@ -837,7 +979,10 @@ __global__ void __launch_bounds__(128) k_m3_prep(const __grid_constant__ M3Prep 
       }
       // the reference's compacted candidate set k1s (:1789-1801): valid and not yet matched; k_m3_commit / k_m3_view clear the
       // entries a view inserts, so every view sees the set as its predecessors left it
-      p.cvalid[j] = (in && p.valid1[j] && !p.matched1[j]) ? 1 : 0;
+      bool matched;
+      if (p.m1_lm) { matched = in && p.m1_lm[j] >= 0; p.matched1[j] = matched ? 1 : 0; }   // the `landmarkId != 0` test of :1792-1795 on M1's result
+      else matched = p.matched1[j] != 0;
+      p.cvalid[j] = (in && p.valid1[j] && !matched) ? 1 : 0;
     }
   }
 }
@@ -1405,8 +1550,13 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
   a.hit_cnt = hit_cnt; a.hit_cap = hit_cap;
   const int fused_mode = g_m3_fused.load();
   const bool fused = fused_mode >= 0 ? fused_mode != 0 : n_frames <= 4;
-  a.scan_qt = fused ? 32 : 128;   // small batches: short query chunks so that one frame's scan still spreads over the SMs
-  k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, (cap0 + a.scan_qt - 1) / a.scan_qt), 256, 0, st>>>(a, hits, hit_cnt);
+  if (g_scan_mma.load()) {
+    a.scan_qt = fused ? 32 : 256;   // small batches: short query chunks so that one frame's scan still spreads over the SMs
+    k_scan_mma<<<dim3((cap1 + 255) / 256, n_frames, (cap0 + a.scan_qt - 1) / a.scan_qt), 128, 0, st>>>(a, hits, hit_cnt);
+  } else {
+    a.scan_qt = fused ? 32 : 128;
+    k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, (cap0 + a.scan_qt - 1) / a.scan_qt), 256, 0, st>>>(a, hits, hit_cnt);
+  }
   if (fused) {
     M3Check none; memset(&none, 0, sizeof(none));
     k_pair_view<4, MODE_M4><<<n_frames, 512, 0, st>>>(a, none, hits, best);
@@ -1453,7 +1603,7 @@ int okb_match_motion_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap
   OKB_CHECK_ARGS(ctx, "okb_match_motion_stereo_device_ptr");
   // one scratch area per context for this form: calls of one context must be issued on streams that serialise them
   return okb::motion_sequence(ctx, ctx->motion, n_frames, cap1, d_kp1, d_desc1, d_count1, model, width, height, T_WC1, T_CW1, n_older, older, cap0,
-                              match_threshold, stream ? (cudaStream_t)stream : MW.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags, nullptr, nullptr);
+                              match_threshold, stream ? (cudaStream_t)stream : MW.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags, nullptr, nullptr, nullptr);
 }
 
 }  // extern "C"
@@ -1484,11 +1634,13 @@ int okb::motion_restage(MotionScratch& ms, int n_frames, int n_older, const okb_
 }
 
 extern "C" void okb_m3_set_fused(int mode) { g_m3_fused.store(mode < 0 ? -1 : (mode ? 1 : 0)); }
+extern "C" void okb_scan_set_mma(int on) { g_scan_mma.store(on ? 1 : 0); }
 
 int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
                          const int32_t* d_count1, const okb_camera_model_t* model, int width, int height, const double* T_WC1, const double* T_CW1,
                          int n_older, const okb_older_view_t* older, int cap0, uint32_t match_threshold, cudaStream_t st, uint8_t* d_matched1,
-                         int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags, const double* d_rays1, const uint8_t* d_valid1)
+                         int32_t* d_out_k1, uint32_t* d_out_dist, double* d_out_hp_W, uint8_t* d_out_flags, const double* d_rays1, const uint8_t* d_valid1,
+                         const int32_t* d_m1_lm)
 {
   OKB_CHECK_ARGS(ctx && n_frames >= 1 && cap1 > 0 && cap1 < (1 << 20) && d_kp1 && d_desc1 && d_count1 && model && T_WC1 && T_CW1 &&
                  n_older >= 0 && (n_older == 0 || older) && cap0 > 0 && cap0 < (1 << 20) && d_matched1 && d_out_k1 && d_out_dist &&
@@ -1504,7 +1656,7 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
   const int hit_cap = 16 * cap0;   // hits (distance < threshold) per frame and view kept for the gate pass
   const size_t n_hits = (size_t)n_older * n_frames * hit_cap;
   const size_t need = b_views + b_frames + al(nq * 24) + 2 * al(nq * 8) + al(nq) + al(nq) /*init*/ + al(n1 * 24) + al(n1 * 24) + 2 * al(n1) +
-                      al(n1 * 4 * n_older) + al(nq * 8) + al(n_hits * 8) + al((size_t)n_older * n_frames * 4);
+                      al(n1 * 4 * n_older) + al(nq * 8) + al(n_hits * 8) + 2 * al((size_t)n_older * n_frames * 4) + al(nq * 4);
   if (need > ms.cap) {
     OKB_CUDA(cudaDeviceSynchronize());
     if (ms.d) cudaFree(ms.d);
@@ -1529,6 +1681,7 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
   uint8_t* valid1 = take(n1); uint8_t* cvalid = take(n1); int32_t* claim = (int32_t*)take(n1 * 4 * n_older);
   unsigned long long* best = (unsigned long long*)take(nq * 8); uint2* hits = (uint2*)take(n_hits * 8);
   int32_t* hit_cnt = (int32_t*)take((size_t)n_older * n_frames * 4);
+  int32_t* q_list_cnt = (int32_t*)take((size_t)n_older * n_frames * 4); int32_t* q_list = (int32_t*)take(nq * 4);
   // descriptors of the views and poses. Asynchronous callers: pageable host staging (cudaMemcpyAsync copies it before it
   // returns, so back-to-back calls cannot overwrite each other's tables). Streaming / CUDA-graph callers (ms.pinned_staging: one
   // call in flight, synchronised per multiframe): the scratch's page-locked mirror, which a captured copy node re-reads at replay
@@ -1551,7 +1704,8 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
   p.q_stride = (size_t)n_older * cap0; p.f0 = 0.5 * (model->fu + model->fv);
   p.e0 = e0; p.c26 = c26; p.c6 = c6; p.use0 = use0;
   p.rays1 = rays1; p.valid1 = valid1; p.count1 = d_count1; p.matched1 = d_matched1; p.e1 = e1; p.cvalid = cvalid;
-  p.best = best; p.claim = claim; p.hit_cnt = hit_cnt;
+  p.best = best; p.claim = claim; p.hit_cnt = hit_cnt; p.m1_lm = d_m1_lm; p.q_list = q_list; p.q_list_cnt = q_list_cnt;
+  OKB_CUDA(cudaMemsetAsync(q_list_cnt, 0, (size_t)n_older * n_frames * 4, st));
   k_m3_prep<<<dim3(gmax, n_frames, n_older), 128, 0, st>>>(p);
   MatchArgs a; memset(&a, 0, sizeof(a));
   a.nq = cap0; a.nc = cap1; a.q_stride = p.q_stride; a.c_stride = (size_t)cap1; a.c_count = d_count1;
@@ -1559,11 +1713,18 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
   a.views = d_views; a.view_stride = n_older; a.frames = d_frames; a.hit_cap = hit_cap;
   {
     MatchArgs s = a;
-    // small batches: short query chunks so that one frame's scan still spreads over the SMs
-    s.q_use = use0; s.view_index = 0; s.scan_views = n_older; static const int qt_env = getenv("OKB_SCAN_QT") ? atoi(getenv("OKB_SCAN_QT")) : 0;   // tuning hook
-    s.scan_qt = qt_env > 0 ? qt_env : (n_frames >= 8 ? 128 : 32); s.scan_chunks = (cap0 + s.scan_qt - 1) / s.scan_qt;
-    s.hit_cnt = hit_cnt;
-    k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, n_older * s.scan_chunks), 256, 0, st>>>(s, hits, hit_cnt);
+    s.q_use = use0; s.view_index = 0; s.scan_views = n_older; s.hit_cnt = hit_cnt;
+    static const int qt_env = getenv("OKB_SCAN_QT") ? atoi(getenv("OKB_SCAN_QT")) : 0;   // tuning hook
+    if (g_scan_mma.load()) {
+      // tensor-core scan over the eligible keypoints of every view; small batches: short query chunks so that one frame's scan
+      // still spreads over the SMs
+      s.q_list = q_list; s.q_list_cnt = q_list_cnt;
+      s.scan_qt = qt_env > 0 ? std::min(qt_env, 256) : (n_frames >= 8 ? 256 : 32); s.scan_chunks = (cap0 + s.scan_qt - 1) / s.scan_qt;
+      k_scan_mma<<<dim3((cap1 + 255) / 256, n_frames, n_older * s.scan_chunks), 128, 0, st>>>(s, hits, hit_cnt);
+    } else {
+      s.scan_qt = qt_env > 0 ? std::min(qt_env, 128) : (n_frames >= 8 ? 128 : 32); s.scan_chunks = (cap0 + s.scan_qt - 1) / s.scan_qt;
+      k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, n_older * s.scan_chunks), 256, 0, st>>>(s, hits, hit_cnt);
+    }
   }
   ctx->launches += 2;
   // ---- per older keyframe, in order (what a view inserts is invisible to the next one's candidates)
@@ -1611,7 +1772,7 @@ int okb_match_motion_stereo_device(okb_context_t* ctx, int cam, int n_frames, co
   OKB_CHECK_ARGS(ws.has_model && n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_motion_stereo_device (camera model set? okb_set_camera_model)");
   // per-camera scratch: the sequences of different cameras run concurrently on their own streams
   return okb::motion_sequence(ctx, ws.motion, n_frames, ws.kp_cap, ws.d_kp, ws.d_desc, ws.d_count, &ws.model, ws.cfg.width, ws.cfg.height, T_WC1, T_CW1,
-                              n_older, older, cap0, match_threshold, ws.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags, ws.d_rays, ws.d_rays_valid);
+                              n_older, older, cap0, match_threshold, ws.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags, ws.d_rays, ws.d_rays_valid, nullptr);
 }
 
 int okb_matched_mask_device(okb_context_t* ctx, int cam, int n_frames, const int32_t* d_lm, uint8_t* d_matched)

@@ -279,12 +279,12 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       }
       OKB_CUDA(cudaEventRecord(S->ev_side[c], sd));
       if (q.n_older > 0) {
-        if (q.n_cand > 0) { rc = okb_matched_mask_device(ctx, c, 1, (const int32_t*)(A.d + A.o_m1l), A.d + A.o_mask); if (rc) return rc; }
-        else OKB_CUDA(cudaMemsetAsync(A.d + A.o_mask, 0, (size_t)cap, st));
+        if (q.n_cand == 0) OKB_CUDA(cudaMemsetAsync(A.d + A.o_mask, 0, (size_t)cap, st));   // else: initialised from M1's result by the sequence
         ws.motion.pinned_staging = 1;   // tables through the page-locked mirror: a captured copy node re-reads it at every replay
         rc = motion_sequence(ctx, ws.motion, 1, cap, ws.d_kp, ws.d_desc, ws.d_count, &ws.model, W, H, (const double*)(A.h + A.o_pose),
                              (const double*)(A.h + A.o_pose + 96), q.n_older, q.older, q.cap0, match_threshold, st, A.d + A.o_mask,
-                             (int32_t*)(A.d + A.o_k1), (uint32_t*)(A.d + A.o_dist), (double*)(A.d + A.o_hp), A.d + A.o_fl, ws.d_rays, ws.d_rays_valid);
+                             (int32_t*)(A.d + A.o_k1), (uint32_t*)(A.d + A.o_dist), (double*)(A.d + A.o_hp), A.d + A.o_fl, ws.d_rays, ws.d_rays_valid,
+                             q.n_cand > 0 ? (const int32_t*)(A.d + A.o_m1l) : nullptr);
         if (rc) return rc;
         m3_compact_launch(1, q.cap0, q.n_older, q.cap_m, (const int32_t*)(A.d + A.o_k1), (const double*)(A.d + A.o_hp), A.d + A.o_fl,
                           (int32_t*)(A.d + A.o_n), (int32_t*)(A.d + A.o_mk0), (int32_t*)(A.d + A.o_mk1), A.d + A.o_mf, (double*)(A.d + A.o_mhp), st);

@@ -102,6 +102,7 @@ _PROTOS = {
     "okb_process_multiframe": (i32, [vp, i32, vp, i32, vp, f64, u32]),
     "okb_stream_use_graph": (i32, [vp, i32]),
     "okb_m3_set_fused": (None, [i32]),
+    "okb_scan_set_mma": (None, [i32]),
     "okb_stream_timing": (i32, [vp, C.POINTER(C.c_double), i32]),
     "okb_stream_stats": (i32, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "okb_device_back_projections": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp)]),

@@ -70,7 +70,15 @@ def T_CW(C_WC, r):
     return T.reshape(12)
 
 
-def test_device_resident_stereo_pipeline_equals_oracle():
+@pytest.fixture(params=["mma", "popc"])
+def scan_form(request):
+    """both forms of the Hamming scan of the device-resident matchers: tensor cores (default) and POPC"""
+    okl.lib().okb_scan_set_mma(1 if request.param == "mma" else 0)
+    yield request.param
+    okl.lib().okb_scan_set_mma(1)
+
+
+def test_device_resident_stereo_pipeline_equals_oracle(scan_form):
     import torch
     B = 3
     fe = Frontend(2, 752, 480, max_batch=B)
@@ -184,7 +192,7 @@ def test_host_buffer_batch_pipeline_equals_oracle(pinned):
     fe.close()
 
 
-def test_stereo_scan_gate_split_with_dense_hits_and_overflow():
+def test_stereo_scan_gate_split_with_dense_hits_and_overflow(scan_form):
     """M4 device form on crafted feature blocks: frame 0 holds near-duplicate descriptors (every pair is below the matching
     threshold: the hit list overflows and the sequential-replay kernel redoes the frame), frame 1 a normal mix with many
     hits per query, frame 2 is empty on the query side. All three must equal the oracle's transcription of the loop."""

@@ -54,11 +54,13 @@ def run_device(fe, scenes, cap0, cap1, n_older):
             fl.cpu().numpy().reshape(sh), d_m.cpu().numpy())
 
 
-@pytest.mark.parametrize("fused", [1, 0])
-def test_motion_stereo_sequence_equals_oracle(fused):
-    """both forms of the per-view step: one launch per view (k_m3_view, the small-batch default) and the separate kernels"""
+@pytest.mark.parametrize("fused,mma", [(1, 1), (0, 1), (1, 0), (0, 0)])
+def test_motion_stereo_sequence_equals_oracle(fused, mma):
+    """both forms of the per-view step (one launch per view, the small-batch default; separate kernels) x both forms of the
+    Hamming scan (tensor cores, the default; POPC)"""
     fe = Frontend(0)
     okl.lib().okb_m3_set_fused(fused)
+    okl.lib().okb_scan_set_mma(mma)
     try:
         scenes = [motion_scene(21, n_views=5, n0=500, n1=700), motion_scene(22, n_views=5, n0=640, n1=520, premated=0.5),
                   motion_scene(23, n_views=5, n0=100, n1=64, premated=0.0)]
@@ -100,4 +102,5 @@ def test_motion_stereo_sequence_equals_oracle(fused):
         assert inserted > 150
     finally:
         okl.lib().okb_m3_set_fused(-1)
+        okl.lib().okb_scan_set_mma(1)
         fe.close()
