@@ -764,18 +764,16 @@ class Replica:
 
 
 def matcher_record(rep):
-    """pairs/s of the Hamming scans of one step against the measured POPC issue rate (bench/ubench_pipes.cu, profiles/popc_rate.json)."""
+    """pairs/s of the Hamming scans of one step against the measured POPC and IMMA issue rates (bench/ubench_pipes.cu, bench/ubench_imma.cu;
+    profiles/popc_rate.json, profiles/imma_rate.json)."""
     cfg, B = rep.cfg, rep.B
     t = rep.time_matchers()
     n = rep.wl_stats["keypoints_per_frame"]
     n0 = float(np.mean([int((v["use"] & v["valid"]).sum()) for vs in rep.wl["older"] for v in vs])) if rep.n_older else 0.0
     m3_pairs = 2 * B * rep.n_older * n0 * n           # two cameras: every (eligible older keypoint, current keypoint) pair is scanned
     m4_pairs = B * n * n
-    rec = {"m1_ms_per_step": t["m1"], "m3_ms_per_step": max(t["m1+m3"] - t["m1"], 0.0), "m4_ms_per_step": t["m4"], "popc_b64_per_pair": 8,
-           "note": "device time of the match stages alone on the features of the last step; M1 is gated by the re-projection radius before any "
-                   "Hamming distance (row binning), M3 and M4 scan every pair; a full 512-bit distance is 16 popc.b32, the scan kernel "
-                   "spends 4 (carry-save tree over the better-discriminating half) and the other half only where a warp still has a pair below "
-                   "the threshold, so frac_of_popc_issue_rate (which charges 16 per pair) can exceed 1"}
+    m1_ms, m3_ms, m4_ms = t["m1"], max(t["m1+m3"] - t["m1"], 0.0), t["m4"]
+    pairs = {"m3": m3_pairs, "m4": m4_pairs}
     rate = imma = None
     try:
         rate = json.load(open(os.path.join(ROOT, "profiles", "popc_rate.json")))["popc_b32_lanes_per_clk_per_sm"]
