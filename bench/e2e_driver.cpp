@@ -259,11 +259,14 @@ static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, st
     fprintf(stderr, "[okb_e2e_replay] per step (ms): detect %.3f / %.3f  map3d %.3f / %.3f  motion %.3f / %.3f  stereo %.3f\n", t_det[0] / n, t_det[1] / n,
             t_m1[0] / n, t_m1[1] / n, t_m3[0] / n, t_m3[1] / n, t_m4 / n);
   }
-  // bytes per step, counted from the copies the three calls issue (row stride = cap)
+  // bytes per step, counted from the copies the calls issue (the feature arrays: the rows filled in some frame of the batch, taken
+  // from the last step; the matcher results: row stride = cap)
   long long h2d = 0, d2h = 0;
   for (int c = 0; c < 2; c++) {
+    int rows = 0;
+    for (int b = 0; b < B; b++) rows = io->n[c][b] > rows ? io->n[c][b] : rows;
     h2d += (long long)B * frame + (long long)io->n_cand[c] * 68 + (long long)B * io->n_lm[c] * 16 + io->n_lm[c];
-    d2h += (long long)B * cap * (28 + 64 + 25) + 8LL * B + (long long)B * cap * 8;
+    d2h += (long long)B * rows * (28 + 64 + 25) + 8LL * B + (long long)B * cap * 8;
   }
   d2h += (long long)B * cap * 41;
   if (io->n_older > 0)

@@ -174,27 +174,35 @@ int okb_detect_describe_batch(okb_context_t* ctx, int cam, int n_frames, const u
   if (rc) return rc;
   OKB_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, 4 * n_frames, cudaMemcpyDeviceToHost, st));
   OKB_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, 4 * n_frames, cudaMemcpyDeviceToHost, st));
-  // keypoint / descriptor payload: capacity-bounded blocks. Page-locked caller buffers receive them directly (rows
-  // k >= n_out[b] are then unspecified); otherwise they land in the pinned staging and are trimmed on the host.
-  const int rows = cap < ws.kp_cap ? cap : ws.kp_cap;
-  const bool out_pinned = rows > 0 && host_pinned(kp_out) && host_pinned(desc_out);
-  if (out_pinned) {
-    OKB_CUDA(cudaMemcpy2DAsync(kp_out, (size_t)cap * sizeof(okb_keypoint_t), ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t),
-                               (size_t)rows * sizeof(okb_keypoint_t), n_frames, cudaMemcpyDeviceToHost, st));
-    OKB_CUDA(cudaMemcpy2DAsync(desc_out, (size_t)cap * 64, ws.d_desc, (size_t)ws.kp_cap * 64, (size_t)rows * 64, n_frames,
-                               cudaMemcpyDeviceToHost, st));
-  } else if (n_frames == 1) {
-    OKB_CUDA(cudaMemcpyAsync(ws.h_kp, ws.d_kp, (size_t)rows * sizeof(okb_keypoint_t), cudaMemcpyDeviceToHost, st));
-    OKB_CUDA(cudaMemcpyAsync(ws.h_desc, ws.d_desc, (size_t)rows * 64, cudaMemcpyDeviceToHost, st));
-  } else {
-    OKB_CUDA(cudaMemcpyAsync(ws.h_kp, ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t) * n_frames, cudaMemcpyDeviceToHost, st));
-    OKB_CUDA(cudaMemcpyAsync(ws.h_desc, ws.d_desc, (size_t)ws.kp_cap * 64 * n_frames, cudaMemcpyDeviceToHost, st));
+  // keypoint / descriptor payload. The counts come back first (one extra synchronisation of a few microseconds): only the rows that
+  // are filled in some frame of the batch cross PCIe (the device arrays are sized by the detector's capacity, ~30 % more than a
+  // capped frame fills). Page-locked caller buffers receive them directly (rows k >= n_out[b] are then unspecified); otherwise they
+  // land in the pinned staging and are trimmed on the host.
+  OKB_CUDA(wait_stream(ctx, st));
+  int max_n = 0;
+  for (int b = 0; b < n_frames; b++) max_n = ws.h_count[b] > max_n ? ws.h_count[b] : max_n;
+  const int rows_cap = cap < ws.kp_cap ? cap : ws.kp_cap;
+  const int rows = max_n < rows_cap ? max_n : rows_cap;
+  const bool out_pinned = rows_cap > 0 && host_pinned(kp_out) && host_pinned(desc_out);
+  if (rows > 0) {
+    if (out_pinned) {
+      OKB_CUDA(cudaMemcpy2DAsync(kp_out, (size_t)cap * sizeof(okb_keypoint_t), ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t),
+                                 (size_t)rows * sizeof(okb_keypoint_t), n_frames, cudaMemcpyDeviceToHost, st));
+      OKB_CUDA(cudaMemcpy2DAsync(desc_out, (size_t)cap * 64, ws.d_desc, (size_t)ws.kp_cap * 64, (size_t)rows * 64, n_frames,
+                                 cudaMemcpyDeviceToHost, st));
+    } else {
+      OKB_CUDA(cudaMemcpy2DAsync(ws.h_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t), ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t),
+                                 (size_t)rows * sizeof(okb_keypoint_t), n_frames, cudaMemcpyDeviceToHost, st));
+      OKB_CUDA(cudaMemcpy2DAsync(ws.h_desc, (size_t)ws.kp_cap * 64, ws.d_desc, (size_t)ws.kp_cap * 64, (size_t)rows * 64, n_frames,
+                                 cudaMemcpyDeviceToHost, st));
+    }
   }
   ws.h_rays_frames = 0;
   if (ws.has_model) {   // the rays of D4 ride along (okb_last_back_projections): no second round trip for computeBackProjections
-    const size_t nr = n_frames == 1 ? (size_t)rows : (size_t)ws.kp_cap * n_frames;
-    OKB_CUDA(cudaMemcpyAsync(ws.h_rays, ws.d_rays, nr * 24, cudaMemcpyDeviceToHost, st));
-    OKB_CUDA(cudaMemcpyAsync(ws.h_rays_valid, ws.d_rays_valid, nr, cudaMemcpyDeviceToHost, st));
+    if (rows > 0) {
+      OKB_CUDA(cudaMemcpy2DAsync(ws.h_rays, (size_t)ws.kp_cap * 24, ws.d_rays, (size_t)ws.kp_cap * 24, (size_t)rows * 24, n_frames, cudaMemcpyDeviceToHost, st));
+      OKB_CUDA(cudaMemcpy2DAsync(ws.h_rays_valid, (size_t)ws.kp_cap, ws.d_rays_valid, (size_t)ws.kp_cap, (size_t)rows, n_frames, cudaMemcpyDeviceToHost, st));
+    }
     ws.h_rays_frames = n_frames;
   }
   OKB_CUDA(wait_stream(ctx, st));
