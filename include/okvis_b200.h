@@ -376,8 +376,7 @@ int okb_stream_stats(okb_context_t* ctx, long long* graph_launches, long long* d
 /* host seconds okb_process_multiframe has spent so far in: staging the inputs, submitting, waiting for the device, copying the results out */
 int okb_stream_timing(okb_context_t* ctx, double* seconds4, int reset);
 /* the per-older-keyframe step of the M3 sequence exists in two forms with identical results: one launch per view (one CTA per frame;
- * default for batches of up to 4 frames) and separate gate / finish / check / commit kernels (larger batches). mode: -1 default rule,
- * 0 separate kernels, 1 one launch per view. Process-wide; a testing / tuning hook. */
+ * the default) and separate gate / finish / check / commit kernels. mode: -1 default, 0 separate kernels, 1 one launch per view. Process-wide; a testing / tuning hook. */
 void okb_m3_set_fused(int mode);
 /* the Hamming scans of the device-resident M3 / M4 matchers exist in two forms with identical results: on the tensor cores (integer
  * MMA over bit planes; default) and with POPC. on = 0 selects the POPC form. Process-wide; a testing / tuning hook. */

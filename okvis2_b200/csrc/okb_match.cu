@@ -87,9 +87,9 @@ __device__ __forceinline__ double depth_in(const double* T, V3 p)
 // ---------------------------------------------------------------------------------------------------------------
 enum { MODE_M2 = 2, MODE_M3 = 3, MODE_M4 = 4 };
 
-// -1: small batches (up to 4 frames) run the gate / finish (/ check / commit) of M3 and M4 as ONE launch per view or pair
-// (k_pair_view, one CTA per frame); larger batches use the separate kernels. 0 / 1 force either form (okb_m3_set_fused).
-static std::atomic<int> g_m3_fused{-1};
+// -1 / 1 (default): the gate / finish (/ check / commit) of M3 and M4 run as ONE launch per view or pair (k_pair_view, one CTA
+// per frame); 0: the separate kernels (okb_m3_set_fused). Both forms give identical results and are in the parity tests.
+static std::atomic<int> g_m3_fused{getenv("OKB_M3_FUSED") ? atoi(getenv("OKB_M3_FUSED")) : -1};   // env: tuning hook
 // 1 (default): the Hamming scans of the device-resident M3 / M4 run on the tensor cores (k_scan_mma); 0: the POPC scan (k_m4_scan)
 static std::atomic<int> g_scan_mma{1};
 
@@ -1549,12 +1549,12 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
   a.out_dist = d_out_dist; a.out_idx = d_out_k1; a.out_hp = d_out_hp_W; a.out_init = d_out_initialisable;
   a.hit_cnt = hit_cnt; a.hit_cap = hit_cap;
   const int fused_mode = g_m3_fused.load();
-  const bool fused = fused_mode >= 0 ? fused_mode != 0 : n_frames <= 4;
+  const bool fused = fused_mode != 0;   // default (-1): the one-launch form for every batch size (measured faster for 1 and for 32 frames)
   if (g_scan_mma.load()) {
-    a.scan_qt = fused ? 32 : 256;   // small batches: short query chunks so that one frame's scan still spreads over the SMs
+    a.scan_qt = n_frames <= 4 ? 32 : 256;   // small batches: short query chunks so that one frame's scan still spreads over the SMs
     k_scan_mma<<<dim3((cap1 + 255) / 256, n_frames, (cap0 + a.scan_qt - 1) / a.scan_qt), 128, 0, st>>>(a, hits, hit_cnt);
   } else {
-    a.scan_qt = fused ? 32 : 128;
+    a.scan_qt = n_frames <= 4 ? 32 : 128;
     k_m4_scan<4><<<dim3((cap1 + 255) / 256, n_frames, (cap0 + a.scan_qt - 1) / a.scan_qt), 256, 0, st>>>(a, hits, hit_cnt);
   }
   if (fused) {
@@ -1729,7 +1729,7 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
   ctx->launches += 2;
   // ---- per older keyframe, in order (what a view inserts is invisible to the next one's candidates)
   const int fused_mode = g_m3_fused.load();
-  const bool fused = fused_mode >= 0 ? fused_mode != 0 : n_frames <= 4;
+  const bool fused = fused_mode != 0;   // default (-1): the one-launch form for every batch size (measured faster for 1 and for 32 frames)
   for (int v = 0; v < n_older; v++) {
     const size_t vo = (size_t)v * cap0;
     a.view_index = v;

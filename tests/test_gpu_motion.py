@@ -56,7 +56,7 @@ def run_device(fe, scenes, cap0, cap1, n_older):
 
 @pytest.mark.parametrize("fused,mma", [(1, 1), (0, 1), (1, 0), (0, 0)])
 def test_motion_stereo_sequence_equals_oracle(fused, mma):
-    """both forms of the per-view step (one launch per view, the small-batch default; separate kernels) x both forms of the
+    """both forms of the per-view step (one launch per view, the default; separate kernels) x both forms of the
     Hamming scan (tensor cores, the default; POPC)"""
     fe = Frontend(0)
     okl.lib().okb_m3_set_fused(fused)
