@@ -1146,8 +1146,9 @@ def main():
     ap.add_argument("--config", default="euroc", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other workloads")
-    ap.add_argument("--e2e-lanes", "--lanes", dest="e2e_lanes", type=int, default=4,
-                    help="independent sequences in flight per GPU (own library handle each) in the value and e2e legs")
+    ap.add_argument("--e2e-lanes", "--lanes", dest="e2e_lanes", type=int, default=0,
+                    help="independent sequences in flight per GPU (own library handle each) in the value and e2e legs; default: 4, fewer "
+                         "when world x lanes x 3 host threads would outnumber the box's cores (never below 2)")
     args = ap.parse_args()
     name, cfg = args.config, CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -1164,7 +1165,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank); sampler.start()   # samples clocks through every leg
-    lanes = max(1, args.e2e_lanes)
+    lanes = args.e2e_lanes
+    if lanes <= 0:
+        # every sequence costs three host threads in the e2e leg (two cameras + the submitting thread); an oversubscribed host was what
+        # limited the end-to-end figure at 8 GPUs in round 1, and one sequence alone now reaches 94 % of the device throughput
+        lanes = max(2, min(4, (os.cpu_count() or 8) // (3 * world)))
     if "rig" in cfg:
         rec = run_sharded(args, name, cfg, rank, world, local_rank, args.steps)
         clocks = sampler.stop()
