@@ -371,7 +371,9 @@ __global__ void __launch_bounds__(TH * 4, 256 / TH) k_score_nms(const __grid_con
   __shared__ __align__(16) uint32_t planes[2][kImgH][kPlaneW];   // E and O
   // score tile with a zero frame: row 0 and row TH + 1 stay zero, bytes 64..79 of every row stay zero, so the 8 neighbours
   // of any tile pixel can be read without bounds checks (outside the tile = 0 = never beats or ties a strong pixel)
-  __shared__ __align__(16) uint8_t sc[TH + 2][kScPitch];
+  // (16 zero bytes in front: the upper-left neighbour of tile pixel (0, 0) is the byte before row 0)
+  __shared__ __align__(16) uint8_t sc_raw[16 + (TH + 2) * kScPitch];
+  uint8_t (*sc)[kScPitch] = reinterpret_cast<uint8_t (*)[kScPitch]>(sc_raw + 16);
   uint32_t (*pe)[kPlaneW] = planes[0];
   uint32_t (*po)[kPlaneW] = planes[1];
   __shared__ __align__(8) uint64_t bar;
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(TH * 4, 256 / TH) k_score_nms(const __grid_con
     tma_load_3d(&tile[0][0], &maps.m[e.layer], &bar, e.x0 - kHaloX, e.y0 - 3, f);
   };
   if (threadIdx.x == 0) { mbar_init(&bar, 1); n_strong2[0] = n_strong2[1] = 0; tma_failed = 0; }
-  for (int i = threadIdx.x; i < (TH + 2) * kScPitch / 4; i += kThreads) reinterpret_cast<uint32_t*>(&sc[0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < (16 + (TH + 2) * kScPitch) / 4; i += kThreads) reinterpret_cast<uint32_t*>(sc_raw)[i] = 0u;
   __syncthreads();
   TileEntry te;
   { const int4 q = __ldg(reinterpret_cast<const int4*>(tiles) + tl); te.layer = q.x; te.x0 = q.y; te.y0 = q.z; te.pad = 0; }
