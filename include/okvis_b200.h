@@ -378,9 +378,9 @@ int okb_stream_timing(okb_context_t* ctx, double* seconds4, int reset);
 /* the per-older-keyframe step of the M3 sequence exists in two forms with identical results: one launch per view (one CTA per frame;
  * the default) and separate gate / finish / check / commit kernels. mode: -1 default, 0 separate kernels, 1 one launch per view. Process-wide; a testing / tuning hook. */
 void okb_m3_set_fused(int mode);
-/* the Hamming scans of the device-resident M3 / M4 matchers exist in two forms with identical results: on the tensor cores (integer
- * MMA over bit planes; default) and with POPC. on = 0 selects the POPC form. Process-wide; a testing / tuning hook. */
-void okb_scan_set_mma(int on);
+/* the Hamming scans of the device-resident M3 / M4 matchers exist in three forms with identical results: mode 2 (default) tcgen05
+ * integer MMA with TMEM accumulators, 1 legacy integer MMA (mma.sync), 0 POPC. Process-wide; a testing / tuning hook. */
+void okb_scan_set_mma(int mode);
 
 /* ---- P1: landmark-candidate preparation. Replaces the serial host loop of Frontend::matchToMap that
  *      builds landmarksToMatch / descriptorPool for one camera (okvis_frontend/src/Frontend.cpp:1196-1360; pose lookups

@@ -75,6 +75,9 @@ int okb_create(int device, int n_cams, const okb_camera_config_t* cfgs, okb_cont
   }
   rc = match_init(ctx);
   if (rc != OKB_OK) { okb_destroy(ctx); return rc; }
+  if (cudaMalloc(&ctx->d_scan_status, 4) != cudaSuccess || cudaMemset(ctx->d_scan_status, 0, 4) != cudaSuccess) {
+    set_error("okb_create: scan status word"); okb_destroy(ctx); return OKB_ERR_CUDA;
+  }
   {
     // self-check of the gate constants: gate_cos must return what THIS machine's libm returns (it restates glibc's
     // algorithm, okb_gatecos.h); 65 536 arguments over the gate's range
@@ -103,6 +106,7 @@ void okb_destroy(okb_context_t* ctx)
   prepare_free(ctx);
   aux_free(ctx);
   if (ctx->stereo_scratch) cudaFree(ctx->stereo_scratch);
+  if (ctx->d_scan_status) cudaFree(ctx->d_scan_status);
   if (ctx->motion.d) cudaFree(ctx->motion.d);
   if (ctx->motion.h) cudaFreeHost(ctx->motion.h);
   tables_free(ctx);
@@ -124,6 +128,11 @@ int okb_sync(okb_context_t* ctx)
   OKB_CUDA(cudaSetDevice(ctx->device));
   for (int i = 0; i < ctx->n_cams; i++) OKB_CUDA(cudaStreamSynchronize(ctx->cams[i].stream));
   for (int i = 0; i < kMatchSlots; i++) OKB_CUDA(cudaStreamSynchronize(ctx->match_slots[i].stream));
+  if (ctx->d_scan_status) {
+    int32_t st = 0;
+    OKB_CUDA(cudaMemcpy(&st, ctx->d_scan_status, 4, cudaMemcpyDeviceToHost));
+    if (st) { set_error("okb_sync: the tensor-core Hamming scan reported a timed-out barrier wait (flags 0x%x)", st); return OKB_ERR_CUDA; }
+  }
   return OKB_OK;
 }
 

@@ -161,6 +161,7 @@ struct okb_context {
   int blocking_sync = 0;     // 1: host-buffer entry points wait on a cudaEventBlockingSync event (the thread sleeps) instead of spinning
   void* prepare = nullptr;   // okb::PrepareState (okb_prepare.cu): keyframe feature store + P1 workspace
   void* aux = nullptr;       // okb::AuxState (okb_aux.cu): keyframe-overlap / BoW workspaces
+  int32_t* d_scan_status = nullptr;   // one word: error flags of k_scan_umma (a timed-out barrier wait: never non-zero in a correct build)
   void* stream_state = nullptr;   // okb::StreamState (okb_stream.cu): arenas + CUDA graph of okb_process_multiframe
 };
 

@@ -17,6 +17,7 @@
 #include <atomic>
 
 #include "okb_internal.h"
+#include "okb_umma.h"
 #include "okb_gatecos.h"
 #include "okb_camdev.h"
 
@@ -90,8 +91,9 @@ enum { MODE_M2 = 2, MODE_M3 = 3, MODE_M4 = 4 };
 // -1 / 1 (default): the gate / finish (/ check / commit) of M3 and M4 run as ONE launch per view or pair (k_pair_view, one CTA
 // per frame); 0: the separate kernels (okb_m3_set_fused). Both forms give identical results and are in the parity tests.
 static std::atomic<int> g_m3_fused{getenv("OKB_M3_FUSED") ? atoi(getenv("OKB_M3_FUSED")) : -1};   // env: tuning hook
-// 1 (default): the Hamming scans of the device-resident M3 / M4 run on the tensor cores (k_scan_mma); 0: the POPC scan (k_m4_scan)
-static std::atomic<int> g_scan_mma{1};
+// the Hamming scans of the device-resident M3 / M4: 2 (default) tcgen05 + TMEM (k_scan_umma), 1 legacy integer MMA (k_scan_mma),
+// 0 POPC (k_m4_scan); identical results (okb_scan_set_mma)
+static std::atomic<int> g_scan_mma{getenv("OKB_SCAN_MODE") ? atoi(getenv("OKB_SCAN_MODE")) : 2};   // env: tuning hook
 
 struct MatchArgs {
   int nq, nc;
@@ -872,6 +874,231 @@ __global__ void __launch_bounds__(128) k_scan_mma(MatchArgs a, uint2* hits, int3
   }
 }
 
+// ---- the Hamming scan on the 5th-generation tensor cores: tcgen05.mma kind::i8, accumulators in TMEM -----------------------
+// Same arithmetic as k_scan_mma (popc(a & b) as a dot product of bit planes), but as a 128 x 128 x 512 integer MMA per tile:
+// operands are u8 planes in shared memory (K-major, no swizzle: 8-row x 16-byte core matrices; K byte 32 j + 4 i + b <-> bit
+// 8 b + i of descriptor word j, value 128 on both sides, so the accumulator is 16384 popc(a & b)), 16 tcgen05.mma of K = 32 per
+// tile issued by ONE thread, D (128 lanes x 128 columns of s32) in TMEM, read back with tcgen05.ld for the hit test.
+// CTA = 13 warps, one CTA per SM (192 KB of operands). The CTA keeps ONE candidate tile (128 descriptors, expanded once) and streams
+// query tiles of 128 through a double-buffered A operand and a double-buffered accumulator, three roles running concurrently:
+//   producers (warps 8-11, thread = tile row): expand query tile t into A[t & 1] (wait for the MMAs of tile t - 2: a_free), arrive
+//             on a_full;
+//   MMA (warp 12, one thread): waits a_full (and acc_free of tile t - 2), 16 MMAs, tcgen05.commit -> a_free and acc_full;
+//   epilogue (warps 0-7: TMEM lanes 32 (w % 4).., column half w / 4): waits acc_full, tcgen05.ld 32 columns at a time, running
+//             maximum of acc - 8192 popc(b), and only if that exceeds the row's limit 8192 (popc(a) - thr) the columns are looked
+//             at one by one (hits are a handful per query); arrive on acc_free.
+// so the MMAs of tile t run under the epilogue of tile t - 1 and the expansion of tile t + 1; the roles share nothing but the
+// operands, the accumulators and the four barrier pairs (the epilogue recomputes popc(a) from the 64 bytes the producers just read). Every barrier wait is bounded
+// (a timeout raises the context's scan-status word, which okb_sync reports, and ends the kernel). bench/umma_probe.cu checks the tile arithmetic stand-alone.
+constexpr int kUmmaRows = 128, kUmmaChunk = kUmmaRows * 16, kUmmaTile = 32 * kUmmaChunk;   // 64 KB per operand tile
+constexpr int kUmmaSmem = 3 * kUmmaTile + 1024;
+
+struct UmmaRow { uint4 v[4]; };
+__device__ __forceinline__ UmmaRow umma_load_row(const uint4* src /* 4 x uint4, or nullptr: zeros */)
+{
+  UmmaRow w;
+#pragma unroll
+  for (int i = 0; i < 4; i++) w.v[i] = src ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+  return w;
+}
+__device__ __forceinline__ int umma_popc_row(const UmmaRow& w)
+{
+  int pc = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) pc += __popc(w.v[i].x) + __popc(w.v[i].y) + __popc(w.v[i].z) + __popc(w.v[i].w);
+  return pc;
+}
+// descriptor row r (16 words) -> u8 bit planes of the operand tile: K byte 32 j + 4 i + b <-> bit 8 b + i of word j, value 128
+__device__ __forceinline__ void umma_expand_row(uint8_t* tile, int r, const UmmaRow& row)
+{
+#pragma unroll
+  for (int q4 = 0; q4 < 4; q4++) {
+    const uint32_t w4[4] = {row.v[q4].x, row.v[q4].y, row.v[q4].z, row.v[q4].w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t w = w4[k];
+      const int j = 4 * q4 + k;
+      uint4 lo, hi;
+      lo.x = (w << 7) & 0x80808080u; lo.y = (w << 6) & 0x80808080u; lo.z = (w << 5) & 0x80808080u; lo.w = (w << 4) & 0x80808080u;
+      hi.x = (w << 3) & 0x80808080u; hi.y = (w << 2) & 0x80808080u; hi.z = (w << 1) & 0x80808080u; hi.w = w & 0x80808080u;
+      uint8_t* p = tile + (size_t)(2 * j) * kUmmaChunk + (r >> 3) * 128 + (r & 7) * 16;
+      *reinterpret_cast<uint4*>(p) = lo;
+      *reinterpret_cast<uint4*>(p + kUmmaChunk) = hi;
+    }
+  }
+}
+
+constexpr int kUmmaThreads = 13 * 32;   // warps 0-7 epilogue, 8-11 producers, 12 MMA issue + TMEM allocation
+
+// the queries of one view (M3) or of the frame (M4) as a CTA sees them
+struct UmmaView { const uint4* q_desc; const int32_t* list; int q_begin, q_end; size_t fq; uint2* hits; int32_t* hit_cnt; };
+
+__global__ void __launch_bounds__(kUmmaThreads, 1) k_scan_umma(MatchArgs a, uint2* hits, int32_t* hit_cnt, int32_t* status)
+{
+  using namespace okb::umma;
+  extern __shared__ uint8_t umma_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(umma_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem; uint8_t* sA0 = smem + kUmmaTile; uint8_t* sA1 = smem + 2 * kUmmaTile;
+  __shared__ uint64_t a_full[2], a_free[2], acc_full[2], acc_free[2];
+  __shared__ int s_pb[kUmmaRows];       // 8192 popc(candidate)
+  __shared__ uint32_t tmem_base;
+  __shared__ int failed;
+  const int frame = blockIdx.y;
+  const size_t fc = (size_t)frame * a.c_stride;
+  const int nc = min(a.c_count[frame], a.nc);
+  const int c_base = blockIdx.x * kUmmaRows;
+  if (c_base >= nc) return;   // whole CTA
+  // which views and which part of their query lists this CTA streams against its candidate tile: scan_qt > 0: one view, one chunk of
+  // scan_qt queries (blockIdx.z = view * chunks + chunk; small batches, many short CTAs); scan_qt == 0: every view, all queries
+  // (blockIdx.z = 0; the candidate tile is expanded once for all of them)
+  const int n_views = a.scan_views > 0 ? a.scan_views : 1;
+  const bool merged = a.scan_qt == 0;
+  const int v_begin = merged ? 0 : (a.scan_views > 0 ? (int)blockIdx.z / a.scan_chunks : 0), v_end = merged ? n_views : v_begin + 1;
+  const int qz = merged ? 0 : (a.scan_views > 0 ? (int)blockIdx.z % a.scan_chunks : (int)blockIdx.z);
+  auto view_of = [&](int vz) {
+    UmmaView V;
+    const M3View* view = a.views ? &a.views[(size_t)frame * a.view_stride + a.view_index + vz] : nullptr;   // M3: queries = an older view
+    V.fq = (size_t)frame * a.q_stride + (size_t)vz * a.nq;
+    V.q_desc = view ? reinterpret_cast<const uint4*>(view->desc) : reinterpret_cast<const uint4*>(a.q_desc) + V.fq * 4;
+    V.list = a.q_list ? a.q_list + ((size_t)vz * gridDim.y + frame) * a.nq : nullptr;
+    const int nq_all = view ? min(view->n, a.nq) : min(a.q_count[frame], a.nq);
+    const int nq = V.list ? min(a.q_list_cnt[(size_t)vz * gridDim.y + frame], nq_all) : nq_all;
+    V.q_begin = merged ? 0 : min(qz * a.scan_qt, nq); V.q_end = merged ? nq : min(nq, (qz + 1) * a.scan_qt);
+    V.hits = hits + ((size_t)vz * gridDim.y + frame) * a.hit_cap; V.hit_cnt = hit_cnt + (size_t)vz * gridDim.y + frame;
+    return V;
+  };
+  if (!merged && view_of(v_begin).q_begin >= view_of(v_begin).q_end) return;   // whole CTA
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; b++) { bar_init(&a_full[b], 4); bar_init(&a_free[b], 1); bar_init(&acc_full[b], 1); bar_init(&acc_free[b], 8); }
+    bar_init_fence();
+    failed = 0;
+  }
+  if (warp == 12) tmem_alloc(&tmem_base, 256);
+  if (warp >= 8 && warp < 12) {   // the candidate tile, once per CTA
+    const int r = threadIdx.x - 256, col = c_base + r;
+    const UmmaRow row = umma_load_row(col < nc ? reinterpret_cast<const uint4*>(a.c_desc) + (fc + col) * 4 : nullptr);
+    umma_expand_row(sB, r, row);
+    s_pb[r] = 8192 * umma_popc_row(row);
+    fence_smem_to_async();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t td = tmem_base;
+  if (warp == 12) {
+    // ---- MMA issue: one thread
+    if (lane == 0) {
+      const uint32_t idesc = idesc_u8(kUmmaRows, kUmmaRows);
+      const uint32_t b_addr = smem_addr(sB), a_addr[2] = {smem_addr(sA0), smem_addr(sA1)};
+      int t = 0; bool ok = true;
+#pragma unroll 1
+      for (int vz = v_begin; vz < v_end && ok; vz++) {
+        const UmmaView V = view_of(vz);
+#pragma unroll 1
+        for (int j0 = V.q_begin; j0 < V.q_end; j0 += kUmmaRows, t++) {
+          const int buf = t & 1;
+          if (!bar_wait(&a_full[buf], (uint32_t)((t >> 1) & 1), &failed)) { ok = false; break; }
+          if (t >= 2 && !bar_wait(&acc_free[buf], (uint32_t)(((t >> 1) - 1) & 1), &failed)) { ok = false; break; }
+          fence_after_sync();
+#pragma unroll 1
+          for (int s = 0; s < 16; s++)
+            mma_u8(td + buf * kUmmaRows, smem_desc(a_addr[buf] + s * 2 * kUmmaChunk, kUmmaChunk, 128), smem_desc(b_addr + s * 2 * kUmmaChunk, kUmmaChunk, 128),
+                   idesc, s > 0);
+          mma_commit(&a_free[buf]);     // the A buffer may be overwritten ...
+          mma_commit(&acc_full[buf]);   // ... and the accumulator read, once these MMAs have completed
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ---- producers: thread = row of the query tile; the next tile's row is in flight while this one is expanded
+    const int r = threadIdx.x - 256;
+    int t = 0; bool ok = true;
+#pragma unroll 1
+    for (int vz = v_begin; vz < v_end && ok; vz++) {
+      const UmmaView V = view_of(vz);
+      auto row_of = [&](int j0) {
+        const int j = j0 + r;
+        const int qi = j < V.q_end ? (V.list ? __ldg(&V.list[j]) : j) : -1;
+        return umma_load_row(qi >= 0 ? V.q_desc + (size_t)qi * 4 : nullptr);
+      };
+      UmmaRow cur = row_of(V.q_begin);
+#pragma unroll 1
+      for (int j0 = V.q_begin; j0 < V.q_end; j0 += kUmmaRows, t++) {
+        const int buf = t & 1;
+        const UmmaRow nxt = j0 + kUmmaRows < V.q_end ? row_of(j0 + kUmmaRows) : cur;
+        if (t >= 2 && !bar_wait(&a_free[buf], (uint32_t)(((t >> 1) - 1) & 1), &failed)) { ok = false; break; }
+        umma_expand_row(buf ? sA1 : sA0, r, cur);
+        fence_smem_to_async();
+        __syncwarp();
+        if (lane == 0) bar_arrive(&a_full[buf]);
+        cur = nxt;
+      }
+    }
+  } else {
+    // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31 (= tile rows) and the column half w / 4
+    const int r = (warp & 3) * 32 + lane, chalf = (warp >> 2) * 64;
+    const int thr = (int)a.thr;
+    int t = 0; bool ok = true;
+#pragma unroll 1
+    for (int vz = v_begin; vz < v_end && ok; vz++) {
+      const UmmaView V = view_of(vz);
+#pragma unroll 1
+      for (int j0 = V.q_begin; j0 < V.q_end; j0 += kUmmaRows, t++) {
+        const int buf = t & 1;
+        // this row's query and its popcount (the producers have just pulled the same 64 bytes through L1 / L2)
+        const int j = j0 + r;
+        const int q = j < V.q_end ? (V.list ? __ldg(&V.list[j]) : j) : -1;
+        const int pa = q >= 0 ? umma_popc_row(umma_load_row(V.q_desc + (size_t)q * 4)) : 0;
+        const int rowlim = 8192 * (pa - thr);   // hit: acc - 8192 popc(b) > rowlim  <=>  popc(a) + popc(b) - 2 popc(a & b) < thr
+        if (!bar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1), &failed)) { ok = false; break; }
+        fence_after_sync();
+#pragma unroll 1
+        for (int c0 = chalf; c0 < chalf + 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(td + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * kUmmaRows + c0), v);
+          int m = -0x7fffffff;
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const int4 pb = *reinterpret_cast<const int4*>(&s_pb[c0 + k]);
+            m = max(m, max(max((int)v[k] - pb.x, (int)v[k + 1] - pb.y), max((int)v[k + 2] - pb.z, (int)v[k + 3] - pb.w)));
+          }
+          if (m > rowlim && q >= 0) {   // rare: a handful of pairs per query are below the threshold
+#pragma unroll
+            for (int k = 0; k < 32; k++) {   // unrolled: v stays in registers
+              const int col = c_base + c0 + k;
+              if ((int)v[k] - s_pb[c0 + k] > rowlim && col < nc && (a.q_use == nullptr || a.q_use[V.fq + q]) && a.c_valid[fc + col]) {
+                const uint32_t d = (uint32_t)(pa + (s_pb[c0 + k] >> 13) - 2 * (int)(v[k] >> 14));
+                const int pos = atomicAdd(V.hit_cnt, 1);
+                if (pos < a.hit_cap) V.hits[pos] = make_uint2((d << 20) | (uint32_t)q, (uint32_t)col);   // d <= 512, q < 2^20
+              }
+            }
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) bar_arrive(&acc_free[buf]);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(td, 256);
+  if (threadIdx.x == 0 && failed) atomicOr(status, 32);   // one word per context, read by okb_sync
+}
+
+// one opt-in to the kernel's 193 KB of dynamic shared memory per device
+static int umma_prepare()
+{
+  static std::mutex m; static std::vector<int> done;
+  int dev = 0; OKB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(m);
+  for (int d : done) if (d == dev) return OKB_OK;
+  OKB_CUDA(cudaFuncSetAttribute(k_scan_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmem));
+  done.push_back(dev);
+  return OKB_OK;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128) k_m4_gate(MatchArgs a, const uint2* hits, unsigned long long* best)
 {
@@ -1550,7 +1777,12 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
   a.hit_cnt = hit_cnt; a.hit_cap = hit_cap;
   const int fused_mode = g_m3_fused.load();
   const bool fused = fused_mode != 0;   // default (-1): the one-launch form for every batch size (measured faster for 1 and for 32 frames)
-  if (g_scan_mma.load()) {
+  const int scan_mode = g_scan_mma.load();
+  if (scan_mode == 2) {
+    a.scan_qt = n_frames <= 4 ? 128 : 0;   // 0: one CTA per (candidate tile, frame) streams all queries
+    { const int rc = umma_prepare(); if (rc) return rc; }
+    k_scan_umma<<<dim3((cap1 + 127) / 128, n_frames, a.scan_qt ? (cap0 + a.scan_qt - 1) / a.scan_qt : 1), kUmmaThreads, kUmmaSmem, st>>>(a, hits, hit_cnt, ctx->d_scan_status);
+  } else if (scan_mode == 1) {
     a.scan_qt = n_frames <= 4 ? 32 : 256;   // small batches: short query chunks so that one frame's scan still spreads over the SMs
     k_scan_mma<<<dim3((cap1 + 255) / 256, n_frames, (cap0 + a.scan_qt - 1) / a.scan_qt), 128, 0, st>>>(a, hits, hit_cnt);
   } else {
@@ -1634,7 +1866,8 @@ int okb::motion_restage(MotionScratch& ms, int n_frames, int n_older, const okb_
 }
 
 extern "C" void okb_m3_set_fused(int mode) { g_m3_fused.store(mode < 0 ? -1 : (mode ? 1 : 0)); }
-extern "C" void okb_scan_set_mma(int on) { g_scan_mma.store(on ? 1 : 0); }
+extern "C" void okb_scan_set_mma(int mode) { g_scan_mma.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
+
 
 int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, int cap1, const okb_keypoint_t* d_kp1, const uint8_t* d_desc1,
                          const int32_t* d_count1, const okb_camera_model_t* model, int width, int height, const double* T_WC1, const double* T_CW1,
@@ -1715,9 +1948,18 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
     MatchArgs s = a;
     s.q_use = use0; s.view_index = 0; s.scan_views = n_older; s.hit_cnt = hit_cnt;
     static const int qt_env = getenv("OKB_SCAN_QT") ? atoi(getenv("OKB_SCAN_QT")) : 0;   // tuning hook
-    if (g_scan_mma.load()) {
-      // tensor-core scan over the eligible keypoints of every view; small batches: short query chunks so that one frame's scan
-      // still spreads over the SMs
+    const int scan_mode = g_scan_mma.load();
+    if (scan_mode == 2) {
+      // tcgen05 scan over the eligible keypoints of every view: 128-candidate tiles, query chunks of 512 (128 for small batches:
+      // one frame's scan then still spreads over the SMs)
+      s.q_list = q_list; s.q_list_cnt = q_list_cnt;
+      // batches: one CTA per (candidate tile, frame) streams the eligible keypoints of ALL views against its tile (expanded once);
+      // small batches: one CTA per (candidate tile, view, chunk of 128 queries), so that a single frame still spreads over the SMs
+      s.scan_qt = n_frames >= 8 ? 0 : 128; s.scan_chunks = s.scan_qt ? (cap0 + s.scan_qt - 1) / s.scan_qt : 1;
+      { const int rc = umma_prepare(); if (rc) return rc; }
+      k_scan_umma<<<dim3((cap1 + 127) / 128, n_frames, s.scan_qt ? n_older * s.scan_chunks : 1), kUmmaThreads, kUmmaSmem, st>>>(s, hits, hit_cnt, ctx->d_scan_status);
+    } else if (scan_mode == 1) {
+      // legacy integer MMA scan; small batches: short query chunks
       s.q_list = q_list; s.q_list_cnt = q_list_cnt;
       s.scan_qt = qt_env > 0 ? std::min(qt_env, 256) : (n_frames >= 8 ? 256 : 32); s.scan_chunks = (cap0 + s.scan_qt - 1) / s.scan_qt;
       k_scan_mma<<<dim3((cap1 + 255) / 256, n_frames, n_older * s.scan_chunks), 128, 0, st>>>(s, hits, hit_cnt);

@@ -1,0 +1,88 @@
+// okb_umma.h -- tcgen05 / TMEM building blocks of the Hamming scan (k_scan_umma, okb_match.cu; bench/umma_probe.cu).
+// sm_100a only. Operand layout, descriptors and instruction encoding follow the PTX ISA's tcgen05 chapter; the bit positions
+// were cross-read against the CUTLASS 4.5 headers vendored in this image (cute/arch/mma_sm100_desc.hpp).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace okb {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier (shared::cta) -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bar_arrive(uint64_t* bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
+__device__ __forceinline__ bool bar_try_wait(uint64_t* bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a wrong descriptor or count must end the kernel with an error flag, not hang the GPU
+__device__ __forceinline__ bool bar_wait(uint64_t* bar, uint32_t parity, volatile int* failed)
+{
+  const long long t0 = clock64();
+  while (!bar_try_wait(bar, parity)) {
+    if (*failed) return false;
+    if (clock64() - t0 > 200000000ll) { *failed = 1; return false; }   // ~0.1 s
+  }
+  return true;
+}
+
+// ---- TMEM -------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols)   // one full warp
+{
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)     // the same warp
+{ asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the tensor core's (async proxy) operand reads
+__device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive 32-bit columns: register j of lane l = TMEM[lane_base + l][col + j]
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
+{
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                 "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                 "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                 "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- MMA ----------------------------------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices of 128 contiguous bytes;
+// lbo = byte distance between the two 16-byte K chunks of one MMA (K = 32 bytes of u8), sbo = byte distance between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) |
+         (1ull << 46);   // version 1 (Blackwell); base offset 0; layout type 0 = SWIZZLE_NONE
+}
+// instruction descriptor, kind::i8: D s32 (c_format 2 at bit 4), A and B unsigned 8 bit (0 at bits 7 and 10), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t idesc_u8(int M, int N) { return (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
+__device__ __forceinline__ void mma_u8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// all MMAs issued so far by this thread arrive on the mbarrier when they have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar)
+{ asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory"); }
+
+}  // namespace umma
+}  // namespace okb

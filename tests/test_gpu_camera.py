@@ -70,12 +70,12 @@ def T_CW(C_WC, r):
     return T.reshape(12)
 
 
-@pytest.fixture(params=["mma", "popc"])
+@pytest.fixture(params=["umma", "mma", "popc"])
 def scan_form(request):
-    """both forms of the Hamming scan of the device-resident matchers: tensor cores (default) and POPC"""
-    okl.lib().okb_scan_set_mma(1 if request.param == "mma" else 0)
+    """the three forms of the Hamming scan of the device-resident matchers: tcgen05 + TMEM (default), legacy integer MMA, POPC"""
+    okl.lib().okb_scan_set_mma({"umma": 2, "mma": 1, "popc": 0}[request.param])
     yield request.param
-    okl.lib().okb_scan_set_mma(1)
+    okl.lib().okb_scan_set_mma(2)
 
 
 def test_device_resident_stereo_pipeline_equals_oracle(scan_form):

@@ -54,10 +54,10 @@ def run_device(fe, scenes, cap0, cap1, n_older):
             fl.cpu().numpy().reshape(sh), d_m.cpu().numpy())
 
 
-@pytest.mark.parametrize("fused,mma", [(1, 1), (0, 1), (1, 0), (0, 0)])
+@pytest.mark.parametrize("fused,mma", [(1, 2), (0, 2), (1, 1), (0, 1), (1, 0), (0, 0)])
 def test_motion_stereo_sequence_equals_oracle(fused, mma):
     """both forms of the per-view step (one launch per view, the default; separate kernels) x both forms of the
-    Hamming scan (tensor cores, the default; POPC)"""
+    Hamming scan (2 tcgen05 + TMEM, the default; 1 legacy integer MMA; 0 POPC)"""
     fe = Frontend(0)
     okl.lib().okb_m3_set_fused(fused)
     okl.lib().okb_scan_set_mma(mma)
@@ -102,5 +102,35 @@ def test_motion_stereo_sequence_equals_oracle(fused, mma):
         assert inserted > 150
     finally:
         okl.lib().okb_m3_set_fused(-1)
-        okl.lib().okb_scan_set_mma(1)
+        okl.lib().okb_scan_set_mma(2)
+        fe.close()
+
+
+@pytest.mark.parametrize("mma", [2, 1])
+def test_motion_stereo_sequence_batch_of_nine(mma):
+    """a batch large enough for the batched forms of the scan (tcgen05: one CTA per candidate tile streams the eligible keypoints of
+    all views; more than one candidate tile; several query tiles per view)"""
+    fe = Frontend(0)
+    okl.lib().okb_scan_set_mma(mma)
+    try:
+        scenes = [motion_scene(40 + i, n_views=4, n0=260 + 37 * (i % 3), n1=300 + 29 * (i % 4), premated=0.3 if i % 2 else 0.0) for i in range(9)]
+        cap0, cap1, n_older = 384, 448, 4
+        k1, dist, hp, fl, m1 = run_device(fe, scenes, cap0, cap1, n_older)
+        inserted = 0
+        for b, s in enumerate(scenes):
+            intr = s["intr"]; cur = s["cur"]
+            rays1, valid1 = oracle.back_project(1, intr[0], intr[1], intr[2], intr[3], list(intr[4:8]), kp_of(cur["xy"], cur["size"]))
+            ref, rm = oracle.match_motion_stereo_sequence(oracle_views(s), cur["desc"], rays1, valid1, cur["xy"], s["T_WC1"], s["T_CW1"], 1,
+                                                          intr, s["W"], s["H"], 60, cur["matched"])
+            for v, (rk1, rdist, rhp, rfl) in enumerate(ref):
+                n = len(rk1)
+                assert np.array_equal(k1[b, v, :n], rk1), (b, v)
+                assert np.array_equal(dist[b, v, :n], rdist), (b, v)
+                assert np.array_equal(hp[b, v, :n].view(np.uint64), rhp.view(np.uint64)), (b, v)
+                assert np.array_equal(fl[b, v, :n], rfl), (b, v)
+                inserted += int(((rfl & 4) != 0).sum())
+            assert np.array_equal(m1[b, :len(rm)], rm)
+        assert inserted > 300
+    finally:
+        okl.lib().okb_scan_set_mma(2)
         fe.close()
