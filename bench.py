@@ -781,12 +781,14 @@ def matcher_record(rep):
     except Exception:
         pass
     rec = {"m1_ms_per_step": m1_ms, "m3_ms_per_step": m3_ms, "m4_ms_per_step": m4_ms,
-           "scan": "tensor cores: Hamming = popc(a) + popc(b) - 2 popc(a & b), popc(a & b) as a 0/1 dot product over bit planes on the integer MMA "
-                   "path (k_scan_mma: mma.sync.m16n8k32.u8 = IMMA.16832, 16 per 16x8 tile of 512-bit pairs; operands expanded in registers)",
+           "scan": "tensor cores (tcgen05): Hamming = popc(a) + popc(b) - 2 popc(a & b), popc(a & b) as a dot product of u8 bit planes: "
+                   "k_scan_umma = tcgen05.mma kind::i8, 128 x 128 x 512 per tile, operands expanded into shared memory by producer warps, "
+                   "accumulators in TMEM, hit test in the tcgen05.ld epilogue",
            "note": "device time of the match stages alone on the features of the last step (scan + gate + outputs + checks); M1 is gated by the "
                    "re-projection radius before any Hamming distance (row binning), M3 and M4 scan every eligible pair. Two ceilings are "
-                   "quoted for the scan: the measured POPC issue rate (16 popc.b32 per pair; what the previous form of the scan ran at) and the "
-                   "measured IMMA.16832 issue rate (bench/ubench_imma.cu, 16 per 128 pairs)",
+                   "quoted for the scan: the measured POPC issue rate (16 popc.b32 per pair; what the round-1 form of the scan ran at) and the "
+                   "measured legacy IMMA.16832 issue rate (bench/ubench_imma.cu, 16 per 128 pairs; the mid-round form); the tcgen05 form's own "
+                   "ceiling is 83 cycles per 128 x 128 x 32 MMA (bench/umma_probe.cu) = 1.8e12 pairs/s",
            "measured_popc_b32_lanes_per_clk_per_sm": rate, "measured_imma_dot512_per_s": imma}
     for key, ms in (("m3", m3_ms), ("m4", m4_ms)):
         if ms > 0:

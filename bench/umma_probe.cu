@@ -25,7 +25,7 @@ __device__ __forceinline__ void expand_row(uint8_t* tile, int r, const uint32_t*
   }
 }
 
-__global__ void __launch_bounds__(160) k_probe(const uint32_t* A, const uint32_t* B, int32_t* D, int* failed_out)
+__global__ void __launch_bounds__(160) k_probe(const uint32_t* A, const uint32_t* B, int32_t* D, int* failed_out, int reps, long long* cycles)
 {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sa = smem; uint8_t* sb = smem + 65536;
@@ -53,15 +53,29 @@ __global__ void __launch_bounds__(160) k_probe(const uint32_t* A, const uint32_t
       mma_u8(td, da, db, idesc, s > 0);
     }
     mma_commit(&bar_done);
+    if (reps > 0) {
+      // issue-rate measurement: reps more tiles of 16 MMAs back to back (same operands, accumulate), one commit at the end
+      __shared__ uint64_t bar_rate;
+      bar_init(&bar_rate, 1); bar_init_fence();
+      const long long t0 = clock64();
+      for (int i = 0; i < reps; i++)
+#pragma unroll 1
+        for (int s = 0; s < 16; s++)
+          mma_u8(td, smem_desc(smem_addr(sa) + s * 2 * kChunkBytes, kChunkBytes, 128), smem_desc(smem_addr(sb) + s * 2 * kChunkBytes, kChunkBytes, 128), idesc, 1);
+      mma_commit(&bar_rate);
+      bar_wait(&bar_rate, 0, &failed);
+      *cycles = clock64() - t0;
+    }
   }
   if (warp < 4) {
     bar_wait(&bar_done, 0, &failed);
     fence_after_sync();
-    if (!failed) {
+    if (!atomicAdd(&failed, 0)) {
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(td + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j++) D[(size_t)(warp * 32 + lane) * 128 + c0 + j] = (int32_t)v[j];
       }
@@ -70,7 +84,7 @@ __global__ void __launch_bounds__(160) k_probe(const uint32_t* A, const uint32_t
   }
   __syncthreads();
   if (warp == 4) tmem_dealloc(td, 128);
-  if (threadIdx.x == 0) *failed_out = failed;
+  if (threadIdx.x == 0) *failed_out = atomicAdd(&failed, 0);
 }
 
 int main()
@@ -82,12 +96,12 @@ int main()
   for (int i = 0; i < 16; i++) { B[5 * 16 + i] = A[9 * 16 + i]; }          // an identical pair
   for (int i = 0; i < 16; i++) { A[100 * 16 + i] = 0xffffffffu; B[77 * 16 + i] = 0xffffffffu; }   // all ones
   for (int i = 0; i < 16; i++) { A[3 * 16 + i] = 0; }
-  uint32_t *dA, *dB; int32_t* dD; int* dF;
+  uint32_t *dA, *dB; int32_t* dD; int* dF; long long* dC; cudaMalloc(&dC, 8);
   cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, 128 * 128 * 4); cudaMalloc(&dF, 4);
   cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
   cudaMemset(dD, 0xff, 128 * 128 * 4);
   cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
-  k_probe<<<1, 160, 131072>>>(dA, dB, dD, dF);
+  k_probe<<<1, 160, 131072>>>(dA, dB, dD, dF, 0, dC);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 2; }
   std::vector<int32_t> D(128 * 128); int failed = 0;
@@ -101,5 +115,12 @@ int main()
       if (D[r * 128 + c] != pc * 16384) { if (bad < 8) printf("mismatch r %d c %d: got %d want %d (popc %d)\n", r, c, D[r * 128 + c], pc * 16384, pc); bad++; }
     }
   printf("umma_probe: %ld mismatches of 16384; D[9][5] = %d (512 * 16384 = %d)\n", bad, D[9 * 128 + 5], 512 * 16384);
+  // issue rate of tcgen05.mma kind::i8 M = N = 128, K = 32 on one SM
+  const int reps = 2000;
+  k_probe<<<1, 160, 131072>>>(dA, dB, dD, dF, reps, dC);
+  if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error in the rate run\n"); return 2; }
+  long long cyc = 0; cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost);
+  printf("umma_probe: %d x 16 MMAs (128 x 128 x 32, u8) in %lld cycles: %.1f cycles per MMA, %.0f cycles per 128 x 128 x 512 tile, %.0f MAC/clk/SM\n",
+         reps, cyc, (double)cyc / (reps * 16.0), (double)cyc / reps, 128.0 * 128 * 32 * 16 * reps / (double)cyc);
   return bad ? 1 : 0;
 }

@@ -1017,16 +1017,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_scan_umma(MatchArgs a, uint
 #pragma unroll 1
     for (int vz = v_begin; vz < v_end && ok; vz++) {
       const UmmaView V = view_of(vz);
-      auto row_of = [&](int j0) {
-        const int j = j0 + r;
-        const int qi = j < V.q_end ? (V.list ? __ldg(&V.list[j]) : j) : -1;
-        return umma_load_row(qi >= 0 ? V.q_desc + (size_t)qi * 4 : nullptr);
-      };
-      UmmaRow cur = row_of(V.q_begin);
+      // software pipeline over the tiles: the list index is fetched two tiles ahead, the 64-byte row one tile ahead, so that neither
+      // of the two dependent loads stalls the expansion
+      auto index_of = [&](int j0) { const int j = j0 + r; return j < V.q_end ? (V.list ? __ldg(&V.list[j]) : j) : -1; };
+      auto row_of = [&](int qi) { return umma_load_row(qi >= 0 ? V.q_desc + (size_t)qi * 4 : nullptr); };
+      UmmaRow cur = row_of(index_of(V.q_begin));
+      int qi_next = index_of(V.q_begin + kUmmaRows);
 #pragma unroll 1
       for (int j0 = V.q_begin; j0 < V.q_end; j0 += kUmmaRows, t++) {
         const int buf = t & 1;
-        const UmmaRow nxt = j0 + kUmmaRows < V.q_end ? row_of(j0 + kUmmaRows) : cur;
+        const UmmaRow nxt = row_of(qi_next);
+        qi_next = index_of(j0 + 2 * kUmmaRows);
         if (t >= 2 && !bar_wait(&a_free[buf], (uint32_t)(((t >> 1) - 1) & 1), &failed)) { ok = false; break; }
         umma_expand_row(buf ? sA1 : sA0, r, cur);
         fence_smem_to_async();
@@ -1043,34 +1044,48 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_scan_umma(MatchArgs a, uint
 #pragma unroll 1
     for (int vz = v_begin; vz < v_end && ok; vz++) {
       const UmmaView V = view_of(vz);
+      // this row's query and its popcount, one tile ahead (the producers pull the same 64 bytes through L1 / L2)
+      auto index_of = [&](int j0) { const int j = j0 + r; return j < V.q_end ? (V.list ? __ldg(&V.list[j]) : j) : -1; };
+      int q_next = index_of(V.q_begin);
+      UmmaRow row_next = umma_load_row(q_next >= 0 ? V.q_desc + (size_t)q_next * 4 : nullptr);
 #pragma unroll 1
       for (int j0 = V.q_begin; j0 < V.q_end; j0 += kUmmaRows, t++) {
         const int buf = t & 1;
-        // this row's query and its popcount (the producers have just pulled the same 64 bytes through L1 / L2)
-        const int j = j0 + r;
-        const int q = j < V.q_end ? (V.list ? __ldg(&V.list[j]) : j) : -1;
-        const int pa = q >= 0 ? umma_popc_row(umma_load_row(V.q_desc + (size_t)q * 4)) : 0;
+        const int q = q_next;
+        const int pa = umma_popc_row(row_next);
+        q_next = index_of(j0 + kUmmaRows);
+        row_next = umma_load_row(q_next >= 0 ? V.q_desc + (size_t)q_next * 4 : nullptr);
         const int rowlim = 8192 * (pa - thr);   // hit: acc - 8192 popc(b) > rowlim  <=>  popc(a) + popc(b) - 2 popc(a & b) < thr
         if (!bar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1), &failed)) { ok = false; break; }
         fence_after_sync();
 #pragma unroll 1
-        for (int c0 = chalf; c0 < chalf + 64; c0 += 32) {
+        for (int half = 0; half < 2; half++) {   // this warp's 64 columns, 32 at a time (128 registers per thread at 13 warps)
+          const int c0 = chalf + 32 * half;
           uint32_t v[32];
           tmem_ld_32x32(td + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * kUmmaRows + c0), v);
-          int m = -0x7fffffff;
+          tmem_ld_wait();
+          // maxima of acc - 8192 popc(b) over groups of 4 columns; a hit in the 32 columns shows in their maximum. Some lane of a
+          // warp has one in most chunks (a few hits per query), so what follows the test is kept short: only the groups of 4 that
+          // contain a hit are opened
+          int g[8];
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
             const int4 pb = *reinterpret_cast<const int4*>(&s_pb[c0 + k]);
-            m = max(m, max(max((int)v[k] - pb.x, (int)v[k + 1] - pb.y), max((int)v[k + 2] - pb.z, (int)v[k + 3] - pb.w)));
+            g[k >> 2] = max(max((int)v[k] - pb.x, (int)v[k + 1] - pb.y), max((int)v[k + 2] - pb.z, (int)v[k + 3] - pb.w));
           }
-          if (m > rowlim && q >= 0) {   // rare: a handful of pairs per query are below the threshold
+          const int m = max(max(max(g[0], g[1]), max(g[2], g[3])), max(max(g[4], g[5]), max(g[6], g[7])));
+          if (m > rowlim && q >= 0) {
 #pragma unroll
-            for (int k = 0; k < 32; k++) {   // unrolled: v stays in registers
-              const int col = c_base + c0 + k;
-              if ((int)v[k] - s_pb[c0 + k] > rowlim && col < nc && (a.q_use == nullptr || a.q_use[V.fq + q]) && a.c_valid[fc + col]) {
-                const uint32_t d = (uint32_t)(pa + (s_pb[c0 + k] >> 13) - 2 * (int)(v[k] >> 14));
-                const int pos = atomicAdd(V.hit_cnt, 1);
-                if (pos < a.hit_cap) V.hits[pos] = make_uint2((d << 20) | (uint32_t)q, (uint32_t)col);   // d <= 512, q < 2^20
+            for (int gi = 0; gi < 8; gi++) {
+              if (g[gi] <= rowlim) continue;
+#pragma unroll
+              for (int kk = 0; kk < 4; kk++) {   // unrolled: v stays in registers
+                const int k = 4 * gi + kk, col = c_base + c0 + k;
+                if ((int)v[k] - s_pb[c0 + k] > rowlim && col < nc && (a.q_use == nullptr || a.q_use[V.fq + q]) && a.c_valid[fc + col]) {
+                  const uint32_t d = (uint32_t)(pa + (s_pb[c0 + k] >> 13) - 2 * (int)(v[k] >> 14));
+                  const int pos = atomicAdd(V.hit_cnt, 1);
+                  if (pos < a.hit_cap) V.hits[pos] = make_uint2((d << 20) | (uint32_t)q, (uint32_t)col);   // d <= 512, q < 2^20
+                }
               }
             }
           }
@@ -1084,7 +1099,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_scan_umma(MatchArgs a, uint
   fence_before_sync();
   __syncthreads();
   if (warp == 12) tmem_dealloc(td, 256);
-  if (threadIdx.x == 0 && failed) atomicOr(status, 32);   // one word per context, read by okb_sync
+  if (threadIdx.x == 0 && atomicAdd(&failed, 0)) atomicOr(status, 32);   // one word per context, read by okb_sync
 }
 
 // one opt-in to the kernel's 193 KB of dynamic shared memory per device

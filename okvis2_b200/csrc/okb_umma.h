@@ -23,13 +23,17 @@ __device__ __forceinline__ bool bar_try_wait(uint64_t* bar, uint32_t parity)
                : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// bounded wait: a wrong descriptor or count must end the kernel with an error flag, not hang the GPU
-__device__ __forceinline__ bool bar_wait(uint64_t* bar, uint32_t parity, volatile int* failed)
+// bounded wait: a wrong descriptor or count must end the kernel with an error flag, not hang the GPU. The bound is generous
+// (~10 s at 2 GHz) so that a kernel slowed down a hundredfold by compute-sanitizer still completes; `failed` is only touched with
+// atomics (the roles poll it concurrently).
+__device__ __forceinline__ bool bar_wait(uint64_t* bar, uint32_t parity, int* failed)
 {
+  if (bar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   while (!bar_try_wait(bar, parity)) {
-    if (*failed) return false;
-    if (clock64() - t0 > 200000000ll) { *failed = 1; return false; }   // ~0.1 s
+    __nanosleep(40);   // the waiting roles share their scheduler with the working ones: do not spin at issue rate
+    if (atomicAdd(failed, 0)) return false;
+    if (clock64() - t0 > 20000000000ll) { atomicExch(failed, 1); return false; }
   }
   return true;
 }
@@ -58,8 +62,9 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the registers of every tmem_ld issued so far are valid after this
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- MMA ----------------------------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices of 128 contiguous bytes;
