@@ -1139,6 +1139,25 @@ def bench_next_rows(fe, cfg):
     return rows
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run its host threads on the CPUs next to that GPU (NVML's ideal CPU set), so that the page-locked
+    buffers of the e2e legs (first touched by these threads) and the copy-engine traffic stay on the GPU's NUMA node. Round 1's
+    end-to-end figure at 8 GPUs was bound by the host memory system. Returns the number of CPUs bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 4:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1163,6 +1182,7 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None   # before any page-locked allocation
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -1232,7 +1252,9 @@ def main():
                         "gate_cos_equals_libm": gate_exact,
                         "orientation_atan2": "device fp64 atan2 (<= 2 ulp before rounding to fp32): a keypoint angle can differ from cv2 with probability ~2^-27"},
                 "workload_stats": head["workload_stats"], "roofline": head["roofline"], "matcher": head.get("matcher"), "cpu_baseline": cpu,
-                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clocks, "configs": configs, "next_rows": next_rows}
+                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clocks, "configs": configs, "next_rows": next_rows,
+                "host": {"cpus": os.cpu_count(), "sequences_in_flight_per_gpu": lanes,
+                         "cpus_bound_per_rank": numa, "note": "N > 1: every rank runs on the CPUs NVML lists as local to its GPU"}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
