@@ -272,7 +272,9 @@ static int replay_one(okb_context_t* ctx, okb_replay_io* io, StartGate* gate, st
   if (io->n_older > 0)
     for (int c = 0; c < 2; c++) {
       h2d += (long long)B * 192 + (long long)B * cap + (long long)B * io->n_older * (long long)sizeof(okb_older_view_t);
-      d2h += (long long)B * io->n_older * (4 + (long long)io->cap_m * 41) + (long long)B * cap;
+      int max_cnt = 0;   // the compact lists come back trimmed to the longest one of the batch
+      for (int i = 0; i < B * io->n_older; i++) max_cnt = io->n_match[c][i] > max_cnt ? io->n_match[c][i] : max_cnt;
+      d2h += (long long)B * io->n_older * (4 + (long long)max_cnt * 41) + (long long)B * cap;
     }
   io->h2d = h2d; io->d2h = d2h;
   long long nkp = 0, nm = 0;   // of the last step (sanity numbers for the bench line)

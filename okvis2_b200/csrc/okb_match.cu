@@ -2087,26 +2087,38 @@ int okb_match_motion_stereo_batch(okb_context_t* ctx, int cam, int n_frames, con
                                                        (int32_t*)(d + o_n), (int32_t*)(d + o_mk0), (int32_t*)(d + o_mk1), d + o_mf, (double*)(d + o_mhp));
   ctx->launches++;
   OKB_CUDA(cudaGetLastError());
-  // results: counts + compact lists + mask, through the pinned mirror (or straight into page-locked caller buffers)
-  auto out = [&](size_t off, void* dst, size_t bytes) -> int {
-    if (host_pinned(dst)) { OKB_CUDA(cudaMemcpyAsync(dst, d + off, bytes, cudaMemcpyDeviceToHost, st)); return 0; }
-    OKB_CUDA(cudaMemcpyAsync(h + off, d + off, bytes, cudaMemcpyDeviceToHost, st)); return 1;
+  // results: the counts first (one extra synchronisation of a few microseconds), then only the filled part of the compact lists
+  // (capacity cap_m per (frame, view); a view typically fills a fraction of it) and the mask, through the pinned mirror or straight
+  // into page-locked caller buffers
+  const bool pin_n = host_pinned(n_match);
+  OKB_CUDA(cudaMemcpyAsync(pin_n ? (void*)n_match : (void*)(h + o_n), d + o_n, (size_t)n_frames * n_older * 4, cudaMemcpyDeviceToHost, st));
+  OKB_CUDA(wait_stream(ctx, st));
+  if (!pin_n) memcpy(n_match, h + o_n, (size_t)n_frames * n_older * 4);
+  int max_cnt = 0;
+  for (int i = 0; i < n_frames * n_older; i++) {
+    if (n_match[i] > cap_m) { set_error("okb_match_motion_stereo_batch: %d matches of view %d exceed the list capacity %d", n_match[i], i, cap_m); return OKB_ERR_CAPACITY; }
+    max_cnt = n_match[i] > max_cnt ? n_match[i] : max_cnt;
+  }
+  const size_t list_rows = (size_t)n_frames * n_older;
+  auto out = [&](size_t off, void* dst, size_t elem) -> int {   // 1: landed in the mirror, 0: in the caller's buffer
+    if (max_cnt == 0) return 0;
+    const bool pinned = host_pinned(dst);
+    OKB_CUDA(cudaMemcpy2DAsync(pinned ? dst : (void*)(h + off), (size_t)cap_m * elem, d + off, (size_t)cap_m * elem, (size_t)max_cnt * elem, list_rows,
+                               cudaMemcpyDeviceToHost, st));
+    return pinned ? 0 : 1;
   };
-  int s_n, s_k0, s_k1, s_f, s_hp;
-  if ((s_n = out(o_n, n_match, (size_t)n_frames * n_older * 4)) < 0 || (s_k0 = out(o_mk0, m_k0, nm * 4)) < 0 || (s_k1 = out(o_mk1, m_k1, nm * 4)) < 0 ||
-      (s_f = out(o_mf, m_flags, nm)) < 0 || (s_hp = out(o_mhp, m_hp_W, nm * 32)) < 0)
+  int s_k0, s_k1, s_f, s_hp;
+  if ((s_k0 = out(o_mk0, m_k0, 4)) < 0 || (s_k1 = out(o_mk1, m_k1, 4)) < 0 || (s_f = out(o_mf, m_flags, 1)) < 0 || (s_hp = out(o_mhp, m_hp_W, 32)) < 0)
     return OKB_ERR_CUDA;
   if (pin_mask) OKB_CUDA(cudaMemcpy2DAsync(matched1, cap, d + o_mask, ws.kp_cap, rows, n_frames, cudaMemcpyDeviceToHost, st));
   else OKB_CUDA(cudaMemcpyAsync(h + o_mask, d + o_mask, n1, cudaMemcpyDeviceToHost, st));
   OKB_CUDA(wait_stream(ctx, st));
-  if (s_n) memcpy(n_match, h + o_n, (size_t)n_frames * n_older * 4);
-  if (s_k0) memcpy(m_k0, h + o_mk0, nm * 4);
-  if (s_k1) memcpy(m_k1, h + o_mk1, nm * 4);
-  if (s_f) memcpy(m_flags, h + o_mf, nm);
-  if (s_hp) memcpy(m_hp_W, h + o_mhp, nm * 32);
+  auto trim = [&](int staged, size_t off, void* dst, size_t elem) {
+    if (!staged) return;
+    for (size_t r = 0; r < list_rows; r++) memcpy((uint8_t*)dst + r * cap_m * elem, h + off + r * cap_m * elem, (size_t)n_match[r] * elem);
+  };
+  trim(s_k0, o_mk0, m_k0, 4); trim(s_k1, o_mk1, m_k1, 4); trim(s_f, o_mf, m_flags, 1); trim(s_hp, o_mhp, m_hp_W, 32);
   if (!pin_mask) for (int b = 0; b < n_frames; b++) memcpy(matched1 + (size_t)b * cap, h + o_mask + (size_t)b * ws.kp_cap, rows);
-  for (int i = 0; i < n_frames * n_older; i++)
-    if (n_match[i] > cap_m) { set_error("okb_match_motion_stereo_batch: %d matches of view %d exceed the list capacity %d", n_match[i], i, cap_m); return OKB_ERR_CAPACITY; }
   return OKB_OK;
 }
 
