@@ -943,6 +943,7 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaStreamCreateWithFlags(&ws.stream2, cudaStreamNonBlocking));
   OKB_CUDA(cudaEventCreateWithFlags(&ws.ev_fork, cudaEventDisableTiming));
   OKB_CUDA(cudaEventCreateWithFlags(&ws.ev_join, cudaEventDisableTiming));
+  OKB_CUDA(cudaEventCreateWithFlags(&ws.ev_pyr, cudaEventDisableTiming));
   OKB_CUDA(cudaMalloc(&ws.d_in, (size_t)W * H * B));
   OKB_CUDA(cudaMalloc(&ws.d_img, off * B));
   OKB_CUDA(cudaMalloc(&ws.d_score, off * B));
@@ -1010,6 +1011,7 @@ void detect_free_camera(okb_context* ctx, int cam)
   if (ws.ev_mid) cudaEventDestroy(ws.ev_mid);
   if (ws.ev_fork) cudaEventDestroy(ws.ev_fork);
   if (ws.ev_join) cudaEventDestroy(ws.ev_join);
+  if (ws.ev_pyr) cudaEventDestroy(ws.ev_pyr);
   if (ws.stream2) cudaStreamDestroy(ws.stream2);
   if (ws.stream) cudaStreamDestroy(ws.stream);
 }

@@ -65,7 +65,7 @@ struct CamWorkspace {
   okb_camera_config_t cfg;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // side stream (integral image)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pyr = nullptr;
   int n_layers = 0;
   LayerGeom geom[kMaxLayers];
   DeviceLayers dl;
@@ -103,7 +103,7 @@ struct CamWorkspace {
   // TMA tensor maps of the internal layers (layer 0 is encoded per call)
   CUtensorMap tma[kMaxLayers]; int tma_use[kMaxLayers] = {0}; int tma_ready = 0;
   int score_tile_h = 32;          // rows per score tile: 32 (128-thread CTAs, default) or 64 (256-thread CTAs)
-  void* d_tiles = nullptr; int n_tiles = 0;   // (layer, x0, y0) of every score tile of a frame
+  void* d_tiles = nullptr; int n_tiles = 0, n_tiles0 = 0;   // (layer, x0, y0) of every score tile of a frame, layer-major; tiles of layer 0
   long long* d_dbg = nullptr;   // per-frame cycle stamps of the single-CTA kernels (okb_debug_stamps)
   uint8_t* d_m1_rows = nullptr; size_t m1_rows_cap = 0;   // M1 row bins of the device-resident form (grown on demand)
   // staging of the host-buffer batch matchers (okb_match_map3d_batch / okb_match_stereo_batch), grown on demand

@@ -589,7 +589,13 @@ int pyramid_score_run(okb_context* ctx, CamWorkspace& ws, const uint8_t* d_image
   const okb_camera_config_t& c = ws.cfg;
   const int B = n_frames;
   cudaStream_t st = ws.stream;
-  // ---- pyramid: the chains that can be carried in shared memory go into ONE launch, the rest layer by layer
+  // ---- pyramid: the chains that can be carried in shared memory go into ONE launch, the rest layer by layer. It runs on the side
+  //      stream underneath the scoring of layer 0 (more than half of all pixels), which needs nothing from it: the pyramid kernel is
+  //      latency-bound on loads, the score kernel on the ALU pipe, so they share the SMs well. The scoring of layers >= 1 waits for it.
+  static const int overlap_env = getenv("OKB_PYR_OVERLAP") ? atoi(getenv("OKB_PYR_OVERLAP")) : 1;   // tuning hook
+  const bool overlap = ws.n_layers > 1 && overlap_env != 0;
+  cudaStream_t sp = overlap ? ws.stream2 : st;
+  if (overlap) { OKB_CUDA(cudaEventRecord(ws.ev_fork, st)); OKB_CUDA(cudaStreamWaitEvent(sp, ws.ev_fork, 0)); }
   bool chained[kMaxLayers] = {false};
   PyrArgs pa; memset(&pa, 0, sizeof(pa));
   if (ws.n_layers > 1) {
@@ -610,7 +616,7 @@ int pyramid_score_run(okb_context* ctx, CamWorkspace& ws, const uint8_t* d_image
     if (!ws.geom[1].fast2) add_chain(1, true);
     if (pa.n_chains == 1) pa.c[1].tiles = 0;
     if (pa.n_chains > 0) {
-      k_pyramid<<<dim3(pa.c[0].tiles + pa.c[1].tiles, B), kPyrThreads, 0, st>>>(pa, ws.dl, d_images, src_pitch, in_stride, ws.d_img);
+      k_pyramid<<<dim3(pa.c[0].tiles + pa.c[1].tiles, B), kPyrThreads, 0, sp>>>(pa, ws.dl, d_images, src_pitch, in_stride, ws.d_img);
       ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
     }
     for (int i = 1; i < ws.n_layers; i++) {
@@ -623,10 +629,11 @@ int pyramid_score_run(okb_context* ctx, CamWorkspace& ws, const uint8_t* d_image
       J.dw = g.w; J.dh = g.h; J.fast2 = g.fast2;
       J.xs = g.d_xs; J.xn = g.d_xn; J.ys = g.d_ys; J.yn = g.d_yn; J.xa = g.d_xa; J.ya = g.d_ya;
       const int tiles_x = (g.w + 31) / 32;
-      k_resize<<<dim3(tiles_x * ((g.h + 31) / 32), B), 256, 0, st>>>(J, tiles_x);
+      k_resize<<<dim3(tiles_x * ((g.h + 31) / 32), B), 256, 0, sp>>>(J, tiles_x);
       ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
     }
   }
+  if (overlap) OKB_CUDA(cudaEventRecord(ws.ev_pyr, sp));
   if (ctx->timers_on) cudaEventRecord(ws.ev_mid, st);
   // ---- scores
   const int TH = ws.score_tile_h;
@@ -636,10 +643,11 @@ int pyramid_score_run(okb_context* ctx, CamWorkspace& ws, const uint8_t* d_image
       for (int y0 = 0; y0 < ws.geom[i].h; y0 += TH)
         for (int x0 = 0; x0 < ws.geom[i].w; x0 += kTileW) tab.push_back(TileEntry{i, x0, y0, 0});
     ws.n_tiles = (int)tab.size();
+    ws.n_tiles0 = 0;
+    for (const TileEntry& e : tab) ws.n_tiles0 += e.layer == 0;
     OKB_CUDA(cudaMalloc(&ws.d_tiles, tab.size() * sizeof(TileEntry)));
     OKB_CUDA(cudaMemcpy(ws.d_tiles, tab.data(), tab.size() * sizeof(TileEntry), cudaMemcpyHostToDevice));
   }
-  const int n_items = ws.n_tiles * B;
   TmaMaps maps;
   build_tma_maps(ws, d_images, src_pitch, in_stride, c.max_batch, TH, maps);
   if (!g_sm_count) {
@@ -650,16 +658,26 @@ int pyramid_score_run(okb_context* ctx, CamWorkspace& ws, const uint8_t* d_image
     for (int i = 0; i < 2; i++) if (g_ctas_per_sm[i] < 1) g_ctas_per_sm[i] = 1;
   }
   const TileEntry* tiles = (const TileEntry*)ws.d_tiles;
-  if (TH == 64) {
-    const int grid = std::min(n_items, g_sm_count * g_ctas_per_sm[0]);
-    k_score_nms<64><<<grid, 256, 0, st>>>(maps, ws.dl, tiles, ws.n_tiles, B, d_images, src_pitch, in_stride, ws.d_img, ws.d_score, ws.d_cand,
-                                          ws.d_cand_count, ws.cand_cap, cr, c.threshold, ws.d_status, ws.d_tie_cells);
+  auto launch = [&](const TileEntry* t0, int n_t) {
+    const int items = n_t * B;
+    if (TH == 64) {
+      const int grid = std::min(items, g_sm_count * g_ctas_per_sm[0]);
+      k_score_nms<64><<<grid, 256, 0, st>>>(maps, ws.dl, t0, n_t, B, d_images, src_pitch, in_stride, ws.d_img, ws.d_score, ws.d_cand,
+                                            ws.d_cand_count, ws.cand_cap, cr, c.threshold, ws.d_status, ws.d_tie_cells);
+    } else {
+      const int grid = std::min(items, g_sm_count * g_ctas_per_sm[1]);
+      k_score_nms<32><<<grid, 128, 0, st>>>(maps, ws.dl, t0, n_t, B, d_images, src_pitch, in_stride, ws.d_img, ws.d_score, ws.d_cand,
+                                            ws.d_cand_count, ws.cand_cap, cr, c.threshold, ws.d_status, ws.d_tie_cells);
+    }
+    ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
+  };
+  if (overlap) {
+    launch(tiles, ws.n_tiles0);                                   // layer 0 (the table is layer-major), next to the pyramid
+    OKB_CUDA(cudaStreamWaitEvent(st, ws.ev_pyr, 0));
+    launch(tiles + ws.n_tiles0, ws.n_tiles - ws.n_tiles0);        // the reduced layers
   } else {
-    const int grid = std::min(n_items, g_sm_count * g_ctas_per_sm[1]);
-    k_score_nms<32><<<grid, 128, 0, st>>>(maps, ws.dl, tiles, ws.n_tiles, B, d_images, src_pitch, in_stride, ws.d_img, ws.d_score, ws.d_cand,
-                                          ws.d_cand_count, ws.cand_cap, cr, c.threshold, ws.d_status, ws.d_tie_cells);
+    launch(tiles, ws.n_tiles);
   }
-  ctx->launches++; if (ctx->timers_on) ws.ps_launches++;
   OKB_CUDA(cudaGetLastError());
   return OKB_OK;
 }
