@@ -652,11 +652,11 @@ __device__ __forceinline__ M4Gate m4_gate(const MatchArgs& a, size_t fq, size_t 
 }
 
 // the gate of the M3 worker loop for one (older keypoint, current keypoint) pair (Frontend.cpp:1849-1884)
-__device__ __forceinline__ M4Gate m3_gate(const MatchArgs& a, size_t fq, size_t fc, int q, int c)
+__device__ __forceinline__ M4Gate m3_gate(const MatchArgs& a, size_t fq, size_t fc, int q, int c, int vi)
 {
   M4Gate g; g.pass = false; g.parallel = false; g.hp = V3{0, 0, 0};
   if (!a.c_valid[fc + c]) return g;
-  const M3View& view = a.views[(size_t)(fc / a.c_stride) * a.view_stride + a.view_index];
+  const M3View& view = a.views[(size_t)(fc / a.c_stride) * a.view_stride + vi];
   const M3Frame& fr = a.frames[fc / a.c_stride];
   const V3 eq = v3(a.q_e + 3 * (fq + q)), e1 = v3(a.c_e + 3 * (fc + c));
   if (dot(eq, e1) < 0.5) return g;
@@ -671,10 +671,11 @@ __device__ __forceinline__ M4Gate m3_gate(const MatchArgs& a, size_t fq, size_t 
   }
   return g;
 }
+// fq: first query slot of the (frame, view); vi: the view (M3), default the one of the arguments
 template <int MODE>
-__device__ __forceinline__ M4Gate pair_gate(const MatchArgs& a, size_t fq, size_t fc, int q, int c)
+__device__ __forceinline__ M4Gate pair_gate(const MatchArgs& a, size_t fq, size_t fc, int q, int c, int vi = -1)
 {
-  if (MODE == MODE_M3) return m3_gate(a, fq, fc, q, c);
+  if (MODE == MODE_M3) return m3_gate(a, fq, fc, q, c, vi < 0 ? a.view_index : vi);
   return m4_gate(a, fq, fc, q, c);
 }
 
@@ -1130,14 +1131,13 @@ __global__ void __launch_bounds__(128) k_m4_gate(MatchArgs a, const uint2* hits,
 }
 
 template <int MODE>
-__device__ __forceinline__ void m4_finish_one(const MatchArgs& a, const unsigned long long b, int frame, int q)
+__device__ __forceinline__ void m4_finish_one(const MatchArgs& a, const unsigned long long b, size_t fq, size_t fc, int q, int vi = -1)
 {
-  const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
   const uint32_t d = (uint32_t)(b >> 32);
   double* hp = a.out_hp + 4 * (fq + q);
   if (d < a.thr) {
     const int c = (int)(uint32_t)b;
-    const M4Gate g = pair_gate<MODE>(a, fq, fc, q, c);
+    const M4Gate g = pair_gate<MODE>(a, fq, fc, q, c, vi);
     a.out_dist[fq + q] = d; a.out_idx[fq + q] = c;
     hp[0] = g.hp.x; hp[1] = g.hp.y; hp[2] = g.hp.z; hp[3] = 1.0;
     a.out_init[fq + q] = g.parallel ? 0 : 1;
@@ -1154,7 +1154,7 @@ __global__ void __launch_bounds__(128) k_m4_finish(MatchArgs a, const unsigned l
   const int frame = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= a.nq || a.hit_cnt[frame] > a.hit_cap) return;
-  m4_finish_one<MODE>(a, best[(size_t)frame * a.q_stride + q], frame, q);
+  m4_finish_one<MODE>(a, best[(size_t)frame * a.q_stride + q], (size_t)frame * a.q_stride, (size_t)frame * a.c_stride, q);
 }
 
 
@@ -1239,9 +1239,8 @@ struct M3Check {
 };
 
 // re-projection check and claim of one (frame, k0): returns the flags (bit 0 matching, bit 1 initialisable)
-__device__ __forceinline__ uint8_t m3_check_one(const M3Check& c, int frame, int k0)
+__device__ __forceinline__ uint8_t m3_check_one(const M3Check& c, int frame, size_t i /* slot of (frame, view, k0) */, int k0, int32_t* claim)
 {
-  const size_t i = (size_t)frame * c.q_stride + k0;
   uint8_t fl = 0;
   const int k1 = c.k1[i];
   if (k1 >= 0 && c.dist[i] < c.thr) {
@@ -1256,7 +1255,7 @@ __device__ __forceinline__ uint8_t m3_check_one(const M3Check& c, int frame, int
     const double dx = (double)kp.x - kx, dy = (double)kp.y - ky;
     const bool matching = st == kProjSuccessful && sqrt(dx * dx + dy * dy) < 4.0;
     fl = (uint8_t)((matching ? 1 : 0) | (c.init[i] ? 2 : 0));
-    if (matching) atomicMin(&c.claim[(size_t)frame * c.cap1 + k1], k0);
+    if (matching) atomicMin(&claim[(size_t)frame * c.cap1 + k1], k0);
   }
   return fl;
 }
@@ -1266,7 +1265,7 @@ __global__ void __launch_bounds__(128) k_m3_check(const __grid_constant__ M3Chec
   const int frame = blockIdx.y;
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (k0 >= c.cap0) return;
-  c.flags[(size_t)frame * c.q_stride + k0] = m3_check_one(c, frame, k0);
+  c.flags[(size_t)frame * c.q_stride + k0] = m3_check_one(c, frame, (size_t)frame * c.q_stride + k0, k0, c.claim);
 }
 
 __global__ void __launch_bounds__(128) k_m3_commit(const __grid_constant__ M3Check c)
@@ -1282,61 +1281,71 @@ __global__ void __launch_bounds__(128) k_m3_commit(const __grid_constant__ M3Che
   if (c.claim[j] == k0) { c.flags[i] = fl | 4; c.matched1[j] = 1; c.cvalid[j] = 0; }
 }
 
-// One older keyframe of the sequence in ONE launch, one CTA per frame (the low-latency form used for small batches, where ten
-// launches per view cost more than their work): gate of the view's hit list -> per-query minimum -> outputs -> 4 px check and
-// claim -> commit. Same device functions as k_m4_gate / k_m4_finish / k_m3_check / k_m3_commit; the phases are separated by block
-// barriers instead of kernel boundaries (the reductions go through L2 atomics and are read back with ld.cg). A frame whose hit
-// list overflowed is matched by brute force here (warp per query, candidates in ascending order by the min over (distance, k1)).
+// The per-view steps of the sequence (or the one step of a stereo pair) in ONE launch, one CTA per frame: for every older keyframe
+// in order -- gate of the view's hit list -> per-query minimum -> outputs -> 4 px check and claim -> commit -- with block barriers
+// where the separate kernels have launch boundaries (the reductions go through L2 atomics and are read back with ld.cg). Same
+// device functions as k_m4_gate / k_m4_finish / k_m3_check / k_m3_commit. A frame whose hit list overflowed is matched by brute
+// force here (warp per query, minimum over (distance, k1) = first minimum in candidate order). The arguments carry the bases of
+// view 0; view v lives nq query slots further in every per-query array, gridDim.x hit lists / counters further, claim_stride claim
+// slots further.
 template <int D16, int MODE>
-__global__ void __launch_bounds__(512) k_pair_view(MatchArgs a, const __grid_constant__ M3Check c, const uint2* hits, unsigned long long* best)
+__global__ void __launch_bounds__(512) k_pair_view(MatchArgs a, const __grid_constant__ M3Check c, const uint2* hits, unsigned long long* best,
+                                                   int v_begin, int v_end, size_t claim_stride)
 {
   const int frame = blockIdx.x;
-  const size_t fq = (size_t)frame * a.q_stride, fc = (size_t)frame * a.c_stride;
-  const int n_hits = a.hit_cnt[frame];
-  if (n_hits <= a.hit_cap) {
-    for (int i = threadIdx.x; i < n_hits; i += blockDim.x) {
-      const uint2 e = hits[(size_t)frame * a.hit_cap + i];
-      const int q = (int)(e.x & 0xfffffu), cc = (int)e.y;
-      if (pair_gate<MODE>(a, fq, fc, q, cc).pass) atomicMin(&best[fq + q], ((unsigned long long)(e.x >> 20) << 32) | (unsigned)cc);
-    }
-  } else {
-    const M3View* view = MODE == MODE_M3 ? &a.views[(size_t)frame * a.view_stride + a.view_index] : nullptr;
-    const int nq = view ? min(view->n, a.nq) : min(a.q_count[frame], a.nq), nc = min(a.c_count[frame], a.nc);
-    const uint4* q_desc = view ? reinterpret_cast<const uint4*>(view->desc) : reinterpret_cast<const uint4*>(a.q_desc) + fq * D16;
-    const int lane = threadIdx.x & 31;
-    for (int q = threadIdx.x >> 5; q < nq; q += blockDim.x >> 5) {
-      if (a.q_use && !a.q_use[fq + q]) continue;
-      uint4 qd[D16];
-#pragma unroll
-      for (int w = 0; w < D16; w++) qd[w] = __ldg(q_desc + (size_t)q * D16 + w);
-      unsigned long long mine = ~0ull;
-      for (int cc = lane; cc < nc; cc += 32) {
-        if (!a.c_valid[fc + cc]) continue;
-        uint32_t d = 0;
-#pragma unroll
-        for (int w = 0; w < D16; w++) {
-          const uint4 cv = __ldg(reinterpret_cast<const uint4*>(a.c_desc) + (fc + cc) * D16 + w);
-          d += __popc(qd[w].x ^ cv.x) + __popc(qd[w].y ^ cv.y) + __popc(qd[w].z ^ cv.z) + __popc(qd[w].w ^ cv.w);
-        }
-        if (d < a.thr && pair_gate<MODE>(a, fq, fc, q, cc).pass) mine = min(mine, ((unsigned long long)d << 32) | (unsigned)cc);
+  const size_t fc = (size_t)frame * a.c_stride;
+#pragma unroll 1
+  for (int v = v_begin; v < v_end; v++) {
+    const size_t fq = (size_t)frame * a.q_stride + (size_t)v * a.nq;
+    const uint2* hits_v = hits + ((size_t)v * gridDim.x + frame) * a.hit_cap;
+    const int n_hits = a.hit_cnt[(size_t)v * gridDim.x + frame];
+    int32_t* claim = MODE == MODE_M3 ? c.claim + (size_t)v * claim_stride : nullptr;
+    if (n_hits <= a.hit_cap) {
+      for (int i = threadIdx.x; i < n_hits; i += blockDim.x) {
+        const uint2 e = hits_v[i];
+        const int q = (int)(e.x & 0xfffffu), cc = (int)e.y;
+        if (pair_gate<MODE>(a, fq, fc, q, cc, v).pass) atomicMin(&best[fq + q], ((unsigned long long)(e.x >> 20) << 32) | (unsigned)cc);
       }
+    } else {
+      const M3View* view = MODE == MODE_M3 ? &a.views[(size_t)frame * a.view_stride + v] : nullptr;
+      const int nq = view ? min(view->n, a.nq) : min(a.q_count[frame], a.nq), nc = min(a.c_count[frame], a.nc);
+      const uint4* q_desc = view ? reinterpret_cast<const uint4*>(view->desc) : reinterpret_cast<const uint4*>(a.q_desc) + fq * D16;
+      const int lane = threadIdx.x & 31;
+      for (int q = threadIdx.x >> 5; q < nq; q += blockDim.x >> 5) {
+        if (a.q_use && !a.q_use[fq + q]) continue;
+        uint4 qd[D16];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
-      if (lane == 0) best[fq + q] = mine;
+        for (int w = 0; w < D16; w++) qd[w] = __ldg(q_desc + (size_t)q * D16 + w);
+        unsigned long long mine = ~0ull;
+        for (int cc = lane; cc < nc; cc += 32) {
+          if (!a.c_valid[fc + cc]) continue;
+          uint32_t d = 0;
+#pragma unroll
+          for (int w = 0; w < D16; w++) {
+            const uint4 cv = __ldg(reinterpret_cast<const uint4*>(a.c_desc) + (fc + cc) * D16 + w);
+            d += __popc(qd[w].x ^ cv.x) + __popc(qd[w].y ^ cv.y) + __popc(qd[w].z ^ cv.z) + __popc(qd[w].w ^ cv.w);
+          }
+          if (d < a.thr && pair_gate<MODE>(a, fq, fc, q, cc, v).pass) mine = min(mine, ((unsigned long long)d << 32) | (unsigned)cc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+        if (lane == 0) best[fq + q] = mine;
+      }
     }
-  }
-  __syncthreads();
-  for (int q = threadIdx.x; q < a.nq; q += blockDim.x) {
-    m4_finish_one<MODE>(a, __ldcg(&best[fq + q]), frame, q);
-    if (MODE == MODE_M3) c.flags[fq + q] = m3_check_one(c, frame, q);   // reads the outputs this thread has just written
-  }
-  if (MODE != MODE_M3) return;
-  __syncthreads();
-  for (int q = threadIdx.x; q < a.nq; q += blockDim.x) {
-    const uint8_t fl = c.flags[fq + q];
-    if (!(fl & 1)) continue;
-    const size_t j = fc + c.k1[fq + q];
-    if (__ldcg(&c.claim[j]) == q) { c.flags[fq + q] = fl | 4; c.matched1[j] = 1; c.cvalid[j] = 0; }
+    __syncthreads();
+    for (int q = threadIdx.x; q < a.nq; q += blockDim.x) {
+      m4_finish_one<MODE>(a, __ldcg(&best[fq + q]), fq, fc, q, v);
+      if (MODE == MODE_M3) c.flags[fq + q] = m3_check_one(c, frame, fq + q, q, claim);   // reads the outputs this thread has just written
+    }
+    if (MODE != MODE_M3) return;
+    __syncthreads();
+    for (int q = threadIdx.x; q < a.nq; q += blockDim.x) {
+      const uint8_t fl = c.flags[fq + q];
+      if (!(fl & 1)) continue;
+      const size_t j = fc + c.k1[fq + q];
+      if (__ldcg(&claim[j]) == q) { c.flags[fq + q] = fl | 4; c.matched1[j] = 1; c.cvalid[j] = 0; }
+    }
+    __syncthreads();   // the next view's gate sees this view's insertions
   }
 }
 
@@ -1806,7 +1815,7 @@ int okb_match_stereo_device_ptr(okb_context_t* ctx, int n_frames, int cap0, cons
   }
   if (fused) {
     M3Check none; memset(&none, 0, sizeof(none));
-    k_pair_view<4, MODE_M4><<<n_frames, 512, 0, st>>>(a, none, hits, best);
+    k_pair_view<4, MODE_M4><<<n_frames, 512, 0, st>>>(a, none, hits, best, 0, 1, 0);
     ctx->launches += 2;
   } else {
     k_m4_gate<MODE_M4><<<dim3(8, n_frames), 128, 0, st>>>(a, hits, best);
@@ -2001,8 +2010,10 @@ int okb::motion_sequence(okb_context_t* ctx, MotionScratch& ms, int n_frames, in
     c.k1 = a.out_idx; c.dist = a.out_dist; c.hp = a.out_hp; c.init = a.out_init; c.flags = d_out_flags + vo;
     c.claim = claim + (size_t)v * n1; c.matched1 = d_matched1; c.cvalid = cvalid;
     if (fused) {
-      k_pair_view<4, MODE_M3><<<n_frames, 512, 0, st>>>(a, c, hits_v, best_v);
+      // one launch for all views: with the bases of view 0 (v == 0 here), the kernel walks the views in order
+      k_pair_view<4, MODE_M3><<<n_frames, 512, 0, st>>>(a, c, hits, best, 0, n_older, n1);
       ctx->launches++;
+      break;
     } else {
       // gate per hit -> outputs; a frame whose hit list overflows is redone by the sequential-replay kernel (which returns at
       // once for all other frames); then the re-projection check / claim and the commit
