@@ -174,6 +174,13 @@ int okb_back_project(okb_context_t* ctx, int cam, int n, const okb_keypoint_t* k
  *      NULL. Synchronous. */
 int okb_camera_awareness_maps(okb_context_t* ctx, int cam, float* rays_out, float* jac_out);
 
+/* D1: the extraction direction Frontend::detectAndDescribe hands to the extractor before every frame (okvis_frontend/src/Frontend.cpp:
+ * 245-251): gravity in the camera frame, T_WC.inverse().C() * (0, 0, -1), as three floats. The library stores it per camera and hands
+ * it back; the BRISK-512 extractor built here is rotation-invariant by its own orientation estimate and does not consume it (it is the
+ * input of the gravity-aligned 48-byte BRISK2 mode, SURVEY 8f rank 1, which is not built). C_WC: row-major 3x3 rotation of T_WC. */
+int okb_set_extraction_direction(okb_context_t* ctx, int cam, const double C_WC[9]);
+int okb_get_extraction_direction(okb_context_t* ctx, int cam, float dir_out[3]);
+
 /* ---- NCameraSystem::computeOverlaps (okvis_cv/src/NCameraSystem.cpp:48-118): for every ordered camera pair (seenBy, cam) every
  *      pixel of `cam` is back-projected, rotated into `seenBy` (C_rel[(seenBy * n + cam) * 9 ..]: the rotation
  *      (T_SC[seenBy]->inverse() * *T_SC[cam]).C(), row-major), projected, and verified by a back-projection of the image point

@@ -228,6 +228,22 @@ int okb_set_camera_model(okb_context_t* ctx, int cam, const okb_camera_model_t* 
 }
 
 
+int okb_set_extraction_direction(okb_context_t* ctx, int cam, const double C_WC[9])
+{
+  if (!ctx || cam < 0 || cam >= ctx->n_cams || !C_WC) { set_error("okb_set_extraction_direction: bad arguments"); return OKB_ERR_ARGUMENT; }
+  // T_WC.inverse().C() = C_WC^T; times g_W = (0, 0, -1): minus the third row of C_WC, evaluated as the 3x3 product does
+  // (0 * a + 0 * b + (-1) * c per component), then narrowed to float as the reference's cv::Vec3f
+  for (int i = 0; i < 3; i++) ctx->cams[cam].extraction_dir[i] = (float)((C_WC[0 + i] * 0.0 + C_WC[3 + i] * 0.0) + C_WC[6 + i] * -1.0);
+  return OKB_OK;
+}
+
+int okb_get_extraction_direction(okb_context_t* ctx, int cam, float dir_out[3])
+{
+  if (!ctx || cam < 0 || cam >= ctx->n_cams || !dir_out) { set_error("okb_get_extraction_direction: bad arguments"); return OKB_ERR_ARGUMENT; }
+  for (int i = 0; i < 3; i++) dir_out[i] = ctx->cams[cam].extraction_dir[i];
+  return OKB_OK;
+}
+
 int okb_camera_awareness_maps(okb_context_t* ctx, int cam, float* rays_out, float* jac_out)
 {
   if (!ctx || cam < 0 || cam >= ctx->n_cams) { set_error("okb_camera_awareness_maps: bad camera"); return OKB_ERR_ARGUMENT; }

@@ -63,6 +63,7 @@ struct MotionScratch { void* d = nullptr; size_t cap = 0; void* h = nullptr; siz
 
 struct CamWorkspace {
   okb_camera_config_t cfg;
+  float extraction_dir[3] = {0.f, 0.f, -1.f};   // D1: gravity in the camera frame (okb_set_extraction_direction)
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // side stream (integral image)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pyr = nullptr;

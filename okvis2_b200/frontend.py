@@ -26,6 +26,7 @@ class Frame:
         self.landmarkIds = np.zeros(0, np.uint64)       # zero-filled after describe (Frame.hpp:170)
         self.backProjections = np.zeros((0, 3), np.float64)
         self.backProjectionsValid = np.zeros(0, np.uint8)
+        self.extractionDirection = None                 # gravity in the camera frame as handed to the extractor (Frontend.cpp:245-251)
 
     def numKeypoints(self):
         return len(self.keypoints)
@@ -402,6 +403,13 @@ class Frontend:
             raise OkbError(_l.OKB_ERR_UNSUPPORTED, "external keypoints currently not supported")
         with self._locks[cameraIndex]:
             fr = frameOut.frames[cameraIndex]
+            if T_WC is not None:
+                # ExtractionDirection == gravity direction in camera frame (Frontend.cpp:245-251); T_WC: 3x3 / 3x4 / 4x4 / 12 values
+                Cm = np.ascontiguousarray(np.asarray(T_WC, np.float64).reshape(-1, 4 if np.size(T_WC) in (12, 16) else 3)[:3, :3])
+                check(_l.lib().okb_set_extraction_direction(self._ctx, cameraIndex, ptr(Cm)))
+                d = np.zeros(3, np.float32)
+                check(_l.lib().okb_get_extraction_direction(self._ctx, cameraIndex, ptr(d)))
+                fr.extractionDirection = d
             img = np.ascontiguousarray(fr.image)
             w, h = self._geom[cameraIndex]
             if img.shape != (h, w):

@@ -339,3 +339,27 @@ def test_export_features_block_layout():
     for b in range(B):
         assert counts[b] == len(feats[b][0]) and kps[b].tobytes() == feats[b][0].tobytes() and np.array_equal(descs[b], feats[b][1])
     fe.close()
+
+
+def test_extraction_direction_is_gravity_in_the_camera_frame():
+    """D1 (Frontend.cpp:245-251): T_WC.inverse().C() * (0, 0, -1) as floats, per camera; BRISK-512 output does not depend on it"""
+    fe = Frontend(2, 752, 480)
+    fe.configure(threshold=30, octaves=3, max_keypoints=600)
+    try:
+        img = synth_stereo(77, 752, 480)[0]
+        a, b = 0.3, -0.2
+        Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+        Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+        T = np.eye(4); T[:3, :3] = Rx @ Ry; T[:3, 3] = [1.0, -2.0, 0.5]
+        mf = MultiFrame(2); mf.setImage(0, img); mf.setImage(1, img)
+        fe.detectAndDescribe(0, mf, T, None)
+        fe.detectAndDescribe(1, mf, None, None)
+        want = (T[:3, :3].T @ np.array([0.0, 0.0, -1.0])).astype(np.float32)
+        assert np.array_equal(mf.frames[0].extractionDirection, want)
+        assert mf.frames[1].extractionDirection is None
+        d = np.zeros(3, np.float32)
+        okl.check(okl.lib().okb_get_extraction_direction(fe.ctx, 1, okl.ptr(d)))
+        assert np.array_equal(d, np.array([0, 0, -1], np.float32))      # default: camera looking along world x/y, z up
+        assert np.array_equal(mf.frames[0].descriptors, mf.frames[1].descriptors)
+    finally:
+        fe.close()
