@@ -218,6 +218,16 @@ int okb_match_map_uninit(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_
                          const int32_t* cand_lm, const double* cand_e_W, const double* cand_r_W, int n_lm,
                          const uint8_t* lm_is3d, const double r_WC1[3], double sigma, uint32_t match_threshold,
                          uint32_t* out_dist, int32_t* out_lm, double* out_hp_W, int32_t* out_ctr);
+/* M2, device-resident batched form: the queries are the features camera `cam` detected last (okb_detect_describe_batch_device): their
+ * descriptors and back-projections stay in HBM, e1_W = T_WC1.C() * e1_C.normalized() is formed on the device per frame (T_WC1: host,
+ * n_frames x 12 = C row-major 9 + r 3; Frontend.cpp:1606-1627), keypoints without a valid back-projection are skipped. The pool
+ * (device pointers, argument meaning as above) is shared by the frames of the batch. d_kp_use (may be NULL): n_frames x capacity mask
+ * of the keypoints to match (`use[k]`, :1630-1633); d_kp_prev_lm (may be NULL): n_frames x capacity; outputs n_frames x capacity
+ * (x 4 for hp_W), d_out_ctr (may be NULL): n_frames counters. Asynchronous on the camera's stream. */
+int okb_match_map_uninit_device(okb_context_t* ctx, int cam, int n_frames, int n_cand, const uint8_t* d_cand_desc, const int32_t* d_cand_lm,
+                                const double* d_cand_e_W, const double* d_cand_r_W, int n_lm, const uint8_t* d_lm_is3d, const double* T_WC1,
+                                double sigma, uint32_t match_threshold, const uint8_t* d_kp_use, const int32_t* d_kp_prev_lm,
+                                uint32_t* d_out_dist, int32_t* d_out_lm, double* d_out_hp_W, int32_t* d_out_ctr);
 
 /* M3: replaces the worker lambda of Frontend::matchMotionStereo (Frontend.cpp:1809-1907) for one (older frame,
  * camera) pair, up to and including the choice of k1_max/hps_W/initialisable; `quality` (acos, :1888) and the

@@ -1001,7 +1001,7 @@ void detect_free_camera(okb_context* ctx, int cam)
     LayerGeom& g = ws.geom[i];
     cudaFree(g.d_xs); cudaFree(g.d_xn); cudaFree(g.d_xa); cudaFree(g.d_ys); cudaFree(g.d_yn); cudaFree(g.d_ya);
   }
-  cudaFree(ws.d_epoch); cudaFree(ws.d_ties); cudaFree(ws.d_tie_sorted); cudaFree(ws.d_tiles); cudaFree(ws.d_ray_map); cudaFree(ws.d_jac_map);
+  cudaFree(ws.m2_d); cudaFree(ws.d_epoch); cudaFree(ws.d_ties); cudaFree(ws.d_tie_sorted); cudaFree(ws.d_tiles); cudaFree(ws.d_ray_map); cudaFree(ws.d_jac_map);
   cudaFree(ws.d_in); cudaFree(ws.d_img); cudaFree(ws.d_score); cudaFree(ws.d_touch); cudaFree(ws.d_integral); cudaFree(ws.d_cand);
   cudaFree(ws.d_cand_count); cudaFree(ws.d_fkey); cudaFree(ws.d_fval); cudaFree(ws.d_fslot); cudaFree(ws.d_kp); cudaFree(ws.d_kscale); cudaFree(ws.d_desc);
   cudaFree(ws.d_count); cudaFree(ws.d_m1_rows); cudaFree(ws.m_d); if (ws.m_h) cudaFreeHost(ws.m_h); cudaFree(ws.m3_d); if (ws.m3_h) cudaFreeHost(ws.m3_h); cudaFree(ws.motion.d); if (ws.motion.h) cudaFreeHost(ws.motion.h); cudaFree(ws.d_dbg); cudaFree(ws.d_rays); cudaFree(ws.d_rays_valid);

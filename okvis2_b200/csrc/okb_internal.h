@@ -63,6 +63,7 @@ struct MotionScratch { void* d = nullptr; size_t cap = 0; void* h = nullptr; siz
 
 struct CamWorkspace {
   okb_camera_config_t cfg;
+  uint8_t* m2_d = nullptr; size_t m2_cap = 0;   // scratch of okb_match_map_uninit_device (poses, world rays, use mask)
   float extraction_dir[3] = {0.f, 0.f, -1.f};   // D1: gravity in the camera frame (okb_set_extraction_direction)
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // side stream (integral image)

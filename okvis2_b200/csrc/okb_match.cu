@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(256, 4) k_match_gated(MatchArgs a)
   V3 r0 = v3(a.r0), r1 = v3(a.r1);
   const double* Tcw0 = nullptr; const double* Tcw1 = nullptr;   // M3 sequence: (C, r) poses of this frame
   if (view) { r0 = v3(view->Twc + 9); r1 = v3(a.frames[blockIdx.y].Twc + 9); Tcw0 = view->Tcw; Tcw1 = a.frames[blockIdx.y].Tcw; }
+  if (MODE == MODE_M2 && a.frames) r1 = v3(a.frames[blockIdx.y].Twc + 9);   // batched device form: the camera position of this frame
   const int n_tiles = (nc + kTile - 1) / kTile;
   if (n_tiles > 0) stage_tile_async<D16>(c_desc, nc, 0, s_desc2[0]);
   for (int tt = 0; tt < n_tiles; tt++) {
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(256, 4) k_match_gated(MatchArgs a)
     if (have_hp) { hp[0] = best_hp.x; hp[1] = best_hp.y; hp[2] = best_hp.z; hp[3] = 1.0; }
     else { hp[0] = hp[1] = hp[2] = hp[3] = 0.0; }
     if (a.out_init) a.out_init[fq + q] = best_init ? 1 : 0;
-    if (MODE == MODE_M2 && a.out_ctr && ctr) atomicAdd(a.out_ctr, ctr);
+    if (MODE == MODE_M2 && a.out_ctr && ctr) atomicAdd(a.out_ctr + (a.frames ? blockIdx.y : 0), ctr);   // per frame in the batched form
   }
 }
 
@@ -1625,6 +1626,66 @@ int okb_match_map_uninit(okb_context_t* ctx, int D, int n_kp, const uint8_t* kp_
   for (int i = 0; i < 3; i++) a.r1[i] = r_WC1[i];
   a.cos26 = gate_cos(2.6 * sigma); a.cos6 = gate_cos(6.0 * sigma);  // the libm algorithm, same function as on the device (okb_gatecos.h)
   return run_gated(ctx, MODE_M2, D, a, in_end, o_dist, o_end, o_idx, o_hp, 0, o_ctr, out_dist, out_lm, out_hp_W, nullptr, out_ctr);
+}
+
+// ---- M2, device-resident batched form: the queries are the camera's last detected features (descriptors, back-projections) ----
+struct M2Prep { const double* rays; const uint8_t* valid; const int32_t* count; const uint8_t* use_in; int cap; const M3Frame* frames; double* e_W; uint8_t* use; };
+// e1_W = T_WC1.C() * e1_C.normalized() (Frontend.cpp:1620-1627) and the use mask: inside the frame's count, back-projection valid,
+// and the caller's mask (keypoints that already carry a landmark outside loop-closure mode)
+__global__ void __launch_bounds__(128) k_m2_prep(const __grid_constant__ M2Prep p)
+{
+  const int frame = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p.cap) return;
+  const size_t i = (size_t)frame * p.cap + k;
+  const bool in = k < min(p.count[frame], p.cap) && p.valid[i] && (p.use_in == nullptr || p.use_in[i]);
+  if (in) {
+    const V3 e = normalized(V3{p.rays[3 * i], p.rays[3 * i + 1], p.rays[3 * i + 2]});
+    const double* C = p.frames[frame].Twc;
+    p.e_W[3 * i] = (C[0] * e.x + C[1] * e.y) + C[2] * e.z;
+    p.e_W[3 * i + 1] = (C[3] * e.x + C[4] * e.y) + C[5] * e.z;
+    p.e_W[3 * i + 2] = (C[6] * e.x + C[7] * e.y) + C[8] * e.z;
+  }
+  p.use[i] = in ? 1 : 0;
+}
+
+int okb_match_map_uninit_device(okb_context_t* ctx, int cam, int n_frames, int n_cand, const uint8_t* d_cand_desc, const int32_t* d_cand_lm,
+                                const double* d_cand_e_W, const double* d_cand_r_W, int n_lm, const uint8_t* d_lm_is3d, const double* T_WC1,
+                                double sigma, uint32_t match_threshold, const uint8_t* d_kp_use, const int32_t* d_kp_prev_lm,
+                                uint32_t* d_out_dist, int32_t* d_out_lm, double* d_out_hp_W, int32_t* d_out_ctr)
+{
+  OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams && n_cand >= 0 && n_lm >= 0 && T_WC1 && d_out_dist && d_out_lm && d_out_hp_W,
+                 "okb_match_map_uninit_device");
+  CamWorkspace& ws = ctx->cams[cam];
+  OKB_CHECK_ARGS(ws.has_model && n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_map_uninit_device (camera model set? okb_set_camera_model)");
+  OKB_CHECK_ARGS(ws.cfg.descriptor_bytes == 64, "okb_match_map_uninit_device (64-byte descriptors)");
+  OKB_CHECK_ARGS(n_cand == 0 || (d_cand_desc && d_cand_lm && d_cand_e_W && d_cand_r_W && d_lm_is3d), "okb_match_map_uninit_device");
+  OKB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ws.stream;
+  const size_t n = (size_t)n_frames * ws.kp_cap;
+  const size_t b_frames = (sizeof(M3Frame) * n_frames + 255) & ~(size_t)255, need = b_frames + ((n * 24 + 255) & ~(size_t)255) + n;
+  if (need > ws.m2_cap) {
+    OKB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(ws.m2_d); ws.m2_d = nullptr; ws.m2_cap = 0;
+    OKB_CUDA(cudaMalloc(&ws.m2_d, need + need / 4)); ws.m2_cap = need + need / 4;
+  }
+  M3Frame* d_frames = (M3Frame*)ws.m2_d; double* e_W = (double*)(ws.m2_d + b_frames); uint8_t* use = ws.m2_d + b_frames + ((n * 24 + 255) & ~(size_t)255);
+  std::vector<M3Frame> hf(n_frames);   // pageable staging: copied before cudaMemcpyAsync returns
+  for (int b = 0; b < n_frames; b++) { memcpy(hf[b].Twc, T_WC1 + 12 * (size_t)b, 96); memset(hf[b].Tcw, 0, 96); }
+  OKB_CUDA(cudaMemcpyAsync(d_frames, hf.data(), sizeof(M3Frame) * n_frames, cudaMemcpyHostToDevice, st));
+  M2Prep p; p.rays = ws.d_rays; p.valid = ws.d_rays_valid; p.count = ws.d_count; p.use_in = d_kp_use; p.cap = ws.kp_cap; p.frames = d_frames;
+  p.e_W = e_W; p.use = use;
+  k_m2_prep<<<dim3((ws.kp_cap + 127) / 128, n_frames), 128, 0, st>>>(p);
+  MatchArgs a; memset(&a, 0, sizeof(a));
+  a.nq = ws.kp_cap; a.q_count = ws.d_count; a.q_stride = (size_t)ws.kp_cap; a.q_desc = ws.d_desc; a.q_e = e_W; a.q_use = use; a.q_prev_lm = d_kp_prev_lm;
+  a.nc = n_cand; a.c_stride = 0; a.c_desc = d_cand_desc; a.c_lm = d_cand_lm; a.c_e = d_cand_e_W; a.c_r = d_cand_r_W; a.lm_is3d = d_lm_is3d;
+  a.frames = d_frames; a.thr = match_threshold;
+  a.cos26 = gate_cos(2.6 * sigma); a.cos6 = gate_cos(6.0 * sigma);
+  a.out_dist = d_out_dist; a.out_idx = d_out_lm; a.out_hp = d_out_hp_W; a.out_ctr = d_out_ctr;
+  if (d_out_ctr) OKB_CUDA(cudaMemsetAsync(d_out_ctr, 0, (size_t)n_frames * 4, st));
+  k_match_gated<4, MODE_M2><<<dim3((ws.kp_cap + 7) / 8, n_frames), 256, 0, st>>>(a);
+  ctx->launches += 2;
+  OKB_CUDA(cudaGetLastError());
+  return OKB_OK;
 }
 
 static int stereo_like(okb_context_t* ctx, int mode, int D, int n0, const uint8_t* desc0, const uint8_t* use0,

@@ -101,6 +101,7 @@ _PROTOS = {
     "okb_match_stereo_device_ptr": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]),
     "okb_process_multiframe": (i32, [vp, i32, vp, i32, vp, f64, u32]),
     "okb_stream_use_graph": (i32, [vp, i32]),
+    "okb_match_map_uninit_device": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, C.c_double, u32, vp, vp, vp, vp, vp, vp]),
     "okb_set_extraction_direction": (i32, [vp, i32, vp]),
     "okb_get_extraction_direction": (i32, [vp, i32, vp]),
     "okb_m3_set_fused": (None, [i32]),

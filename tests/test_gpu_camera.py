@@ -7,7 +7,7 @@ import pytest
 import oracle
 from okvis2_b200 import lib as okl
 from okvis2_b200.frontend import Frontend, MultiFrame
-from okvis2_b200.synth import synth_stereo
+from okvis2_b200.synth import map_scene, synth_stereo
 
 pytestmark = pytest.mark.gpu
 
@@ -361,5 +361,78 @@ def test_extraction_direction_is_gravity_in_the_camera_frame():
         okl.check(okl.lib().okb_get_extraction_direction(fe.ctx, 1, okl.ptr(d)))
         assert np.array_equal(d, np.array([0, 0, -1], np.float32))      # default: camera looking along world x/y, z up
         assert np.array_equal(mf.frames[0].descriptors, mf.frames[1].descriptors)
+    finally:
+        fe.close()
+
+
+@pytest.mark.parametrize("loop", [False, True])
+def test_device_resident_m2_equals_oracle(loop):
+    """M2 (matchToMapByThreadUnitialised) on the features that stay on the device: e1_W = T_WC1.C() * e1_C.normalized() per frame, the
+    use mask from the back-projection validity and the caller's mask, per-frame pose and early-break counter; against the oracle"""
+    import torch
+    B = 3
+    fe = Frontend(1, 752, 480, max_batch=B)
+    fe.configure(threshold=30, octaves=3, max_keypoints=800)
+    fe.setCameraModel(0, **EUROC[0])
+    L_ = okl.lib()
+    try:
+        imgs = np.stack([synth_stereo(900 + t, 752, 480)[0] for t in range(B)])
+        d_img = torch.from_numpy(imgs).cuda()
+        okl.check(L_.okb_detect_describe_batch_device(fe.ctx, 0, B, d_img.data_ptr()))
+        cap = C.c_int(0)
+        L_.okb_device_features(fe.ctx, 0, None, None, None, C.byref(cap)); cap = cap.value
+        feats = []
+        for b in range(B):
+            kp = np.zeros(cap, okl.KP_DTYPE); d = np.zeros((cap, 64), np.uint8); n = C.c_int(0)
+            okl.check(L_.okb_fetch_features(fe.ctx, 0, b, kp.ctypes.data, d.ctypes.data, cap, C.byref(n)))
+            feats.append((kp[:n.value], d[:n.value]))
+        rng = np.random.default_rng(11)
+        # pool from frame 0's descriptors; copied candidates get geometry that triangulates with their source keypoint
+        kp0, d0 = feats[0]
+        rays0, _ = oracle_bp(EUROC[0], kp0)
+        m = map_scene(23, np.zeros((len(d0), 2)), d0, 1500, frac_3d=0.4, flip_p=0.05)
+        poses = []
+        for b in range(B):
+            a = 0.02 * b
+            Cm = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+            poses.append((Cm, np.array([0.05 + 0.01 * b, 0.0, 0.002 * b])))
+        e0n = rays0 / np.sqrt((rays0[:, 0] ** 2 + rays0[:, 1] ** 2) + rays0[:, 2] ** 2)[:, None]
+        ke0 = world_rays(poses[0][0], e0n)
+        P = ke0[m["src"][m["cand_lm"]]] * rng.uniform(0.3, 30.0, (len(m["cand_lm"]), 1)) + poses[0][1]
+        r = rng.normal(0, 0.4, P.shape)
+        e = P - r; e /= np.linalg.norm(e, axis=1, keepdims=True)
+        cp = m["is_copy"][m["cand_lm"]] & (rng.random(len(P)) < 0.8)
+        m["cand_e_W"][cp] = e[cp]; m["cand_r_W"][cp] = r[cp]
+        use = np.zeros((B, cap), np.uint8); prev = np.full((B, cap), -1, np.int32)
+        for b in range(B):
+            nb = len(feats[b][0])
+            use[b, :nb] = rng.random(nb) > 0.05
+            if loop:
+                prev[b, :nb] = np.where(rng.random(nb) < 0.5, rng.integers(0, len(m["lm_is3d"]), nb), -1)
+        T = np.stack([np.concatenate([Cm.reshape(9), rr]) for Cm, rr in poses])
+        dev = {k: torch.from_numpy(np.ascontiguousarray(m[k])).cuda() for k in ("cand_desc", "cand_lm", "cand_e_W", "cand_r_W", "lm_is3d")}
+        d_use = torch.from_numpy(use).cuda(); d_prev = torch.from_numpy(prev).cuda()
+        dist = torch.zeros((B, cap), dtype=torch.int32, device="cuda"); lm = torch.zeros((B, cap), dtype=torch.int32, device="cuda")
+        hp = torch.zeros((B, cap, 4), dtype=torch.float64, device="cuda"); ctr = torch.zeros(B, dtype=torch.int32, device="cuda")
+        okl.check(L_.okb_match_map_uninit_device(fe.ctx, 0, B, len(m["cand_lm"]), dev["cand_desc"].data_ptr(), dev["cand_lm"].data_ptr(),
+                                                 dev["cand_e_W"].data_ptr(), dev["cand_r_W"].data_ptr(), len(m["lm_is3d"]), dev["lm_is3d"].data_ptr(),
+                                                 np.ascontiguousarray(T).ctypes.data, 1.0 / 458.0, 60, d_use.data_ptr(),
+                                                 d_prev.data_ptr() if loop else None, dist.data_ptr(), lm.data_ptr(), hp.data_ptr(), ctr.data_ptr()))
+        okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+        dist, lm, hp, ctr = dist.cpu().numpy().view(np.uint32), lm.cpu().numpy(), hp.cpu().numpy(), ctr.cpu().numpy()
+        matched = 0
+        for b in range(B):
+            kp, d = feats[b]; nb = len(kp)
+            rays, valid = oracle_bp(EUROC[0], kp)
+            en = rays / np.sqrt((rays[:, 0] * rays[:, 0] + rays[:, 1] * rays[:, 1]) + rays[:, 2] * rays[:, 2])[:, None]
+            Cm, rr = poses[b]
+            ke = np.ascontiguousarray(np.stack([(Cm[i, 0] * en[:, 0] + Cm[i, 1] * en[:, 1]) + Cm[i, 2] * en[:, 2] for i in range(3)], 1))
+            ref = oracle.match_map_uninit(d, ke, (use[b, :nb] & valid).astype(np.uint8), prev[b, :nb] if loop else None, m["cand_desc"], m["cand_lm"],
+                                          m["cand_e_W"], m["cand_r_W"], m["lm_is3d"], rr, 1.0 / 458.0, 60)
+            assert np.array_equal(dist[b, :nb], ref[0]) and np.array_equal(lm[b, :nb], ref[1]), b
+            assert np.array_equal(hp[b, :nb].view(np.uint64), ref[2].view(np.uint64)), b
+            assert ctr[b] == ref[3], b
+            matched += int((ref[1] >= 0).sum())
+        assert matched > 20
     finally:
         fe.close()
