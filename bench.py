@@ -1159,6 +1159,11 @@ def bind_to_gpu_numa_node(index):
 
 
 def main():
+    # stdout carries ONE JSON line: NCCL's version banner / debug output (torch's process group, okb_comm_init_*) goes to stderr
+    # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, and prints the banner at VERSION and WARN)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
