@@ -196,9 +196,21 @@ def test_stereo_scan_gate_split_with_dense_hits_and_overflow(scan_form):
     """M4 device form on crafted feature blocks: frame 0 holds near-duplicate descriptors (every pair is below the matching
     threshold: the hit list overflows and the sequential-replay kernel redoes the frame), frame 1 a normal mix with many
     hits per query, frame 2 is empty on the query side. All three must equal the oracle's transcription of the loop."""
+    matched = _stereo_ptr_case(3, 320, [[300, 250, 0], [310, 280, 100]], dense_div=3)
+    assert matched[0] > 100 and matched[1] > 30 and matched[2] == 0
+
+
+def test_stereo_device_form_batch_of_eight_large_frames(scan_form):
+    """the batched forms of the scan (tcgen05: one CTA per candidate tile streams all query tiles) at TUM-VI sizes: 8 frames of
+    ~2 000 keypoints in blocks of capacity 2 496 (20 candidate tiles, 16 query tiles)"""
+    counts = [[2000, 1900, 2496, 1, 1777, 2048, 2100, 1500], [1950, 2010, 2496, 300, 1800, 2047, 1, 1600]]
+    matched = _stereo_ptr_case(8, 2496, counts, dense_div=25, all_near_first=False)
+    assert sum(matched) > 400
+
+
+def _stereo_ptr_case(B, cap, counts, dense_div, all_near_first=True):
     import torch
     rng = np.random.default_rng(42)
-    B, cap = 3, 320
     fe = Frontend(0)
     L_ = okl.lib()
     models = []
@@ -217,7 +229,6 @@ def test_stereo_scan_gate_split_with_dense_hits_and_overflow(scan_form):
                 d[i, b // 8] ^= 1 << (b % 8)
         return d
 
-    counts = [[300, 250, 0], [310, 280, 100]]
     kps = [np.zeros((B, cap), okl.KP_DTYPE) for _ in range(2)]
     descs = [np.zeros((B, cap, 64), np.uint8) for _ in range(2)]
     for c in range(2):
@@ -225,11 +236,11 @@ def test_stereo_scan_gate_split_with_dense_hits_and_overflow(scan_form):
             n = counts[c][b]
             kps[c][b]["x"][:n] = rng.uniform(40, 700, n); kps[c][b]["y"][:n] = rng.uniform(40, 440, n)
             kps[c][b]["size"][:n] = rng.choice([12.0, 18.0, 24.0, 36.0], n)
-            if b == 0:
+            if b == 0 and all_near_first:
                 descs[c][b, :n] = near(n, 8)                                          # all pairs < 60
             else:
                 descs[c][b, :n] = rng.integers(0, 256, (n, 64), dtype=np.uint8)
-                descs[c][b, : n // 3] = near(n // 3, 20)                               # a third of them: dense hits
+                descs[c][b, : n // dense_div] = near(n // dense_div, 20)               # a part of them: dense hits
     # stereo geometry: points in front of both cameras so that many gates pass: camera 1 keypoints = camera 0 shifted
     for b in range(B):
         n = min(counts[0][b], counts[1][b])
@@ -259,8 +270,8 @@ def test_stereo_scan_gate_split_with_dense_hits_and_overflow(scan_form):
         assert np.array_equal(hp[b, :n0].view(np.uint64), ref[2].view(np.uint64)) and np.array_equal(init[b, :n0], ref[3]), b
         assert (k1[b, n0:] == -1).all()
         matched.append(int((ref[0] >= 0).sum()))
-    assert matched[0] > 100 and matched[1] > 30 and matched[2] == 0
     fe.close()
+    return matched
 
 
 def test_gate_cos_is_libm_and_both_m4_forms_agree():
