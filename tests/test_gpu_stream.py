@@ -159,3 +159,26 @@ def test_process_multiframe_equals_oracle(use_graph):
         assert np.array_equal(sb["hp"][:n0].view(np.uint64), ref[2].view(np.uint64)) and np.array_equal(sb["init"][:n0], ref[3])
         m4_total += int((ref[0] >= 0).sum())
     assert m1_total > 100 and m3_total > 100 and m4_total > 10
+
+
+def test_process_multiframe_mono_detect_only():
+    """the smallest multiframe: one camera, no landmark pool, no older keyframes, no stereo pair (graph captured at the second call)"""
+    fe = Frontend(1, W, H)
+    fe.configure(threshold=30, octaves=3, max_keypoints=MAXKP)
+    L_ = okl.lib()
+    o = oracle.Brisk(30, 3)
+    try:
+        for t in range(4):
+            img = np.ascontiguousarray(synth_stereo(520 + t, W, H)[0])
+            io = (okl.MultiframeCam * 1)()
+            kp = np.zeros(MAXKP, okl.KP_DTYPE); desc = np.zeros((MAXKP, 64), np.uint8)
+            q = io[0]
+            q.image = img.ctypes.data; q.stride_bytes = W; q.cap = MAXKP; q.kp = kp.ctypes.data; q.desc = desc.ctypes.data
+            okl.check(L_.okb_process_multiframe(fe.ctx, 1, io, 0, None, 20.0, 60))
+            rk, rd = o.detect_and_compute(img, MAXKP)
+            assert io[0].n == len(rk) and kp[:len(rk)].tobytes() == rk.tobytes() and np.array_equal(desc[:len(rk)], rd), t
+        g, d = C.c_longlong(), C.c_longlong()
+        okl.check(L_.okb_stream_stats(fe.ctx, C.byref(g), C.byref(d)))
+        assert (g.value, d.value) == (3, 1)
+    finally:
+        fe.close()
