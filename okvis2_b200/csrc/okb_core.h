@@ -450,23 +450,44 @@ struct RefineResult {
   ScanTrace above;
 };
 
-// Everything the reference does for one candidate that passed the 2-D maximum test (getKeypoints loop body).
-OKB_HDN void refine_candidate(const LayerView* L, int n_layers, int layer, int x_layer, int y_layer, int threshold,
-                              RefineResult& r)
+// Everything the reference does for one candidate that passed the 2-D maximum test (getKeypoints loop body), in two stages so
+// that the device can regroup the candidates in between: stage 1 is the search in the layer above (about half of the candidates
+// are not a maximum across scales and end there), stage 2 the layer below, the own patch and the scale / position fit.
+struct RefineMid {
+  float max_above, dx_above, dy_above;
+  int center;
+  int mode;   // 0: ended in stage 1 (no keypoint); 1: single-layer pyramid; 2: top layer; 3: between two layers (refine3D)
+};
+
+OKB_HDN void refine_stage1(const LayerView* L, int n_layers, int layer, int x_layer, int y_layer, RefineResult& r, RefineMid& m)
 {
-  const float basicSize = 12.0f;
-  const LayerView& tl = L[layer];
   r.keep = 0; r.own_touch = 0; r.has_above = 0;
   r.above.n_queries = 0; r.above.exited = 1; r.above.max_x = r.above.max_y = 0;
   r.x = r.y = r.size = r.response = 0.f;
-  if (n_layers == 1) {
+  m.max_above = m.dx_above = m.dy_above = 0.f; m.center = 0;
+  if (n_layers == 1) { m.mode = 1; return; }
+  if (layer == n_layers - 1) { m.mode = 2; return; }
+  // refine3D, first part
+  bool ismax = true;
+  m.center = b0(L[layer], x_layer, y_layer);
+  r.has_above = 1;
+  m.max_above = score_max_above(L, layer, x_layer, y_layer, m.center, ismax, m.dx_above, m.dy_above, &r.above);
+  m.mode = ismax ? 3 : 0;
+}
+
+OKB_HDN void refine_stage2(const LayerView* L, int n_layers, int layer, int x_layer, int y_layer, int threshold, const RefineMid& m,
+                           RefineResult& r)
+{
+  const float basicSize = 12.0f;
+  const LayerView& tl = L[layer];
+  if (m.mode == 1) {
     float dx, dy;
     const float mx = patch_subpixel(tl, x_layer, y_layer, dx, dy);
     r.x = (float)x_layer + dx; r.y = (float)y_layer + dy; r.size = basicSize; r.response = mx;
     r.keep = 1; r.own_touch = 2;
     return;
   }
-  if (layer == n_layers - 1) {
+  if (m.mode == 2) {
     bool ismax; float dx, dy;
     const int center = (uint8_t)(float)b0(tl, x_layer, y_layer);  // score is >= threshold here
     score_max_below(L, layer, x_layer, y_layer, center, ismax, dx, dy);
@@ -478,13 +499,10 @@ OKB_HDN void refine_candidate(const LayerView* L, int n_layers, int layer, int x
     r.size = basicSize * tl.scale; r.response = mx; r.keep = 1; r.own_touch = 2;
     return;
   }
-  // refine3D
+  // refine3D, second part
   bool ismax = true;
-  const int center = b0(tl, x_layer, y_layer);
-  float delta_x_above = 0, delta_y_above = 0;
-  r.has_above = 1;
-  const float max_above = score_max_above(L, layer, x_layer, y_layer, center, ismax, delta_x_above, delta_y_above, &r.above);
-  if (!ismax) return;
+  const int center = m.center;
+  const float max_above = m.max_above, delta_x_above = m.dx_above, delta_y_above = m.dy_above;
   float max, scale, x, y;
   if (layer % 2 == 0) {
     float delta_x_below, delta_y_below;
@@ -549,6 +567,14 @@ OKB_HDN void refine_candidate(const LayerView* L, int n_layers, int layer, int x
   }
   scale *= tl.scale;
   if (max > (float)threshold) { r.x = x; r.y = y; r.size = basicSize * scale; r.response = max; r.keep = 1; }
+}
+
+OKB_HDN void refine_candidate(const LayerView* L, int n_layers, int layer, int x_layer, int y_layer, int threshold,
+                              RefineResult& r)
+{
+  RefineMid m;
+  refine_stage1(L, n_layers, layer, x_layer, y_layer, r, m);
+  if (m.mode) refine_stage2(L, n_layers, layer, x_layer, y_layer, threshold, m, r);
 }
 
 // ---- tie-cell bitmap -------------------------------------------------------------------------------------------
