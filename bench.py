@@ -14,7 +14,8 @@ A step = one pass of the hot path over one batch of synthetic stereo frames; per
   * cpu_baseline / --impl reference : the CPU arm (oracle/: C++ std::thread driver over the C restatement of OpenCV-BRISK and the
             transcribed match loops; cv2.BRISK when importable) on the host cores, bounded sample. The only place this file
             executes oracle/ code.
-  * configs : sub-records of the other BASELINE.json workloads measured in the same run: euroc_octaves0 (the shipped okvis
+  * configs : sub-records of the other BASELINE.json workloads measured in the same run: euroc_okvis48 (Harris + BRISK2-48, the
+    reference's own detector / extractor pair, parity unpinned), euroc_octaves0 (the shipped okvis
             setting), tumvi (1024x1024, 2000 keypoints, 50 000 landmarks = config 3 and, run per GPU, config 5) and
             hilti_sharded (5-camera rig, camera c on GPU c % N, NCCL all-gather of the feature blocks = config 4).
 N > 1: one process per GPU (torchrun), each rank replays its own independent sequences (replicas, no data-path collective);
@@ -836,6 +837,129 @@ def run_replica(name, cfg, args, rank, world, local_rank, lanes, steps, full):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs[1] in the detector / extractor pair OKVIS2 itself constructs: Harris + uniformity enforcement,
+# 48-byte camera-aware, gravity-aligned BRISK2, octaves = 0 (config/euroc.yaml:63-67). The uniformity radius / threshold are chosen so
+# that the detector cap binds on the synthetic frames and >= 700 keypoints (euroc.yaml:67) survive the extractor's border removal.
+OKVIS48 = dict(W=752, H=480, kpts=700, max_kp=864, radius=8.0, abs_threshold=20, n_lm=5000, batch=32, ring=6, f=458.0)
+
+
+def run_okvis48(args, rank, world, local_rank, steps, with_cpu):
+    """value: device-resident step = per camera okb_detect_describe_batch_device (Harris, uniformity, BRISK2-48 with the camera-awareness
+    maps and the extraction direction, D4) + okb_match_map3d_device on the 48-byte rows; e2e: okb_detect_describe_batch from host buffers
+    (+ the same M1 on the device); cpu_baseline: the oracle's detect + describe on one core."""
+    import torch
+    from okvis2_b200 import lib as okl
+    from okvis2_b200.frontend import Frontend
+    cfg = OKVIS48
+    W, H, B, ring = cfg["W"], cfg["H"], cfg["batch"], cfg["ring"]
+    L_ = okl.lib()
+    fe = Frontend(2, W, H, device=local_rank, max_batch=B, descriptor_bytes=48)
+    fe.configure(threshold=cfg["radius"], absolute_threshold=cfg["abs_threshold"], octaves=0, max_keypoints=cfg["max_kp"])
+    T_WC = np.eye(4); T_WC[:3, :3] = np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0.]])   # camera looking horizontally: gravity = image +y
+    maps = []
+    for c in range(2):
+        fu, fv, cu, cv = intrinsics(cfg, c)
+        fe.setCameraModel(c, "radialtangential", (fu, fv), (cu, cv), DIST)
+        maps.append(fe.cameraAwarenessMaps(c))
+        okl.check(L_.okb_set_extraction_direction(fe.ctx, c, np.ascontiguousarray(T_WC[:3, :3]).ctypes.data))
+    Lf, Rf = make_frames(cfg, ring * B, 1000 + 100 * rank)
+    d_img = [torch.from_numpy(Lf).cuda(), torch.from_numpy(Rf).cuda()]
+    first = [fe.detectAndDescribeBatch(c, img[:1])[0] for c, img in enumerate((Lf, Rf))]
+    pools = [make_map(cfg, kp, desc, 40 + c) for c, (kp, desc) in enumerate(first)]
+    cap = C.c_int(0); L_.okb_device_features(fe.ctx, 0, None, None, None, C.byref(cap))
+    kp_cap = cap.value
+    d_maps, outs = [], []
+    for m in pools:
+        proj = np.broadcast_to(m["lm_proj"], (B,) + m["lm_proj"].shape).copy()
+        d_maps.append(dict(desc=torch.from_numpy(m["cand_desc"]).cuda(), lm=torch.from_numpy(m["cand_lm"]).cuda(), proj=torch.from_numpy(proj).cuda(),
+                           is3d=torch.from_numpy(m["lm_is3d"]).cuda()))
+        outs.append(dict(dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), lm=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda")))
+    streams = [torch.cuda.ExternalStream(L_.okb_stream(fe.ctx, c)) for c in range(2)]
+
+    def m1(c):
+        dm, o = d_maps[c], outs[c]
+        okl.check(L_.okb_match_map3d_device(fe.ctx, c, 48, B, len(dm["lm"]), dm["desc"].data_ptr(), dm["lm"].data_ptr(), len(dm["is3d"]),
+                                            dm["proj"].data_ptr(), dm["is3d"].data_ptr(), 20.0, 60, o["dist"].data_ptr(), o["lm"].data_ptr()))
+
+    def step(s):
+        for c in range(2):
+            okl.check(L_.okb_detect_describe_batch_device(fe.ctx, c, B, d_img[c][(s % ring) * B:(s % ring + 1) * B].data_ptr()))
+            m1(c)
+    warm = max(args.warmup, 3)
+    for s in range(warm):
+        step(s)
+    okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    l0 = L_.okb_launch_count(fe.ctx)
+    ev0 = torch.cuda.Event(enable_timing=True); ev0.record(streams[0])
+    streams[1].wait_event(ev0)
+    for s in range(steps):
+        step(warm + s)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for c in range(2):
+        ends[c].record(streams[c])
+    okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    dev_ms = max(ev0.elapsed_time(e) for e in ends)
+    launches = L_.okb_launch_count(fe.ctx) - l0
+    cnt = []
+    for c in range(2):
+        for b in range(B):
+            n = C.c_int(0); okl.check(L_.okb_fetch_features(fe.ctx, c, b, None, None, kp_cap, C.byref(n))); cnt.append(n.value)
+    if np.mean(cnt) < 0.95 * cfg["kpts"]:
+        raise RuntimeError(f"okvis48 workload: {np.mean(cnt):.0f} keypoints per frame < 0.95 x {cfg['kpts']}")
+    m1_matches = float(sum((o["lm"] >= 0).sum().item() for o in outs) / (2 * B))
+    # ---- end to end: host buffers (page-locked) through okb_detect_describe_batch, every copy inside the timed region
+    h_img = [torch.from_numpy(x).pin_memory() for x in (Lf, Rf)]
+    h_kp = [torch.zeros((B, kp_cap, 28), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h_desc = [torch.zeros((B, kp_cap, 48), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    n_out = np.zeros((2, B), np.int32)
+
+    def cam_job(c, s):
+        okl.check(L_.okb_detect_describe_batch(fe.ctx, c, B, h_img[c][(s % ring) * B:(s % ring + 1) * B].data_ptr(), W, h_kp[c].data_ptr(),
+                                               h_desc[c].data_ptr(), kp_cap, n_out[c].ctypes.data))
+        m1(c)
+
+    def host_step(s):
+        ts = [threading.Thread(target=cam_job, args=(c, s)) for c in range(2)]
+        for t in ts: t.start()
+        for t in ts: t.join()
+        okl.check(L_.okb_sync(fe.ctx))
+    for s in range(2):
+        host_step(s)
+    okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(steps):
+        host_step(2 + s)
+    okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    rec = {"value": B * steps / (dev_ms * 1e-3), "unit": "stereo frames/s", "ms_per_step": dev_ms / steps, "steps": steps,
+           "stereo_frames_per_step_per_gpu": B, "gpu_launches": int(launches),
+           "workload_stats": {"keypoints_per_frame": float(np.mean(cnt)), "keypoints_per_frame_min": int(min(cnt)), "m1_matches_per_frame": m1_matches},
+           "e2e": {"value": B * steps / e2e_s, "unit": "stereo frames/s", "h2d_bytes_per_step": 2 * B * W * H,
+                   "d2h_bytes_per_step": int(n_out.max(1).sum() * B * (28 + 48 + 25)),
+                   "api": "okb_detect_describe_batch (one host thread per camera, page-locked buffers) + okb_match_map3d_device"},
+           "config": {"workload": "euroc_okvis48", "W": W, "H": H, "keypoints_per_frame": cfg["kpts"], "detector_max_keypoints": cfg["max_kp"],
+                      "uniformity_radius": cfg["radius"], "absolute_threshold": cfg["abs_threshold"], "octaves": 0, "descriptor_bytes": 48, "n_lm": cfg["n_lm"],
+                      "camera_aware": True, "step": "per stereo frame: Harris + uniformity detect, camera-aware gravity-aligned BRISK2-48 describe, "
+                      "back-project, M1 match-to-map per camera", "l2_policy": f"ring of {ring} batches"},
+           "parity": "bit-exact vs oracle/brisk_oracle.c section 6; PARITY UNPINNED vs smartroboticslab/brisk@1ef8b42a (source absent)"}
+    if with_cpu:
+        import oracle
+        o = oracle.HarrisBrisk2(cfg["radius"], cfg["abs_threshold"], cfg["max_kp"])
+        d = np.zeros(3, np.float32); okl.check(L_.okb_get_extraction_direction(fe.ctx, 0, d.ctypes.data))
+        fu = float(np.float32(intrinsics(cfg, 0)[0]))
+        n_s = 6
+        t0 = time.perf_counter()
+        for i in range(n_s):
+            for c, img in enumerate((Lf, Rf)):
+                o.detect_and_compute(img[i], maps[c][0], maps[c][1], fu, d)
+        dt = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": n_s / dt, "unit": "stereo frames/s", "cores": 1, "kind": "port",
+                               "sample": f"{n_s} stereo frames, detect + describe only (no M1), oracle restatement on one core"}
+    fe.close()
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def run_sharded(args, name, cfg, rank, world, local_rank, steps):
     """Camera-sharded multiframe pipeline (BASELINE config 4): camera c on rank c % world; per step every rank runs
     detect+describe+back-project+M1 for its cameras on a batch of B multiframes, contributes its fixed-capacity feature
@@ -1208,6 +1332,9 @@ def main():
             dist.destroy_process_group()
         return
 
+    if os.environ.get("OKB_BENCH_OKVIS48_ONLY"):   # development hook: the D = 48 sub-record alone
+        print(json.dumps(run_okvis48(args, rank, world, local_rank, args.steps, with_cpu=not args.no_cpu_baseline)))
+        return
     head = run_replica(name, cfg, args, rank, world, local_rank, lanes, args.steps, full=True)
     rep = head.pop("_rep")
     gate_exact = bool(rep.L_.okb_gate_cos_exact(rep.fes[0].ctx))
@@ -1226,6 +1353,12 @@ def main():
                 raise
             except Exception as e:   # never lose the headline line to a sub-record
                 configs[sub] = {"error": repr(e)}
+        try:
+            configs["euroc_okvis48"] = run_okvis48(args, rank, world, local_rank, sub_steps, with_cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline))
+        except SystemExit:
+            raise
+        except Exception as e:
+            configs["euroc_okvis48"] = {"error": repr(e)}
         try:
             configs["hilti_sharded"] = run_sharded(args, "hilti", CONFIGS["hilti"], rank, world, local_rank, max(4, min(args.steps, 8)))
         except Exception as e:

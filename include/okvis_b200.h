@@ -25,7 +25,7 @@ typedef enum {
   OKB_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed */
   OKB_ERR_ARGUMENT = -3,    /* bad argument (null pointer, size out of range, unsupported D) */
   OKB_ERR_CAPACITY = -4,    /* a fixed-capacity device buffer overflowed (raise the config capacity) */
-  OKB_ERR_UNSUPPORTED = -5, /* feature not built (e.g. D=48 describe: reference extractor source absent) */
+  OKB_ERR_UNSUPPORTED = -5, /* feature not built (e.g. a device-resident matcher form on a D = 48 context, octaves > 0 with D = 48) */
   OKB_ERR_NCCL = -6
 } okb_status;
 
@@ -42,12 +42,16 @@ typedef struct {
  * FrontendParameters (okvis_common/include/okvis/Parameters.hpp:123-133). */
 typedef struct {
   int32_t width, height;    /* image size (u8, single channel) */
-  int32_t threshold;        /* AGAST corner threshold (absolute) */
+  int32_t threshold;        /* D = 64: AGAST corner threshold (1..254); D = 48: absolute Harris corner threshold (>= 1) */
   int32_t octaves;          /* 0 = single scale (the shipped okvis setting), n>0 = 2n scale-space layers */
   int32_t max_keypoints;    /* FrontendParameters::max_num_keypoints: keep the N strongest; 0 = no cap */
-  int32_t descriptor_bytes; /* 64 = BRISK-512 (north_star). 48 is accepted by the matchers only. */
+  int32_t descriptor_bytes; /* 64 = AGAST + BRISK-512 (north_star, pinned to OpenCV 4.13). 48 = the pair OKVIS2 itself constructs
+                             * (Frontend.cpp:2406-2412): Harris + uniformity-enforcement detector and 48-byte BRISK2 extractor; then
+                             * `threshold` is the absolute Harris threshold (Parameters.hpp:125), `uniformity_radius` the radius in
+                             * pixels (Parameters.hpp:124), octaves must be 0. PARITY UNPINNED vs smartroboticslab/brisk@1ef8b42a. */
   int32_t max_batch;        /* frames per batched call (>=1) */
   float pattern_scale;      /* BRISK pattern scale (1.0) */
+  float uniformity_radius;  /* D = 48 only: FrontendParameters::detection_threshold ("uniformity radius in pixels") */
 } okb_camera_config_t;
 
 typedef struct okb_context okb_context_t;

@@ -60,16 +60,22 @@ int okb_create(int device, int n_cams, const okb_camera_config_t* cfgs, okb_cont
     okb_camera_config_t& c = ctx->cams[i].cfg;
     if (c.max_batch < 1) c.max_batch = 1;
     if (c.descriptor_bytes == 0) c.descriptor_bytes = 64;
-    if (c.descriptor_bytes != 64) {
-      set_error("camera %d: descriptor_bytes=%d: detect/describe implements the 64-byte BRISK-512 descriptor only; the "
-                "48-byte camera-aware BRISK2 extractor of smartroboticslab/brisk has no available specification",
-                i, c.descriptor_bytes);
-      okb_destroy(ctx); return OKB_ERR_UNSUPPORTED;
+    if (c.descriptor_bytes != 64 && c.descriptor_bytes != 48) {
+      set_error("camera %d: descriptor_bytes=%d (64 = AGAST + BRISK-512, 48 = Harris + BRISK2)", i, c.descriptor_bytes);
+      okb_destroy(ctx); return OKB_ERR_ARGUMENT;
     }
     if (c.octaves < 0 || c.max_keypoints < 0 || c.max_keypoints >= (1 << 20)) {
       set_error("camera %d: octaves %d / max_keypoints %d out of range", i, c.octaves, c.max_keypoints); okb_destroy(ctx); return OKB_ERR_ARGUMENT;
     }
-    if (c.threshold < 1 || c.threshold > 254) { set_error("camera %d: threshold %d", i, c.threshold); okb_destroy(ctx); return OKB_ERR_ARGUMENT; }
+    if (c.descriptor_bytes == 48) {
+      if (c.octaves != 0) {
+        set_error("camera %d: the Harris + BRISK2 mode (descriptor_bytes = 48) is single-scale: octaves must be 0 (every shipped okvis configuration)", i);
+        okb_destroy(ctx); return OKB_ERR_UNSUPPORTED;
+      }
+      if (!(c.uniformity_radius > 0.f) || c.threshold < 1) {
+        set_error("camera %d: uniformity_radius %g / absolute threshold %d", i, c.uniformity_radius, c.threshold); okb_destroy(ctx); return OKB_ERR_ARGUMENT;
+      }
+    } else if (c.threshold < 1 || c.threshold > 254) { set_error("camera %d: threshold %d", i, c.threshold); okb_destroy(ctx); return OKB_ERR_ARGUMENT; }
     rc = detect_init_camera(ctx, i);
     if (rc != OKB_OK) { okb_destroy(ctx); return rc; }
   }
@@ -160,6 +166,7 @@ int okb_detect_describe_batch(okb_context_t* ctx, int cam, int n_frames, const u
   if (rc) return rc;
   CamWorkspace& ws = ctx->cams[cam];
   const int W = ws.cfg.width, H = ws.cfg.height;
+  const size_t D = (size_t)ws.cfg.descriptor_bytes;
   if (!images || !kp_out || !desc_out || !n_out || cap < 0 || n_frames < 1 || n_frames > ws.cfg.max_batch || stride_bytes < (size_t)W) {
     set_error("okb_detect_describe: bad arguments (n_frames %d of max_batch %d)", n_frames, ws.cfg.max_batch);
     return OKB_ERR_ARGUMENT;
@@ -197,12 +204,12 @@ int okb_detect_describe_batch(okb_context_t* ctx, int cam, int n_frames, const u
     if (out_pinned) {
       OKB_CUDA(cudaMemcpy2DAsync(kp_out, (size_t)cap * sizeof(okb_keypoint_t), ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t),
                                  (size_t)rows * sizeof(okb_keypoint_t), n_frames, cudaMemcpyDeviceToHost, st));
-      OKB_CUDA(cudaMemcpy2DAsync(desc_out, (size_t)cap * 64, ws.d_desc, (size_t)ws.kp_cap * 64, (size_t)rows * 64, n_frames,
+      OKB_CUDA(cudaMemcpy2DAsync(desc_out, (size_t)cap * D, ws.d_desc, (size_t)ws.kp_cap * D, (size_t)rows * D, n_frames,
                                  cudaMemcpyDeviceToHost, st));
     } else {
       OKB_CUDA(cudaMemcpy2DAsync(ws.h_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t), ws.d_kp, (size_t)ws.kp_cap * sizeof(okb_keypoint_t),
                                  (size_t)rows * sizeof(okb_keypoint_t), n_frames, cudaMemcpyDeviceToHost, st));
-      OKB_CUDA(cudaMemcpy2DAsync(ws.h_desc, (size_t)ws.kp_cap * 64, ws.d_desc, (size_t)ws.kp_cap * 64, (size_t)rows * 64, n_frames,
+      OKB_CUDA(cudaMemcpy2DAsync(ws.h_desc, (size_t)ws.kp_cap * D, ws.d_desc, (size_t)ws.kp_cap * D, (size_t)rows * D, n_frames,
                                  cudaMemcpyDeviceToHost, st));
     }
   }
@@ -223,7 +230,7 @@ int okb_detect_describe_batch(okb_context_t* ctx, int cam, int n_frames, const u
     n_out[b] = n;
     if (out_pinned) continue;
     memcpy(kp_out + (size_t)b * cap, ws.h_kp + (size_t)b * ws.kp_cap, (size_t)n * sizeof(okb_keypoint_t));
-    memcpy(desc_out + (size_t)b * cap * 64, ws.h_desc + (size_t)b * ws.kp_cap * 64, (size_t)n * 64);
+    memcpy(desc_out + (size_t)b * cap * D, ws.h_desc + (size_t)b * ws.kp_cap * D, (size_t)n * D);
   }
   return OKB_OK;
 }
@@ -276,7 +283,7 @@ int okb_fetch_features(okb_context_t* ctx, int cam, int frame, okb_keypoint_t* k
   if (n > cap) { set_error("okb_fetch_features: %d keypoints > capacity %d", n, cap); return OKB_ERR_CAPACITY; }
   *n_out = n;
   if (kp_out) OKB_CUDA(cudaMemcpy(kp_out, ws.d_kp + (size_t)frame * ws.kp_cap, (size_t)n * sizeof(okb_keypoint_t), cudaMemcpyDeviceToHost));
-  if (desc_out) OKB_CUDA(cudaMemcpy(desc_out, ws.d_desc + (size_t)frame * ws.kp_cap * 64, (size_t)n * 64, cudaMemcpyDeviceToHost));
+  if (desc_out) OKB_CUDA(cudaMemcpy(desc_out, ws.d_desc + (size_t)frame * ws.kp_cap * ws.cfg.descriptor_bytes, (size_t)n * ws.cfg.descriptor_bytes, cudaMemcpyDeviceToHost));
   return OKB_OK;
 }
 
@@ -316,6 +323,7 @@ int okb_export_features(okb_context_t* ctx, int cam, int n_frames, void* d_block
   if (rc) return rc;
   CamWorkspace& ws = ctx->cams[cam];
   if (!d_block || n_frames < 1 || n_frames > ws.cfg.max_batch) { set_error("okb_export_features: bad arguments"); return OKB_ERR_ARGUMENT; }
+  if (ws.cfg.descriptor_bytes != 64) { set_error("okb_export_features: the feature block holds 64-byte rows (camera %d has %d)", cam, ws.cfg.descriptor_bytes); return OKB_ERR_UNSUPPORTED; }
   OKB_CUDA(cudaSetDevice(ctx->device));
   uint8_t* p = (uint8_t*)d_block;
   const size_t counts = ((size_t)n_frames * 4 + 255) & ~(size_t)255;

@@ -684,14 +684,12 @@ OKB_UNROLL
 struct PatternPoint { float x, y, sigma; };
 
 // BRISK smoothed intensity of one pattern point. image: pitch-linear u8; integral: (w+1) x (h+1) int32, pitch ipitch.
-OKB_HDN int smoothed_intensity(const uint8_t* image, int pitch, const int32_t* integral, int ipitch,
-                               const float key_x, const float key_y, const PatternPoint bp)
+// (xf, yf) = position of the sample in the image, sigma_half = its smoothing half-width
+OKB_HDN int smoothed_intensity_at(const uint8_t* image, int pitch, const int32_t* integral, int ipitch,
+                                  const float xf, const float yf, const float sigma_half)
 {
-  const float xf = bp.x + key_x;
-  const float yf = bp.y + key_y;
   const int x = (int)xf;
   const int y = (int)yf;
-  const float sigma_half = bp.sigma;
   const float area = 4.0f * sigma_half * sigma_half;
   int ret_val;
   if (sigma_half < 0.5f) {
@@ -754,6 +752,11 @@ OKB_HDN int smoothed_intensity(const uint8_t* image, int pitch, const int32_t* i
            (uint32_t)right * (uint32_t)r_x1_i + (uint32_t)bottom * (uint32_t)r_y1_i;
   }
   return (int)(acc + (uint32_t)(scaling2 / 2)) / scaling2;
+}
+OKB_HDN int smoothed_intensity(const uint8_t* image, int pitch, const int32_t* integral, int ipitch,
+                               const float key_x, const float key_y, const PatternPoint bp)
+{
+  return smoothed_intensity_at(image, pitch, integral, ipitch, bp.x + key_x, bp.y + key_y, bp.sigma);
 }
 
 }  // namespace okb

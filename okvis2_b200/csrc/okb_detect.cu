@@ -991,12 +991,14 @@ int detect_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaEventCreate(&ws.ev_mid));
   OKB_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalizeSmem));
   OKB_CUDA(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, kResolveSmem));
+  if (c.descriptor_bytes == 48) return harris_init_camera(ctx, cam);
   return OKB_OK;
 }
 
 void detect_free_camera(okb_context* ctx, int cam)
 {
   CamWorkspace& ws = ctx->cams[cam];
+  harris_free_camera(ctx, cam);
   for (int i = 0; i < kMaxLayers; i++) {
     LayerGeom& g = ws.geom[i];
     cudaFree(g.d_xs); cudaFree(g.d_xn); cudaFree(g.d_xa); cudaFree(g.d_ys); cudaFree(g.d_yn); cudaFree(g.d_ya);
@@ -1045,11 +1047,19 @@ __global__ void __launch_bounds__(256) k_touch_clear(const uint32_t* epoch, uint
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) touch[i] = 0u;
 }
 
+// the integral images of a batch on `st` (also used by the D = 48 mode, okb_harris.cu)
+void integral_run(CamWorkspace& ws, const uint8_t* d_images, int src_pitch, size_t in_stride, int W, int H, int B, cudaStream_t st)
+{
+  k_integral_rows<<<dim3((H + 7) / 8, B), 256, 0, st>>>(d_images, src_pitch, in_stride, W, H, ws.d_integral, W + 1);
+  k_integral_cols<<<dim3((W + 31) / 32, B), 1024, 0, st>>>(W, H, ws.d_integral, W + 1);
+}
+
 // all frames are device resident: d_images = n_frames x H x src_pitch
 int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch, cudaEvent_t input_ready)
 {
   CamWorkspace& ws = ctx->cams[cam];
   const okb_camera_config_t& c = ws.cfg;
+  if (c.descriptor_bytes == 48) return harris_run_device(ctx, cam, n_frames, d_images, src_pitch, input_ready);
   const int W = c.width, H = c.height, B = n_frames;
   cudaStream_t st = ws.stream;
   if (ctx->timers_on) collect_timing(ctx, ws);

@@ -25,6 +25,16 @@ void set_error(const char* fmt, ...);
     }                                                                                         \
   } while (0)
 
+// the device-resident matcher forms and the live path read the camera's descriptor block with 64-byte rows
+#define OKB_REQUIRE_D64(ws, who)                                                                                              \
+  do {                                                                                                                        \
+    if ((ws).cfg.descriptor_bytes != 64) {                                                                                    \
+      okb::set_error("%s: device-resident form for 64-byte descriptors only (this camera has %d; use the host-buffer matcher " \
+                     "forms, which take D = 48)", who, (ws).cfg.descriptor_bytes);                                           \
+      return OKB_ERR_UNSUPPORTED;                                                                                             \
+    }                                                                                                                         \
+  } while (0)
+
 struct LayerGeom {
   int w, h, pitch;
   size_t offset;  // byte offset of this layer inside one frame's layer block
@@ -64,6 +74,7 @@ struct MotionScratch { void* d = nullptr; size_t cap = 0; void* h = nullptr; siz
 struct CamWorkspace {
   okb_camera_config_t cfg;
   uint8_t* m2_d = nullptr; size_t m2_cap = 0;   // scratch of okb_match_map_uninit_device (poses, world rays, use mask)
+  void* harris = nullptr;                     // okb::HarrisState (okb_harris.cu): workspace of the D = 48 mode
   float extraction_dir[3] = {0.f, 0.f, -1.f};   // D1: gravity in the camera frame (okb_set_extraction_direction)
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // side stream (integral image)
@@ -155,6 +166,8 @@ struct okb_context {
   float* d_scale_bounds = nullptr;         // 63 float boundaries of the keypoint-size -> scale-index map
   uint32_t* d_size_list = nullptr;         // pattern extent per scale index
   float pattern_scale = 1.0f;
+  okb::PatternPoint h_pat0[okb::kPoints];  // host copy: the pattern at scale 0, rotation 0 (pair classification)
+  uint32_t h_size_list[okb::kScales];      // host copy of the pattern extents
   int timers_on = 0;
   void* stereo_scratch = nullptr; size_t stereo_cap = 0;   // device scratch of okb_match_stereo_device*
   okb::MotionScratch motion;   // scratch of okb_match_motion_stereo_device_ptr (one per context)
@@ -172,6 +185,10 @@ int detect_init_camera(okb_context* ctx, int cam);
 void detect_free_camera(okb_context* ctx, int cam);
 int detect_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch, cudaEvent_t input_ready = nullptr);
 int camera_backproject_batch(okb_context* ctx, int cam, int n_frames);
+// D = 48 mode (okb_harris.cu)
+int harris_init_camera(okb_context* ctx, int cam);
+void harris_free_camera(okb_context* ctx, int cam);
+int harris_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch, cudaEvent_t input_ready);
 struct Model;
 int camera_stereo_prep_pair(okb_context* ctx, const okb_camera_model_t* const model[2], const double* const C_WC[2], const okb_keypoint_t* const d_kp[2],
                             const int32_t* const d_count[2], const int cap[2], int n_frames, double* const d_rays[2], uint8_t* const d_valid[2],

@@ -302,9 +302,10 @@ int okb_store_frame_from_last(okb_context_t* ctx, int slot, int cam, int batch_i
   const int rc = store_slot(ctx, slot, cam, n, &e);
   if (rc) return rc;
   PrepareState* s = static_cast<PrepareState*>(ctx->prepare);
-  if (s->D != 64) { set_error("okb_store_frame_from_last: the store holds %d-byte descriptors", s->D); return OKB_ERR_ARGUMENT; }
+  const size_t D = (size_t)ws.cfg.descriptor_bytes;
+  if (s->D != (int)D) { set_error("okb_store_frame_from_last: the store holds %d-byte descriptors, camera %d makes %d-byte ones", s->D, cam, (int)D); return OKB_ERR_ARGUMENT; }
   if (n > 0) {
-    OKB_CUDA(cudaMemcpyAsync(e->d_desc, ws.d_desc + (size_t)batch_index * ws.kp_cap * 64, (size_t)n * 64, cudaMemcpyDeviceToDevice, s->stream));
+    OKB_CUDA(cudaMemcpyAsync(e->d_desc, ws.d_desc + (size_t)batch_index * ws.kp_cap * D, (size_t)n * D, cudaMemcpyDeviceToDevice, s->stream));
     OKB_CUDA(cudaMemcpyAsync(e->d_rays, ws.d_rays + (size_t)batch_index * ws.kp_cap * 3, (size_t)n * 24, cudaMemcpyDeviceToDevice, s->stream));
     OKB_CUDA(cudaStreamSynchronize(s->stream));
   }

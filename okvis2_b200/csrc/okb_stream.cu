@@ -127,6 +127,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
   if (!ctx || n_cams < 1 || n_cams != ctx->n_cams || !io || n_pairs < 0 || (n_pairs > 0 && !pairs)) {
     set_error("okb_process_multiframe: bad arguments (one okb_multiframe_cam_t per camera of the context)"); return OKB_ERR_ARGUMENT;
   }
+  for (int c = 0; c < n_cams; c++) OKB_REQUIRE_D64(ctx->cams[c], "okb_process_multiframe");
   OKB_CUDA(cudaSetDevice(ctx->device));
   StreamState* S = state(ctx);
   auto now = [] { return std::chrono::steady_clock::now(); };

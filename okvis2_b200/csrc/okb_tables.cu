@@ -23,6 +23,8 @@ int tables_init(okb_context* ctx, float pattern_scale)
   OKB_CUDA(cudaMemcpy(ctx->d_scale_bounds, T.scale_bounds.data(), T.scale_bounds.size() * 4, cudaMemcpyHostToDevice));
   OKB_CUDA(cudaMalloc(&ctx->d_size_list, T.size_list.size() * 4));
   OKB_CUDA(cudaMemcpy(ctx->d_size_list, T.size_list.data(), T.size_list.size() * 4, cudaMemcpyHostToDevice));
+  for (int i = 0; i < kPoints; i++) ctx->h_pat0[i] = T.pattern[i];
+  for (int i = 0; i < kScales; i++) ctx->h_size_list[i] = T.size_list[i];
   ctx->n_short = (int)T.short_pairs.size(); ctx->n_long = (int)T.long_pairs.size();
   return OKB_OK;
 }

@@ -118,9 +118,10 @@ class Frontend:
     def setBriskMatchingThreshold(self, threshold):
         self.briskMatchingThreshold_ = float(threshold)
 
-    def configure(self, threshold=None, octaves=None, max_keypoints=None, matching_threshold=None):
+    def configure(self, threshold=None, octaves=None, max_keypoints=None, matching_threshold=None, absolute_threshold=None):
         """Set several parameters with a single re-initialisation."""
         if threshold is not None: self.briskDetectionThreshold_ = float(threshold)
+        if absolute_threshold is not None: self.briskDetectionAbsoluteThreshold_ = float(absolute_threshold)
         if octaves is not None: self.briskDetectionOctaves_ = int(octaves)
         if max_keypoints is not None: self.briskDetectionMaximumKeypoints_ = int(max_keypoints)
         if matching_threshold is not None: self.briskMatchingThreshold_ = float(matching_threshold)
@@ -369,8 +370,12 @@ class Frontend:
         self.close()
         cfgs = (CameraConfig * self.numCameras)()
         for i, (w, h) in enumerate(self._geom):
-            cfgs[i] = CameraConfig(w, h, int(self.briskDetectionThreshold_), self.briskDetectionOctaves_,
-                                   self.briskDetectionMaximumKeypoints_, self._D, self._max_batch, 1.0)
+            if self._D == 48:   # the reference's own pair (Frontend.cpp:2406-2409): (uniformity radius, octaves, absolute threshold, max keypoints)
+                cfgs[i] = CameraConfig(w, h, int(self.briskDetectionAbsoluteThreshold_), self.briskDetectionOctaves_,
+                                       self.briskDetectionMaximumKeypoints_, 48, self._max_batch, 1.0, float(self.briskDetectionThreshold_))
+            else:               # AGAST + BRISK-512: briskDetectionThreshold_ re-interpreted as the AGAST threshold
+                cfgs[i] = CameraConfig(w, h, int(self.briskDetectionThreshold_), self.briskDetectionOctaves_,
+                                       self.briskDetectionMaximumKeypoints_, self._D, self._max_batch, 1.0, 0.0)
         ctx = C.c_void_p()
         check(_l.lib().okb_create(self._device, self.numCameras, cfgs, C.byref(ctx)))
         self._ctx = ctx

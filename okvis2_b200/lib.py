@@ -29,7 +29,7 @@ class OkbError(RuntimeError):
 class CameraConfig(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("threshold", C.c_int32), ("octaves", C.c_int32),
                 ("max_keypoints", C.c_int32), ("descriptor_bytes", C.c_int32), ("max_batch", C.c_int32),
-                ("pattern_scale", C.c_float)]
+                ("pattern_scale", C.c_float), ("uniformity_radius", C.c_float)]
 
 
 class CameraModel(C.Structure):

@@ -377,3 +377,65 @@ def compute_overlaps(models, intr, widths, heights, C_rel, masks=False):
         return out.astype(bool)
     mats = [[data[offs[s * n + c]:offs[s * n + c] + int(widths[c]) * int(heights[c])].reshape(int(heights[c]), int(widths[c])) for c in range(n)] for s in range(n)]
     return out.astype(bool), mats
+
+
+class HarrisBrisk2:
+    """The detector / extractor pair OKVIS2 constructs (Frontend.cpp:2406-2412): Harris score + uniformity enforcement, 48-byte BRISK2
+    at one pattern scale, optionally camera-aware and aligned with the extraction direction (Frontend.cpp:232-251). octaves = 0.
+    PARITY UNPINNED vs smartroboticslab/brisk@1ef8b42a (oracle/brisk_oracle.c section 6)."""
+
+    def __init__(self, uniformity_radius=38.0, absolute_threshold=150, max_keypoints=700, pattern_scale=1.0):
+        L = lib()
+        L.okvo_brisk_create_dmax.restype = C.c_void_p
+        L.okvo_brisk_create_dmax.argtypes = [C.c_int, C.c_int, C.c_float, C.c_double]
+        L.okvo_harris_scores.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.okvo_harris_maxima.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.okvo_harris_lut.restype = C.c_float
+        L.okvo_harris_lut.argtypes = [C.c_float, C.c_int, C.c_int]
+        L.okvo_harris_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.okvo_brisk2_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_float, C.c_void_p]
+        L.okvo_brisk2_warp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        self.h = L.okvo_brisk_create_dmax(0, 0, pattern_scale, 5.1)
+        self.D = L.okvo_brisk_descriptor_bytes(self.h)
+        self.radius, self.threshold, self.max_kp = float(uniformity_radius), int(absolute_threshold), int(max_keypoints)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().okvo_brisk_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def scores(img):
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.zeros(img.shape, np.int32)
+        lib().okvo_harris_scores(_p(img), img.shape[1], img.shape[0], img.shape[1], _p(out))
+        return out
+
+    def maxima(self, score):
+        score = np.ascontiguousarray(score, np.int32)
+        n = lib().okvo_harris_maxima(_p(score), score.shape[1], score.shape[0], self.threshold, None, 0)
+        xy = np.zeros((max(n, 1), 2), np.int32)
+        lib().okvo_harris_maxima(_p(score), score.shape[1], score.shape[0], self.threshold, _p(xy), n)
+        return xy[:n]
+
+    def detect(self, img, cap=1 << 16):
+        img = np.ascontiguousarray(img, np.uint8)
+        kp = np.zeros(cap, KP_DTYPE)
+        n = lib().okvo_harris_detect(_p(img), img.shape[1], img.shape[0], img.shape[1], self.radius, self.threshold, self.max_kp, _p(kp), cap)
+        assert 0 <= n <= cap
+        return kp[:n].copy()
+
+    def compute(self, img, kp, rays=None, jac=None, fu=0.0, direction=None):
+        img = np.ascontiguousarray(img, np.uint8)
+        kp = np.ascontiguousarray(kp, KP_DTYPE).copy()
+        desc = np.zeros((max(len(kp), 1), self.D), np.uint8)
+        if rays is not None:
+            rays = _c(rays, np.float32); jac = _c(jac, np.float32); direction = _c(direction, np.float32)
+        m = lib().okvo_brisk2_compute(self.h, _p(img), img.shape[1], img.shape[0], _p(kp), len(kp), _p(desc),
+                                      None if rays is None else _p(rays), None if rays is None else _p(jac), float(fu),
+                                      None if rays is None else _p(direction))
+        return kp[:m].copy(), desc[:m].copy()
+
+    def detect_and_compute(self, img, rays=None, jac=None, fu=0.0, direction=None):
+        return self.compute(img, self.detect(img), rays, jac, fu, direction)

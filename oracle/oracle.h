@@ -39,6 +39,18 @@ int okvo_cap_strongest(okvo_keypoint_t* kp, int n, int max_kp);
 int okvo_brisk_detect_and_compute(okvo_brisk_t* b, const uint8_t* img, int W, int H, int stride, int max_kp,
                                   okvo_keypoint_t* kp, int cap, uint8_t* desc);
 
+
+/* Harris + uniformity detector and 48-byte BRISK2 extractor (PARITY UNPINNED vs smartroboticslab/brisk) */
+okvo_brisk_t* okvo_brisk_create_dmax(int threshold, int octaves, float pattern_scale, double dmax_factor);
+void okvo_harris_scores(const uint8_t* img, int W, int H, int stride, int32_t* score);
+int okvo_harris_maxima(const int32_t* score, int W, int H, int threshold, int* xy, int cap);
+float okvo_harris_lut(float radius, int dx, int dy);
+int okvo_harris_detect(const uint8_t* img, int W, int H, int stride, float radius, int threshold, int max_kp, okvo_keypoint_t* kp, int cap);
+int okvo_brisk2_basic_scale(void);
+int okvo_brisk2_warp(const float e[3], const float J[6], const float d[3], float fu, float M[4]);
+int okvo_brisk2_compute(const okvo_brisk_t* b, const uint8_t* image, int W, int H, okvo_keypoint_t* kp, int n, uint8_t* desc,
+                        const float* rays, const float* jac, float fu, const float* dir);
+
 #ifdef __cplusplus
 }
 #endif

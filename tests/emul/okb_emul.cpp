@@ -297,3 +297,141 @@ extern "C" long okb_emul_gate_cos_sizes(double f, unsigned first_bits, unsigned 
   }
   return bad;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// D = 48 mode (okvis2_b200/csrc/okb_harris.cu): the same per-element functions (okb_harris_core.h) and the same parallel
+// formulation -- run-parity maxima, occupancy as a per-candidate sum over higher-ranked accepted candidates, decided in rounds --
+// executed serially. Returns the number of keypoints; stats[0] = maxima, [1] = rounds, [2] = accepted before the border test.
+#include "../../okvis2_b200/csrc/okb_harris_core.h"
+
+extern "C" int okb_emul_harris_brisk2(const uint8_t* img, int W, int H, float radius, int threshold, int max_kp, const float* rays,
+                                      const float* jac, float fu, const float* dir, Kp* kp_out, uint8_t* desc_out, int cap, int* stats)
+{
+  if (!g_tables) { g_tables = new HostTables(); if (!build_host_tables(1.0f, *g_tables)) return -1; }
+  const HostTables& T = *g_tables;
+  std::vector<int32_t> score((size_t)W * H, 0);
+  {
+    std::vector<int8_t> gx((size_t)W * H, 0), gy((size_t)W * H, 0);
+    for (int y = 1; y <= H - 2; y++)
+      for (int x = 1; x <= W - 2; x++) {
+        int a, b;
+        harris_grad(img + (size_t)(y - 1) * W, img + (size_t)y * W, img + (size_t)(y + 1) * W, x, a, b);
+        gx[(size_t)y * W + x] = (int8_t)a; gy[(size_t)y * W + x] = (int8_t)b;
+      }
+    for (int y = 2; y < H - 2; y++)
+      for (int x = 2; x < W - 2; x++) {
+        int a = 0, b = 0, c = 0;
+        for (int j = 0; j < 3; j++)
+          for (int k = 0; k < 3; k++) {
+            const int w = (j == 1 ? 2 : 1) * (k == 1 ? 2 : 1);
+            const int u = gx[(size_t)(y + j - 1) * W + x + k - 1], v = gy[(size_t)(y + j - 1) * W + x + k - 1];
+            a += w * u * u; b += w * v * v; c += w * u * v;
+          }
+        score[(size_t)y * W + x] = harris_score(a, b, c);
+      }
+  }
+  struct C { uint64_t key; float nsc; int state; };
+  std::vector<C> cs;
+  for (int y = 2; y < H - 2; y++)
+    for (int x = W - 3; x >= 2; x--)   // any visiting order: the test is a pure function of the map
+      if (harris_is_maximum(score.data(), W, x, y, threshold))
+        cs.push_back(C{((uint64_t)(~(uint32_t)score[(size_t)y * W + x]) << 32) | ((uint32_t)x | ((uint32_t)y << 16)), 0.f, 0});
+  std::sort(cs.begin(), cs.end(), [](const C& a, const C& b) { return a.key < b.key; });
+  const int n = (int)cs.size();
+  stats[0] = n; stats[1] = 0; stats[2] = 0;
+  if (n == 0) return 0;
+  float lut[kUniLut * kUniLut];
+  for (int j = 0; j < kUniLut; j++) for (int i = 0; i < kUniLut; i++) lut[j * kUniLut + i] = uni_lut_host(radius, i - kUniWin, j - kUniWin);
+  const float max_score = (float)(int)(~(uint32_t)(cs[0].key >> 32));
+  auto sc_of = [&](int i) { return (int)(~(uint32_t)(cs[i].key >> 32)); };
+  auto hx_of = [&](int i) { return (int)((uint32_t)cs[i].key & 0xffffu) >> 1; };
+  auto hy_of = [&](int i) { return (int)((uint32_t)cs[i].key >> 16) >> 1; };
+  for (int i = 0; i < n; i++) cs[i].nsc = uni_nsc(uni_ratio(sc_of(i), max_score));
+  int lo = 0, acc = 0;
+  while (lo < n && !(max_kp > 0 && acc >= max_kp)) {
+    stats[1]++;
+    std::vector<int> next(n);
+    for (int i = 0; i < n; i++) next[i] = cs[i].state;
+    int first = n;
+    for (int i = lo; i < n; i++) {   // a round: every decision is taken from the states at the START of the round
+      if (cs[i].state) continue;
+      int sum = 0; bool blocked = false;
+      for (int j = 0; j < i && !blocked; j++) {
+        const int dx = hx_of(i) - hx_of(j), dy = hy_of(i) - hy_of(j);
+        if (dx < -kUniWin || dx > kUniWin || dy < -kUniWin || dy > kUniWin) continue;
+        const float l = lut[(dy + kUniWin) * kUniLut + dx + kUniWin];
+        if (l == 0.0f) continue;
+        if (cs[j].state == 0) blocked = true;
+        else if (cs[j].state == 1) sum += uni_stamp(cs[j].nsc, l);
+      }
+      if (blocked) { first = std::min(first, i); continue; }
+      next[i] = uni_rejected(uni_ratio(sc_of(i), max_score), sum) ? 2 : 1;
+    }
+    for (int i = 0; i < n; i++) cs[i].state = next[i];
+    for (int i = lo; i < first; i++) acc += cs[i].state == 1;
+    lo = first;
+  }
+  const int basic = brisk2_basic_scale_host();
+  const PatternPoint* pat0 = &T.pattern[(size_t)basic * kRot * kPoints];
+  const int border = (int)T.size_list[basic];
+  std::vector<uint32_t> sp;
+  {
+    const float d_max = (float)(kDmax48 * 1.0), d_min = (float)(8.2 * 1.0);
+    for (unsigned i = 1; i < (unsigned)kPoints; i++)
+      for (unsigned j = 0; j < i; j++) {
+        const float dx = T.pattern[j].x - T.pattern[i].x, dy = T.pattern[j].y - T.pattern[i].y, n2 = dx * dx + dy * dy;
+        if (n2 > d_min * d_min) continue;
+        if (n2 < d_max * d_max) sp.push_back(i | (j << 8));
+      }
+    if ((int)sp.size() != kShortPairs48) return -2;
+  }
+  std::vector<int32_t> integral((size_t)(W + 1) * (H + 1), 0);
+  for (int y = 0; y < H; y++) {
+    int rs = 0;
+    for (int x = 0; x < W; x++) { rs += img[(size_t)y * W + x]; integral[(size_t)(y + 1) * (W + 1) + x + 1] = integral[(size_t)y * (W + 1) + x + 1] + rs; }
+  }
+  int m = 0, kept = 0;
+  for (int i = 0; i < lo; i++) {
+    if (cs[i].state != 1) continue;
+    if (max_kp > 0 && kept >= max_kp) break;
+    kept++;
+    const int x = (int)((uint32_t)cs[i].key & 0xffffu), y = (int)((uint32_t)cs[i].key >> 16);
+    float dx, dy;
+    harris_subpixel(score.data(), W, x, y, dx, dy);
+    const float fx = (float)x + dx, fy = (float)y + dy;
+    int val[kPoints];
+    float angle;
+    if (!rays) {
+      if ((fx < (float)border) || (fx >= (float)(W - border)) || (fy < (float)border) || (fy >= (float)(H - border))) continue;
+      for (int p = 0; p < kPoints; p++) val[p] = smoothed_intensity(img, W, integral.data(), W + 1, fx, fy, pat0[p]);
+      int e0 = 0, e1 = 0;
+      for (const LongPair& lp : T.long_pairs) { const int dt = val[lp.i] - val[lp.j]; e0 += dt * lp.wdx / 1024; e1 += dt * lp.wdy / 1024; }
+      angle = (float)(atan2((double)(float)e1, (double)(float)e0) / 3.14159265358979323846 * 180.0);
+      int theta = (int)((double)kRot * ((double)angle / 360.0) + 0.5);
+      if (theta < 0) theta += kRot;
+      if (theta >= kRot) theta -= kRot;
+      if (angle < 0) angle += 360.f;
+      for (int p = 0; p < kPoints; p++) val[p] = smoothed_intensity(img, W, integral.data(), W + 1, fx, fy, pat0[(size_t)theta * kPoints + p]);
+    } else {
+      int u = (int)(fx + 0.5f), v = (int)(fy + 0.5f);
+      u = u < 0 ? 0 : (u > W - 1 ? W - 1 : u); v = v < 0 ? 0 : (v > H - 1 ? H - 1 : v);
+      float M[4];
+      bool ok = brisk2_warp(rays + ((size_t)v * W + u) * 3, jac + ((size_t)v * W + u) * 6, dir, fu, M);
+      float xs[kPoints], ys[kPoints];
+      for (int p = 0; ok && p < kPoints; p++) { brisk2_sample_pos(M, fx, fy, pat0[p], xs[p], ys[p]); ok = brisk2_sample_inside(xs[p], ys[p], pat0[p].sigma, W, H); }
+      if (!ok) continue;
+      for (int p = 0; p < kPoints; p++) val[p] = smoothed_intensity_at(img, W, integral.data(), W + 1, xs[p], ys[p], pat0[p].sigma);
+      angle = (float)(atan2((double)M[2], (double)M[0]) / 3.14159265358979323846 * 180.0);
+      if (angle < 0) angle += 360.f;
+    }
+    if (m < cap) {
+      kp_out[m] = Kp{fx, fy, 12.0f, angle, (float)sc_of(i), 0, -1};
+      uint32_t* w = reinterpret_cast<uint32_t*>(desc_out + (size_t)m * 48);
+      for (int q = 0; q < 12; q++) w[q] = 0;
+      for (int q = 0; q < kShortPairs48; q++) if (val[sp[q] & 255] > val[sp[q] >> 8]) w[q >> 5] |= 1u << (q & 31);
+    }
+    m++;
+  }
+  stats[2] = kept;
+  return m;
+}

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_keypoint_record_is_cv_keypoint_layout():
     assert L.KP_DTYPE.itemsize == 28
     assert L.KP_DTYPE.names == ("x", "y", "size", "angle", "response", "octave", "class_id")
-    assert C.sizeof(L.CameraConfig) == 32
+    assert C.sizeof(L.CameraConfig) == 36
 
 
 @pytest.mark.skipif(_has_gpu(), reason="CPU-only behaviour")
