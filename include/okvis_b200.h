@@ -180,8 +180,10 @@ int okb_camera_awareness_maps(okb_context_t* ctx, int cam, float* rays_out, floa
 
 /* D1: the extraction direction Frontend::detectAndDescribe hands to the extractor before every frame (okvis_frontend/src/Frontend.cpp:
  * 245-251): gravity in the camera frame, T_WC.inverse().C() * (0, 0, -1), as three floats. The library stores it per camera and hands
- * it back; the BRISK-512 extractor built here is rotation-invariant by its own orientation estimate and does not consume it (it is the
- * input of the gravity-aligned 48-byte BRISK2 mode, SURVEY 8f rank 1, which is not built). C_WC: row-major 3x3 rotation of T_WC. */
+ * it back. The D = 48 extractor (descriptor_bytes = 48) aligns its pattern with it when the camera-awareness maps are on the device
+ * (okb_camera_awareness_maps after okb_set_camera_model; without the maps it falls back to the gradient orientation of plain BRISK);
+ * the BRISK-512 extractor is rotation-invariant by its own orientation estimate and does not consume it. C_WC: row-major 3x3 rotation
+ * of T_WC. */
 int okb_set_extraction_direction(okb_context_t* ctx, int cam, const double C_WC[9]);
 int okb_get_extraction_direction(okb_context_t* ctx, int cam, float dir_out[3]);
 

@@ -224,6 +224,7 @@ int okb_set_camera_model(okb_context_t* ctx, int cam, const okb_camera_model_t* 
     set_error("okb_set_camera_model: bad arguments"); return OKB_ERR_ARGUMENT;
   }
   ctx->cams[cam].model = *model; ctx->cams[cam].has_model = 1;
+  ctx->cams[cam].maps_ready = 0;   // camera-awareness maps of an earlier model are stale (okb_camera_awareness_maps recomputes them)
   return OKB_OK;
 }
 

@@ -6,17 +6,21 @@
 // PARITY UNPINNED vs smartroboticslab/brisk@1ef8b42a (okb_harris_core.h). Bit-exact against oracle/brisk_oracle.c section 6.
 //
 // Kernels (one batch of frames per launch):
-//   k_harris_score   64x16 tiles: u8 tile + 2-pixel ring in shared memory -> Scharr/32 gradients as char2 -> 3x3 binomial sums of the
-//                    three products -> int32 score map (written once, 4 B per pixel)
-//   k_harris_maxima  one thread per pixel: 8-neighbour test against the score map (L2), the row scan's skip rule resolved by the
-//                    parity of the run of candidates to the left, append (score, x | y << 16)
+//   k_harris_score   a warp per 32-column strip marching down a band of rows, everything in registers + warp shuffles: pixel row ->
+//                    Scharr/32 gradients -> 3x3 binomial sums of the three products -> int32 score row (stored once) -> flags of the
+//                    8-neighbour test one row behind (stored as bytes)
+//   k_harris_maxima  one thread per 16 flags: the row scan's skip rule resolved by the parity of the run of candidates to the left,
+//                    append (score, x | y << 16)
 //   k_uniformity     one CTA per frame: bitonic sort of the maxima by (score desc, y, x) in shared memory, 32-pixel cell lists, then the
-//                    greedy uniformity enforcement as ROUNDS: a candidate is decided once every higher-ranked candidate whose stamp
-//                    can reach its cell is decided (occupancy of its own cell = min(255, sum of accepted stamps)); stops as soon as
-//                    max_keypoints are accepted in the decided prefix; sub-pixel refinement, border / warp validity, ordered
-//                    compaction into cv::KeyPoint records
+//                    greedy uniformity enforcement as WAVES: every candidate counts the higher-ranked candidates whose stamp can
+//                    reach its cell; a candidate whose count is zero is decided (occupancy of its own cell = min(255, sum of accepted
+//                    stamps)) and pushes its decision to the lower-ranked ones in reach with one shared-memory atomic each (stamp
+//                    added, count decremented); stops as soon as max_keypoints are accepted in the decided prefix; sub-pixel
+//                    refinement, border / warp validity, ordered compaction into cv::KeyPoint records
 //   k_describe48     one warp per keypoint: 60 smoothed samples at the one pattern scale, placed by the per-keypoint 2x2 warp
 //                    (camera-aware) or by the rotation table after the long-pair orientation (plain), 383 comparisons -> 12 words
+#include <type_traits>
+
 #include "okb_harris_core.h"
 #include "okb_internal.h"
 
@@ -24,8 +28,11 @@ namespace okb {
 
 struct HarrisState {
   int32_t* d_score = nullptr;         // [B][H][W]
+  uint8_t* d_cond = nullptr;          // [B][H][cpitch] maximum-candidate flags
+  int cpitch = 0;
   uint2* d_cand = nullptr;            // [B][kHarrisCandCap]
   int32_t* d_sorted_score = nullptr;  // [B][kHarrisCandCap]
+  uint32_t* d_sorted_xy = nullptr;    // [B][kHarrisCandCap]
   float* d_lut = nullptr;             // 31 x 31 stamp weights
   uint32_t* d_short48 = nullptr;      // 384 packed pairs (i | j << 8), the last one (0, 0)
   int basic_scale = 0;
@@ -36,69 +43,123 @@ struct HarrisState {
 void integral_run(CamWorkspace& ws, const uint8_t* d_images, int src_pitch, size_t in_stride, int W, int H, int B, cudaStream_t st);   // okb_detect.cu
 
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kHT_W = 64, kHT_H = 16;
-__global__ void __launch_bounds__(256) k_harris_score(const uint8_t* in0, int pitch, size_t frame_stride, int W, int H, int32_t* score)
+// Score + maximum-candidate pass. A warp owns a strip of 32 columns (26 of them produce output: the derivative, the horizontal
+// binomial sum and the neighbour test each cost one column on either side) and marches down a band of rows; everything between the
+// pixel load and the two stores lives in registers, horizontal neighbours come from warp shuffles, vertical ones from the previous
+// rows' registers. Per row step: pixel row r -> gradient row r-1 -> horizontal sums of the three products -> score row r-2
+// (stored) -> candidate flags of row r-3 (stored as bytes: at or above the threshold and no 8-neighbour strictly greater).
+constexpr int kHsCols = 26, kHsBand = 60, kHsWarps = 4;
+__global__ void __launch_bounds__(32 * kHsWarps) k_harris_score(const uint8_t* __restrict__ in0, int pitch, size_t frame_stride, int W, int H,
+                                                                 int threshold, int32_t* __restrict__ score, uint8_t* __restrict__ cond, int cpitch)
 {
-  __shared__ uint8_t img[kHT_H + 4][kHT_W + 8];
-  __shared__ char2 grad[kHT_H + 2][kHT_W + 2];
-  const int frame = blockIdx.z, x0 = blockIdx.x * kHT_W, y0 = blockIdx.y * kHT_H;
+  const int lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * kHsWarps + (threadIdx.x >> 5);
+  const int x = strip * kHsCols - 3 + lane;
+  if (strip * kHsCols >= W) return;
+  const int yb = blockIdx.y * kHsBand, ye = min(yb + kHsBand, H);
+  const int frame = blockIdx.z;
   const uint8_t* in = in0 + (size_t)frame * frame_stride;
-  for (int i = threadIdx.x; i < (kHT_H + 4) * (kHT_W + 4); i += 256) {
-    const int r = i / (kHT_W + 4), c = i % (kHT_W + 4);
-    const int y = y0 - 2 + r, x = x0 - 2 + c;
-    img[r][c] = (x >= 0 && x < W && y >= 0 && y < H) ? in[(size_t)y * pitch + x] : (uint8_t)0;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < (kHT_H + 2) * (kHT_W + 2); i += 256) {
-    const int r = i / (kHT_W + 2), c = i % (kHT_W + 2);
-    const int y = y0 - 1 + r, x = x0 - 1 + c;
-    int gx = 0, gy = 0;
-    if (x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2) harris_grad(img[r], img[r + 1], img[r + 2], c + 1, gx, gy);
-    grad[r][c] = make_char2((signed char)gx, (signed char)gy);
-  }
-  __syncthreads();
   int32_t* out = score + (size_t)frame * W * H;
-  for (int i = threadIdx.x; i < kHT_H * kHT_W; i += 256) {
-    const int oy = i / kHT_W, ox = i % kHT_W;
-    const int y = y0 + oy, x = x0 + ox;
-    if (x >= W || y >= H) continue;
-    int s = 0;
-    if (x >= 2 && x < W - 2 && y >= 2 && y < H - 2) {
-      int a = 0, b = 0, c = 0;
-#pragma unroll
-      for (int j = 0; j < 3; j++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const char2 g = grad[oy + j][ox + k];
-          const int w = (j == 1 ? 2 : 1) * (k == 1 ? 2 : 1);
-          const int u = g.x, v = g.y;
-          a += w * u * u; b += w * v * v; c += w * u * v;
-        }
-      s = harris_score(a, b, c);
-    }
-    out[(size_t)y * W + x] = s;
-  }
+  uint8_t* cnd = cond + (size_t)frame * cpitch * H;
+  const bool x_in = x >= 0 && x < W;
+  const bool x_grad = x >= 1 && x <= W - 2, x_score = x >= 2 && x < W - 2;
+  const bool x_store = lane >= 3 && lane < 3 + kHsCols && x < W;
+  int I0 = 0, I1 = 0;                       // pixel rows r-2, r-1
+  int hA0 = 0, hA1 = 0, hB0 = 0, hB1 = 0, hC0 = 0, hC1 = 0;   // horizontal sums of gradient rows r-3, r-2
+  int S1 = 0;                               // score row r-3
+  int M0 = 0, side1 = 0;                    // row maximum over (x-1, x, x+1) of score row r-4; max(x-1, x+1) of score row r-3
+  // rows yb-3 .. ye+2 are loaded; the first steps only fill the pipeline. kFull: every row condition of the step holds (rows inside the
+  // image with their margins, both stores inside the band), which is the case for all but the first six and the last one to three steps of
+  // a band. The candidate test needs no position check at all: scores are zero where they are not defined and
+  // the threshold is at least 1.
+  auto step = [&](const int r, auto full) {
+    constexpr bool kFull = decltype(full)::value;
+    const int I2 = (x_in && (kFull || (r >= 0 && r < H))) ? (int)in[(size_t)r * pitch + x] : 0;
+    // gradient row g = r - 1
+    const int g = r - 1;
+    const int v = 3 * (I0 + I2) + 10 * I1, dv = I2 - I0;
+    const int pk = (v << 16) | (dv & 0xffff);
+    const int pkL = __shfl_up_sync(0xffffffffu, pk, 1), pkR = __shfl_down_sync(0xffffffffu, pk, 1);
+    const int sx = (pkR >> 16) - (pkL >> 16);
+    const int sy = 3 * ((int)(short)(pkL & 0xffff) + (int)(short)(pkR & 0xffff)) + 10 * dv;
+    int gpk = 0;
+    if (x_grad && (kFull || (g >= 1 && g <= H - 2))) gpk = ((sx >> 5) & 0xff) | (((sy >> 5) & 0xff) << 8);
+    // horizontal binomial sums of the three products as int8 dot products: (gL, g, g, gR) . (gL, g, g, gR) = gL^2 + 2 g^2 + gR^2
+    const int gL = __shfl_up_sync(0xffffffffu, gpk, 1), gR = __shfl_down_sync(0xffffffffu, gpk, 1);
+    const int P = (int)__byte_perm(__byte_perm(gL, gpk, 0x0440), gR, 0x4210);
+    const int Q = (int)__byte_perm(__byte_perm(gL, gpk, 0x1551), gR, 0x5210);
+    const int hA2 = __dp4a(P, P, 0), hB2 = __dp4a(Q, Q, 0), hC2 = __dp4a(P, Q, 0);
+    // score row s = r - 2
+    const int srow = r - 2;
+    int S2 = 0;
+    if (x_score && (kFull || (srow >= 2 && srow < H - 2))) S2 = harris_score(hA0 + 2 * hA1 + hA2, hB0 + 2 * hB1 + hB2, hC0 + 2 * hC1 + hC2);
+    if (x_store && (kFull || (srow >= yb && srow < ye))) out[(size_t)srow * W + x] = S2;
+    const int S2L = __shfl_up_sync(0xffffffffu, S2, 1), S2R = __shfl_down_sync(0xffffffffu, S2, 1);
+    const int side2 = max(S2L, S2R), M2 = max(side2, S2);
+    // candidate flags of row m = r - 3
+    const int m = r - 3;
+    if (x_store && (kFull || (m >= yb && m < ye))) cnd[(size_t)m * cpitch + x] = (S1 >= threshold && max(max(M0, M2), side1) <= S1) ? 1 : 0;
+    I0 = I1; I1 = I2; hA0 = hA1; hA1 = hA2; hB0 = hB1; hB1 = hB2; hC0 = hC1; hC1 = hC2;
+    M0 = max(side1, S1); S1 = S2; side1 = side2;
+  };
+  using Yes = std::true_type; using No = std::false_type;
+  const int r_lo = max(yb + 3, 4), r_hi = min(ye + 1, H - 1);   // the steps in [r_lo, r_hi] need no row checks
+  for (int r = yb - 3; r < r_lo; r++) step(r, No());
+#pragma unroll 2
+  for (int r = r_lo; r <= r_hi; r++) step(r, Yes());
+  for (int r = max(r_hi + 1, r_lo); r <= ye + 2; r++) step(r, No());
 }
 
-__global__ void __launch_bounds__(128) k_harris_maxima(const int32_t* score, int W, int H, int threshold, uint2* cand, int32_t* count,
-                                                       int count_stride, int32_t* status)
+// maxima from the candidate flags: inside a run of consecutive candidates of a row every second one is kept (the row scan skips the
+// pixel right of an accepted maximum). One thread per 16 flags.
+__global__ void __launch_bounds__(256) k_harris_maxima(const int32_t* score, const uint8_t* cond, int cpitch, int W, int H, uint2* cand,
+                                                       int32_t* count, int count_stride, int32_t* status)
 {
-  const int frame = blockIdx.z;
-  const int x = blockIdx.x * 128 + threadIdx.x + 2, y = blockIdx.y + 2;
-  if (x >= W - 2 || y >= H - 2) return;
-  const int32_t* sc = score + (size_t)frame * W * H;
-  if (!harris_is_maximum(sc, W, x, y, threshold)) return;
-  const int slot = atomicAdd(&count[frame * count_stride], 1);
-  if (slot < kHarrisCandCap) cand[(size_t)frame * kHarrisCandCap + slot] = make_uint2((uint32_t)sc[(size_t)y * W + x], (uint32_t)x | ((uint32_t)y << 16));
-  else atomicOr(&status[frame], 1);
+  __shared__ int s_n, s_base;
+  __shared__ uint2 s_c[256 * 8];   // 16 flags hold at most 8 maxima (every second pixel of a run)
+  const int frame = blockIdx.y;
+  const int chunks = cpitch >> 4;
+  const int id = blockIdx.x * 256 + threadIdx.x;
+  const int y = id / chunks, x0 = (id - y * chunks) * 16;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  if (y < H) {
+    const uint8_t* row = cond + ((size_t)frame * H + y) * cpitch;
+    const uint4 f = *reinterpret_cast<const uint4*>(row + x0);
+    if ((f.x | f.y | f.z | f.w) != 0u) {
+      const uint32_t wds[4] = {f.x, f.y, f.z, f.w};
+      const int32_t* sc = score + (size_t)frame * W * H + (size_t)y * W;
+      for (int i = 0; i < 16; i++) {
+        if (!((wds[i >> 2] >> (8 * (i & 3))) & 1u)) continue;
+        const int x = x0 + i;
+        int run = 0;
+        while (x - 1 - run >= 2 && row[x - 1 - run]) run++;
+        if (run & 1) continue;
+        s_c[atomicAdd(&s_n, 1)] = make_uint2((uint32_t)sc[x], (uint32_t)x | ((uint32_t)y << 16));
+      }
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(&count[frame * count_stride], n);   // one global atomic per CTA: the per-frame counter is one address
+  __syncthreads();
+  const int base = s_base;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    if (base + i < kHarrisCandCap) cand[(size_t)frame * kHarrisCandCap + base + i] = s_c[i];
+    else atomicOr(&status[frame], 1);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kUniThreads = 1024;
 constexpr int kUniMaxCells = 64 * 64;
-constexpr int kUniWindow = 4096;   // ranks beyond the first undecided one that a round looks at
+// shared memory: [sort keys (8 B per candidate) | afterwards: cell-ordered entries + per-candidate words (4 + 4 B)] state, ready queue,
+// cell ends, stamp weights, the pattern at rotation 0, scalars
 constexpr size_t kUniSmem = (size_t)kHarrisCandCap * 8 + kHarrisCandCap + (size_t)kHarrisCandCap * 2 + (size_t)(kUniMaxCells + 1) * 4 +
                             (size_t)kUniLut * kUniLut * 4 + (size_t)kPoints * sizeof(PatternPoint) + 64 * 4;
+constexpr int kPendShift = 20;   // word = pending higher-ranked neighbours << 20 | sum of the accepted neighbours' stamps
+// at most 31 x 31 maxima share a 62 x 62 pixel window (no two are 8-neighbours): 961 < 2^12 pending, 961 x 255 < 2^20 of stamps
 
 // exclusive prefix sum of one value per thread over the block; returns the thread's offset, *total = the block's sum
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums /*32 ints of shared memory*/, int* total)
@@ -122,25 +183,54 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums /*32 i
   return base + incl - v;
 }
 
-__global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score_maps, int W, int H, const uint2* cand, const int32_t* cand_count,
-                                                            int count_stride, int32_t* sorted_score, const float* lut_g, const PatternPoint* pat0_g,
-                                                            int max_kp, int kp_cap, int border, const float* ray_map, const float* jac_map,
-                                                            float fu, float d0, float d1, float d2, okb_keypoint_t* kp_out, int32_t* count_out,
-                                                            int32_t* status)
+// The neighbours of a candidate at half-resolution position (hx, hy) whose stamps can reach it (and which it can reach) lie in the
+// 3 x 3 cells of 16 x 16 positions around its cell; the cells of one cell row are contiguous in the cell-ordered entry list.
+// entry = rank << 14 | hx << 4 | (hy & 15). f(rank, dx, dy) is called by the kUniGroup lanes that share the candidate (sub = lane
+// within the group) for every entry in the window. A full warp per candidate leaves the kernel latency-bound (a dependent chain of
+// shared-memory loads and one atomic per entry, ~40 entries per candidate): groups of 8 keep 128 candidates in flight per CTA.
+constexpr int kUniGroup = 8;                          // lanes that share one candidate
+constexpr int kUniGroups = kUniThreads / kUniGroup;   // candidates in flight per CTA
+template <typename F>
+__device__ __forceinline__ void for_each_neighbour(const uint32_t* entries, const int* cell_end, int cw, int ch, int hx, int hy, int sub, F f)
 {
-  extern __shared__ unsigned long long keys[];                                   // kHarrisCandCap
+  const int cx = hx >> 4, cy = hy >> 4;
+  const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, cw - 1);
+  for (int yy = max(cy - 1, 0); yy <= min(cy + 1, ch - 1); yy++) {
+    const int c0 = yy * cw + x_lo, c1 = yy * cw + x_hi;
+    const int t0 = c0 ? cell_end[c0 - 1] : 0, t1 = cell_end[c1];
+    for (int t = t0 + sub; t < t1; t += kUniGroup) {
+      const uint32_t e = entries[t];
+      const int dx = (int)((e >> 4) & 1023u) - hx, dy = (yy << 4) + (int)(e & 15u) - hy;
+      if (dx < -kUniWin || dx > kUniWin || dy < -kUniWin || dy > kUniWin) continue;
+      f((int)(e >> 14), dx, dy);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score_maps, int W, int H, const uint2* cand, const int32_t* cand_count,
+                                                            int count_stride, int32_t* sorted_score, uint32_t* sorted_xy, const float* lut_g,
+                                                            const PatternPoint* pat0_g, int max_kp, int kp_cap, int border, const float* ray_map,
+                                                            const float* jac_map, float fu, float d0, float d1, float d2, okb_keypoint_t* kp_out,
+                                                            int32_t* count_out, int32_t* status, long long* dbg)
+{
+#define OKB_STAMP(i) if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + (i)] = clock64()
+  OKB_STAMP(0);
+  extern __shared__ unsigned long long keys[];                                   // kHarrisCandCap sort keys ...
+  uint32_t* entries = reinterpret_cast<uint32_t*>(keys);                         // ... then: kHarrisCandCap cell-ordered entries
+  uint32_t* word = entries + kHarrisCandCap;                                     //           kHarrisCandCap pending / stamp-sum words
   uint8_t* state = reinterpret_cast<uint8_t*>(keys + kHarrisCandCap);            // 0 undecided, 1 accepted, 2 rejected, 3 kept + valid
-  uint16_t* list = reinterpret_cast<uint16_t*>(state + kHarrisCandCap);          // ranks grouped by cell
-  int* cell = reinterpret_cast<int*>(list + kHarrisCandCap);                     // kUniMaxCells + 1
+  uint16_t* queue = reinterpret_cast<uint16_t*>(state + kHarrisCandCap);         // ranks in the order they became decidable
+  int* cell = reinterpret_cast<int*>(queue + kHarrisCandCap);                    // kUniMaxCells + 1 cell ends
   float* lut = reinterpret_cast<float*>(cell + kUniMaxCells + 1);                // 31 x 31
   PatternPoint* pat0 = reinterpret_cast<PatternPoint*>(lut + kUniLut * kUniLut); // 60
   int* sh = reinterpret_cast<int*>(pat0 + kPoints);                              // 32 scan words + scalars
-  int* s_lo = sh + 32; int* s_acc = sh + 33; int* s_first = sh + 34;
+  int* s_tail = sh + 32; int* s_acc = sh + 33; int* s_first = sh + 34;
   const int frame = blockIdx.x, tid = threadIdx.x;
   const int n = min(cand_count[frame * count_stride], kHarrisCandCap);
   const uint2* cd = cand + (size_t)frame * kHarrisCandCap;
   const int32_t* smap = score_maps + (size_t)frame * W * H;
   int32_t* ss = sorted_score + (size_t)frame * kHarrisCandCap;
+  uint32_t* sxy = sorted_xy + (size_t)frame * kHarrisCandCap;
   okb_keypoint_t* kps = kp_out + (size_t)frame * kp_cap;
   for (int i = tid; i < kUniLut * kUniLut; i += kUniThreads) lut[i] = lut_g[i];
   for (int i = tid; i < kPoints * 3; i += kUniThreads) reinterpret_cast<float*>(pat0)[i] = reinterpret_cast<const float*>(pat0_g)[i];
@@ -164,17 +254,17 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
       }
       __syncthreads();
     }
+  OKB_STAMP(1);
   const float max_score = (float)(int)(~(uint32_t)(keys[0] >> 32));
-  // ---- cells of 16 x 16 half-resolution positions (a stamp reaches +-15): counting sort of the ranks by cell
+  // ---- the ranked list goes to global memory (the key array is reused below); cells of 16 x 16 half-resolution positions
   const int cw = ((W - 1) / 2) / 16 + 1, ch = ((H - 1) / 2) / 16 + 1, n_cells = cw * ch;
   for (int i = tid; i <= n_cells; i += kUniThreads) cell[i] = 0;
   __syncthreads();
   for (int i = tid; i < n; i += kUniThreads) {
     const unsigned long long k = keys[i];
-    const int sc = (int)(~(uint32_t)(k >> 32));
     const uint32_t xy = (uint32_t)k;
-    ss[i] = sc;
-    keys[i] = ((unsigned long long)__float_as_uint(uni_nsc(uni_ratio(sc, max_score))) << 32) | xy;
+    ss[i] = (int)(~(uint32_t)(k >> 32));
+    sxy[i] = xy;
     state[i] = 0;
     const int hx = (int)(xy & 0xffffu) >> 1, hy = (int)(xy >> 16) >> 1;
     atomicAdd(&cell[(hy >> 4) * cw + (hx >> 4)], 1);
@@ -192,74 +282,101 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
   }
   __syncthreads();
   for (int i = tid; i < n; i += kUniThreads) {   // cell[c] advances to the END of cell c: afterwards cell c = [c ? cell[c - 1] : 0, cell[c])
-    const uint32_t xy = (uint32_t)keys[i];
+    const uint32_t xy = sxy[i];
     const int hx = (int)(xy & 0xffffu) >> 1, hy = (int)(xy >> 16) >> 1;
-    list[atomicAdd(&cell[(hy >> 4) * cw + (hx >> 4)], 1)] = (uint16_t)i;
+    entries[atomicAdd(&cell[(hy >> 4) * cw + (hx >> 4)], 1)] = ((uint32_t)i << 14) | ((uint32_t)hx << 4) | (uint32_t)(hy & 15);
   }
-  if (tid == 0) { *s_lo = 0; *s_acc = 0; *s_first = n; }
+  if (tid == 0) { *s_tail = 0; *s_acc = 0; *s_first = n; }
   __syncthreads();
-  // ---- rounds
-  volatile uint8_t* vstate = state;
-  int lo = 0, acc = 0;
-  while (true) {
-    const int hi = min(n, lo + kUniWindow);
-    for (int i = lo + tid; i < hi; i += kUniThreads) {
-      if (vstate[i]) continue;
-      const unsigned long long ki = keys[i];
-      const uint32_t xy = (uint32_t)ki;
+  // ---- pending counts: higher-ranked candidates whose stamp reaches this one's cell (a warp per candidate, lanes over the entries)
+  const int group = tid / kUniGroup, sub = tid % kUniGroup;
+  {
+    uint32_t xy_next = group < n ? sxy[group] : 0u;
+    for (int base = 0; base < n; base += kUniGroups) {   // the trip count is uniform over the warp (shuffles inside)
+      const int i = base + group;
+      const uint32_t xy = xy_next;
+      if (i + kUniGroups < n) xy_next = sxy[i + kUniGroups];
+      int cnt = 0;
+      if (i < n) {
+        const int hx = (int)(xy & 0xffffu) >> 1, hy = (int)(xy >> 16) >> 1;
+        for_each_neighbour(entries, cell, cw, ch, hx, hy, sub, [&](int j, int dx, int dy) {
+          if (j < i && lut[(dy + kUniWin) * kUniLut + dx + kUniWin] != 0.0f) cnt++;
+        });
+      }
+#pragma unroll
+      for (int o = kUniGroup / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (sub == 0 && i < n) {
+        word[i] = (uint32_t)cnt << kPendShift;
+        if (cnt == 0) queue[atomicAdd(s_tail, 1)] = (uint16_t)i;
+      }
+    }
+  }
+  __syncthreads();
+  OKB_STAMP(2);
+  // ---- waves: the candidates that became decidable in the previous wave are decided (their stamp sum is complete) and PUSH their
+  //      decision to the lower-ranked candidates in reach: one atomic adds the stamp and takes one off the pending count
+  int head = 0, tail = *s_tail, lo = 0, acc = 0, waves = 0;
+  while (head < tail) {
+    waves++;
+    for (int q = head + group; q < tail; q += kUniGroups) {
+      const int j = queue[q];
+      const uint32_t xy = sxy[j];
       const int hx = (int)(xy & 0xffffu) >> 1, hy = (int)(xy >> 16) >> 1;
-      const int cx = hx >> 4, cy = hy >> 4;
-      int sum = 0; bool blocked = false;
-      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, ch - 1) && !blocked; yy++)
-        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, cw - 1) && !blocked; xx++) {
-          const int c = yy * cw + xx;
-          for (int t = c ? cell[c - 1] : 0, te = cell[c]; t < te; t++) {
-            const int j = list[t];
-            if (j >= i) continue;
-            const unsigned long long kj = keys[j];
-            const int dx = hx - ((int)((uint32_t)kj & 0xffffu) >> 1), dy = hy - ((int)((uint32_t)kj >> 16) >> 1);
-            if (dx < -kUniWin || dx > kUniWin || dy < -kUniWin || dy > kUniWin) continue;
-            const float l = lut[(dy + kUniWin) * kUniLut + dx + kUniWin];
-            if (l == 0.0f) continue;
-            const int sj = vstate[j];
-            if (sj == 0) { blocked = true; break; }
-            if (sj == 1) sum += uni_stamp(__uint_as_float((uint32_t)(kj >> 32)), l);
-          }
-        }
-      if (blocked) { atomicMin(s_first, i); continue; }
-      const float nsc = __uint_as_float((uint32_t)(ki >> 32));
-      // ratio = score / max is recomputed from the sorted score (nsc is its fourth root)
-      const float ratio = uni_ratio(ss[i], max_score);
-      (void)nsc;
-      vstate[i] = uni_rejected(ratio, sum) ? 2 : 1;
+      const float ratio = uni_ratio(ss[j], max_score);
+      const bool accepted = !uni_rejected(ratio, (int)(word[j] & ((1u << kPendShift) - 1u)));
+      const float nsc = uni_nsc(ratio);
+      if (sub == 0) state[j] = accepted ? 1 : 2;
+      for_each_neighbour(entries, cell, cw, ch, hx, hy, sub, [&](int i, int dx, int dy) {
+        if (i <= j) return;
+        const float l = lut[(-dy + kUniWin) * kUniLut - dx + kUniWin];   // the stamp of j at the cell of i: offset (i - j)
+        if (l == 0.0f) return;
+        const uint32_t delta = (accepted ? (uint32_t)uni_stamp(nsc, l) : 0u) - (1u << kPendShift);
+        const uint32_t old = atomicAdd(&word[i], delta);
+        if ((old >> kPendShift) == 1u) queue[atomicAdd(s_tail, 1)] = (uint16_t)i;
+      });
     }
     __syncthreads();
-    const int first = min(*s_first, hi);   // every rank below `first` is decided
-    int mine = 0;
-    for (int i = lo + tid; i < first; i += kUniThreads) mine += state[i] == 1;
-    if (mine) atomicAdd(s_acc, mine);
-    __syncthreads();
-    acc = *s_acc; lo = first;
-    __syncthreads();
-    if (tid == 0) *s_first = n;
-    __syncthreads();
-    if (lo >= n || (max_kp > 0 && acc >= max_kp)) break;
+    head = tail; tail = *s_tail;
+    if (max_kp > 0) {   // ranks below the first undecided one are final: stop once they hold max_kp accepted candidates
+      int mine = n;
+      for (int i = lo + tid; i < n; i += kUniThreads) if (state[i] == 0) { mine = i; break; }
+      if (mine < n) atomicMin(s_first, mine);
+      __syncthreads();
+      const int first = *s_first;
+      int c = 0;
+      for (int i = lo + tid; i < first; i += kUniThreads) c += state[i] == 1;
+      if (c) atomicAdd(s_acc, c);
+      __syncthreads();
+      acc = *s_acc; lo = first;
+      __syncthreads();
+      if (tid == 0) *s_first = n;
+      if (acc >= max_kp) break;
+    } else {
+      __syncthreads();
+    }
   }
-  // ---- ranks [0, lo) are decided. Keep the first max_kp accepted ones, refine, test the pattern against the image border, compact.
+  if (max_kp <= 0 || acc < max_kp) lo = n;   // every candidate was decided
+  __syncthreads();
+  OKB_STAMP(3);
+  if (dbg && tid == 0) { dbg[blockIdx.x * 16 + 5] = waves; dbg[blockIdx.x * 16 + 6] = n; dbg[blockIdx.x * 16 + 7] = lo; }
+  // ---- ranks [0, lo) are decided. The first max_kp accepted ones, in rank order, go into a compact list (one thread each from here
+  //      on): sub-pixel refinement, the pattern against the image border, ordered compaction into keypoint records.
   const int per = (lo + kUniThreads - 1) / kUniThreads;
   const int r0 = min(tid * per, lo), r1 = min(r0 + per, lo);
   int cnt = 0;
   for (int i = r0; i < r1; i++) cnt += state[i] == 1;
   int total_acc;
   int a = block_exclusive_scan(cnt, sh, &total_acc);
+  const int n_keep = max_kp > 0 ? min(total_acc, max_kp) : total_acc;
+  uint16_t* kept = queue;                            // the ready queue is dead
+  for (int i = r0; i < r1; i++) if (state[i] == 1) { if (a < n_keep) kept[a] = (uint16_t)i; a++; }
   const bool aware = ray_map != nullptr;
   const float d[3] = {d0, d1, d2};
-  int valid = 0;
-  for (int i = r0; i < r1; i++) {
-    if (state[i] != 1) continue;
-    const int idx = a++;
-    if (max_kp > 0 && idx >= max_kp) { state[i] = 2; continue; }
-    const uint32_t xy = (uint32_t)keys[i];
+  float2* pos = reinterpret_cast<float2*>(keys);     // the entry / word arrays are dead too
+  uint8_t* okf = state;                              // and so are the states once the list is made
+  __syncthreads();
+  for (int t = tid; t < n_keep; t += kUniThreads) {
+    const uint32_t xy = sxy[kept[t]];
     const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
     float dx, dy;
     harris_subpixel(smap, W, x, y, dx, dy);
@@ -279,28 +396,31 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
           ok = ok && brisk2_sample_inside(xf, yf, pat0[p].sigma, W, H);
         }
     }
-    if (ok) {
-      state[i] = 3; valid++;
-      keys[i] = ((unsigned long long)__float_as_uint(fy) << 32) | __float_as_uint(fx);
-    } else {
-      state[i] = 2;
-    }
+    pos[t] = make_float2(fx, fy);
+    okf[t] = ok ? 1 : 0;
   }
+  __syncthreads();
+  const int per2 = (n_keep + kUniThreads - 1) / kUniThreads;
+  const int t0 = min(tid * per2, n_keep), t1 = min(t0 + per2, n_keep);
+  int valid = 0;
+  for (int t = t0; t < t1; t++) valid += okf[t];
   int total;
   int f = block_exclusive_scan(valid, sh, &total);
-  for (int i = r0; i < r1; i++) {
-    if (state[i] != 3) continue;
+  for (int t = t0; t < t1; t++) {
+    if (!okf[t]) continue;
     const int idx = f++;
     if (idx >= kp_cap) continue;
     okb_keypoint_t k;
-    k.x = __uint_as_float((uint32_t)keys[i]); k.y = __uint_as_float((uint32_t)(keys[i] >> 32));
-    k.size = 12.0f; k.angle = -1.0f; k.response = (float)ss[i]; k.octave = 0; k.class_id = -1;
+    k.x = pos[t].x; k.y = pos[t].y;
+    k.size = 12.0f; k.angle = -1.0f; k.response = (float)ss[kept[t]]; k.octave = 0; k.class_id = -1;
     kps[idx] = k;
   }
   if (tid == 0) {
     if (total > kp_cap) atomicOr(&status[frame], 8);
     count_out[frame] = min(total, kp_cap);
   }
+  OKB_STAMP(4);
+#undef OKB_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -379,8 +499,12 @@ int harris_init_camera(okb_context* ctx, int cam)
   hs->basic_scale = brisk2_basic_scale_host();
   if (hs->basic_scale >= kScales) { set_error("BRISK2 basic scale %d", hs->basic_scale); return OKB_ERR_ARGUMENT; }
   OKB_CUDA(cudaMalloc(&hs->d_score, (size_t)c.width * c.height * 4 * B));
+  hs->cpitch = (c.width + 15) / 16 * 16;
+  OKB_CUDA(cudaMalloc(&hs->d_cond, (size_t)hs->cpitch * c.height * B));
+  OKB_CUDA(cudaMemset(hs->d_cond, 0, (size_t)hs->cpitch * c.height * B));
   OKB_CUDA(cudaMalloc(&hs->d_cand, (size_t)kHarrisCandCap * sizeof(uint2) * B));
   OKB_CUDA(cudaMalloc(&hs->d_sorted_score, (size_t)kHarrisCandCap * 4 * B));
+  OKB_CUDA(cudaMalloc(&hs->d_sorted_xy, (size_t)kHarrisCandCap * 4 * B));
   float lut[kUniLut * kUniLut];
   for (int j = 0; j < kUniLut; j++) for (int i = 0; i < kUniLut; i++) lut[j * kUniLut + i] = uni_lut_host(hs->radius, i - kUniWin, j - kUniWin);
   OKB_CUDA(cudaMalloc(&hs->d_lut, sizeof(lut)));
@@ -413,7 +537,7 @@ void harris_free_camera(okb_context* ctx, int cam)
   CamWorkspace& ws = ctx->cams[cam];
   HarrisState* hs = (HarrisState*)ws.harris;
   if (!hs) return;
-  cudaFree(hs->d_score); cudaFree(hs->d_cand); cudaFree(hs->d_sorted_score); cudaFree(hs->d_lut); cudaFree(hs->d_short48);
+  cudaFree(hs->d_score); cudaFree(hs->d_cond); cudaFree(hs->d_cand); cudaFree(hs->d_sorted_score); cudaFree(hs->d_sorted_xy); cudaFree(hs->d_lut); cudaFree(hs->d_short48);
   delete hs;
   ws.harris = nullptr;
 }
@@ -435,18 +559,22 @@ int harris_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   OKB_CUDA(cudaStreamWaitEvent(ws.stream2, ws.ev_fork, 0));
   integral_run(ws, d_images, src_pitch, in_stride, W, H, B, ws.stream2);
   OKB_CUDA(cudaEventRecord(ws.ev_join, ws.stream2));
-  k_harris_score<<<dim3((W + kHT_W - 1) / kHT_W, (H + kHT_H - 1) / kHT_H, B), 256, 0, st>>>(d_images, src_pitch, in_stride, W, H, hs->d_score);
-  k_harris_maxima<<<dim3((W - 4 + 127) / 128, H - 4, B), 128, 0, st>>>(hs->d_score, W, H, c.threshold, hs->d_cand, ws.d_cand_count, kMaxLayers,
-                                                                       ws.d_status);
+  {
+    const int strips = (W + kHsCols - 1) / kHsCols;
+    k_harris_score<<<dim3((strips + kHsWarps - 1) / kHsWarps, (H + kHsBand - 1) / kHsBand, B), 32 * kHsWarps, 0, st>>>(
+        d_images, src_pitch, in_stride, W, H, c.threshold, hs->d_score, hs->d_cond, hs->cpitch);
+    k_harris_maxima<<<dim3((hs->cpitch / 16 * H + 255) / 256, B), 256, 0, st>>>(hs->d_score, hs->d_cond, hs->cpitch, W, H, hs->d_cand,
+                                                                               ws.d_cand_count, kMaxLayers, ws.d_status);
+  }
   if (ctx->timers_on) { cudaEventRecord(ws.ev_mid, st); cudaEventRecord(ws.ev[1], st); }
   const bool aware = ws.maps_ready && ws.has_model;
   const float* rays = aware ? ws.d_ray_map : nullptr;
   const float* jac = aware ? ws.d_jac_map : nullptr;
   const float fu = aware ? (float)ws.model.fu : 1.0f;
   const PatternPoint* pat = ctx->d_pattern + (size_t)hs->basic_scale * kRot * kPoints;
-  k_uniformity<<<B, kUniThreads, kUniSmem, st>>>(hs->d_score, W, H, hs->d_cand, ws.d_cand_count, kMaxLayers, hs->d_sorted_score, hs->d_lut, pat,
+  k_uniformity<<<B, kUniThreads, kUniSmem, st>>>(hs->d_score, W, H, hs->d_cand, ws.d_cand_count, kMaxLayers, hs->d_sorted_score, hs->d_sorted_xy, hs->d_lut, pat,
                                                  c.max_keypoints, ws.kp_cap, hs->border, rays, jac, fu, ws.extraction_dir[0], ws.extraction_dir[1],
-                                                 ws.extraction_dir[2], ws.d_kp, ws.d_count, ws.d_status);
+                                                 ws.extraction_dir[2], ws.d_kp, ws.d_count, ws.d_status, ws.d_dbg);
   if (ctx->timers_on) cudaEventRecord(ws.ev[2], st);
   OKB_CUDA(cudaStreamWaitEvent(st, ws.ev_join, 0));
   k_describe48<<<dim3((ws.kp_cap + 3) / 4, B), 128, 0, st>>>(d_images, src_pitch, in_stride, W, H, ws.d_integral, ipitch, pat, hs->d_short48,

@@ -140,6 +140,7 @@ class Frontend:
             m.k[i] = distortion_coefficients[i] if i < len(distortion_coefficients) else 0.0
         self._models[cameraIndex] = m
         check(_l.lib().okb_set_camera_model(self._ctx, cameraIndex, C.byref(m)))
+        self._aware = set(getattr(self, "_aware", ())) - {cameraIndex}   # maps of the previous model are stale
 
     def computeBackProjections(self, frameOut, cameraIndex):
         """MultiFrame::computeBackProjections(im) (Frame.hpp:178-193): fills backProjections / backProjectionsValid."""
@@ -159,6 +160,7 @@ class Frontend:
         w, h = self._geom[cameraIndex]
         rays = np.zeros((h, w, 3), np.float32); jac = np.zeros((h, w, 6), np.float32)
         check(_l.lib().okb_camera_awareness_maps(self._ctx, cameraIndex, ptr(rays), ptr(jac)))
+        self._aware = set(getattr(self, "_aware", ())) | {cameraIndex}
         return rays, jac
 
     def computeOverlaps(self, models, intrinsics, widths, heights, C_rel, masks=False):
@@ -381,6 +383,9 @@ class Frontend:
         self._ctx = ctx
         for i, m in getattr(self, "_models", {}).items():   # the camera models survive a re-initialisation
             check(_l.lib().okb_set_camera_model(self._ctx, i, C.byref(m)))
+        for i in getattr(self, "_aware", ()):               # and so do the camera-awareness maps the D = 48 extractor reads
+            if i in self._models:
+                check(_l.lib().okb_camera_awareness_maps(self._ctx, i, None, None))
 
     def close(self):
         if getattr(self, "_ctx", None):
