@@ -942,6 +942,31 @@ def run_okvis48(args, rank, world, local_rank, steps, with_cpu):
                       "camera_aware": True, "step": "per stereo frame: Harris + uniformity detect, camera-aware gravity-aligned BRISK2-48 describe, "
                       "back-project, M1 match-to-map per camera", "l2_policy": f"ring of {ring} batches"},
            "parity": "bit-exact vs oracle/brisk_oracle.c section 6; PARITY UNPINNED vs smartroboticslab/brisk@1ef8b42a (source absent)"}
+    # ---- live use: one stereo frame per call (one host thread per camera, okb_detect_describe on a page-locked frame; D4 rides along)
+    fe.close()
+    fe = Frontend(2, W, H, device=local_rank, max_batch=1, descriptor_bytes=48)
+    fe.configure(threshold=cfg["radius"], absolute_threshold=cfg["abs_threshold"], octaves=0, max_keypoints=cfg["max_kp"])
+    for c in range(2):
+        fu, fv, cu, cv = intrinsics(cfg, c)
+        fe.setCameraModel(c, "radialtangential", (fu, fv), (cu, cv), DIST)
+        okl.check(L_.okb_camera_awareness_maps(fe.ctx, c, None, None))
+        okl.check(L_.okb_set_extraction_direction(fe.ctx, c, np.ascontiguousarray(T_WC[:3, :3]).ctypes.data))
+    n1 = np.zeros(2, np.int32)
+
+    def live_job(c, i):
+        okl.check(L_.okb_detect_describe(fe.ctx, c, h_img[c][i].data_ptr(), W, h_kp[c].data_ptr(), h_desc[c].data_ptr(), kp_cap, n1[c:].ctypes.data))
+
+    def live_frame(i):
+        t = threading.Thread(target=live_job, args=(1, i)); t.start(); live_job(0, i); t.join()
+    n_live = min(200, ring * B)
+    for i in range(10):
+        live_frame(i)
+    t0 = time.perf_counter()
+    for i in range(n_live):
+        live_frame(i)
+    live_s = time.perf_counter() - t0
+    rec["e2e"]["streaming"] = {"ms_per_stereo_frame": 1e3 * live_s / n_live, "value": n_live / live_s, "unit": "stereo frames/s",
+                               "api": "okb_detect_describe per camera and frame (two host threads), page-locked frames, detect + describe + back-project"}
     if with_cpu:
         import oracle
         o = oracle.HarrisBrisk2(cfg["radius"], cfg["abs_threshold"], cfg["max_kp"])

@@ -38,6 +38,7 @@ struct HarrisState {
   int basic_scale = 0;
   int border = 0;
   float radius = 0.f;
+  int cshift = 4;                     // log2 of the uniformity kernel's cell size in half-resolution positions
 };
 
 void integral_run(CamWorkspace& ws, const uint8_t* d_images, int src_pitch, size_t in_stride, int W, int H, int B, cudaStream_t st);   // okb_detect.cu
@@ -184,23 +185,23 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums /*32 i
 }
 
 // The neighbours of a candidate at half-resolution position (hx, hy) whose stamps can reach it (and which it can reach) lie in the
-// 3 x 3 cells of 16 x 16 positions around its cell; the cells of one cell row are contiguous in the cell-ordered entry list.
+// 3 x 3 cells of (1 << cshift)^2 positions around its cell (cshift = 3 when no stamp reaches further than 8 positions, else 4); the cells of one cell row are contiguous in the cell-ordered entry list.
 // entry = rank << 14 | hx << 4 | (hy & 15). f(rank, dx, dy) is called by the kUniGroup lanes that share the candidate (sub = lane
 // within the group) for every entry in the window. A full warp per candidate leaves the kernel latency-bound (a dependent chain of
 // shared-memory loads and one atomic per entry, ~40 entries per candidate): groups of 8 keep 128 candidates in flight per CTA.
 constexpr int kUniGroup = 8;                          // lanes that share one candidate
 constexpr int kUniGroups = kUniThreads / kUniGroup;   // candidates in flight per CTA
 template <typename F>
-__device__ __forceinline__ void for_each_neighbour(const uint32_t* entries, const int* cell_end, int cw, int ch, int hx, int hy, int sub, F f)
+__device__ __forceinline__ void for_each_neighbour(const uint32_t* entries, const int* cell_end, int cw, int ch, int cshift, int hx, int hy, int sub, F f)
 {
-  const int cx = hx >> 4, cy = hy >> 4;
+  const int cx = hx >> cshift, cy = hy >> cshift;
   const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, cw - 1);
   for (int yy = max(cy - 1, 0); yy <= min(cy + 1, ch - 1); yy++) {
     const int c0 = yy * cw + x_lo, c1 = yy * cw + x_hi;
     const int t0 = c0 ? cell_end[c0 - 1] : 0, t1 = cell_end[c1];
     for (int t = t0 + sub; t < t1; t += kUniGroup) {
       const uint32_t e = entries[t];
-      const int dx = (int)((e >> 4) & 1023u) - hx, dy = (yy << 4) + (int)(e & 15u) - hy;
+      const int dx = (int)((e >> 4) & 1023u) - hx, dy = (yy << cshift) + (int)(e & 15u & ((1u << cshift) - 1u)) - hy;
       if (dx < -kUniWin || dx > kUniWin || dy < -kUniWin || dy > kUniWin) continue;
       f((int)(e >> 14), dx, dy);
     }
@@ -208,7 +209,7 @@ __device__ __forceinline__ void for_each_neighbour(const uint32_t* entries, cons
 }
 
 __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score_maps, int W, int H, const uint2* cand, const int32_t* cand_count,
-                                                            int count_stride, int32_t* sorted_score, uint32_t* sorted_xy, const float* lut_g,
+                                                            int count_stride, int32_t* sorted_score, uint32_t* sorted_xy, const float* lut_g, int cshift,
                                                             const PatternPoint* pat0_g, int max_kp, int kp_cap, int border, const float* ray_map,
                                                             const float* jac_map, float fu, float d0, float d1, float d2, okb_keypoint_t* kp_out,
                                                             int32_t* count_out, int32_t* status, long long* dbg)
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
   OKB_STAMP(1);
   const float max_score = (float)(int)(~(uint32_t)(keys[0] >> 32));
   // ---- the ranked list goes to global memory (the key array is reused below); cells of 16 x 16 half-resolution positions
-  const int cw = ((W - 1) / 2) / 16 + 1, ch = ((H - 1) / 2) / 16 + 1, n_cells = cw * ch;
+  const int cw = (((W - 1) / 2) >> cshift) + 1, ch = (((H - 1) / 2) >> cshift) + 1, n_cells = cw * ch;
   for (int i = tid; i <= n_cells; i += kUniThreads) cell[i] = 0;
   __syncthreads();
   for (int i = tid; i < n; i += kUniThreads) {
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
     sxy[i] = xy;
     state[i] = 0;
     const int hx = (int)(xy & 0xffffu) >> 1, hy = (int)(xy >> 16) >> 1;
-    atomicAdd(&cell[(hy >> 4) * cw + (hx >> 4)], 1);
+    atomicAdd(&cell[(hy >> cshift) * cw + (hx >> cshift)], 1);
   }
   __syncthreads();
   {
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
   for (int i = tid; i < n; i += kUniThreads) {   // cell[c] advances to the END of cell c: afterwards cell c = [c ? cell[c - 1] : 0, cell[c])
     const uint32_t xy = sxy[i];
     const int hx = (int)(xy & 0xffffu) >> 1, hy = (int)(xy >> 16) >> 1;
-    entries[atomicAdd(&cell[(hy >> 4) * cw + (hx >> 4)], 1)] = ((uint32_t)i << 14) | ((uint32_t)hx << 4) | (uint32_t)(hy & 15);
+    entries[atomicAdd(&cell[(hy >> cshift) * cw + (hx >> cshift)], 1)] = ((uint32_t)i << 14) | ((uint32_t)hx << 4) | (uint32_t)(hy & 15);
   }
   if (tid == 0) { *s_tail = 0; *s_acc = 0; *s_first = n; }
   __syncthreads();
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
       int cnt = 0;
       if (i < n) {
         const int hx = (int)(xy & 0xffffu) >> 1, hy = (int)(xy >> 16) >> 1;
-        for_each_neighbour(entries, cell, cw, ch, hx, hy, sub, [&](int j, int dx, int dy) {
+        for_each_neighbour(entries, cell, cw, ch, cshift, hx, hy, sub, [&](int j, int dx, int dy) {
           if (j < i && lut[(dy + kUniWin) * kUniLut + dx + kUniWin] != 0.0f) cnt++;
         });
       }
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
       const bool accepted = !uni_rejected(ratio, (int)(word[j] & ((1u << kPendShift) - 1u)));
       const float nsc = uni_nsc(ratio);
       if (sub == 0) state[j] = accepted ? 1 : 2;
-      for_each_neighbour(entries, cell, cw, ch, hx, hy, sub, [&](int i, int dx, int dy) {
+      for_each_neighbour(entries, cell, cw, ch, cshift, hx, hy, sub, [&](int i, int dx, int dy) {
         if (i <= j) return;
         const float l = lut[(-dy + kUniWin) * kUniLut - dx + kUniWin];   // the stamp of j at the cell of i: offset (i - j)
         if (l == 0.0f) return;
@@ -507,6 +508,14 @@ int harris_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMalloc(&hs->d_sorted_xy, (size_t)kHarrisCandCap * 4 * B));
   float lut[kUniLut * kUniLut];
   for (int j = 0; j < kUniLut; j++) for (int i = 0; i < kUniLut; i++) lut[j * kUniLut + i] = uni_lut_host(hs->radius, i - kUniWin, j - kUniWin);
+  {
+    // cells of 8 x 8 positions when every stamp weight beyond 8 positions is zero (small radii: 4 x fewer entries per 3 x 3 block) and
+    // the image has no more than kUniMaxCells of them
+    int reach = 0;
+    for (int i = 0; i <= kUniWin; i++) if (lut[kUniWin * kUniLut + kUniWin + i] != 0.0f) reach = i;
+    const long long cells8 = (long long)((((c.width - 1) / 2) >> 3) + 1) * ((((c.height - 1) / 2) >> 3) + 1);
+    hs->cshift = (reach <= 8 && cells8 <= kUniMaxCells) ? 3 : 4;
+  }
   OKB_CUDA(cudaMalloc(&hs->d_lut, sizeof(lut)));
   OKB_CUDA(cudaMemcpy(hs->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
   // short pairs below 5.1 x patternScale, in the (i, j < i) enumeration order of the pattern generator
@@ -572,7 +581,7 @@ int harris_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   const float* jac = aware ? ws.d_jac_map : nullptr;
   const float fu = aware ? (float)ws.model.fu : 1.0f;
   const PatternPoint* pat = ctx->d_pattern + (size_t)hs->basic_scale * kRot * kPoints;
-  k_uniformity<<<B, kUniThreads, kUniSmem, st>>>(hs->d_score, W, H, hs->d_cand, ws.d_cand_count, kMaxLayers, hs->d_sorted_score, hs->d_sorted_xy, hs->d_lut, pat,
+  k_uniformity<<<B, kUniThreads, kUniSmem, st>>>(hs->d_score, W, H, hs->d_cand, ws.d_cand_count, kMaxLayers, hs->d_sorted_score, hs->d_sorted_xy, hs->d_lut, hs->cshift, pat,
                                                  c.max_keypoints, ws.kp_cap, hs->border, rays, jac, fu, ws.extraction_dir[0], ws.extraction_dir[1],
                                                  ws.extraction_dir[2], ws.d_kp, ws.d_count, ws.d_status, ws.d_dbg);
   if (ctx->timers_on) cudaEventRecord(ws.ev[2], st);
