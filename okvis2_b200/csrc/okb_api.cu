@@ -323,14 +323,13 @@ int okb_export_features(okb_context_t* ctx, int cam, int n_frames, void* d_block
   if (rc) return rc;
   CamWorkspace& ws = ctx->cams[cam];
   if (!d_block || n_frames < 1 || n_frames > ws.cfg.max_batch) { set_error("okb_export_features: bad arguments"); return OKB_ERR_ARGUMENT; }
-  if (ws.cfg.descriptor_bytes != 64) { set_error("okb_export_features: the feature block holds 64-byte rows (camera %d has %d)", cam, ws.cfg.descriptor_bytes); return OKB_ERR_UNSUPPORTED; }
   OKB_CUDA(cudaSetDevice(ctx->device));
   uint8_t* p = (uint8_t*)d_block;
   const size_t counts = ((size_t)n_frames * 4 + 255) & ~(size_t)255;
   const size_t kp_bytes = (size_t)n_frames * ws.kp_cap * sizeof(okb_keypoint_t);
   OKB_CUDA(cudaMemcpyAsync(p, ws.d_count, (size_t)n_frames * 4, cudaMemcpyDeviceToDevice, ws.stream));
   OKB_CUDA(cudaMemcpyAsync(p + counts, ws.d_kp, kp_bytes, cudaMemcpyDeviceToDevice, ws.stream));
-  OKB_CUDA(cudaMemcpyAsync(p + counts + kp_bytes, ws.d_desc, (size_t)n_frames * ws.kp_cap * 64, cudaMemcpyDeviceToDevice, ws.stream));
+  OKB_CUDA(cudaMemcpyAsync(p + counts + kp_bytes, desc_slots(ws), (size_t)n_frames * ws.kp_cap * 64, cudaMemcpyDeviceToDevice, ws.stream));
   return OKB_OK;
 }
 

@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
 __global__ void __launch_bounds__(128) k_describe48(const uint8_t* in0, int in_pitch, size_t in_frame_stride, int W, int H, const int32_t* integral,
                                                     int ipitch, const PatternPoint* pattern /*[rot][point] of the one scale*/, const uint32_t* short48,
                                                     const int4* long_pairs, const float* ray_map, const float* jac_map, float fu, float d0, float d1,
-                                                    float d2, okb_keypoint_t* kp, const int32_t* count, int kp_cap, uint8_t* desc)
+                                                    float d2, okb_keypoint_t* kp, const int32_t* count, int kp_cap, uint8_t* desc, uint8_t* desc64)
 {
   __shared__ int values[4][64];
   const int frame = blockIdx.y;
@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(128) k_describe48(const uint8_t* in0, int in_p
     if (lane == w) mine = word;
   }
   if (lane < 12) reinterpret_cast<uint32_t*>(desc + ((size_t)frame * kp_cap + k) * 48)[lane] = mine;
+  if (lane < 16) reinterpret_cast<uint32_t*>(desc64 + ((size_t)frame * kp_cap + k) * 64)[lane] = lane < 12 ? mine : 0u;   // 64-byte slot, zero tail
   if (lane == 0) kpp->angle = angle;
 }
 
@@ -537,6 +538,8 @@ int harris_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMalloc(&hs->d_short48, 384 * 4));
   OKB_CUDA(cudaMemcpy(hs->d_short48, sp.data(), 384 * 4, cudaMemcpyHostToDevice));
   hs->border = (int)ctx->h_size_list[hs->basic_scale];
+  OKB_CUDA(cudaMalloc(&ws.d_desc64, (size_t)ws.kp_cap * 64 * B));
+  OKB_CUDA(cudaMemset(ws.d_desc64, 0, (size_t)ws.kp_cap * 64 * B));
   OKB_CUDA(cudaFuncSetAttribute(k_uniformity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUniSmem));
   return OKB_OK;
 }
@@ -549,6 +552,7 @@ void harris_free_camera(okb_context* ctx, int cam)
   cudaFree(hs->d_score); cudaFree(hs->d_cond); cudaFree(hs->d_cand); cudaFree(hs->d_sorted_score); cudaFree(hs->d_sorted_xy); cudaFree(hs->d_lut); cudaFree(hs->d_short48);
   delete hs;
   ws.harris = nullptr;
+  cudaFree(ws.d_desc64); ws.d_desc64 = nullptr;
 }
 
 int harris_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch, cudaEvent_t input_ready)
@@ -588,7 +592,7 @@ int harris_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   OKB_CUDA(cudaStreamWaitEvent(st, ws.ev_join, 0));
   k_describe48<<<dim3((ws.kp_cap + 3) / 4, B), 128, 0, st>>>(d_images, src_pitch, in_stride, W, H, ws.d_integral, ipitch, pat, hs->d_short48,
                                                              ctx->d_long_pairs, rays, jac, fu, ws.extraction_dir[0], ws.extraction_dir[1],
-                                                             ws.extraction_dir[2], ws.d_kp, ws.d_count, ws.kp_cap, ws.d_desc);
+                                                             ws.extraction_dir[2], ws.d_kp, ws.d_count, ws.kp_cap, ws.d_desc, ws.d_desc64);
   ctx->launches += 6;
   { int rc = camera_backproject_batch(ctx, cam, B); if (rc) return rc; }
   if (ctx->timers_on) { cudaEventRecord(ws.ev[3], st); ws.pending_timing = 1; }

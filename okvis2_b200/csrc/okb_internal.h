@@ -75,6 +75,7 @@ struct CamWorkspace {
   okb_camera_config_t cfg;
   uint8_t* m2_d = nullptr; size_t m2_cap = 0;   // scratch of okb_match_map_uninit_device (poses, world rays, use mask)
   void* harris = nullptr;                     // okb::HarrisState (okb_harris.cu): workspace of the D = 48 mode
+  uint8_t* d_desc64 = nullptr;                // D = 48 only: the same rows in 64-byte slots with a zero tail (desc_slots)
   float extraction_dir[3] = {0.f, 0.f, -1.f};   // D1: gravity in the camera frame (okb_set_extraction_direction)
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // side stream (integral image)
@@ -150,6 +151,13 @@ struct MatchWorkspace {
   std::mutex* mtx = nullptr;
 };
 
+}  // namespace okb
+
+namespace okb {
+// The device-resident matcher forms (tensor-core Hamming scans of M3 / M4, the feature block of the camera-sharded exchange) read
+// descriptor rows in 64-byte slots. A 48-byte row in such a slot with a zero tail has the same Hamming distances (the tails cancel),
+// so a D = 48 camera keeps a second copy of its rows in that layout and those forms work on it unchanged.
+inline const uint8_t* desc_slots(const CamWorkspace& ws) { return ws.cfg.descriptor_bytes == 48 ? ws.d_desc64 : ws.d_desc; }
 }  // namespace okb
 
 struct okb_context {

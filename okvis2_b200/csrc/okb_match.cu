@@ -1896,13 +1896,12 @@ int okb_match_stereo_device(okb_context_t* ctx, int cam0, int cam1, int n_frames
   CamWorkspace& w0 = ctx->cams[cam0]; CamWorkspace& w1 = ctx->cams[cam1];
   OKB_CHECK_ARGS(w0.has_model && w1.has_model && n_frames >= 1 && n_frames <= w0.cfg.max_batch && n_frames <= w1.cfg.max_batch,
                  "okb_match_stereo_device (camera models set? okb_set_camera_model)");
-  OKB_REQUIRE_D64(w0, "okb_match_stereo_device"); OKB_REQUIRE_D64(w1, "okb_match_stereo_device");
   OKB_CUDA(cudaSetDevice(ctx->device));
   // runs on camera 0's stream once camera 1's features are complete
   OKB_CUDA(cudaEventRecord(w1.ev_done, w1.stream));
   OKB_CUDA(cudaStreamWaitEvent(w0.stream, w1.ev_done, 0));
-  int rc = okb_match_stereo_device_ptr(ctx, n_frames, w0.kp_cap, w0.d_kp, w0.d_desc, w0.d_count, &w0.model, C_WC0, r_WC0, w1.kp_cap,
-                                       w1.d_kp, w1.d_desc, w1.d_count, &w1.model, C_WC1, r_WC1, match_threshold, (void*)w0.stream,
+  int rc = okb_match_stereo_device_ptr(ctx, n_frames, w0.kp_cap, w0.d_kp, desc_slots(w0), w0.d_count, &w0.model, C_WC0, r_WC0, w1.kp_cap,
+                                       w1.d_kp, desc_slots(w1), w1.d_count, &w1.model, C_WC1, r_WC1, match_threshold, (void*)w0.stream,
                                        d_out_k1, d_out_dist, d_out_hp_W, d_out_initialisable);
   if (rc) return rc;
   // camera 1 must not overwrite its features before the matcher has read them
@@ -2100,9 +2099,8 @@ int okb_match_motion_stereo_device(okb_context_t* ctx, int cam, int n_frames, co
   OKB_CHECK_ARGS(ctx && cam >= 0 && cam < ctx->n_cams, "okb_match_motion_stereo_device");
   CamWorkspace& ws = ctx->cams[cam];
   OKB_CHECK_ARGS(ws.has_model && n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_motion_stereo_device (camera model set? okb_set_camera_model)");
-  OKB_REQUIRE_D64(ws, "okb_match_motion_stereo_device");
   // per-camera scratch: the sequences of different cameras run concurrently on their own streams
-  return okb::motion_sequence(ctx, ws.motion, n_frames, ws.kp_cap, ws.d_kp, ws.d_desc, ws.d_count, &ws.model, ws.cfg.width, ws.cfg.height, T_WC1, T_CW1,
+  return okb::motion_sequence(ctx, ws.motion, n_frames, ws.kp_cap, ws.d_kp, desc_slots(ws), ws.d_count, &ws.model, ws.cfg.width, ws.cfg.height, T_WC1, T_CW1,
                               n_older, older, cap0, match_threshold, ws.stream, d_matched1, d_out_k1, d_out_dist, d_out_hp_W, d_out_flags, ws.d_rays, ws.d_rays_valid, nullptr);
 }
 
@@ -2126,7 +2124,6 @@ int okb_match_motion_stereo_batch(okb_context_t* ctx, int cam, int n_frames, con
                  n_older >= 1 && cap0 > 0, "okb_match_motion_stereo_batch");
   CamWorkspace& ws = ctx->cams[cam];
   OKB_CHECK_ARGS(n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_motion_stereo_batch");
-  OKB_REQUIRE_D64(ws, "okb_match_motion_stereo_batch");
   OKB_CUDA(cudaSetDevice(ctx->device));
   // device side: mask [frames][kp_cap], dense results, compact lists (own scratch: the camera's m_d staging holds the M1 / M4 results)
   const size_t nq = (size_t)n_frames * n_older * cap0, nm = (size_t)n_frames * n_older * cap_m, n1 = (size_t)n_frames * ws.kp_cap;
@@ -2283,7 +2280,6 @@ int okb_match_stereo_batch(okb_context_t* ctx, int cam0, int cam1, int n_frames,
   OKB_CHECK_ARGS(ctx && cam0 >= 0 && cam0 < ctx->n_cams && cap > 0 && out_k1 && out_dist && out_hp_W && out_initialisable, "okb_match_stereo_batch");
   CamWorkspace& ws = ctx->cams[cam0];
   OKB_CHECK_ARGS(n_frames >= 1 && n_frames <= ws.cfg.max_batch, "okb_match_stereo_batch");
-  OKB_REQUIRE_D64(ws, "okb_match_stereo_batch");
   OKB_CUDA(cudaSetDevice(ctx->device));
   CamStage S{ws, ws.stream};
   const size_t n = (size_t)n_frames * ws.kp_cap;

@@ -134,3 +134,119 @@ def test_rejections():
     with pytest.raises(OkbError) as e:
         Frontend(1, 752, 480, descriptor_bytes=32)
     assert e.value.status == _l.OKB_ERR_ARGUMENT
+
+
+def test_device_resident_matchers_on_48_byte_rows():
+    """A D = 48 camera keeps its rows a second time in 64-byte slots with a zero tail, so the device-resident forms built for 64-byte rows
+    (the tensor-core Hamming scans of M4 and of the M3 sequence, the feature block of the camera-sharded exchange) run on them unchanged:
+    M4 (okb_match_stereo_device), the export block and the M3 sequence (okb_match_motion_stereo_device) against the oracle on the 48-byte rows."""
+    import torch
+    from okvis2_b200 import sharding as sh
+    from okvis2_b200.synth import pose12, rot, synth_stereo
+    from test_gpu_camera import EUROC as EU, T_CW, oracle_bp, world_rays
+    B, W, H = 3, 752, 480
+    fe = make(W, H, 10.0, 30, 800, max_batch=B, n_cams=2)
+    L_ = _l.lib()
+    for c in range(2):
+        fe.setCameraModel(c, **EU[c])
+        fe.cameraAwarenessMaps(c)
+    T_WC = np.eye(4); T_WC[:3, :3] = np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0.]])
+    for c in range(2):
+        _l.check(L_.okb_set_extraction_direction(fe.ctx, c, np.ascontiguousarray(T_WC[:3, :3]).ctypes.data))
+    imgs = [np.stack([synth_stereo(700 + t, W, H)[c] for t in range(B)]) for c in range(2)]
+    d_imgs = [torch.from_numpy(a).cuda() for a in imgs]
+    for c in range(2):
+        _l.check(L_.okb_detect_describe_batch_device(fe.ctx, c, B, d_imgs[c].data_ptr()))
+    cap = C.c_int(0); L_.okb_device_features(fe.ctx, 0, None, None, None, C.byref(cap)); cap = cap.value
+    feats = [[None] * B for _ in range(2)]
+    for c in range(2):
+        for b in range(B):
+            kp = np.zeros(cap, _l.KP_DTYPE); d = np.zeros((cap, 48), np.uint8); n = C.c_int(0)
+            _l.check(L_.okb_fetch_features(fe.ctx, c, b, kp.ctypes.data, d.ctypes.data, cap, C.byref(n)))
+            feats[c][b] = (kp[:n.value].copy(), d[:n.value].copy())
+    assert min(len(f[0]) for fc in feats for f in fc) > 300
+    # ---- M4 on the tensor-core scan
+    C0 = np.eye(3); r0 = np.zeros(3); a = 0.01
+    C1 = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]); r1 = np.array([0.11, 0.001, -0.002])
+    k1 = torch.zeros((B, cap), dtype=torch.int32, device="cuda"); dist = torch.zeros((B, cap), dtype=torch.int32, device="cuda")
+    hp = torch.zeros((B, cap, 4), dtype=torch.float64, device="cuda"); init = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
+    _l.check(L_.okb_match_stereo_device(fe.ctx, 0, 1, B, C0.ctypes.data, r0.ctypes.data, np.ascontiguousarray(C1).ctypes.data, r1.ctypes.data, 60,
+                                        k1.data_ptr(), dist.data_ptr(), hp.data_ptr(), init.data_ptr()))
+    _l.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    k1, dist, hp, init = k1.cpu().numpy(), dist.cpu().numpy().view(np.uint32), hp.cpu().numpy(), init.cpu().numpy()
+    total = 0
+    for b in range(B):
+        (kp0, d0), (kp1, d1) = feats[0][b], feats[1][b]
+        rays0, v0 = oracle_bp(EU[0], kp0); rays1, v1 = oracle_bp(EU[1], kp1)
+        f0 = 0.5 * sum(EU[0]["focal_length"]); f1 = 0.5 * sum(EU[1]["focal_length"])
+        ref = oracle.match_stereo(d0, v0, world_rays(C0, rays0), kp0["size"].astype(np.float64) / f0, d1, v1, world_rays(C1, rays1),
+                                  kp1["size"].astype(np.float64) / f1, r0, r1, T_CW(C0, r0), T_CW(C1, r1), 60)
+        n0 = len(kp0)
+        assert np.array_equal(k1[b, :n0], ref[0]) and np.array_equal(dist[b, :n0], ref[1])
+        assert np.array_equal(hp[b, :n0].view(np.uint64), ref[2].view(np.uint64)) and np.array_equal(init[b, :n0], ref[3])
+        total += int((ref[0] >= 0).sum())
+    assert total > 5
+    # ---- the export block: 64-byte slots, the first 48 bytes are the row, the tail is zero
+    blk = torch.zeros(L_.okb_feature_block_bytes(B, cap), dtype=torch.uint8, device="cuda")
+    _l.check(L_.okb_export_features(fe.ctx, 1, B, blk.data_ptr()))
+    _l.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    counts, kps, descs = sh.unpack_block(blk.cpu().numpy(), B, cap, _l.KP_DTYPE)
+    for b in range(B):
+        kp1, d1 = feats[1][b]
+        assert counts[b] == len(kp1) and kps[b].tobytes() == kp1.tobytes()
+        assert np.array_equal(descs[b][:, :48], d1) and not descs[b][:, 48:].any()
+    # ---- the M3 sequence of camera 0 against three older views made from frame 0's own features (device blocks in 64-byte slots)
+    kp0, d0 = feats[0][0]
+    rays0, v0 = oracle_bp(EU[0], kp0)
+    rng = np.random.default_rng(5)
+    Tw1, Tc1 = pose12(np.eye(3), np.zeros(3))
+    e = rays0 / np.linalg.norm(rays0, axis=1, keepdims=True)
+    P = e * np.exp(rng.uniform(np.log(1.5), np.log(25.0), len(kp0)))[:, None]
+    views = []
+    for v in range(3):
+        Cv = rot((0, 1, 0), 0.012 * (v + 1)); rv = np.array([-0.06 * (v + 1), 0.01 * v, -0.02 * (v + 1)])
+        pc = (P - rv) @ Cv
+        idx = np.nonzero((v0 != 0) & (pc[:, 2] > 0.3) & (rng.random(len(kp0)) < 0.5))[0]
+        bits = np.unpackbits(d0[idx], axis=1)
+        d = np.packbits(bits ^ (rng.random(bits.shape) < 0.04).astype(np.uint8), axis=1)
+        d[:, 47] &= 0x7f                                            # bit 383 does not exist
+        ry = np.stack([pc[idx, 0] / pc[idx, 2], pc[idx, 1] / pc[idx, 2], np.ones(len(idx))], 1)
+        d = np.concatenate([d, rng.integers(0, 256, (200, 48), dtype=np.uint8)])
+        ry = np.concatenate([ry, np.stack([rng.uniform(-0.7, 0.7, 200), rng.uniform(-0.45, 0.45, 200), np.ones(200)], 1)])
+        Tw, Tc = pose12(Cv, rv)
+        views.append(dict(desc=np.ascontiguousarray(d), rays=np.ascontiguousarray(ry), valid=(rng.random(len(d)) > 0.02).astype(np.uint8),
+                          size=(rng.choice([12.0, 18.0], len(d)) * rng.uniform(0.9, 1.1, len(d))).astype(np.float32),
+                          use=(rng.random(len(d)) > 0.2).astype(np.uint8), T_WC=Tw, T_CW=Tc))
+    cap0 = (max(len(v["desc"]) for v in views) + 63) // 64 * 64
+    tab = (_l.OlderView * (B * 3))(); keep = []
+    for b in range(B):
+        for vi, v in enumerate(views):
+            slots = np.zeros((len(v["desc"]), 64), np.uint8); slots[:, :48] = v["desc"]
+            t = dict(desc=torch.from_numpy(slots).cuda(), **{k: torch.from_numpy(np.ascontiguousarray(v[k])).cuda() for k in ("rays", "valid", "size", "use")})
+            keep.append(t)
+            en = tab[b * 3 + vi]
+            en.d_desc, en.d_rays, en.d_valid, en.d_size, en.d_use = (t[k].data_ptr() for k in ("desc", "rays", "valid", "size", "use"))
+            en.n = len(v["desc"]); en.T_WC[:] = list(v["T_WC"]); en.T_CW[:] = list(v["T_CW"])
+    TwB = np.ascontiguousarray(np.broadcast_to(Tw1, (B, 12))); TcB = np.ascontiguousarray(np.broadcast_to(Tc1, (B, 12)))
+    mask = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
+    mk1 = torch.zeros((B, 3, cap0), dtype=torch.int32, device="cuda"); md = torch.zeros((B, 3, cap0), dtype=torch.int32, device="cuda")
+    mhp = torch.zeros((B, 3, cap0, 4), dtype=torch.float64, device="cuda"); mfl = torch.zeros((B, 3, cap0), dtype=torch.uint8, device="cuda")
+    _l.check(L_.okb_match_motion_stereo_device(fe.ctx, 0, B, TwB.ctypes.data, TcB.ctypes.data, 3, tab, cap0, 60, mask.data_ptr(), mk1.data_ptr(),
+                                               md.data_ptr(), mhp.data_ptr(), mfl.data_ptr()))
+    _l.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    mk1, md, mhp, mfl = mk1.cpu().numpy(), md.cpu().numpy().view(np.uint32), mhp.cpu().numpy(), mfl.cpu().numpy()
+    m = EU[0]
+    intr = np.array(list(m["focal_length"]) + list(m["principal_point"]) + list(m["distortion_coefficients"]))
+    inserted = 0
+    for b in range(B):
+        kpb, db = feats[0][b]
+        raysb, vb = oracle_bp(EU[0], kpb)
+        ref, _ = oracle.match_motion_stereo_sequence([dict(v) for v in views], db, raysb, vb, np.stack([kpb["x"], kpb["y"]], 1), Tw1, Tc1, 1, intr, W, H, 60,
+                                                     np.zeros(len(kpb), np.uint8))
+        for v, (rk1, rdist, rhp, rfl) in enumerate(ref):
+            n = len(rk1)
+            assert np.array_equal(mk1[b, v, :n], rk1) and np.array_equal(md[b, v, :n], rdist), (b, v)
+            assert np.array_equal(mhp[b, v, :n].view(np.uint64), rhp.view(np.uint64)) and np.array_equal(mfl[b, v, :n], rfl), (b, v)
+            inserted += int(((rfl & 4) != 0).sum())
+    assert inserted > 50
+    fe.close()
