@@ -117,7 +117,7 @@ def make_older_views(cfg, c, kp, desc, rays, valid, seed):
         ry = np.stack([pc[idx, 0] / pc[idx, 2], pc[idx, 1] / pc[idx, 2], np.ones(len(idx))], 1)
         ry[:, :2] += rng.normal(0, 3e-4, (len(idx), 2))
         n_out = max(cfg["kpts"] - len(idx), 0)
-        d = np.concatenate([d, random_descriptors(rng, n_out, 64)])
+        d = np.concatenate([d, random_descriptors(rng, n_out, desc.shape[1])])
         ry = np.concatenate([ry, np.stack([rng.uniform(-0.7, 0.7, n_out), rng.uniform(-0.45, 0.45, n_out), np.ones(n_out)], 1)])
         perm = rng.permutation(len(d))
         Tw, Tc = pose12(Cv, rv)
@@ -553,6 +553,15 @@ class Replica:
                  "m1_matches_per_frame": float(sum((o["m1"][c]["lm"] >= 0).sum().item() for c in range(2)) / (2 * self.B)),
                  "m3_inserted_per_frame": float(sum(((o["m1"][c]["fl3"] & 4) != 0).sum().item() for c in range(2)) / (2 * self.B)) if self.n_older else 0.0,
                  "m4_matches_per_stereo_frame": float((o["st"]["k1"] >= 0).sum().item() / self.B)}
+        # the landmark pool and the older views are built from frame 0 of the ring (the other frames are other scenes / shifted copies whose
+        # geometry the pool does not fit, so they load the Hamming scans but rarely pass a gate): one more untimed step on the batch that
+        # holds frame 0 shows what the gate / triangulate / insert stages do on a frame the map fits
+        self.device_step(0, 0)
+        okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+        stats["frame0"] = {"m1_matches": int((o["m1"][0]["lm"][0] >= 0).sum().item()),
+                           "m3_matching": int(((o["m1"][0]["fl3"][0] & 1) != 0).sum().item()) if self.n_older else 0,
+                           "m3_inserted": int(((o["m1"][0]["fl3"][0] & 4) != 0).sum().item()) if self.n_older else 0,
+                           "m4_matches": int((o["st"]["k1"][0] >= 0).sum().item())}
         return dev_ms, launches, stats
 
     def measure_roofline(self, warm, steps):
@@ -840,13 +849,14 @@ def run_replica(name, cfg, args, rank, world, local_rank, lanes, steps, full):
 # BASELINE configs[1] in the detector / extractor pair OKVIS2 itself constructs: Harris + uniformity enforcement,
 # 48-byte camera-aware, gravity-aligned BRISK2, octaves = 0 (config/euroc.yaml:63-67). The uniformity radius / threshold are chosen so
 # that the detector cap binds on the synthetic frames and >= 700 keypoints (euroc.yaml:67) survive the extractor's border removal.
-OKVIS48 = dict(W=752, H=480, kpts=700, max_kp=864, radius=8.0, abs_threshold=20, n_lm=5000, batch=32, ring=6, f=458.0)
+OKVIS48 = dict(W=752, H=480, kpts=700, max_kp=864, radius=8.0, abs_threshold=20, n_lm=5000, batch=32, ring=6, f=458.0, n_older=5)
 
 
 def run_okvis48(args, rank, world, local_rank, steps, with_cpu):
     """value: device-resident step = per camera okb_detect_describe_batch_device (Harris, uniformity, BRISK2-48 with the camera-awareness
-    maps and the extraction direction, D4) + okb_match_map3d_device on the 48-byte rows; e2e: okb_detect_describe_batch from host buffers
-    (+ the same M1 on the device); cpu_baseline: the oracle's detect + describe on one core."""
+    maps and the extraction direction, D4), okb_match_map3d_device on the 48-byte rows, the M3 sequence against 5 older keyframes, then M4
+    (the headline step in the D = 48 mode); e2e: okb_detect_describe_batch from host buffers (+ the same matchers on the device);
+    cpu_baseline: the oracle's detect + describe on one core."""
     import torch
     from okvis2_b200 import lib as okl
     from okvis2_b200.frontend import Frontend
@@ -864,16 +874,43 @@ def run_okvis48(args, rank, world, local_rank, steps, with_cpu):
         okl.check(L_.okb_set_extraction_direction(fe.ctx, c, np.ascontiguousarray(T_WC[:3, :3]).ctypes.data))
     Lf, Rf = make_frames(cfg, ring * B, 1000 + 100 * rank)
     d_img = [torch.from_numpy(Lf).cuda(), torch.from_numpy(Rf).cuda()]
-    first = [fe.detectAndDescribeBatch(c, img[:1])[0] for c, img in enumerate((Lf, Rf))]
-    pools = [make_map(cfg, kp, desc, 40 + c) for c, (kp, desc) in enumerate(first)]
+    from okvis2_b200.frontend import MultiFrame
+    pools, older = [], []
+    for c, img in enumerate((Lf[0], Rf[0])):
+        mf = MultiFrame(2); mf.setImage(c, img); fe.detectAndDescribe(c, mf); fe.computeBackProjections(mf, c)
+        fr = mf.frames[c]
+        pools.append(make_map(cfg, fr.keypoints, fr.descriptors, 40 + c))
+        older.append(make_older_views(cfg, c, fr.keypoints, fr.descriptors, fr.backProjections, fr.backProjectionsValid, 90 + c))
     cap = C.c_int(0); L_.okb_device_features(fe.ctx, 0, None, None, None, C.byref(cap))
     kp_cap = cap.value
-    d_maps, outs = [], []
-    for m in pools:
+    n_older = cfg["n_older"]
+    cap0 = (max(len(v["desc"]) for vs in older for v in vs) + 63) // 64 * 64
+    z = lambda shape, dt: torch.zeros(shape, dtype=dt, device="cuda")
+    d_maps, outs, views, keep = [], [], [], []
+    for c, m in enumerate(pools):
         proj = np.broadcast_to(m["lm_proj"], (B,) + m["lm_proj"].shape).copy()
         d_maps.append(dict(desc=torch.from_numpy(m["cand_desc"]).cuda(), lm=torch.from_numpy(m["cand_lm"]).cuda(), proj=torch.from_numpy(proj).cuda(),
                            is3d=torch.from_numpy(m["lm_is3d"]).cuda()))
-        outs.append(dict(dist=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda"), lm=torch.zeros((B, kp_cap), dtype=torch.int32, device="cuda")))
+        outs.append(dict(dist=z((B, kp_cap), torch.int32), lm=z((B, kp_cap), torch.int32), mask=z((B, kp_cap), torch.uint8),
+                         k1=z((B, n_older, cap0), torch.int32), d3=z((B, n_older, cap0), torch.int32), hp3=z((B, n_older, cap0, 4), torch.float64),
+                         fl3=z((B, n_older, cap0), torch.uint8)))
+        # older keyframe views as device blocks: descriptor rows in 64-byte slots with a zero tail (what the tensor-core scans read)
+        tab = (okl.OlderView * (B * n_older))()
+        blocks = []
+        for v in older[c]:
+            slots = np.zeros((len(v["desc"]), 64), np.uint8); slots[:, :48] = v["desc"]
+            t = dict(desc=torch.from_numpy(slots).cuda(), **{k: torch.from_numpy(np.ascontiguousarray(v[k])).cuda() for k in ("rays", "valid", "size", "use")})
+            keep.append(t); blocks.append((t, v))
+        for b in range(B):
+            for vi, (t, v) in enumerate(blocks):
+                e = tab[b * n_older + vi]
+                e.d_desc, e.d_rays, e.d_valid, e.d_size, e.d_use = (t[k].data_ptr() for k in ("desc", "rays", "valid", "size", "use"))
+                e.n = len(v["desc"]); e.T_WC[:] = list(v["T_WC"]); e.T_CW[:] = list(v["T_CW"])
+        views.append(tab)
+    Tw1 = [np.ascontiguousarray(np.broadcast_to(cam_pose(c)[0], (B, 12))) for c in range(2)]
+    Tc1 = [np.ascontiguousarray(np.broadcast_to(cam_pose(c)[1], (B, 12))) for c in range(2)]
+    st4 = dict(k1=z((B, kp_cap), torch.int32), dist=z((B, kp_cap), torch.int32), hp=z((B, kp_cap, 4), torch.float64), init=z((B, kp_cap), torch.uint8))
+    C_WC = [np.eye(3), np.eye(3)]; r_WC = [np.zeros(3), np.array([0.11, 0.0, 0.0])]
     streams = [torch.cuda.ExternalStream(L_.okb_stream(fe.ctx, c)) for c in range(2)]
 
     def m1(c):
@@ -881,10 +918,21 @@ def run_okvis48(args, rank, world, local_rank, steps, with_cpu):
         okl.check(L_.okb_match_map3d_device(fe.ctx, c, 48, B, len(dm["lm"]), dm["desc"].data_ptr(), dm["lm"].data_ptr(), len(dm["is3d"]),
                                             dm["proj"].data_ptr(), dm["is3d"].data_ptr(), 20.0, 60, o["dist"].data_ptr(), o["lm"].data_ptr()))
 
+    def m3(c):
+        o = outs[c]
+        okl.check(L_.okb_matched_mask_device(fe.ctx, c, B, o["lm"].data_ptr(), o["mask"].data_ptr()))
+        okl.check(L_.okb_match_motion_stereo_device(fe.ctx, c, B, Tw1[c].ctypes.data, Tc1[c].ctypes.data, n_older, views[c], cap0, 60, o["mask"].data_ptr(),
+                                                    o["k1"].data_ptr(), o["d3"].data_ptr(), o["hp3"].data_ptr(), o["fl3"].data_ptr()))
+
+    def m4():
+        okl.check(L_.okb_match_stereo_device(fe.ctx, 0, 1, B, C_WC[0].ctypes.data, r_WC[0].ctypes.data, C_WC[1].ctypes.data, r_WC[1].ctypes.data, 60,
+                                             st4["k1"].data_ptr(), st4["dist"].data_ptr(), st4["hp"].data_ptr(), st4["init"].data_ptr()))
+
     def step(s):
         for c in range(2):
             okl.check(L_.okb_detect_describe_batch_device(fe.ctx, c, B, d_img[c][(s % ring) * B:(s % ring + 1) * B].data_ptr()))
-            m1(c)
+            m1(c); m3(c)
+        m4()
     warm = max(args.warmup, 3)
     for s in range(warm):
         step(s)
@@ -907,6 +955,12 @@ def run_okvis48(args, rank, world, local_rank, steps, with_cpu):
     if np.mean(cnt) < 0.95 * cfg["kpts"]:
         raise RuntimeError(f"okvis48 workload: {np.mean(cnt):.0f} keypoints per frame < 0.95 x {cfg['kpts']}")
     m1_matches = float(sum((o["lm"] >= 0).sum().item() for o in outs) / (2 * B))
+    m3_inserted = float(sum(((o["fl3"] & 4) != 0).sum().item() for o in outs) / (2 * B))
+    m4_matches = float((st4["k1"] >= 0).sum().item() / B)
+    step(0)   # untimed: the batch that holds frame 0, which the pool and the older views were built from
+    okl.check(L_.okb_sync(fe.ctx)); torch.cuda.synchronize()
+    frame0 = {"m1_matches": int((outs[0]["lm"][0] >= 0).sum().item()), "m3_matching": int(((outs[0]["fl3"][0] & 1) != 0).sum().item()),
+              "m3_inserted": int(((outs[0]["fl3"][0] & 4) != 0).sum().item()), "m4_matches": int((st4["k1"][0] >= 0).sum().item())}
     # ---- end to end: host buffers (page-locked) through okb_detect_describe_batch, every copy inside the timed region
     h_img = [torch.from_numpy(x).pin_memory() for x in (Lf, Rf)]
     h_kp = [torch.zeros((B, kp_cap, 28), dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -916,12 +970,13 @@ def run_okvis48(args, rank, world, local_rank, steps, with_cpu):
     def cam_job(c, s):
         okl.check(L_.okb_detect_describe_batch(fe.ctx, c, B, h_img[c][(s % ring) * B:(s % ring + 1) * B].data_ptr(), W, h_kp[c].data_ptr(),
                                                h_desc[c].data_ptr(), kp_cap, n_out[c].ctypes.data))
-        m1(c)
+        m1(c); m3(c)
 
     def host_step(s):
         ts = [threading.Thread(target=cam_job, args=(c, s)) for c in range(2)]
         for t in ts: t.start()
         for t in ts: t.join()
+        m4()
         okl.check(L_.okb_sync(fe.ctx))
     for s in range(2):
         host_step(s)
@@ -933,14 +988,17 @@ def run_okvis48(args, rank, world, local_rank, steps, with_cpu):
     e2e_s = time.perf_counter() - t0
     rec = {"value": B * steps / (dev_ms * 1e-3), "unit": "stereo frames/s", "ms_per_step": dev_ms / steps, "steps": steps,
            "stereo_frames_per_step_per_gpu": B, "gpu_launches": int(launches),
-           "workload_stats": {"keypoints_per_frame": float(np.mean(cnt)), "keypoints_per_frame_min": int(min(cnt)), "m1_matches_per_frame": m1_matches},
+           "workload_stats": {"keypoints_per_frame": float(np.mean(cnt)), "keypoints_per_frame_min": int(min(cnt)), "m1_matches_per_frame": m1_matches,
+                              "m3_inserted_per_frame": m3_inserted, "m4_matches_per_stereo_frame": m4_matches, "frame0": frame0},
            "e2e": {"value": B * steps / e2e_s, "unit": "stereo frames/s", "h2d_bytes_per_step": 2 * B * W * H,
                    "d2h_bytes_per_step": int(n_out.max(1).sum() * B * (28 + 48 + 25)),
-                   "api": "okb_detect_describe_batch (one host thread per camera, page-locked buffers) + okb_match_map3d_device"},
+                   "api": "okb_detect_describe_batch (one host thread per camera, page-locked buffers) + the device-resident matchers"},
            "config": {"workload": "euroc_okvis48", "W": W, "H": H, "keypoints_per_frame": cfg["kpts"], "detector_max_keypoints": cfg["max_kp"],
                       "uniformity_radius": cfg["radius"], "absolute_threshold": cfg["abs_threshold"], "octaves": 0, "descriptor_bytes": 48, "n_lm": cfg["n_lm"],
+                      "older_keyframes": n_older, "older_keypoints_eligible": ELIGIBLE,
                       "camera_aware": True, "step": "per stereo frame: Harris + uniformity detect, camera-aware gravity-aligned BRISK2-48 describe, "
-                      "back-project, M1 match-to-map per camera", "l2_policy": f"ring of {ring} batches"},
+                      "back-project, M1 match-to-map per camera, M3 motion stereo per camera against the older keyframes, M4 stereo match "
+                      "(the headline step in the D = 48 mode)", "l2_policy": f"ring of {ring} batches"},
            "parity": "bit-exact vs oracle/brisk_oracle.c section 6; PARITY UNPINNED vs smartroboticslab/brisk@1ef8b42a (source absent)"}
     # ---- live use: one stereo frame per call (one host thread per camera, okb_detect_describe on a page-locked frame; D4 rides along)
     fe.close()

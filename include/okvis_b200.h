@@ -105,7 +105,14 @@ int okb_device_features(okb_context_t* ctx, int cam, const okb_keypoint_t** d_kp
  * rays [max_batch][capacity][3] doubles (x, y, 1), valid [max_batch][capacity]; valid until the next detect call on it */
 int okb_device_back_projections(okb_context_t* ctx, int cam, const double** d_rays, const uint8_t** d_valid);
 
-/* Fixed-capacity feature block of a batch, the unit the camera-sharded multi-GPU mode all-gathers:
+/* Descriptor rows on the device. okb_device_features hands out rows of the camera's own width (descriptor_bytes: 64 or 48). The
+ * device-resident matcher forms built on the tensor-core Hamming scans (okb_match_stereo_device*, okb_match_motion_stereo_device*) and the
+ * feature block below read rows in 64-BYTE SLOTS; a 48-byte row sits in the first 48 bytes of its slot with a zero tail (the Hamming
+ * distances are the same). A D = 48 camera keeps that second layout itself, so the forms that take a camera index work on it unchanged;
+ * blocks the caller passes by pointer (okb_older_view_t::d_desc, the *_ptr forms) use the slot layout. okb_process_multiframe is built
+ * for D = 64 cameras (OKB_ERR_UNSUPPORTED otherwise).
+ *
+ * Fixed-capacity feature block of a batch, the unit the camera-sharded multi-GPU mode all-gathers:
  *   [counts: n_frames x int32, padded to 256 B][keypoints: n_frames x capacity x 28 B][descriptors: n_frames x capacity x 64 B]
  * okb_export_features packs the last result of camera `cam` into the caller's DEVICE buffer (asynchronous on the camera
  * stream; capacity = okb_device_features). The block layout is what okb_match_stereo_device_ptr consumes. */
