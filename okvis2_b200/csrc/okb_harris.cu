@@ -38,6 +38,9 @@ struct HarrisState {
   int basic_scale = 0;
   int border = 0;
   float radius = 0.f;
+  float* d_dir = nullptr;             // live path: the extraction direction on the device (a captured graph cannot carry it as an argument)
+  float* h_dir = nullptr;             //            and its page-locked mirror
+  int dir_from_device = 0;
   int cshift = 4;                     // log2 of the uniformity kernel's cell size in half-resolution positions
 };
 
@@ -211,9 +214,10 @@ __device__ __forceinline__ void for_each_neighbour(const uint32_t* entries, cons
 __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score_maps, int W, int H, const uint2* cand, const int32_t* cand_count,
                                                             int count_stride, int32_t* sorted_score, uint32_t* sorted_xy, const float* lut_g, int cshift,
                                                             const PatternPoint* pat0_g, int max_kp, int kp_cap, int border, const float* ray_map,
-                                                            const float* jac_map, float fu, float d0, float d1, float d2, okb_keypoint_t* kp_out,
-                                                            int32_t* count_out, int32_t* status, long long* dbg)
+                                                            const float* jac_map, float fu, float d0, float d1, float d2, const float* dir_dev,
+                                                            okb_keypoint_t* kp_out, int32_t* count_out, int32_t* status, long long* dbg)
 {
+  if (dir_dev) { d0 = dir_dev[0]; d1 = dir_dev[1]; d2 = dir_dev[2]; }
 #define OKB_STAMP(i) if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + (i)] = clock64()
   OKB_STAMP(0);
   extern __shared__ unsigned long long keys[];                                   // kHarrisCandCap sort keys ...
@@ -428,9 +432,10 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
 __global__ void __launch_bounds__(128) k_describe48(const uint8_t* in0, int in_pitch, size_t in_frame_stride, int W, int H, const int32_t* integral,
                                                     int ipitch, const PatternPoint* pattern /*[rot][point] of the one scale*/, const uint32_t* short48,
                                                     const int4* long_pairs, const float* ray_map, const float* jac_map, float fu, float d0, float d1,
-                                                    float d2, okb_keypoint_t* kp, const int32_t* count, int kp_cap, uint8_t* desc, uint8_t* desc64)
+                                                    float d2, const float* dir_dev, okb_keypoint_t* kp, const int32_t* count, int kp_cap, uint8_t* desc, uint8_t* desc64)
 {
   __shared__ int values[4][64];
+  if (dir_dev) { d0 = dir_dev[0]; d1 = dir_dev[1]; d2 = dir_dev[2]; }
   const int frame = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.x * 4 + warp;
@@ -538,6 +543,7 @@ int harris_init_camera(okb_context* ctx, int cam)
   OKB_CUDA(cudaMalloc(&hs->d_short48, 384 * 4));
   OKB_CUDA(cudaMemcpy(hs->d_short48, sp.data(), 384 * 4, cudaMemcpyHostToDevice));
   hs->border = (int)ctx->h_size_list[hs->basic_scale];
+  OKB_CUDA(cudaMalloc(&hs->d_dir, 16)); OKB_CUDA(cudaMemset(hs->d_dir, 0, 16)); OKB_CUDA(cudaMallocHost(&hs->h_dir, 16));
   OKB_CUDA(cudaMalloc(&ws.d_desc64, (size_t)ws.kp_cap * 64 * B));
   OKB_CUDA(cudaMemset(ws.d_desc64, 0, (size_t)ws.kp_cap * 64 * B));
   OKB_CUDA(cudaFuncSetAttribute(k_uniformity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUniSmem));
@@ -549,7 +555,7 @@ void harris_free_camera(okb_context* ctx, int cam)
   CamWorkspace& ws = ctx->cams[cam];
   HarrisState* hs = (HarrisState*)ws.harris;
   if (!hs) return;
-  cudaFree(hs->d_score); cudaFree(hs->d_cond); cudaFree(hs->d_cand); cudaFree(hs->d_sorted_score); cudaFree(hs->d_sorted_xy); cudaFree(hs->d_lut); cudaFree(hs->d_short48);
+  cudaFree(hs->d_score); cudaFree(hs->d_cond); cudaFree(hs->d_cand); cudaFree(hs->d_sorted_score); cudaFree(hs->d_sorted_xy); cudaFree(hs->d_dir); if (hs->h_dir) cudaFreeHost(hs->h_dir); cudaFree(hs->d_lut); cudaFree(hs->d_short48);
   delete hs;
   ws.harris = nullptr;
   cudaFree(ws.d_desc64); ws.d_desc64 = nullptr;
@@ -585,19 +591,32 @@ int harris_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   const float* jac = aware ? ws.d_jac_map : nullptr;
   const float fu = aware ? (float)ws.model.fu : 1.0f;
   const PatternPoint* pat = ctx->d_pattern + (size_t)hs->basic_scale * kRot * kPoints;
+  // live path (okb_process_multiframe): the direction comes from the page-locked mirror through a copy node, so that a replayed graph
+  // sees this frame's value; everywhere else it is a launch argument
+  const float* dir_dev = nullptr;
+  if (hs->dir_from_device) { memcpy(hs->h_dir, ws.extraction_dir, 12); OKB_CUDA(cudaMemcpyAsync(hs->d_dir, hs->h_dir, 12, cudaMemcpyHostToDevice, st)); dir_dev = hs->d_dir; hs->dir_from_device = 0; }
   k_uniformity<<<B, kUniThreads, kUniSmem, st>>>(hs->d_score, W, H, hs->d_cand, ws.d_cand_count, kMaxLayers, hs->d_sorted_score, hs->d_sorted_xy, hs->d_lut, hs->cshift, pat,
                                                  c.max_keypoints, ws.kp_cap, hs->border, rays, jac, fu, ws.extraction_dir[0], ws.extraction_dir[1],
-                                                 ws.extraction_dir[2], ws.d_kp, ws.d_count, ws.d_status, ws.d_dbg);
+                                                 ws.extraction_dir[2], dir_dev, ws.d_kp, ws.d_count, ws.d_status, ws.d_dbg);
   if (ctx->timers_on) cudaEventRecord(ws.ev[2], st);
   OKB_CUDA(cudaStreamWaitEvent(st, ws.ev_join, 0));
   k_describe48<<<dim3((ws.kp_cap + 3) / 4, B), 128, 0, st>>>(d_images, src_pitch, in_stride, W, H, ws.d_integral, ipitch, pat, hs->d_short48,
                                                              ctx->d_long_pairs, rays, jac, fu, ws.extraction_dir[0], ws.extraction_dir[1],
-                                                             ws.extraction_dir[2], ws.d_kp, ws.d_count, ws.kp_cap, ws.d_desc, ws.d_desc64);
+                                                             ws.extraction_dir[2], dir_dev, ws.d_kp, ws.d_count, ws.kp_cap, ws.d_desc, ws.d_desc64);
   ctx->launches += 6;
   { int rc = camera_backproject_batch(ctx, cam, B); if (rc) return rc; }
   if (ctx->timers_on) { cudaEventRecord(ws.ev[3], st); ws.pending_timing = 1; }
   OKB_CUDA(cudaGetLastError());
   return OKB_OK;
+}
+
+void harris_stage_direction(okb_context* ctx, int cam)
+{
+  CamWorkspace& ws = ctx->cams[cam];
+  HarrisState* hs = (HarrisState*)ws.harris;
+  if (!hs) return;
+  memcpy(hs->h_dir, ws.extraction_dir, 12);
+  hs->dir_from_device = 1;   // consumed by the next harris_run_device (direct submission or capture); a replay only needs the mirror
 }
 
 }  // namespace okb

@@ -197,6 +197,7 @@ int camera_backproject_batch(okb_context* ctx, int cam, int n_frames);
 int harris_init_camera(okb_context* ctx, int cam);
 void harris_free_camera(okb_context* ctx, int cam);
 int harris_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_images, int src_pitch, cudaEvent_t input_ready);
+void harris_stage_direction(okb_context* ctx, int cam);   // live path: refresh the page-locked mirror of the extraction direction
 struct Model;
 int camera_stereo_prep_pair(okb_context* ctx, const okb_camera_model_t* const model[2], const double* const C_WC[2], const okb_keypoint_t* const d_kp[2],
                             const int32_t* const d_count[2], const int cap[2], int n_frames, double* const d_rays[2], uint8_t* const d_valid[2],

@@ -127,7 +127,6 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
   if (!ctx || n_cams < 1 || n_cams != ctx->n_cams || !io || n_pairs < 0 || (n_pairs > 0 && !pairs)) {
     set_error("okb_process_multiframe: bad arguments (one okb_multiframe_cam_t per camera of the context)"); return OKB_ERR_ARGUMENT;
   }
-  for (int c = 0; c < n_cams; c++) OKB_REQUIRE_D64(ctx->cams[c], "okb_process_multiframe");
   OKB_CUDA(cudaSetDevice(ctx->device));
   StreamState* S = state(ctx);
   auto now = [] { return std::chrono::steady_clock::now(); };
@@ -152,7 +151,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       if (!q.pool_changed && q.n_cand > 0 && A.n_cand >= 0) { set_error("okb_process_multiframe: camera %d: pool sizes changed without pool_changed", c); return OKB_ERR_ARGUMENT; }
       const int no = q.n_older > 0 ? q.n_older : 1, c0 = q.cap0 > 0 ? q.cap0 : 1, cm = q.cap_m > 0 ? q.cap_m : 1;
       size_t o = 0; auto take = [&](size_t b) { const size_t r = o; o += al(b); return r; };
-      A.o_desc = take((size_t)q.n_cand * 64); A.o_lm = take((size_t)q.n_cand * 4); A.o_3d = take((size_t)q.n_lm); A.o_proj = take((size_t)q.n_lm * 16);
+      A.o_desc = take((size_t)q.n_cand * ws.cfg.descriptor_bytes); A.o_lm = take((size_t)q.n_cand * 4); A.o_3d = take((size_t)q.n_lm); A.o_proj = take((size_t)q.n_lm * 16);
       A.o_mask = take((size_t)cap);
       A.o_k1 = take((size_t)no * c0 * 4); A.o_dist = take((size_t)no * c0 * 4); A.o_hp = take((size_t)no * c0 * 32); A.o_fl = take((size_t)no * c0);
       // what the host reads back, contiguous (one copy): M1 results, M3 counts and compact lists
@@ -177,12 +176,13 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
         prev = lm;
       }
       OKB_CUDA(cudaStreamSynchronize(ws.stream));
-      OKB_CUDA(cudaMemcpy(A.d + A.o_desc, q.cand_desc, (size_t)q.n_cand * 64, cudaMemcpyHostToDevice));
+      OKB_CUDA(cudaMemcpy(A.d + A.o_desc, q.cand_desc, (size_t)q.n_cand * ws.cfg.descriptor_bytes, cudaMemcpyHostToDevice));
       OKB_CUDA(cudaMemcpy(A.d + A.o_lm, q.cand_lm, (size_t)q.n_cand * 4, cudaMemcpyHostToDevice));
       OKB_CUDA(cudaMemcpy(A.d + A.o_3d, q.lm_is3d, (size_t)q.n_lm, cudaMemcpyHostToDevice));
     }
     sig = mix(mix(mix(mix(mix(sig, q.n_cand), q.n_lm), q.n_older), q.cap0), q.cap_m);
     sig = mix(sig, q.rays ? 1 : 0);
+    sig = mix(mix(sig, ws.cfg.descriptor_bytes), ws.maps_ready);   // D = 48: camera-aware or plain extraction is a launch argument
   }
   if ((int)S->pairs.size() < n_pairs) S->pairs.resize(n_pairs);
   for (int p = 0; p < n_pairs; p++) {
@@ -233,6 +233,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       if (st_proj) memcpy(A.h + A.o_proj, q.lm_proj, (size_t)q.n_lm * 16);
     }
     if (q.n_older > 0) { memcpy(A.h + A.o_pose, q.T_WC1, 96); memcpy(A.h + A.o_pose + 96, q.T_CW1, 96); }
+    harris_stage_direction(ctx, c);   // D = 48: the extraction direction of this frame, through the page-locked mirror the graph copies from
   }
   for (auto& e : S->ev) if (!e) OKB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if (S->side.empty()) {
@@ -264,7 +265,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       if (rc) return rc;
       OKB_CUDA(cudaEventRecord(S->ev_det[c], st));
       if (q.n_cand > 0) {
-        rc = match_map3d_enqueue(ctx, c, 64, 1, q.n_cand, A.d + A.o_desc, (const int32_t*)(A.d + A.o_lm), q.n_lm, (const double*)(A.d + A.o_proj),
+        rc = match_map3d_enqueue(ctx, c, ws.cfg.descriptor_bytes, 1, q.n_cand, A.d + A.o_desc, (const int32_t*)(A.d + A.o_lm), q.n_lm, (const double*)(A.d + A.o_proj),
                                  A.d + A.o_3d, reprojection_threshold, match_threshold, (uint32_t*)(A.d + A.o_m1d), (int32_t*)(A.d + A.o_m1l), sd, S->ev_bin[c]);
         if (rc) return rc;
       }
@@ -273,7 +274,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       OKB_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, 4, cudaMemcpyDeviceToHost, sd));
       OKB_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, 4, cudaMemcpyDeviceToHost, sd));
       OKB_CUDA(cudaMemcpyAsync(ws.h_kp, ws.d_kp, (size_t)cap * sizeof(okb_keypoint_t), cudaMemcpyDeviceToHost, sd));
-      OKB_CUDA(cudaMemcpyAsync(ws.h_desc, ws.d_desc, (size_t)cap * 64, cudaMemcpyDeviceToHost, sd));
+      OKB_CUDA(cudaMemcpyAsync(ws.h_desc, ws.d_desc, (size_t)cap * ws.cfg.descriptor_bytes, cudaMemcpyDeviceToHost, sd));
       if (ws.has_model) {
         OKB_CUDA(cudaMemcpyAsync(ws.h_rays, ws.d_rays, (size_t)cap * 24, cudaMemcpyDeviceToHost, sd));
         OKB_CUDA(cudaMemcpyAsync(ws.h_rays_valid, ws.d_rays_valid, (size_t)cap, cudaMemcpyDeviceToHost, sd));
@@ -282,7 +283,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       if (q.n_older > 0) {
         if (q.n_cand == 0) OKB_CUDA(cudaMemsetAsync(A.d + A.o_mask, 0, (size_t)cap, st));   // else: initialised from M1's result by the sequence
         ws.motion.pinned_staging = 1;   // tables through the page-locked mirror: a captured copy node re-reads it at every replay
-        rc = motion_sequence(ctx, ws.motion, 1, cap, ws.d_kp, ws.d_desc, ws.d_count, &ws.model, W, H, (const double*)(A.h + A.o_pose),
+        rc = motion_sequence(ctx, ws.motion, 1, cap, ws.d_kp, desc_slots(ws), ws.d_count, &ws.model, W, H, (const double*)(A.h + A.o_pose),
                              (const double*)(A.h + A.o_pose + 96), q.n_older, q.older, q.cap0, match_threshold, st, A.d + A.o_mask,
                              (int32_t*)(A.d + A.o_k1), (uint32_t*)(A.d + A.o_dist), (double*)(A.d + A.o_hp), A.d + A.o_fl, ws.d_rays, ws.d_rays_valid,
                              q.n_cand > 0 ? (const int32_t*)(A.d + A.o_m1l) : nullptr);
@@ -309,7 +310,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
       uint8_t* d = A.d; const size_t o_k1 = 0, o_d = al(n * 4), o_hp = 2 * al(n * 4), o_in = o_hp + al(n * 32);
       OKB_CUDA(cudaStreamWaitEvent(sp, S->ev_det[P.cam0], 0));
       OKB_CUDA(cudaStreamWaitEvent(sp, S->ev_det[P.cam1], 0));
-      int rc = okb_match_stereo_device_ptr(ctx, 1, w0.kp_cap, w0.d_kp, w0.d_desc, w0.d_count, &w0.model, P.C_WC0, P.r_WC0, w1.kp_cap, w1.d_kp, w1.d_desc,
+      int rc = okb_match_stereo_device_ptr(ctx, 1, w0.kp_cap, w0.d_kp, desc_slots(w0), w0.d_count, &w0.model, P.C_WC0, P.r_WC0, w1.kp_cap, w1.d_kp, desc_slots(w1),
                                            w1.d_count, &w1.model, P.C_WC1, P.r_WC1, match_threshold, (void*)sp, (int32_t*)(d + o_k1),
                                            (uint32_t*)(d + o_d), (double*)(d + o_hp), d + o_in);
       if (rc) return rc;
@@ -405,7 +406,7 @@ int okb_process_multiframe(okb_context_t* ctx, int n_cams, okb_multiframe_cam_t*
     const int n = ws.h_count[0];
     if (n > q.cap) { set_error("okb_process_multiframe: camera %d: %d keypoints do not fit the caller's capacity %d", c, n, q.cap); return OKB_ERR_CAPACITY; }
     q.n = n;
-    memcpy(q.kp, ws.h_kp, (size_t)n * sizeof(okb_keypoint_t)); memcpy(q.desc, ws.h_desc, (size_t)n * 64);
+    memcpy(q.kp, ws.h_kp, (size_t)n * sizeof(okb_keypoint_t)); memcpy(q.desc, ws.h_desc, (size_t)n * ws.cfg.descriptor_bytes);
     if (q.rays) memcpy(q.rays, ws.h_rays, (size_t)n * 24);
     if (q.rays_valid) memcpy(q.rays_valid, ws.h_rays_valid, (size_t)n);
     ws.h_rays_frames = ws.has_model ? 1 : 0;

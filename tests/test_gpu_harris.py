@@ -250,3 +250,135 @@ def test_device_resident_matchers_on_48_byte_rows():
             inserted += int(((rfl & 4) != 0).sum())
     assert inserted > 50
     fe.close()
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_process_multiframe_in_the_48_byte_mode(use_graph):
+    """The live path (okb_process_multiframe: one call per stereo frame, CUDA-graph replay from the third call on) with D = 48 cameras:
+    camera-aware extraction whose direction changes with every frame (it reaches a replayed graph through a page-locked mirror), M1 on a
+    48-byte pool, the M3 sequence against older views in 64-byte slots, M4 -- every stage against the oracle."""
+    import torch
+    from okvis2_b200.synth import pose12, rot, synth_stereo
+    from test_gpu_camera import EUROC as EU, T_CW, oracle_bp, world_rays
+    W, H, MAXKP, CAP_M, NV, RAD, THR = 752, 480, 700, 256, 3, 12.0, 40
+    fe = make(W, H, RAD, THR, MAXKP, n_cams=2)
+    L_ = _l.lib()
+    maps = []
+    for c in range(2):
+        fe.setCameraModel(c, **EU[c])
+        maps.append(fe.cameraAwarenessMaps(c))
+    _l.check(L_.okb_stream_use_graph(fe.ctx, 1 if use_graph else 0))
+    n_calls = 5
+    frames = [synth_stereo(500 + t % 2, W, H) for t in range(n_calls)]
+    o = oracle.HarrisBrisk2(RAD, THR, MAXKP)
+    intr = [np.array(list(EU[c]["focal_length"]) + list(EU[c]["principal_point"]) + list(EU[c]["distortion_coefficients"])) for c in range(2)]
+    fu = [float(np.float32(EU[c]["focal_length"][0])) for c in range(2)]
+
+    def C_WC_at(t):   # the camera rolls a little from frame to frame: the extraction direction changes
+        return rot((0, 0, 1), 0.05 * t) @ np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0.]])
+
+    def direction(c, t):
+        _l.check(L_.okb_set_extraction_direction(fe.ctx, c, np.ascontiguousarray(C_WC_at(t)).ctypes.data))
+        d = np.zeros(3, np.float32); _l.check(L_.okb_get_extraction_direction(fe.ctx, c, d.ctypes.data))
+        return d
+    poses = [pose12(np.eye(3), np.array([0.11 * c, 0.0, 0.0])) for c in range(2)]
+    pools, views, dviews = [], [], []
+    rng = np.random.default_rng(11)
+    for c in range(2):
+        kp, d = o.detect_and_compute(frames[0][c], maps[c][0], maps[c][1], fu[c], direction(c, 0))
+        rays, valid = oracle_bp(EU[c], kp)
+        pools.append(map_scene(7 + c, np.stack([kp["x"], kp["y"]], 1).astype(np.float64), d, 1200, W=W, H=H, frac_near=0.3))
+        e = rays / np.linalg.norm(rays, axis=1, keepdims=True)
+        P = poses[c][0][9:] + e * np.exp(rng.uniform(np.log(1.5), np.log(25.0), len(kp)))[:, None]
+        vs = []
+        for v in range(NV):
+            Cv = rot((0, 1, 0), 0.012 * (v + 1)); rv = poses[c][0][9:] + np.array([-0.06 * (v + 1), 0.01 * v, -0.02 * (v + 1)])
+            pc = (P - rv) @ Cv
+            idx = np.nonzero((valid != 0) & (pc[:, 2] > 0.3) & (rng.random(len(kp)) < 0.4))[0]
+            bits = np.unpackbits(d[idx], axis=1)
+            dd = np.packbits(bits ^ (rng.random(bits.shape) < 0.04).astype(np.uint8), axis=1)
+            ry = np.stack([pc[idx, 0] / pc[idx, 2], pc[idx, 1] / pc[idx, 2], np.ones(len(idx))], 1)
+            dd = np.concatenate([dd, rng.integers(0, 256, (200, 48), dtype=np.uint8)])
+            ry = np.concatenate([ry, np.stack([rng.uniform(-0.7, 0.7, 200), rng.uniform(-0.45, 0.45, 200), np.ones(200)], 1)])
+            Tw, Tc = pose12(Cv, rv)
+            vs.append(dict(desc=np.ascontiguousarray(dd), rays=np.ascontiguousarray(ry), valid=(rng.random(len(dd)) > 0.02).astype(np.uint8),
+                           size=(rng.choice([12.0, 18.0], len(dd)) * rng.uniform(0.9, 1.1, len(dd))).astype(np.float32),
+                           use=(rng.random(len(dd)) > 0.2).astype(np.uint8), T_WC=Tw, T_CW=Tc))
+        views.append(vs)
+        dv = []
+        for v in vs:
+            slots = np.zeros((len(v["desc"]), 64), np.uint8); slots[:, :48] = v["desc"]
+            dv.append(dict(desc=torch.from_numpy(slots).cuda(), **{k: torch.from_numpy(np.ascontiguousarray(v[k])).cuda() for k in ("rays", "valid", "size", "use")}))
+        dviews.append(dv)
+    cap0 = (max(len(v["desc"]) for vs in views for v in vs) + 63) // 64 * 64
+    cap = MAXKP
+    C0 = np.eye(3); r0 = np.zeros(3); r1 = np.array([0.11, 0.0, 0.0])
+    totals = dict(m1=0, m3=0, m4=0)
+    try:
+        for t in range(n_calls):
+            io = (_l.MultiframeCam * 2)(); bufs = []; tabs = []; dirs = []
+            for c in range(2):
+                dirs.append(direction(c, t))
+                q = io[c]
+                tab = (_l.OlderView * NV)()
+                for vi in range(NV):
+                    v, dvv = views[c][(vi + t) % NV], dviews[c][(vi + t) % NV]
+                    e = tab[vi]
+                    e.d_desc, e.d_rays, e.d_valid, e.d_size, e.d_use = (dvv[k].data_ptr() for k in ("desc", "rays", "valid", "size", "use"))
+                    e.n = len(v["desc"]); e.T_WC[:] = list(v["T_WC"]); e.T_CW[:] = list(v["T_CW"])
+                tabs.append(tab)
+                img = np.ascontiguousarray(frames[t][c]); m = pools[c]
+                proj = np.ascontiguousarray(m["lm_proj"] + 0.7 * t)
+                b = dict(img=img, proj=proj, kp=np.zeros(cap, _l.KP_DTYPE), desc=np.zeros((cap, 48), np.uint8), rays=np.zeros((cap, 3)),
+                         valid=np.zeros(cap, np.uint8), m1d=np.zeros(cap, np.uint32), m1l=np.zeros(cap, np.int32), m3n=np.zeros(NV, np.int32),
+                         k0=np.zeros((NV, CAP_M), np.int32), k1=np.zeros((NV, CAP_M), np.int32), fl=np.zeros((NV, CAP_M), np.uint8),
+                         hp=np.zeros((NV, CAP_M, 4)), Tw=np.ascontiguousarray(poses[c][0]), Tc=np.ascontiguousarray(poses[c][1]),
+                         cd=np.ascontiguousarray(m["cand_desc"]), cl=np.ascontiguousarray(m["cand_lm"]), c3=np.ascontiguousarray(m["lm_is3d"]))
+                bufs.append(b)
+                q.image = img.ctypes.data; q.stride_bytes = W
+                q.n_cand = len(b["cl"]); q.n_lm = len(b["c3"]); q.pool_changed = 1 if t == 0 else 0
+                q.cand_desc, q.cand_lm, q.lm_is3d, q.lm_proj = b["cd"].ctypes.data, b["cl"].ctypes.data, b["c3"].ctypes.data, proj.ctypes.data
+                q.T_WC1, q.T_CW1 = b["Tw"].ctypes.data, b["Tc"].ctypes.data
+                q.n_older, q.cap0, q.older = NV, cap0, C.addressof(tab)
+                q.cap = cap; q.kp, q.desc, q.rays, q.rays_valid = (b[k].ctypes.data for k in ("kp", "desc", "rays", "valid"))
+                q.m1_dist, q.m1_lm = b["m1d"].ctypes.data, b["m1l"].ctypes.data
+                q.cap_m = CAP_M; q.m3_n, q.m3_k0, q.m3_k1, q.m3_flags, q.m3_hp_W = (b[k].ctypes.data for k in ("m3n", "k0", "k1", "fl", "hp"))
+            st = _l.MultiframeStereo(); st.cam0, st.cam1 = 0, 1
+            st.C_WC0[:] = [1, 0, 0, 0, 1, 0, 0, 0, 1]; st.C_WC1[:] = [1, 0, 0, 0, 1, 0, 0, 0, 1]; st.r_WC0[:] = [0, 0, 0]; st.r_WC1[:] = [0.11, 0, 0]
+            sb = dict(k1=np.zeros(cap, np.int32), dist=np.zeros(cap, np.uint32), hp=np.zeros((cap, 4)), init=np.zeros(cap, np.uint8))
+            st.k1, st.dist, st.hp_W, st.initialisable = (sb[k].ctypes.data for k in ("k1", "dist", "hp", "init"))
+            _l.check(L_.okb_process_multiframe(fe.ctx, 2, io, 1, C.byref(st), 20.0, 60))
+            feats = []
+            for c in range(2):
+                b = bufs[c]; n = io[c].n
+                rk, rd = o.detect_and_compute(frames[t][c], maps[c][0], maps[c][1], fu[c], dirs[c])
+                same48(b["kp"][:n], b["desc"][:n], rk, rd, f"call {t} camera {c}")
+                rays, valid = oracle_bp(EU[c], rk)
+                assert np.array_equal(b["rays"][:n].view(np.uint64), rays.view(np.uint64)) and np.array_equal(b["valid"][:n], valid)
+                m = pools[c]
+                xy = np.stack([rk["x"], rk["y"]], 1).astype(np.float64)
+                rdist, rlm = oracle.match_map3d(rd, xy, None, m["cand_desc"], m["cand_lm"], b["proj"], m["lm_is3d"], 20.0, 60)
+                assert np.array_equal(b["m1d"][:n], rdist.astype(np.uint32)) and np.array_equal(b["m1l"][:n], rlm), (t, c)
+                totals["m1"] += int((rlm >= 0).sum())
+                ov = [dict(views[c][(vi + t) % NV]) for vi in range(NV)]
+                ref, _ = oracle.match_motion_stereo_sequence(ov, rd, rays, valid, np.stack([rk["x"], rk["y"]], 1), poses[c][0], poses[c][1], 1, intr[c], W, H, 60,
+                                                             (rlm >= 0).astype(np.uint8))
+                for v, (k1, dist, hp, fl) in enumerate(ref):
+                    k0s = np.nonzero(fl & 1)[0]
+                    assert b["m3n"][v] == len(k0s), (t, c, v)
+                    assert np.array_equal(b["k0"][v, :len(k0s)], k0s) and np.array_equal(b["k1"][v, :len(k0s)], k1[k0s])
+                    assert np.array_equal(b["fl"][v, :len(k0s)], fl[k0s]) and np.array_equal(b["hp"][v, :len(k0s)].view(np.uint64), hp[k0s].view(np.uint64))
+                    totals["m3"] += int(((fl & 4) != 0).sum())
+                f = 0.5 * sum(EU[c]["focal_length"])
+                feats.append((rd, valid, world_rays(C0, rays), rk["size"].astype(np.float64) / f))
+            ref = oracle.match_stereo(*feats[0], *feats[1], r0, r1, T_CW(C0, r0), T_CW(C0, r1), 60)
+            n0 = io[0].n
+            assert np.array_equal(sb["k1"][:n0], ref[0]) and np.array_equal(sb["dist"][:n0], ref[1])
+            assert np.array_equal(sb["hp"][:n0].view(np.uint64), ref[2].view(np.uint64)) and np.array_equal(sb["init"][:n0], ref[3])
+            totals["m4"] += int((ref[0] >= 0).sum())
+        g, dcalls = C.c_longlong(), C.c_longlong()
+        _l.check(L_.okb_stream_stats(fe.ctx, C.byref(g), C.byref(dcalls)))
+        assert (g.value, dcalls.value) == ((n_calls - 1, 1) if use_graph else (0, n_calls))
+    finally:
+        fe.close()
+    assert totals["m1"] > 50 and totals["m3"] > 30 and totals["m4"] > 5, totals
