@@ -1009,22 +1009,26 @@ def run_okvis48(args, rank, world, local_rank, steps, with_cpu):
         fe.setCameraModel(c, "radialtangential", (fu, fv), (cu, cv), DIST)
         okl.check(L_.okb_camera_awareness_maps(fe.ctx, c, None, None))
         okl.check(L_.okb_set_extraction_direction(fe.ctx, c, np.ascontiguousarray(T_WC[:3, :3]).ctypes.data))
-    n1 = np.zeros(2, np.int32)
-
-    def live_job(c, i):
-        okl.check(L_.okb_detect_describe(fe.ctx, c, h_img[c][i].data_ptr(), W, h_kp[c].data_ptr(), h_desc[c].data_ptr(), kp_cap, n1[c:].ctypes.data))
-
-    def live_frame(i):
-        t = threading.Thread(target=live_job, args=(1, i)); t.start(); live_job(0, i); t.join()
-    n_live = min(200, ring * B)
-    for i in range(10):
-        live_frame(i)
-    t0 = time.perf_counter()
-    for i in range(n_live):
-        live_frame(i)
-    live_s = time.perf_counter() - t0
-    rec["e2e"]["streaming"] = {"ms_per_stereo_frame": 1e3 * live_s / n_live, "value": n_live / live_s, "unit": "stereo frames/s",
-                               "api": "okb_detect_describe per camera and frame (two host threads), page-locked frames, detect + describe + back-project"}
+    drv = C.CDLL(os.path.join(ROOT, "bench", "libokb_e2e.so"))
+    drv.okb_e2e_multiframe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 13
+    sm3 = StreamM3(n_older, cap0, CAP_M, 0)
+    for c in range(2):
+        sm3.older[c] = C.addressof(views[c]); sm3.T_WC1[c] = Tw1[c].ctypes.data; sm3.T_CW1[c] = Tc1[c].ctypes.data
+    arr_i = lambda v: (C.c_int * 2)(*v)
+    arr_p = lambda v: (C.c_void_p * 2)(*[x.ctypes.data for x in v])
+    keepm = [[np.ascontiguousarray(m[k]) for m in pools] for k in ("cand_desc", "cand_lm", "lm_is3d")]
+    p_proj = [torch.from_numpy(np.ascontiguousarray(m["lm_proj"])).pin_memory() for m in pools]
+    n_live = min(128, ring * B)
+    sec2 = C.c_double(); worst = C.c_double(); h2 = C.c_longlong(); d2 = C.c_longlong(); nk2 = C.c_longlong(); nm2 = C.c_longlong()
+    okl.check(drv.okb_e2e_multiframe(fe.ctx, n_live, 6, W, H, h_img[0].data_ptr(), h_img[1].data_ptr(), kp_cap, arr_i([len(x) for x in keepm[1]]),
+                                     arr_p(keepm[0]), arr_p(keepm[1]), arr_i([len(x) for x in keepm[2]]), arr_p([x.numpy() for x in p_proj]), arr_p(keepm[2]),
+                                     C.byref(sm3), C.byref(sec2), C.byref(worst), C.byref(h2), C.byref(d2), C.byref(nk2), C.byref(nm2)))
+    g_l = C.c_longlong(); d_l = C.c_longlong(); L_.okb_stream_stats(fe.ctx, C.byref(g_l), C.byref(d_l))
+    rec["e2e"]["streaming"] = {"ms_per_stereo_frame": 1e3 * sec2.value / n_live, "value": n_live / sec2.value, "unit": "stereo frames/s",
+                               "ms_worst_frame": worst.value, "frames": n_live, "cuda_graph_launches": int(g_l.value), "direct_submissions": int(d_l.value),
+                               "keypoints_per_frame": nk2.value / n_live / 2, "matches_per_frame": nm2.value / n_live,
+                               "step": "one stereo frame per call (okb_process_multiframe: detect + describe both cameras, M1, M3 sequence, M4, replayed "
+                                       "as a CUDA graph) from page-locked host buffers, D = 48"}
     if with_cpu:
         import oracle
         o = oracle.HarrisBrisk2(cfg["radius"], cfg["abs_threshold"], cfg["max_kp"])

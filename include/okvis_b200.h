@@ -109,8 +109,8 @@ int okb_device_back_projections(okb_context_t* ctx, int cam, const double** d_ra
  * device-resident matcher forms built on the tensor-core Hamming scans (okb_match_stereo_device*, okb_match_motion_stereo_device*) and the
  * feature block below read rows in 64-BYTE SLOTS; a 48-byte row sits in the first 48 bytes of its slot with a zero tail (the Hamming
  * distances are the same). A D = 48 camera keeps that second layout itself, so the forms that take a camera index work on it unchanged;
- * blocks the caller passes by pointer (okb_older_view_t::d_desc, the *_ptr forms) use the slot layout. okb_process_multiframe is built
- * for D = 64 cameras (OKB_ERR_UNSUPPORTED otherwise).
+ * blocks the caller passes by pointer (okb_older_view_t::d_desc, the *_ptr forms) use the slot layout. okb_process_multiframe takes
+ * cameras of either width (pool rows and returned rows in the camera's own width, older views in slots).
  *
  * Fixed-capacity feature block of a batch, the unit the camera-sharded multi-GPU mode all-gathers:
  *   [counts: n_frames x int32, padded to 256 B][keypoints: n_frames x capacity x 28 B][descriptors: n_frames x capacity x 64 B]
