@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
   float* lut = reinterpret_cast<float*>(cell + kUniMaxCells + 1);                // 31 x 31
   PatternPoint* pat0 = reinterpret_cast<PatternPoint*>(lut + kUniLut * kUniLut); // 60
   int* sh = reinterpret_cast<int*>(pat0 + kPoints);                              // 32 scan words + scalars
-  int* s_tail = sh + 32; int* s_acc = sh + 33; int* s_first = sh + 34;
+  int* s_tail = sh + 32; int* s_acc = sh + 33; int* s_first = sh + 34; int* s_total = sh + 35; int* s_ext = sh + 36;   // s_ext: 2 words
   const int frame = blockIdx.x, tid = threadIdx.x;
   const int n = min(cand_count[frame * count_stride], kHarrisCandCap);
   const uint2* cd = cand + (size_t)frame * kHarrisCandCap;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
     const int hx = (int)(xy & 0xffffu) >> 1, hy = (int)(xy >> 16) >> 1;
     entries[atomicAdd(&cell[(hy >> cshift) * cw + (hx >> cshift)], 1)] = ((uint32_t)i << 14) | ((uint32_t)hx << 4) | (uint32_t)(hy & 15);
   }
-  if (tid == 0) { *s_tail = 0; *s_acc = 0; *s_first = n; }
+  if (tid == 0) { *s_tail = 0; *s_acc = 0; *s_first = n; *s_total = 0; s_ext[0] = 0; s_ext[1] = 0; }
   __syncthreads();
   // ---- pending counts: higher-ranked candidates whose stamp reaches this one's cell (a warp per candidate, lanes over the entries)
   const int group = tid / kUniGroup, sub = tid % kUniGroup;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
       const float ratio = uni_ratio(ss[j], max_score);
       const bool accepted = !uni_rejected(ratio, (int)(word[j] & ((1u << kPendShift) - 1u)));
       const float nsc = uni_nsc(ratio);
-      if (sub == 0) state[j] = accepted ? 1 : 2;
+      if (sub == 0) { state[j] = accepted ? 1 : 2; if (accepted && max_kp > 0) atomicAdd(s_total, 1); }
       for_each_neighbour(entries, cell, cw, ch, cshift, hx, hy, sub, [&](int i, int dx, int dy) {
         if (i <= j) return;
         const float l = lut[(-dy + kUniWin) * kUniLut - dx + kUniWin];   // the stamp of j at the cell of i: offset (i - j)
@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
     }
     __syncthreads();
     head = tail; tail = *s_tail;
-    if (max_kp > 0) {   // ranks below the first undecided one are final: stop once they hold max_kp accepted candidates
+    if (max_kp > 0 && *s_total >= max_kp) {   // ranks below the first undecided one are final: stop once they hold max_kp accepted candidates
+      // (looked at only once max_kp candidates have been accepted anywhere)
       int mine = n;
       for (int i = lo + tid; i < n; i += kUniThreads) if (state[i] == 0) { mine = i; break; }
       if (mine < n) atomicMin(s_first, mine);
@@ -377,6 +378,12 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
   for (int i = r0; i < r1; i++) if (state[i] == 1) { if (a < n_keep) kept[a] = (uint16_t)i; a++; }
   const bool aware = ray_map != nullptr;
   const float d[3] = {d0, d1, d2};
+  // the largest |coordinate| and the largest sigma of the pattern: a keypoint further than their warped bound from the border needs no
+  // per-sample test (non-negative floats order like their bits)
+  if (tid < kPoints) {
+    atomicMax(&s_ext[0], __float_as_int(fmaxf(fabsf(pat0[tid].x), fabsf(pat0[tid].y))));
+    atomicMax(&s_ext[1], __float_as_int(pat0[tid].sigma));
+  }
   float2* pos = reinterpret_cast<float2*>(keys);     // the entry / word arrays are dead too
   uint8_t* okf = state;                              // and so are the states once the list is made
   __syncthreads();
@@ -394,7 +401,9 @@ __global__ void __launch_bounds__(kUniThreads) k_uniformity(const int32_t* score
       u = u < 0 ? 0 : (u > W - 1 ? W - 1 : u); v = v < 0 ? 0 : (v > H - 1 ? H - 1 : v);
       float M[4];
       ok = brisk2_warp(ray_map + ((size_t)v * W + u) * 3, jac_map + ((size_t)v * W + u) * 6, d, fu, M);
-      if (ok)
+      const float ext = fmaxf(fabsf(M[0]) + fabsf(M[1]), fabsf(M[2]) + fabsf(M[3])) * __int_as_float(s_ext[0]) + __int_as_float(s_ext[1]) + 0.05f;
+      const bool surely_inside = (fx - ext >= 1.0f) && (fx + ext < (float)(W - 2)) && (fy - ext >= 1.0f) && (fy + ext < (float)(H - 2));
+      if (ok && !surely_inside)
         for (int p = 0; p < kPoints; p++) {
           float xf, yf;
           brisk2_sample_pos(M, fx, fy, pat0[p], xf, yf);
