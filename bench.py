@@ -1440,12 +1440,14 @@ def main():
                 raise
             except Exception as e:   # never lose the headline line to a sub-record
                 configs[sub] = {"error": repr(e)}
-        try:
-            configs["euroc_okvis48"] = run_okvis48(args, rank, world, local_rank, sub_steps, with_cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline))
-        except SystemExit:
-            raise
-        except Exception as e:
-            configs["euroc_okvis48"] = {"error": repr(e)}
+        if rank == 0:   # one GPU's number at any N (the other ranks wait in the next collective)
+            try:
+                configs["euroc_okvis48"] = run_okvis48(args, rank, world, local_rank, sub_steps, with_cpu=(world == 1 and not args.no_cpu_baseline))
+                configs["euroc_okvis48"]["n_gpus"] = 1
+            except SystemExit:
+                raise
+            except Exception as e:
+                configs["euroc_okvis48"] = {"error": repr(e)}
         try:
             configs["hilti_sharded"] = run_sharded(args, "hilti", CONFIGS["hilti"], rank, world, local_rank, max(4, min(args.steps, 8)))
         except Exception as e:

@@ -52,15 +52,16 @@ void integral_run(CamWorkspace& ws, const uint8_t* d_images, int src_pitch, size
 // pixel load and the two stores lives in registers, horizontal neighbours come from warp shuffles, vertical ones from the previous
 // rows' registers. Per row step: pixel row r -> gradient row r-1 -> horizontal sums of the three products -> score row r-2
 // (stored) -> candidate flags of row r-3 (stored as bytes: at or above the threshold and no 8-neighbour strictly greater).
-constexpr int kHsCols = 26, kHsBand = 60, kHsWarps = 4;
+constexpr int kHsCols = 26, kHsWarps = 4;   // rows per band: a launch parameter (60 for batches; 20 for a single frame, whose ~230 warps of
+                                            // 66 dependent row steps would otherwise be one long latency chain)
 __global__ void __launch_bounds__(32 * kHsWarps) k_harris_score(const uint8_t* __restrict__ in0, int pitch, size_t frame_stride, int W, int H,
-                                                                 int threshold, int32_t* __restrict__ score, uint8_t* __restrict__ cond, int cpitch)
+                                                                 int threshold, int32_t* __restrict__ score, uint8_t* __restrict__ cond, int cpitch, int band)
 {
   const int lane = threadIdx.x & 31;
   const int strip = blockIdx.x * kHsWarps + (threadIdx.x >> 5);
   const int x = strip * kHsCols - 3 + lane;
   if (strip * kHsCols >= W) return;
-  const int yb = blockIdx.y * kHsBand, ye = min(yb + kHsBand, H);
+  const int yb = blockIdx.y * band, ye = min(yb + band, H);
   const int frame = blockIdx.z;
   const uint8_t* in = in0 + (size_t)frame * frame_stride;
   int32_t* out = score + (size_t)frame * W * H;
@@ -589,8 +590,9 @@ int harris_run_device(okb_context* ctx, int cam, int n_frames, const uint8_t* d_
   OKB_CUDA(cudaEventRecord(ws.ev_join, ws.stream2));
   {
     const int strips = (W + kHsCols - 1) / kHsCols;
-    k_harris_score<<<dim3((strips + kHsWarps - 1) / kHsWarps, (H + kHsBand - 1) / kHsBand, B), 32 * kHsWarps, 0, st>>>(
-        d_images, src_pitch, in_stride, W, H, c.threshold, hs->d_score, hs->d_cond, hs->cpitch);
+    const int band = B >= 8 ? 60 : (B >= 2 ? 30 : 20);
+    k_harris_score<<<dim3((strips + kHsWarps - 1) / kHsWarps, (H + band - 1) / band, B), 32 * kHsWarps, 0, st>>>(
+        d_images, src_pitch, in_stride, W, H, c.threshold, hs->d_score, hs->d_cond, hs->cpitch, band);
     k_harris_maxima<<<dim3((hs->cpitch / 16 * H + 255) / 256, B), 256, 0, st>>>(hs->d_score, hs->d_cond, hs->cpitch, W, H, hs->d_cand,
                                                                                ws.d_cand_count, kMaxLayers, ws.d_status);
   }

@@ -382,3 +382,51 @@ def test_process_multiframe_in_the_48_byte_mode(use_graph):
     finally:
         fe.close()
     assert totals["m1"] > 50 and totals["m3"] > 30 and totals["m4"] > 5, totals
+
+
+def test_cuda_equals_the_frozen_vectors():
+    """the CUDA path against tests/golden/harris_brisk2_oracle.npz (frozen outputs of this repository's restatement; parity unpinned)"""
+    import os
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "harris_brisk2_oracle.npz"))
+    euroc0 = EUROC[0]
+    for name in sorted(k[:-4] for k in g.files if k.endswith("_cfg")):
+        seed, W, H, radius, thr, max_kp, aware = g[name + "_cfg"]
+        W, H = int(W), int(H)
+        fe = make(W, H, float(radius), int(thr), int(max_kp))
+        T_WC = None
+        if aware:
+            fe.setCameraModel(0, **euroc0)
+            fe.cameraAwarenessMaps(0)
+            # a rotation whose third row is minus the frozen direction: gravity in the camera frame = R_CW (0, 0, -1) = -(row 2 of C_WC)
+            d = g[name + "_dir"].astype(np.float64)
+            a = np.cross(d, [1.0, 0, 0]); a /= np.linalg.norm(a); b = np.cross(d, a)
+            T_WC = np.stack([a, b, -d])
+            if np.linalg.det(T_WC) < 0:
+                T_WC[0] = -T_WC[0]
+        fr = run(fe, synth_frame(int(seed), W, H), 0, T_WC)
+        rk = np.frombuffer(g[name + "_kp"].tobytes(), _l.KP_DTYPE)
+        if aware:
+            assert np.array_equal(fr.extractionDirection, g[name + "_dir"]), "the test's rotation must reproduce the frozen direction bit for bit"
+        same48(fr.keypoints, fr.descriptors, rk, g[name + "_desc"], name)
+        fe.close()
+
+
+def test_candidate_overflow_is_a_loud_error():
+    """more maxima than the uniformity kernel ranks (16384 per frame): OKB_ERR_CAPACITY, never a silently truncated result"""
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (1024, 1024), dtype=np.uint8)
+    fe = make(1024, 1024, 20.0, 1, 500)
+    with pytest.raises(OkbError) as e:
+        run(fe, img)
+    assert e.value.status == _l.OKB_ERR_CAPACITY
+    # the context stays usable: a frame with a handful of corners
+    img2 = np.full((1024, 1024), 20, np.uint8)
+    for i in range(6):
+        for j in range(6):
+            img2[100 + 140 * i:160 + 140 * i, 100 + 140 * j:160 + 140 * j] = 220
+    fr = run(fe, img2)
+    rk, rd = oracle.HarrisBrisk2(20.0, 1, 500).detect_and_compute(img2)
+    assert len(rk) >= 36
+    same48(fr.keypoints, fr.descriptors, rk, rd, "after the overflow")
+    fe.close()

@@ -170,3 +170,26 @@ def test_parallel_formulation_equals_oracle(emul, seed, W, H, radius, thr, max_k
     assert st[0] > 100 and st[1] > 1, "the case must need more than one round"
     assert len(rk) == len(kp) and rk.tobytes() == kp.tobytes()
     assert np.array_equal(rd, d48)
+
+
+def test_oracle_equals_its_frozen_vectors():
+    """tests/golden/harris_brisk2_oracle.npz (made by tests/golden/make_golden_harris_brisk2.py) freezes the definition of DESIGN.md 2b:
+    outputs of this repository's own restatement, NOT of smartroboticslab/brisk (parity unpinned)."""
+    import os
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "harris_brisk2_oracle.npz"))
+    names = sorted(k[:-4] for k in g.files if k.endswith("_cfg"))
+    assert len(names) == 3
+    for name in names:
+        seed, W, H, radius, thr, max_kp, aware = g[name + "_cfg"]
+        img = synth_frame(int(seed), int(W), int(H))
+        o = oracle.HarrisBrisk2(float(radius), int(thr), int(max_kp))
+        args = ()
+        if aware:
+            rays, jac = oracle.camera_awareness_maps(EUROC0["model"], EUROC0["intr"], int(W), int(H))
+            args = (rays, jac, float(np.float32(EUROC0["intr"][0])), g[name + "_dir"])
+        kp, desc = o.detect_and_compute(img, *args)
+        assert kp.view(np.uint8).reshape(len(kp), 28).tobytes() == g[name + "_kp"].tobytes(), name
+        assert np.array_equal(desc, g[name + "_desc"]), name
+        sc = o.scores(img).astype(np.int64)
+        assert [int(sc.sum()), int(np.abs(sc).sum()), len(o.maxima(sc.astype(np.int32)))] == list(g[name + "_score_sum"]), name
