@@ -61,7 +61,7 @@ def config_dict(name, cfg):
     in_mib = (2 * cfg["ring"] * cfg["batch"] * cfg["W"] * cfg["H"]) >> 20
     return {"workload": name, "W": cfg["W"], "H": cfg["H"], "keypoints_per_frame": cfg["kpts"], "detector_max_keypoints": cfg["max_kp"],
             "threshold": cfg["threshold"], "octaves": cfg["octaves"], "n_lm": cfg["n_lm"], "older_keyframes": cfg["n_older"], "older_keypoints_eligible": ELIGIBLE,
-            "step": STEP_TEXT, "parallelism": "replicas (independent sequences per GPU)",
+            "step": STEP_TEXT, "frames": FRAMES_TEXT, "parallelism": "replicas (independent sequences per GPU)",
             "l2_policy": f"GPU arm: inputs larger than L2, a ring of {cfg['ring']} batches = {in_mib} MiB per GPU"}
 
 
@@ -70,8 +70,18 @@ def intrinsics(cfg, c):
     return cfg["f"], cfg["f"] * 0.997, cfg["W"] / 2 - 8.8 + 12 * c, cfg["H"] / 2 + 8.4 + 7 * c
 
 
+COHERENT = bool(os.environ.get("OKB_BENCH_COHERENT"))   # experimental workload, see make_frames_coherent
+FRAMES_TEXT = ("8 rendered stereo scenes + integer-shifted copies (distinct pixels, same statistics); the landmark pool and the older keyframes are "
+               "built from frame 0, so frame 0 is the frame the map fits (workload_stats.frame0 gives its match yields); the other frames load the "
+               "Hamming scans but rarely pass a gate") if not COHERENT else (
+               "EXPERIMENTAL (OKB_BENCH_COHERENT=1): one rendered stereo scene in every frame with photometric jitter (gain within +-3 %, Gaussian "
+               "noise of 1.5 grey levels): ~94 % of the keypoints repeat, the pool and the older keyframes fit every frame")
+
+
 def make_frames(cfg, n, seed0, base=8):
     """n stereo pairs: `base` rendered scenes + integer-shifted variants (distinct pixels, same statistics)."""
+    if COHERENT:
+        return make_frames_coherent(cfg, n, seed0)
     from okvis2_b200.synth import synth_stereo
     W, H = cfg["W"], cfg["H"]
     scenes = [synth_stereo(seed0 + i, W, H) for i in range(min(base, n))]
@@ -80,6 +90,29 @@ def make_frames(cfg, n, seed0, base=8):
         l, r = scenes[i % len(scenes)]
         s = i // len(scenes)
         L[i] = np.roll(l, (3 * s, 5 * s), (0, 1)); R[i] = np.roll(r, (3 * s, 5 * s), (0, 1))
+    return L, R
+
+
+def make_frames_coherent(cfg, n, seed0):
+    """EXPERIMENTAL workload (OKB_BENCH_COHERENT=1): n stereo pairs of ONE scene, frame 0 as rendered, frame i > 0 with its own gain and
+    noise, so that the landmark pool and the older keyframes (built from frame 0) fit EVERY frame and every frame passes through the
+    gate / triangulate / insert stages (EuRoC: 167 M1 matches and 426 M3 insertions per frame instead of ~0 outside frame 0; 23.4 k instead
+    of 25.3 k stereo frames/s). Not the default: at the TUM-VI size (2 000 keypoints, 50 000 landmarks) this workload ended 2 of 12 runs
+    in a device fault and one in a hang that the default workload has never shown and that memcheck / initcheck runs of the same step do
+    not reproduce; not root-caused yet."""
+    from okvis2_b200.synth import synth_stereo
+    W, H = cfg["W"], cfg["H"]
+    l, r = synth_stereo(seed0, W, H)
+    L = np.empty((n, H, W), np.uint8); R = np.empty((n, H, W), np.uint8)
+    lf, rf = l.astype(np.float32), r.astype(np.float32)
+    for i in range(n):
+        if i == 0:
+            L[i], R[i] = l, r
+            continue
+        rng = np.random.default_rng(7000 + 131 * seed0 + i)
+        g = np.float32(1.0 + 0.03 * np.sin(0.7 * i))
+        L[i] = np.clip(np.rint(lf * g + rng.normal(0, 1.5, lf.shape).astype(np.float32)), 0, 255).astype(np.uint8)
+        R[i] = np.clip(np.rint(rf * g + rng.normal(0, 1.5, rf.shape).astype(np.float32)), 0, 255).astype(np.uint8)
     return L, R
 
 
@@ -996,7 +1029,7 @@ def run_okvis48(args, rank, world, local_rank, steps, with_cpu):
            "config": {"workload": "euroc_okvis48", "W": W, "H": H, "keypoints_per_frame": cfg["kpts"], "detector_max_keypoints": cfg["max_kp"],
                       "uniformity_radius": cfg["radius"], "absolute_threshold": cfg["abs_threshold"], "octaves": 0, "descriptor_bytes": 48, "n_lm": cfg["n_lm"],
                       "older_keyframes": n_older, "older_keypoints_eligible": ELIGIBLE,
-                      "camera_aware": True, "step": "per stereo frame: Harris + uniformity detect, camera-aware gravity-aligned BRISK2-48 describe, "
+                      "camera_aware": True, "frames": FRAMES_TEXT, "step": "per stereo frame: Harris + uniformity detect, camera-aware gravity-aligned BRISK2-48 describe, "
                       "back-project, M1 match-to-map per camera, M3 motion stereo per camera against the older keyframes, M4 stereo match "
                       "(the headline step in the D = 48 mode)", "l2_policy": f"ring of {ring} batches"},
            "parity": "bit-exact vs oracle/brisk_oracle.c section 6; PARITY UNPINNED vs smartroboticslab/brisk@1ef8b42a (source absent)"}
@@ -1430,7 +1463,7 @@ def main():
     if not args.no_configs:
         sub_steps = max(4, min(args.steps, 8))
         for sub in ("euroc_octaves0", "tumvi"):
-            if sub == name:
+            if sub == name or (os.environ.get("OKB_BENCH_SUBS") and sub not in os.environ["OKB_BENCH_SUBS"].split(",")):   # development hook
                 continue
             try:
                 r = run_replica(sub, CONFIGS[sub], args, rank, world, local_rank, lanes if sub != "tumvi" else min(lanes, 2), sub_steps, full=False)
