@@ -350,6 +350,9 @@ int okb_fetch_layer(okb_context_t* ctx, int cam, int frame, int layer, uint8_t* 
 {
   int rc = check_cam(ctx, cam, "okb_fetch_layer");
   if (rc) return rc;
+  if (ctx->cams[cam].cfg.descriptor_bytes == 48) {   // the D = 48 mode has no pyramid and no AGAST score maps
+    set_error("okb_fetch_layer: camera %d runs the Harris + BRISK2 mode (no scale-space layers)", cam); return OKB_ERR_UNSUPPORTED;
+  }
   CamWorkspace& ws = ctx->cams[cam];
   if (layer < 0 || layer >= ws.n_layers || frame < 0 || frame >= ws.cfg.max_batch) { set_error("okb_fetch_layer: bad index"); return OKB_ERR_ARGUMENT; }
   OKB_CUDA(cudaSetDevice(ctx->device));
