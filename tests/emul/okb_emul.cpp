@@ -300,7 +300,7 @@ extern "C" long okb_emul_gate_cos_sizes(double f, unsigned first_bits, unsigned 
 
 // ---------------------------------------------------------------------------------------------------------------
 // D = 48 mode (okvis2_b200/csrc/okb_harris.cu): the same per-element functions (okb_harris_core.h) and the same parallel
-// formulation -- run-parity maxima, occupancy as a per-candidate sum over higher-ranked accepted candidates, decided in rounds --
+// formulation -- run-parity maxima, occupancy as a per-candidate sum over higher-ranked accepted candidates, decided in push waves --
 // executed serially. Returns the number of keypoints; stats[0] = maxima, [1] = rounds, [2] = accepted before the border test.
 #include "../../okvis2_b200/csrc/okb_harris_core.h"
 
@@ -347,30 +347,52 @@ extern "C" int okb_emul_harris_brisk2(const uint8_t* img, int W, int H, float ra
   auto hx_of = [&](int i) { return (int)((uint32_t)cs[i].key & 0xffffu) >> 1; };
   auto hy_of = [&](int i) { return (int)((uint32_t)cs[i].key >> 16) >> 1; };
   for (int i = 0; i < n; i++) cs[i].nsc = uni_nsc(uni_ratio(sc_of(i), max_score));
-  int lo = 0, acc = 0;
-  while (lo < n && !(max_kp > 0 && acc >= max_kp)) {
-    stats[1]++;
-    std::vector<int> next(n);
-    for (int i = 0; i < n; i++) next[i] = cs[i].state;
-    int first = n;
-    for (int i = lo; i < n; i++) {   // a round: every decision is taken from the states at the START of the round
-      if (cs[i].state) continue;
-      int sum = 0; bool blocked = false;
-      for (int j = 0; j < i && !blocked; j++) {
-        const int dx = hx_of(i) - hx_of(j), dy = hy_of(i) - hy_of(j);
-        if (dx < -kUniWin || dx > kUniWin || dy < -kUniWin || dy > kUniWin) continue;
-        const float l = lut[(dy + kUniWin) * kUniLut + dx + kUniWin];
-        if (l == 0.0f) continue;
-        if (cs[j].state == 0) blocked = true;
-        else if (cs[j].state == 1) sum += uni_stamp(cs[j].nsc, l);
-      }
-      if (blocked) { first = std::min(first, i); continue; }
-      next[i] = uni_rejected(uni_ratio(sc_of(i), max_score), sum) ? 2 : 1;
-    }
-    for (int i = 0; i < n; i++) cs[i].state = next[i];
-    for (int i = lo; i < first; i++) acc += cs[i].state == 1;
-    lo = first;
+  // the kernel's formulation (k_uniformity): every candidate counts the higher-ranked candidates whose stamp reaches its cell
+  // (word = pending << 20 | stamp sum); the candidates without pending neighbours form the first wave; a wave decides its candidates
+  // from their (complete) stamp sums and pushes the decisions -- one add per lower-ranked candidate in reach: the stamp, and one
+  // off the pending count -- and whoever drops to zero joins the next wave. After every wave: ranks below the first undecided one
+  // are final; stop once they hold max_kp accepted candidates.
+  auto reaches = [&](int i, int j, float& l) {   // offset of i seen from j
+    const int dx = hx_of(i) - hx_of(j), dy = hy_of(i) - hy_of(j);
+    if (dx < -kUniWin || dx > kUniWin || dy < -kUniWin || dy > kUniWin) return false;
+    l = lut[(dy + kUniWin) * kUniLut + dx + kUniWin];
+    return l != 0.0f;
+  };
+  std::vector<uint32_t> word(n, 0);
+  std::vector<int> queue; queue.reserve(n);
+  for (int i = 0; i < n; i++) {
+    uint32_t pend = 0; float l;
+    for (int j = 0; j < i; j++) if (reaches(i, j, l)) pend++;
+    word[i] = pend << 20;
+    if (pend == 0) queue.push_back(i);
   }
+  int lo = 0, acc = 0;
+  size_t head = 0;
+  while (head < queue.size()) {
+    stats[1]++;
+    const size_t tail = queue.size();
+    for (size_t q = head; q < tail; q++) {
+      const int j = queue[q];
+      const bool accepted = !uni_rejected(uni_ratio(sc_of(j), max_score), (int)(word[j] & 0xfffffu));
+      cs[j].state = accepted ? 1 : 2;
+      for (int i = j + 1; i < n; i++) {
+        float l;
+        if (!reaches(i, j, l)) continue;
+        const uint32_t old = word[i];
+        word[i] = old + (accepted ? (uint32_t)uni_stamp(cs[j].nsc, l) : 0u) - (1u << 20);
+        if ((old >> 20) == 1u) queue.push_back(i);
+      }
+    }
+    head = tail;
+    if (max_kp > 0) {
+      int first = lo;
+      while (first < n && cs[first].state != 0) first++;
+      for (int i = lo; i < first; i++) acc += cs[i].state == 1;
+      lo = first;
+      if (acc >= max_kp) break;
+    }
+  }
+  if (max_kp <= 0 || acc < max_kp) lo = n;
   const int basic = brisk2_basic_scale_host();
   const PatternPoint* pat0 = &T.pattern[(size_t)basic * kRot * kPoints];
   const int border = (int)T.size_list[basic];
