@@ -25,7 +25,7 @@ typedef enum {
   OKB_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed */
   OKB_ERR_ARGUMENT = -3,    /* bad argument (null pointer, size out of range, unsupported D) */
   OKB_ERR_CAPACITY = -4,    /* a fixed-capacity device buffer overflowed (raise the config capacity) */
-  OKB_ERR_UNSUPPORTED = -5, /* feature not built (e.g. a device-resident matcher form on a D = 48 context, octaves > 0 with D = 48) */
+  OKB_ERR_UNSUPPORTED = -5, /* feature not built (octaves > 0 with descriptor_bytes = 48, okb_fetch_layer on such a camera) */
   OKB_ERR_NCCL = -6
 } okb_status;
 
